@@ -1,0 +1,148 @@
+/* cledb_b200.h - C ABI of the B200-native CLEDB 2-line database search.
+ *
+ * The reference (arparaschiv/solar-coronal-inversion, CLEDB 0.7.0-beta) is pure Python and has no FFI layer;
+ * its boundary for this path is the Python function surface of CLEDB_PROC / CLEDB_PREPINV.  This header is
+ * the C-ABI a binding for that surface loads (ctypes.CDLL in solar-coronal-inversion_b200/cledb_b200/native.py;
+ * INTEGRATION.md shows the stub a reference maintainer would add).  Each entry point names the reference
+ * code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints.  No C++ or torch types cross the boundary, no exceptions.
+ *   - return 0 on success, a negative CLEDB_ERR_* otherwise; cledb_last_error() gives the text.
+ *   - one context per CUDA device and per thread of control; calls on one context are serialised by the
+ *     caller; different contexts are independent.
+ *   - "host" entry points take C-contiguous host buffers (pageable or pinned), copy in, run, copy out and
+ *     return when the results are in the output buffers.  "_dev" entry points take device pointers that are
+ *     valid on the context's device and enqueue on the given cudaStream_t (passed as void*; NULL = the
+ *     context's own stream) without synchronising.
+ *   - all arrays are row-major; float = IEEE binary32.
+ */
+#ifndef CLEDB_B200_H
+#define CLEDB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cledb_ctx cledb_ctx;
+
+#define CLEDB_OK            0
+#define CLEDB_ERR_ARG      -1   /* bad argument (null pointer, size, unknown id, nsearch out of range)   */
+#define CLEDB_ERR_CUDA     -2   /* a CUDA runtime call failed                                             */
+#define CLEDB_ERR_NODB     -3   /* a pixel refers to a database id that was never put                     */
+#define CLEDB_ERR_DBFORMAT -4   /* database violates the layout contract (component 0 != 1, non-finite)   */
+#define CLEDB_ERR_NOMEM    -5   /* device or host allocation failed                                       */
+
+#define CLEDB_MODE_IQUV 0       /* cledb_matchiquv, CLEDB_PROC.py:921  */
+#define CLEDB_MODE_IQUD 1       /* cledb_matchiqud, CLEDB_PROC.py:1094 */
+
+#define CLEDB_ENC_F32 0         /* database kept as float32 in HBM (lossless)                             */
+#define CLEDB_ENC_I16 1         /* database kept as int16 codes in HBM (see cledb_codec_*)                */
+
+#define CLEDB_PREC_FP32 0       /* production kernel: fp32 FMA residuals                                  */
+#define CLEDB_PREC_FP64 1       /* validation kernel: the reference's operation order in f32/f64          */
+
+#define CLEDB_MAX_NSEARCH 32
+
+/* per-pixel status written by cledb_match (why a pixel was or was not searched) */
+#define CLEDB_PIX_SEARCHED   0
+#define CLEDB_PIX_NULL       1  /* NaN / all-zero observation: CLEDB_PROC.py:944-948, 1118-1122          */
+#define CLEDB_PIX_ALLNAN     2  /* every chi^2 is NaN in the reference (0/0, x/0 with weight 0, nf == 0)  */
+#define CLEDB_PIX_REFRAISES  3  /* the reference raises for this pixel (empty candidate set / NaN max)   */
+#define CLEDB_PIX_ALLINF     4  /* every chi^2 is +inf in the reference (zero sigma on a fitted component) */
+
+/* ---- library / context ----------------------------------------------------------------------------- */
+const char* cledb_version(void);
+int         cledb_create(int device, cledb_ctx** ctx);
+int         cledb_destroy(cledb_ctx* ctx);
+const char* cledb_last_error(cledb_ctx* ctx);                 /* ctx may be NULL: last error of cledb_create */
+/* props[0]=SM count, [1]=SM clock kHz, [2]=total HBM bytes, [3]=L2 bytes, [4]=cc major*10+minor,
+ * [5]=resident search CTAs per SM, [6]=search kernel registers/thread, [7]=search kernel smem bytes/CTA */
+int         cledb_device_props(cledb_ctx* ctx, int64_t props[8]);
+int         cledb_synchronize(cledb_ctx* ctx);
+/* number of kernels this library has launched on the context since creation (bench.py "gpu_launches") */
+int64_t     cledb_launch_count(cledb_ctx* ctx);
+/* CUDA-event timing of the search kernel alone: begin resets, every cledb_match[_dev] call records one
+ * sample, collect synchronises and returns up to cap durations in ms (returns the number written). */
+int         cledb_profile_begin(cledb_ctx* ctx);
+int         cledb_profile_collect(cledb_ctx* ctx, float* ms, int cap);
+
+/* FFMA-only microkernel: measured FP32 CUDA-core peak of this device in TFLOP/s (best of 5 after warm-up).
+ * It is the roofline denominator of the search kernel, which is bound by the FP32 pipe, not by HBM. */
+int         cledb_measure_fp32_peak(cledb_ctx* ctx, double* tflops);
+
+/* ---- database residency ---------------------------------------------------------------------------- *
+ * Replaces the per-pixel pickling of database[db_enc[xx,yy]] into every pool task (CLEDB_PROC.py:304-307):
+ * a database is uploaded once, partitioned by sign(V1) (the prefilter of CLEDB_PROC.py:974), optionally
+ * int16-encoded, and stays in HBM until dropped.  db is the [n,8] float32 array that sdb_preprocess produces
+ * (CLEDB_PREPINV.py:306-317): component 0 must be exactly 1. */
+int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t n, int encoding);
+int cledb_db_drop(cledb_ctx* ctx, int db_id);
+/* info[0]=n, [1]=rows with V1>0, [2]=V1<0, [3]=V1==0, [4]=V1 NaN (never candidates), [5]=encoding,
+ * [6]=HBM bytes, [7]=entries per tile, [8..15]=power-of-two shift of components 0..7 (int16 encoding) */
+int cledb_db_info(cledb_ctx* ctx, int db_id, int64_t info[16]);
+/* the database exactly as the kernels see it after decoding, [n,8] float32 (rows with NaN V1 come back as
+ * [1,0,0,NaN,0,0,0,0]); this is the array the oracle is given in parity tests */
+int cledb_db_decoded(cledb_ctx* ctx, int db_id, float* out);
+/* decoded rows by original index, rows_out[n,8]; idx < 0 gives zeros (database_sel[ixr,:], CLEDB_PROC.py:1064) */
+int cledb_gather_rows(cledb_ctx* ctx, int db_id, const int32_t* idx, int64_t n, float* rows_out);
+
+/* ---- the search ------------------------------------------------------------------------------------ *
+ * Replaces, for every pixel at once, the candidate selection, chi^2 evaluation and partial sort of
+ * cledb_matchiquv / cledb_matchiqud (CLEDB_PROC.py:944-1013 / 1118-1188): for pixel p the nsearch smallest
+ * reduced chi^2 over the candidate rows of database db_id[p] (IQUV: rows whose sign(V1) equals sign(sobs[p,3]);
+ * IQUD: all rows with non-NaN V1), ties to the lowest original row index.
+ *   sobs[npix,8], snr[npix,8] float32, db_id[npix] int32
+ *   idx_out [npix,nsearch]  original row index, -1 = empty slot
+ *   chi_out [npix,nsearch]  reduced chi^2 (float32)             chi64_out: same in float64 (may be NULL)
+ *   kpos_out[npix,nsearch]  position of the row inside the pixel's candidate list (needed to replay the
+ *                           reference's cledb_partsort index quirk, CLEDB_PROC.py:1620-1625); may be NULL
+ *   rows_out[npix,nsearch,8] decoded database rows of the winners (may be NULL)
+ *   status_out[npix] uint8  CLEDB_PIX_*                         ncand_out[npix] int64 candidates evaluated (may be NULL)
+ * Thresholds (maxchisq), field strength, geometry and issue flags are O(nsearch) work on these outputs and
+ * stay in the host binding (CLEDB_PROC.py:1027-1082). */
+int cledb_match(cledb_ctx* ctx, int mode, int precision, int64_t npix,
+                const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
+                int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out,
+                float* rows_out, uint8_t* status_out, int64_t* ncand_out);
+int cledb_match_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
+                    const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
+                    int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out,
+                    float* rows_out, uint8_t* status_out, int64_t* ncand_out, void* stream);
+/* tuning knobs: pixels per work item (<=32) and how many chunks each candidate list is cut into (>=1;
+ * 0 = choose from the pixel count).  Results do not depend on them. */
+int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split);
+
+/* ---- elementwise neighbours ------------------------------------------------------------------------ *
+ * cledb_blos: blos_proc_1pix (CLEDB_PROC.py:874-914) for npix pixels of one line.
+ *   iquv[npix,4]; kfac = 1e9*h*c/mu_B/lambda_ref^2, g_eff, ffac = F_factor as Python floats (they are
+ *   rounded to float32 exactly where NumPy's weak-scalar promotion rounds them)
+ *   out[npix,4] = [B_deg+, B_deg-, B_classic, azimuth]; flags[npix,2] = issue codes 32 / 64 raised */
+int cledb_blos(cledb_ctx* ctx, int64_t npix, const float* iquv, double kfac, double g_eff, double ffac,
+               float* out, uint8_t* flags);
+int cledb_blos_dev(cledb_ctx* ctx, int64_t npix, const float* iquv, double kfac, double g_eff, double ffac,
+                   float* out, uint8_t* flags, void* stream);
+/* cledb_qurotate: obs_qurotate + obs_calcheight (CLEDB_PREPINV.py:1277-1350, 897-926).
+ *   xs[nx], ys[ny]: the per-row / per-column coordinates crval'+i*cdelt evaluated by the caller in the
+ *   scalar types the header carries (float64), or hpxy[2,nx,ny] float32 (Cryo-NIRSP grid) when non-NULL;
+ *   in[nx,ny,8] -> out[nx,ny,8] (Q,U of both lines rotated by 2*aobs), aobs[nx,ny], yobs[nx,ny] */
+int cledb_qurotate(cledb_ctx* ctx, int nx, int ny, const double* xs, const double* ys, double linpolref,
+                   const float* hpxy, const float* in, float* out, float* aobs, float* yobs);
+int cledb_qurotate_dev(cledb_ctx* ctx, int nx, int ny, const double* xs, const double* ys, double linpolref,
+                       const float* hpxy, const float* in, float* out, float* aobs, float* yobs, void* stream);
+
+/* ---- int16 database codec (pure host code, usable without a GPU) ------------------------------------ *
+ * code = IEEE binary16 bit pattern of x * 2^shift (round to nearest even), stored as int16;
+ * decode = float(binary16) * 2^-shift, exact in float32.  cledb_codec_shift picks the shift that puts the
+ * largest finite |x[i*stride]| just below 2^15.  The legacy log-scale int16 scheme of the reference
+ * (sdb_dcompress, CLEDB_PREPINV.py:1618-1644) is disabled upstream; this codec is defined by this library. */
+int  cledb_codec_shift(const float* x, int64_t n, int64_t stride);
+void cledb_codec_encode(const float* x, int64_t n, int shift, int16_t* codes);
+void cledb_codec_decode(const int16_t* codes, int64_t n, int shift, float* x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLEDB_B200_H */

@@ -278,7 +278,7 @@ def invert_map(sobs_totrot, sobs_dopp, database, db_enc, yobs, aobs, dobs, snr, 
 # --------------------------------------------------------------------------------------------------
 # raw search (what the CUDA kernel returns before solution building) for big parity cases
 # --------------------------------------------------------------------------------------------------
-def raw_topk(mode, sobs, snr, database, nsearch):
+def raw_topk(mode, sobs, snr, database, nsearch, return_all=False):
     """(orig_index[k], chi[k] float64, kept_position[k], ncand) of the stable top-k of one pixel, or None for
     a null pixel.  Same arithmetic as ``match_pixel``; this is the quantity ``cledb_match`` (C-ABI) returns."""
     sobs = np.asarray(sobs)
@@ -294,6 +294,8 @@ def raw_topk(mode, sobs, snr, database, nsearch):
             nf = sobs[np.argwhere(sobs == np.max(sobs))[0, 0]]
     chi = chi2_of_rows(flat[keep], sobs, snr, nf)
     pos = stable_topk(chi, nsearch)
+    if return_all:
+        return keep[pos], chi[pos], pos, keep.size, chi
     return keep[pos], chi[pos], pos, keep.size
 
 

@@ -1,0 +1,208 @@
+"""B200-native drop-in for the hot path of the reference's ``CLEDB_PROC/CLEDB_PROC.py``.
+
+Same function names, positional arguments, return arity and error conventions as the reference
+(arparaschiv/solar-coronal-inversion, CLEDB 0.7.0-beta):
+
+    cledb_invproc(...)      CLEDB_PROC.py:93-363    2-line inversion of a map
+    cledb_matchiquv(...)    CLEDB_PROC.py:921-1087  one pixel, full Stokes
+    cledb_matchiqud(...)    CLEDB_PROC.py:1094-1252 one pixel, IQU + Doppler
+    blos_proc(...)          CLEDB_PROC.py:388-486   1-line analytic B_LOS
+
+The chi^2 search over the database runs in hand-written sm_100a kernels through the C-ABI of
+``libcledb_b200.so``; there is no CPU fallback (a missing library or GPU raises).  ``ncpu`` and the Numba flags
+are accepted and ignored.  Everything after the search (thresholds, field strength, geometry, issue codes) is
+NumPy on ``[npix, nsearch]`` arrays in ``cledb_b200.solution``.
+
+Module-level options (not part of the reference surface; the defaults reproduce the reference):
+    OPTIONS['dbencoding']  0 = database kept as float32 in HBM (lossless, default here), 1 = int16 codes
+    OPTIONS['precision']   0 = fp32 kernel, 1 = fp64 validation kernel (reference operation order)
+    OPTIONS['strict_topk'] False = reproduce the cledb_partsort index quirk, True = true top-nsearch
+    OPTIONS['device']      CUDA ordinal (default: $CLEDB_B200_DEVICE, else $LOCAL_RANK, else 0)
+"""
+import os
+
+import numpy as np
+
+from cledb_b200 import native, solution
+
+OPTIONS = dict(dbencoding=int(os.environ.get('CLEDB_B200_DBENCODING', '0')),
+               precision=int(os.environ.get('CLEDB_B200_PRECISION', '0')),
+               strict_topk=False,
+               device=int(os.environ.get('CLEDB_B200_DEVICE', os.environ.get('LOCAL_RANK', '0'))))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# database residency: upload each distinct database array once and keep it in HBM across calls
+# ---------------------------------------------------------------------------------------------------------
+class _Resident:
+    def __init__(self):
+        self.ids = {}          # fingerprint -> db_id
+        self.next_id = 0
+
+    @staticmethod
+    def fingerprint(arr, encoding):
+        flat = arr.reshape(-1)
+        step = max(1, flat.size // 4096)
+        return (arr.__array_interface__['data'][0], arr.shape, int(encoding), hash(flat[::step].tobytes()))
+
+    def ensure(self, ctx, arr, encoding):
+        arr = np.ascontiguousarray(arr, dtype=np.float32)
+        key = self.fingerprint(arr, encoding)
+        db_id = self.ids.get(key)
+        if db_id is None:
+            db_id = self.next_id
+            self.next_id += 1
+            ctx.db_put(db_id, arr, encoding)
+            self.ids[key] = db_id
+        return db_id
+
+    def clear(self, ctx):
+        for db_id in self.ids.values():
+            ctx.db_drop(db_id)
+        self.ids.clear()
+
+
+_resident = {}
+
+
+def _context():
+    return native.get_context(OPTIONS['device'])
+
+
+def release_databases():
+    """Drop every database this module has made resident (frees HBM)."""
+    dev = OPTIONS['device']
+    if dev in _resident:
+        _resident[dev].clear(_context())
+
+
+def _upload(database, used):
+    ctx = _context()
+    res = _resident.setdefault(OPTIONS['device'], _Resident())
+    encs = {k[2] for k in res.ids}
+    if encs and encs != {OPTIONS['dbencoding']}:
+        res.clear(ctx)                      # one encoding at a time lives on the device
+    return ctx, {int(k): res.ensure(ctx, database[int(k)], OPTIONS['dbencoding']) for k in used}
+
+
+def _search_and_build(mode, sobs, sobs_dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc):
+    """Flattened pixels in, (invout[npix,k,11], sfound[npix,k,8]) out."""
+    sobs = np.ascontiguousarray(sobs, dtype=np.float32).reshape(-1, 8)
+    snr = np.ascontiguousarray(snr, dtype=np.float32).reshape(-1, 8)
+    enc = np.asarray(db_enc).reshape(-1)
+    ctx, ids = _upload(database, np.unique(enc))
+    lut = np.zeros(int(enc.max()) + 1, dtype=np.int32)
+    for k, v in ids.items():
+        lut[k] = v
+    raw = ctx.match(mode, sobs, snr, lut[enc], nsearch, precision=OPTIONS['precision'], want_rows=True,
+                    want_chi64=OPTIONS['precision'] == native.PREC_FP64)
+    return solution.build_solutions(raw, mode, sobs, sobs_dopp, np.asarray(yobs).reshape(-1), np.asarray(aobs).reshape(-1),
+                                    np.asarray(dobs).reshape(-1), dbhdr, nsearch, maxchisq, bcalc,
+                                    strict_topk=OPTIONS['strict_topk'])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference's call surface
+# ---------------------------------------------------------------------------------------------------------
+def cledb_invproc(sobs_totrot, sobs_dopp, database, db_enc, yobs, aobs, dobs, snr, issuemask, dbhdr, keyvals,
+                  nsearch, maxchisq, bcalc, iqud, ncpu, reduced, verbose):
+    """2-line inversion of a preprocessed map; reference CLEDB_PROC.py:93-363.
+
+    Returns ``(invout[nx,ny,nsearch,11], sfound[nx,ny,nsearch,8])`` float32 and updates ``issuemask`` in place
+    with codes 512 / 1024 / 2048.  Fatal input problems do not raise: they return ``invout[...,0] == -1``.
+    """
+    if verbose >= 1:
+        print('--------------------------------------\n----CLEDB_INVPROC - INVERSION START---\n--------------------------------------')
+    nx, ny = keyvals[0:2]
+    invout = np.zeros((nx, ny, nsearch, 11), dtype=np.float32)
+    sfound = np.zeros((nx, ny, nsearch, 8), dtype=np.float32)
+
+    if np.shape(sobs_totrot)[-1] != 8 or database[0].shape[-1] != 8:                      # CLEDB_PROC.py:166-171
+        if verbose >= 1:
+            print('CLEDB_INVPROC: FATAL! Must have a two-line observation and a corresponding two-line database; Aborting!')
+            print("Shapes are: ", np.shape(sobs_totrot), " and ", database[0].shape)
+        invout[:, :, :, 0] = -1
+        return invout, sfound
+    if (iqud == True and bcalc != 3) or (iqud != True and bcalc == 3):                    # CLEDB_PROC.py:174-178
+        invout[:, :, :, 0] = -1
+        if verbose >= 1:
+            print("CLEDB_INVPROC: FATAL! Field strength calculation incompatible with requested input data! Check bcalc and iqud keywords; Aborting!")
+        return invout, sfound
+    if reduced == True:
+        raise NotImplementedError("cledb_b200: the reduced-database presort (cledb_getsubsetiquv/iqud) is not built yet; "
+                                  "run with reduced=False (full search is the default of the reference)")
+    if verbose >= 2:
+        print("CLEDB_INVPROC: Using a full database search of size:", dbhdr[1] * dbhdr[2] * dbhdr[3] * dbhdr[4])
+
+    mode = native.MODE_IQUD if iqud == True else native.MODE_IQUV
+    dopp = None
+    if mode == native.MODE_IQUD:
+        dopp = np.asarray(sobs_dopp)
+        dopp = dopp.reshape(nx * ny, -1)
+    inv, sf = _search_and_build(mode, sobs_totrot, dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc)
+    invout[...] = inv.reshape(nx, ny, nsearch, 11)
+    sfound[...] = sf.reshape(nx, ny, nsearch, 8)
+    solution.update_issuemask(issuemask, invout, np.asarray(snr), nx, ny)
+    if verbose >= 1:
+        print('--------------------------------------\n--CLEDB_INVPROC - INVERSION FINALIZED-\n--------------------------------------')
+    return invout, sfound
+
+
+def cledb_matchiquv(xx, yy, sobs_1pix, yobs_1pix, aobs_1pix, dobs_1pix, database_in, dbhdr, snr, nsearch, maxchisq,
+                    bcalc, reduced, verbose):
+    """One pixel, full Stokes IQUV; reference CLEDB_PROC.py:921-1087.  Returns ``(xx, yy, out, smatch)``."""
+    if reduced == True:
+        raise NotImplementedError("cledb_b200: reduced database search is not built yet")
+    inv, sf = _search_and_build(native.MODE_IQUV, np.asarray(sobs_1pix).reshape(1, 8), None, [database_in], np.zeros(1, np.int32),
+                                np.array([yobs_1pix]), np.array([aobs_1pix]), np.array([dobs_1pix]), np.asarray(snr).reshape(1, 8),
+                                dbhdr, nsearch, maxchisq, bcalc)
+    return xx, yy, inv[0], sf[0]
+
+
+def cledb_matchiqud(xx, yy, sobs_1pix, sobsd_1pix, yobs_1pix, aobs_1pix, dobs_1pix, database_in, dbhdr, snr, nsearch,
+                    maxchisq, bcalc, reduced, verbose):
+    """One pixel, IQU + Doppler; reference CLEDB_PROC.py:1094-1252.  Returns ``(xx, yy, out, smatch)``."""
+    if reduced == True:
+        raise NotImplementedError("cledb_b200: reduced database search is not built yet")
+    inv, sf = _search_and_build(native.MODE_IQUD, np.asarray(sobs_1pix).reshape(1, 8), np.asarray(sobsd_1pix).reshape(1, -1),
+                                [database_in], np.zeros(1, np.int32), np.array([yobs_1pix]), np.array([aobs_1pix]),
+                                np.array([dobs_1pix]), np.asarray(snr).reshape(1, 8), dbhdr, nsearch, maxchisq, bcalc)
+    return xx, yy, inv[0], sf[0]
+
+
+def blos_proc(sobs_tot, snr, issuemask, keyvals, consts, params):
+    """1-line analytic B_LOS for every line of the observation; reference CLEDB_PROC.py:388-486.
+
+    Returns ``blosout[nx,ny,nline,4]`` float32 and adds issue codes 32 / 64 to ``issuemask``.  ``consts`` is the
+    constants *module* (``consts.Constants(line)`` is instantiated per line).  Returns 0 for ``params.iqud``.
+    """
+    if params.iqud == True:
+        print("BLOS_PROC: FATAL! No Stokes V data available to compute analytical line-of-sight projected magnetic fields.")
+        return 0
+    if params.verbose >= 1:
+        print('--------------------------------------\n---BLOS_PROC: B LOS ESTIMATION START--\n--------------------------------------')
+    nx, ny = keyvals[0:2]
+    nline, tline = keyvals[3], keyvals[4]
+    blosout = np.zeros((nx, ny, nline, 4), dtype=np.float32)
+    ctx = _context()
+    sobs_tot = np.asarray(sobs_tot)
+    for zz in range(nline):
+        const = consts.Constants(tline[zz])
+        kfac = 1.e9 * (const.planckconst * const.l_speed / const.bohrmagneton / (const.line_ref ** 2))
+        iquv = np.ascontiguousarray(sobs_tot[:, :, 4 * zz:4 * (zz + 1)], dtype=np.float32).reshape(-1, 4)
+        out, flags = ctx.blos(iquv, kfac, const.g_eff, const.F_factor)
+        blosout[:, :, zz, :] = out.reshape(nx, ny, 4)
+        flags = flags.reshape(nx, ny, 2)
+        m = issuemask[:, :, zz]
+        for col, code in ((0, 32), (1, 64)):                                               # CLEDB_PROC.py:478-479
+            add = (flags[:, :, col] != 0) & ((m.astype(np.int64) & code) == 0)
+            m[add] += code
+    if params.verbose >= 1:
+        print('--------------------------------------\n-BLOS_PROC: BLOS ESTIMATION FINALIZED-\n--------------------------------------')
+    return blosout
+
+
+def iss_block(x):
+    """Issue codes set in one issuemask value (list of powers of two, zeros for clear bits); CLEDB_PREPINV.py:1563-1576."""
+    x = int(x)
+    return [(1 << b) if (x >> b) & 1 else 0 for b in range(x.bit_length())] if x > 0 else []

@@ -1,0 +1,253 @@
+"""ctypes binding of libcledb_b200.so (include/cledb_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no sm_100 device is present, creating a
+:class:`Context` raises.  NumPy arrays are passed as C-contiguous host buffers; the ``*_dev`` methods take raw
+device addresses (e.g. ``torch.Tensor.data_ptr()``) and a CUDA stream handle.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcledb_b200.so')
+
+MODE_IQUV, MODE_IQUD = 0, 1
+ENC_F32, ENC_I16 = 0, 1
+PREC_FP32, PREC_FP64 = 0, 1
+MAX_NSEARCH = 32
+PIX_SEARCHED, PIX_NULL, PIX_ALLNAN, PIX_REFRAISES, PIX_ALLINF = 0, 1, 2, 3, 4
+
+# every symbol include/cledb_b200.h declares, with (restype, argtypes)
+_c = ctypes
+_P = ctypes.c_void_p
+SIGNATURES = {
+    'cledb_version': (_c.c_char_p, []),
+    'cledb_create': (_c.c_int, [_c.c_int, _c.POINTER(_P)]),
+    'cledb_destroy': (_c.c_int, [_P]),
+    'cledb_last_error': (_c.c_char_p, [_P]),
+    'cledb_device_props': (_c.c_int, [_P, _P]),
+    'cledb_synchronize': (_c.c_int, [_P]),
+    'cledb_launch_count': (_c.c_int64, [_P]),
+    'cledb_profile_begin': (_c.c_int, [_P]),
+    'cledb_profile_collect': (_c.c_int, [_P, _P, _c.c_int]),
+    'cledb_measure_fp32_peak': (_c.c_int, [_P, _P]),
+    'cledb_db_put': (_c.c_int, [_P, _c.c_int, _P, _c.c_int64, _c.c_int]),
+    'cledb_db_drop': (_c.c_int, [_P, _c.c_int]),
+    'cledb_db_info': (_c.c_int, [_P, _c.c_int, _P]),
+    'cledb_db_decoded': (_c.c_int, [_P, _c.c_int, _P]),
+    'cledb_gather_rows': (_c.c_int, [_P, _c.c_int, _P, _c.c_int64, _P]),
+    'cledb_match': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    'cledb_match_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'cledb_set_tuning': (_c.c_int, [_P, _c.c_int, _c.c_int]),
+    'cledb_blos': (_c.c_int, [_P, _c.c_int64, _P, _c.c_double, _c.c_double, _c.c_double, _P, _P]),
+    'cledb_blos_dev': (_c.c_int, [_P, _c.c_int64, _P, _c.c_double, _c.c_double, _c.c_double, _P, _P, _P]),
+    'cledb_qurotate': (_c.c_int, [_P, _c.c_int, _c.c_int, _P, _P, _c.c_double, _P, _P, _P, _P, _P]),
+    'cledb_qurotate_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _P, _P, _c.c_double, _P, _P, _P, _P, _P, _P]),
+    'cledb_codec_shift': (_c.c_int, [_P, _c.c_int64, _c.c_int64]),
+    'cledb_codec_encode': (None, [_P, _c.c_int64, _c.c_int, _P]),
+    'cledb_codec_decode': (None, [_P, _c.c_int64, _c.c_int, _P]),
+}
+
+_lib = None
+
+
+class CledbError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """Load the shared library (once) and declare the prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise CledbError('%s is missing: build it with `python __graft_entry__.py` (or make -C '
+                         'solar-coronal-inversion_b200/csrc); there is no CPU fallback' % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _as(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+# ---- int16 codec (host only) ---------------------------------------------------------------------------------
+def codec_shift(x):
+    x = _as(x, np.float32).reshape(-1)
+    return int(load_library().cledb_codec_shift(_ptr(x), x.size, 1))
+
+
+def codec_encode(x, shift):
+    x = _as(x, np.float32)
+    out = np.empty(x.shape, dtype=np.int16)
+    load_library().cledb_codec_encode(_ptr(x), x.size, int(shift), _ptr(out))
+    return out
+
+
+def codec_decode(codes, shift):
+    codes = _as(codes, np.int16)
+    out = np.empty(codes.shape, dtype=np.float32)
+    load_library().cledb_codec_decode(_ptr(codes), codes.size, int(shift), _ptr(out))
+    return out
+
+
+class Context:
+    """One CUDA device.  Owns the resident databases and the search workspace."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.cledb_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise CledbError(self.lib.cledb_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.cledb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise CledbError('cledb error %d: %s' % (rc, self.lib.cledb_last_error(self.h).decode()))
+        return rc
+
+    # ---- introspection
+    def device_props(self):
+        p = np.zeros(8, dtype=np.int64)
+        self._check(self.lib.cledb_device_props(self.h, _ptr(p)))
+        keys = ('sm_count', 'sm_clock_khz', 'hbm_bytes', 'l2_bytes', 'cc', 'match_ctas_per_sm', 'match_regs', 'match_smem')
+        return dict(zip(keys, (int(v) for v in p)))
+
+    def synchronize(self):
+        self._check(self.lib.cledb_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.cledb_launch_count(self.h))
+
+    def profile_begin(self):
+        self._check(self.lib.cledb_profile_begin(self.h))
+
+    def profile_collect(self, cap=256):
+        ms = np.zeros(cap, dtype=np.float32)
+        n = self._check(self.lib.cledb_profile_collect(self.h, _ptr(ms), cap))
+        return ms[:n].copy()
+
+    def measure_fp32_peak(self):
+        v = ctypes.c_double(0.0)
+        self._check(self.lib.cledb_measure_fp32_peak(self.h, ctypes.byref(v)))
+        return float(v.value)
+
+    def set_tuning(self, pixels_per_item=32, split=0):
+        self._check(self.lib.cledb_set_tuning(self.h, int(pixels_per_item), int(split)))
+
+    # ---- databases
+    def db_put(self, db_id, db, encoding=ENC_I16):
+        flat = _as(db, np.float32).reshape(-1, 8)
+        self._check(self.lib.cledb_db_put(self.h, int(db_id), _ptr(flat), flat.shape[0], int(encoding)))
+
+    def db_drop(self, db_id):
+        self._check(self.lib.cledb_db_drop(self.h, int(db_id)))
+
+    def db_info(self, db_id):
+        v = np.zeros(16, dtype=np.int64)
+        self._check(self.lib.cledb_db_info(self.h, int(db_id), _ptr(v)))
+        return dict(n=int(v[0]), npos=int(v[1]), nneg=int(v[2]), nzero=int(v[3]), nnan=int(v[4]), encoding=int(v[5]),
+                    hbm_bytes=int(v[6]), tile=int(v[7]), shift=[int(s) for s in v[8:16]])
+
+    def db_decoded(self, db_id):
+        n = self.db_info(db_id)['n']
+        out = np.empty((n, 8), dtype=np.float32)
+        self._check(self.lib.cledb_db_decoded(self.h, int(db_id), _ptr(out)))
+        return out
+
+    def gather_rows(self, db_id, idx):
+        idx = _as(idx, np.int32).reshape(-1)
+        out = np.empty((idx.size, 8), dtype=np.float32)
+        self._check(self.lib.cledb_gather_rows(self.h, int(db_id), _ptr(idx), idx.size, _ptr(out)))
+        return out
+
+    # ---- search
+    def match(self, mode, sobs, snr, db_id, nsearch, precision=PREC_FP32, want_rows=True, want_chi64=False, out=None):
+        """Raw top-``nsearch`` of every pixel.  Returns a dict of NumPy arrays (see cledb_match in the header).
+        ``out``: optional dict of preallocated (e.g. pinned) output arrays with the same keys, reused across calls."""
+        sobs = _as(sobs, np.float32).reshape(-1, 8)
+        snr = _as(snr, np.float32).reshape(-1, 8)
+        npix = sobs.shape[0]
+        db_id = _as(np.broadcast_to(np.asarray(db_id, dtype=np.int32).reshape(-1), (npix,)), np.int32)
+        k = int(nsearch)
+        if out is None:
+            out = dict(idx=np.empty((npix, k), np.int32), chi=np.empty((npix, k), np.float32),
+                       kpos=np.empty((npix, k), np.int32), status=np.empty(npix, np.uint8),
+                       ncand=np.empty(npix, np.int64),
+                       rows=np.empty((npix, k, 8), np.float32) if want_rows else None,
+                       chi64=np.empty((npix, k), np.float64) if want_chi64 else None)
+        self._check(self.lib.cledb_match(self.h, int(mode), int(precision), npix, _ptr(sobs), _ptr(snr), _ptr(db_id), k,
+                                         _ptr(out['idx']), _ptr(out['chi']), _ptr(out['chi64']), _ptr(out['kpos']),
+                                         _ptr(out['rows']), _ptr(out['status']), _ptr(out['ncand'])))
+        return out
+
+    def match_dev(self, mode, npix, sobs_ptr, snr_ptr, dbid_ptr, nsearch, idx_ptr, chi_ptr, chi64_ptr=None, kpos_ptr=None,
+                  rows_ptr=None, status_ptr=None, ncand_ptr=None, stream=None, precision=PREC_FP32):
+        self._check(self.lib.cledb_match_dev(self.h, int(mode), int(precision), int(npix), sobs_ptr, snr_ptr, dbid_ptr,
+                                             int(nsearch), idx_ptr, chi_ptr, chi64_ptr, kpos_ptr, rows_ptr, status_ptr,
+                                             ncand_ptr, stream))
+
+    # ---- elementwise
+    def blos(self, iquv, kfac, g_eff, ffac):
+        iquv = _as(iquv, np.float32).reshape(-1, 4)
+        out = np.empty_like(iquv)
+        flags = np.empty((iquv.shape[0], 2), dtype=np.uint8)
+        self._check(self.lib.cledb_blos(self.h, iquv.shape[0], _ptr(iquv), float(kfac), float(g_eff), float(ffac),
+                                        _ptr(out), _ptr(flags)))
+        return out, flags
+
+    def blos_dev(self, npix, in_ptr, kfac, g_eff, ffac, out_ptr, flags_ptr, stream=None):
+        self._check(self.lib.cledb_blos_dev(self.h, int(npix), in_ptr, float(kfac), float(g_eff), float(ffac), out_ptr,
+                                            flags_ptr, stream))
+
+    def qurotate(self, sobs_tot, xs, ys, linpolref, hpxy=None):
+        s = _as(sobs_tot, np.float32)
+        nx, ny = s.shape[0], s.shape[1]
+        out = np.empty_like(s)
+        aobs = np.empty((nx, ny), np.float32)
+        yobs = np.empty((nx, ny), np.float32)
+        xs = None if xs is None else _as(xs, np.float64)
+        ys = None if ys is None else _as(ys, np.float64)
+        hp = None if hpxy is None else _as(hpxy, np.float32)
+        self._check(self.lib.cledb_qurotate(self.h, nx, ny, _ptr(xs), _ptr(ys), float(linpolref), _ptr(hp), _ptr(s),
+                                            _ptr(out), _ptr(aobs), _ptr(yobs)))
+        return out, aobs, yobs
+
+    def qurotate_dev(self, nx, ny, xs_ptr, ys_ptr, linpolref, hpxy_ptr, in_ptr, out_ptr, aobs_ptr, yobs_ptr, stream=None):
+        self._check(self.lib.cledb_qurotate_dev(self.h, int(nx), int(ny), xs_ptr, ys_ptr, float(linpolref), hpxy_ptr,
+                                                in_ptr, out_ptr, aobs_ptr, yobs_ptr, stream))
+
+
+_contexts = {}
+
+
+def get_context(device=0):
+    """Process-wide context per device (the reference's functions are stateless; the GPU state lives here)."""
+    ctx = _contexts.get(device)
+    if ctx is None or ctx.h is None:
+        ctx = _contexts[device] = Context(device)
+    return ctx

@@ -1,0 +1,116 @@
+// Internal declarations shared by the translation units of libcledb_b200.so (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cledb_b200.h"
+
+namespace cledb {
+
+constexpr int kTile     = 256;   // database entries per tile = one warp step (32 lanes x 8 entries)
+constexpr int kEPL      = 8;     // entries per lane
+constexpr int kNC       = 5;     // components that enter chi^2: Q1 U1 I2 Q2 U2 (indices 1 2 4 5 6)
+constexpr int kMaxP     = 32;    // pixels per work item
+constexpr int kWarps    = 8;     // compute warps per CTA
+constexpr int kThreads  = kWarps * 32;
+constexpr int kParts    = 3;     // sign(V1) classes: 0 = positive, 1 = negative, 2 = zero
+
+__host__ __device__ constexpr int chi_comp(int c) { return c == 0 ? 1 : c == 1 ? 2 : c == 2 ? 4 : c == 3 ? 5 : 6; }
+
+// One resident database as the kernels see it (lives in a device array indexed by slot).
+struct DbSlot {
+    const void*    tiles;            // [ntiles_total][kNC][kTile] half bits (I16) or float (F32)
+    const void*    vcomp;            // [npad][2]  V1, V2 in the same element type
+    const int32_t* perm;             // [npad] original row index of each stored entry, -1 = padding
+    const int32_t* kept_rank;        // [n] rank of a row among rows with non-NaN V1 (NULL if none is NaN)
+    int64_t        n;                // rows of the original database
+    int32_t        part_tile0[kParts];   // first tile of each sign class
+    int32_t        part_ntiles[kParts];
+    int32_t        part_cnt[kParts];     // entries in each class
+    int32_t        part_zero[kParts];    // bit c set: some entry of the class has decoded chi-component c == 0
+    int32_t        encoding;
+    int32_t        live;
+    float          scale[8];         // 2^-shift per original component (1 for F32)
+};
+
+// What one CTA of the search kernel processes: <= kMaxP pixels of one bucket against a tile range.
+struct Item {
+    int32_t slot;        // database slot
+    int32_t tile0;       // first tile (absolute index into DbSlot::tiles)
+    int32_t ntiles;      // tiles to scan (may be 0)
+    int32_t entry0;      // position of the first entry of the partition (for kpos)
+    int32_t pix0;        // first pixel (index into the bucket-sorted order array)
+    int32_t npx;         // pixels in this item (<= kMaxP)
+    int32_t cnt_end;     // one past the last valid position (absolute) of the partition
+    int32_t pad;
+};
+
+struct HostDb {
+    DbSlot   slot;
+    void*    d_tiles = nullptr;
+    void*    d_vcomp = nullptr;
+    int32_t* d_perm = nullptr;
+    int32_t* d_invperm = nullptr;
+    int32_t* d_kept_rank = nullptr;
+    int64_t  npad = 0, nnan = 0, bytes = 0;
+    int      shift[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+struct Workspace {
+    void*  ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace cledb
+
+struct cledb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop;
+    std::string err;
+    std::map<int, int> slot_of_id;                 // db_id -> slot
+    std::vector<cledb::HostDb> dbs;                // by slot
+    std::vector<int> free_slots;
+    cledb::DbSlot* d_slots = nullptr;              // device mirror [slots_cap]
+    int32_t* d_slot_of_id = nullptr;               // device table  [id_cap]
+    int slots_cap = 0, id_cap = 0;
+    bool tables_dirty = true;
+    cledb::Workspace ws;                           // search workspace (grown on demand)
+    cledb::Workspace io;                           // staging for the host entry points
+    int64_t launches = 0;
+    int pixels_per_item = cledb::kMaxP;
+    int split = 0;
+    int occ = 0, regs = 0, smem = 0;               // search kernel occupancy facts
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;   // event pairs around the search kernel
+    int prof_used = 0;
+    bool prof_on = false;
+};
+
+#define CLEDB_CUDA(ctx, call)                                                                   \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+            return CLEDB_ERR_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+namespace cledb {
+int  ensure_workspace(cledb_ctx* ctx, Workspace& w, size_t bytes);
+int  sync_tables(cledb_ctx* ctx, cudaStream_t st);
+int  match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const float* sobs, const float* snr,
+                  const int32_t* db_id, int nsearch, int32_t* idx_out, float* chi_out, double* chi64_out,
+                  int32_t* kpos_out, float* rows_out, uint8_t* status_out, int64_t* ncand_out, cudaStream_t st);
+int  match_occupancy(cledb_ctx* ctx);
+int  launch_decode_db(cledb_ctx* ctx, int slot, float* d_out, cudaStream_t st);
+int  launch_gather_rows(cledb_ctx* ctx, int slot, const int32_t* d_idx, int64_t n, float* d_rows, cudaStream_t st);
+int  launch_blos(cledb_ctx* ctx, int64_t npix, const float* iquv, double kfac, double g_eff, double ffac,
+                 float* out, uint8_t* flags, cudaStream_t st);
+int  measure_fp32_peak(cledb_ctx* ctx, double* tflops);
+int  launch_qurotate(cledb_ctx* ctx, int nx, int ny, const double* xs, const double* ys, double linpolref,
+                     const float* hpxy, const float* in, float* out, float* aobs, float* yobs, cudaStream_t st);
+}  // namespace cledb

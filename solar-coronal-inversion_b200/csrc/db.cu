@@ -1,0 +1,360 @@
+// Database residency: sign partitioning, int16 encoding, upload.  Replaces the per-task pickling of
+// database[db_enc[xx,yy]] (CLEDB_PROC.py:304-307) and the per-pixel argwhere/gather on sign(V1)
+// (CLEDB_PROC.py:974-976) of the reference: both are done once per database here.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "cledb_internal.h"
+
+using namespace cledb;
+
+// ------------------------------------------------------------------------------------------------------
+// codec: int16 code = binary16 bit pattern of x * 2^shift
+// ------------------------------------------------------------------------------------------------------
+static inline uint16_t f32_to_f16_bits_rn(float f) {
+    // round-to-nearest-even float32 -> binary16, written out so that host results do not depend on F16C
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    const uint32_t absx = x & 0x7fffffffu;
+    if (absx >= 0x7f800000u) return (uint16_t)(sign | (absx > 0x7f800000u ? 0x7e00u : 0x7c00u));   // NaN / inf
+    if (absx >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);            // rounds to >= 65520 -> inf
+    if (absx < 0x33000001u) return (uint16_t)sign;                         // <= 2^-25 -> +-0
+    int32_t exp = (int32_t)(absx >> 23) - 127;
+    uint32_t man = (absx & 0x7fffffu) | 0x800000u;                         // 24-bit significand
+    int shift;                                                             // bits to drop
+    uint32_t hexp;
+    if (exp < -14) { shift = 13 + (-14 - exp); hexp = 0; }                 // subnormal half
+    else { shift = 13; hexp = (uint32_t)(exp + 15); }
+    const uint32_t keep = man >> shift;
+    const uint32_t rem = man & ((1u << shift) - 1u);
+    const uint32_t halfway = 1u << (shift - 1);
+    uint32_t h = (hexp << 10) + (hexp ? (keep & 0x3ffu) : keep);
+    if (rem > halfway || (rem == halfway && (keep & 1u))) h += 1;          // carries propagate into the exponent
+    return (uint16_t)(sign | h);
+}
+static inline float f16_bits_to_f32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    const uint32_t exp = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+    uint32_t x;
+    if (exp == 0) {
+        if (man == 0) x = sign;
+        else {
+            float v = std::ldexp((float)man, -24);
+            std::memcpy(&x, &v, 4);
+            x |= sign;
+        }
+    } else if (exp == 31) x = sign | 0x7f800000u | (man << 13);
+    else x = sign | ((exp + 112u) << 23) | (man << 13);
+    float f;
+    std::memcpy(&f, &x, 4);
+    return f;
+}
+
+extern "C" int cledb_codec_shift(const float* x, int64_t n, int64_t stride) {
+    float mx = 0.f;
+    for (int64_t i = 0; i < n; ++i) {
+        const float a = std::fabs(x[i * stride]);
+        if (std::isfinite(a) && a > mx) mx = a;
+    }
+    if (mx == 0.f) return 0;
+    int e;
+    std::frexp(mx, &e);                 // mx = m * 2^e, m in [0.5, 1)  ->  mx * 2^(15-e) in [2^14, 2^15)
+    int s = 15 - e;
+    if (s > 100) s = 100;
+    if (s < -100) s = -100;
+    return s;
+}
+extern "C" void cledb_codec_encode(const float* x, int64_t n, int shift, int16_t* codes) {
+    for (int64_t i = 0; i < n; ++i) codes[i] = (int16_t)f32_to_f16_bits_rn(std::ldexp(x[i], shift));
+}
+extern "C" void cledb_codec_decode(const int16_t* codes, int64_t n, int shift, float* x) {
+    for (int64_t i = 0; i < n; ++i) x[i] = std::ldexp(f16_bits_to_f32((uint16_t)codes[i]), -shift);
+}
+
+// ------------------------------------------------------------------------------------------------------
+namespace cledb {
+
+int ensure_workspace(cledb_ctx* ctx, Workspace& w, size_t bytes) {
+    if (bytes <= w.bytes) return CLEDB_OK;
+    if (w.ptr) {
+        CLEDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CLEDB_CUDA(ctx, cudaDeviceSynchronize());
+        cudaFree(w.ptr);
+        w.ptr = nullptr;
+        w.bytes = 0;
+    }
+    const size_t want = bytes + bytes / 4;
+    if (cudaMalloc(&w.ptr, want) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->err = "out of device memory for the search workspace";
+        return CLEDB_ERR_NOMEM;
+    }
+    w.bytes = want;
+    return CLEDB_OK;
+}
+
+int sync_tables(cledb_ctx* ctx, cudaStream_t st) {
+    if (!ctx->tables_dirty) return CLEDB_OK;
+    const int nslots = (int)ctx->dbs.size();
+    int max_id = -1;
+    for (auto& kv : ctx->slot_of_id) max_id = std::max(max_id, kv.first);
+    if (nslots > ctx->slots_cap || !ctx->d_slots) {
+        CLEDB_CUDA(ctx, cudaDeviceSynchronize());
+        if (ctx->d_slots) cudaFree(ctx->d_slots);
+        ctx->slots_cap = std::max(16, nslots * 2);
+        CLEDB_CUDA(ctx, cudaMalloc(&ctx->d_slots, sizeof(DbSlot) * ctx->slots_cap));
+    }
+    if (max_id + 1 > ctx->id_cap || !ctx->d_slot_of_id) {
+        CLEDB_CUDA(ctx, cudaDeviceSynchronize());
+        if (ctx->d_slot_of_id) cudaFree(ctx->d_slot_of_id);
+        ctx->id_cap = std::max(64, (max_id + 1) * 2);
+        CLEDB_CUDA(ctx, cudaMalloc(&ctx->d_slot_of_id, sizeof(int32_t) * ctx->id_cap));
+    }
+    std::vector<DbSlot> hs(ctx->slots_cap);
+    std::memset(hs.data(), 0, sizeof(DbSlot) * hs.size());
+    for (int i = 0; i < nslots; ++i) hs[i] = ctx->dbs[i].slot;
+    std::vector<int32_t> hid(ctx->id_cap, -1);
+    for (auto& kv : ctx->slot_of_id) hid[kv.first] = kv.second;
+    // synchronous copies from pageable memory: the tables are tiny and change only when databases change
+    CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
+    CLEDB_CUDA(ctx, cudaMemcpy(ctx->d_slots, hs.data(), sizeof(DbSlot) * hs.size(), cudaMemcpyHostToDevice));
+    CLEDB_CUDA(ctx, cudaMemcpy(ctx->d_slot_of_id, hid.data(), sizeof(int32_t) * hid.size(), cudaMemcpyHostToDevice));
+    ctx->tables_dirty = false;
+    return CLEDB_OK;
+}
+
+static void free_db(HostDb& h) {
+    if (h.d_tiles) cudaFree(h.d_tiles);
+    if (h.d_vcomp) cudaFree(h.d_vcomp);
+    if (h.d_perm) cudaFree(h.d_perm);
+    if (h.d_invperm) cudaFree(h.d_invperm);
+    if (h.d_kept_rank) cudaFree(h.d_kept_rank);
+    h = HostDb();
+    std::memset(&h.slot, 0, sizeof(DbSlot));
+}
+
+}  // namespace cledb
+
+extern "C" int cledb_db_drop(cledb_ctx* ctx, int db_id) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    auto it = ctx->slot_of_id.find(db_id);
+    if (it == ctx->slot_of_id.end()) { ctx->err = "cledb_db_drop: unknown database id"; return CLEDB_ERR_NODB; }
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CLEDB_CUDA(ctx, cudaDeviceSynchronize());
+    free_db(ctx->dbs[it->second]);
+    ctx->free_slots.push_back(it->second);
+    ctx->slot_of_id.erase(it);
+    ctx->tables_dirty = true;
+    return CLEDB_OK;
+}
+
+extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t n, int encoding) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    if (!db || n <= 0 || db_id < 0 || db_id > (1 << 24)) { ctx->err = "cledb_db_put: bad argument"; return CLEDB_ERR_ARG; }
+    if (n > (int64_t)1 << 30) { ctx->err = "cledb_db_put: more than 2^30 rows"; return CLEDB_ERR_ARG; }
+    if (encoding != CLEDB_ENC_F32 && encoding != CLEDB_ENC_I16) { ctx->err = "cledb_db_put: unknown encoding"; return CLEDB_ERR_ARG; }
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    // ---- classify rows by sign(V1); validate the layout contract
+    std::vector<int8_t> cls(n);
+    int64_t cnt[kParts] = {0, 0, 0}, nnan = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* r = db + i * 8;
+        if (r[0] != 1.0f) {
+            ctx->err = "cledb_db_put: component 0 of row " + std::to_string(i) + " is not exactly 1 (database must be normalised by I1, CLEDB_PREPINV.py:306-317)";
+            return CLEDB_ERR_DBFORMAT;
+        }
+        const float v = r[3];
+        int c;
+        if (std::isnan(v)) { c = -1; ++nnan; }
+        else if (v > 0.f) c = 0;
+        else if (v < 0.f) c = 1;
+        else c = 2;
+        cls[i] = (int8_t)c;
+        if (c >= 0) {
+            ++cnt[c];
+            if (!(std::isfinite(r[1]) && std::isfinite(r[2]) && std::isfinite(r[4]) && std::isfinite(r[5]) && std::isfinite(r[6]))) {
+                ctx->err = "cledb_db_put: non-finite Stokes I/Q/U in candidate row " + std::to_string(i);
+                return CLEDB_ERR_DBFORMAT;
+            }
+        }
+    }
+    if (cledb_db_drop(ctx, db_id) != CLEDB_OK) ctx->err.clear();   // replace an existing database of this id
+
+    HostDb h;
+    std::memset(&h.slot, 0, sizeof(DbSlot));
+    int64_t tile = 0;
+    int64_t pos0[kParts];
+    for (int q = 0; q < kParts; ++q) {
+        h.slot.part_tile0[q] = (int32_t)tile;
+        h.slot.part_ntiles[q] = (int32_t)((cnt[q] + kTile - 1) / kTile);
+        h.slot.part_cnt[q] = (int32_t)cnt[q];
+        pos0[q] = tile * kTile;
+        tile += h.slot.part_ntiles[q];
+    }
+    const int64_t ntiles = tile, npad = ntiles * kTile;
+    h.npad = npad;
+    h.nnan = nnan;
+
+    // ---- block exponents per component (int16 encoding); scale = 2^-shift
+    for (int c = 0; c < 8; ++c) { h.shift[c] = 0; h.slot.scale[c] = 1.0f; }
+    if (encoding == CLEDB_ENC_I16) {
+        for (int c = 1; c < 8; ++c) {
+            float mx = 0.f;
+            for (int64_t i = 0; i < n; ++i) {
+                if (cls[i] < 0) continue;
+                const float a = std::fabs(db[i * 8 + c]);
+                if (std::isfinite(a) && a > mx) mx = a;
+            }
+            int s = 0;
+            if (mx > 0.f) { int e; std::frexp(mx, &e); s = std::max(-100, std::min(100, 15 - e)); }
+            h.shift[c] = s;
+            h.slot.scale[c] = std::ldexp(1.0f, -s);
+        }
+    }
+
+    // ---- fill the partitioned arrays
+    const int elem = encoding == CLEDB_ENC_I16 ? 2 : 4;
+    std::vector<unsigned char> tiles((size_t)std::max<int64_t>(1, npad) * kNC * elem);
+    std::vector<unsigned char> vcomp((size_t)std::max<int64_t>(1, npad) * 2 * elem);
+    std::vector<int32_t> perm(std::max<int64_t>(1, npad), -1), invperm(n, -1), kept_rank;
+    {   // NaN padding: a padded entry can never win (x <= tau is false for NaN)
+        if (encoding == CLEDB_ENC_I16) {
+            uint16_t* t = reinterpret_cast<uint16_t*>(tiles.data());
+            for (size_t i = 0; i < tiles.size() / 2; ++i) t[i] = 0x7e00u;
+            uint16_t* v = reinterpret_cast<uint16_t*>(vcomp.data());
+            for (size_t i = 0; i < vcomp.size() / 2; ++i) v[i] = 0x7e00u;
+        } else {
+            const float qnan = std::nanf("");
+            float* t = reinterpret_cast<float*>(tiles.data());
+            for (size_t i = 0; i < tiles.size() / 4; ++i) t[i] = qnan;
+            float* v = reinterpret_cast<float*>(vcomp.data());
+            for (size_t i = 0; i < vcomp.size() / 4; ++i) v[i] = qnan;
+        }
+    }
+    if (nnan > 0) kept_rank.assign(n, -1);
+    int64_t cur[kParts] = {pos0[0], pos0[1], pos0[2]};
+    int32_t zero_bits[kParts] = {0, 0, 0};
+    int64_t rank = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int q = cls[i];
+        if (q < 0) continue;
+        if (nnan > 0) kept_rank[i] = (int32_t)rank;
+        ++rank;
+        const int64_t pos = cur[q]++;
+        perm[pos] = (int32_t)i;
+        invperm[i] = (int32_t)pos;
+        const int64_t tl = pos / kTile, in = pos % kTile;
+        const float* r = db + i * 8;
+        for (int c = 0; c < kNC; ++c) {
+            const int oc = chi_comp(c);
+            const size_t e = ((size_t)tl * kNC + c) * kTile + in;
+            if (encoding == CLEDB_ENC_I16) {
+                const uint16_t code = f32_to_f16_bits_rn(std::ldexp(r[oc], h.shift[oc]));
+                reinterpret_cast<uint16_t*>(tiles.data())[e] = code;
+                if ((code & 0x7fffu) == 0) zero_bits[q] |= 1 << c;
+            } else {
+                reinterpret_cast<float*>(tiles.data())[e] = r[oc];
+                if (r[oc] == 0.f) zero_bits[q] |= 1 << c;
+            }
+        }
+        for (int w = 0; w < 2; ++w) {
+            const int oc = w ? 7 : 3;
+            if (encoding == CLEDB_ENC_I16)
+                reinterpret_cast<uint16_t*>(vcomp.data())[pos * 2 + w] = f32_to_f16_bits_rn(std::ldexp(r[oc], h.shift[oc]));
+            else
+                reinterpret_cast<float*>(vcomp.data())[pos * 2 + w] = r[oc];
+        }
+    }
+    for (int q = 0; q < kParts; ++q) h.slot.part_zero[q] = zero_bits[q];
+
+    // ---- upload
+    auto fail = [&](const char* what) {
+        cudaGetLastError();
+        free_db(h);
+        ctx->err = std::string("cledb_db_put: ") + what;
+        return CLEDB_ERR_NOMEM;
+    };
+    if (cudaMalloc(&h.d_tiles, tiles.size()) != cudaSuccess) return fail("out of device memory (tiles)");
+    if (cudaMalloc(&h.d_vcomp, vcomp.size()) != cudaSuccess) return fail("out of device memory (V components)");
+    if (cudaMalloc(&h.d_perm, perm.size() * 4) != cudaSuccess) return fail("out of device memory (perm)");
+    if (cudaMalloc(&h.d_invperm, invperm.size() * 4) != cudaSuccess) return fail("out of device memory (invperm)");
+    if (nnan > 0 && cudaMalloc(&h.d_kept_rank, kept_rank.size() * 4) != cudaSuccess) return fail("out of device memory (rank)");
+    CLEDB_CUDA(ctx, cudaMemcpy(h.d_tiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
+    CLEDB_CUDA(ctx, cudaMemcpy(h.d_vcomp, vcomp.data(), vcomp.size(), cudaMemcpyHostToDevice));
+    CLEDB_CUDA(ctx, cudaMemcpy(h.d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
+    CLEDB_CUDA(ctx, cudaMemcpy(h.d_invperm, invperm.data(), invperm.size() * 4, cudaMemcpyHostToDevice));
+    if (nnan > 0) CLEDB_CUDA(ctx, cudaMemcpy(h.d_kept_rank, kept_rank.data(), kept_rank.size() * 4, cudaMemcpyHostToDevice));
+    h.bytes = (int64_t)(tiles.size() + vcomp.size() + perm.size() * 4 + invperm.size() * 4 + kept_rank.size() * 4);
+    h.slot.tiles = h.d_tiles;
+    h.slot.vcomp = h.d_vcomp;
+    h.slot.perm = h.d_perm;
+    h.slot.kept_rank = h.d_kept_rank;
+    h.slot.n = n;
+    h.slot.encoding = encoding;
+    h.slot.live = 1;
+
+    int slot;
+    if (!ctx->free_slots.empty()) { slot = ctx->free_slots.back(); ctx->free_slots.pop_back(); ctx->dbs[slot] = h; }
+    else { slot = (int)ctx->dbs.size(); ctx->dbs.push_back(h); }
+    ctx->slot_of_id[db_id] = slot;
+    ctx->tables_dirty = true;
+    return CLEDB_OK;
+}
+
+extern "C" int cledb_db_info(cledb_ctx* ctx, int db_id, int64_t info[16]) {
+    if (!ctx || !info) return CLEDB_ERR_ARG;
+    auto it = ctx->slot_of_id.find(db_id);
+    if (it == ctx->slot_of_id.end()) { ctx->err = "cledb_db_info: unknown database id"; return CLEDB_ERR_NODB; }
+    const HostDb& h = ctx->dbs[it->second];
+    info[0] = h.slot.n;
+    info[1] = h.slot.part_cnt[0];
+    info[2] = h.slot.part_cnt[1];
+    info[3] = h.slot.part_cnt[2];
+    info[4] = h.nnan;
+    info[5] = h.slot.encoding;
+    info[6] = h.bytes;
+    info[7] = kTile;
+    for (int c = 0; c < 8; ++c) info[8 + c] = h.shift[c];
+    return CLEDB_OK;
+}
+
+extern "C" int cledb_db_decoded(cledb_ctx* ctx, int db_id, float* out) {
+    if (!ctx || !out) return CLEDB_ERR_ARG;
+    auto it = ctx->slot_of_id.find(db_id);
+    if (it == ctx->slot_of_id.end()) { ctx->err = "cledb_db_decoded: unknown database id"; return CLEDB_ERR_NODB; }
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = sync_tables(ctx, ctx->stream);
+    if (rc) return rc;
+    const int64_t n = ctx->dbs[it->second].slot.n;
+    float* d = nullptr;
+    if (cudaMalloc(&d, (size_t)n * 32) != cudaSuccess) { cudaGetLastError(); ctx->err = "cledb_db_decoded: out of device memory"; return CLEDB_ERR_NOMEM; }
+    rc = launch_decode_db(ctx, it->second, d, ctx->stream);
+    if (rc == CLEDB_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("cledb_db_decoded: ") + cudaGetErrorString(e); rc = CLEDB_ERR_CUDA; }
+    }
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int cledb_gather_rows(cledb_ctx* ctx, int db_id, const int32_t* idx, int64_t n, float* rows_out) {
+    if (!ctx || !idx || !rows_out || n < 0) return CLEDB_ERR_ARG;
+    auto it = ctx->slot_of_id.find(db_id);
+    if (it == ctx->slot_of_id.end()) { ctx->err = "cledb_gather_rows: unknown database id"; return CLEDB_ERR_NODB; }
+    if (n == 0) return CLEDB_OK;
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = sync_tables(ctx, ctx->stream);
+    if (rc) return rc;
+    if ((rc = ensure_workspace(ctx, ctx->io, (size_t)n * 36 + 512))) return rc;
+    int32_t* d_idx = reinterpret_cast<int32_t*>(ctx->io.ptr);
+    float* d_rows = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx->io.ptr) + ((size_t)n * 4 + 255) / 256 * 256);
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(d_idx, idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_gather_rows(ctx, it->second, d_idx, n, d_rows, ctx->stream))) return rc;
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(rows_out, d_rows, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CLEDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CLEDB_OK;
+}

@@ -1,0 +1,142 @@
+// The two elementwise, HBM-bandwidth-bound neighbours of the search:
+//   k_blos      1-line analytic B_LOS, blos_proc_1pix of the reference (CLEDB_PROC.py:874-914)
+//   k_qurotate  linear-polarisation frame rotation + height map, obs_qurotate + obs_calcheight
+//               (CLEDB_PREPINV.py:1277-1350, 897-926)
+// One thread per pixel, 128-bit coalesced loads/stores, grid sized from the pixel count.
+#include <math_constants.h>
+
+#include "cledb_internal.h"
+
+namespace cledb {
+
+// 34 B/pixel: 16 in, 16 out, 2 flag bytes
+__global__ void __launch_bounds__(256) k_blos(int64_t npix, const float4* __restrict__ iquv, float kfac, float geff, float c66f,
+                                              float4* __restrict__ out, uchar2* __restrict__ flags) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const float4 s = iquv[p];
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    uchar2 f = make_uchar2(0, 0);
+    const bool bad = (s.x == 0.f) || isnan(s.x) || isnan(s.y) || isnan(s.z) || isnan(s.w);   // CLEDB_PROC.py:882
+    if (!bad) {
+        // float32 arithmetic in the reference: NumPy float32 scalars with Python-float constants (weak promotion)
+        const float lpol = __fsqrt_rn(__fadd_rn(__fmul_rn(s.y, s.y), __fmul_rn(s.z, s.z)));
+        const float nv = -s.w;
+        const float d0 = __fsub_rn(__fmul_rn(geff, __fsub_rn(s.x, lpol)), __fmul_rn(c66f, lpol));
+        const float d1 = __fadd_rn(__fmul_rn(geff, __fadd_rn(s.x, lpol)), __fmul_rn(c66f, lpol));
+        const float d2 = __fmul_rn(geff, s.x);
+        o.x = __fmul_rn(kfac, __fdiv_rn(nv, d0));
+        o.y = __fmul_rn(kfac, __fdiv_rn(nv, d1));
+        o.z = __fmul_rn(kfac, __fdiv_rn(nv, d2));
+        o.w = 0.5f * atan2f(s.z, s.y);
+        const float qi = __fdiv_rn(s.y, s.x), ui = __fdiv_rn(s.z, s.x);
+        if (fabsf(qi) < 1e-6f || fabsf(ui) < 1e-6f) {            // :907
+            f.x = 1;
+            if (qi < 1e-6f && ui < 1e-6f) f.y = 1;                // :909 (signed comparison, as in the reference)
+        }
+    }
+    out[p] = o;
+    flags[p] = f;
+}
+
+// 72 B/pixel (+8 with a coordinate grid): 32 in, 32 out, aobs, yobs
+__global__ void __launch_bounds__(256) k_qurotate(int nx, int ny, const double* __restrict__ xs, const double* __restrict__ ys,
+                                                  float linpolref, const float* __restrict__ hpxy, const float4* __restrict__ in,
+                                                  float4* __restrict__ out, float* __restrict__ aobs, float* __restrict__ yobs) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t npix = (int64_t)nx * ny;
+    if (p >= npix) return;
+    float a, y;
+    if (hpxy) {   // Cryo-NIRSP coordinate grid: float32 arithmetic (CLEDB_PREPINV.py:923, 1326)
+        const float px = hpxy[p], py = hpxy[npix + p];
+        y = __fsqrt_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)));
+        a = -atan2f(px, py);
+    } else {      // header keywords are Python floats: float64 until the store into the float32 arrays
+        const double px = xs[p / ny], py = ys[p % ny];
+        y = (float)sqrt(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
+        a = (float)(-atan2(px, py));
+    }
+    const float twopi = 6.283185307179586f;
+    if (a < 0.f) a = __fadd_rn(twopi, a);
+    a = (a < linpolref) ? __fsub_rn(twopi, a) : __fadd_rn(a, linpolref);
+    float sn, cs;
+    sincosf(__fmul_rn(2.0f, a), &sn, &cs);
+    const float4 l1 = in[2 * p], l2 = in[2 * p + 1];
+    float4 o1 = l1, o2 = l2;
+    o1.y = __fsub_rn(__fmul_rn(l1.y, cs), __fmul_rn(l1.z, sn));
+    o1.z = __fadd_rn(__fmul_rn(l1.y, sn), __fmul_rn(l1.z, cs));
+    o2.y = __fsub_rn(__fmul_rn(l2.y, cs), __fmul_rn(l2.z, sn));
+    o2.z = __fadd_rn(__fmul_rn(l2.y, sn), __fmul_rn(l2.z, cs));
+    out[2 * p] = o1;
+    out[2 * p + 1] = o2;
+    aobs[p] = a;
+    yobs[p] = y;
+}
+
+// FP32 FFMA-pipe peak: 16 independent FMA chains per thread, no memory traffic.  The denominator of the search
+// kernel's roofline (MEASURED_PEAKS.json only carries HBM and bf16 tensor peaks).
+__global__ void __launch_bounds__(256) k_ffma_peak(float* sink, int iters, float x, float y) {
+    float a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = (float)(threadIdx.x + j) * 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = fmaf(a[j], x, y);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += a[j];
+    if (s == 123.456f) sink[0] = s;    // never true; keeps the chains alive
+}
+
+int measure_fp32_peak(cledb_ctx* ctx, double* tflops) {
+    float* sink = nullptr;
+    CLEDB_CUDA(ctx, cudaMalloc(&sink, 256));
+    const int iters = 1 << 14, grid = ctx->prop.multiProcessorCount * 8;
+    cudaEvent_t a, b;
+    CLEDB_CUDA(ctx, cudaEventCreate(&a));
+    CLEDB_CUDA(ctx, cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CLEDB_CUDA(ctx, cudaEventRecord(a, ctx->stream));
+        k_ffma_peak<<<grid, 256, 0, ctx->stream>>>(sink, iters, 0.999f, 1e-3f);
+        CLEDB_CUDA(ctx, cudaEventRecord(b, ctx->stream));
+        CLEDB_CUDA(ctx, cudaEventSynchronize(b));
+        float ms = 0.f;
+        CLEDB_CUDA(ctx, cudaEventElapsedTime(&ms, a, b));
+        const double tf = 2.0 * 16.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+        ctx->launches++;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    *tflops = best;
+    return CLEDB_OK;
+}
+
+int launch_blos(cledb_ctx* ctx, int64_t npix, const float* iquv, double kfac, double g_eff, double ffac, float* out,
+                uint8_t* flags, cudaStream_t st) {
+    if (npix == 0) return CLEDB_OK;
+    // Python evaluates 0.66*F_factor in float64; NumPy then rounds that product, g_eff and the constant K to
+    // float32 when they meet float32 scalars (CLEDB_PROC.py:889-896)
+    k_blos<<<(int)((npix + 255) / 256), 256, 0, st>>>(npix, reinterpret_cast<const float4*>(iquv), (float)kfac, (float)g_eff,
+                                                      (float)(0.66 * ffac), reinterpret_cast<float4*>(out),
+                                                      reinterpret_cast<uchar2*>(flags));
+    ctx->launches++;
+    CLEDB_CUDA(ctx, cudaGetLastError());
+    return CLEDB_OK;
+}
+
+int launch_qurotate(cledb_ctx* ctx, int nx, int ny, const double* xs, const double* ys, double linpolref, const float* hpxy,
+                    const float* in, float* out, float* aobs, float* yobs, cudaStream_t st) {
+    const int64_t npix = (int64_t)nx * ny;
+    if (npix == 0) return CLEDB_OK;
+    k_qurotate<<<(int)((npix + 255) / 256), 256, 0, st>>>(nx, ny, xs, ys, (float)linpolref, hpxy,
+                                                          reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), aobs, yobs);
+    ctx->launches++;
+    CLEDB_CUDA(ctx, cudaGetLastError());
+    return CLEDB_OK;
+}
+
+}  // namespace cledb

@@ -1,0 +1,938 @@
+// The 2-line database search on sm_100a: classification/bucketing of pixels, the chi^2 + top-nsearch kernel
+// and the merge/finalise kernel.  Replaces the per-pixel body of cledb_matchiquv / cledb_matchiqud
+// (CLEDB_PROC.py:944-1013 and 1118-1188 of the reference) for a whole map at once.
+//
+// Work decomposition:
+//   bucket  = all pixels that search the same candidate list: (database, sign(V_obs)) for IQUV, database for IQUD
+//   item    = <= 32 pixels of one bucket  x  one contiguous tile range of one sign partition of the database
+//   CTA     = 8 warps; the warps take tiles of the item round-robin.  A lane holds 8 database entries
+//             (5 chi^2 components each, decoded from int16 in registers) and streams the item's pixels past
+//             them: per pixel 3 broadcast LDS.128 (10 coefficients + constant + threshold) feed 80 FFMA.
+//   top-k   = per pixel one list of nsearch (value, position) pairs in shared memory, kept sorted, distributed
+//             over the lanes of whichever warp inserts (warp shuffles); the k-th value is the running threshold
+//             tau that every warp compares against, so after the bootstrap tile insertions are rare.
+//   TMA     = database tiles are contiguous 2.5 KB (int16) / 5 KB (fp32) blocks moved global->shared with
+//             cp.async.bulk + mbarrier complete_tx, double buffered per warp; no __syncthreads in the main loop.
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "cledb_internal.h"
+
+namespace cledb {
+
+// ------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// per-pixel records and per-list entries for the two arithmetic variants
+// ------------------------------------------------------------------------------------------------------
+template <int PREC> struct Rec;
+// fp32 production: residual r_c = d_c * a_c + nb_c with a_c = w_c/sigma_c (x 2^-shift), nb_c = -a_c * s~_c
+template <> struct __align__(16) Rec<CLEDB_PREC_FP32> {
+    float a[kNC];
+    float nb[kNC];
+    float c0;    // constant component-0 term ((1 - s~_0)/sigma_0)^2, 0 for IQUV
+    float tau;   // running threshold: k-th best value so far (same units as the accumulators)
+};
+// fp64 validation: the reference's operation order, needs s~ and sigma themselves
+template <> struct __align__(16) Rec<CLEDB_PREC_FP64> {
+    float  st[kNC];
+    float  sig[kNC];
+    float  pad[2];
+    double c0;
+    double tau;
+};
+template <int PREC> struct Val { using type = float; };
+template <> struct Val<CLEDB_PREC_FP64> { using type = double; };
+
+template <int PREC> struct __align__(8) Cand { float v; int32_t pos; };
+template <> struct __align__(16) Cand<CLEDB_PREC_FP64> { double v; int32_t pos; int32_t pad; };
+
+template <int ENC> struct EncTraits;
+template <> struct EncTraits<CLEDB_ENC_I16> { static constexpr int kElem = 2; };
+template <> struct EncTraits<CLEDB_ENC_F32> { static constexpr int kElem = 4; };
+template <int ENC> __host__ __device__ constexpr int tile_bytes() { return kNC * kTile * EncTraits<ENC>::kElem; }
+
+constexpr int kStages = 2;
+
+// position inside a tile of entry e of a lane.  Chosen so that the lane's shared-memory reads are 16-byte
+// vectors at a 16-byte lane stride (conflict free): int16 -> 8 consecutive entries per lane and component,
+// fp32 -> two groups of 4 consecutive entries, 128 entries apart.
+template <int ENC> __device__ __forceinline__ int pos_in_tile(int lane, int e) {
+    if (ENC == CLEDB_ENC_I16) return lane * 8 + e;
+    return (e >> 2) * 128 + lane * 4 + (e & 3);
+}
+
+// decode one tile from shared memory into registers: d[e][c] for the lane's 8 entries
+template <int ENC> __device__ __forceinline__ void load_tile_regs(const unsigned char* stage, int lane, float (&d)[kEPL][kNC]) {
+    if (ENC == CLEDB_ENC_I16) {
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) {
+            const uint4 w = *reinterpret_cast<const uint4*>(stage + (c * kTile + lane * 8) * 2);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __half2 h = *reinterpret_cast<const __half2*>(&ww[j]);
+                const float2 f = __half22float2(h);   // exact: the int16 code is a binary16 bit pattern
+                d[2 * j][c] = f.x;
+                d[2 * j + 1][c] = f.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) {
+            const float4 lo = *reinterpret_cast<const float4*>(stage + (c * kTile + lane * 4) * 4);
+            const float4 hi = *reinterpret_cast<const float4*>(stage + (c * kTile + 128 + lane * 4) * 4);
+            d[0][c] = lo.x; d[1][c] = lo.y; d[2][c] = lo.z; d[3][c] = lo.w;
+            d[4][c] = hi.x; d[5][c] = hi.y; d[6][c] = hi.z; d[7][c] = hi.w;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// chi^2 of one (pixel, entry) pair
+// ------------------------------------------------------------------------------------------------------
+// fp32: 10 FFMA.  acc = c0 + sum_c (d_c*a_c + nb_c)^2 = 2 * chi^2 (the halving is exact and done at the end).
+__device__ __forceinline__ float eval_fp32(const float (&d)[kNC], const float (&a)[kNC], const float (&nb)[kNC], float c0) {
+    float acc = c0;
+#pragma unroll
+    for (int c = 0; c < kNC; ++c) {
+        const float r = fmaf(d[c], a[c], nb[c]);
+        acc = fmaf(r, r, acc);
+    }
+    return acc;
+}
+// fp64 validation: float32 subtract and divide, float64 weight/square, NumPy's pairwise order over the 8 terms
+// ((t0+t1)+(t2+t3))+((t4+t5)+(t6+t7)) with t3 = t7 = +0, /2, round to 15 decimals as rint(x*1e15)/1e15
+// (CLEDB_PROC.py:989-1005).  d must already be the decoded database value.
+__device__ __forceinline__ double eval_fp64(const float (&d)[kNC], const float (&st)[kNC], const float (&sig)[kNC], double c0) {
+    double q[kNC];
+#pragma unroll
+    for (int c = 0; c < kNC; ++c) {
+        const float r = __fdiv_rn(__fsub_rn(d[c], st[c]), sig[c]);
+        const double t = (c == 2) ? __dmul_rn((double)r, 0.01) : (double)r;
+        q[c] = __dmul_rn(t, t);
+    }
+    const double left = __dadd_rn(__dadd_rn(c0, q[0]), q[1]);
+    const double right = __dadd_rn(__dadd_rn(q[2], q[3]), q[4]);
+    const double half = __dmul_rn(__dadd_rn(left, right), 0.5);
+    return __ddiv_rn(rint(__dmul_rn(half, 1e15)), 1e15);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// warp helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_min(float v) {   // values are >= +0 or +inf: the bit patterns order like uints
+    return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float  inf_of(float)  { return CUDART_INF_F; }
+__device__ __forceinline__ double inf_of(double) { return CUDART_INF; }
+
+// Insert candidate (v, pos) into the sorted list of one pixel.  Called by a whole warp with warp-uniform
+// arguments.  Lane j < k holds list element j; order is lexicographic (value, position) so that equal chi^2
+// resolve to the lowest database row (NumPy argmin = first occurrence).  The list is shared by the 8 warps
+// of the CTA: a spin lock in shared memory serialises writers (insertions are rare after the bootstrap).
+template <int PREC>
+__device__ __forceinline__ void list_insert(volatile Cand<PREC>* list, int* lock, volatile typename Val<PREC>::type* tau,
+                                            int k, typename Val<PREC>::type v, int pos, int lane) {
+    using V = typename Val<PREC>::type;
+    if (lane == 0) {
+        while (atomicCAS(lock, 0, 1) != 0) {
+        }
+    }
+    __syncwarp();
+    V lv = inf_of(V());
+    uint32_t lp = 0xffffffffu;
+    if (lane < k) {
+        lv = list[lane].v;
+        lp = (uint32_t)list[lane].pos;
+    }
+    const bool before = (lane < k) && (lv < v || (lv == v && lp < (uint32_t)pos));
+    const int q = __popc(__ballot_sync(0xffffffffu, before));   // elements that stay in front (a prefix: list is sorted)
+    if (q < k) {
+        const V uv = __shfl_up_sync(0xffffffffu, lv, 1);
+        const uint32_t up = __shfl_up_sync(0xffffffffu, lp, 1);
+        if (lane == q) {
+            lv = v;
+            lp = (uint32_t)pos;
+        } else if (lane > q) {
+            lv = uv;
+            lp = up;
+        }
+        if (lane >= q && lane < k) {
+            list[lane].v = lv;
+            list[lane].pos = (int32_t)lp;
+        }
+        if (lane == k - 1) *tau = lv;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        atomicExch(lock, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// device-side bookkeeping shared by the kernels
+// ------------------------------------------------------------------------------------------------------
+struct Plan {                 // all pointers are device pointers into the workspace
+    int32_t* key;             // [npix]  bucket of a pixel, -1 = not searched
+    int32_t* rank;            // [npix]  position of the pixel in `order`
+    int32_t* order;           // [npix]  pixels sorted by bucket
+    int32_t* cnt;             // [nkeys] pixels per bucket
+    int32_t* cursor;          // [nkeys]
+    int32_t* off;             // [nkeys] first position of the bucket in `order`
+    int32_t* item0;           // [nkeys+1] first item of the bucket; item0[nkeys] = total items
+    int32_t* nsub;            // [nkeys] candidate-list pieces (sign partitions x chunks) per pixel tile
+    int32_t* counters;        // [0] next item to hand out, [1] error flag, [2] total items
+    void*    recs;            // [npix] Rec<PREC>
+    void*    plist;           // [maxitems][P][k] Cand<PREC>
+    uint8_t* status;          // [npix]
+    int32_t  nkeys;
+    int32_t  P;               // pixels per item
+    int32_t  split;           // chunks per sign partition
+    int32_t  mode;
+    int32_t  k;
+    int64_t  npix;
+};
+
+__device__ __forceinline__ int nonempty_parts(const DbSlot& s) {
+    return (s.part_cnt[0] > 0) + (s.part_cnt[1] > 0) + (s.part_cnt[2] > 0);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// kernel 1: classify pixels, build their records, count bucket sizes
+// ------------------------------------------------------------------------------------------------------
+template <int PREC>
+__global__ void __launch_bounds__(256) k_classify(Plan pl, const float* __restrict__ sobs, const float* __restrict__ snr,
+                                                   const int32_t* __restrict__ db_id, const DbSlot* __restrict__ slots,
+                                                   const int32_t* __restrict__ slot_of_id, int id_cap) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pl.npix) return;
+    float s[8], n[8];
+    {
+        const float4 a = reinterpret_cast<const float4*>(sobs)[2 * p], b = reinterpret_cast<const float4*>(sobs)[2 * p + 1];
+        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+        const float4 c = reinterpret_cast<const float4*>(snr)[2 * p], d = reinterpret_cast<const float4*>(snr)[2 * p + 1];
+        n[0] = c.x; n[1] = c.y; n[2] = c.z; n[3] = c.w; n[4] = d.x; n[5] = d.y; n[6] = d.z; n[7] = d.w;
+    }
+    pl.key[p] = -1;
+    const int id = db_id[p];
+    int slot = (id >= 0 && id < id_cap) ? slot_of_id[id] : -1;
+    int nnan = 0, nzero = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        nnan += isnan(s[c]) ? 1 : 0;
+        nzero += (s[c] == 0.0f) ? 1 : 0;
+    }
+    // null pixel: CLEDB_PROC.py:944 (.any()) for IQUV, :1118 (.all()) for IQUD
+    const bool null_pix = (pl.mode == CLEDB_MODE_IQUV) ? (nnan > 0 || nzero == 8) : (nnan == 8 || nzero == 8);
+    if (null_pix) {
+        pl.status[p] = CLEDB_PIX_NULL;
+        return;
+    }
+    if (slot < 0 || !slots[slot].live) {     // only searched pixels need their database
+        atomicExch(&pl.counters[1], 1);
+        pl.status[p] = CLEDB_PIX_NULL;
+        return;
+    }
+    const DbSlot& db = slots[slot];
+    if (pl.mode == CLEDB_MODE_IQUD && nnan > 0) {   // np.max is NaN -> argwhere()[0,0] raises (CLEDB_PROC.py:1155)
+        pl.status[p] = CLEDB_PIX_REFRAISES;
+        return;
+    }
+    int cls = 0;
+    float nf;
+    if (pl.mode == CLEDB_MODE_IQUV) {
+        cls = s[3] > 0.0f ? 0 : (s[3] < 0.0f ? 1 : 2);          // np.sign(sobs[3]) against np.sign(D[:,3]), :974
+        nf = s[0];                                               // :980
+        if (db.part_cnt[cls] == 0) {                             // empty candidate list: argmin of empty raises
+            pl.status[p] = CLEDB_PIX_REFRAISES;
+            return;
+        }
+    } else {
+        nf = s[0];
+#pragma unroll
+        for (int c = 1; c < 8; ++c) nf = fmaxf(nf, s[c]);       // :1155 (no NaN here)
+        if (nonempty_parts(db) == 0) {
+            pl.status[p] = CLEDB_PIX_REFRAISES;
+            return;
+        }
+    }
+    float st[8], sig[8];
+    bool allnan = false, allinf = false;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        st[c] = __fdiv_rn(s[c], nf);                             // sobs/norm_fact, float32
+        sig[c] = __fdiv_rn(st[c], n[c]);                         // sobs/norm_fact/snr, float32
+        if (!isfinite(st[c]) || isnan(sig[c])) allnan = true;
+    }
+    if (sig[3] == 0.0f || sig[7] == 0.0f) allnan = true;         // x/0 = inf or NaN, times weight 0 = NaN
+    if (sig[0] == 0.0f) allinf = true;                           // (1 - 0)/0 = inf with weight 1
+#pragma unroll
+    for (int c = 0; c < kNC; ++c) {
+        const int oc = chi_comp(c);
+        if (sig[oc] == 0.0f) {
+            // (D - s~)/0 is +-inf, or NaN for an entry with D == s~ (== 0): argmin then lands on the NaN
+            bool has_equal = false;
+            if (st[oc] == 0.0f) {
+                if (pl.mode == CLEDB_MODE_IQUV) has_equal = (db.part_zero[cls] >> c) & 1;
+                else has_equal = ((db.part_zero[0] | db.part_zero[1] | db.part_zero[2]) >> c) & 1;
+            }
+            if (has_equal) allnan = true; else allinf = true;
+        }
+    }
+    if (allnan) { pl.status[p] = CLEDB_PIX_ALLNAN; return; }
+    if (allinf) { pl.status[p] = CLEDB_PIX_ALLINF; return; }
+
+    const float r0 = __fdiv_rn(__fsub_rn(1.0f, st[0]), sig[0]);  // component 0 of the database is exactly 1
+    const double c0 = (double)r0 * (double)r0;
+    Rec<PREC>* rec = reinterpret_cast<Rec<PREC>*>(pl.recs) + p;
+    if (PREC == CLEDB_PREC_FP32) {
+        Rec<CLEDB_PREC_FP32> r;
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) {
+            const int oc = chi_comp(c);
+            const double w = (oc == 4) ? 0.01 : 1.0;             // wtg_fact, CLEDB_PROC.py:981
+            const float a = (float)(w / (double)sig[oc]);
+            r.nb[c] = (float)(-(double)a * (double)st[oc]);
+            r.a[c] = a * db.scale[oc];                           // fold the int16 block exponent (exact)
+        }
+        r.c0 = (float)c0;
+        r.tau = CUDART_INF_F;
+        *reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(rec) = r;
+    } else {
+        Rec<CLEDB_PREC_FP64> r;
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) {
+            r.st[c] = st[chi_comp(c)];
+            r.sig[c] = sig[chi_comp(c)];
+        }
+        r.pad[0] = r.pad[1] = 0.f;
+        r.c0 = c0;
+        r.tau = CUDART_INF;
+        *reinterpret_cast<Rec<CLEDB_PREC_FP64>*>(rec) = r;
+    }
+    const int key = slot * kParts + cls;
+    pl.key[p] = key;
+    pl.status[p] = CLEDB_PIX_SEARCHED;
+    atomicAdd(&pl.cnt[key], 1);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// kernel 2: one block scans the bucket sizes into pixel offsets and item offsets
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan(Plan pl, const DbSlot* __restrict__ slots) {
+    __shared__ int s_pix[1024], s_item[1024];
+    const int tid = threadIdx.x;
+    const int per = (pl.nkeys + 1023) / 1024;
+    const int k0 = tid * per, k1 = min(pl.nkeys, k0 + per);
+    int pix = 0, items = 0;
+    for (int key = k0; key < k1; ++key) {
+        const int c = pl.cnt[key];
+        int ns = 0;
+        if (c > 0) {
+            const DbSlot& db = slots[key / kParts];
+            ns = (pl.mode == CLEDB_MODE_IQUV) ? pl.split : nonempty_parts(db) * pl.split;
+        }
+        pl.nsub[key] = ns;
+        pix += c;
+        items += ((c + pl.P - 1) / pl.P) * ns;
+    }
+    s_pix[tid] = pix;
+    s_item[tid] = items;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {        // Hillis-Steele inclusive scan
+        int a = 0, b = 0;
+        if (tid >= o) { a = s_pix[tid - o]; b = s_item[tid - o]; }
+        __syncthreads();
+        s_pix[tid] += a;
+        s_item[tid] += b;
+        __syncthreads();
+    }
+    int po = s_pix[tid] - pix, io = s_item[tid] - items;
+    for (int key = k0; key < k1; ++key) {
+        const int c = pl.cnt[key];
+        pl.off[key] = po;
+        pl.item0[key] = io;
+        po += c;
+        io += ((c + pl.P - 1) / pl.P) * pl.nsub[key];
+    }
+    if (tid == 1023) {
+        pl.item0[pl.nkeys] = s_item[1023];
+        pl.counters[2] = s_item[1023];
+    }
+}
+
+// kernel 3: scatter pixels into bucket order
+__global__ void __launch_bounds__(256) k_scatter(Plan pl) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pl.npix) return;
+    const int key = pl.key[p];
+    if (key < 0) { pl.rank[p] = -1; return; }
+    const int r = pl.off[key] + atomicAdd(&pl.cursor[key], 1);
+    pl.order[r] = (int32_t)p;
+    pl.rank[p] = r;
+}
+
+// item index -> descriptor (binary search over the per-bucket item offsets)
+__device__ __forceinline__ Item make_item(const Plan& pl, const DbSlot* slots, int it) {
+    int lo = 0, hi = pl.nkeys;                  // largest key with item0[key] <= it (and items in it)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pl.item0[mid] <= it) lo = mid; else hi = mid;
+    }
+    const int key = lo;
+    const int ns = pl.nsub[key];
+    const int local = it - pl.item0[key];
+    const int tile = local / ns, sub = local - tile * ns;
+    const DbSlot& db = slots[key / kParts];
+    int part = key % kParts, chunk = sub;
+    if (pl.mode == CLEDB_MODE_IQUD) {
+        int which = sub / pl.split;
+        chunk = sub - which * pl.split;
+        part = 0;
+        for (int q = 0; q < kParts; ++q) {
+            if (db.part_cnt[q] > 0) {
+                if (which == 0) { part = q; break; }
+                --which;
+            }
+        }
+    }
+    const int T = db.part_ntiles[part];
+    const int t0 = (int)(((int64_t)T * chunk) / pl.split), t1 = (int)(((int64_t)T * (chunk + 1)) / pl.split);
+    Item im;
+    im.slot = key / kParts;
+    im.tile0 = db.part_tile0[part] + t0;
+    im.ntiles = t1 - t0;
+    im.entry0 = db.part_tile0[part] * kTile;
+    im.pix0 = pl.off[key] + tile * pl.P;
+    im.npx = min(pl.P, pl.cnt[key] - tile * pl.P);
+    im.cnt_end = im.entry0 + db.part_cnt[part];
+    im.pad = 0;
+    return im;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// kernel 4: the search
+// ------------------------------------------------------------------------------------------------------
+template <int PREC> struct SmemLayout {
+    static constexpr int kRecBytes = (int)sizeof(Rec<PREC>) * kMaxP;
+    static constexpr int kListBytes = (int)sizeof(Cand<PREC>) * kMaxP * CLEDB_MAX_NSEARCH;
+};
+
+// evaluate the lane's 8 entries against the pixel record in shared memory; returns the 8 values
+template <int ENC, int PREC>
+__device__ __forceinline__ void eval_pixel(const Rec<PREC>* rec, const float (&d)[kEPL][kNC], const float (&scale)[kNC],
+                                           typename Val<PREC>::type (&v)[kEPL], typename Val<PREC>::type& tau) {
+    if (PREC == CLEDB_PREC_FP32) {
+        const float4* rp = reinterpret_cast<const float4*>(rec);
+        const float4 x0 = rp[0], x1 = rp[1], x2 = rp[2];          // three broadcast LDS.128
+        const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
+        const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
+#pragma unroll
+        for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
+        tau = x2.w;
+    } else {
+        const Rec<CLEDB_PREC_FP64>* r = reinterpret_cast<const Rec<CLEDB_PREC_FP64>*>(rec);
+        float st[kNC], sig[kNC];
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) { st[c] = r->st[c]; sig[c] = r->sig[c]; }
+        const double c0 = r->c0;
+#pragma unroll
+        for (int e = 0; e < kEPL; ++e) {
+            float dd[kNC];
+#pragma unroll
+            for (int c = 0; c < kNC; ++c) dd[c] = d[e][c] * scale[c];   // decoded database value (exact)
+            v[e] = eval_fp64(dd, st, sig, c0);
+        }
+        tau = *reinterpret_cast<const volatile double*>(&r->tau);
+    }
+}
+
+template <int ENC, int PREC>
+__global__ void __launch_bounds__(kThreads, PREC == CLEDB_PREC_FP32 ? 2 : 1)
+k_match(Plan pl, const DbSlot* __restrict__ slots) {
+    using V = typename Val<PREC>::type;
+    using CandT = Cand<PREC>;
+    using RecT = Rec<PREC>;
+    constexpr int TB = tile_bytes<ENC>();
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* stages = smem;                                        // [kWarps][kStages][TB]
+    unsigned char* boot = stages + kWarps * kStages * TB;                // [TB] first tile of the item, all warps
+    RecT* recs = reinterpret_cast<RecT*>(boot + TB);                     // [kMaxP]
+    CandT* lists = reinterpret_cast<CandT*>(recs + kMaxP);               // [kMaxP][k]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kMaxP * pl.k);  // [kWarps*kStages + 1]
+    int* locks = reinterpret_cast<int*>(bars + kWarps * kStages + 1);    // [kMaxP]
+    __shared__ Item s_item;
+    __shared__ int s_it;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = pl.k;
+    uint64_t* my_bars = bars + warp * kStages;
+    uint64_t* boot_bar = bars + kWarps * kStages;
+    unsigned char* my_stages = stages + warp * kStages * TB;
+    uint32_t boot_phase = 0;
+    uint32_t stage_phase[kStages];
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) stage_phase[s] = 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWarps * kStages + 1; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const int it = atomicAdd(&pl.counters[0], 1);
+            s_it = it;
+            if (it < pl.counters[2]) s_item = make_item(pl, slots, it);
+        }
+        __syncthreads();
+        const int it = s_it;
+        if (it >= pl.counters[2]) break;
+        const Item im = s_item;
+        const DbSlot& db = slots[im.slot];
+        const unsigned char* gt = reinterpret_cast<const unsigned char*>(db.tiles) + (size_t)im.tile0 * TB;
+        CandT* gout = reinterpret_cast<CandT*>(pl.plist) + (size_t)it * pl.P * k;
+
+        // ---- stage the item: pixel records, empty lists, first tile for the bootstrap, per-warp prefetch
+        if (threadIdx.x == 0 && im.ntiles > 0) {
+            mbar_expect_tx(boot_bar, TB);
+            tma_load_1d(boot, gt, TB, boot_bar);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kStages; ++s) {
+                const int t = 1 + warp + s * kWarps;
+                if (t < im.ntiles) {
+                    mbar_expect_tx(&my_bars[s], TB);
+                    tma_load_1d(my_stages + s * TB, gt + (size_t)t * TB, TB, &my_bars[s]);
+                }
+            }
+        }
+        for (int i = threadIdx.x; i < im.npx * (int)(sizeof(RecT) / 16); i += kThreads) {
+            const int j = i / (int)(sizeof(RecT) / 16), w = i % (int)(sizeof(RecT) / 16);
+            const int p = pl.order[im.pix0 + j];
+            reinterpret_cast<uint4*>(recs + j)[w] = reinterpret_cast<const uint4*>(reinterpret_cast<const RecT*>(pl.recs) + p)[w];
+        }
+        for (int i = threadIdx.x; i < im.npx * k; i += kThreads) {
+            lists[i].v = inf_of(V());
+            lists[i].pos = -1;
+        }
+        if (threadIdx.x < kMaxP) locks[threadIdx.x] = 0;
+        __syncthreads();
+
+        float scale[kNC];
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) scale[c] = db.scale[chi_comp(c)];
+
+        float d[kEPL][kNC];
+        if (im.ntiles > 0) {
+            // ---- bootstrap: warp w ranks the first tile for pixels w, w+8, ...: k rounds of warp-min selection
+            mbar_wait(boot_bar, boot_phase);
+            boot_phase ^= 1;
+            load_tile_regs<ENC>(boot, lane, d);
+            const int base = im.tile0 * kTile;
+            for (int j = warp; j < im.npx; j += kWarps) {
+                V v[kEPL], tau_unused;
+                eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau_unused);
+                int ps[kEPL];
+#pragma unroll
+                for (int e = 0; e < kEPL; ++e) {
+                    const int pos = base + pos_in_tile<ENC>(lane, e);
+                    const bool ok = !isnan(v[e]) && pos < im.cnt_end;    // padding decodes to NaN
+                    ps[e] = ok ? pos : 0x7fffffff;
+                    if (!ok) v[e] = inf_of(V());
+                }
+                uint32_t used = 0;
+                V keep_v = inf_of(V());
+                int keep_p = -1;
+                for (int r = 0; r < k; ++r) {
+                    V lm = inf_of(V());
+                    int lp = 0x7fffffff;
+#pragma unroll
+                    for (int e = 0; e < kEPL; ++e) {
+                        const bool free_e = !((used >> e) & 1u);
+                        if (free_e && (v[e] < lm || (v[e] == lm && ps[e] < lp))) { lm = v[e]; lp = ps[e]; }
+                    }
+                    const V gm = warp_min(lm);
+                    const int gp = (int)__reduce_min_sync(0xffffffffu, (uint32_t)((lm == gm) ? lp : 0x7fffffff));
+                    if (gp != 0x7fffffff) {
+#pragma unroll
+                        for (int e = 0; e < kEPL; ++e)
+                            if (ps[e] == gp) used |= 1u << e;
+                    }
+                    if (lane == r) { keep_v = gm; keep_p = (gp == 0x7fffffff) ? -1 : gp; }
+                }
+                if (lane < k) {
+                    lists[j * k + lane].v = keep_v;
+                    lists[j * k + lane].pos = keep_p;
+                }
+                if (lane == k - 1) *const_cast<V*>(&recs[j].tau) = keep_v;
+            }
+        }
+        __syncthreads();
+
+        // ---- main loop: this warp's tiles 1+warp, 1+warp+8, ...
+        int iter = 0;
+        for (int t = 1 + warp; t < im.ntiles; t += kWarps, ++iter) {
+            const int s = iter % kStages;
+            mbar_wait(&my_bars[s], stage_phase[s]);
+            stage_phase[s] ^= 1;
+            load_tile_regs<ENC>(my_stages + s * TB, lane, d);
+            __syncwarp();                         // every lane has its registers: the stage can be refilled
+            if (lane == 0) {
+                const int tn = t + kStages * kWarps;
+                if (tn < im.ntiles) {
+                    mbar_expect_tx(&my_bars[s], TB);
+                    tma_load_1d(my_stages + s * TB, gt + (size_t)tn * TB, TB, &my_bars[s]);
+                }
+            }
+            const int base = (im.tile0 + t) * kTile;
+#pragma unroll 2
+            for (int j = 0; j < im.npx; ++j) {
+                V v[kEPL], tau;
+                eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau);
+                V m = fmin(fmin(fmin(v[0], v[1]), fmin(v[2], v[3])), fmin(fmin(v[4], v[5]), fmin(v[6], v[7])));
+                if (__any_sync(0xffffffffu, m <= tau)) {
+                    // rare path: some entry may enter the list of pixel j
+#pragma unroll
+                    for (int e = 0; e < kEPL; ++e) {
+                        const int pos = base + pos_in_tile<ENC>(lane, e);
+                        const V tnow = *reinterpret_cast<volatile V*>(&recs[j].tau);
+                        uint32_t hits = __ballot_sync(0xffffffffu, v[e] <= tnow && pos < im.cnt_end);
+                        while (hits) {
+                            const int src = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            const V cv = __shfl_sync(0xffffffffu, v[e], src);
+                            const int cp = __shfl_sync(0xffffffffu, pos, src);
+                            list_insert<PREC>(lists + j * k, &locks[j], reinterpret_cast<volatile V*>(&recs[j].tau), k, cv, cp, lane);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- write the item's partial lists
+        for (int i = threadIdx.x; i < im.npx * k; i += kThreads) gout[i] = lists[i];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// kernel 5: merge the partial lists of a pixel, map positions to original rows, decode winner rows
+// ------------------------------------------------------------------------------------------------------
+template <int ENC> __device__ __forceinline__ float decode_chi_comp(const DbSlot& db, int pos, int c) {
+    const int tile = pos / kTile, in = pos - tile * kTile;
+    const size_t e = ((size_t)tile * kNC + c) * kTile + in;
+    const float sc = db.scale[chi_comp(c)];
+    if (ENC == CLEDB_ENC_I16) return __half2float(__ushort_as_half(reinterpret_cast<const unsigned short*>(db.tiles)[e])) * sc;
+    return reinterpret_cast<const float*>(db.tiles)[e];
+}
+template <int ENC> __device__ __forceinline__ float decode_v(const DbSlot& db, int pos, int which) {
+    const size_t e = (size_t)pos * 2 + which;
+    if (ENC == CLEDB_ENC_I16)
+        return __half2float(__ushort_as_half(reinterpret_cast<const unsigned short*>(db.vcomp)[e])) * db.scale[which ? 7 : 3];
+    return reinterpret_cast<const float*>(db.vcomp)[e];
+}
+__device__ __forceinline__ void decode_row(const DbSlot& db, int pos, float* row) {
+    row[0] = 1.0f;
+    if (db.encoding == CLEDB_ENC_I16) {
+        row[1] = decode_chi_comp<CLEDB_ENC_I16>(db, pos, 0); row[2] = decode_chi_comp<CLEDB_ENC_I16>(db, pos, 1);
+        row[3] = decode_v<CLEDB_ENC_I16>(db, pos, 0);        row[4] = decode_chi_comp<CLEDB_ENC_I16>(db, pos, 2);
+        row[5] = decode_chi_comp<CLEDB_ENC_I16>(db, pos, 3); row[6] = decode_chi_comp<CLEDB_ENC_I16>(db, pos, 4);
+        row[7] = decode_v<CLEDB_ENC_I16>(db, pos, 1);
+    } else {
+        row[1] = decode_chi_comp<CLEDB_ENC_F32>(db, pos, 0); row[2] = decode_chi_comp<CLEDB_ENC_F32>(db, pos, 1);
+        row[3] = decode_v<CLEDB_ENC_F32>(db, pos, 0);        row[4] = decode_chi_comp<CLEDB_ENC_F32>(db, pos, 2);
+        row[5] = decode_chi_comp<CLEDB_ENC_F32>(db, pos, 3); row[6] = decode_chi_comp<CLEDB_ENC_F32>(db, pos, 4);
+        row[7] = decode_v<CLEDB_ENC_F32>(db, pos, 1);
+    }
+}
+
+constexpr int kMaxSub = 24;   // 3 sign partitions x up to 8 chunks
+
+template <int PREC>
+__global__ void __launch_bounds__(128) k_finalize(Plan pl, const DbSlot* __restrict__ slots, int32_t* __restrict__ idx_out,
+                                                   float* __restrict__ chi_out, double* __restrict__ chi64_out,
+                                                   int32_t* __restrict__ kpos_out, float* __restrict__ rows_out,
+                                                   int64_t* __restrict__ ncand_out) {
+    using V = typename Val<PREC>::type;
+    using CandT = Cand<PREC>;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pl.npix) return;
+    const int k = pl.k;
+    const int key = pl.key[p];
+    if (key < 0) {
+        for (int r = 0; r < k; ++r) {
+            idx_out[p * k + r] = -1;
+            chi_out[p * k + r] = 0.f;
+            if (chi64_out) chi64_out[p * k + r] = 0.0;
+            if (kpos_out) kpos_out[p * k + r] = -1;
+            if (rows_out) for (int c = 0; c < 8; ++c) rows_out[(p * k + r) * 8 + c] = 0.f;
+        }
+        if (ncand_out) ncand_out[p] = 0;
+        return;
+    }
+    const DbSlot& db = slots[key / kParts];
+    const int local = pl.rank[p] - pl.off[key];
+    const int tile = local / pl.P, j = local - tile * pl.P;
+    const int ns = pl.nsub[key];
+    const CandT* base = reinterpret_cast<const CandT*>(pl.plist) + ((size_t)(pl.item0[key] + tile * ns) * pl.P + j) * k;
+    const size_t sub_stride = (size_t)pl.P * k;
+    unsigned char head[kMaxSub];
+    for (int s = 0; s < ns; ++s) head[s] = 0;
+    const int cls = key % kParts;
+    for (int r = 0; r < k; ++r) {
+        int best = -1, bpos = -1, bidx = 0x7fffffff;
+        V bv = inf_of(V());
+        for (int s = 0; s < ns; ++s) {
+            if (head[s] >= k) continue;
+            const CandT c = base[s * sub_stride + head[s]];
+            if (c.pos < 0) { head[s] = (unsigned char)k; continue; }
+            const int oi = db.perm[c.pos];
+            if (best < 0 || c.v < bv || (c.v == bv && oi < bidx)) { best = s; bv = c.v; bpos = c.pos; bidx = oi; }
+        }
+        const int64_t o = p * k + r;
+        if (best < 0) {
+            idx_out[o] = -1;
+            chi_out[o] = 0.f;
+            if (chi64_out) chi64_out[o] = 0.0;
+            if (kpos_out) kpos_out[o] = -1;
+            if (rows_out) for (int c = 0; c < 8; ++c) rows_out[o * 8 + c] = 0.f;
+            continue;
+        }
+        head[best]++;
+        idx_out[o] = bidx;
+        const double chi = (PREC == CLEDB_PREC_FP32) ? (double)(0.5f * (float)bv) : (double)bv;
+        chi_out[o] = (float)chi;
+        if (chi64_out) chi64_out[o] = chi;
+        if (kpos_out) {
+            if (pl.mode == CLEDB_MODE_IQUV) kpos_out[o] = bpos - db.part_tile0[cls] * kTile;
+            else kpos_out[o] = db.kept_rank ? db.kept_rank[bidx] : bidx;
+        }
+        if (rows_out) {
+            float row[8];
+            decode_row(db, bpos, row);
+            for (int c = 0; c < 8; ++c) rows_out[o * 8 + c] = row[c];
+        }
+    }
+    if (ncand_out)
+        ncand_out[p] = (pl.mode == CLEDB_MODE_IQUV) ? db.part_cnt[cls] : (int64_t)db.part_cnt[0] + db.part_cnt[1] + db.part_cnt[2];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+template <int ENC, int PREC> static size_t match_smem_bytes(int k) {
+    return (size_t)kWarps * kStages * tile_bytes<ENC>() + tile_bytes<ENC>() + sizeof(Rec<PREC>) * kMaxP +
+           sizeof(Cand<PREC>) * kMaxP * k + sizeof(uint64_t) * (kWarps * kStages + 1) + sizeof(int) * kMaxP + 16;
+}
+
+template <int ENC, int PREC> static int configure_match(cledb_ctx* ctx, int k, int* occ_out, size_t* smem_out) {
+    const size_t smem = match_smem_bytes<ENC, PREC>(k);
+    CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_match<ENC, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CLEDB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_match<ENC, PREC>, kThreads, smem));
+    if (occ < 1) { ctx->err = "search kernel does not fit on an SM"; return CLEDB_ERR_CUDA; }
+    *occ_out = occ;
+    *smem_out = smem;
+    return CLEDB_OK;
+}
+
+int match_occupancy(cledb_ctx* ctx) {
+    int occ = 0;
+    size_t smem = 0;
+    int rc = configure_match<CLEDB_ENC_I16, CLEDB_PREC_FP32>(ctx, 8, &occ, &smem);
+    if (rc) return rc;
+    cudaFuncAttributes fa;
+    CLEDB_CUDA(ctx, cudaFuncGetAttributes(&fa, k_match<CLEDB_ENC_I16, CLEDB_PREC_FP32>));
+    ctx->occ = occ;
+    ctx->regs = fa.numRegs;
+    ctx->smem = (int)smem;
+    return CLEDB_OK;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <int PREC>
+static int run_match(cledb_ctx* ctx, int enc, Plan& pl, const float* sobs, const float* snr, const int32_t* db_id,
+                     int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out, float* rows_out,
+                     int64_t* ncand_out, cudaStream_t st) {
+    const int64_t npix = pl.npix;
+    const int nb = (int)((npix + 255) / 256);
+    k_classify<PREC><<<nb, 256, 0, st>>>(pl, sobs, snr, db_id, ctx->d_slots, ctx->d_slot_of_id, ctx->id_cap);
+    k_scan<<<1, 1024, 0, st>>>(pl, ctx->d_slots);
+    k_scatter<<<nb, 256, 0, st>>>(pl);
+    ctx->launches += 3;
+    int occ = 0;
+    size_t smem = 0;
+    int rc;
+    if (enc == CLEDB_ENC_I16) rc = configure_match<CLEDB_ENC_I16, PREC>(ctx, pl.k, &occ, &smem);
+    else rc = configure_match<CLEDB_ENC_F32, PREC>(ctx, pl.k, &occ, &smem);
+    if (rc) return rc;
+    const int64_t max_items = ((npix + pl.P - 1) / pl.P + pl.nkeys) * (int64_t)kParts * pl.split;
+    const int grid = (int)std::min<int64_t>((int64_t)ctx->prop.multiProcessorCount * occ, std::max<int64_t>(1, max_items));
+    const bool prof = ctx->prof_on && ctx->prof_used < (int)ctx->prof.size();
+    if (prof) CLEDB_CUDA(ctx, cudaEventRecord(ctx->prof[ctx->prof_used].first, st));
+    if (enc == CLEDB_ENC_I16) k_match<CLEDB_ENC_I16, PREC><<<grid, kThreads, smem, st>>>(pl, ctx->d_slots);
+    else k_match<CLEDB_ENC_F32, PREC><<<grid, kThreads, smem, st>>>(pl, ctx->d_slots);
+    if (prof) {
+        CLEDB_CUDA(ctx, cudaEventRecord(ctx->prof[ctx->prof_used].second, st));
+        ctx->prof_used++;
+    }
+    k_finalize<PREC><<<(int)((npix + 127) / 128), 128, 0, st>>>(pl, ctx->d_slots, idx_out, chi_out, chi64_out, kpos_out,
+                                                               rows_out, ncand_out);
+    ctx->launches += 2;
+    CLEDB_CUDA(ctx, cudaGetLastError());
+    return CLEDB_OK;
+}
+
+int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const float* sobs, const float* snr,
+                 const int32_t* db_id, int nsearch, int32_t* idx_out, float* chi_out, double* chi64_out,
+                 int32_t* kpos_out, float* rows_out, uint8_t* status_out, int64_t* ncand_out, cudaStream_t st) {
+    if (npix < 0 || !sobs || !snr || !db_id || !idx_out || !chi_out) { ctx->err = "cledb_match: null argument"; return CLEDB_ERR_ARG; }
+    if (nsearch < 1 || nsearch > CLEDB_MAX_NSEARCH) { ctx->err = "cledb_match: nsearch must be in 1..32"; return CLEDB_ERR_ARG; }
+    if (mode != CLEDB_MODE_IQUV && mode != CLEDB_MODE_IQUD) { ctx->err = "cledb_match: unknown mode"; return CLEDB_ERR_ARG; }
+    if (precision != CLEDB_PREC_FP32 && precision != CLEDB_PREC_FP64) { ctx->err = "cledb_match: unknown precision"; return CLEDB_ERR_ARG; }
+    if (npix == 0) return CLEDB_OK;
+    if (npix > (int64_t)1 << 30) { ctx->err = "cledb_match: more than 2^30 pixels in one call"; return CLEDB_ERR_ARG; }
+    int enc = -1;
+    for (auto& h : ctx->dbs) {
+        if (!h.slot.live) continue;
+        if (enc < 0) enc = h.slot.encoding;
+        else if (enc != h.slot.encoding) { ctx->err = "cledb_match: resident databases mix encodings"; return CLEDB_ERR_ARG; }
+    }
+    if (enc < 0) { ctx->err = "cledb_match: no database resident"; return CLEDB_ERR_NODB; }
+    int rc = sync_tables(ctx, st);
+    if (rc) return rc;
+    if (ctx->occ == 0 && (rc = match_occupancy(ctx))) return rc;
+
+    Plan pl;
+    std::memset(&pl, 0, sizeof(pl));
+    pl.npix = npix;
+    pl.mode = mode;
+    pl.k = nsearch;
+    pl.P = std::max(1, std::min(ctx->pixels_per_item, kMaxP));
+    pl.nkeys = ctx->slots_cap * kParts;
+    int split = ctx->split;
+    if (split <= 0) {   // few pixels: cut the candidate lists so that the machine is still filled
+        const int64_t tiles = (npix + pl.P - 1) / pl.P;
+        const int64_t want = 2ll * ctx->prop.multiProcessorCount * std::max(1, ctx->occ);
+        split = (int)std::min<int64_t>(8, std::max<int64_t>(1, want / std::max<int64_t>(1, tiles)));
+    }
+    pl.split = std::min(split, 8);
+    const size_t rec_sz = precision == CLEDB_PREC_FP32 ? sizeof(Rec<CLEDB_PREC_FP32>) : sizeof(Rec<CLEDB_PREC_FP64>);
+    const size_t cand_sz = precision == CLEDB_PREC_FP32 ? sizeof(Cand<CLEDB_PREC_FP32>) : sizeof(Cand<CLEDB_PREC_FP64>);
+    const int64_t max_items = ((npix + pl.P - 1) / pl.P + pl.nkeys) * (int64_t)kParts * pl.split;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_key = take(npix * 4), o_rank = take(npix * 4), o_order = take(npix * 4);
+    const size_t o_small = take((size_t)(5 * pl.nkeys + 1 + 4) * 4);
+    const size_t o_recs = take(npix * rec_sz), o_status = take(npix);
+    const size_t o_plist = take((size_t)max_items * pl.P * pl.k * cand_sz);
+    if ((rc = ensure_workspace(ctx, ctx->ws, off))) return rc;
+    unsigned char* w = reinterpret_cast<unsigned char*>(ctx->ws.ptr);
+    pl.key = reinterpret_cast<int32_t*>(w + o_key);
+    pl.rank = reinterpret_cast<int32_t*>(w + o_rank);
+    pl.order = reinterpret_cast<int32_t*>(w + o_order);
+    int32_t* small = reinterpret_cast<int32_t*>(w + o_small);
+    pl.cnt = small;
+    pl.cursor = small + pl.nkeys;
+    pl.off = small + 2 * pl.nkeys;
+    pl.nsub = small + 3 * pl.nkeys;
+    pl.item0 = small + 4 * pl.nkeys;                 // nkeys + 1 entries
+    pl.counters = small + 5 * pl.nkeys + 1;
+    pl.recs = w + o_recs;
+    pl.status = status_out ? status_out : (w + o_status);
+    pl.plist = w + o_plist;
+    CLEDB_CUDA(ctx, cudaMemsetAsync(small, 0, (size_t)(5 * pl.nkeys + 1 + 4) * 4, st));
+    if (precision == CLEDB_PREC_FP32)
+        rc = run_match<CLEDB_PREC_FP32>(ctx, enc, pl, sobs, snr, db_id, idx_out, chi_out, chi64_out, kpos_out, rows_out, ncand_out, st);
+    else
+        rc = run_match<CLEDB_PREC_FP64>(ctx, enc, pl, sobs, snr, db_id, idx_out, chi_out, chi64_out, kpos_out, rows_out, ncand_out, st);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// small database kernels: decoded read-back and row gather
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_decode_db(const DbSlot* slots, int slot, const int32_t* invperm, float* out) {
+    const DbSlot& db = slots[slot];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= db.n) return;
+    const int pos = invperm[i];
+    float row[8] = {1.f, 0.f, 0.f, CUDART_NAN_F, 0.f, 0.f, 0.f, 0.f};
+    if (pos >= 0) decode_row(db, pos, row);
+    for (int c = 0; c < 8; ++c) out[i * 8 + c] = row[c];
+}
+__global__ void k_gather_rows(const DbSlot* slots, int slot, const int32_t* invperm, const int32_t* idx, int64_t n, float* rows) {
+    const DbSlot& db = slots[slot];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ix = idx[i];
+    float row[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ix >= 0 && ix < db.n) {
+        const int pos = invperm[ix];
+        if (pos >= 0) decode_row(db, pos, row);
+        else { row[0] = 1.f; row[3] = CUDART_NAN_F; }
+    }
+    for (int c = 0; c < 8; ++c) rows[i * 8 + c] = row[c];
+}
+int launch_decode_db(cledb_ctx* ctx, int slot, float* d_out, cudaStream_t st) {
+    const int64_t n = ctx->dbs[slot].slot.n;
+    k_decode_db<<<(int)((n + 255) / 256), 256, 0, st>>>(ctx->d_slots, slot, ctx->dbs[slot].d_invperm, d_out);
+    ctx->launches++;
+    CLEDB_CUDA(ctx, cudaGetLastError());
+    return CLEDB_OK;
+}
+int launch_gather_rows(cledb_ctx* ctx, int slot, const int32_t* d_idx, int64_t n, float* d_rows, cudaStream_t st) {
+    if (n == 0) return CLEDB_OK;
+    k_gather_rows<<<(int)((n + 255) / 256), 256, 0, st>>>(ctx->d_slots, slot, ctx->dbs[slot].d_invperm, d_idx, n, d_rows);
+    ctx->launches++;
+    CLEDB_CUDA(ctx, cudaGetLastError());
+    return CLEDB_OK;
+}
+
+}  // namespace cledb

@@ -1,0 +1,348 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI of
+libcledb_b200.so, either directly (cledb_b200.native) or through the reference-shaped Python surface
+(CLEDB_PROC / CLEDB_PREPINV), and is compared with the CPU oracle / the golden outputs of the unmodified reference.
+
+Tolerances (north_star: "bit-exact top-nsearch indices except chi^2 near-ties within 1e-5 relative"):
+  fp64 validation kernel : indices, chi^2 (float64) and every derived column bit-exact against the reference
+  fp32 production kernel : chi^2 within rtol 2e-5 (+1e-9 abs); an index may differ from the oracle only where the
+                           oracle's own chi^2 of the two candidates agree within that tolerance (near-tie)
+  B, Bx, By, Bz, sfound  : rtol 1e-6 given equal index; ne, y, gx, phi, theta bit-equal given equal index
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle.cledb_oracle as orc
+import cledb_b200.synth as synth
+from cledb_b200 import native, codec
+from helpers import hdr_from_g, same
+
+pytestmark = pytest.mark.gpu
+
+CHI_RTOL, CHI_ATOL = 2e-5, 1e-9
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    c = native.Context(0)
+    yield c
+    c.close()
+
+
+def check_raw_against_oracle(raw, mode, sobs, snr, dbs_decoded, enc, k, exact=False):
+    """Compare cledb_match output with the oracle pixel by pixel.  Returns (#pixels searched, #pixels whose index
+    list differs from the oracle's by a near-tie reordering)."""
+    npix = sobs.shape[0]
+    searched = reordered = 0
+    for p in range(npix):
+        db = dbs_decoded[int(enc[p])]
+        ref = orc.raw_topk(mode, sobs[p], snr[p], db, k, return_all=True)
+        if ref is None:
+            assert raw['status'][p] == native.PIX_NULL, p
+            assert (raw['idx'][p] == -1).all()
+            continue
+        ridx, rchi, rpos, ncand, allchi = ref
+        if ncand == 0:
+            assert raw['status'][p] == native.PIX_REFRAISES, p
+            continue
+        if np.isnan(allchi).any():
+            assert raw['status'][p] == native.PIX_ALLNAN, (p, raw['status'][p])
+            continue
+        if np.isinf(rchi).all():
+            assert raw['status'][p] == native.PIX_ALLINF, (p, raw['status'][p])
+            continue
+        assert raw['status'][p] == native.PIX_SEARCHED, (p, raw['status'][p])
+        assert raw['ncand'][p] == ncand
+        searched += 1
+        n = min(k, ncand)
+        gidx, gchi = raw['idx'][p], raw['chi'][p]
+        assert (gidx[n:] == -1).all()
+        if exact:
+            assert np.array_equal(gidx[:n], ridx[:n]), (p, gidx, ridx)
+            assert np.array_equal(raw['chi64'][p][:n], rchi[:n]), (p, raw['chi64'][p], rchi)
+            assert np.array_equal(raw['kpos'][p][:n], rpos[:n])
+        else:
+            np.testing.assert_allclose(gchi[:n], rchi[:n], rtol=CHI_RTOL, atol=CHI_ATOL, err_msg='pixel %d' % p)
+            if not np.array_equal(gidx[:n], ridx[:n]):
+                reordered += 1
+                # every index the GPU reports must be a genuine near-tie member: its ORACLE chi^2 matches the slot
+                keep = np.flatnonzero(np.sign(db[:, 3]) == np.sign(sobs[p, 3])) if mode == 0 else np.flatnonzero(db[:, 3] == db[:, 3])
+                lookup = dict(zip(keep.tolist(), allchi.tolist()))
+                for r in range(n):
+                    assert gidx[r] in lookup, (p, r, gidx[r])
+                    np.testing.assert_allclose(lookup[int(gidx[r])], rchi[r], rtol=CHI_RTOL, atol=CHI_ATOL)
+                assert len(set(gidx[:n].tolist())) == n
+        # decoded rows returned by the kernel are the database rows of the reported indices
+        assert np.array_equal(raw['rows'][p][:n], db[gidx[:n]], equal_nan=True)
+    return searched, reordered
+
+
+def small_case(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'small_maps.npz'))
+    return g, [g['db0'], g['db1'], g['db2']]
+
+
+@pytest.mark.parametrize('encoding', [native.ENC_F32, native.ENC_I16])
+def test_db_roundtrip(ctx, golden_dir, encoding):
+    """What the kernels see == the NumPy codec mirror; partition counts; gather_rows."""
+    g, dbs = small_case(golden_dir)
+    db = dbs[2].reshape(-1, 8).copy()
+    db[7, 3] = np.nan                     # a row that can never be a candidate
+    db[11, 3] = 0.0                       # a zero-V row (third sign class)
+    ctx.db_put(5, db, encoding)
+    info = ctx.db_info(5)
+    assert info['n'] == db.shape[0] and info['nnan'] == 1 and info['nzero'] == 1
+    assert info['npos'] == int((db[:, 3] > 0).sum()) and info['nneg'] == int((db[:, 3] < 0).sum())
+    dec = codec.decoded_database(db, encoding)
+    assert np.array_equal(ctx.db_decoded(5), dec, equal_nan=True)
+    if encoding == native.ENC_F32:
+        keep = ~np.isnan(db[:, 3])
+        assert np.array_equal(dec[keep], db[keep])
+    else:
+        keep = ~np.isnan(db[:, 3])
+        rel = np.abs(dec[keep] - db[keep]) / np.maximum(np.abs(db[keep]), 1e-30)
+        big = np.abs(db[keep]) > np.abs(db[keep]).max(axis=0) * 1e-6
+        assert rel[big].max() < 2.0 ** -11 * 1.0001        # half-precision significand
+    idx = np.array([0, 7, 11, 1500, -1, db.shape[0] - 1], np.int32)
+    rows = ctx.gather_rows(5, idx)
+    assert np.array_equal(rows[[0, 2, 3, 5]], dec[[0, 11, 1500, db.shape[0] - 1]])
+    assert (rows[4] == 0).all() and np.isnan(rows[1, 3])
+    ctx.db_drop(5)
+    with pytest.raises(native.CledbError):
+        ctx.db_info(5)
+    bad = db.copy()
+    bad[3, 0] = 0.5
+    with pytest.raises(native.CledbError):
+        ctx.db_put(6, bad, encoding)          # component 0 must be exactly 1
+
+
+@pytest.mark.parametrize('encoding', [native.ENC_F32, native.ENC_I16])
+@pytest.mark.parametrize('mode', [native.MODE_IQUV, native.MODE_IQUD])
+@pytest.mark.parametrize('k', [8, 1, 16, 32])
+def test_raw_search_small(ctx, golden_dir, encoding, mode, k):
+    """120 pixels with engineered edge cases over three small databases (3 240 entries each)."""
+    g, dbs = small_case(golden_dir)
+    for i, db in enumerate(dbs):
+        ctx.db_put(i, db, encoding)
+    dec = [codec.decoded_database(db, encoding) for db in dbs]
+    tag = 'iquv_b0' if mode == 0 else 'iqud'
+    sobs = g['sobs_' + tag].reshape(-1, 8).copy()
+    snr = g['snr'].reshape(-1, 8)
+    enc = g['db_enc'].reshape(-1)
+    if mode == 0:
+        sobs[13] = g['sobs_iqud'].reshape(-1, 8)[13]      # the V == 0 pixel the reference cannot survive (status 3)
+    raw = ctx.match(mode, sobs, snr, enc, k, want_chi64=True)
+    searched, reordered = check_raw_against_oracle(raw, mode, sobs, snr, dec, enc, k)
+    assert searched > 90 and reordered <= 3
+    raw64 = ctx.match(mode, sobs, snr, enc, k, precision=native.PREC_FP64, want_chi64=True)
+    check_raw_against_oracle(raw64, mode, sobs, snr, dec, enc, k, exact=True)
+    for i in range(3):
+        ctx.db_drop(i)
+
+
+@pytest.mark.parametrize('split,ppi', [(1, 32), (3, 32), (8, 7), (2, 1)])
+def test_tuning_does_not_change_results(ctx, golden_dir, split, ppi):
+    g, dbs = small_case(golden_dir)
+    for i, db in enumerate(dbs):
+        ctx.db_put(i, db, native.ENC_I16)
+    sobs, snr, enc = g['sobs_iqud'].reshape(-1, 8), g['snr'].reshape(-1, 8), g['db_enc'].reshape(-1)
+    ctx.set_tuning(32, 1)
+    base = ctx.match(native.MODE_IQUD, sobs, snr, enc, 8)
+    ctx.set_tuning(ppi, split)
+    other = ctx.match(native.MODE_IQUD, sobs, snr, enc, 8)
+    ctx.set_tuning(32, 0)
+    for key in ('idx', 'chi', 'kpos', 'status', 'rows'):
+        assert np.array_equal(base[key], other[key], equal_nan=True), key
+    for i in range(3):
+        ctx.db_drop(i)
+
+
+def run_surface(tag_cfg, g, dbs, hdr, nx, ny, precision, encoding, sobs_key):
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    iqud, bcalc, nsearch, maxchisq = tag_cfg
+    procinv.OPTIONS.update(precision=precision, dbencoding=encoding, strict_topk=False)
+    kv = synth.make_keyvals(nx, ny, cdelt=float(g['cdelt']))
+    iss = np.zeros((nx, ny, 2), np.int32)
+    inv, sf = procinv.cledb_invproc(g[sobs_key], g['sobs_dopp'], dbs, g['db_enc'] if 'db_enc' in g else np.zeros((nx, ny), np.int32),
+                                    g['yobs'], g['aobs'], g['dobs'], g['snr'], iss, hdr, kv, int(nsearch), maxchisq, int(bcalc),
+                                    bool(iqud), 4, False, 0)
+    return inv, sf, iss
+
+
+TAGS = ['iquv_b0', 'iquv_b1', 'iquv_b2_k4', 'iquv_b0_chi3', 'iquv_b0_k16', 'iqud', 'iqud_chi3', 'iqud_badbcalc']
+
+
+@pytest.mark.parametrize('tag', TAGS)
+def test_invproc_golden_fp64(golden_dir, tag):
+    """cledb_invproc through the validation kernel on the lossless database == the unmodified reference,
+    bit-for-bit in indices (including partsort-quirk duplicates), chi^2, geometry and issuemask."""
+    g, dbs = small_case(golden_dir)
+    hdr = hdr_from_g(g['hdr_g'])
+    inv, sf, iss = run_surface(g['cfg_' + tag], g, dbs, hdr, 10, 12, native.PREC_FP64, native.ENC_F32, 'sobs_' + tag)
+    ref_inv, ref_sf = g['invout_' + tag], g['sfound_' + tag]
+    assert np.array_equal(inv[..., 0], ref_inv[..., 0])
+    assert np.array_equal(inv[..., 1], ref_inv[..., 1])
+    assert np.array_equal(inv[..., [2, 3, 4, 6, 7]], ref_inv[..., [2, 3, 4, 6, 7]])
+    np.testing.assert_allclose(inv[..., [5, 8, 9, 10]], ref_inv[..., [5, 8, 9, 10]], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(sf, ref_sf, rtol=1e-6, atol=0)
+    assert same(iss, g['issuemask_' + tag])
+
+
+@pytest.mark.parametrize('tag', ['iquv_b0', 'iquv_b2_k4', 'iqud'])
+def test_invproc_golden_fp32(golden_dir, tag):
+    """Same through the production fp32 kernel: indices equal except near-ties, chi^2 within tolerance."""
+    g, dbs = small_case(golden_dir)
+    hdr = hdr_from_g(g['hdr_g'])
+    inv, sf, iss = run_surface(g['cfg_' + tag], g, dbs, hdr, 10, 12, native.PREC_FP32, native.ENC_F32, 'sobs_' + tag)
+    ref_inv, ref_sf = g['invout_' + tag], g['sfound_' + tag]
+    same_idx = inv[..., 0] == ref_inv[..., 0]
+    assert same_idx.mean() > 0.98
+    np.testing.assert_allclose(inv[..., 1], ref_inv[..., 1], rtol=CHI_RTOL, atol=CHI_ATOL)
+    m = same_idx
+    assert np.array_equal(inv[m][:, [2, 3, 4, 6, 7]], ref_inv[m][:, [2, 3, 4, 6, 7]])
+    np.testing.assert_allclose(inv[m][:, [5, 8, 9, 10]], ref_inv[m][:, [5, 8, 9, 10]], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(sf[m], ref_sf[m], rtol=1e-6, atol=0)
+    assert (iss == g['issuemask_' + tag]).mean() > 0.98
+
+
+def test_full_db_golden(golden_dir):
+    """36 pixels against the full-size 340 200-entry database: validation kernel bit-exact, fp32 kernel in tolerance."""
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    g = np.load(os.path.join(golden_dir, 'full_db_pixels.npz'))
+    db = synth.make_database(*[int(v) for v in g['db_hd']])
+    import hashlib
+    if hashlib.sha256(db.tobytes()).hexdigest() != str(g['db_sha']):
+        pytest.skip('synthetic database generator is not bit-reproducible on this CPU')
+    hdr = hdr_from_g(g['hdr_g'])
+    kv = synth.make_keyvals(6, 6, cdelt=float(g['cdelt']))
+    for tag, iqud, bcalc in (('iquv', False, 0), ('iqud', True, 3)):
+        for prec in (native.PREC_FP64, native.PREC_FP32):
+            procinv.OPTIONS.update(precision=prec, dbencoding=native.ENC_F32)
+            iss = np.zeros((6, 6, 2), np.int32)
+            inv, sf = procinv.cledb_invproc(g['sobs'], g['sobs_dopp'], [db], np.zeros((6, 6), np.int32), g['yobs'], g['aobs'],
+                                            g['dobs'], g['snr'], iss, hdr, kv, 8, 1000, bcalc, iqud, 4, False, 0)
+            ref = g['invout_' + tag]
+            if prec == native.PREC_FP64:
+                assert np.array_equal(inv[..., :5], ref[..., :5]) and np.array_equal(inv[..., 6:8], ref[..., 6:8])
+                assert same(iss, g['issuemask_' + tag])
+                np.testing.assert_allclose(sf, g['sfound_' + tag], rtol=1e-6, atol=0)
+            else:
+                assert (inv[..., 0] == ref[..., 0]).mean() > 0.97
+                np.testing.assert_allclose(inv[..., 1], ref[..., 1], rtol=CHI_RTOL, atol=CHI_ATOL)
+    procinv.OPTIONS.update(precision=0, dbencoding=0)
+    procinv.release_databases()
+
+
+def test_single_pixel_surface(golden_dir):
+    """cledb_matchiquv / cledb_matchiqud on the reference's unit-test pixel (tests/test_functions.py:124-140)."""
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    g = np.load(os.path.join(golden_dir, 'unit_pixel.npz'))
+    rng = np.random.default_rng(99)
+    pairs = {}
+    for hi, name in ((5, 'DB_h106_d895.npy'), (8, 'DB_h109_d795.npy'), (8, 'DB_h109_d895.npy')):
+        pairs[name] = synth.make_raw_line_pair(hi, 59 if 'd895' in name else 39, rng)
+    db = orc.normalise_database(*pairs[str(g['db_file'])], np.float32(g['wl0']))
+    hdr = hdr_from_g(g['hdr_g'])
+    procinv.OPTIONS.update(precision=native.PREC_FP64, dbencoding=native.ENC_F32)
+    xx, yy, out, sm = procinv.cledb_matchiquv(0, 0, g['sobs_totrot'][0, 0], g['yobs'][0, 0], g['aobs'][0, 0], g['dobs'][0, 0], db, hdr,
+                                              g['snr'][0, 0], 8, 1000, 0, False, 0)
+    assert np.array_equal(out[:, :5], g['invout_iquv'][0, 0][:, :5])
+    np.testing.assert_allclose(out, g['invout_iquv'][0, 0], rtol=1e-6)
+    np.testing.assert_allclose(sm, g['sfound_iquv'][0, 0], rtol=1e-6)
+    xx, yy, out, sm = procinv.cledb_matchiqud(0, 0, g['sobs_totrot'][0, 0], g['dopp'][0, 0], g['yobs'][0, 0], g['aobs'][0, 0],
+                                              g['dobs'][0, 0], db, hdr, g['snr'][0, 0], 8, 1000, 3, False, 0)
+    assert np.array_equal(out[:, :5], g['invout_iqud'][0, 0][:, :5])
+    np.testing.assert_allclose(out, g['invout_iqud'][0, 0], rtol=1e-6)
+    # relations the reference's own test asserts
+    assert np.isin(g['invout_iquv'][0, 0, :2, 0], out[:4, 0]).all()
+    procinv.OPTIONS.update(precision=0, dbencoding=0)
+    procinv.release_databases()
+
+
+def test_map_256_subsample(ctx):
+    """BASELINE config 2/3 shape: 256x256 map, one full-size database, int16 encoding.  The whole map runs on the
+    GPU; a seeded subset of 160 pixels is checked against the oracle (which needs ~30 ms per pixel)."""
+    db = synth.make_database(9, 40)
+    obs = synth.make_observation(256, 256, [db], seed=7)
+    ctx.db_put(0, db, native.ENC_I16)
+    dec = codec.decoded_database(db, native.ENC_I16)
+    sobs, snr = obs['sobs_totrot'].reshape(-1, 8), obs['snr'].reshape(-1, 8)
+    enc = np.zeros(sobs.shape[0], np.int32)
+    pick = np.random.default_rng(1).choice(sobs.shape[0], 160, replace=False)
+    for mode in (native.MODE_IQUV, native.MODE_IQUD):
+        raw = ctx.match(mode, sobs, snr, enc, 8)
+        sub = {k: (v[pick] if v is not None else None) for k, v in raw.items()}
+        searched, reordered = check_raw_against_oracle(sub, mode, sobs[pick], snr[pick], [dec], enc[pick], 8)
+        assert searched > 150 and reordered <= 8
+        # size-independent properties on the full map
+        ok = raw['status'] == native.PIX_SEARCHED
+        chi = raw['chi'][ok]
+        assert (np.diff(chi, axis=1) >= 0).all(), 'chi^2 ascending in every pixel'
+        idx = raw['idx'][ok]
+        assert (idx >= 0).all() and (idx < dec.shape[0]).all()
+        assert (np.sort(idx, axis=1)[:, 1:] != np.sort(idx, axis=1)[:, :-1]).all(), 'no index twice in a true top-k'
+        if mode == native.MODE_IQUV:
+            sv = np.sign(dec[idx.reshape(-1), 3]).reshape(idx.shape)
+            assert (sv == np.sign(sobs[ok][:, 3])[:, None]).all(), 'winners have the sign of the observed V'
+        # idempotence: the same call again gives the same bits
+        again = ctx.match(mode, sobs, snr, enc, 8)
+        assert np.array_equal(raw['idx'], again['idx']) and np.array_equal(raw['chi'], again['chi'])
+    ctx.db_drop(0)
+
+
+def test_elementwise_golden(ctx, golden_dir):
+    """blos_proc and obs_qurotate/obs_calcheight through the product surface against the reference's outputs."""
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    import CLEDB_PREPINV.CLEDB_PREPINV as prepinv
+    import constants as consts
+    import ctrlparams
+    params = ctrlparams.ctrlparams()
+    params.verbose = 0
+    g = np.load(os.path.join(golden_dir, 'elementwise.npz'))
+    nx, ny = g['one'].shape[:2]
+    for nline, key, lines in ((1, 'one', ['si-x_1430', 0]), (2, 'two', ['fe-xiii_1074', 'fe-xiii_1079'])):
+        kv = synth.make_keyvals(nx, ny, nline=nline)
+        kv[4] = lines
+        iss = np.zeros((nx, ny, nline), np.int32)
+        blos = procinv.blos_proc(g[key], np.ones_like(g[key]), iss, kv, consts, params)
+        ref = g['blos%d' % nline]
+        np.testing.assert_allclose(blos[..., :3], ref[..., :3], rtol=2e-6, atol=0)
+        np.testing.assert_allclose(blos[..., 3], ref[..., 3], rtol=0, atol=1e-6)
+        assert same(iss, g['blos%d_iss' % nline])
+    for tag in ('std', 'crpix_linpol', 'hpxy'):
+        v = g['kv_' + tag]
+        kv = synth.make_keyvals(nx, ny)
+        kv[5], kv[6], kv[8], kv[9], kv[11], kv[12], kv[14] = (int(v[0]), int(v[1]), float(v[2]), float(v[3]),
+                                                              float(v[4]), float(v[5]), float(v[6]))
+        rot, aobs = prepinv.obs_qurotate(g['raw'], kv, g['hp_' + tag])
+        yobs = prepinv.obs_calcheight(kv, g['hp_' + tag])
+        np.testing.assert_allclose(aobs, g['aobs_' + tag], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(yobs, g['yobs_' + tag], rtol=1e-6, atol=0)
+        scale = np.abs(g['raw']).max(axis=-1, keepdims=True)
+        np.testing.assert_allclose(rot, g['rot_' + tag], rtol=1e-5, atol=float(1e-6 * scale.max()))
+        assert np.array_equal(rot[..., [0, 3, 4, 7]], g['raw'][..., [0, 3, 4, 7]], equal_nan=True)
+    # known answer of tests/debug_unittests.ipynb cells 9-10
+    out, flags = ctx.blos(np.array([[2.7957714e-09, 3.3037444e-11, -5.7222532e-11, -1.2028063e-13]], np.float32),
+                          1.e9 * (6.62607004e-34 * 2.9979e+8 / (9.274009994e-24 * 1.e-4) / (1074.6153 ** 2)), 1.25, 0.0)
+    np.testing.assert_allclose(out[0], [5.4486594, 5.197059, 5.319886, -0.5235988], rtol=2e-6)
+
+
+def test_error_paths(ctx):
+    with pytest.raises(native.CledbError):
+        ctx.match(0, np.ones((4, 8), np.float32), np.ones((4, 8), np.float32), np.zeros(4, np.int32), 8)     # no database
+    db = synth.make_database(8, 39, ngx=3, nbphi=8, nbtheta=6)
+    ctx.db_put(0, db, native.ENC_I16)
+    with pytest.raises(native.CledbError):
+        ctx.match(0, np.ones((4, 8), np.float32), np.ones((4, 8), np.float32), np.zeros(4, np.int32), 33)    # nsearch > 32
+    raw = ctx.match(0, np.zeros((0, 8), np.float32), np.zeros((0, 8), np.float32), np.zeros(0, np.int32), 8)  # empty map
+    assert raw['idx'].shape == (0, 8)
+    # a database smaller than nsearch: the missing slots are -1
+    tiny = db.reshape(-1, 8)[:5].copy()
+    tiny[:, 3] = np.abs(tiny[:, 3]) + 1e-9
+    ctx.db_put(1, tiny, native.ENC_I16)
+    s = (tiny[2] * 2e-9).astype(np.float32)[None, :]
+    raw = ctx.match(0, s, np.full((1, 8), 5, np.float32), np.ones(1, np.int32), 8)
+    assert raw['idx'][0, 0] == 2 and (raw['idx'][0, 5:] == -1).all() and sorted(raw['idx'][0, :5]) == [0, 1, 2, 3, 4]
+    ctx.db_drop(0)
+    ctx.db_drop(1)
