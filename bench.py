@@ -35,7 +35,7 @@ NSEARCH = 8
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--mode', default='iquv', choices=['iquv', 'iqud'])
@@ -132,7 +132,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(',')])
         except Exception:
@@ -194,7 +194,8 @@ def main():
     gather_chi = [torch.empty_like(chi_d) for _ in range(world)] if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)      # an explicit stream: the library and the CUDA events share it
+    torch.cuda.set_stream(stream)
 
     def step():
         ctx.match_dev(mode, npix, sobs_d.data_ptr(), snr_d.data_ptr(), id_d.data_ptr(), k, idx_d.data_ptr(), chi_d.data_ptr(),

@@ -157,7 +157,7 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
     if (encoding != CLEDB_ENC_F32 && encoding != CLEDB_ENC_I16) { ctx->err = "cledb_db_put: unknown encoding"; return CLEDB_ERR_ARG; }
     CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
 
-    // ---- classify rows by sign(V1); validate the layout contract
+    // ---- validate the layout contract; find the rows that can ever be candidates (V1 not NaN)
     std::vector<int8_t> cls(n);
     int64_t cnt[kParts] = {0, 0, 0}, nnan = 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -166,38 +166,17 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
             ctx->err = "cledb_db_put: component 0 of row " + std::to_string(i) + " is not exactly 1 (database must be normalised by I1, CLEDB_PREPINV.py:306-317)";
             return CLEDB_ERR_DBFORMAT;
         }
-        const float v = r[3];
-        int c;
-        if (std::isnan(v)) { c = -1; ++nnan; }
-        else if (v > 0.f) c = 0;
-        else if (v < 0.f) c = 1;
-        else c = 2;
-        cls[i] = (int8_t)c;
-        if (c >= 0) {
-            ++cnt[c];
-            if (!(std::isfinite(r[1]) && std::isfinite(r[2]) && std::isfinite(r[4]) && std::isfinite(r[5]) && std::isfinite(r[6]))) {
-                ctx->err = "cledb_db_put: non-finite Stokes I/Q/U in candidate row " + std::to_string(i);
-                return CLEDB_ERR_DBFORMAT;
-            }
+        if (std::isnan(r[3])) { cls[i] = -1; ++nnan; continue; }
+        cls[i] = 0;
+        if (!(std::isfinite(r[1]) && std::isfinite(r[2]) && std::isfinite(r[4]) && std::isfinite(r[5]) && std::isfinite(r[6]))) {
+            ctx->err = "cledb_db_put: non-finite Stokes I/Q/U in candidate row " + std::to_string(i);
+            return CLEDB_ERR_DBFORMAT;
         }
     }
     if (cledb_db_drop(ctx, db_id) != CLEDB_OK) ctx->err.clear();   // replace an existing database of this id
 
     HostDb h;
     std::memset(&h.slot, 0, sizeof(DbSlot));
-    int64_t tile = 0;
-    int64_t pos0[kParts];
-    for (int q = 0; q < kParts; ++q) {
-        h.slot.part_tile0[q] = (int32_t)tile;
-        h.slot.part_ntiles[q] = (int32_t)((cnt[q] + kTile - 1) / kTile);
-        h.slot.part_cnt[q] = (int32_t)cnt[q];
-        pos0[q] = tile * kTile;
-        tile += h.slot.part_ntiles[q];
-    }
-    const int64_t ntiles = tile, npad = ntiles * kTile;
-    h.npad = npad;
-    h.nnan = nnan;
-
     // ---- block exponents per component (int16 encoding); scale = 2^-shift
     for (int c = 0; c < 8; ++c) { h.shift[c] = 0; h.slot.scale[c] = 1.0f; }
     if (encoding == CLEDB_ENC_I16) {
@@ -214,6 +193,28 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
             h.slot.scale[c] = std::ldexp(1.0f, -s);
         }
     }
+    // ---- sign classes of the DECODED V1 (the decoded array is the database: a V1 that underflows the int16
+    //      code is a zero, exactly as the oracle sees it), CLEDB_PROC.py:974
+    for (int64_t i = 0; i < n; ++i) {
+        if (cls[i] < 0) continue;
+        float v = db[i * 8 + 3];
+        if (encoding == CLEDB_ENC_I16) v = f16_bits_to_f32(f32_to_f16_bits_rn(std::ldexp(v, h.shift[3])));
+        const int c = v > 0.f ? 0 : (v < 0.f ? 1 : 2);
+        cls[i] = (int8_t)c;
+        ++cnt[c];
+    }
+    int64_t tile = 0;
+    int64_t pos0[kParts];
+    for (int q = 0; q < kParts; ++q) {
+        h.slot.part_tile0[q] = (int32_t)tile;
+        h.slot.part_ntiles[q] = (int32_t)((cnt[q] + kTile - 1) / kTile);
+        h.slot.part_cnt[q] = (int32_t)cnt[q];
+        pos0[q] = tile * kTile;
+        tile += h.slot.part_ntiles[q];
+    }
+    const int64_t ntiles = tile, npad = ntiles * kTile;
+    h.npad = npad;
+    h.nnan = nnan;
 
     // ---- fill the partitioned arrays
     const int elem = encoding == CLEDB_ENC_I16 ? 2 : 4;

@@ -92,9 +92,10 @@ def test_db_roundtrip(ctx, golden_dir, encoding):
     db[11, 3] = 0.0                       # a zero-V row (third sign class)
     ctx.db_put(5, db, encoding)
     info = ctx.db_info(5)
-    assert info['n'] == db.shape[0] and info['nnan'] == 1 and info['nzero'] == 1
-    assert info['npos'] == int((db[:, 3] > 0).sum()) and info['nneg'] == int((db[:, 3] < 0).sum())
+    assert info['n'] == db.shape[0] and info['nnan'] == 1 and info['nzero'] >= 1
     dec = codec.decoded_database(db, encoding)
+    assert info['npos'] == int((dec[:, 3] > 0).sum()) and info['nneg'] == int((dec[:, 3] < 0).sum())
+    assert info['nzero'] == int((dec[:, 3] == 0).sum())
     assert np.array_equal(ctx.db_decoded(5), dec, equal_nan=True)
     if encoding == native.ENC_F32:
         keep = ~np.isnan(db[:, 3])
@@ -134,7 +135,7 @@ def test_raw_search_small(ctx, golden_dir, encoding, mode, k):
         sobs[13] = g['sobs_iqud'].reshape(-1, 8)[13]      # the V == 0 pixel the reference cannot survive (status 3)
     raw = ctx.match(mode, sobs, snr, enc, k, want_chi64=True)
     searched, reordered = check_raw_against_oracle(raw, mode, sobs, snr, dec, enc, k)
-    assert searched > 90 and reordered <= 3
+    assert searched > 90 and reordered <= max(3, k // 4)     # near-tie reorderings only (checked member by member above)
     raw64 = ctx.match(mode, sobs, snr, enc, k, precision=native.PREC_FP64, want_chi64=True)
     check_raw_against_oracle(raw64, mode, sobs, snr, dec, enc, k, exact=True)
     for i in range(3):
