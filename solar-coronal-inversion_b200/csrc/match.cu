@@ -56,6 +56,13 @@ __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// 128-bit shared-memory load from a 32-bit shared address (keeps the hot loop free of generic->shared conversions)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // per-pixel records and per-list entries for the two arithmetic variants
 // ------------------------------------------------------------------------------------------------------
@@ -500,7 +507,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
     unsigned char* stages = smem;                                        // [kWarps][kStages][TB]
     unsigned char* boot = stages + kWarps * kStages * TB;                // [TB] first tile of the item, all warps
     RecT* recs = reinterpret_cast<RecT*>(boot + TB);                     // [kMaxP]
-    CandT* lists = reinterpret_cast<CandT*>(recs + kMaxP);               // [kMaxP][k]
+    CandT* lists = reinterpret_cast<CandT*>(recs + kMaxP + 1);           // [kMaxP][k]  (one spare record: prefetch overrun)
     uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kMaxP * pl.k);  // [kWarps*kStages + 1]
     int* locks = reinterpret_cast<int*>(bars + kWarps * kStages + 1);    // [kMaxP]
     __shared__ Item s_item;
@@ -615,6 +622,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
         __syncthreads();
 
         // ---- main loop: this warp's tiles 1+warp, 1+warp+8, ...
+        const uint32_t rec_base = smem_u32(recs);
         int iter = 0;
         for (int t = 1 + warp; t < im.ntiles; t += kWarps, ++iter) {
             const int s = iter % kStages;
@@ -630,13 +638,44 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                 }
             }
             const int base = (im.tile0 + t) * kTile;
+            // fast pass: no control flow.  Bit j of hmask = "one of my 8 entries may enter the list of pixel j"
+            uint32_t hmask = 0;
+            if (PREC == CLEDB_PREC_FP32) {
+                uint32_t ra = rec_base;
+                float4 n0 = lds128(ra), n1 = lds128(ra + 16), n2 = lds128(ra + 32);
 #pragma unroll 2
-            for (int j = 0; j < im.npx; ++j) {
-                V v[kEPL], tau;
-                eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau);
-                V m = fmin(fmin(fmin(v[0], v[1]), fmin(v[2], v[3])), fmin(fmin(v[4], v[5]), fmin(v[6], v[7])));
-                if (__any_sync(0xffffffffu, m <= tau)) {
-                    // rare path: some entry may enter the list of pixel j
+                for (int j = 0; j < im.npx; ++j) {
+                    const float4 x0 = n0, x1 = n1, x2 = n2;
+                    ra += (uint32_t)sizeof(RecT);
+                    n0 = lds128(ra); n1 = lds128(ra + 16); n2 = lds128(ra + 32);     // prefetch (recs has a spare slot)
+                    const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
+                    const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
+                    float v[kEPL];
+#pragma unroll
+                    for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
+                    const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
+                    if (m <= x2.w) hmask |= 1u << j;
+                }
+            } else {
+                for (int j = 0; j < im.npx; ++j) {
+                    V v[kEPL], tau;
+                    eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau);
+                    const V m = fmin(fmin(fmin(v[0], v[1]), fmin(v[2], v[3])), fmin(fmin(v[4], v[5]), fmin(v[6], v[7])));
+                    if (m <= tau) hmask |= 1u << j;
+                }
+            }
+            // rare pass: pixels flagged by any lane are re-evaluated and their candidates inserted.  Each warp
+            // starts at a different pixel so that the 8 warps of the CTA seldom meet on one list lock.
+            uint32_t any = __reduce_or_sync(0xffffffffu, hmask);
+            if (any) {
+                const int rot = (warp * 4) & 31;
+                any = __funnelshift_r(any, any, rot);
+                while (any) {
+                    const int b = __ffs(any) - 1;
+                    any &= any - 1;
+                    const int j = (b + rot) & 31;
+                    V v[kEPL], tau;
+                    eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau);
 #pragma unroll
                     for (int e = 0; e < kEPL; ++e) {
                         const int pos = base + pos_in_tile<ENC>(lane, e);
@@ -766,7 +805,7 @@ __global__ void __launch_bounds__(128) k_finalize(Plan pl, const DbSlot* __restr
 // host side
 // ------------------------------------------------------------------------------------------------------
 template <int ENC, int PREC> static size_t match_smem_bytes(int k) {
-    return (size_t)kWarps * kStages * tile_bytes<ENC>() + tile_bytes<ENC>() + sizeof(Rec<PREC>) * kMaxP +
+    return (size_t)kWarps * kStages * tile_bytes<ENC>() + tile_bytes<ENC>() + sizeof(Rec<PREC>) * (kMaxP + 1) +
            sizeof(Cand<PREC>) * kMaxP * k + sizeof(uint64_t) * (kWarps * kStages + 1) + sizeof(int) * kMaxP + 16;
 }
 
