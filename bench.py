@@ -43,6 +43,7 @@ def parse():
     ap.add_argument('--encoding', type=int, default=1)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dbg', type=int, default=0, help='kernel timing experiment (results invalid)')
     return ap.parse_args()
 
 
@@ -177,6 +178,8 @@ def main():
     ctx = native.Context(local)
     ctx.db_put(0, db, args.encoding)
     props = ctx.device_props()
+    if args.dbg:
+        ctx.set_tuning(-args.dbg, 0)
     npix = args.nx * args.nx
     k = NSEARCH
 

@@ -121,6 +121,11 @@ extern "C" int cledb_measure_fp32_peak(cledb_ctx* ctx, double* tflops) {
 
 extern "C" int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split) {
     if (!ctx) return CLEDB_ERR_ARG;
+    if (pixels_per_item < 0) {   // undocumented: timing experiments (results invalid), see Plan::dbg
+        ctx->dbg = -pixels_per_item;
+        return CLEDB_OK;
+    }
+    ctx->dbg = 0;
     if (pixels_per_item < 1 || pixels_per_item > kMaxP || split < 0 || split > 8) { ctx->err = "cledb_set_tuning: out of range"; return CLEDB_ERR_ARG; }
     ctx->pixels_per_item = pixels_per_item;
     ctx->split = split;

@@ -84,6 +84,7 @@ struct cledb_ctx {
     int64_t launches = 0;
     int pixels_per_item = cledb::kMaxP;
     int split = 0;
+    int dbg = 0;
     int occ = 0, regs = 0, smem = 0;               // search kernel occupancy facts
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;   // event pairs around the search kernel
     int prof_used = 0;

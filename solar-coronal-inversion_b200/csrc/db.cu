@@ -153,7 +153,7 @@ extern "C" int cledb_db_drop(cledb_ctx* ctx, int db_id) {
 extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t n, int encoding) {
     if (!ctx) return CLEDB_ERR_ARG;
     if (!db || n <= 0 || db_id < 0 || db_id > (1 << 24)) { ctx->err = "cledb_db_put: bad argument"; return CLEDB_ERR_ARG; }
-    if (n > (int64_t)1 << 30) { ctx->err = "cledb_db_put: more than 2^30 rows"; return CLEDB_ERR_ARG; }
+    if (n > (int64_t)1 << 29) { ctx->err = "cledb_db_put: more than 2^29 rows"; return CLEDB_ERR_ARG; }
     if (encoding != CLEDB_ENC_F32 && encoding != CLEDB_ENC_I16) { ctx->err = "cledb_db_put: unknown encoding"; return CLEDB_ERR_ARG; }
     CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
 

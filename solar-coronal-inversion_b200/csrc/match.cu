@@ -179,9 +179,9 @@ __device__ __forceinline__ double inf_of(double) { return CUDART_INF; }
 // of the CTA: a spin lock in shared memory serialises writers (insertions are rare after the bootstrap).
 template <int PREC>
 __device__ __forceinline__ void list_insert(volatile Cand<PREC>* list, int* lock, volatile typename Val<PREC>::type* tau,
-                                            int k, typename Val<PREC>::type v, int pos, int lane) {
+                                            int k, typename Val<PREC>::type v, int pos, int lane, bool use_lock = true) {
     using V = typename Val<PREC>::type;
-    if (lane == 0) {
+    if (use_lock && lane == 0) {
         while (atomicCAS(lock, 0, 1) != 0) {
         }
     }
@@ -211,9 +211,65 @@ __device__ __forceinline__ void list_insert(volatile Cand<PREC>* list, int* lock
         if (lane == k - 1) *tau = lv;
     }
     __syncwarp();
-    if (lane == 0) {
+    if (use_lock && lane == 0) {
         __threadfence_block();
         atomicExch(lock, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// candidate queues (fp32 kernel).  The list of pixel j is owned by warp j/4: only the owner modifies it, so no
+// lock is needed and nobody ever waits for an insertion.  A warp that finds a candidate for a foreign pixel
+// pushes it (one 64-bit shared store: value | position<<2 | pixel-in-group) into the owner's ring; the owner
+// drains its ring at tile boundaries.  A slot is published by the store itself (sentinel = empty).
+// ------------------------------------------------------------------------------------------------------
+constexpr int kQCap = 64;                 // entries per owner ring (power of two)
+constexpr uint32_t kQEmpty = 0xffffffffu;
+
+struct Queues {
+    uint2* q;          // [kWarps][kQCap]
+    int*   tail;       // [kWarps] next slot to allocate (atomic)
+    int*   head;       // [kWarps] first slot not yet consumed (written by the owner only)
+};
+
+__device__ __forceinline__ void drain_own(const Queues& Q, int warp, int lane, int& my_head, Cand<CLEDB_PREC_FP32>* lists,
+                                          Rec<CLEDB_PREC_FP32>* recs, int k) {
+    const int t = *reinterpret_cast<volatile int*>(&Q.tail[warp]);
+    if (my_head == t) return;
+    int h = my_head;
+    while (h != t) {
+        volatile unsigned long long* slot = reinterpret_cast<volatile unsigned long long*>(&Q.q[warp * kQCap + (h & (kQCap - 1))]);
+        uint32_t packed, bits;
+        do {                                   // allocated but not yet written: the store is on its way
+            const unsigned long long w = *slot;            // one 64-bit load: value and tag always belong together
+            bits = (uint32_t)w;
+            packed = (uint32_t)(w >> 32);
+        } while (packed == kQEmpty);
+        __syncwarp();
+        if (lane == 0) *slot = ((unsigned long long)kQEmpty << 32);
+        const int j = warp * 4 + (int)(packed & 3u);
+        list_insert<CLEDB_PREC_FP32>(lists + j * k, nullptr, reinterpret_cast<volatile float*>(&recs[j].tau), k,
+                                     __uint_as_float(bits), (int)(packed >> 2), lane, false);
+        ++h;
+    }
+    my_head = h;
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        *reinterpret_cast<volatile int*>(&Q.head[warp]) = h;
+    }
+}
+
+__device__ __forceinline__ void push_candidate(const Queues& Q, int owner, float v, int pos, int jj, int warp, int lane,
+                                               int& my_head, Cand<CLEDB_PREC_FP32>* lists, Rec<CLEDB_PREC_FP32>* recs, int k) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(&Q.tail[owner], 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    while (slot - *reinterpret_cast<volatile int*>(&Q.head[owner]) >= kQCap)
+        drain_own(Q, warp, lane, my_head, lists, recs, k);        // ring full: keep my own ring moving meanwhile
+    if (lane == 0) {   // one 64-bit store publishes the entry
+        const unsigned long long w = ((unsigned long long)(((uint32_t)pos << 2) | (uint32_t)jj) << 32) | __float_as_uint(v);
+        *reinterpret_cast<volatile unsigned long long*>(&Q.q[owner * kQCap + (slot & (kQCap - 1))]) = w;
     }
 }
 
@@ -238,6 +294,7 @@ struct Plan {                 // all pointers are device pointers into the works
     int32_t  split;           // chunks per sign partition
     int32_t  mode;
     int32_t  k;
+    int32_t  dbg;             // timing experiments only: 1 = no list lock, 2 = skip the rare pass (results invalid)
     int64_t  npix;
 };
 
@@ -510,6 +567,11 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
     CandT* lists = reinterpret_cast<CandT*>(recs + kMaxP + 1);           // [kMaxP][k]  (one spare record: prefetch overrun)
     uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kMaxP * pl.k);  // [kWarps*kStages + 1]
     int* locks = reinterpret_cast<int*>(bars + kWarps * kStages + 1);    // [kMaxP]
+    Queues Q;
+    Q.tail = locks + kMaxP;                                              // [kWarps]
+    Q.head = Q.tail + kWarps;                                            // [kWarps]
+    Q.q = reinterpret_cast<uint2*>(Q.head + kWarps);                     // [kWarps][kQCap]
+    int my_head = 0;
     __shared__ Item s_item;
     __shared__ int s_it;
 
@@ -568,6 +630,9 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
             lists[i].pos = -1;
         }
         if (threadIdx.x < kMaxP) locks[threadIdx.x] = 0;
+        if (threadIdx.x < 2 * kWarps) Q.tail[threadIdx.x] = 0;            // tail[] and head[] are adjacent
+        for (int i = threadIdx.x; i < kWarps * kQCap; i += kThreads) Q.q[i] = make_uint2(0u, kQEmpty);
+        my_head = 0;
         __syncthreads();
 
         float scale[kNC];
@@ -667,7 +732,9 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
             // rare pass: pixels flagged by any lane are re-evaluated and their candidates inserted.  Each warp
             // starts at a different pixel so that the 8 warps of the CTA seldom meet on one list lock.
             uint32_t any = __reduce_or_sync(0xffffffffu, hmask);
-            if (any) {
+            if (PREC == CLEDB_PREC_FP32) drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
+                                                   reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
+            if (any && pl.dbg != 2) {
                 const int rot = (warp * 4) & 31;
                 any = __funnelshift_r(any, any, rot);
                 while (any) {
@@ -676,21 +743,36 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                     const int j = (b + rot) & 31;
                     V v[kEPL], tau;
                     eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau);
+                    const V tnow = *reinterpret_cast<volatile V*>(&recs[j].tau);
 #pragma unroll
                     for (int e = 0; e < kEPL; ++e) {
                         const int pos = base + pos_in_tile<ENC>(lane, e);
-                        const V tnow = *reinterpret_cast<volatile V*>(&recs[j].tau);
                         uint32_t hits = __ballot_sync(0xffffffffu, v[e] <= tnow && pos < im.cnt_end);
                         while (hits) {
                             const int src = __ffs(hits) - 1;
                             hits &= hits - 1;
                             const V cv = __shfl_sync(0xffffffffu, v[e], src);
-                            const int cp = __shfl_sync(0xffffffffu, pos, src);
-                            list_insert<PREC>(lists + j * k, &locks[j], reinterpret_cast<volatile V*>(&recs[j].tau), k, cv, cp, lane);
+                            const int cp = base + pos_in_tile<ENC>(src, e);
+                            if (PREC == CLEDB_PREC_FP32) {
+                                // lists are owned by warp j/4: insert my own, queue the others (nobody waits)
+                                if ((j >> 2) == warp)
+                                    list_insert<PREC>(lists + j * k, nullptr, reinterpret_cast<volatile V*>(&recs[j].tau), k, cv, cp, lane, false);
+                                else
+                                    push_candidate(Q, j >> 2, (float)cv, cp, j & 3, warp, lane, my_head,
+                                                   reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
+                                                   reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
+                            } else {
+                                list_insert<PREC>(lists + j * k, &locks[j], reinterpret_cast<volatile V*>(&recs[j].tau), k, cv, cp, lane, true);
+                            }
                         }
                     }
                 }
             }
+        }
+        if (PREC == CLEDB_PREC_FP32) {        // all pushes are done: every owner empties its ring
+            __syncthreads();
+            drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
+                      reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
         }
         __syncthreads();
         // ---- write the item's partial lists
@@ -806,7 +888,8 @@ __global__ void __launch_bounds__(128) k_finalize(Plan pl, const DbSlot* __restr
 // ------------------------------------------------------------------------------------------------------
 template <int ENC, int PREC> static size_t match_smem_bytes(int k) {
     return (size_t)kWarps * kStages * tile_bytes<ENC>() + tile_bytes<ENC>() + sizeof(Rec<PREC>) * (kMaxP + 1) +
-           sizeof(Cand<PREC>) * kMaxP * k + sizeof(uint64_t) * (kWarps * kStages + 1) + sizeof(int) * kMaxP + 16;
+           sizeof(Cand<PREC>) * kMaxP * k + sizeof(uint64_t) * (kWarps * kStages + 1) + sizeof(int) * (kMaxP + 2 * kWarps) +
+           sizeof(uint2) * kWarps * kQCap + 16;
 }
 
 template <int ENC, int PREC> static int configure_match(cledb_ctx* ctx, int k, int* occ_out, size_t* smem_out) {
@@ -894,6 +977,7 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     pl.mode = mode;
     pl.k = nsearch;
     pl.P = std::max(1, std::min(ctx->pixels_per_item, kMaxP));
+    pl.dbg = ctx->dbg;
     pl.nkeys = ctx->slots_cap * kParts;
     int split = ctx->split;
     if (split <= 0) {   // few pixels: cut the candidate lists so that the machine is still filled
