@@ -230,6 +230,7 @@ struct Queues {
     uint2* q;          // [kWarps][kQCap]
     int*   tail;       // [kWarps] next slot to allocate (atomic)
     int*   head;       // [kWarps] first slot not yet consumed (written by the owner only)
+    int*   done;       // [1] warps that have finished their tiles of the current item
 };
 
 __device__ __forceinline__ void drain_own(const Queues& Q, int warp, int lane, int& my_head, Cand<CLEDB_PREC_FP32>* lists,
@@ -570,7 +571,8 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
     Queues Q;
     Q.tail = locks + kMaxP;                                              // [kWarps]
     Q.head = Q.tail + kWarps;                                            // [kWarps]
-    Q.q = reinterpret_cast<uint2*>(Q.head + kWarps);                     // [kWarps][kQCap]
+    Q.done = Q.head + kWarps;                                            // [1] (+1 pad)
+    Q.q = reinterpret_cast<uint2*>(Q.done + 2);                          // [kWarps][kQCap]
     int my_head = 0;
     __shared__ Item s_item;
     __shared__ int s_it;
@@ -630,7 +632,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
             lists[i].pos = -1;
         }
         if (threadIdx.x < kMaxP) locks[threadIdx.x] = 0;
-        if (threadIdx.x < 2 * kWarps) Q.tail[threadIdx.x] = 0;            // tail[] and head[] are adjacent
+        if (threadIdx.x < 2 * kWarps + 2) Q.tail[threadIdx.x] = 0;        // tail[], head[] and done are adjacent
         for (int i = threadIdx.x; i < kWarps * kQCap; i += kThreads) Q.q[i] = make_uint2(0u, kQEmpty);
         my_head = 0;
         __syncthreads();
@@ -769,8 +771,17 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                 }
             }
         }
-        if (PREC == CLEDB_PREC_FP32) {        // all pushes are done: every owner empties its ring
-            __syncthreads();
+        if (PREC == CLEDB_PREC_FP32) {
+            // A warp that is done with its tiles must keep serving its ring until every warp is done: a producer
+            // may be waiting for space in it (a plain __syncthreads here would deadlock against that wait).
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(Q.done, 1);
+            }
+            while (*reinterpret_cast<volatile int*>(Q.done) < kWarps)
+                drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
+                          reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
             drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
                       reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
         }
@@ -888,7 +899,7 @@ __global__ void __launch_bounds__(128) k_finalize(Plan pl, const DbSlot* __restr
 // ------------------------------------------------------------------------------------------------------
 template <int ENC, int PREC> static size_t match_smem_bytes(int k) {
     return (size_t)kWarps * kStages * tile_bytes<ENC>() + tile_bytes<ENC>() + sizeof(Rec<PREC>) * (kMaxP + 1) +
-           sizeof(Cand<PREC>) * kMaxP * k + sizeof(uint64_t) * (kWarps * kStages + 1) + sizeof(int) * (kMaxP + 2 * kWarps) +
+           sizeof(Cand<PREC>) * kMaxP * k + sizeof(uint64_t) * (kWarps * kStages + 1) + sizeof(int) * (kMaxP + 2 * kWarps + 2) +
            sizeof(uint2) * kWarps * kQCap + 16;
 }
 
