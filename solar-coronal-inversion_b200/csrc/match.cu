@@ -236,7 +236,6 @@ struct Queues {
 __device__ __forceinline__ void drain_own(const Queues& Q, int warp, int lane, int& my_head, Cand<CLEDB_PREC_FP32>* lists,
                                           Rec<CLEDB_PREC_FP32>* recs, int k) {
     const int t = *reinterpret_cast<volatile int*>(&Q.tail[warp]);
-    if (my_head == t) return;
     int h = my_head;
     while (h != t) {
         volatile unsigned long long* slot = reinterpret_cast<volatile unsigned long long*>(&Q.q[warp * kQCap + (h & (kQCap - 1))]);
@@ -246,19 +245,20 @@ __device__ __forceinline__ void drain_own(const Queues& Q, int warp, int lane, i
             bits = (uint32_t)w;
             packed = (uint32_t)(w >> 32);
         } while (packed == kQEmpty);
+        ++h;
         __syncwarp();
-        if (lane == 0) *slot = ((unsigned long long)kQEmpty << 32);
+        if (lane == 0) {
+            // free the slot and publish the new head at once: a producer whose slot is still beyond the ring is
+            // waiting for exactly this, and this loop may in turn be waiting for that producer's entry
+            *slot = ((unsigned long long)kQEmpty << 32);
+            __threadfence_block();
+            *reinterpret_cast<volatile int*>(&Q.head[warp]) = h;
+        }
         const int j = warp * 4 + (int)(packed & 3u);
         list_insert<CLEDB_PREC_FP32>(lists + j * k, nullptr, reinterpret_cast<volatile float*>(&recs[j].tau), k,
                                      __uint_as_float(bits), (int)(packed >> 2), lane, false);
-        ++h;
     }
     my_head = h;
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence_block();
-        *reinterpret_cast<volatile int*>(&Q.head[warp]) = h;
-    }
 }
 
 __device__ __forceinline__ void push_candidate(const Queues& Q, int owner, float v, int pos, int jj, int warp, int lane,
