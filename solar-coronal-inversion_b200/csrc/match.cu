@@ -239,12 +239,11 @@ __device__ __forceinline__ void drain_own(const Queues& Q, int warp, int lane, i
     int h = my_head;
     while (h != t) {
         volatile unsigned long long* slot = reinterpret_cast<volatile unsigned long long*>(&Q.q[warp * kQCap + (h & (kQCap - 1))]);
-        uint32_t packed, bits;
-        do {                                   // allocated but not yet written: the store is on its way
-            const unsigned long long w = *slot;            // one 64-bit load: value and tag always belong together
-            bits = (uint32_t)w;
-            packed = (uint32_t)(w >> 32);
-        } while (packed == kQEmpty);
+        const unsigned long long w = *slot;                // one 64-bit load: value and tag always belong together
+        const uint32_t bits = (uint32_t)w, packed = (uint32_t)(w >> 32);
+        // Allocated but not yet written: come back later.  NEVER wait here - the producer of this slot may itself be
+        // inside its own drain while it waits for ring space that only this warp can free (cyclic wait).
+        if (packed == kQEmpty) break;
         ++h;
         __syncwarp();
         if (lane == 0) {
@@ -782,8 +781,10 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
             while (*reinterpret_cast<volatile int*>(Q.done) < kWarps)
                 drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
                           reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
-            drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
-                      reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
+            // every producer has fenced its last entry before counting itself done: what is left is complete
+            while (my_head != *reinterpret_cast<volatile int*>(&Q.tail[warp]))
+                drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
+                          reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
         }
         __syncthreads();
         // ---- write the item's partial lists
