@@ -94,6 +94,7 @@ template <> struct EncTraits<CLEDB_ENC_F32> { static constexpr int kElem = 4; };
 template <int ENC> __host__ __device__ constexpr int tile_bytes() { return kNC * kTile * EncTraits<ENC>::kElem; }
 
 constexpr int kStages = 2;
+constexpr int kBootTiles = 9;     // tiles ranked by the owner-computes bootstrap before the shared main loop
 
 // position inside a tile of entry e of a lane.  Chosen so that the lane's shared-memory reads are 16-byte
 // vectors at a 16-byte lane stride (conflict free): int16 -> 8 consecutive entries per lane and component,
@@ -607,6 +608,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
         CandT* gout = reinterpret_cast<CandT*>(pl.plist) + (size_t)it * pl.P * k;
 
         // ---- stage the item: pixel records, empty lists, first tile for the bootstrap, per-warp prefetch
+        const int nb = min(im.ntiles, kBootTiles);       // tiles handled by the bootstrap
         if (threadIdx.x == 0 && im.ntiles > 0) {
             mbar_expect_tx(boot_bar, TB);
             tma_load_1d(boot, gt, TB, boot_bar);
@@ -614,7 +616,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
         if (lane == 0) {
 #pragma unroll
             for (int s = 0; s < kStages; ++s) {
-                const int t = 1 + warp + s * kWarps;
+                const int t = nb + warp + s * kWarps;
                 if (t < im.ntiles) {
                     mbar_expect_tx(&my_bars[s], TB);
                     tma_load_1d(my_stages + s * TB, gt + (size_t)t * TB, TB, &my_bars[s]);
@@ -641,15 +643,39 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
         for (int c = 0; c < kNC; ++c) scale[c] = db.scale[chi_comp(c)];
 
         float d[kEPL][kNC];
-        if (im.ntiles > 0) {
-            // ---- bootstrap: warp w ranks the first tile for pixels w, w+8, ...: k rounds of warp-min selection
+        // ---- bootstrap over the first nb tiles, owner-computes: warp w alone handles pixels 4w..4w+3 (the lists it
+        //      owns), so nothing is shared yet.  Tile 0: exact top-k by k rounds of warp-min selection.  Tiles 1..nb-1:
+        //      online insertion against the live threshold.  After ~2300 entries tau is tight enough that the main
+        //      loop's first round produces about one candidate per pixel and warp instead of eight.
+        for (int b = 0; b < nb; ++b) {
             mbar_wait(boot_bar, boot_phase);
             boot_phase ^= 1;
             load_tile_regs<ENC>(boot, lane, d);
-            const int base = im.tile0 * kTile;
-            for (int j = warp; j < im.npx; j += kWarps) {
+            __syncthreads();                                   // every warp holds tile b in registers
+            if (threadIdx.x == 0 && b + 1 < nb) {              // fetch the next bootstrap tile while this one is ranked
+                mbar_expect_tx(boot_bar, TB);
+                tma_load_1d(boot, gt + (size_t)(b + 1) * TB, TB, boot_bar);
+            }
+            const int base = (im.tile0 + b) * kTile;
+            for (int j = warp * 4; j < min(im.npx, warp * 4 + 4); ++j) {
                 V v[kEPL], tau_unused;
                 eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau_unused);
+                if (b > 0) {
+#pragma unroll
+                    for (int e = 0; e < kEPL; ++e) {
+                        const int pos = base + pos_in_tile<ENC>(lane, e);
+                        const V tnow = *reinterpret_cast<volatile V*>(&recs[j].tau);
+                        uint32_t hits = __ballot_sync(0xffffffffu, v[e] <= tnow && pos < im.cnt_end);
+                        while (hits) {
+                            const int src = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            const V cv = __shfl_sync(0xffffffffu, v[e], src);
+                            list_insert<PREC>(lists + j * k, nullptr, reinterpret_cast<volatile V*>(&recs[j].tau), k, cv,
+                                              base + pos_in_tile<ENC>(src, e), lane, false);
+                        }
+                    }
+                    continue;
+                }
                 int ps[kEPL];
 #pragma unroll
                 for (int e = 0; e < kEPL; ++e) {
@@ -683,14 +709,15 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                     lists[j * k + lane].pos = keep_p;
                 }
                 if (lane == k - 1) *const_cast<V*>(&recs[j].tau) = keep_v;
+                __syncwarp();
             }
         }
         __syncthreads();
 
-        // ---- main loop: this warp's tiles 1+warp, 1+warp+8, ...
+        // ---- main loop: this warp's tiles nb+warp, nb+warp+8, ...
         const uint32_t rec_base = smem_u32(recs);
         int iter = 0;
-        for (int t = 1 + warp; t < im.ntiles; t += kWarps, ++iter) {
+        for (int t = nb + warp; t < im.ntiles; t += kWarps, ++iter) {
             const int s = iter % kStages;
             mbar_wait(&my_bars[s], stage_phase[s]);
             stage_phase[s] ^= 1;

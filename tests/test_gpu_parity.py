@@ -290,7 +290,7 @@ def test_error_paths(ctx):
     raw = ctx.match(0, np.zeros((0, 8), np.float32), np.zeros((0, 8), np.float32), np.zeros(0, np.int32), 8)  # empty map
     assert raw['idx'].shape == (0, 8)
     # a database smaller than nsearch: the missing slots are -1
-    tiny = db.reshape(-1, 8)[50:55].copy()      # rows with non-zero Q and U
+    tiny = db.reshape(-1, 8)[55:60].copy()      # rows with non-zero Q and U (phi, theta > 0)
     tiny[:, 3] = np.abs(tiny[:, 3]) + 1e-9
     ctx.db_put(1, tiny, native.ENC_I16)
     s = (tiny[2] * 2e-9).astype(np.float32)[None, :]
