@@ -225,38 +225,34 @@ __device__ __forceinline__ void list_insert(volatile Cand<PREC>* list, int* lock
 // drains its ring at tile boundaries.  A slot is published by the store itself (sentinel = empty).
 // ------------------------------------------------------------------------------------------------------
 constexpr int kQCap = 64;                 // entries per owner ring (power of two)
-constexpr uint32_t kQEmpty = 0xffffffffu;
+constexpr int kQShift = 6;
 
 struct Queues {
-    uint2* q;          // [kWarps][kQCap]
-    int*   tail;       // [kWarps] next slot to allocate (atomic)
-    int*   head;       // [kWarps] first slot not yet consumed (written by the owner only)
-    int*   done;       // [1] warps that have finished their tiles of the current item
+    unsigned long long* q;   // [kWarps][kQCap]  low word: value bits | lap parity << 31, high word: position << 2 | pixel-in-group
+    int* tail;               // [kWarps] next slot to allocate (atomic)
+    int* head;               // [kWarps] first slot not yet consumed (written by the owner only)
+    int* done;               // [1] warps that have finished their tiles of the current item
 };
 
+// chi^2 accumulators are >= +0, so the sign bit of the value word is free: it carries the parity of the lap
+// (slot index / kQCap).  A slot is "ready" when its parity matches the consumer's lap - no reset store and no
+// fence are needed; rings start with parity 1 (not ready for lap 0).
 __device__ __forceinline__ void drain_own(const Queues& Q, int warp, int lane, int& my_head, Cand<CLEDB_PREC_FP32>* lists,
                                           Rec<CLEDB_PREC_FP32>* recs, int k) {
     const int t = *reinterpret_cast<volatile int*>(&Q.tail[warp]);
     int h = my_head;
     while (h != t) {
-        volatile unsigned long long* slot = reinterpret_cast<volatile unsigned long long*>(&Q.q[warp * kQCap + (h & (kQCap - 1))]);
-        const unsigned long long w = *slot;                // one 64-bit load: value and tag always belong together
+        const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&Q.q[warp * kQCap + (h & (kQCap - 1))]);
         const uint32_t bits = (uint32_t)w, packed = (uint32_t)(w >> 32);
         // Allocated but not yet written: come back later.  NEVER wait here - the producer of this slot may itself be
         // inside its own drain while it waits for ring space that only this warp can free (cyclic wait).
-        if (packed == kQEmpty) break;
+        if ((bits >> 31) != (uint32_t)((h >> kQShift) & 1)) break;
         ++h;
-        __syncwarp();
-        if (lane == 0) {
-            // free the slot and publish the new head at once: a producer whose slot is still beyond the ring is
-            // waiting for exactly this, and this loop may in turn be waiting for that producer's entry
-            *slot = ((unsigned long long)kQEmpty << 32);
-            __threadfence_block();
-            *reinterpret_cast<volatile int*>(&Q.head[warp]) = h;
-        }
+        // publish at once: a producer whose slot is still beyond the ring waits for exactly this
+        if (lane == 0) *reinterpret_cast<volatile int*>(&Q.head[warp]) = h;
         const int j = warp * 4 + (int)(packed & 3u);
         list_insert<CLEDB_PREC_FP32>(lists + j * k, nullptr, reinterpret_cast<volatile float*>(&recs[j].tau), k,
-                                     __uint_as_float(bits), (int)(packed >> 2), lane, false);
+                                     __uint_as_float(bits & 0x7fffffffu), (int)(packed >> 2), lane, false);
     }
     my_head = h;
 }
@@ -269,7 +265,8 @@ __device__ __forceinline__ void push_candidate(const Queues& Q, int owner, float
     while (slot - *reinterpret_cast<volatile int*>(&Q.head[owner]) >= kQCap)
         drain_own(Q, warp, lane, my_head, lists, recs, k);        // ring full: keep my own ring moving meanwhile
     if (lane == 0) {   // one 64-bit store publishes the entry
-        const unsigned long long w = ((unsigned long long)(((uint32_t)pos << 2) | (uint32_t)jj) << 32) | __float_as_uint(v);
+        const uint32_t lo = __float_as_uint(v) | ((uint32_t)((slot >> kQShift) & 1) << 31);
+        const unsigned long long w = ((unsigned long long)(((uint32_t)pos << 2) | (uint32_t)jj) << 32) | lo;
         *reinterpret_cast<volatile unsigned long long*>(&Q.q[owner * kQCap + (slot & (kQCap - 1))]) = w;
     }
 }
@@ -572,7 +569,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
     Q.tail = locks + kMaxP;                                              // [kWarps]
     Q.head = Q.tail + kWarps;                                            // [kWarps]
     Q.done = Q.head + kWarps;                                            // [1] (+1 pad)
-    Q.q = reinterpret_cast<uint2*>(Q.done + 2);                          // [kWarps][kQCap]
+    Q.q = reinterpret_cast<unsigned long long*>(Q.done + 2);             // [kWarps][kQCap]
     int my_head = 0;
     __shared__ Item s_item;
     __shared__ int s_it;
@@ -634,7 +631,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
         }
         if (threadIdx.x < kMaxP) locks[threadIdx.x] = 0;
         if (threadIdx.x < 2 * kWarps + 2) Q.tail[threadIdx.x] = 0;        // tail[], head[] and done are adjacent
-        for (int i = threadIdx.x; i < kWarps * kQCap; i += kThreads) Q.q[i] = make_uint2(0u, kQEmpty);
+        for (int i = threadIdx.x; i < kWarps * kQCap; i += kThreads) Q.q[i] = 0x80000000ull;   // parity 1: not ready
         my_head = 0;
         __syncthreads();
 
@@ -731,55 +728,65 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                 }
             }
             const int base = (im.tile0 + t) * kTile;
-            // fast pass: no control flow.  Bit j of hmask = "one of my 8 entries may enter the list of pixel j"
+            // fast pass: groups of 8 pixels without control flow.  Bit j of hmask = "one of my 8 entries may enter
+            // the list of pixel j".  Between groups the warp serves its own candidate ring so that tau stays fresh.
             uint32_t hmask = 0;
             if (PREC == CLEDB_PREC_FP32) {
                 uint32_t ra = rec_base;
                 float4 n0 = lds128(ra), n1 = lds128(ra + 16), n2 = lds128(ra + 32);
+                for (int j0 = 0; j0 < im.npx; j0 += 8) {
+                    const int j1 = min(im.npx, j0 + 8);
 #pragma unroll 2
-                for (int j = 0; j < im.npx; ++j) {
-                    const float4 x0 = n0, x1 = n1, x2 = n2;
-                    ra += (uint32_t)sizeof(RecT);
-                    n0 = lds128(ra); n1 = lds128(ra + 16); n2 = lds128(ra + 32);     // prefetch (recs has a spare slot)
-                    const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
-                    const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
-                    float v[kEPL];
+                    for (int j = j0; j < j1; ++j) {
+                        const float4 x0 = n0, x1 = n1, x2 = n2;
+                        ra += (uint32_t)sizeof(RecT);
+                        n0 = lds128(ra); n1 = lds128(ra + 16); n2 = lds128(ra + 32);     // prefetch (recs has a spare slot)
+                        const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
+                        const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
+                        float v[kEPL];
 #pragma unroll
-                    for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
-                    const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
-                    if (m <= x2.w) hmask |= 1u << j;
+                        for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
+                        const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
+                        hmask = (hmask << 1) | (m <= x2.w ? 1u : 0u);          // pixel j ends up at bit npx-1-j
+                    }
+                    if (*reinterpret_cast<volatile int*>(&Q.tail[warp]) != my_head)
+                        drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
+                                  reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
                 }
             } else {
                 for (int j = 0; j < im.npx; ++j) {
                     V v[kEPL], tau;
                     eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau);
                     const V m = fmin(fmin(fmin(v[0], v[1]), fmin(v[2], v[3])), fmin(fmin(v[4], v[5]), fmin(v[6], v[7])));
-                    if (m <= tau) hmask |= 1u << j;
+                    hmask = (hmask << 1) | (m <= tau ? 1u : 0u);
                 }
             }
-            // rare pass: pixels flagged by any lane are re-evaluated and their candidates inserted.  Each warp
-            // starts at a different pixel so that the 8 warps of the CTA seldom meet on one list lock.
+            // rare pass: pixels flagged by any lane are re-evaluated and their candidates handed to the list owner
             uint32_t any = __reduce_or_sync(0xffffffffu, hmask);
-            if (PREC == CLEDB_PREC_FP32) drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
-                                                   reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
             if (any && pl.dbg != 2) {
-                const int rot = (warp * 4) & 31;
-                any = __funnelshift_r(any, any, rot);
                 while (any) {
-                    const int b = __ffs(any) - 1;
-                    any &= any - 1;
-                    const int j = (b + rot) & 31;
+                    const int b = 31 - __clz(any);                       // highest bit first = lowest pixel first
+                    any &= ~(1u << b);
+                    const int j = im.npx - 1 - b;
                     V v[kEPL], tau;
                     eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau);
                     const V tnow = *reinterpret_cast<volatile V*>(&recs[j].tau);
+                    uint32_t em = 0;                                     // my entries that beat the threshold
 #pragma unroll
-                    for (int e = 0; e < kEPL; ++e) {
-                        const int pos = base + pos_in_tile<ENC>(lane, e);
-                        uint32_t hits = __ballot_sync(0xffffffffu, v[e] <= tnow && pos < im.cnt_end);
-                        while (hits) {
-                            const int src = __ffs(hits) - 1;
-                            hits &= hits - 1;
-                            const V cv = __shfl_sync(0xffffffffu, v[e], src);
+                    for (int e = 0; e < kEPL; ++e)
+                        em |= (v[e] <= tnow && base + pos_in_tile<ENC>(lane, e) < im.cnt_end) ? (1u << e) : 0u;
+                    uint32_t lanes = __ballot_sync(0xffffffffu, em != 0);
+                    while (lanes) {
+                        const int src = __ffs(lanes) - 1;
+                        lanes &= lanes - 1;
+                        uint32_t m = __shfl_sync(0xffffffffu, em, src);
+                        while (m) {
+                            const int e = __ffs(m) - 1;
+                            m &= m - 1;
+                            V mine = v[0];                               // v[e] for a warp-uniform runtime e, kept in registers
+#pragma unroll
+                            for (int q = 1; q < kEPL; ++q) mine = (e == q) ? v[q] : mine;
+                            const V cv = __shfl_sync(0xffffffffu, mine, src);
                             const int cp = base + pos_in_tile<ENC>(src, e);
                             if (PREC == CLEDB_PREC_FP32) {
                                 // lists are owned by warp j/4: insert my own, queue the others (nobody waits)
@@ -802,7 +809,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
             // may be waiting for space in it (a plain __syncthreads here would deadlock against that wait).
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
+                __threadfence_block();        // my last ring entries are visible before I count as done
                 atomicAdd(Q.done, 1);
             }
             while (*reinterpret_cast<volatile int*>(Q.done) < kWarps)
