@@ -126,7 +126,7 @@ extern "C" int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split) 
         return CLEDB_OK;
     }
     ctx->dbg = 0;
-    if (pixels_per_item < 1 || pixels_per_item > kMaxP || split < 0 || split > 8) { ctx->err = "cledb_set_tuning: out of range"; return CLEDB_ERR_ARG; }
+    if (pixels_per_item > kMaxP || split < 0 || split > 8) { ctx->err = "cledb_set_tuning: out of range"; return CLEDB_ERR_ARG; }
     ctx->pixels_per_item = pixels_per_item;
     ctx->split = split;
     return CLEDB_OK;

@@ -82,7 +82,7 @@ struct cledb_ctx {
     cledb::Workspace ws;                           // search workspace (grown on demand)
     cledb::Workspace io;                           // staging for the host entry points
     int64_t launches = 0;
-    int pixels_per_item = cledb::kMaxP;
+    int pixels_per_item = 0;                      // 0 = choose from the pixel count
     int split = 0;
     int dbg = 0;
     int occ = 0, regs = 0, smem = 0;               // search kernel occupancy facts

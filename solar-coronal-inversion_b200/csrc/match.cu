@@ -5,14 +5,17 @@
 // Work decomposition:
 //   bucket  = all pixels that search the same candidate list: (database, sign(V_obs)) for IQUV, database for IQUD
 //   item    = <= 32 pixels of one bucket  x  one contiguous tile range of one sign partition of the database
-//   CTA     = 8 warps; the warps take tiles of the item round-robin.  A lane holds 8 database entries
-//             (5 chi^2 components each, decoded from int16 in registers) and streams the item's pixels past
-//             them: per pixel 3 broadcast LDS.128 (10 coefficients + constant + threshold) feed 80 FFMA.
-//   top-k   = per pixel one list of nsearch (value, position) pairs in shared memory, kept sorted, distributed
-//             over the lanes of whichever warp inserts (warp shuffles); the k-th value is the running threshold
-//             tau that every warp compares against, so after the bootstrap tile insertions are rare.
+//   warp    = the unit of work: a warp fetches an item, owns its pixels exclusively and streams ALL tiles of the
+//             item past them.  Nothing is shared between warps: no locks, no queues, no __syncthreads.
+//             A lane holds 8 database entries (5 chi^2 components each, decoded from int16 in registers); per pixel
+//             3 broadcast LDS.128 (10 coefficients + constant + threshold tau) feed 80 FFMA.
+//   top-k   = per pixel a sorted list of nsearch (value, position) pairs in the warp's shared-memory slice, kept
+//             distributed over the lanes while inserting (warp shuffles).  The k-th value tau is the pruning
+//             threshold: a lane whose entry beats tau drops (value, pixel, slot) into the warp's candidate buffer
+//             from inside the FFMA loop (rare, divergent, values still in registers); the buffer is merged into
+//             the lists once per tile, so tau is exact again before the pixel is visited next.
 //   TMA     = database tiles are contiguous 2.5 KB (int16) / 5 KB (fp32) blocks moved global->shared with
-//             cp.async.bulk + mbarrier complete_tx, double buffered per warp; no __syncthreads in the main loop.
+//             cp.async.bulk + mbarrier complete_tx, double buffered per warp.
 #include <math_constants.h>
 
 #include <algorithm>
@@ -94,7 +97,6 @@ template <> struct EncTraits<CLEDB_ENC_F32> { static constexpr int kElem = 4; };
 template <int ENC> __host__ __device__ constexpr int tile_bytes() { return kNC * kTile * EncTraits<ENC>::kElem; }
 
 constexpr int kStages = 2;
-constexpr int kBootTiles = 9;     // tiles ranked by the owner-computes bootstrap before the shared main loop
 
 // position inside a tile of entry e of a lane.  Chosen so that the lane's shared-memory reads are 16-byte
 // vectors at a 16-byte lane stride (conflict free): int16 -> 8 consecutive entries per lane and component,
@@ -175,18 +177,12 @@ __device__ __forceinline__ float  inf_of(float)  { return CUDART_INF_F; }
 __device__ __forceinline__ double inf_of(double) { return CUDART_INF; }
 
 // Insert candidate (v, pos) into the sorted list of one pixel.  Called by a whole warp with warp-uniform
-// arguments.  Lane j < k holds list element j; order is lexicographic (value, position) so that equal chi^2
-// resolve to the lowest database row (NumPy argmin = first occurrence).  The list is shared by the 8 warps
-// of the CTA: a spin lock in shared memory serialises writers (insertions are rare after the bootstrap).
+// arguments; the list belongs to this warp alone.  Lane j < k holds list element j; order is lexicographic
+// (value, position) so that equal chi^2 resolve to the lowest database row (NumPy argmin = first occurrence).
 template <int PREC>
-__device__ __forceinline__ void list_insert(volatile Cand<PREC>* list, int* lock, volatile typename Val<PREC>::type* tau,
-                                            int k, typename Val<PREC>::type v, int pos, int lane, bool use_lock = true) {
+__device__ __forceinline__ void list_insert(Cand<PREC>* list, typename Val<PREC>::type* tau, int k,
+                                            typename Val<PREC>::type v, int pos, int lane) {
     using V = typename Val<PREC>::type;
-    if (use_lock && lane == 0) {
-        while (atomicCAS(lock, 0, 1) != 0) {
-        }
-    }
-    __syncwarp();
     V lv = inf_of(V());
     uint32_t lp = 0xffffffffu;
     if (lane < k) {
@@ -212,63 +208,6 @@ __device__ __forceinline__ void list_insert(volatile Cand<PREC>* list, int* lock
         if (lane == k - 1) *tau = lv;
     }
     __syncwarp();
-    if (use_lock && lane == 0) {
-        __threadfence_block();
-        atomicExch(lock, 0);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// candidate queues (fp32 kernel).  The list of pixel j is owned by warp j/4: only the owner modifies it, so no
-// lock is needed and nobody ever waits for an insertion.  A warp that finds a candidate for a foreign pixel
-// pushes it (one 64-bit shared store: value | position<<2 | pixel-in-group) into the owner's ring; the owner
-// drains its ring at tile boundaries.  A slot is published by the store itself (sentinel = empty).
-// ------------------------------------------------------------------------------------------------------
-constexpr int kQCap = 64;                 // entries per owner ring (power of two)
-constexpr int kQShift = 6;
-
-struct Queues {
-    unsigned long long* q;   // [kWarps][kQCap]  low word: value bits | lap parity << 31, high word: position << 2 | pixel-in-group
-    int* tail;               // [kWarps] next slot to allocate (atomic)
-    int* head;               // [kWarps] first slot not yet consumed (written by the owner only)
-    int* done;               // [1] warps that have finished their tiles of the current item
-};
-
-// chi^2 accumulators are >= +0, so the sign bit of the value word is free: it carries the parity of the lap
-// (slot index / kQCap).  A slot is "ready" when its parity matches the consumer's lap - no reset store and no
-// fence are needed; rings start with parity 1 (not ready for lap 0).
-__device__ __forceinline__ void drain_own(const Queues& Q, int warp, int lane, int& my_head, Cand<CLEDB_PREC_FP32>* lists,
-                                          Rec<CLEDB_PREC_FP32>* recs, int k) {
-    const int t = *reinterpret_cast<volatile int*>(&Q.tail[warp]);
-    int h = my_head;
-    while (h != t) {
-        const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&Q.q[warp * kQCap + (h & (kQCap - 1))]);
-        const uint32_t bits = (uint32_t)w, packed = (uint32_t)(w >> 32);
-        // Allocated but not yet written: come back later.  NEVER wait here - the producer of this slot may itself be
-        // inside its own drain while it waits for ring space that only this warp can free (cyclic wait).
-        if ((bits >> 31) != (uint32_t)((h >> kQShift) & 1)) break;
-        ++h;
-        // publish at once: a producer whose slot is still beyond the ring waits for exactly this
-        if (lane == 0) *reinterpret_cast<volatile int*>(&Q.head[warp]) = h;
-        const int j = warp * 4 + (int)(packed & 3u);
-        list_insert<CLEDB_PREC_FP32>(lists + j * k, nullptr, reinterpret_cast<volatile float*>(&recs[j].tau), k,
-                                     __uint_as_float(bits & 0x7fffffffu), (int)(packed >> 2), lane, false);
-    }
-    my_head = h;
-}
-
-__device__ __forceinline__ void push_candidate(const Queues& Q, int owner, float v, int pos, int jj, int warp, int lane,
-                                               int& my_head, Cand<CLEDB_PREC_FP32>* lists, Rec<CLEDB_PREC_FP32>* recs, int k) {
-    int slot = 0;
-    if (lane == 0) slot = atomicAdd(&Q.tail[owner], 1);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    while (slot - *reinterpret_cast<volatile int*>(&Q.head[owner]) >= kQCap)
-        drain_own(Q, warp, lane, my_head, lists, recs, k);        // ring full: keep my own ring moving meanwhile
-    if (lane == 0) {   // one 64-bit store publishes the entry
-        const uint32_t lo = __float_as_uint(v) | ((uint32_t)((slot >> kQShift) & 1) << 31);
-        const unsigned long long w = ((unsigned long long)(((uint32_t)pos << 2) | (uint32_t)jj) << 32) | lo;
-        *reinterpret_cast<volatile unsigned long long*>(&Q.q[owner * kQCap + (slot & (kQCap - 1))]) = w;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -516,9 +455,16 @@ __device__ __forceinline__ Item make_item(const Plan& pl, const DbSlot* slots, i
 // ------------------------------------------------------------------------------------------------------
 // kernel 4: the search
 // ------------------------------------------------------------------------------------------------------
-template <int PREC> struct SmemLayout {
-    static constexpr int kRecBytes = (int)sizeof(Rec<PREC>) * kMaxP;
-    static constexpr int kListBytes = (int)sizeof(Cand<PREC>) * kMaxP * CLEDB_MAX_NSEARCH;
+constexpr int kCandCap = 128;     // candidate buffer entries per warp and tile
+constexpr int kListCap = 256;     // list entries per warp: pixels per item x nsearch <= 256
+
+template <int ENC, int PREC> struct KCfg {
+    static constexpr int kWpc = (ENC == CLEDB_ENC_I16) ? 8 : 6;       // independent warps per CTA (shared memory budget)
+    static constexpr int kTB = tile_bytes<ENC>();
+    static constexpr int kRecBytes = (kMaxP + 1) * (int)sizeof(Rec<PREC>);   // one spare record: prefetch overrun
+    static constexpr int kListBytes = kListCap * (int)sizeof(Cand<PREC>);
+    static constexpr int kCandBytes = kCandCap * 8;
+    static constexpr int kWarpBytes = kStages * kTB + kRecBytes + kListBytes + kCandBytes + kStages * 8 + 16;
 };
 
 // evaluate the lane's 8 entries against the pixel record in shared memory; returns the 8 values
@@ -546,284 +492,216 @@ __device__ __forceinline__ void eval_pixel(const Rec<PREC>* rec, const float (&d
             for (int c = 0; c < kNC; ++c) dd[c] = d[e][c] * scale[c];   // decoded database value (exact)
             v[e] = eval_fp64(dd, st, sig, c0);
         }
-        tau = *reinterpret_cast<const volatile double*>(&r->tau);
+        tau = r->tau;
     }
 }
 
+// exact, unhurried handling of one (tile, pixel): evaluate, insert every entry that beats the live threshold.
+// Used by the fp64 validation kernel for every step and by the fp32 kernel when a candidate buffer overflows.
 template <int ENC, int PREC>
-__global__ void __launch_bounds__(kThreads, PREC == CLEDB_PREC_FP32 ? 2 : 1)
+__device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, Cand<PREC>* list, const float (&d)[kEPL][kNC],
+                                           const float (&scale)[kNC], int base, int cnt_end, int k, int lane) {
+    using V = typename Val<PREC>::type;
+    V v[kEPL], tau;
+    eval_pixel<ENC, PREC>(rec, d, scale, v, tau);
+    uint32_t em = 0;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) em |= (v[e] <= tau && base + pos_in_tile<ENC>(lane, e) < cnt_end) ? (1u << e) : 0u;
+    uint32_t lanes = __ballot_sync(0xffffffffu, em != 0);
+    while (lanes) {
+        const int src = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        uint32_t m = __shfl_sync(0xffffffffu, em, src);
+        while (m) {
+            const int e = __ffs(m) - 1;
+            m &= m - 1;
+            V mine = v[0];                               // v[e] for a warp-uniform runtime e, kept in registers
+#pragma unroll
+            for (int q = 1; q < kEPL; ++q) mine = (e == q) ? v[q] : mine;
+            const V cv = __shfl_sync(0xffffffffu, mine, src);
+            list_insert<PREC>(list, &rec->tau, k, cv, base + pos_in_tile<ENC>(src, e), lane);   // re-checks against the list
+        }
+    }
+}
+
+// first tile of an item: exact top-k of its 256 entries by k rounds of warp-min selection
+template <int ENC, int PREC>
+__device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, Cand<PREC>* list, const float (&d)[kEPL][kNC],
+                                                const float (&scale)[kNC], int base, int cnt_end, int k, int lane) {
+    using V = typename Val<PREC>::type;
+    V v[kEPL], tau_unused;
+    eval_pixel<ENC, PREC>(rec, d, scale, v, tau_unused);
+    int ps[kEPL];
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) {
+        const int pos = base + pos_in_tile<ENC>(lane, e);
+        const bool ok = !isnan(v[e]) && pos < cnt_end;    // padding decodes to NaN
+        ps[e] = ok ? pos : 0x7fffffff;
+        if (!ok) v[e] = inf_of(V());
+    }
+    uint32_t used = 0;
+    V keep_v = inf_of(V());
+    int keep_p = -1;
+    for (int r = 0; r < k; ++r) {
+        V lm = inf_of(V());
+        int lp = 0x7fffffff;
+#pragma unroll
+        for (int e = 0; e < kEPL; ++e) {
+            const bool free_e = !((used >> e) & 1u);
+            if (free_e && (v[e] < lm || (v[e] == lm && ps[e] < lp))) { lm = v[e]; lp = ps[e]; }
+        }
+        const V gm = warp_min(lm);
+        const int gp = (int)__reduce_min_sync(0xffffffffu, (uint32_t)((lm == gm) ? lp : 0x7fffffff));
+        if (gp != 0x7fffffff) {
+#pragma unroll
+            for (int e = 0; e < kEPL; ++e)
+                if (ps[e] == gp) used |= 1u << e;
+        }
+        if (lane == r) { keep_v = gm; keep_p = (gp == 0x7fffffff) ? -1 : gp; }
+    }
+    if (lane < k) {
+        list[lane].v = keep_v;
+        list[lane].pos = keep_p;
+    }
+    if (lane == k - 1) rec->tau = keep_v;
+    __syncwarp();
+}
+
+template <int ENC, int PREC>
+__global__ void __launch_bounds__(KCfg<ENC, PREC>::kWpc * 32, PREC == CLEDB_PREC_FP32 ? 2 : 1)
 k_match(Plan pl, const DbSlot* __restrict__ slots) {
+    using C = KCfg<ENC, PREC>;
     using V = typename Val<PREC>::type;
     using CandT = Cand<PREC>;
     using RecT = Rec<PREC>;
-    constexpr int TB = tile_bytes<ENC>();
+    constexpr int TB = C::kTB;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* stages = smem;                                        // [kWarps][kStages][TB]
-    unsigned char* boot = stages + kWarps * kStages * TB;                // [TB] first tile of the item, all warps
-    RecT* recs = reinterpret_cast<RecT*>(boot + TB);                     // [kMaxP]
-    CandT* lists = reinterpret_cast<CandT*>(recs + kMaxP + 1);           // [kMaxP][k]  (one spare record: prefetch overrun)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + kMaxP * pl.k);  // [kWarps*kStages + 1]
-    int* locks = reinterpret_cast<int*>(bars + kWarps * kStages + 1);    // [kMaxP]
-    Queues Q;
-    Q.tail = locks + kMaxP;                                              // [kWarps]
-    Q.head = Q.tail + kWarps;                                            // [kWarps]
-    Q.done = Q.head + kWarps;                                            // [1] (+1 pad)
-    Q.q = reinterpret_cast<unsigned long long*>(Q.done + 2);             // [kWarps][kQCap]
-    int my_head = 0;
-    __shared__ Item s_item;
-    __shared__ int s_it;
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* stages = smem + (size_t)warp * C::kWarpBytes;                        // [kStages][TB]
+    RecT* recs = reinterpret_cast<RecT*>(stages + kStages * TB);                        // [kMaxP + 1]
+    CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);   // [npx][k]
+    uint2* cand = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);  // [kCandCap]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(cand) + C::kCandBytes);   // [kStages]
+    int* ccnt = reinterpret_cast<int*>(bars + kStages);
     const int k = pl.k;
-    uint64_t* my_bars = bars + warp * kStages;
-    uint64_t* boot_bar = bars + kWarps * kStages;
-    unsigned char* my_stages = stages + warp * kStages * TB;
-    uint32_t boot_phase = 0;
-    uint32_t stage_phase[kStages];
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) stage_phase[s] = 0;
+    uint32_t phase_bits = 0;
 
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kWarps * kStages + 1; ++i) mbar_init(&bars[i], 1);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
         fence_barrier_init();
     }
-    __syncthreads();
+    __syncwarp();
 
     for (;;) {
-        if (threadIdx.x == 0) {
-            const int it = atomicAdd(&pl.counters[0], 1);
-            s_it = it;
-            if (it < pl.counters[2]) s_item = make_item(pl, slots, it);
-        }
-        __syncthreads();
-        const int it = s_it;
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&pl.counters[0], 1);
+        it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= pl.counters[2]) break;
-        const Item im = s_item;
+        const Item im = make_item(pl, slots, it);
         const DbSlot& db = slots[im.slot];
         const unsigned char* gt = reinterpret_cast<const unsigned char*>(db.tiles) + (size_t)im.tile0 * TB;
         CandT* gout = reinterpret_cast<CandT*>(pl.plist) + (size_t)it * pl.P * k;
 
-        // ---- stage the item: pixel records, empty lists, first tile for the bootstrap, per-warp prefetch
-        const int nb = min(im.ntiles, kBootTiles);       // tiles handled by the bootstrap
-        if (threadIdx.x == 0 && im.ntiles > 0) {
-            mbar_expect_tx(boot_bar, TB);
-            tma_load_1d(boot, gt, TB, boot_bar);
-        }
+        // ---- stage the item: first tiles in flight, pixel records, empty lists
         if (lane == 0) {
 #pragma unroll
             for (int s = 0; s < kStages; ++s) {
-                const int t = nb + warp + s * kWarps;
-                if (t < im.ntiles) {
-                    mbar_expect_tx(&my_bars[s], TB);
-                    tma_load_1d(my_stages + s * TB, gt + (size_t)t * TB, TB, &my_bars[s]);
+                if (s < im.ntiles) {
+                    mbar_expect_tx(&bars[s], TB);
+                    tma_load_1d(stages + s * TB, gt + (size_t)s * TB, TB, &bars[s]);
                 }
             }
+            *ccnt = 0;
         }
-        for (int i = threadIdx.x; i < im.npx * (int)(sizeof(RecT) / 16); i += kThreads) {
+        for (int i = lane; i < im.npx * (int)(sizeof(RecT) / 16); i += 32) {
             const int j = i / (int)(sizeof(RecT) / 16), w = i % (int)(sizeof(RecT) / 16);
             const int p = pl.order[im.pix0 + j];
             reinterpret_cast<uint4*>(recs + j)[w] = reinterpret_cast<const uint4*>(reinterpret_cast<const RecT*>(pl.recs) + p)[w];
         }
-        for (int i = threadIdx.x; i < im.npx * k; i += kThreads) {
+        for (int i = lane; i < im.npx * k; i += 32) {
             lists[i].v = inf_of(V());
             lists[i].pos = -1;
         }
-        if (threadIdx.x < kMaxP) locks[threadIdx.x] = 0;
-        if (threadIdx.x < 2 * kWarps + 2) Q.tail[threadIdx.x] = 0;        // tail[], head[] and done are adjacent
-        for (int i = threadIdx.x; i < kWarps * kQCap; i += kThreads) Q.q[i] = 0x80000000ull;   // parity 1: not ready
-        my_head = 0;
-        __syncthreads();
+        __syncwarp();
 
         float scale[kNC];
 #pragma unroll
         for (int c = 0; c < kNC; ++c) scale[c] = db.scale[chi_comp(c)];
+        const uint32_t rec_base = smem_u32(recs);
 
         float d[kEPL][kNC];
-        // ---- bootstrap over the first nb tiles, owner-computes: warp w alone handles pixels 4w..4w+3 (the lists it
-        //      owns), so nothing is shared yet.  Tile 0: exact top-k by k rounds of warp-min selection.  Tiles 1..nb-1:
-        //      online insertion against the live threshold.  After ~2300 entries tau is tight enough that the main
-        //      loop's first round produces about one candidate per pixel and warp instead of eight.
-        for (int b = 0; b < nb; ++b) {
-            mbar_wait(boot_bar, boot_phase);
-            boot_phase ^= 1;
-            load_tile_regs<ENC>(boot, lane, d);
-            __syncthreads();                                   // every warp holds tile b in registers
-            if (threadIdx.x == 0 && b + 1 < nb) {              // fetch the next bootstrap tile while this one is ranked
-                mbar_expect_tx(boot_bar, TB);
-                tma_load_1d(boot, gt + (size_t)(b + 1) * TB, TB, boot_bar);
-            }
-            const int base = (im.tile0 + b) * kTile;
-            for (int j = warp * 4; j < min(im.npx, warp * 4 + 4); ++j) {
-                V v[kEPL], tau_unused;
-                eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau_unused);
-                if (b > 0) {
-#pragma unroll
-                    for (int e = 0; e < kEPL; ++e) {
-                        const int pos = base + pos_in_tile<ENC>(lane, e);
-                        const V tnow = *reinterpret_cast<volatile V*>(&recs[j].tau);
-                        uint32_t hits = __ballot_sync(0xffffffffu, v[e] <= tnow && pos < im.cnt_end);
-                        while (hits) {
-                            const int src = __ffs(hits) - 1;
-                            hits &= hits - 1;
-                            const V cv = __shfl_sync(0xffffffffu, v[e], src);
-                            list_insert<PREC>(lists + j * k, nullptr, reinterpret_cast<volatile V*>(&recs[j].tau), k, cv,
-                                              base + pos_in_tile<ENC>(src, e), lane, false);
-                        }
-                    }
-                    continue;
-                }
-                int ps[kEPL];
-#pragma unroll
-                for (int e = 0; e < kEPL; ++e) {
-                    const int pos = base + pos_in_tile<ENC>(lane, e);
-                    const bool ok = !isnan(v[e]) && pos < im.cnt_end;    // padding decodes to NaN
-                    ps[e] = ok ? pos : 0x7fffffff;
-                    if (!ok) v[e] = inf_of(V());
-                }
-                uint32_t used = 0;
-                V keep_v = inf_of(V());
-                int keep_p = -1;
-                for (int r = 0; r < k; ++r) {
-                    V lm = inf_of(V());
-                    int lp = 0x7fffffff;
-#pragma unroll
-                    for (int e = 0; e < kEPL; ++e) {
-                        const bool free_e = !((used >> e) & 1u);
-                        if (free_e && (v[e] < lm || (v[e] == lm && ps[e] < lp))) { lm = v[e]; lp = ps[e]; }
-                    }
-                    const V gm = warp_min(lm);
-                    const int gp = (int)__reduce_min_sync(0xffffffffu, (uint32_t)((lm == gm) ? lp : 0x7fffffff));
-                    if (gp != 0x7fffffff) {
-#pragma unroll
-                        for (int e = 0; e < kEPL; ++e)
-                            if (ps[e] == gp) used |= 1u << e;
-                    }
-                    if (lane == r) { keep_v = gm; keep_p = (gp == 0x7fffffff) ? -1 : gp; }
-                }
-                if (lane < k) {
-                    lists[j * k + lane].v = keep_v;
-                    lists[j * k + lane].pos = keep_p;
-                }
-                if (lane == k - 1) *const_cast<V*>(&recs[j].tau) = keep_v;
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-
-        // ---- main loop: this warp's tiles nb+warp, nb+warp+8, ...
-        const uint32_t rec_base = smem_u32(recs);
-        int iter = 0;
-        for (int t = nb + warp; t < im.ntiles; t += kWarps, ++iter) {
-            const int s = iter % kStages;
-            mbar_wait(&my_bars[s], stage_phase[s]);
-            stage_phase[s] ^= 1;
-            load_tile_regs<ENC>(my_stages + s * TB, lane, d);
+        for (int t = 0; t < im.ntiles; ++t) {
+            const int s = t % kStages;
+            mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            phase_bits ^= 1u << s;
+            load_tile_regs<ENC>(stages + s * TB, lane, d);
             __syncwarp();                         // every lane has its registers: the stage can be refilled
-            if (lane == 0) {
-                const int tn = t + kStages * kWarps;
-                if (tn < im.ntiles) {
-                    mbar_expect_tx(&my_bars[s], TB);
-                    tma_load_1d(my_stages + s * TB, gt + (size_t)tn * TB, TB, &my_bars[s]);
-                }
+            if (lane == 0 && t + kStages < im.ntiles) {
+                mbar_expect_tx(&bars[s], TB);
+                tma_load_1d(stages + s * TB, gt + (size_t)(t + kStages) * TB, TB, &bars[s]);
             }
             const int base = (im.tile0 + t) * kTile;
-            // fast pass: groups of 8 pixels without control flow.  Bit j of hmask = "one of my 8 entries may enter
-            // the list of pixel j".  Between groups the warp serves its own candidate ring so that tau stays fresh.
-            uint32_t hmask = 0;
-            if (PREC == CLEDB_PREC_FP32) {
+            if (t == 0) {
+                for (int j = 0; j < im.npx; ++j)
+                    bootstrap_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, k, lane);
+                continue;
+            }
+            if (PREC == CLEDB_PREC_FP32 && pl.dbg != 3) {
+                // fast pass: 80 FFMA per pixel.  A lane whose entry beats tau leaves the straight-line code for a
+                // moment and drops (value, pixel, slot in tile) into the warp's candidate buffer.
                 uint32_t ra = rec_base;
                 float4 n0 = lds128(ra), n1 = lds128(ra + 16), n2 = lds128(ra + 32);
-                for (int j0 = 0; j0 < im.npx; j0 += 8) {
-                    const int j1 = min(im.npx, j0 + 8);
 #pragma unroll 2
-                    for (int j = j0; j < j1; ++j) {
-                        const float4 x0 = n0, x1 = n1, x2 = n2;
-                        ra += (uint32_t)sizeof(RecT);
-                        n0 = lds128(ra); n1 = lds128(ra + 16); n2 = lds128(ra + 32);     // prefetch (recs has a spare slot)
-                        const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
-                        const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
-                        float v[kEPL];
-#pragma unroll
-                        for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
-                        const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
-                        hmask = (hmask << 1) | (m <= x2.w ? 1u : 0u);          // pixel j ends up at bit npx-1-j
-                    }
-                    if (*reinterpret_cast<volatile int*>(&Q.tail[warp]) != my_head)
-                        drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
-                                  reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
-                }
-            } else {
                 for (int j = 0; j < im.npx; ++j) {
-                    V v[kEPL], tau;
-                    eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau);
-                    const V m = fmin(fmin(fmin(v[0], v[1]), fmin(v[2], v[3])), fmin(fmin(v[4], v[5]), fmin(v[6], v[7])));
-                    hmask = (hmask << 1) | (m <= tau ? 1u : 0u);
-                }
-            }
-            // rare pass: pixels flagged by any lane are re-evaluated and their candidates handed to the list owner
-            uint32_t any = __reduce_or_sync(0xffffffffu, hmask);
-            if (any && pl.dbg != 2) {
-                while (any) {
-                    const int b = 31 - __clz(any);                       // highest bit first = lowest pixel first
-                    any &= ~(1u << b);
-                    const int j = im.npx - 1 - b;
-                    V v[kEPL], tau;
-                    eval_pixel<ENC, PREC>(recs + j, d, scale, v, tau);
-                    const V tnow = *reinterpret_cast<volatile V*>(&recs[j].tau);
-                    uint32_t em = 0;                                     // my entries that beat the threshold
+                    const float4 x0 = n0, x1 = n1, x2 = n2;
+                    ra += (uint32_t)sizeof(RecT);
+                    n0 = lds128(ra); n1 = lds128(ra + 16); n2 = lds128(ra + 32);     // prefetch (recs has a spare slot)
+                    const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
+                    const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
+                    float v[kEPL];
 #pragma unroll
-                    for (int e = 0; e < kEPL; ++e)
-                        em |= (v[e] <= tnow && base + pos_in_tile<ENC>(lane, e) < im.cnt_end) ? (1u << e) : 0u;
-                    uint32_t lanes = __ballot_sync(0xffffffffu, em != 0);
-                    while (lanes) {
-                        const int src = __ffs(lanes) - 1;
-                        lanes &= lanes - 1;
-                        uint32_t m = __shfl_sync(0xffffffffu, em, src);
-                        while (m) {
-                            const int e = __ffs(m) - 1;
-                            m &= m - 1;
-                            V mine = v[0];                               // v[e] for a warp-uniform runtime e, kept in registers
+                    for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
+                    const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
+                    if (m <= x2.w && pl.dbg != 2) {
 #pragma unroll
-                            for (int q = 1; q < kEPL; ++q) mine = (e == q) ? v[q] : mine;
-                            const V cv = __shfl_sync(0xffffffffu, mine, src);
-                            const int cp = base + pos_in_tile<ENC>(src, e);
-                            if (PREC == CLEDB_PREC_FP32) {
-                                // lists are owned by warp j/4: insert my own, queue the others (nobody waits)
-                                if ((j >> 2) == warp)
-                                    list_insert<PREC>(lists + j * k, nullptr, reinterpret_cast<volatile V*>(&recs[j].tau), k, cv, cp, lane, false);
-                                else
-                                    push_candidate(Q, j >> 2, (float)cv, cp, j & 3, warp, lane, my_head,
-                                                   reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
-                                                   reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
-                            } else {
-                                list_insert<PREC>(lists + j * k, &locks[j], reinterpret_cast<volatile V*>(&recs[j].tau), k, cv, cp, lane, true);
+                        for (int e = 0; e < kEPL; ++e) {
+                            if (v[e] <= x2.w) {
+                                const int sl = atomicAdd(ccnt, 1);
+                                if (sl < kCandCap) cand[sl] = make_uint2(__float_as_uint(v[e]), (uint32_t)((j << 8) | pos_in_tile<ENC>(lane, e)));
                             }
                         }
                     }
                 }
+                __syncwarp();
+                const int n = *reinterpret_cast<volatile int*>(ccnt);
+                if (n > 0) {
+                    if (n <= kCandCap) {
+                        for (int i = 0; i < n; ++i) {
+                            const unsigned long long cw = *reinterpret_cast<volatile unsigned long long*>(&cand[i]);
+                            const uint2 c = make_uint2((uint32_t)cw, (uint32_t)(cw >> 32));
+                            const int j = (int)(c.y >> 8), pos = base + (int)(c.y & 255u);
+                            if (pos < im.cnt_end)
+                                list_insert<PREC>(reinterpret_cast<CandT*>(lists) + j * k, reinterpret_cast<V*>(&recs[j].tau), k,
+                                                  (V)__uint_as_float(c.x), pos, lane);
+                        }
+                    } else {                      // buffer overflow (first tiles of an item): redo this tile exactly
+                        for (int j = 0; j < im.npx; ++j)
+                            slow_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, k, lane);
+                    }
+                    __syncwarp();
+                    if (lane == 0) *ccnt = 0;
+                    __syncwarp();
+                }
+            } else {
+                for (int j = 0; j < im.npx; ++j)
+                    slow_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, k, lane);
             }
         }
-        if (PREC == CLEDB_PREC_FP32) {
-            // A warp that is done with its tiles must keep serving its ring until every warp is done: a producer
-            // may be waiting for space in it (a plain __syncthreads here would deadlock against that wait).
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();        // my last ring entries are visible before I count as done
-                atomicAdd(Q.done, 1);
-            }
-            while (*reinterpret_cast<volatile int*>(Q.done) < kWarps)
-                drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
-                          reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
-            // every producer has fenced its last entry before counting itself done: what is left is complete
-            while (my_head != *reinterpret_cast<volatile int*>(&Q.tail[warp]))
-                drain_own(Q, warp, lane, my_head, reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(lists),
-                          reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs), k);
-        }
-        __syncthreads();
-        // ---- write the item's partial lists
-        for (int i = threadIdx.x; i < im.npx * k; i += kThreads) gout[i] = lists[i];
-        __syncthreads();
+        __syncwarp();
+        for (int i = lane; i < im.npx * k; i += 32) gout[i] = lists[i];
+        __syncwarp();
     }
 }
 
@@ -932,17 +810,15 @@ __global__ void __launch_bounds__(128) k_finalize(Plan pl, const DbSlot* __restr
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
-template <int ENC, int PREC> static size_t match_smem_bytes(int k) {
-    return (size_t)kWarps * kStages * tile_bytes<ENC>() + tile_bytes<ENC>() + sizeof(Rec<PREC>) * (kMaxP + 1) +
-           sizeof(Cand<PREC>) * kMaxP * k + sizeof(uint64_t) * (kWarps * kStages + 1) + sizeof(int) * (kMaxP + 2 * kWarps + 2) +
-           sizeof(uint2) * kWarps * kQCap + 16;
+template <int ENC, int PREC> static size_t match_smem_bytes(int) {
+    return (size_t)KCfg<ENC, PREC>::kWpc * KCfg<ENC, PREC>::kWarpBytes + 128;
 }
 
 template <int ENC, int PREC> static int configure_match(cledb_ctx* ctx, int k, int* occ_out, size_t* smem_out) {
     const size_t smem = match_smem_bytes<ENC, PREC>(k);
     CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_match<ENC, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CLEDB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_match<ENC, PREC>, kThreads, smem));
+    CLEDB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_match<ENC, PREC>, KCfg<ENC, PREC>::kWpc * 32, smem));
     if (occ < 1) { ctx->err = "search kernel does not fit on an SM"; return CLEDB_ERR_CUDA; }
     *occ_out = occ;
     *smem_out = smem;
@@ -981,11 +857,12 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, const float* sobs, const
     else rc = configure_match<CLEDB_ENC_F32, PREC>(ctx, pl.k, &occ, &smem);
     if (rc) return rc;
     const int64_t max_items = ((npix + pl.P - 1) / pl.P + pl.nkeys) * (int64_t)kParts * pl.split;
-    const int grid = (int)std::min<int64_t>((int64_t)ctx->prop.multiProcessorCount * occ, std::max<int64_t>(1, max_items));
+    const int wpc = enc == CLEDB_ENC_I16 ? KCfg<CLEDB_ENC_I16, PREC>::kWpc : KCfg<CLEDB_ENC_F32, PREC>::kWpc;
+    const int grid = (int)std::min<int64_t>((int64_t)ctx->prop.multiProcessorCount * occ, std::max<int64_t>(1, (max_items + wpc - 1) / wpc));
     const bool prof = ctx->prof_on && ctx->prof_used < (int)ctx->prof.size();
     if (prof) CLEDB_CUDA(ctx, cudaEventRecord(ctx->prof[ctx->prof_used].first, st));
-    if (enc == CLEDB_ENC_I16) k_match<CLEDB_ENC_I16, PREC><<<grid, kThreads, smem, st>>>(pl, ctx->d_slots);
-    else k_match<CLEDB_ENC_F32, PREC><<<grid, kThreads, smem, st>>>(pl, ctx->d_slots);
+    if (enc == CLEDB_ENC_I16) k_match<CLEDB_ENC_I16, PREC><<<grid, KCfg<CLEDB_ENC_I16, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
+    else k_match<CLEDB_ENC_F32, PREC><<<grid, KCfg<CLEDB_ENC_F32, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
     if (prof) {
         CLEDB_CUDA(ctx, cudaEventRecord(ctx->prof[ctx->prof_used].second, st));
         ctx->prof_used++;
@@ -1022,14 +899,21 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     pl.npix = npix;
     pl.mode = mode;
     pl.k = nsearch;
-    pl.P = std::max(1, std::min(ctx->pixels_per_item, kMaxP));
     pl.dbg = ctx->dbg;
-    pl.nkeys = ctx->slots_cap * kParts;
+    // Pixels per warp item.  Every warp streams the whole candidate list of its item, so more pixels per item
+    // amortise the tile loads better, while the number of items should fill the resident warps in whole rounds.
+    const int wpc_est = enc == CLEDB_ENC_I16 ? 8 : 6;
+    const int64_t wslots = (int64_t)ctx->prop.multiProcessorCount * std::max(1, ctx->occ) * wpc_est;
+    const int pmax = std::max(1, std::min(kMaxP, kListCap / nsearch));
+    if (ctx->pixels_per_item > 0) pl.P = std::min(ctx->pixels_per_item, pmax);
+    else {
+        const int64_t rounds = std::max<int64_t>(1, (npix + wslots * pmax - 1) / (wslots * pmax));
+        pl.P = (int)std::max<int64_t>(std::min(4, pmax), std::min<int64_t>(pmax, (npix + wslots * rounds - 1) / (wslots * rounds)));
+    }
     int split = ctx->split;
     if (split <= 0) {   // few pixels: cut the candidate lists so that the machine is still filled
         const int64_t tiles = (npix + pl.P - 1) / pl.P;
-        const int64_t want = 2ll * ctx->prop.multiProcessorCount * std::max(1, ctx->occ);
-        split = (int)std::min<int64_t>(8, std::max<int64_t>(1, want / std::max<int64_t>(1, tiles)));
+        split = (int)std::min<int64_t>(8, std::max<int64_t>(1, wslots / std::max<int64_t>(1, tiles)));
     }
     pl.split = std::min(split, 8);
     const size_t rec_sz = precision == CLEDB_PREC_FP32 ? sizeof(Rec<CLEDB_PREC_FP32>) : sizeof(Rec<CLEDB_PREC_FP64>);
