@@ -664,7 +664,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
 #pragma unroll
                     for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
                     const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
-                    if (m <= x2.w && pl.dbg != 2) {
+                    if (__builtin_expect(m <= x2.w && pl.dbg != 2, 0)) {
 #pragma unroll
                         for (int e = 0; e < kEPL; ++e) {
                             if (v[e] <= x2.w) {
@@ -900,6 +900,7 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     pl.mode = mode;
     pl.k = nsearch;
     pl.dbg = ctx->dbg;
+    pl.nkeys = ctx->slots_cap * kParts;
     // Pixels per warp item.  Every warp streams the whole candidate list of its item, so more pixels per item
     // amortise the tile loads better, while the number of items should fill the resident warps in whole rounds.
     const int wpc_est = enc == CLEDB_ENC_I16 ? 8 : 6;
