@@ -26,6 +26,8 @@ struct DbSlot {
     const void*    tiles;            // [ntiles_total][kNC][kTile] half bits (I16) or float (F32)
     const void*    vcomp;            // [npad][2]  V1, V2 in the same element type
     const int32_t* perm;             // [npad] original row index of each stored entry, -1 = padding
+    const int32_t* row_pos;          // [n] stored position of an original row, -1 = never a candidate (NaN V1)
+    const int32_t* row_kpos;         // [n] rank of a row among the rows of its own sign class (original order)
     const int32_t* kept_rank;        // [n] rank of a row among rows with non-NaN V1 (NULL if none is NaN)
     int64_t        n;                // rows of the original database
     int32_t        part_tile0[kParts];   // first tile of each sign class
@@ -56,6 +58,7 @@ struct HostDb {
     int32_t* d_perm = nullptr;
     int32_t* d_invperm = nullptr;
     int32_t* d_kept_rank = nullptr;
+    int32_t* d_row_kpos = nullptr;
     int64_t  npad = 0, nnan = 0, bytes = 0;
     int      shift[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };

@@ -131,6 +131,7 @@ static void free_db(HostDb& h) {
     if (h.d_perm) cudaFree(h.d_perm);
     if (h.d_invperm) cudaFree(h.d_invperm);
     if (h.d_kept_rank) cudaFree(h.d_kept_rank);
+    if (h.d_row_kpos) cudaFree(h.d_row_kpos);
     h = HostDb();
     std::memset(&h.slot, 0, sizeof(DbSlot));
 }
@@ -236,7 +237,25 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
         }
     }
     if (nnan > 0) kept_rank.assign(n, -1);
-    int64_t cur[kParts] = {pos0[0], pos0[1], pos0[2]};
+    std::vector<int32_t> row_kpos(n, -1);
+    // Stored order inside a sign class: a golden-ratio stride permutation of the original order.  The original
+    // order walks (gx, phi, theta), so chi^2 is smooth along it and improvements of the running threshold would
+    // arrive in bursts; with the stride order every tile samples the whole class evenly, the threshold converges
+    // as for a random order (about nsearch*ln(N/nsearch) insertions per pixel) and insertions spread out in time.
+    // Ties still resolve to the lowest ORIGINAL row: the top-k lists carry original indices.
+    int64_t stride[kParts];
+    for (int q = 0; q < kParts; ++q) {
+        const int64_t c = cnt[q];
+        int64_t st = 1;
+        if (c > 2) {
+            st = (int64_t)(0.6180339887498949 * (double)c);
+            if (st < 1) st = 1;
+            auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+            while (gcd(st, c) != 1) ++st;
+        }
+        stride[q] = st;
+    }
+    int64_t seen[kParts] = {0, 0, 0};
     int32_t zero_bits[kParts] = {0, 0, 0};
     int64_t rank = 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -244,29 +263,31 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
         if (q < 0) continue;
         if (nnan > 0) kept_rank[i] = (int32_t)rank;
         ++rank;
-        const int64_t pos = cur[q]++;
+        const int64_t r = seen[q]++;                                  // rank inside the class, original order
+        row_kpos[i] = (int32_t)r;
+        const int64_t pos = pos0[q] + (int64_t)(((__int128)r * stride[q]) % cnt[q]);
         perm[pos] = (int32_t)i;
         invperm[i] = (int32_t)pos;
         const int64_t tl = pos / kTile, in = pos % kTile;
-        const float* r = db + i * 8;
+        const float* rr = db + i * 8;
         for (int c = 0; c < kNC; ++c) {
             const int oc = chi_comp(c);
             const size_t e = ((size_t)tl * kNC + c) * kTile + in;
             if (encoding == CLEDB_ENC_I16) {
-                const uint16_t code = f32_to_f16_bits_rn(std::ldexp(r[oc], h.shift[oc]));
+                const uint16_t code = f32_to_f16_bits_rn(std::ldexp(rr[oc], h.shift[oc]));
                 reinterpret_cast<uint16_t*>(tiles.data())[e] = code;
                 if ((code & 0x7fffu) == 0) zero_bits[q] |= 1 << c;
             } else {
-                reinterpret_cast<float*>(tiles.data())[e] = r[oc];
-                if (r[oc] == 0.f) zero_bits[q] |= 1 << c;
+                reinterpret_cast<float*>(tiles.data())[e] = rr[oc];
+                if (rr[oc] == 0.f) zero_bits[q] |= 1 << c;
             }
         }
         for (int w = 0; w < 2; ++w) {
             const int oc = w ? 7 : 3;
             if (encoding == CLEDB_ENC_I16)
-                reinterpret_cast<uint16_t*>(vcomp.data())[pos * 2 + w] = f32_to_f16_bits_rn(std::ldexp(r[oc], h.shift[oc]));
+                reinterpret_cast<uint16_t*>(vcomp.data())[pos * 2 + w] = f32_to_f16_bits_rn(std::ldexp(rr[oc], h.shift[oc]));
             else
-                reinterpret_cast<float*>(vcomp.data())[pos * 2 + w] = r[oc];
+                reinterpret_cast<float*>(vcomp.data())[pos * 2 + w] = rr[oc];
         }
     }
     for (int q = 0; q < kParts; ++q) h.slot.part_zero[q] = zero_bits[q];
@@ -283,16 +304,20 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
     if (cudaMalloc(&h.d_perm, perm.size() * 4) != cudaSuccess) return fail("out of device memory (perm)");
     if (cudaMalloc(&h.d_invperm, invperm.size() * 4) != cudaSuccess) return fail("out of device memory (invperm)");
     if (nnan > 0 && cudaMalloc(&h.d_kept_rank, kept_rank.size() * 4) != cudaSuccess) return fail("out of device memory (rank)");
+    if (cudaMalloc(&h.d_row_kpos, row_kpos.size() * 4) != cudaSuccess) return fail("out of device memory (kpos)");
     CLEDB_CUDA(ctx, cudaMemcpy(h.d_tiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
     CLEDB_CUDA(ctx, cudaMemcpy(h.d_vcomp, vcomp.data(), vcomp.size(), cudaMemcpyHostToDevice));
     CLEDB_CUDA(ctx, cudaMemcpy(h.d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
     CLEDB_CUDA(ctx, cudaMemcpy(h.d_invperm, invperm.data(), invperm.size() * 4, cudaMemcpyHostToDevice));
     if (nnan > 0) CLEDB_CUDA(ctx, cudaMemcpy(h.d_kept_rank, kept_rank.data(), kept_rank.size() * 4, cudaMemcpyHostToDevice));
-    h.bytes = (int64_t)(tiles.size() + vcomp.size() + perm.size() * 4 + invperm.size() * 4 + kept_rank.size() * 4);
+    CLEDB_CUDA(ctx, cudaMemcpy(h.d_row_kpos, row_kpos.data(), row_kpos.size() * 4, cudaMemcpyHostToDevice));
+    h.bytes = (int64_t)(tiles.size() + vcomp.size() + perm.size() * 4 + invperm.size() * 4 + kept_rank.size() * 4 + row_kpos.size() * 4);
     h.slot.tiles = h.d_tiles;
     h.slot.vcomp = h.d_vcomp;
     h.slot.perm = h.d_perm;
     h.slot.kept_rank = h.d_kept_rank;
+    h.slot.row_pos = h.d_invperm;
+    h.slot.row_kpos = h.d_row_kpos;
     h.slot.n = n;
     h.slot.encoding = encoding;
     h.slot.live = 1;

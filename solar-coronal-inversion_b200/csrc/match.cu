@@ -88,6 +88,7 @@ template <> struct __align__(16) Rec<CLEDB_PREC_FP64> {
 template <int PREC> struct Val { using type = float; };
 template <> struct Val<CLEDB_PREC_FP64> { using type = double; };
 
+// one top-k list element: value and ORIGINAL row index (-1 = empty slot)
 template <int PREC> struct __align__(8) Cand { float v; int32_t pos; };
 template <> struct __align__(16) Cand<CLEDB_PREC_FP64> { double v; int32_t pos; int32_t pad; };
 
@@ -500,7 +501,8 @@ __device__ __forceinline__ void eval_pixel(const Rec<PREC>* rec, const float (&d
 // Used by the fp64 validation kernel for every step and by the fp32 kernel when a candidate buffer overflows.
 template <int ENC, int PREC>
 __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, Cand<PREC>* list, const float (&d)[kEPL][kNC],
-                                           const float (&scale)[kNC], int base, int cnt_end, int k, int lane) {
+                                           const float (&scale)[kNC], int base, int cnt_end, const int32_t* __restrict__ perm,
+                                           int k, int lane) {
     using V = typename Val<PREC>::type;
     V v[kEPL], tau;
     eval_pixel<ENC, PREC>(rec, d, scale, v, tau);
@@ -519,7 +521,7 @@ __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, Cand<PREC>* list, con
 #pragma unroll
             for (int q = 1; q < kEPL; ++q) mine = (e == q) ? v[q] : mine;
             const V cv = __shfl_sync(0xffffffffu, mine, src);
-            list_insert<PREC>(list, &rec->tau, k, cv, base + pos_in_tile<ENC>(src, e), lane);   // re-checks against the list
+            list_insert<PREC>(list, &rec->tau, k, cv, perm[base + pos_in_tile<ENC>(src, e)], lane);   // re-checks against the list
         }
     }
 }
@@ -527,7 +529,8 @@ __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, Cand<PREC>* list, con
 // first tile of an item: exact top-k of its 256 entries by k rounds of warp-min selection
 template <int ENC, int PREC>
 __device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, Cand<PREC>* list, const float (&d)[kEPL][kNC],
-                                                const float (&scale)[kNC], int base, int cnt_end, int k, int lane) {
+                                                const float (&scale)[kNC], int base, int cnt_end, const int32_t* __restrict__ perm,
+                                                int k, int lane) {
     using V = typename Val<PREC>::type;
     V v[kEPL], tau_unused;
     eval_pixel<ENC, PREC>(rec, d, scale, v, tau_unused);
@@ -536,7 +539,7 @@ __device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, Cand<PREC>* list
     for (int e = 0; e < kEPL; ++e) {
         const int pos = base + pos_in_tile<ENC>(lane, e);
         const bool ok = !isnan(v[e]) && pos < cnt_end;    // padding decodes to NaN
-        ps[e] = ok ? pos : 0x7fffffff;
+        ps[e] = ok ? perm[pos] : 0x7fffffff;              // ties go to the lowest original row
         if (!ok) v[e] = inf_of(V());
     }
     uint32_t used = 0;
@@ -645,7 +648,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
             const int base = (im.tile0 + t) * kTile;
             if (t == 0) {
                 for (int j = 0; j < im.npx; ++j)
-                    bootstrap_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, k, lane);
+                    bootstrap_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
                 continue;
             }
             if (PREC == CLEDB_PREC_FP32 && pl.dbg != 3) {
@@ -684,11 +687,11 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                             const int j = (int)(c.y >> 8), pos = base + (int)(c.y & 255u);
                             if (pos < im.cnt_end)
                                 list_insert<PREC>(reinterpret_cast<CandT*>(lists) + j * k, reinterpret_cast<V*>(&recs[j].tau), k,
-                                                  (V)__uint_as_float(c.x), pos, lane);
+                                                  (V)__uint_as_float(c.x), db.perm[pos], lane);
                         }
                     } else {                      // buffer overflow (first tiles of an item): redo this tile exactly
                         for (int j = 0; j < im.npx; ++j)
-                            slow_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, k, lane);
+                            slow_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
                     }
                     __syncwarp();
                     if (lane == 0) *ccnt = 0;
@@ -696,7 +699,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                 }
             } else {
                 for (int j = 0; j < im.npx; ++j)
-                    slow_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, k, lane);
+                    slow_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
             }
         }
         __syncwarp();
@@ -776,8 +779,8 @@ __global__ void __launch_bounds__(128) k_finalize(Plan pl, const DbSlot* __restr
             if (head[s] >= k) continue;
             const CandT c = base[s * sub_stride + head[s]];
             if (c.pos < 0) { head[s] = (unsigned char)k; continue; }
-            const int oi = db.perm[c.pos];
-            if (best < 0 || c.v < bv || (c.v == bv && oi < bidx)) { best = s; bv = c.v; bpos = c.pos; bidx = oi; }
+            const int oi = c.pos;                          // lists carry original row indices
+            if (best < 0 || c.v < bv || (c.v == bv && oi < bidx)) { best = s; bv = c.v; bidx = oi; }
         }
         const int64_t o = p * k + r;
         if (best < 0) {
@@ -789,12 +792,13 @@ __global__ void __launch_bounds__(128) k_finalize(Plan pl, const DbSlot* __restr
             continue;
         }
         head[best]++;
+        bpos = db.row_pos[bidx];
         idx_out[o] = bidx;
         const double chi = (PREC == CLEDB_PREC_FP32) ? (double)(0.5f * (float)bv) : (double)bv;
         chi_out[o] = (float)chi;
         if (chi64_out) chi64_out[o] = chi;
         if (kpos_out) {
-            if (pl.mode == CLEDB_MODE_IQUV) kpos_out[o] = bpos - db.part_tile0[cls] * kTile;
+            if (pl.mode == CLEDB_MODE_IQUV) kpos_out[o] = db.row_kpos[bidx];
             else kpos_out[o] = db.kept_rank ? db.kept_rank[bidx] : bidx;
         }
         if (rows_out) {
