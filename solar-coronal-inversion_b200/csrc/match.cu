@@ -462,7 +462,7 @@ constexpr int kListCap = 256;     // list entries per warp: pixels per item x ns
 template <int ENC, int PREC> struct KCfg {
     static constexpr int kWpc = (ENC == CLEDB_ENC_I16) ? 8 : 6;       // independent warps per CTA (shared memory budget)
     static constexpr int kTB = tile_bytes<ENC>();
-    static constexpr int kRecBytes = (kMaxP + 1) * (int)sizeof(Rec<PREC>);   // one spare record: prefetch overrun
+    static constexpr int kRecBytes = (kMaxP + 2) * (int)sizeof(Rec<PREC>);   // two spare records: prefetch overrun
     static constexpr int kListBytes = kListCap * (int)sizeof(Cand<PREC>);
     static constexpr int kCandBytes = kCandCap * 8;
     static constexpr int kWarpBytes = kStages * kTB + kRecBytes + kListBytes + kCandBytes + kStages * 8 + 16;
@@ -582,7 +582,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* stages = smem + (size_t)warp * C::kWarpBytes;                        // [kStages][TB]
-    RecT* recs = reinterpret_cast<RecT*>(stages + kStages * TB);                        // [kMaxP + 1]
+    RecT* recs = reinterpret_cast<RecT*>(stages + kStages * TB);                        // [kMaxP + 2]
     CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);   // [npx][k]
     uint2* cand = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);  // [kCandCap]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(cand) + C::kCandBytes);   // [kStages]
@@ -652,27 +652,43 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                 continue;
             }
             if (PREC == CLEDB_PREC_FP32 && pl.dbg != 3) {
-                // fast pass: 80 FFMA per pixel.  A lane whose entry beats tau leaves the straight-line code for a
-                // moment and drops (value, pixel, slot in tile) into the warp's candidate buffer.
+                // fast pass, two pixels per trip: 160 FFMA, then ONE test.  A lane whose entry beats a threshold
+                // leaves the straight-line code for a moment and drops (value, pixel, slot in tile) into the warp's
+                // candidate buffer.  Pairing lets the second pixel's FFMAs cover the first pixel's min/compare chain.
                 uint32_t ra = rec_base;
-                float4 n0 = lds128(ra), n1 = lds128(ra + 16), n2 = lds128(ra + 32);
-#pragma unroll 2
-                for (int j = 0; j < im.npx; ++j) {
-                    const float4 x0 = n0, x1 = n1, x2 = n2;
-                    ra += (uint32_t)sizeof(RecT);
-                    n0 = lds128(ra); n1 = lds128(ra + 16); n2 = lds128(ra + 32);     // prefetch (recs has a spare slot)
-                    const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
-                    const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
-                    float v[kEPL];
+                float4 a0 = lds128(ra), a1 = lds128(ra + 16), a2 = lds128(ra + 32);
+#pragma unroll 1
+                for (int j = 0; j < im.npx; j += 2) {
+                    const float4 b0 = lds128(ra + 48), b1 = lds128(ra + 64), b2 = lds128(ra + 80);
+                    float va[kEPL], vb[kEPL];
+                    {
+                        const float ca[kNC] = {a0.x, a0.y, a0.z, a0.w, a1.x};
+                        const float cn[kNC] = {a1.y, a1.z, a1.w, a2.x, a2.y};
 #pragma unroll
-                    for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
-                    const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
-                    if (__builtin_expect(m <= x2.w && pl.dbg != 2, 0)) {
+                        for (int e = 0; e < kEPL; ++e) va[e] = eval_fp32(d[e], ca, cn, a2.z);
+                    }
+                    const float tau_a = a2.w;
+                    ra += 2u * (uint32_t)sizeof(RecT);
+                    a0 = lds128(ra); a1 = lds128(ra + 16); a2 = lds128(ra + 32);     // next pair (recs has two spare slots)
+                    {
+                        const float ca[kNC] = {b0.x, b0.y, b0.z, b0.w, b1.x};
+                        const float cn[kNC] = {b1.y, b1.z, b1.w, b2.x, b2.y};
+#pragma unroll
+                        for (int e = 0; e < kEPL; ++e) vb[e] = eval_fp32(d[e], ca, cn, b2.z);
+                    }
+                    const float tau_b = (j + 1 < im.npx) ? b2.w : -1.0f;          // odd pixel count: the spare never fires
+                    const float ma = fminf(fminf(fminf(va[0], va[1]), fminf(va[2], va[3])), fminf(fminf(va[4], va[5]), fminf(va[6], va[7])));
+                    const float mb = fminf(fminf(fminf(vb[0], vb[1]), fminf(vb[2], vb[3])), fminf(fminf(vb[4], vb[5]), fminf(vb[6], vb[7])));
+                    if (__builtin_expect((ma <= tau_a || mb <= tau_b) && pl.dbg != 2, 0)) {
 #pragma unroll
                         for (int e = 0; e < kEPL; ++e) {
-                            if (v[e] <= x2.w) {
+                            if (va[e] <= tau_a) {
                                 const int sl = atomicAdd(ccnt, 1);
-                                if (sl < kCandCap) cand[sl] = make_uint2(__float_as_uint(v[e]), (uint32_t)((j << 8) | pos_in_tile<ENC>(lane, e)));
+                                if (sl < kCandCap) cand[sl] = make_uint2(__float_as_uint(va[e]), (uint32_t)((j << 8) | pos_in_tile<ENC>(lane, e)));
+                            }
+                            if (vb[e] <= tau_b) {
+                                const int sl = atomicAdd(ccnt, 1);
+                                if (sl < kCandCap) cand[sl] = make_uint2(__float_as_uint(vb[e]), (uint32_t)(((j + 1) << 8) | pos_in_tile<ENC>(lane, e)));
                             }
                         }
                     }
