@@ -88,7 +88,7 @@ template <> struct __align__(16) Rec<CLEDB_PREC_FP64> {
 template <int PREC> struct Val { using type = float; };
 template <> struct Val<CLEDB_PREC_FP64> { using type = double; };
 
-// one top-k list element: value and ORIGINAL row index (-1 = empty slot)
+// one top-k list element: value and position in the stored (stride-permuted) layout, -1 = empty slot
 template <int PREC> struct __align__(8) Cand { float v; int32_t pos; };
 template <> struct __align__(16) Cand<CLEDB_PREC_FP64> { double v; int32_t pos; int32_t pad; };
 
@@ -178,33 +178,39 @@ __device__ __forceinline__ float  inf_of(float)  { return CUDART_INF_F; }
 __device__ __forceinline__ double inf_of(double) { return CUDART_INF; }
 
 // Insert candidate (v, pos) into the sorted list of one pixel.  Called by a whole warp with warp-uniform
-// arguments; the list belongs to this warp alone.  Lane j < k holds list element j; order is lexicographic
-// (value, position) so that equal chi^2 resolve to the lowest database row (NumPy argmin = first occurrence).
+// arguments; the list belongs to this warp alone.  Lane j < k holds list element j.  Order: ascending value; equal
+// values by ascending ORIGINAL row (NumPy argmin = first occurrence).  Lists store positions in the stride-permuted
+// layout, so the original rows are looked up (perm[]) only in the rare case that values are exactly equal.
 template <int PREC>
 __device__ __forceinline__ void list_insert(Cand<PREC>* list, typename Val<PREC>::type* tau, int k,
-                                            typename Val<PREC>::type v, int pos, int lane) {
+                                            typename Val<PREC>::type v, int pos, const int32_t* __restrict__ perm, int lane) {
     using V = typename Val<PREC>::type;
     V lv = inf_of(V());
-    uint32_t lp = 0xffffffffu;
+    int lp = -1;
     if (lane < k) {
         lv = list[lane].v;
-        lp = (uint32_t)list[lane].pos;
+        lp = list[lane].pos;
     }
-    const bool before = (lane < k) && (lv < v || (lv == v && lp < (uint32_t)pos));
+    bool before = (lane < k) && (lv < v);
+    const bool equal = (lane < k) && (lv == v) && lp >= 0;
+    if (__any_sync(0xffffffffu, equal)) {
+        const int cand_row = perm[pos];
+        if (equal) before = perm[lp] < cand_row;
+    }
     const int q = __popc(__ballot_sync(0xffffffffu, before));   // elements that stay in front (a prefix: list is sorted)
     if (q < k) {
         const V uv = __shfl_up_sync(0xffffffffu, lv, 1);
-        const uint32_t up = __shfl_up_sync(0xffffffffu, lp, 1);
+        const int up = __shfl_up_sync(0xffffffffu, lp, 1);
         if (lane == q) {
             lv = v;
-            lp = (uint32_t)pos;
+            lp = pos;
         } else if (lane > q) {
             lv = uv;
             lp = up;
         }
         if (lane >= q && lane < k) {
             list[lane].v = lv;
-            list[lane].pos = (int32_t)lp;
+            list[lane].pos = lp;
         }
         if (lane == k - 1) *tau = lv;
     }
@@ -456,16 +462,14 @@ __device__ __forceinline__ Item make_item(const Plan& pl, const DbSlot* slots, i
 // ------------------------------------------------------------------------------------------------------
 // kernel 4: the search
 // ------------------------------------------------------------------------------------------------------
-constexpr int kCandCap = 128;     // candidate buffer entries per warp and tile
 constexpr int kListCap = 256;     // list entries per warp: pixels per item x nsearch <= 256
 
 template <int ENC, int PREC> struct KCfg {
     static constexpr int kWpc = (ENC == CLEDB_ENC_I16) ? 8 : 6;       // independent warps per CTA (shared memory budget)
     static constexpr int kTB = tile_bytes<ENC>();
-    static constexpr int kRecBytes = (kMaxP + 2) * (int)sizeof(Rec<PREC>);   // two spare records: prefetch overrun
+    static constexpr int kRecBytes = (kMaxP + 1) * (int)sizeof(Rec<PREC>);   // one spare record: prefetch overrun
     static constexpr int kListBytes = kListCap * (int)sizeof(Cand<PREC>);
-    static constexpr int kCandBytes = kCandCap * 8;
-    static constexpr int kWarpBytes = kStages * kTB + kRecBytes + kListBytes + kCandBytes + kStages * 8 + 16;
+    static constexpr int kWarpBytes = kStages * kTB + kRecBytes + kListBytes + kStages * 8 + 16;
 };
 
 // evaluate the lane's 8 entries against the pixel record in shared memory; returns the 8 values
@@ -508,7 +512,7 @@ __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, Cand<PREC>* list, con
     eval_pixel<ENC, PREC>(rec, d, scale, v, tau);
     uint32_t em = 0;
 #pragma unroll
-    for (int e = 0; e < kEPL; ++e) em |= (v[e] <= tau && base + pos_in_tile<ENC>(lane, e) < cnt_end) ? (1u << e) : 0u;
+    for (int e = 0; e < kEPL; ++e) em |= (v[e] <= tau) ? (1u << e) : 0u;        // padding evaluates to NaN: never true
     uint32_t lanes = __ballot_sync(0xffffffffu, em != 0);
     while (lanes) {
         const int src = __ffs(lanes) - 1;
@@ -521,7 +525,8 @@ __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, Cand<PREC>* list, con
 #pragma unroll
             for (int q = 1; q < kEPL; ++q) mine = (e == q) ? v[q] : mine;
             const V cv = __shfl_sync(0xffffffffu, mine, src);
-            list_insert<PREC>(list, &rec->tau, k, cv, perm[base + pos_in_tile<ENC>(src, e)], lane);   // re-checks against the list
+            const int cp = base + pos_in_tile<ENC>(src, e);
+            if (cp < cnt_end) list_insert<PREC>(list, &rec->tau, k, cv, cp, perm, lane);   // re-checks against the list
         }
     }
 }
@@ -529,7 +534,7 @@ __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, Cand<PREC>* list, con
 // first tile of an item: exact top-k of its 256 entries by k rounds of warp-min selection
 template <int ENC, int PREC>
 __device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, Cand<PREC>* list, const float (&d)[kEPL][kNC],
-                                                const float (&scale)[kNC], int base, int cnt_end, const int32_t* __restrict__ perm,
+                                                const float (&scale)[kNC], int base, int cnt_end, const int (&rows)[kEPL],
                                                 int k, int lane) {
     using V = typename Val<PREC>::type;
     V v[kEPL], tau_unused;
@@ -539,7 +544,7 @@ __device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, Cand<PREC>* list
     for (int e = 0; e < kEPL; ++e) {
         const int pos = base + pos_in_tile<ENC>(lane, e);
         const bool ok = !isnan(v[e]) && pos < cnt_end;    // padding decodes to NaN
-        ps[e] = ok ? perm[pos] : 0x7fffffff;              // ties go to the lowest original row
+        ps[e] = ok ? rows[e] : 0x7fffffff;                // ties go to the lowest original row
         if (!ok) v[e] = inf_of(V());
     }
     uint32_t used = 0;
@@ -560,7 +565,12 @@ __device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, Cand<PREC>* list
             for (int e = 0; e < kEPL; ++e)
                 if (ps[e] == gp) used |= 1u << e;
         }
-        if (lane == r) { keep_v = gm; keep_p = (gp == 0x7fffffff) ? -1 : gp; }
+        int won_pos = -1;                                   // stored position of the winner (the owner lane knows it)
+#pragma unroll
+        for (int e = 0; e < kEPL; ++e)
+            if (ps[e] == gp && gp != 0x7fffffff) won_pos = base + pos_in_tile<ENC>(lane, e);
+        won_pos = (int)__reduce_max_sync(0xffffffffu, won_pos);
+        if (lane == r) { keep_v = gm; keep_p = won_pos; }
     }
     if (lane < k) {
         list[lane].v = keep_v;
@@ -582,11 +592,9 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* stages = smem + (size_t)warp * C::kWarpBytes;                        // [kStages][TB]
-    RecT* recs = reinterpret_cast<RecT*>(stages + kStages * TB);                        // [kMaxP + 2]
+    RecT* recs = reinterpret_cast<RecT*>(stages + kStages * TB);                        // [kMaxP + 1]
     CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);   // [npx][k]
-    uint2* cand = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);  // [kCandCap]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(cand) + C::kCandBytes);   // [kStages]
-    int* ccnt = reinterpret_cast<int*>(bars + kStages);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);   // [kStages]
     const int k = pl.k;
     uint32_t phase_bits = 0;
 
@@ -616,7 +624,6 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                     tma_load_1d(stages + s * TB, gt + (size_t)s * TB, TB, &bars[s]);
                 }
             }
-            *ccnt = 0;
         }
         for (int i = lane; i < im.npx * (int)(sizeof(RecT) / 16); i += 32) {
             const int j = i / (int)(sizeof(RecT) / 16), w = i % (int)(sizeof(RecT) / 16);
@@ -647,71 +654,43 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
             }
             const int base = (im.tile0 + t) * kTile;
             if (t == 0) {
+                int rows[kEPL];                  // original rows of my 8 entries of the first tile (tie-break only)
+#pragma unroll
+                for (int e = 0; e < kEPL; ++e) {
+                    const int pos = base + pos_in_tile<ENC>(lane, e);
+                    rows[e] = pos < im.cnt_end ? db.perm[pos] : 0x7fffffff;
+                }
                 for (int j = 0; j < im.npx; ++j)
-                    bootstrap_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
+                    bootstrap_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, rows, k, lane);
                 continue;
             }
             if (PREC == CLEDB_PREC_FP32 && pl.dbg != 3) {
-                // fast pass, two pixels per trip: 160 FFMA, then ONE test.  A lane whose entry beats a threshold
-                // leaves the straight-line code for a moment and drops (value, pixel, slot in tile) into the warp's
-                // candidate buffer.  Pairing lets the second pixel's FFMAs cover the first pixel's min/compare chain.
+                // fast pass: 80 FFMA per pixel, no control flow.  Bit (npx-1-j) of hmask = "one of my 8 entries beats the
+                // threshold of pixel j".
+                uint32_t hmask = 0;
                 uint32_t ra = rec_base;
-                float4 a0 = lds128(ra), a1 = lds128(ra + 16), a2 = lds128(ra + 32);
-#pragma unroll 1
-                for (int j = 0; j < im.npx; j += 2) {
-                    const float4 b0 = lds128(ra + 48), b1 = lds128(ra + 64), b2 = lds128(ra + 80);
-                    float va[kEPL], vb[kEPL];
-                    {
-                        const float ca[kNC] = {a0.x, a0.y, a0.z, a0.w, a1.x};
-                        const float cn[kNC] = {a1.y, a1.z, a1.w, a2.x, a2.y};
+                float4 n0 = lds128(ra), n1 = lds128(ra + 16), n2 = lds128(ra + 32);
+#pragma unroll 2
+                for (int j = 0; j < im.npx; ++j) {
+                    const float4 x0 = n0, x1 = n1, x2 = n2;
+                    ra += (uint32_t)sizeof(RecT);
+                    n0 = lds128(ra); n1 = lds128(ra + 16); n2 = lds128(ra + 32);     // prefetch (recs has a spare slot)
+                    const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
+                    const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
+                    float v[kEPL];
 #pragma unroll
-                        for (int e = 0; e < kEPL; ++e) va[e] = eval_fp32(d[e], ca, cn, a2.z);
-                    }
-                    const float tau_a = a2.w;
-                    ra += 2u * (uint32_t)sizeof(RecT);
-                    a0 = lds128(ra); a1 = lds128(ra + 16); a2 = lds128(ra + 32);     // next pair (recs has two spare slots)
-                    {
-                        const float ca[kNC] = {b0.x, b0.y, b0.z, b0.w, b1.x};
-                        const float cn[kNC] = {b1.y, b1.z, b1.w, b2.x, b2.y};
-#pragma unroll
-                        for (int e = 0; e < kEPL; ++e) vb[e] = eval_fp32(d[e], ca, cn, b2.z);
-                    }
-                    const float tau_b = (j + 1 < im.npx) ? b2.w : -1.0f;          // odd pixel count: the spare never fires
-                    const float ma = fminf(fminf(fminf(va[0], va[1]), fminf(va[2], va[3])), fminf(fminf(va[4], va[5]), fminf(va[6], va[7])));
-                    const float mb = fminf(fminf(fminf(vb[0], vb[1]), fminf(vb[2], vb[3])), fminf(fminf(vb[4], vb[5]), fminf(vb[6], vb[7])));
-                    if (__builtin_expect((ma <= tau_a || mb <= tau_b) && pl.dbg != 2, 0)) {
-#pragma unroll
-                        for (int e = 0; e < kEPL; ++e) {
-                            if (va[e] <= tau_a) {
-                                const int sl = atomicAdd(ccnt, 1);
-                                if (sl < kCandCap) cand[sl] = make_uint2(__float_as_uint(va[e]), (uint32_t)((j << 8) | pos_in_tile<ENC>(lane, e)));
-                            }
-                            if (vb[e] <= tau_b) {
-                                const int sl = atomicAdd(ccnt, 1);
-                                if (sl < kCandCap) cand[sl] = make_uint2(__float_as_uint(vb[e]), (uint32_t)(((j + 1) << 8) | pos_in_tile<ENC>(lane, e)));
-                            }
-                        }
-                    }
+                    for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
+                    const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
+                    hmask = (hmask << 1) | (m <= x2.w ? 1u : 0u);
                 }
-                __syncwarp();
-                const int n = *reinterpret_cast<volatile int*>(ccnt);
-                if (n > 0) {
-                    if (n <= kCandCap) {
-                        for (int i = 0; i < n; ++i) {
-                            const unsigned long long cw = *reinterpret_cast<volatile unsigned long long*>(&cand[i]);
-                            const uint2 c = make_uint2((uint32_t)cw, (uint32_t)(cw >> 32));
-                            const int j = (int)(c.y >> 8), pos = base + (int)(c.y & 255u);
-                            if (pos < im.cnt_end)
-                                list_insert<PREC>(reinterpret_cast<CandT*>(lists) + j * k, reinterpret_cast<V*>(&recs[j].tau), k,
-                                                  (V)__uint_as_float(c.x), db.perm[pos], lane);
-                        }
-                    } else {                      // buffer overflow (first tiles of an item): redo this tile exactly
-                        for (int j = 0; j < im.npx; ++j)
-                            slow_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
-                    }
-                    __syncwarp();
-                    if (lane == 0) *ccnt = 0;
-                    __syncwarp();
+                // rare pass: pixels flagged by any lane are evaluated again and their candidates inserted at once, so
+                // the threshold is exact before the pixel is visited for the next tile
+                uint32_t any = pl.dbg == 2 ? 0u : __reduce_or_sync(0xffffffffu, hmask);
+                while (any) {
+                    const int b = 31 - __clz(any);
+                    any &= ~(1u << b);
+                    const int j = im.npx - 1 - b;
+                    slow_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
                 }
             } else {
                 for (int j = 0; j < im.npx; ++j)
@@ -795,8 +774,8 @@ __global__ void __launch_bounds__(128) k_finalize(Plan pl, const DbSlot* __restr
             if (head[s] >= k) continue;
             const CandT c = base[s * sub_stride + head[s]];
             if (c.pos < 0) { head[s] = (unsigned char)k; continue; }
-            const int oi = c.pos;                          // lists carry original row indices
-            if (best < 0 || c.v < bv || (c.v == bv && oi < bidx)) { best = s; bv = c.v; bidx = oi; }
+            const int oi = db.perm[c.pos];                 // lists carry stored positions; ties go to the lowest original row
+            if (best < 0 || c.v < bv || (c.v == bv && oi < bidx)) { best = s; bv = c.v; bpos = c.pos; bidx = oi; }
         }
         const int64_t o = p * k + r;
         if (best < 0) {
@@ -808,7 +787,6 @@ __global__ void __launch_bounds__(128) k_finalize(Plan pl, const DbSlot* __restr
             continue;
         }
         head[best]++;
-        bpos = db.row_pos[bidx];
         idx_out[o] = bidx;
         const double chi = (PREC == CLEDB_PREC_FP32) ? (double)(0.5f * (float)bv) : (double)bv;
         chi_out[o] = (float)chi;
