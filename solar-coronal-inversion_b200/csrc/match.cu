@@ -146,6 +146,31 @@ __device__ __forceinline__ float eval_fp32(const float (&d)[kNC], const float (&
     }
     return acc;
 }
+// The same arithmetic for two entries at once with the packed FP32 FMA of sm_100 (fma.rn.f32x2, FFMA2 in SASS): one
+// issue slot per two FMAs.  The coefficients are scalars; ptxas encodes pack(a, a) as a broadcast .F32 operand.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void eval_fp32_pair(const float (&d0)[kNC], const float (&d1)[kNC], const float (&a)[kNC],
+                                               const float (&nb)[kNC], float c0, float& v0, float& v1) {
+    unsigned long long acc = pack2(c0, c0);
+#pragma unroll
+    for (int c = 0; c < kNC; ++c) {
+        const unsigned long long r = fma2(pack2(d0[c], d1[c]), pack2(a[c], a[c]), pack2(nb[c], nb[c]));
+        acc = fma2(r, r, acc);
+    }
+    unpack2(acc, v0, v1);
+}
 // fp64 validation: float32 subtract and divide, float64 weight/square, NumPy's pairwise order over the 8 terms
 // ((t0+t1)+(t2+t3))+((t4+t5)+(t6+t7)) with t3 = t7 = +0, /2, round to 15 decimals as rint(x*1e15)/1e15
 // (CLEDB_PROC.py:989-1005).  d must already be the decoded database value.
@@ -679,7 +704,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                     const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
                     float v[kEPL];
 #pragma unroll
-                    for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
+                    for (int e = 0; e < kEPL; e += 2) eval_fp32_pair(d[e], d[e + 1], a, nb, x2.z, v[e], v[e + 1]);
                     const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
                     hmask = (hmask << 1) | (m <= x2.w ? 1u : 0u);
                 }
