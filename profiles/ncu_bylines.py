@@ -31,3 +31,10 @@ print('# %s: %.4e warp instructions, %d stall samples' % (rep.split('/')[-1], to
 data.sort(key=lambda r: -num(r[ii]))
 for r in data[:top]:
     print('%5s inst %6.2f%% samp %6.2f%%  %s' % (r[0], num(r[ii]) / tot * 100, num(r[si]) / ts * 100, r[1].strip()[:120]))
+
+# optional: share per named line range, e.g.  name:lo-hi,lo-hi  as extra arguments
+for spec in sys.argv[3:]:
+    name, rngs = spec.split(':')
+    rr = [tuple(int(x) for x in r.split('-')) for r in rngs.split(',')]
+    sel = [r for r in data if any(lo <= int(r[0]) <= hi for lo, hi in rr)]
+    print('range %-14s inst %6.2f%% samp %6.2f%%' % (name, sum(num(r[ii]) for r in sel) / tot * 100, sum(num(r[si]) for r in sel) / ts * 100))
