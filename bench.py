@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dbg', type=int, default=0, help='kernel timing experiment (results invalid)')
+    ap.add_argument('--ppi', type=int, default=0, help='tuning: pixels per warp item (0 = library default)')
+    ap.add_argument('--split', type=int, default=0, help='tuning: chunks per candidate list (0 = library default)')
     return ap.parse_args()
 
 
@@ -178,6 +180,8 @@ def main():
     ctx = native.Context(local)
     ctx.db_put(0, db, args.encoding)
     props = ctx.device_props()
+    if args.ppi or args.split:
+        ctx.set_tuning(args.ppi, args.split)
     if args.dbg:
         ctx.set_tuning(-args.dbg, 0)
     npix = args.nx * args.nx

@@ -14,7 +14,8 @@
  *   - "host" entry points take C-contiguous host buffers (pageable or pinned), copy in, run, copy out and
  *     return when the results are in the output buffers.  "_dev" entry points take device pointers that are
  *     valid on the context's device and enqueue on the given cudaStream_t (passed as void*; NULL = the
- *     context's own stream) without synchronising.
+ *     context's own stream) without waiting for the results.  (cledb_match_dev synchronises that stream once
+ *     internally, after its classification kernel, to size its work items from the bucket counts.)
  *   - all arrays are row-major; float = IEEE binary32.
  */
 #ifndef CLEDB_B200_H

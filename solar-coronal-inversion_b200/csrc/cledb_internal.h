@@ -83,7 +83,11 @@ struct cledb_ctx {
     int slots_cap = 0, id_cap = 0;
     bool tables_dirty = true;
     cledb::Workspace ws;                           // search workspace (grown on demand)
+    cledb::Workspace ws2;                          // partial top-k lists of the search (sized once the work shape is known)
     cledb::Workspace io;                           // staging for the host entry points
+    int32_t* h_cnt = nullptr;                      // pinned host copy of the bucket sizes
+    size_t h_cnt_cap = 0;
+    int last_P = 0, last_split = 0;                // work shape of the last search
     int64_t launches = 0;
     int pixels_per_item = 0;                      // 0 = choose from the pixel count
     int split = 0;

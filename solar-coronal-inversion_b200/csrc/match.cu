@@ -74,9 +74,17 @@ template <int PREC> struct Rec;
 template <> struct __align__(16) Rec<CLEDB_PREC_FP32> {
     float a[kNC];
     float nb[kNC];
-    float c0;    // constant component-0 term ((1 - s~_0)/sigma_0)^2, 0 for IQUV
+    float cm;    // in HBM: c0 = constant component-0 term ((1 - s~_0)/sigma_0)^2, 0 for IQUV.  In shared memory:
+                 // c0 - tau*(1 + 2^-19), the start value of the flagging accumulators (c0 itself moves to a side array)
     float tau;   // running threshold: k-th best value so far (same units as the accumulators)
 };
+// Flagging without a min tree: the hot loop accumulates v' = (c0 - tau_m) + sum r^2 with tau_m = tau*(1 + 2^-19), so
+// that "some entry may beat the threshold" is the OR of the sign bits of the eight v'.  The 32-ulp margin covers the
+// rounding of the two different summation chains (each at most 6 half-ulps of max(v, tau)): v <= tau implies v' < 0.
+// Flagged pixels are re-evaluated exactly (accumulators started at c0) before anything is inserted.
+__device__ __forceinline__ float flag_start(float c0, float tau) {
+    return c0 - fmaxf(fmaf(tau, 1.9073486328125e-06f, tau), 1e-37f);
+}
 // fp64 validation: the reference's operation order, needs s~ and sigma themselves
 template <> struct __align__(16) Rec<CLEDB_PREC_FP64> {
     float  st[kNC];
@@ -171,6 +179,12 @@ __device__ __forceinline__ void eval_fp32_pair(const float (&d0)[kNC], const flo
     }
     unpack2(acc, v0, v1);
 }
+// all 8 entries of a lane, bit-identical to eval_fp32 per entry
+__device__ __forceinline__ void eval_fp32_all(const float (&d)[kEPL][kNC], const float (&a)[kNC], const float (&nb)[kNC], float c0,
+                                              float (&v)[kEPL]) {
+#pragma unroll
+    for (int e = 0; e < kEPL; e += 2) eval_fp32_pair(d[e], d[e + 1], a, nb, c0, v[e], v[e + 1]);
+}
 // fp64 validation: float32 subtract and divide, float64 weight/square, NumPy's pairwise order over the 8 terms
 // ((t0+t1)+(t2+t3))+((t4+t5)+(t6+t7)) with t3 = t7 = +0, /2, round to 15 decimals as rint(x*1e15)/1e15
 // (CLEDB_PROC.py:989-1005).  d must already be the decoded database value.
@@ -206,8 +220,15 @@ __device__ __forceinline__ double inf_of(double) { return CUDART_INF; }
 // arguments; the list belongs to this warp alone.  Lane j < k holds list element j.  Order: ascending value; equal
 // values by ascending ORIGINAL row (NumPy argmin = first occurrence).  Lists store positions in the stride-permuted
 // layout, so the original rows are looked up (perm[]) only in the rare case that values are exactly equal.
+template <int PREC> __device__ __forceinline__ void set_tau(Rec<PREC>* rec, float c0, typename Val<PREC>::type tau);
+template <> __device__ __forceinline__ void set_tau<CLEDB_PREC_FP32>(Rec<CLEDB_PREC_FP32>* rec, float c0, float tau) {
+    rec->tau = tau;
+    rec->cm = flag_start(c0, tau);
+}
+template <> __device__ __forceinline__ void set_tau<CLEDB_PREC_FP64>(Rec<CLEDB_PREC_FP64>* rec, float, double tau) { rec->tau = tau; }
+
 template <int PREC>
-__device__ __forceinline__ void list_insert(Cand<PREC>* list, typename Val<PREC>::type* tau, int k,
+__device__ __forceinline__ void list_insert(Cand<PREC>* list, Rec<PREC>* rec, float c0, int k,
                                             typename Val<PREC>::type v, int pos, const int32_t* __restrict__ perm, int lane) {
     using V = typename Val<PREC>::type;
     V lv = inf_of(V());
@@ -237,7 +258,7 @@ __device__ __forceinline__ void list_insert(Cand<PREC>* list, typename Val<PREC>
             list[lane].v = lv;
             list[lane].pos = lp;
         }
-        if (lane == k - 1) *tau = lv;
+        if (lane == k - 1) set_tau<PREC>(rec, c0, lv);
     }
     __syncwarp();
 }
@@ -369,7 +390,7 @@ __global__ void __launch_bounds__(256) k_classify(Plan pl, const float* __restri
             r.nb[c] = (float)(-(double)a * (double)st[oc]);
             r.a[c] = a * db.scale[oc];                           // fold the int16 block exponent (exact)
         }
-        r.c0 = (float)c0;
+        r.cm = (float)c0;                                      // c0 in HBM, see Rec
         r.tau = CUDART_INF_F;
         *reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(rec) = r;
     } else {
@@ -494,20 +515,23 @@ template <int ENC, int PREC> struct KCfg {
     static constexpr int kTB = tile_bytes<ENC>();
     static constexpr int kRecBytes = (kMaxP + 1) * (int)sizeof(Rec<PREC>);   // one spare record: prefetch overrun
     static constexpr int kListBytes = kListCap * (int)sizeof(Cand<PREC>);
-    static constexpr int kWarpBytes = kStages * kTB + kRecBytes + kListBytes + kStages * 8 + 16;
+    static constexpr int kC0Bytes = ((kMaxP + 3) / 4) * 16;                    // c0 of the item's pixels (fp32 kernel)
+    static constexpr int kWarpBytes = kStages * kTB + kRecBytes + kListBytes + kStages * 8 + 16 + kC0Bytes;
 };
 
 // evaluate the lane's 8 entries against the pixel record in shared memory; returns the 8 values
 template <int ENC, int PREC>
-__device__ __forceinline__ void eval_pixel(const Rec<PREC>* rec, const float (&d)[kEPL][kNC], const float (&scale)[kNC],
+__device__ __forceinline__ void eval_pixel(const Rec<PREC>* rec, float c0f, const float (&d)[kEPL][kNC], const float (&scale)[kNC],
                                            typename Val<PREC>::type (&v)[kEPL], typename Val<PREC>::type& tau) {
     if (PREC == CLEDB_PREC_FP32) {
         const float4* rp = reinterpret_cast<const float4*>(rec);
         const float4 x0 = rp[0], x1 = rp[1], x2 = rp[2];          // three broadcast LDS.128
         const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
         const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
+        float vf[kEPL];
+        eval_fp32_all(d, a, nb, c0f, vf);
 #pragma unroll
-        for (int e = 0; e < kEPL; ++e) v[e] = eval_fp32(d[e], a, nb, x2.z);
+        for (int e = 0; e < kEPL; ++e) v[e] = vf[e];
         tau = x2.w;
     } else {
         const Rec<CLEDB_PREC_FP64>* r = reinterpret_cast<const Rec<CLEDB_PREC_FP64>*>(rec);
@@ -529,12 +553,12 @@ __device__ __forceinline__ void eval_pixel(const Rec<PREC>* rec, const float (&d
 // exact, unhurried handling of one (tile, pixel): evaluate, insert every entry that beats the live threshold.
 // Used by the fp64 validation kernel for every step and by the fp32 kernel when a candidate buffer overflows.
 template <int ENC, int PREC>
-__device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, Cand<PREC>* list, const float (&d)[kEPL][kNC],
+__device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, float c0f, Cand<PREC>* list, const float (&d)[kEPL][kNC],
                                            const float (&scale)[kNC], int base, int cnt_end, const int32_t* __restrict__ perm,
                                            int k, int lane) {
     using V = typename Val<PREC>::type;
     V v[kEPL], tau;
-    eval_pixel<ENC, PREC>(rec, d, scale, v, tau);
+    eval_pixel<ENC, PREC>(rec, c0f, d, scale, v, tau);
     uint32_t em = 0;
 #pragma unroll
     for (int e = 0; e < kEPL; ++e) em |= (v[e] <= tau) ? (1u << e) : 0u;        // padding evaluates to NaN: never true
@@ -551,19 +575,19 @@ __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, Cand<PREC>* list, con
             for (int q = 1; q < kEPL; ++q) mine = (e == q) ? v[q] : mine;
             const V cv = __shfl_sync(0xffffffffu, mine, src);
             const int cp = base + pos_in_tile<ENC>(src, e);
-            if (cp < cnt_end) list_insert<PREC>(list, &rec->tau, k, cv, cp, perm, lane);   // re-checks against the list
+            if (cp < cnt_end) list_insert<PREC>(list, rec, c0f, k, cv, cp, perm, lane);   // re-checks against the list
         }
     }
 }
 
 // first tile of an item: exact top-k of its 256 entries by k rounds of warp-min selection
 template <int ENC, int PREC>
-__device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, Cand<PREC>* list, const float (&d)[kEPL][kNC],
+__device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, float c0f, Cand<PREC>* list, const float (&d)[kEPL][kNC],
                                                 const float (&scale)[kNC], int base, int cnt_end, const int (&rows)[kEPL],
                                                 int k, int lane) {
     using V = typename Val<PREC>::type;
     V v[kEPL], tau_unused;
-    eval_pixel<ENC, PREC>(rec, d, scale, v, tau_unused);
+    eval_pixel<ENC, PREC>(rec, c0f, d, scale, v, tau_unused);
     int ps[kEPL];
 #pragma unroll
     for (int e = 0; e < kEPL; ++e) {
@@ -601,7 +625,7 @@ __device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, Cand<PREC>* list
         list[lane].v = keep_v;
         list[lane].pos = keep_p;
     }
-    if (lane == k - 1) rec->tau = keep_v;
+    if (lane == k - 1) set_tau<PREC>(rec, c0f, keep_v);
     __syncwarp();
 }
 
@@ -620,6 +644,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
     RecT* recs = reinterpret_cast<RecT*>(stages + kStages * TB);                        // [kMaxP + 1]
     CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);   // [npx][k]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);   // [kStages]
+    float* c0s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + kStages * 8 + 16);         // [kMaxP]
     const int k = pl.k;
     uint32_t phase_bits = 0;
 
@@ -660,6 +685,14 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
             lists[i].pos = -1;
         }
         __syncwarp();
+        if (PREC == CLEDB_PREC_FP32) {          // c0 moves to the side array; the record slot holds the flagging start value
+            for (int j = lane; j < im.npx; j += 32) {
+                Rec<CLEDB_PREC_FP32>* r = reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(recs) + j;
+                c0s[j] = r->cm;
+                r->cm = -CUDART_INF_F;
+            }
+            __syncwarp();
+        }
 
         float scale[kNC];
 #pragma unroll
@@ -667,6 +700,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
         const uint32_t rec_base = smem_u32(recs);
 
         float d[kEPL][kNC];
+        bool exact_only = false;
         for (int t = 0; t < im.ntiles; ++t) {
             const int s = t % kStages;
             mbar_wait(&bars[s], (phase_bits >> s) & 1u);
@@ -685,13 +719,19 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                     const int pos = base + pos_in_tile<ENC>(lane, e);
                     rows[e] = pos < im.cnt_end ? db.perm[pos] : 0x7fffffff;
                 }
-                for (int j = 0; j < im.npx; ++j)
-                    bootstrap_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, rows, k, lane);
+                bool unfilled = false;            // a list that the first tile could not fill keeps tau = inf
+                for (int j = 0; j < im.npx; ++j) {
+                    bootstrap_pixel<ENC, PREC>(recs + j, PREC == CLEDB_PREC_FP32 ? c0s[j] : 0.f, lists + j * k, d, scale, base,
+                                               im.cnt_end, rows, k, lane);
+                    unfilled |= !(recs[j].tau < inf_of(V()));
+                }
+                exact_only = unfilled;
                 continue;
             }
-            if (PREC == CLEDB_PREC_FP32 && pl.dbg != 3) {
-                // fast pass: 80 FFMA per pixel, no control flow.  Bit (npx-1-j) of hmask = "one of my 8 entries beats the
-                // threshold of pixel j".
+            if (PREC == CLEDB_PREC_FP32 && pl.dbg != 3 && !exact_only) {
+                // fast pass: 40 packed FMAs per pixel, no control flow, no min tree.  The accumulators start at
+                // c0 - tau*(1 + 2^-19), so the OR of the sign bits says "one of my 8 entries may beat the threshold of
+                // pixel j"; one funnel shift moves that bit into bit (npx-1-j) of hmask.
                 uint32_t hmask = 0;
                 uint32_t ra = rec_base;
                 float4 n0 = lds128(ra), n1 = lds128(ra + 16), n2 = lds128(ra + 32);
@@ -703,10 +743,11 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                     const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
                     const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
                     float v[kEPL];
-#pragma unroll
-                    for (int e = 0; e < kEPL; e += 2) eval_fp32_pair(d[e], d[e + 1], a, nb, x2.z, v[e], v[e + 1]);
-                    const float m = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
-                    hmask = (hmask << 1) | (m <= x2.w ? 1u : 0u);
+                    eval_fp32_all(d, a, nb, x2.z, v);
+                    const uint32_t sg = ((__float_as_uint(v[0]) | __float_as_uint(v[1]) | __float_as_uint(v[2])) |
+                                         (__float_as_uint(v[3]) | __float_as_uint(v[4]) | __float_as_uint(v[5]))) |
+                                        (__float_as_uint(v[6]) | __float_as_uint(v[7]));
+                    hmask = __funnelshift_l(sg, hmask, 1);
                 }
                 // rare pass: pixels flagged by any lane are evaluated again and their candidates inserted at once, so
                 // the threshold is exact before the pixel is visited for the next tile
@@ -715,11 +756,12 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                     const int b = 31 - __clz(any);
                     any &= ~(1u << b);
                     const int j = im.npx - 1 - b;
-                    slow_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
+                    slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
                 }
             } else {
                 for (int j = 0; j < im.npx; ++j)
-                    slow_pixel<ENC, PREC>(recs + j, lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
+                    slow_pixel<ENC, PREC>(recs + j, PREC == CLEDB_PREC_FP32 ? c0s[j] : 0.f, lists + j * k, d, scale, base,
+                                          im.cnt_end, db.perm, k, lane);
             }
         }
         __syncwarp();
@@ -863,23 +905,82 @@ int match_occupancy(cledb_ctx* ctx) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Work-shape choice once the bucket sizes are known (host side, after the classify kernel): pixels per warp item P and
+// chunks per candidate list.  Model, in units of one (pixel, tile) step of the hot loop: an item of P pixels over T tiles
+// costs T*(P + c_tile) + P*c_boot + P*k*ln(T+1)*c_event; with no more items than resident warps the kernel lasts as long
+// as its longest item, otherwise the warps pull items from a queue: the work spreads evenly, plus a penalty for a partly
+// filled last round (constants fitted to B200 timings of the 256x256 map at P = 9..32, profiles/r01_tuning.txt).
+static void choose_shape(cledb_ctx* ctx, const int32_t* cnt, int nkeys, int mode, int k, int64_t wslots, int pmax, int* P_out,
+                         int* split_out) {
+    const double c_tile = 2.5, c_boot = 5.0, c_event = 2.5;
+    double best = 1e300;
+    int bp = pmax, bs = 1;
+    const int p_lo = ctx->pixels_per_item > 0 ? std::min(ctx->pixels_per_item, pmax) : 1, p_hi = ctx->pixels_per_item > 0 ? p_lo : pmax;
+    const int s_lo = ctx->split > 0 ? ctx->split : 1, s_hi = ctx->split > 0 ? ctx->split : 8;
+    for (int P = p_hi; P >= p_lo; --P) {
+        for (int split = s_lo; split <= s_hi; ++split) {
+            double work = 0.0, longest = 0.0;
+            int64_t items = 0;
+            for (int key = 0; key < nkeys; ++key) {
+                const int c = cnt[key];
+                if (c <= 0) continue;
+                const DbSlot& db = ctx->dbs[key / kParts].slot;
+                const int64_t ptiles = (c + P - 1) / P;
+                for (int q = 0; q < kParts; ++q) {
+                    if (mode == CLEDB_MODE_IQUV ? q != key % kParts : db.part_cnt[q] == 0) continue;
+                    const double T = std::max(1.0, (double)db.part_ntiles[q] / split);
+                    const double cost = T * (P + c_tile) + P * c_boot + P * k * std::log(T + 1.0) * c_event;
+                    work += cost * ptiles * split;
+                    items += ptiles * split;
+                    longest = std::max(longest, cost);
+                }
+            }
+            if (items == 0) continue;
+            const double rounds = (double)items / (double)wslots, f = rounds - std::floor(rounds);
+            const double span = items <= wslots ? longest : work / (double)wslots + 0.8 * f * (1.0 - f) * work / (double)items;
+            if (span < best * 0.999) { best = span; bp = P; bs = split; }
+        }
+    }
+    *P_out = bp;
+    *split_out = bs;
+}
+
 template <int PREC>
-static int run_match(cledb_ctx* ctx, int enc, Plan& pl, const float* sobs, const float* snr, const int32_t* db_id,
-                     int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out, float* rows_out,
-                     int64_t* ncand_out, cudaStream_t st) {
+static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax, const float* sobs, const float* snr,
+                     const int32_t* db_id, int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out,
+                     float* rows_out, int64_t* ncand_out, cudaStream_t st) {
     const int64_t npix = pl.npix;
     const int nb = (int)((npix + 255) / 256);
     k_classify<PREC><<<nb, 256, 0, st>>>(pl, sobs, snr, db_id, ctx->d_slots, ctx->d_slot_of_id, ctx->id_cap);
+    ctx->launches += 1;
+    // ---- the bucket sizes come back to the host (a few hundred bytes, one stream synchronisation) and fix the work shape
+    if ((int)ctx->h_cnt_cap < pl.nkeys) {
+        if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
+        ctx->h_cnt = nullptr;
+        CLEDB_CUDA(ctx, cudaMallocHost(&ctx->h_cnt, sizeof(int32_t) * pl.nkeys));
+        ctx->h_cnt_cap = pl.nkeys;
+    }
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(ctx->h_cnt, pl.cnt, sizeof(int32_t) * pl.nkeys, cudaMemcpyDeviceToHost, st));
+    CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
+    choose_shape(ctx, ctx->h_cnt, std::min<int>(pl.nkeys, (int)ctx->dbs.size() * kParts), pl.mode, pl.k, wslots, pmax, &pl.P, &pl.split);
+    int64_t tiles_of_pixels = 0;
+    for (int key = 0; key < pl.nkeys; ++key) tiles_of_pixels += (ctx->h_cnt[key] + pl.P - 1) / pl.P;
+    ctx->last_P = pl.P;
+    ctx->last_split = pl.split;
+    const size_t cand_sz = sizeof(Cand<PREC>);
+    const int64_t max_items = tiles_of_pixels * (int64_t)(pl.mode == CLEDB_MODE_IQUV ? 1 : kParts) * pl.split;
+    int rc = ensure_workspace(ctx, ctx->ws2, std::max<size_t>(256, (size_t)max_items * pl.P * pl.k * cand_sz));
+    if (rc) return rc;
+    pl.plist = ctx->ws2.ptr;
+
     k_scan<<<1, 1024, 0, st>>>(pl, ctx->d_slots);
     k_scatter<<<nb, 256, 0, st>>>(pl);
-    ctx->launches += 3;
+    ctx->launches += 2;
     int occ = 0;
     size_t smem = 0;
-    int rc;
     if (enc == CLEDB_ENC_I16) rc = configure_match<CLEDB_ENC_I16, PREC>(ctx, pl.k, &occ, &smem);
     else rc = configure_match<CLEDB_ENC_F32, PREC>(ctx, pl.k, &occ, &smem);
     if (rc) return rc;
-    const int64_t max_items = ((npix + pl.P - 1) / pl.P + pl.nkeys) * (int64_t)kParts * pl.split;
     const int wpc = enc == CLEDB_ENC_I16 ? KCfg<CLEDB_ENC_I16, PREC>::kWpc : KCfg<CLEDB_ENC_F32, PREC>::kWpc;
     const int grid = (int)std::min<int64_t>((int64_t)ctx->prop.multiProcessorCount * occ, std::max<int64_t>(1, (max_items + wpc - 1) / wpc));
     const bool prof = ctx->prof_on && ctx->prof_used < (int)ctx->prof.size();
@@ -924,31 +1025,21 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     pl.k = nsearch;
     pl.dbg = ctx->dbg;
     pl.nkeys = ctx->slots_cap * kParts;
-    // Pixels per warp item.  Every warp streams the whole candidate list of its item, so more pixels per item
-    // amortise the tile loads better, while the number of items should fill the resident warps in whole rounds.
-    const int wpc_est = enc == CLEDB_ENC_I16 ? 8 : 6;
-    const int64_t wslots = (int64_t)ctx->prop.multiProcessorCount * std::max(1, ctx->occ) * wpc_est;
+    // Every warp streams the whole candidate list of its item past the item's pixels: more pixels per item amortise the
+    // tile loads better, while the number of items should fill the resident warps in whole rounds (choose_shape).
+    const int wpc_est = precision == CLEDB_PREC_FP32
+                            ? (enc == CLEDB_ENC_I16 ? KCfg<CLEDB_ENC_I16, CLEDB_PREC_FP32>::kWpc : KCfg<CLEDB_ENC_F32, CLEDB_PREC_FP32>::kWpc)
+                            : (enc == CLEDB_ENC_I16 ? KCfg<CLEDB_ENC_I16, CLEDB_PREC_FP64>::kWpc : KCfg<CLEDB_ENC_F32, CLEDB_PREC_FP64>::kWpc);
+    int occ = ctx->occ;
+    if (precision == CLEDB_PREC_FP64) occ = 1;
+    const int64_t wslots = (int64_t)ctx->prop.multiProcessorCount * std::max(1, occ) * wpc_est;
     const int pmax = std::max(1, std::min(kMaxP, kListCap / nsearch));
-    if (ctx->pixels_per_item > 0) pl.P = std::min(ctx->pixels_per_item, pmax);
-    else {
-        const int64_t rounds = std::max<int64_t>(1, (npix + wslots * pmax - 1) / (wslots * pmax));
-        pl.P = (int)std::max<int64_t>(std::min(4, pmax), std::min<int64_t>(pmax, (npix + wslots * rounds - 1) / (wslots * rounds)));
-    }
-    int split = ctx->split;
-    if (split <= 0) {   // few pixels: cut the candidate lists so that the machine is still filled
-        const int64_t tiles = (npix + pl.P - 1) / pl.P;
-        split = (int)std::min<int64_t>(8, std::max<int64_t>(1, wslots / std::max<int64_t>(1, tiles)));
-    }
-    pl.split = std::min(split, 8);
     const size_t rec_sz = precision == CLEDB_PREC_FP32 ? sizeof(Rec<CLEDB_PREC_FP32>) : sizeof(Rec<CLEDB_PREC_FP64>);
-    const size_t cand_sz = precision == CLEDB_PREC_FP32 ? sizeof(Cand<CLEDB_PREC_FP32>) : sizeof(Cand<CLEDB_PREC_FP64>);
-    const int64_t max_items = ((npix + pl.P - 1) / pl.P + pl.nkeys) * (int64_t)kParts * pl.split;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_key = take(npix * 4), o_rank = take(npix * 4), o_order = take(npix * 4);
     const size_t o_small = take((size_t)(5 * pl.nkeys + 1 + 4) * 4);
     const size_t o_recs = take(npix * rec_sz), o_status = take(npix);
-    const size_t o_plist = take((size_t)max_items * pl.P * pl.k * cand_sz);
     if ((rc = ensure_workspace(ctx, ctx->ws, off))) return rc;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx->ws.ptr);
     pl.key = reinterpret_cast<int32_t*>(w + o_key);
@@ -963,12 +1054,11 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     pl.counters = small + 5 * pl.nkeys + 1;
     pl.recs = w + o_recs;
     pl.status = status_out ? status_out : (w + o_status);
-    pl.plist = w + o_plist;
     CLEDB_CUDA(ctx, cudaMemsetAsync(small, 0, (size_t)(5 * pl.nkeys + 1 + 4) * 4, st));
     if (precision == CLEDB_PREC_FP32)
-        rc = run_match<CLEDB_PREC_FP32>(ctx, enc, pl, sobs, snr, db_id, idx_out, chi_out, chi64_out, kpos_out, rows_out, ncand_out, st);
+        rc = run_match<CLEDB_PREC_FP32>(ctx, enc, pl, wslots, pmax, sobs, snr, db_id, idx_out, chi_out, chi64_out, kpos_out, rows_out, ncand_out, st);
     else
-        rc = run_match<CLEDB_PREC_FP64>(ctx, enc, pl, sobs, snr, db_id, idx_out, chi_out, chi64_out, kpos_out, rows_out, ncand_out, st);
+        rc = run_match<CLEDB_PREC_FP64>(ctx, enc, pl, wslots, pmax, sobs, snr, db_id, idx_out, chi_out, chi64_out, kpos_out, rows_out, ncand_out, st);
     return rc;
 }
 
