@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--mode', default='iquv', choices=['iquv', 'iqud'])
     ap.add_argument('--nx', type=int, default=256)
     ap.add_argument('--encoding', type=int, default=1)
+    ap.add_argument('--ndb', type=int, default=1, help='number of distinct (height, density) databases the map touches')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dbg', type=int, default=0, help='kernel timing experiment (results invalid)')
@@ -50,15 +51,29 @@ def parse():
 
 
 def workload_name(args):
-    return ('2-line Fe XIII %s inversion, %dx%d synthetic map per GPU, single synthetic PyCELP-shaped DB '
-            '(21x180x90 = 340200 entries), nsearch %d' % (args.mode.upper(), args.nx, args.nx, NSEARCH))
+    dbs = 'single synthetic PyCELP-shaped DB' if args.ndb == 1 else '%d synthetic PyCELP-shaped DBs (height x density grid points)' % args.ndb
+    return ('2-line Fe XIII %s inversion, %dx%d synthetic map per GPU, %s '
+            '(21x180x90 = 340200 entries each), nsearch %d' % (args.mode.upper(), args.nx, args.nx, dbs, NSEARCH))
 
 
 def make_inputs(args, rank):
+    """Returns (list of databases, observation dict).  With --ndb K the map touches K databases: rows of the map
+    fall into height bands (as yobs does on a real map) and the density index varies inside a band."""
     from cledb_b200 import synth
-    db = synth.make_database(9, 40)
-    obs = synth.make_observation(args.nx, args.nx, [db], seed=7 + rank)
-    return db, obs
+    if args.ndb == 1:
+        dbs = [synth.make_database(9, 40)]
+        enc = None
+    else:
+        nh = max(1, int(round(args.ndb ** 0.5)))
+        nd = (args.ndb + nh - 1) // nh
+        grid = [(h, d) for h in range(nh) for d in range(nd)][:args.ndb]
+        dbs = [synth.make_database(5 + 3 * h, 30 + 2 * d) for h, d in grid]
+        rng = np.random.default_rng(1234 + rank)
+        band = (np.arange(args.nx) * nh // args.nx)[:, None]                       # height band of a map row
+        dens = rng.integers(0, nd, (args.nx, args.nx))
+        enc = np.minimum(band * nd + dens, args.ndb - 1).astype(np.int32)
+    obs = synth.make_observation(args.nx, args.nx, dbs, db_enc=enc, seed=7 + rank)
+    return dbs, obs
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -67,7 +82,7 @@ def make_inputs(args, rank):
 def cpu_run(args, db, obs, npixels, workers, seed):
     import oracle.cledb_oracle as orc
     from cledb_b200 import synth, codec
-    dec = codec.decoded_database(db, args.encoding).reshape(db.shape)
+    dec = [codec.decoded_database(d, args.encoding).reshape(d.shape) for d in db]
     hdr = synth.make_dbhdr()
     nx = args.nx
     rng = np.random.default_rng(seed)
@@ -75,7 +90,7 @@ def cpu_run(args, db, obs, npixels, workers, seed):
     pixels = [(int(f // nx), int(f % nx)) for f in flat]
     iss = obs['issuemask'].copy()
     t0 = time.perf_counter()
-    orc.invert_map(obs['sobs_totrot'], obs['sobs_dopp'], [dec], obs['db_enc'], obs['yobs'], obs['aobs'], obs['dobs'],
+    orc.invert_map(obs['sobs_totrot'], obs['sobs_dopp'], dec, obs['db_enc'], obs['yobs'], obs['aobs'], obs['dobs'],
                    obs['snr'], iss, hdr, obs['keyvals'], NSEARCH, 1000, 3 if args.mode == 'iqud' else 0,
                    args.mode == 'iqud', workers=workers, pixels=pixels)
     return time.perf_counter() - t0
@@ -178,7 +193,8 @@ def main():
 
     db, obs = make_inputs(args, rank)
     ctx = native.Context(local)
-    ctx.db_put(0, db, args.encoding)
+    for i, d in enumerate(db):
+        ctx.db_put(i, d, args.encoding)
     props = ctx.device_props()
     if args.ppi or args.split:
         ctx.set_tuning(args.ppi, args.split)
@@ -189,7 +205,7 @@ def main():
 
     sobs_h = torch.from_numpy(obs['sobs_totrot'].reshape(-1, 8)).pin_memory()
     snr_h = torch.from_numpy(obs['snr'].reshape(-1, 8)).pin_memory()
-    id_h = torch.zeros(npix, dtype=torch.int32).pin_memory()
+    id_h = torch.from_numpy(np.ascontiguousarray(obs['db_enc'].reshape(-1).astype(np.int32))).pin_memory()
     sobs_d, snr_d, id_d = sobs_h.to(dev), snr_h.to(dev), id_h.to(dev)
     idx_d = torch.empty((npix, k), dtype=torch.int32, device=dev)
     chi_d = torch.empty((npix, k), dtype=torch.float32, device=dev)

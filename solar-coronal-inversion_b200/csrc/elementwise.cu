@@ -9,34 +9,50 @@
 
 namespace cledb {
 
-// 34 B/pixel: 16 in, 16 out, 2 flag bytes
+// 34 B/pixel: 16 in, 16 out, 2 flag bytes.  Four pixels per thread, 256 apart: four independent coalesced 16-byte loads
+// in flight per thread before the first use.
+__device__ __forceinline__ void blos_one(const float4 s, float kfac, float geff, float c66f, float4& o, uchar2& f) {
+    o = make_float4(0.f, 0.f, 0.f, 0.f);
+    f = make_uchar2(0, 0);
+    const bool bad = (s.x == 0.f) || isnan(s.x) || isnan(s.y) || isnan(s.z) || isnan(s.w);   // CLEDB_PROC.py:882
+    if (bad) return;
+    // float32 arithmetic in the reference: NumPy float32 scalars with Python-float constants (weak promotion)
+    const float lpol = __fsqrt_rn(__fadd_rn(__fmul_rn(s.y, s.y), __fmul_rn(s.z, s.z)));
+    const float nv = -s.w;
+    const float d0 = __fsub_rn(__fmul_rn(geff, __fsub_rn(s.x, lpol)), __fmul_rn(c66f, lpol));
+    const float d1 = __fadd_rn(__fmul_rn(geff, __fadd_rn(s.x, lpol)), __fmul_rn(c66f, lpol));
+    const float d2 = __fmul_rn(geff, s.x);
+    o.x = __fmul_rn(kfac, __fdiv_rn(nv, d0));
+    o.y = __fmul_rn(kfac, __fdiv_rn(nv, d1));
+    o.z = __fmul_rn(kfac, __fdiv_rn(nv, d2));
+    o.w = 0.5f * atan2f(s.z, s.y);
+    const float qi = __fdiv_rn(s.y, s.x), ui = __fdiv_rn(s.z, s.x);
+    if (fabsf(qi) < 1e-6f || fabsf(ui) < 1e-6f) {            // :907
+        f.x = 1;
+        if (qi < 1e-6f && ui < 1e-6f) f.y = 1;                // :909 (signed comparison, as in the reference)
+    }
+}
+
 __global__ void __launch_bounds__(256) k_blos(int64_t npix, const float4* __restrict__ iquv, float kfac, float geff, float c66f,
                                               float4* __restrict__ out, uchar2* __restrict__ flags) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npix) return;
-    const float4 s = iquv[p];
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    uchar2 f = make_uchar2(0, 0);
-    const bool bad = (s.x == 0.f) || isnan(s.x) || isnan(s.y) || isnan(s.z) || isnan(s.w);   // CLEDB_PROC.py:882
-    if (!bad) {
-        // float32 arithmetic in the reference: NumPy float32 scalars with Python-float constants (weak promotion)
-        const float lpol = __fsqrt_rn(__fadd_rn(__fmul_rn(s.y, s.y), __fmul_rn(s.z, s.z)));
-        const float nv = -s.w;
-        const float d0 = __fsub_rn(__fmul_rn(geff, __fsub_rn(s.x, lpol)), __fmul_rn(c66f, lpol));
-        const float d1 = __fadd_rn(__fmul_rn(geff, __fadd_rn(s.x, lpol)), __fmul_rn(c66f, lpol));
-        const float d2 = __fmul_rn(geff, s.x);
-        o.x = __fmul_rn(kfac, __fdiv_rn(nv, d0));
-        o.y = __fmul_rn(kfac, __fdiv_rn(nv, d1));
-        o.z = __fmul_rn(kfac, __fdiv_rn(nv, d2));
-        o.w = 0.5f * atan2f(s.z, s.y);
-        const float qi = __fdiv_rn(s.y, s.x), ui = __fdiv_rn(s.z, s.x);
-        if (fabsf(qi) < 1e-6f || fabsf(ui) < 1e-6f) {            // :907
-            f.x = 1;
-            if (qi < 1e-6f && ui < 1e-6f) f.y = 1;                // :909 (signed comparison, as in the reference)
+    const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x;      // pixels base + i*256: every access is coalesced
+    float4 s[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t p = base + i * 256;
+        s[i] = p < npix ? __ldcs(iquv + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t p = base + i * 256;
+        float4 o;
+        uchar2 f;
+        blos_one(s[i], kfac, geff, c66f, o, f);
+        if (p < npix) {
+            __stcs(out + p, o);
+            flags[p] = f;
         }
     }
-    out[p] = o;
-    flags[p] = f;
 }
 
 // 72 B/pixel (+8 with a coordinate grid): 32 in, 32 out, aobs, yobs
@@ -120,7 +136,7 @@ int launch_blos(cledb_ctx* ctx, int64_t npix, const float* iquv, double kfac, do
     if (npix == 0) return CLEDB_OK;
     // Python evaluates 0.66*F_factor in float64; NumPy then rounds that product, g_eff and the constant K to
     // float32 when they meet float32 scalars (CLEDB_PROC.py:889-896)
-    k_blos<<<(int)((npix + 255) / 256), 256, 0, st>>>(npix, reinterpret_cast<const float4*>(iquv), (float)kfac, (float)g_eff,
+    k_blos<<<(int)((npix + 1023) / 1024), 256, 0, st>>>(npix, reinterpret_cast<const float4*>(iquv), (float)kfac, (float)g_eff,
                                                       (float)(0.66 * ffac), reinterpret_cast<float4*>(out),
                                                       reinterpret_cast<uchar2*>(flags));
     ctx->launches++;
