@@ -270,28 +270,37 @@ def main():
     else:
         ncand_all, nsearched_all = ncand, nsearched
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host memory in, pinned host memory out)
-    out_h = dict(idx=torch.empty((npix, k), dtype=torch.int32).pin_memory().numpy(),
-                 chi=torch.empty((npix, k), dtype=torch.float32).pin_memory().numpy(),
-                 kpos=torch.empty((npix, k), dtype=torch.int32).pin_memory().numpy(),
-                 status=torch.empty(npix, dtype=torch.uint8).pin_memory().numpy(),
-                 ncand=torch.empty(npix, dtype=torch.int64).pin_memory().numpy(),
-                 rows=torch.empty((npix, k, 8), dtype=torch.float32).pin_memory().numpy(), chi64=None)
+    # ---- end to end through the host-buffer C-ABI call a reference binding makes (cledb_invert: search + solution
+    #      building, pinned host memory in, the finished invout / sfound maps in pinned host memory out)
+    from cledb_b200 import synth
+    hdr = synth.make_dbhdr()
+    out_h = dict(invout=torch.empty((npix, k, 11), dtype=torch.float32).pin_memory().numpy(),
+                 sfound=torch.empty((npix, k, 8), dtype=torch.float32).pin_memory().numpy(),
+                 status=torch.empty(npix, dtype=torch.uint8).pin_memory().numpy())
     sobs_n, snr_n, id_n = sobs_h.numpy(), snr_h.numpy(), id_h.numpy()
+    yobs_n = torch.from_numpy(obs['yobs'].reshape(-1).copy()).pin_memory().numpy()
+    dobs_n = torch.from_numpy(obs['dobs'].reshape(-1).copy()).pin_memory().numpy()
+    aobs_n = obs['aobs'].reshape(-1)
+    dopp_n = np.ascontiguousarray(obs['sobs_dopp'].reshape(npix, -1)[:, 0]) if args.mode == 'iqud' else None
+    bcalc = 3 if args.mode == 'iqud' else 0
+
+    def e2e_step():
+        ctx.invert(mode, sobs_n, snr_n, id_n, k, yobs_n, dobs_n, aobs_n, dopp_n, hdr, 1000, bcalc, out=out_h)
+
     for _ in range(3):
-        ctx.match(mode, sobs_n, snr_n, id_n, k, out=out_h)
+        e2e_step()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.match(mode, sobs_n, snr_n, id_n, k, out=out_h)
+        e2e_step()
     e2e_s = (time.perf_counter() - t0) / args.steps
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    h2d = npix * (32 + 32 + 4)
-    d2h = npix * (k * (4 + 4 + 4 + 32) + 1 + 8)
+    h2d = npix * (32 + 32 + 4 + 4 + 4 + 4 + 4 + (4 if args.mode == 'iqud' else 0))
+    d2h = npix * (k * (44 + 32) + 1)
 
     if rank != 0:
         if world > 1:
@@ -316,7 +325,7 @@ def main():
         pixels_searched=nsearched_all,
         gpu_launches=int(launches),
         e2e=dict(value=world * npix / e2e_s, unit='pixels/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                 api='cledb_match (C-ABI, pinned host buffers)', ms_per_step=e2e_s * 1e3),
+                 api='cledb_invert (C-ABI, pinned host buffers in, finished invout/sfound maps out)', ms_per_step=e2e_s * 1e3),
         roofline=dict(bound='fp32', kernel='k_match<int16,fp32>', achieved=achieved, peak=peak, unit='TFLOP/s',
                       frac=achieved / peak if peak else None, traffic=None, kernel_ms=kms,
                       kernel_share_of_step=kms / float(np.mean(step_ms)),

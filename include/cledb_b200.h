@@ -116,6 +116,41 @@ int cledb_match_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  * 0 = choose from the pixel count (default).  Results do not depend on them. */
 int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split);
 
+/* ---- search + solution building in one call --------------------------------------------------------- *
+ * Replaces everything cledb_invproc does per pixel (CLEDB_PROC.py:304-319 with the bodies of cledb_matchiquv /
+ * cledb_matchiqud, :944-1087 / :1118-1252): the search above, then - on the device - the replay of the
+ * cledb_partsort index quirk (:1620-1625, unless strict_topk), the maxchisq cut-offs (:1027-1044 / :1202-1219),
+ * the field strength (:1049-1059, :1225), cledb_phys/cledb_physcle/cledb_params (:1634-1749) and cledb_quderotate
+ * (:1575-1588).  Only PyCELP-type databases (dbtype 1, density taken from the observation) are built on the
+ * device; CLE-type headers return CLEDB_ERR_ARG and the binding builds those solutions from cledb_match.
+ *
+ * Transcendentals are NOT evaluated on the device, so that the numbers are the caller's own libm/NumPy bits:
+ *   grid->sin_bphi/cos_bphi[nbphi], sin_btheta/cos_btheta[nbtheta]: sin/cos of the float32 grid angles
+ *   rot_cos[npix], rot_sin[npix]: cos(-2*aobs), sin(-2*aobs) of every pixel (float32)
+ *   yobs[npix], dobs[npix] float32; dopp: B_POS of every pixel for IQUD (element p at dopp[p*dopp_stride],
+ *   float32 or float64 as dopp_is_f64 says; NULL for IQUV); maxchisq, bcalc as in ctrlparams
+ *   invout[npix,nsearch,11], sfound[npix,nsearch,8] float32; status_out[npix] (may be NULL)
+ * The Van-Vleck / chi^2 / SNR issue codes (:323-355) are O(npix) work on invout and stay in the binding. */
+typedef struct cledb_dbgrid {
+    int32_t dbtype, ngx, nbphi, nbtheta;               /* dbhdr[14], [2], [3], [4]  (CLEDB_PREPINV.py:482-508) */
+    float   gxmin, gxmax, bphimin, bphimax, bthetamin, bthetamax;
+    const float* sin_bphi;   const float* cos_bphi;    /* [nbphi]   */
+    const float* sin_btheta; const float* cos_btheta;  /* [nbtheta] */
+} cledb_dbgrid;
+int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npix,
+                 const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
+                 const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
+                 const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
+                 double maxchisq, int bcalc, int strict_topk,
+                 float* invout, float* sfound, uint8_t* status_out);
+/* device-pointer variant: every array, including the four tables inside *grid, lives on the context's device */
+int cledb_invert_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
+                     const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
+                     const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
+                     const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
+                     double maxchisq, int bcalc, int strict_topk,
+                     float* invout, float* sfound, uint8_t* status_out, void* stream);
+
 /* ---- elementwise neighbours ------------------------------------------------------------------------ *
  * cledb_blos: blos_proc_1pix (CLEDB_PROC.py:874-914) for npix pixels of one line.
  *   iquv[npix,4]; kfac = 1e9*h*c/mu_B/lambda_ref^2, g_eff, ffac = F_factor as Python floats (they are

@@ -17,6 +17,8 @@ Module-level options (not part of the reference surface; the defaults reproduce 
     OPTIONS['dbencoding']  0 = database kept as float32 in HBM (lossless, default here), 1 = int16 codes
     OPTIONS['precision']   0 = fp32 kernel, 1 = fp64 validation kernel (reference operation order)
     OPTIONS['strict_topk'] False = reproduce the cledb_partsort index quirk, True = true top-nsearch
+    OPTIONS['solution']    'device' = solutions built on the GPU right after the search (cledb_invert; PyCELP-type databases),
+                           'host' = NumPy on the raw search result (cledb_b200.solution); both give the same bits
     OPTIONS['device']      CUDA ordinal (default: $CLEDB_B200_DEVICE, else $LOCAL_RANK, else 0)
 """
 import os
@@ -28,6 +30,7 @@ from cledb_b200 import native, solution
 OPTIONS = dict(dbencoding=int(os.environ.get('CLEDB_B200_DBENCODING', '0')),
                precision=int(os.environ.get('CLEDB_B200_PRECISION', '0')),
                strict_topk=False,
+               solution=os.environ.get('CLEDB_B200_SOLUTION', 'device'),
                device=int(os.environ.get('CLEDB_B200_DEVICE', os.environ.get('LOCAL_RANK', '0'))))
 
 
@@ -94,6 +97,11 @@ def _search_and_build(mode, sobs, sobs_dopp, database, db_enc, yobs, aobs, dobs,
     lut = np.zeros(int(enc.max()) + 1, dtype=np.int32)
     for k, v in ids.items():
         lut[k] = v
+    if OPTIONS['solution'] == 'device' and int(dbhdr[14]) == 1:
+        dopp0 = None if sobs_dopp is None else np.asarray(sobs_dopp).reshape(sobs.shape[0], -1)[:, 0]
+        inv, sf, _ = ctx.invert(mode, sobs, snr, lut[enc], nsearch, yobs, dobs, aobs, dopp0, dbhdr, maxchisq, bcalc,
+                                strict_topk=OPTIONS['strict_topk'], precision=OPTIONS['precision'])
+        return inv, sf
     raw = ctx.match(mode, sobs, snr, lut[enc], nsearch, precision=OPTIONS['precision'], want_rows=True,
                     want_chi64=OPTIONS['precision'] == native.PREC_FP64)
     return solution.build_solutions(raw, mode, sobs, sobs_dopp, np.asarray(yobs).reshape(-1), np.asarray(aobs).reshape(-1),
@@ -114,20 +122,21 @@ def cledb_invproc(sobs_totrot, sobs_dopp, database, db_enc, yobs, aobs, dobs, sn
     if verbose >= 1:
         print('--------------------------------------\n----CLEDB_INVPROC - INVERSION START---\n--------------------------------------')
     nx, ny = keyvals[0:2]
-    invout = np.zeros((nx, ny, nsearch, 11), dtype=np.float32)
-    sfound = np.zeros((nx, ny, nsearch, 8), dtype=np.float32)
+
+    def aborted():
+        invout = np.zeros((nx, ny, nsearch, 11), dtype=np.float32)
+        invout[:, :, :, 0] = -1
+        return invout, np.zeros((nx, ny, nsearch, 8), dtype=np.float32)
 
     if np.shape(sobs_totrot)[-1] != 8 or database[0].shape[-1] != 8:                      # CLEDB_PROC.py:166-171
         if verbose >= 1:
             print('CLEDB_INVPROC: FATAL! Must have a two-line observation and a corresponding two-line database; Aborting!')
             print("Shapes are: ", np.shape(sobs_totrot), " and ", database[0].shape)
-        invout[:, :, :, 0] = -1
-        return invout, sfound
+        return aborted()
     if (iqud == True and bcalc != 3) or (iqud != True and bcalc == 3):                    # CLEDB_PROC.py:174-178
-        invout[:, :, :, 0] = -1
         if verbose >= 1:
             print("CLEDB_INVPROC: FATAL! Field strength calculation incompatible with requested input data! Check bcalc and iqud keywords; Aborting!")
-        return invout, sfound
+        return aborted()
     if reduced == True:
         raise NotImplementedError("cledb_b200: the reduced-database presort (cledb_getsubsetiquv/iqud) is not built yet; "
                                   "run with reduced=False (full search is the default of the reference)")
@@ -140,8 +149,8 @@ def cledb_invproc(sobs_totrot, sobs_dopp, database, db_enc, yobs, aobs, dobs, sn
         dopp = np.asarray(sobs_dopp)
         dopp = dopp.reshape(nx * ny, -1)
     inv, sf = _search_and_build(mode, sobs_totrot, dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc)
-    invout[...] = inv.reshape(nx, ny, nsearch, 11)
-    sfound[...] = sf.reshape(nx, ny, nsearch, 8)
+    invout = np.ascontiguousarray(inv, dtype=np.float32).reshape(nx, ny, nsearch, 11)
+    sfound = np.ascontiguousarray(sf, dtype=np.float32).reshape(nx, ny, nsearch, 8)
     solution.update_issuemask(issuemask, invout, np.asarray(snr), nx, ny)
     if verbose >= 1:
         print('--------------------------------------\n--CLEDB_INVPROC - INVERSION FINALIZED-\n--------------------------------------')

@@ -40,6 +40,10 @@ SIGNATURES = {
     'cledb_match': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_match_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_set_tuning': (_c.c_int, [_P, _c.c_int, _c.c_int]),
+    'cledb_invert': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
+                                _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P]),
+    'cledb_invert_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
+                                    _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'cledb_blos': (_c.c_int, [_P, _c.c_int64, _P, _c.c_double, _c.c_double, _c.c_double, _P, _P]),
     'cledb_blos_dev': (_c.c_int, [_P, _c.c_int64, _P, _c.c_double, _c.c_double, _c.c_double, _P, _P, _P]),
     'cledb_qurotate': (_c.c_int, [_P, _c.c_int, _c.c_int, _P, _P, _c.c_double, _P, _P, _P, _P, _P]),
@@ -54,6 +58,34 @@ _lib = None
 
 class CledbError(RuntimeError):
     pass
+
+
+class DbGrid(ctypes.Structure):
+    """``cledb_dbgrid`` of the header: the part of ``dbhdr`` (CLEDB_PREPINV.py:507-508) that solution building needs,
+    plus sin/cos tables of the float32 grid angles evaluated here with NumPy (the reference's own bits)."""
+    _fields_ = [('dbtype', _c.c_int32), ('ngx', _c.c_int32), ('nbphi', _c.c_int32), ('nbtheta', _c.c_int32),
+                ('gxmin', _c.c_float), ('gxmax', _c.c_float), ('bphimin', _c.c_float), ('bphimax', _c.c_float),
+                ('bthetamin', _c.c_float), ('bthetamax', _c.c_float),
+                ('sin_bphi', _P), ('cos_bphi', _P), ('sin_btheta', _P), ('cos_btheta', _P)]
+
+    @classmethod
+    def from_dbhdr(cls, dbhdr):
+        dbcgrid, ned, ngx, nbphi, nbtheta, xed, gxmin, gxmax, bphimin, bphimax, bthetamin, bthetamax, nline, wavel, dbtype = dbhdr
+        f32 = np.float32
+
+        def angles(lo, hi, n):      # cledb_physcle, CLEDB_PROC.py:1737-1739: float64 arithmetic on an int64 index, then float32
+            k = np.arange(int(n), dtype=np.int64).astype(np.float64)
+            with np.errstate(all='ignore'):
+                return (np.float64(lo) + (k * np.float64(f32(hi) - f32(lo))) / np.float64(int(n) - 1)).astype(f32)
+
+        g = cls()
+        g.dbtype, g.ngx, g.nbphi, g.nbtheta = int(dbtype), int(ngx), int(nbphi), int(nbtheta)
+        g.gxmin, g.gxmax, g.bphimin, g.bphimax = float(f32(gxmin)), float(f32(gxmax)), float(f32(bphimin)), float(f32(bphimax))
+        g.bthetamin, g.bthetamax = float(f32(bthetamin)), float(f32(bthetamax))
+        phi, th = angles(bphimin, bphimax, nbphi), angles(bthetamin, bthetamax, nbtheta)
+        g._tables = [np.ascontiguousarray(t, dtype=f32) for t in (np.sin(phi), np.cos(phi), np.sin(th), np.cos(th))]
+        g.sin_bphi, g.cos_bphi, g.sin_btheta, g.cos_btheta = (t.ctypes.data for t in g._tables)
+        return g
 
 
 def load_library(path=None):
@@ -204,6 +236,36 @@ class Context:
                                          _ptr(out['idx']), _ptr(out['chi']), _ptr(out['chi64']), _ptr(out['kpos']),
                                          _ptr(out['rows']), _ptr(out['status']), _ptr(out['ncand'])))
         return out
+
+    def invert(self, mode, sobs, snr, db_id, nsearch, yobs, dobs, aobs, dopp, dbhdr, maxchisq, bcalc, strict_topk=False,
+               precision=PREC_FP32, out=None):
+        """Search + solution building on the device (cledb_invert).  Returns ``(invout[npix,k,11], sfound[npix,k,8], status)``.
+        ``dopp``: per-pixel B_POS (float32 or float64, [npix]) for IQUD, else None."""
+        sobs = _as(sobs, np.float32).reshape(-1, 8)
+        snr = _as(snr, np.float32).reshape(-1, 8)
+        npix = sobs.shape[0]
+        db_id = _as(np.broadcast_to(np.asarray(db_id, dtype=np.int32).reshape(-1), (npix,)), np.int32)
+        k = int(nsearch)
+        yobs = _as(np.asarray(yobs).reshape(-1), np.float32)
+        dobs = _as(np.asarray(dobs).reshape(-1), np.float32)
+        ang = _as(np.asarray(aobs).reshape(-1), np.float32)
+        with np.errstate(all='ignore'):
+            rot_cos = np.cos(-2. * ang)           # cledb_quderotate, CLEDB_PROC.py:1584-1587, in the reference's float32
+            rot_sin = np.sin(-2. * ang)
+        is64 = 0
+        if dopp is not None:
+            dopp = np.asarray(dopp).reshape(-1)
+            is64 = 1 if dopp.dtype == np.float64 else 0
+            dopp = _as(dopp, np.float64 if is64 else np.float32)
+        grid = DbGrid.from_dbhdr(dbhdr)
+        if out is None:
+            out = dict(invout=np.empty((npix, k, 11), np.float32), sfound=np.empty((npix, k, 8), np.float32),
+                       status=np.empty(npix, np.uint8))
+        self._check(self.lib.cledb_invert(self.h, int(mode), int(precision), npix, _ptr(sobs), _ptr(snr), _ptr(db_id), k,
+                                          _ptr(yobs), _ptr(dobs), _ptr(rot_cos), _ptr(rot_sin), _ptr(dopp), is64, 1,
+                                          ctypes.addressof(grid), float(maxchisq), int(bcalc), 1 if strict_topk else 0,
+                                          _ptr(out['invout']), _ptr(out['sfound']), _ptr(out['status'])))
+        return out['invout'], out['sfound'], out['status']
 
     def match_dev(self, mode, npix, sobs_ptr, snr_ptr, dbid_ptr, nsearch, idx_ptr, chi_ptr, chi64_ptr=None, kpos_ptr=None,
                   rows_ptr=None, status_ptr=None, ncand_ptr=None, stream=None, precision=PREC_FP32):

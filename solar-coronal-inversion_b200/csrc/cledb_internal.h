@@ -84,6 +84,7 @@ struct cledb_ctx {
     bool tables_dirty = true;
     cledb::Workspace ws;                           // search workspace (grown on demand)
     cledb::Workspace ws2;                          // partial top-k lists of the search (sized once the work shape is known)
+    cledb::Workspace raw;                          // raw search outputs of the fused search + solution call
     cledb::Workspace io;                           // staging for the host entry points
     int32_t* h_cnt = nullptr;                      // pinned host copy of the bucket sizes
     size_t h_cnt_cap = 0;
@@ -121,4 +122,12 @@ int  launch_blos(cledb_ctx* ctx, int64_t npix, const float* iquv, double kfac, d
 int  measure_fp32_peak(cledb_ctx* ctx, double* tflops);
 int  launch_qurotate(cledb_ctx* ctx, int nx, int ny, const double* xs, const double* ys, double linpolref,
                      const float* hpxy, const float* in, float* out, float* aobs, float* yobs, cudaStream_t st);
+}  // namespace cledb
+
+namespace cledb {
+int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsearch, const float* sobs, const float* yobs,
+                 const float* dobs, const float* rot_cos, const float* rot_sin, const void* dopp, int dopp_is_f64,
+                 int64_t dopp_stride, const cledb_dbgrid& grid_dev, double maxchisq, int bcalc, int strict_topk,
+                 const int32_t* idx, const float* chi, const double* chi64, const int32_t* kpos, const float* rows,
+                 const uint8_t* status, float* invout, float* sfound, cudaStream_t st);
 }  // namespace cledb

@@ -1,0 +1,320 @@
+// Solution building on the device: what cledb_matchiquv / cledb_matchiqud do with the nsearch winners after the search
+// (CLEDB_PROC.py:1010-1082 / 1185-1247 of the reference) for every pixel of a map at once, and the fused entry points
+// cledb_invert / cledb_invert_dev (search + solutions in one call).
+//
+// One thread per pixel.  Every floating-point operation is written with explicit rounding intrinsics in the
+// reference's dtype and order (NumPy float32 scalars, float64 where an int64 index meets float32 header values), so
+// nothing is contracted into FMAs; sines and cosines come from caller-evaluated tables (see the header), so the
+// outputs are bit-identical to the NumPy host path of cledb_b200/solution.py.
+#include <math_constants.h>
+
+#include <cstring>
+
+#include "cledb_internal.h"
+
+namespace cledb {
+
+constexpr int kMaxK = CLEDB_MAX_NSEARCH;
+
+// The reference's partial selection sort reports argmin(tmp[i:]) + i of an array it is swapping in place
+// (CLEDB_PROC.py:1620-1625): an early candidate that is itself a winner, but not at its turn, is swapped away and found
+// again at the old position of an earlier winner, so that earlier winner is reported twice.  Only the winners'
+// positions q[] and the first k positions are ever touched, so the sort is replayed on that sparse set.
+// sel[i] = which of the true top-k the reference shows in slot i.
+__device__ void replay_partsort(int k, const int32_t* q, const double* chi, int* sel) {
+    int pos[2 * kMaxK];
+    double work[2 * kMaxK];
+    int slot[2 * kMaxK];
+    int n = 0;
+    // sorted union of 0..k-1 and q[]: q is not sorted by position, so insert one by one
+    for (int i = 0; i < k; ++i) { pos[n] = i; work[n] = CUDART_INF; slot[n] = -1; ++n; }
+    for (int m = 0; m < k; ++m) {
+        const int p = q[m];
+        if (p < k) { work[p] = chi[m]; slot[p] = m; continue; }
+        int at = n;
+        while (at > k && pos[at - 1] > p) { pos[at] = pos[at - 1]; work[at] = work[at - 1]; slot[at] = slot[at - 1]; --at; }
+        pos[at] = p; work[at] = chi[m]; slot[at] = m;
+        ++n;
+    }
+    for (int i = 0; i < k; ++i) {
+        int a = i;
+        for (int j = i + 1; j < n; ++j)
+            if (work[j] < work[a]) a = j;            // first minimum, like np.argmin
+        // the winner's identity stays with its ORIGINAL position: the reference reads chisq[asrt[i]] from the
+        // unswapped array (CLEDB_PROC.py:1043), so slot[] is not swapped along with work[]
+        sel[i] = slot[a] >= 0 ? slot[a] : i;
+        const double t = work[i]; work[i] = work[a]; work[a] = t;
+    }
+}
+
+template <bool DOPP64>
+__global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, const float* __restrict__ sobs,
+                                               const float* __restrict__ yobs, const float* __restrict__ dobs,
+                                               const float* __restrict__ rot_cos, const float* __restrict__ rot_sin,
+                                               const void* __restrict__ dopp, int64_t dopp_stride, cledb_dbgrid g, double maxchisq,
+                                               int bcalc, int strict_topk, const int32_t* __restrict__ idx,
+                                               const float* __restrict__ chi, const double* __restrict__ chi64,
+                                               const int32_t* __restrict__ kpos, const float* __restrict__ rows,
+                                               const uint8_t* __restrict__ status, float* __restrict__ invout,
+                                               float* __restrict__ sfound) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    float* inv = invout + p * k * 11;
+    float* sf = sfound + p * k * 8;
+    for (int s = 0; s < k; ++s) {
+        inv[s * 11] = -1.0f;
+#pragma unroll
+        for (int c = 1; c < 11; ++c) inv[s * 11 + c] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sf[s * 8 + c] = 0.0f;
+    }
+    const int st = status[p];
+    if (st == CLEDB_PIX_ALLINF) {                       // every chi^2 is +inf in the reference: rejected with that value
+        for (int s = 0; s < k; ++s) inv[s * 11 + 1] = CUDART_INF_F;
+        return;
+    }
+    if (st != CLEDB_PIX_SEARCHED) return;
+
+    const int32_t* ix = idx + p * k;
+    const int32_t* kp = kpos + p * k;
+    double c64[kMaxK];
+    bool all_valid = true, touched = false;
+    for (int s = 0; s < k; ++s) {
+        c64[s] = chi64 ? chi64[p * k + s] : (double)chi[p * k + s];
+        all_valid = all_valid && ix[s] >= 0;
+        touched = touched || (ix[s] >= 0 && kp[s] >= 0 && kp[s] < k);
+    }
+    int sel[kMaxK];
+    for (int s = 0; s < k; ++s) sel[s] = s;
+    if (!strict_topk && touched && all_valid) replay_partsort(k, kp, c64, sel);
+
+    const double limit = mode == CLEDB_MODE_IQUV ? maxchisq * 10.0 : maxchisq;          // CLEDB_PROC.py:1027 / 1202
+    const int s0 = sel[0];
+    if (ix[s0] >= 0 && c64[s0] > limit) {
+        const float best = (float)c64[s0];
+        for (int s = 0; s < k; ++s) inv[s * 11 + 1] = best;
+        return;
+    }
+    float so[8];
+    {
+        const float4 a = reinterpret_cast<const float4*>(sobs)[2 * p], b = reinterpret_cast<const float4*>(sobs)[2 * p + 1];
+        so[0] = a.x; so[1] = a.y; so[2] = a.z; so[3] = a.w; so[4] = b.x; so[5] = b.y; so[6] = b.z; so[7] = b.w;
+    }
+    float nf = so[0];                                                                    // :980
+    if (mode == CLEDB_MODE_IQUD) {
+#pragma unroll
+        for (int c = 1; c < 8; ++c) nf = fmaxf(nf, so[c]);                              // :1155 (no NaN in a searched IQUD pixel)
+    }
+    const float yo = yobs[p], ed = dobs[p], rc = rot_cos[p], rs = rot_sin[p];
+    const int64_t n3 = g.nbtheta, n4 = (int64_t)g.nbphi * g.nbtheta;
+    const double dgx = (double)__fsub_rn(g.gxmax, g.gxmin), dphi = (double)__fsub_rn(g.bphimax, g.bphimin),
+                 dth = (double)__fsub_rn(g.bthetamax, g.bthetamin);
+    for (int s = 0; s < k; ++s) {
+        const int w = sel[s];
+        if (ix[w] < 0 || !(c64[w] <= maxchisq)) continue;                                // :1044 / :1219
+        const float* r = rows + ((size_t)p * k + w) * 8;
+        // ---- field strength
+        float b32 = 0.f;
+        double b64 = 0.0;
+        if (mode == CLEDB_MODE_IQUV) {                                                   // :1049-1059
+            const float r3 = fabsf(r[3]) > 1e-7f ? __fdiv_rn(__fdiv_rn(so[3], nf), r[3]) : 0.f;
+            const float r7 = fabsf(r[7]) > 1e-7f ? __fdiv_rn(__fdiv_rn(so[7], nf), r[7]) : 0.f;
+            b32 = bcalc == 0 ? r3 : (bcalc == 1 ? r7 : __fmul_rn(0.5f, __fadd_rn(r7, r3)));
+        } else if (DOPP64) {
+            b64 = reinterpret_cast<const double*>(dopp)[p * dopp_stride];                // :1225
+        } else {
+            b32 = reinterpret_cast<const float*>(dopp)[p * dopp_stride];
+        }
+        // ---- grid position of the entry, cledb_params + cledb_physcle (:1634-1659, :1727-1749); PyCELP type: i = 0
+        const int64_t index = ix[w];
+        const int64_t j = index / n4, kk = (index - j * n4) / n3, l = index - j * n4 - kk * n3;
+        const float gx = (float)__dadd_rn((double)g.gxmin, __ddiv_rn(__dmul_rn((double)j, dgx), (double)(g.ngx - 1)));
+        const float bphi = (float)__dadd_rn((double)g.bphimin, __ddiv_rn(__dmul_rn((double)kk, dphi), (double)(g.nbphi - 1)));
+        const float bth = (float)__dadd_rn((double)g.bthetamin, __ddiv_rn(__dmul_rn((double)l, dth), (double)(g.nbtheta - 1)));
+        const float sp = g.sin_bphi[kk], cp = g.cos_bphi[kk], sth = g.sin_btheta[l], cth = g.cos_btheta[l];
+        float bo, bx, by, bz;
+        if (DOPP64 && mode == CLEDB_MODE_IQUD) {                                         // float64 B_POS: NumPy promotes to float64
+            double b = b64;
+            if (bcalc == 3) {
+                const float den = __fsqrt_rn(__fadd_rn(__fmul_rn(__fmul_rn(sth, sth), __fmul_rn(sp, sp)), __fmul_rn(cth, cth)));
+                b = __ddiv_rn(b, (double)den);
+            }
+            const double ab = fabs(b);
+            bo = (float)b;
+            bx = (float)__dmul_rn(__dmul_rn(ab, (double)sth), (double)cp);
+            by = (float)__dmul_rn(__dmul_rn(ab, (double)sth), (double)sp);
+            bz = (float)__dmul_rn(ab, (double)cth);
+        } else {
+            float b = b32;
+            if (bcalc == 3) {                                                            // :1712-1713
+                const float den = __fsqrt_rn(__fadd_rn(__fmul_rn(__fmul_rn(sth, sth), __fmul_rn(sp, sp)), __fmul_rn(cth, cth)));
+                b = __fdiv_rn(b, den);
+            }
+            const float ab = fabsf(b);
+            bo = b;
+            bx = __fmul_rn(__fmul_rn(ab, sth), cp);
+            by = __fmul_rn(__fmul_rn(ab, sth), sp);
+            bz = __fmul_rn(ab, cth);
+        }
+        float* o = inv + s * 11;
+        o[0] = (float)index;                       // the reference stores the index in a float32 array (exact below 2^24)
+        o[1] = (float)c64[w];
+        o[2] = ed; o[3] = yo; o[4] = gx; o[5] = bo; o[6] = bphi; o[7] = bth; o[8] = bx; o[9] = by; o[10] = bz;
+        // ---- matched profile, rotated back: cledb_quderotate (:1575-1588)
+        float* f = sf + s * 8;
+        const float q1 = __fmul_rn(r[1], nf), u1 = __fmul_rn(r[2], nf), q2 = __fmul_rn(r[5], nf), u2 = __fmul_rn(r[6], nf);
+        f[0] = __fmul_rn(r[0], nf);
+        f[1] = __fsub_rn(__fmul_rn(q1, rc), __fmul_rn(u1, rs));
+        f[2] = __fadd_rn(__fmul_rn(q1, rs), __fmul_rn(u1, rc));
+        f[3] = __fmul_rn(r[3], nf);
+        f[4] = __fmul_rn(r[4], nf);
+        f[5] = __fsub_rn(__fmul_rn(q2, rc), __fmul_rn(u2, rs));
+        f[6] = __fadd_rn(__fmul_rn(q2, rs), __fmul_rn(u2, rc));
+        f[7] = __fmul_rn(r[7], nf);
+    }
+}
+
+int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsearch, const float* sobs, const float* yobs,
+                 const float* dobs, const float* rot_cos, const float* rot_sin, const void* dopp, int dopp_is_f64,
+                 int64_t dopp_stride, const cledb_dbgrid& g, double maxchisq, int bcalc, int strict_topk, const int32_t* idx,
+                 const float* chi, const double* chi64, const int32_t* kpos, const float* rows, const uint8_t* status,
+                 float* invout, float* sfound, cudaStream_t st) {
+    (void)precision;
+    const int nb = (int)((npix + 127) / 128);
+    if (dopp_is_f64)
+        k_build<true><<<nb, 128, 0, st>>>(mode, npix, nsearch, sobs, yobs, dobs, rot_cos, rot_sin, dopp, dopp_stride, g, maxchisq,
+                                          bcalc, strict_topk, idx, chi, chi64, kpos, rows, status, invout, sfound);
+    else
+        k_build<false><<<nb, 128, 0, st>>>(mode, npix, nsearch, sobs, yobs, dobs, rot_cos, rot_sin, dopp, dopp_stride, g, maxchisq,
+                                           bcalc, strict_topk, idx, chi, chi64, kpos, rows, status, invout, sfound);
+    ctx->launches++;
+    CLEDB_CUDA(ctx, cudaGetLastError());
+    return CLEDB_OK;
+}
+
+}  // namespace cledb
+
+using namespace cledb;
+
+static inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+
+static int check_invert_args(cledb_ctx* ctx, int mode, int64_t npix, const void* sobs, const void* snr, const void* db_id,
+                             int nsearch, const void* yobs, const void* dobs, const void* rc, const void* rs, const void* dopp,
+                             const cledb_dbgrid* g, int bcalc, const void* invout, const void* sfound) {
+    if (npix < 0 || !sobs || !snr || !db_id || !yobs || !dobs || !rc || !rs || !g || !invout || !sfound) {
+        ctx->err = "cledb_invert: null argument";
+        return CLEDB_ERR_ARG;
+    }
+    if (nsearch < 1 || nsearch > CLEDB_MAX_NSEARCH) { ctx->err = "cledb_invert: nsearch must be in 1..32"; return CLEDB_ERR_ARG; }
+    if (mode != CLEDB_MODE_IQUV && mode != CLEDB_MODE_IQUD) { ctx->err = "cledb_invert: unknown mode"; return CLEDB_ERR_ARG; }
+    if (g->dbtype != 1) { ctx->err = "cledb_invert: only PyCELP-type databases (dbtype 1) are built on the device"; return CLEDB_ERR_ARG; }
+    if (g->ngx < 1 || g->nbphi < 1 || g->nbtheta < 1 || !g->sin_bphi || !g->cos_bphi || !g->sin_btheta || !g->cos_btheta) {
+        ctx->err = "cledb_invert: incomplete grid description";
+        return CLEDB_ERR_ARG;
+    }
+    if (bcalc < 0 || bcalc > 3 || (mode == CLEDB_MODE_IQUD) != (bcalc == 3)) {           // CLEDB_PROC.py:174-178
+        ctx->err = "cledb_invert: bcalc 3 goes with IQUD and only with IQUD";
+        return CLEDB_ERR_ARG;
+    }
+    if (mode == CLEDB_MODE_IQUD && !dopp) { ctx->err = "cledb_invert: IQUD needs the Doppler field strengths"; return CLEDB_ERR_ARG; }
+    return CLEDB_OK;
+}
+
+// raw search outputs of the fused call live in their own workspace
+struct RawBufs { int32_t* idx; float* chi; double* chi64; int32_t* kpos; float* rows; uint8_t* status; size_t bytes; };
+static RawBufs carve_raw(unsigned char* base, size_t n, size_t k, bool want64) {
+    RawBufs r;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = up256(off + b); return o; };
+    const size_t o_idx = take(n * k * 4), o_chi = take(n * k * 4), o_c64 = take(want64 ? n * k * 8 : 0), o_kp = take(n * k * 4),
+                 o_rows = take(n * k * 32), o_st = take(n);
+    r.idx = reinterpret_cast<int32_t*>(base + o_idx);
+    r.chi = reinterpret_cast<float*>(base + o_chi);
+    r.chi64 = want64 ? reinterpret_cast<double*>(base + o_c64) : nullptr;
+    r.kpos = reinterpret_cast<int32_t*>(base + o_kp);
+    r.rows = reinterpret_cast<float*>(base + o_rows);
+    r.status = base + o_st;
+    r.bytes = off;
+    return r;
+}
+
+extern "C" int cledb_invert_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix, const float* sobs, const float* snr,
+                                const int32_t* db_id, int nsearch, const float* yobs, const float* dobs, const float* rot_cos,
+                                const float* rot_sin, const void* dopp, int dopp_is_f64, int64_t dopp_stride,
+                                const cledb_dbgrid* grid, double maxchisq, int bcalc, int strict_topk, float* invout,
+                                float* sfound, uint8_t* status_out, void* stream) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    int rc = check_invert_args(ctx, mode, npix, sobs, snr, db_id, nsearch, yobs, dobs, rot_cos, rot_sin, dopp, grid, bcalc, invout, sfound);
+    if (rc) return rc;
+    if (npix == 0) return CLEDB_OK;
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const bool want64 = precision == CLEDB_PREC_FP64;
+    RawBufs probe = carve_raw(nullptr, (size_t)npix, (size_t)nsearch, want64);
+    if ((rc = ensure_workspace(ctx, ctx->raw, probe.bytes))) return rc;
+    RawBufs raw = carve_raw(reinterpret_cast<unsigned char*>(ctx->raw.ptr), (size_t)npix, (size_t)nsearch, want64);
+    uint8_t* status = status_out ? status_out : raw.status;
+    rc = match_device(ctx, mode, precision, npix, sobs, snr, db_id, nsearch, raw.idx, raw.chi, raw.chi64, raw.kpos, raw.rows, status,
+                      nullptr, st);
+    if (rc) return rc;
+    return launch_build(ctx, mode, precision, npix, nsearch, sobs, yobs, dobs, rot_cos, rot_sin, dopp, dopp_is_f64,
+                        dopp_stride > 0 ? dopp_stride : 1, *grid, maxchisq, bcalc, strict_topk, raw.idx, raw.chi, raw.chi64, raw.kpos,
+                        raw.rows, status, invout, sfound, st);
+}
+
+extern "C" int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npix, const float* sobs, const float* snr,
+                            const int32_t* db_id, int nsearch, const float* yobs, const float* dobs, const float* rot_cos,
+                            const float* rot_sin, const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
+                            double maxchisq, int bcalc, int strict_topk, float* invout, float* sfound, uint8_t* status_out) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    int rc = check_invert_args(ctx, mode, npix, sobs, snr, db_id, nsearch, yobs, dobs, rot_cos, rot_sin, dopp, grid, bcalc, invout, sfound);
+    if (rc) return rc;
+    if (npix == 0) return CLEDB_OK;
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)npix, k = (size_t)nsearch;
+    const size_t dsz = dopp ? (dopp_is_f64 ? 8 : 4) : 0;
+    if (dopp_stride <= 0) dopp_stride = 1;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = up256(off + b); return o; };
+    const size_t o_sobs = take(n * 32), o_snr = take(n * 32), o_id = take(n * 4), o_y = take(n * 4), o_d = take(n * 4),
+                 o_rc = take(n * 4), o_rs = take(n * 4), o_dopp = take(n * dsz),
+                 o_tab = take((size_t)(2 * grid->nbphi + 2 * grid->nbtheta) * 4), o_inv = take(n * k * 44), o_sf = take(n * k * 32),
+                 o_st = take(n);
+    if ((rc = ensure_workspace(ctx, ctx->io, off))) return rc;
+    unsigned char* w = reinterpret_cast<unsigned char*>(ctx->io.ptr);
+    cudaStream_t st = ctx->stream;
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_sobs, sobs, n * 32, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_snr, snr, n * 32, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_id, db_id, n * 4, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_y, yobs, n * 4, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_d, dobs, n * 4, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_rc, rot_cos, n * 4, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_rs, rot_sin, n * 4, cudaMemcpyHostToDevice, st));
+    const void* d_dopp = nullptr;
+    if (dopp) {
+        if (dopp_stride == 1) CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_dopp, dopp, n * dsz, cudaMemcpyHostToDevice, st));
+        else CLEDB_CUDA(ctx, cudaMemcpy2DAsync(w + o_dopp, dsz, dopp, (size_t)dopp_stride * dsz, dsz, n, cudaMemcpyHostToDevice, st));
+        d_dopp = w + o_dopp;
+    }
+    cledb_dbgrid g = *grid;
+    float* tab = reinterpret_cast<float*>(w + o_tab);
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab, grid->sin_bphi, (size_t)g.nbphi * 4, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab + g.nbphi, grid->cos_bphi, (size_t)g.nbphi * 4, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab + 2 * g.nbphi, grid->sin_btheta, (size_t)g.nbtheta * 4, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab + 2 * g.nbphi + g.nbtheta, grid->cos_btheta, (size_t)g.nbtheta * 4, cudaMemcpyHostToDevice, st));
+    g.sin_bphi = tab;
+    g.cos_bphi = tab + g.nbphi;
+    g.sin_btheta = tab + 2 * g.nbphi;
+    g.cos_btheta = tab + 2 * g.nbphi + g.nbtheta;
+    rc = cledb_invert_dev(ctx, mode, precision, npix, reinterpret_cast<float*>(w + o_sobs), reinterpret_cast<float*>(w + o_snr),
+                          reinterpret_cast<int32_t*>(w + o_id), nsearch, reinterpret_cast<float*>(w + o_y),
+                          reinterpret_cast<float*>(w + o_d), reinterpret_cast<float*>(w + o_rc), reinterpret_cast<float*>(w + o_rs),
+                          d_dopp, dopp_is_f64, 1, &g, maxchisq, bcalc, strict_topk, reinterpret_cast<float*>(w + o_inv),
+                          reinterpret_cast<float*>(w + o_sf), w + o_st, st);
+    if (rc) return rc;
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(invout, w + o_inv, n * k * 44, cudaMemcpyDeviceToHost, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(sfound, w + o_sf, n * k * 32, cudaMemcpyDeviceToHost, st));
+    if (status_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(status_out, w + o_st, n, cudaMemcpyDeviceToHost, st));
+    CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
+    return CLEDB_OK;
+}

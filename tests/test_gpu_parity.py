@@ -157,6 +157,32 @@ def test_invproc_golden_fp32(golden_dir, tag):
     assert (iss == g['issuemask_' + tag]).mean() > 0.98
 
 
+@pytest.mark.parametrize('tag', TAGS)
+@pytest.mark.parametrize('precision', [native.PREC_FP32, native.PREC_FP64])
+def test_device_solution_equals_host(golden_dir, tag, precision):
+    """Solutions built on the GPU (cledb_invert) == the NumPy host path on the same raw search result, bit for bit
+    (every float operation is in the reference's dtype and order; sines/cosines come from NumPy tables)."""
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    g, dbs = small_case(golden_dir)
+    hdr = hdr_from_g(g['hdr_g'])
+    res = {}
+    for where in ('host', 'device'):
+        procinv.OPTIONS.update(solution=where)
+        res[where] = run_surface(g['cfg_' + tag], g, dbs, hdr, 10, 12, precision, native.ENC_I16, 'sobs_' + tag)
+    procinv.OPTIONS.update(solution='device')
+    for a, b, name in zip(res['host'], res['device'], ('invout', 'sfound', 'issuemask')):
+        assert same(a, b), name
+    # a float64 Doppler input stays float64 through the field-strength arithmetic (NumPy promotion)
+    if tag == 'iqud':
+        g64 = {k: g[k] for k in g.files}
+        g64['sobs_dopp'] = g['sobs_dopp'].astype(np.float64) * 1.0000001
+        for where in ('host', 'device'):
+            procinv.OPTIONS.update(solution=where)
+            res[where] = run_surface(g['cfg_' + tag], g64, dbs, hdr, 10, 12, precision, native.ENC_I16, 'sobs_' + tag)
+        procinv.OPTIONS.update(solution='device')
+        assert same(res['host'][0], res['device'][0]) and same(res['host'][1], res['device'][1])
+
+
 def test_full_db_golden(golden_dir):
     """36 pixels against the full-size 340 200-entry database: validation kernel bit-exact, fp32 kernel in tolerance."""
     import CLEDB_PROC.CLEDB_PROC as procinv
