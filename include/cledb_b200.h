@@ -90,6 +90,20 @@ int cledb_db_decoded(cledb_ctx* ctx, int db_id, float* out);
 /* decoded rows by original index, rows_out[n,8]; idx < 0 gives zeros (database_sel[ixr,:], CLEDB_PROC.py:1064) */
 int cledb_gather_rows(cledb_ctx* ctx, int db_id, const int32_t* idx, int64_t n, float* rows_out);
 
+/* cledb_db_select: sdb_findelongationanddens (CLEDB_PREPINV.py:458-468) for every pixel of a map at once.
+ *   table[nfiles,3] float32 = dbynumbers of sdb_fileingest (CLEDB_PREPINV.py:402-412): file index, 100*height,
+ *   100*log10(density), in the order of the sorted file list.  For pixel p the files whose |height/100 - yobs[p]| is
+ *   minimal are found, and among the range [first match, last match) - the reference's slice never reaches the last
+ *   file of a height - the one whose |density/100 - dobs[p]| is smallest (first on ties); all in float32 as NumPy does.
+ *   file_out[p] = table[.,0] of that file, or CLEDB_SELECT_NAN (yobs is NaN: the reference raises IndexError) or
+ *   CLEDB_SELECT_EMPTY (a single file matches the height: the reference raises ValueError on the empty slice). */
+#define CLEDB_SELECT_NAN   -1
+#define CLEDB_SELECT_EMPTY -2
+int cledb_db_select(cledb_ctx* ctx, int64_t npix, const float* yobs, const float* dobs, int nfiles, const float* table,
+                    int32_t* file_out);
+int cledb_db_select_dev(cledb_ctx* ctx, int64_t npix, const float* yobs, const float* dobs, int nfiles, const float* table,
+                        int32_t* file_out, void* stream);
+
 /* ---- the search ------------------------------------------------------------------------------------ *
  * Replaces, for every pixel at once, the candidate selection, chi^2 evaluation and partial sort of
  * cledb_matchiquv / cledb_matchiqud (CLEDB_PROC.py:944-1013 / 1118-1188): for pixel p the nsearch smallest

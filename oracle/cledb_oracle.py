@@ -326,6 +326,26 @@ def nearest_database(y, d, dbynumbers):
     return np.int32(dbynumbers[first + dd, 0])
 
 
+def file_table(names):
+    """(index, 100*height, 100*log10 density) of a sorted list of database file names; CLEDB_PREPINV.py:402-412."""
+    at = str.find(names[0], 'DB_h')
+    table = np.empty((len(names), 3), dtype=np.float32)
+    for i in range(len(names)):
+        table[i, 0] = i
+        table[i, 1] = np.float32(names[i][at + 4:at + 7])
+        table[i, 2] = np.float32(names[i][at + 9:-4])
+    return table
+
+
+def select_databases(yobs, dobs, dbynumbers):
+    """``db_enc_flnm`` of sdb_preprocess (CLEDB_PREPINV.py:262-283): ``nearest_database`` for every pixel of a map."""
+    yobs, dobs = np.asarray(yobs), np.asarray(dobs)
+    out = np.zeros(yobs.shape, dtype=np.int32)
+    for pos in np.ndindex(*yobs.shape):
+        out[pos] = nearest_database(yobs[pos], dobs[pos], dbynumbers)
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # elementwise neighbours
 # --------------------------------------------------------------------------------------------------

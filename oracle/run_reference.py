@@ -66,8 +66,19 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def reference_first():
+    """The product mirrors the reference's module names (CLEDB_PROC, CLEDB_PREPINV, constants, ctrlparams): once the
+    input generator is imported, take the product directory off sys.path so that those names resolve to /root/reference."""
+    pkg = os.path.join(REPO, 'solar-coronal-inversion_b200')
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p) != pkg]
+    for name in list(sys.modules):
+        if name.split('.')[0] in ('CLEDB_PROC', 'CLEDB_PREPINV', 'constants', 'ctrlparams'):
+            del sys.modules[name]
+
+
 def main():
     import cledb_b200.synth as synth
+    reference_first()
     scratch = scratch_layout()
     os.chdir(scratch)
     raw_line_files(scratch, synth)

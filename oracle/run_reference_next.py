@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""Golden vectors for the rows SURVEY.md section 8(f) marks "next", from the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
+
+    python oracle/run_reference_next.py        # (re)writes tests/golden/dbselect.npz
+
+Runs only in the build container (needs /root/reference).  Same recipe as oracle/run_reference.py: astropy stub, scratch
+working directory that mirrors the relative paths the reference opens.
+
+dbselect.npz
+  * the reference's ``sdb_findelongationanddens`` on a file table shaped like the full 99 x 121 (height, density) grid in the
+    order ``sorted(glob(...))`` gives it (``d1000`` before ``d600``), for 4 000 seeded (height, density) pairs including exact
+    grid points, mid-points and out-of-range values;
+  * the reference's ``sdb_preprocess`` (verbose = 4, its unit-test switch) over a 9 x 8 map on a scratch directory of
+    4 heights x 5 densities of small synthetic PyCELP-type files: db_enc, db_enc_flnm, db_uniq, file names and a SHA-256 of
+    every normalised database it returns.
+"""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, 'oracle'))
+import run_reference as rr  # noqa: E402  (sets sys.path for the reference + stub, provides the scratch layout)
+import numpy as np  # noqa: E402
+
+MINI_HEIGHTS = (106, 109, 112, 120)
+MINI_DENS = (600, 795, 895, 1000, 1200)
+MINI_SHAPE = dict(ngx=3, nbphi=12, nbtheta=8)
+
+
+def mini_files(root, synth):
+    """4 x 5 small synthetic per-line files DB_h###_d###.npy under root/fe-xiii_107{4,9}/ (un-normalised, V per Angstrom)."""
+    rng = np.random.default_rng(4242)
+    for h in MINI_HEIGHTS:
+        for d in MINI_DENS:
+            l1, l2 = synth.make_raw_line_pair(h - 101, (d - 600) // 5, rng, **MINI_SHAPE)
+            name = 'DB_h%03d_d%d.npy' % (h, d)
+            np.save(os.path.join(root, 'fe-xiii_1074', name), l1)
+            np.save(os.path.join(root, 'fe-xiii_1079', name), l2)
+
+
+def mini_map():
+    rng = np.random.default_rng(77)
+    nx, ny = 9, 8
+    yobs = rng.uniform(1.03, 1.23, (nx, ny)).astype(np.float32)
+    dobs = rng.uniform(5.5, 12.5, (nx, ny)).astype(np.float32)
+    yobs[0, 0], dobs[0, 0] = np.float32(1.09), np.float32(7.95)        # exact grid point
+    yobs[0, 1], dobs[0, 1] = np.float32(1.075), np.float32(8.45)       # mid-points (ties in float32 or not: as NumPy decides)
+    yobs[0, 2], dobs[0, 2] = np.float32(1.2), np.float32(12.0)         # the last density of a height is never selected
+    yobs[0, 3], dobs[0, 3] = np.float32(0.9), np.float32(3.0)          # below every grid value
+    yobs[0, 4], dobs[0, 4] = np.float32(3.0), np.float32(20.0)         # above every grid value
+    dobs[0, 5] = np.nan                                                # NaN density: argmin returns the first NaN
+    return nx, ny, yobs, dobs
+
+
+def main():
+    import cledb_b200.synth as synth
+    rr.reference_first()
+    scratch = rr.scratch_layout()
+    os.chdir(scratch)
+    import CLEDB_PREPINV.CLEDB_PREPINV as prepinv
+    import ctrlparams
+    assert prepinv.__file__.startswith(rr.REF), prepinv.__file__
+    out = {}
+
+    # ---- selection on a full-grid-shaped table
+    names = sorted('DB_h%03d_d%d.npy' % (101 + h, 600 + 5 * d) for h in range(99) for d in range(121))
+    at = names[0].find('DB_h')
+    table = np.empty((len(names), 3), dtype=np.float32)
+    for i, n in enumerate(names):
+        table[i] = (i, np.float32(n[at + 4:at + 7]), np.float32(n[at + 9:-4]))
+    rng = np.random.default_rng(31)
+    ny = 4000
+    ys = rng.uniform(0.95, 2.05, ny).astype(np.float32)
+    ds = rng.uniform(5.5, 12.5, ny).astype(np.float32)
+    ys[:200] = (np.float32(1.01) + np.float32(0.01) * rng.integers(0, 99, 200)).astype(np.float32)     # on the grid
+    ds[100:300] = (np.float32(6.0) + np.float32(0.05) * rng.integers(0, 121, 200)).astype(np.float32)
+    ys[300:400] = (np.float32(1.015) + np.float32(0.01) * rng.integers(0, 98, 100)).astype(np.float32)  # between two heights
+    ds[400:500] = (np.float32(6.025) + np.float32(0.05) * rng.integers(0, 120, 100)).astype(np.float32)
+    sel = np.array([prepinv.sdb_findelongationanddens(0, 0, ys[i], ds[i], table)[2] for i in range(ny)], dtype=np.int32)
+    out.update(grid_names=np.array(names), grid_table=table, grid_y=ys, grid_d=ds, grid_sel=sel)
+    print('grid selection: %d pairs, %d distinct files' % (ny, np.unique(sel).size))
+
+    # ---- sdb_preprocess on the mini grid
+    for line in ('fe-xiii_1074', 'fe-xiii_1079'):
+        for f in os.listdir(os.path.join('tests', 'dbfiles', line)):
+            if f.endswith('.npy'):
+                os.remove(os.path.join('tests', 'dbfiles', line, f))
+    mini_files(os.path.join(scratch, 'tests', 'dbfiles'), synth)
+    nx, nyy, yobs, dobs = mini_map()
+    params = ctrlparams.ctrlparams()
+    params.verbose = 4
+    params.ncpu = 4
+    keyvals = synth.make_keyvals(nx, nyy)
+    wlarr = np.array([[1074.2571372 + 0.00538654 * i for i in range(4)], [1079.4203968 + 0.00541243 * i for i in range(4)]])
+    db_enc, database, dbhdr, dbnames, db_enc_flnm, db_uniq = prepinv.sdb_preprocess(yobs, dobs, keyvals, wlarr, params)
+    out.update(mini_yobs=yobs, mini_dobs=dobs, mini_db_enc=db_enc, mini_db_enc_flnm=db_enc_flnm, mini_db_uniq=db_uniq,
+               mini_names=np.array([os.path.basename(n) for n in dbnames[0]]), mini_wlarr=wlarr, mini_hdr_g=dbhdr[0],
+               mini_sha=np.array([rr.sha(np.asarray(d)) for d in database]),
+               mini_shape=np.array(np.asarray(database[0]).shape))
+    print('sdb_preprocess: %d distinct databases of shape %s, db_enc[0] = %s' % (len(database), np.asarray(database[0]).shape, db_enc[0]))
+    np.savez_compressed(os.path.join(rr.GOLDEN, 'dbselect.npz'), **out)
+    import shutil
+    shutil.rmtree(scratch, ignore_errors=True)
+
+
+if __name__ == '__main__':
+    main()

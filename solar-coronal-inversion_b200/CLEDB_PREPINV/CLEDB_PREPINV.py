@@ -2,13 +2,20 @@
 
     obs_qurotate(sobs_tot, keyvals, hpxygrid) -> (sobs_totrot, aobs)      CLEDB_PREPINV.py:1277-1350
     obs_calcheight(keyvals, hpxygrid)          -> yobs                    CLEDB_PREPINV.py:897-926
-    sdb_parseheader(dbheaderfile)              -> dbhdr 15-tuple          CLEDB_PREPINV.py:475-508
+    sdb_preprocess(yobs, dobs, keyvals, wlarr, params) -> (db_enc, database, dbhdr)   CLEDB_PREPINV.py:201-367
+    sdb_fileingest / sdb_findelongationanddens / sdb_read / sdb_parseheader / sdb_lcgrid   CLEDB_PREPINV.py:380-569
     iss_block(x)                                                          CLEDB_PREPINV.py:1563-1576
 
-The rotation and the height map are one fused elementwise kernel (72 B/pixel) behind the C-ABI.  Instrument
-header ingestion, spectral integration and the density look-up of ``sobs_preprocess`` are outside the scope of
-this build.
+The rotation and the height map are one fused elementwise kernel (72 B/pixel) behind the C-ABI.  ``sdb_preprocess``
+picks the (height, density) database of every pixel with one kernel over the whole map (``cledb_db_select``) instead of
+a pool task per pixel, loads and normalises only the distinct files, and uploads them to HBM once, so that
+``cledb_invproc`` finds them resident.  Instrument header ingestion, spectral integration and the density look-up
+of ``sobs_preprocess`` are outside the scope of this build.
 """
+import glob
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 from cledb_b200 import native
@@ -77,3 +84,129 @@ def sdb_parseheader(dbheaderfile):
     return (g, ned, ngx, nbphi, nbtheta, sdb_lcgrid(np.float32(g[5]), np.float32(g[6]), ned),
             np.float32(g[7]), np.float32(g[8]), np.float32(g[9]), np.float32(g[10]), np.float32(g[11]), np.float32(g[12]),
             nline, wavel, np.int32(g[-1]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# database side: which file for which pixel, load the distinct ones, make them resident
+# ---------------------------------------------------------------------------------------------------------
+_ION_DIRS = ("fe-xiii_1074/", "fe-xiii_1079/", "si-x_1430/", "si-ix_3934/", "mg-viii_3028/")
+_INGEST_ERROR = ([None, None], None, 'Ingest Error')
+
+
+def sdb_fileingest(dbdir, nline, tline, verbose):
+    """File names and the (index, 100*height, 100*log density) table of a database directory; CLEDB_PREPINV.py:380-451.
+
+    Returns ``([names_line1, names_line2], dbynumbers[nfiles,3] float32, [subdir1, subdir2])`` or the ingest-error triple
+    ``([None, None], None, 'Ingest Error')``.  File order is Python's lexicographic ``sorted`` of the glob, exactly as in
+    the reference (so ``d1000`` sorts before ``d600``); heights are characters 4..6 and densities characters 9..-4 after
+    ``DB_h``.  Which sub-directories are taken follows the reference's own pairing rule (:402-405).
+    """
+    present = [os.path.isdir(dbdir + d) for d in _ION_DIRS]
+    npresent = int(np.sum(present))
+    if nline == 2:
+        if npresent >= 2:
+            where = np.where(present)[0]
+            subdirs = [_ION_DIRS[where[i]] for i in range(npresent) if _ION_DIRS[i][:-1] in (tline[0], tline[1])]
+            names = [sorted(glob.glob(dbdir + subdirs[0] + "DB_*")), sorted(glob.glob(dbdir + subdirs[1] + "DB_*"))]
+            at = names[0][0].find('DB_h')
+            table = np.empty((len(names[0]), 3), dtype=np.float32)
+            for i, name in enumerate(names[0]):
+                table[i] = (i, np.float32(name[at + 4:at + 7]), np.float32(name[at + 9:-4]))
+            return names, table, subdirs
+        if verbose >= 2 and verbose < 4:
+            print("SDB_FILEINGEST: FATAL! Two line observation provided! Requires two individual ion databases in directory. "
+                  "Only one database is computed." if npresent == 1 else
+                  "SDB_FILEINGEST: FATAL! No database or incomplete calculations found in directory ")
+        return _INGEST_ERROR
+    # one-line database ingestion is unfinished upstream (CLEDB_PREPINV.py:434-446 cannot run); report it as an ingest error
+    if verbose >= 1 and verbose < 4:
+        print("SDB_FILEINGEST: one-line observations are solved analytically (blos_proc); no database is loaded.")
+    return _INGEST_ERROR
+
+
+def _select_files(yobs, dobs, dbynumbers):
+    """Nearest database file of every pixel (cledb_db_select); raises what the reference raises for impossible pixels."""
+    sel = native.get_context(OPTIONS['device']).db_select(yobs, dobs, dbynumbers)
+    if (sel == -1).any():
+        raise IndexError("index 0 is out of bounds for axis 0 with size 0")      # NaN height: CLEDB_PREPINV.py:465-466
+    if (sel == -2).any():
+        raise ValueError("attempt to get argmin of an empty sequence")           # one file at that height: the empty slice of :466
+    return sel
+
+
+def sdb_findelongationanddens(xx, yy, y, d, dbynumbers):
+    """Database file index for one pixel; CLEDB_PREPINV.py:458-468.  Returns ``(xx, yy, index)``."""
+    return xx, yy, np.int32(_select_files(np.float32(y), np.float32(d), dbynumbers)[0])
+
+
+def sdb_read(fildb, dbhdr, verbose):
+    """One database file as the generator wrote it; CLEDB_PREPINV.py:514-553 (PyCELP ``.npy`` or raw CLE float32)."""
+    dbcgrid, ned, ngx, nbphi, nbtheta, xed, gxmin, gxmax, bphimin, bphimax, bthetamin, bthetamax, nline, wavel, dbtype = dbhdr
+    if verbose >= 2 and verbose < 4:
+        print("INDIVIDUAL DB file location:", fildb)
+    if dbtype == 0:
+        return np.reshape(np.fromfile(fildb, dtype=np.float32), (ned, ngx, nbphi, nbtheta, nline * 4))
+    return np.load(fildb)
+
+
+def _two_line_database(file1, file2, dbhdr, wl0, verbose):
+    """Both lines side by side, every component divided by I1 (component 0 last, so that it ends up exactly 1); PyCELP
+    Stokes V additionally scaled by the nm/Angstrom factor; CLEDB_PREPINV.py:306-317."""
+    db = np.append(sdb_read(file1, dbhdr, verbose), sdb_read(file2, dbhdr, verbose), axis=-1)
+    with np.errstate(all='ignore'):
+        if dbhdr[-1] == 1:
+            vscale = 10 ** np.rint(np.log10(wl0 / 10000))
+            for comp in range(7, -1, -1):
+                if comp in (3, 7):
+                    db[..., comp] = vscale * db[..., comp] / db[..., 0]
+                else:
+                    db[..., comp] = db[..., comp] / db[..., 0]
+        else:
+            for comp in range(7, -1, -1):
+                db[..., comp] = db[..., comp] / db[..., 0]
+    return db
+
+
+def sdb_preprocess(yobs, dobs, keyvals, wlarr, params):
+    """Find, load and make resident every database the observation needs; CLEDB_PREPINV.py:201-367.
+
+    Returns ``(db_enc[nx,ny] int32, database (list of float32 arrays), dbhdr)``; with ``params.verbose == 4`` (the
+    reference's unit-test switch, which also redirects to ``./tests/dbfiles/``) additionally ``dbnames, db_enc_flnm,
+    db_uniq``; ``(None, None, None)`` when no database directory can be ingested.
+    """
+    chatty = params.verbose >= 1 and params.verbose < 4
+    if chatty:
+        print('------------------------------------\n----SDB_PREPROCESS - READ START-----\n------------------------------------')
+    nx, ny, nline, tline = keyvals[0], keyvals[1], keyvals[3], keyvals[4]
+    dbdir = params.dbdir if params.verbose != 4 else "./tests/dbfiles/"
+    dbnames, dbynumbers, dbsubdirs = sdb_fileingest(dbdir, nline, tline, params.verbose)
+    if dbsubdirs == 'Ingest Error':
+        if chatty:
+            print("SDB_PREPROCESS: FATAL! Could not read database.")
+        return None, None, None
+
+    # one kernel over the map instead of one pool task per pixel
+    db_enc_flnm = _select_files(np.asarray(yobs, dtype=np.float32).reshape(-1), np.asarray(dobs, dtype=np.float32).reshape(-1),
+                                dbynumbers).reshape(nx, ny).astype(np.int32)
+    db_uniq = np.unique(db_enc_flnm)
+    if chatty:
+        print("Available CLEDB databases cover a span of", len(np.unique(dbynumbers[:, 1])), "solar heights between",
+              dbynumbers[0, 1] / 100, "-", dbynumbers[-1, 1] / 100, " radius")
+        print("Load ", db_uniq.shape[0], " heights x densities  DB datafiles in memory for each of ", nline,
+              "line(s).\n------------------------------------")
+    dbhdr = sdb_parseheader(dbdir + dbsubdirs[0] + 'db.hdr')
+    if nline != 2:
+        raise NotImplementedError("cledb_b200: only two-line databases are searched (one-line data is solved by blos_proc)")
+    wl0 = wlarr[0, 0]
+    with ThreadPoolExecutor(max_workers=max(1, min(8, db_uniq.shape[0]))) as pool:      # file reads overlap
+        database = list(pool.map(lambda u: _two_line_database(dbnames[0][u], dbnames[1][u], dbhdr, wl0, params.verbose), db_uniq))
+    db_enc = np.searchsorted(db_uniq, db_enc_flnm).astype(np.int32)        # position of a pixel's file in the loaded list
+
+    # make the distinct databases resident now: cledb_invproc recognises the arrays and does not upload them again
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    procinv.make_resident(database)
+    if chatty:
+        print('------------------------------------\n--SDB_PREPROCESS - READ FINALIZED---\n------------------------------------')
+    if params.verbose == 4:
+        return db_enc, database, dbhdr, dbnames, db_enc_flnm, db_uniq
+    return db_enc, database, dbhdr

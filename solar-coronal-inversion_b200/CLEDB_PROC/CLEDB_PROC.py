@@ -88,6 +88,12 @@ def _upload(database, used):
     return ctx, {int(k): res.ensure(ctx, database[int(k)], OPTIONS['dbencoding']) for k in used}
 
 
+def make_resident(database):
+    """Upload every array of ``database`` to HBM now (used by ``sdb_preprocess``); a later ``cledb_invproc`` with the same
+    arrays finds them resident."""
+    _upload(database, range(len(database)))
+
+
 def _search_and_build(mode, sobs, sobs_dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc):
     """Flattened pixels in, (invout[npix,k,11], sfound[npix,k,8]) out."""
     sobs = np.ascontiguousarray(sobs, dtype=np.float32).reshape(-1, 8)

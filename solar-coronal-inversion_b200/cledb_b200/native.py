@@ -17,6 +17,12 @@ ENC_F32, ENC_I16 = 0, 1
 PREC_FP32, PREC_FP64 = 0, 1
 MAX_NSEARCH = 32
 PIX_SEARCHED, PIX_NULL, PIX_ALLNAN, PIX_REFRAISES, PIX_ALLINF = 0, 1, 2, 3, 4
+SELECT_NAN, SELECT_EMPTY = -1, -2
+
+
+def lib_const(name):
+    """Value of a ``#define`` of include/cledb_b200.h by name (the tests read the constants through here)."""
+    return {'CLEDB_SELECT_NAN': SELECT_NAN, 'CLEDB_SELECT_EMPTY': SELECT_EMPTY}[name]
 
 # every symbol include/cledb_b200.h declares, with (restype, argtypes)
 _c = ctypes
@@ -37,6 +43,8 @@ SIGNATURES = {
     'cledb_db_info': (_c.c_int, [_P, _c.c_int, _P]),
     'cledb_db_decoded': (_c.c_int, [_P, _c.c_int, _P]),
     'cledb_gather_rows': (_c.c_int, [_P, _c.c_int, _P, _c.c_int64, _P]),
+    'cledb_db_select': (_c.c_int, [_P, _c.c_int64, _P, _P, _c.c_int, _P, _P]),
+    'cledb_db_select_dev': (_c.c_int, [_P, _c.c_int64, _P, _P, _c.c_int, _P, _P, _P]),
     'cledb_match': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_match_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_set_tuning': (_c.c_int, [_P, _c.c_int, _c.c_int]),
@@ -215,6 +223,16 @@ class Context:
         idx = _as(idx, np.int32).reshape(-1)
         out = np.empty((idx.size, 8), dtype=np.float32)
         self._check(self.lib.cledb_gather_rows(self.h, int(db_id), _ptr(idx), idx.size, _ptr(out)))
+        return out
+
+    def db_select(self, yobs, dobs, dbynumbers):
+        """File index of the nearest (height, density) database for every pixel; sdb_findelongationanddens.
+        Negative entries mark the pixels for which the reference raises (see the header)."""
+        y = _as(np.asarray(yobs).reshape(-1), np.float32)
+        d = _as(np.asarray(dobs).reshape(-1), np.float32)
+        t = _as(dbynumbers, np.float32).reshape(-1, 3)
+        out = np.empty(y.size, dtype=np.int32)
+        self._check(self.lib.cledb_db_select(self.h, y.size, _ptr(y), _ptr(d), t.shape[0], _ptr(t), _ptr(out)))
         return out
 
     # ---- search

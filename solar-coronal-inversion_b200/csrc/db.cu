@@ -1,6 +1,8 @@
 // Database residency: sign partitioning, int16 encoding, upload.  Replaces the per-task pickling of
 // database[db_enc[xx,yy]] (CLEDB_PROC.py:304-307) and the per-pixel argwhere/gather on sign(V1)
 // (CLEDB_PROC.py:974-976) of the reference: both are done once per database here.
+#include <math_constants.h>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -381,6 +383,77 @@ extern "C" int cledb_gather_rows(cledb_ctx* ctx, int db_id, const int32_t* idx, 
     CLEDB_CUDA(ctx, cudaMemcpyAsync(d_idx, idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = launch_gather_rows(ctx, it->second, d_idx, n, d_rows, ctx->stream))) return rc;
     CLEDB_CUDA(ctx, cudaMemcpyAsync(rows_out, d_rows, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CLEDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CLEDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// database selection per pixel: sdb_findelongationanddens (CLEDB_PREPINV.py:458-468)
+// ------------------------------------------------------------------------------------------------------
+namespace cledb {
+// One thread per pixel; the table is a few thousand rows that every lane reads at the same address (broadcast, cached).
+__global__ void __launch_bounds__(256) k_db_select(int64_t npix, const float* __restrict__ yobs, const float* __restrict__ dobs,
+                                                   int nfiles, const float* __restrict__ table, int32_t* __restrict__ out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const float y = yobs[p], d = dobs[p];
+    if (isnan(y)) { out[p] = CLEDB_SELECT_NAN; return; }              // np.min is NaN, argwhere(x == NaN) is empty
+    float best = CUDART_INF_F;
+    for (int i = 0; i < nfiles; ++i) best = fminf(best, fabsf(__fsub_rn(__fdiv_rn(table[3 * i + 1], 100.0f), y)));
+    int first = -1, last = -1;
+    for (int i = 0; i < nfiles; ++i) {
+        if (fabsf(__fsub_rn(__fdiv_rn(table[3 * i + 1], 100.0f), y)) == best) {
+            if (first < 0) first = i;
+            last = i;
+        }
+    }
+    if (first < 0) { out[p] = CLEDB_SELECT_NAN; return; }             // only with NaN heights in the table
+    if (last <= first) { out[p] = CLEDB_SELECT_EMPTY; return; }       // argmin of an empty slice raises
+    int arg = first;
+    float bd = fabsf(__fsub_rn(__fdiv_rn(table[3 * first + 2], 100.0f), d));
+    if (!isnan(bd)) {                                                 // np.argmin returns the first NaN if there is one
+        for (int i = first + 1; i < last; ++i) {
+            const float v = fabsf(__fsub_rn(__fdiv_rn(table[3 * i + 2], 100.0f), d));
+            if (isnan(v)) { arg = i; break; }
+            if (v < bd) { bd = v; arg = i; }
+        }
+    }
+    out[p] = (int32_t)table[3 * arg];
+}
+}  // namespace cledb
+
+extern "C" int cledb_db_select_dev(cledb_ctx* ctx, int64_t npix, const float* yobs, const float* dobs, int nfiles,
+                                   const float* table, int32_t* file_out, void* stream) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    if (npix < 0 || nfiles < 1 || !yobs || !dobs || !table || !file_out) { ctx->err = "cledb_db_select: bad argument"; return CLEDB_ERR_ARG; }
+    if (npix == 0) return CLEDB_OK;
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    k_db_select<<<(int)((npix + 255) / 256), 256, 0, st>>>(npix, yobs, dobs, nfiles, table, file_out);
+    ctx->launches++;
+    CLEDB_CUDA(ctx, cudaGetLastError());
+    return CLEDB_OK;
+}
+
+extern "C" int cledb_db_select(cledb_ctx* ctx, int64_t npix, const float* yobs, const float* dobs, int nfiles, const float* table,
+                               int32_t* file_out) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    if (npix < 0 || nfiles < 1 || !yobs || !dobs || !table || !file_out) { ctx->err = "cledb_db_select: bad argument"; return CLEDB_ERR_ARG; }
+    if (npix == 0) return CLEDB_OK;
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)npix;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_y = 0, o_d = up(n * 4), o_t = o_d + up(n * 4), o_o = o_t + up((size_t)nfiles * 12), total = o_o + up(n * 4);
+    int rc = ensure_workspace(ctx, ctx->io, total);
+    if (rc) return rc;
+    unsigned char* w = reinterpret_cast<unsigned char*>(ctx->io.ptr);
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_y, yobs, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_d, dobs, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_t, table, (size_t)nfiles * 12, cudaMemcpyHostToDevice, ctx->stream));
+    rc = cledb_db_select_dev(ctx, npix, reinterpret_cast<float*>(w + o_y), reinterpret_cast<float*>(w + o_d), nfiles,
+                             reinterpret_cast<float*>(w + o_t), reinterpret_cast<int32_t*>(w + o_o), ctx->stream);
+    if (rc) return rc;
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(file_out, w + o_o, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CLEDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CLEDB_OK;
 }

@@ -324,3 +324,73 @@ def test_error_paths(ctx):
     assert raw['idx'][0, 0] == 2 and (raw['idx'][0, 5:] == -1).all() and sorted(raw['idx'][0, :5]) == [0, 1, 2, 3, 4]
     ctx.db_drop(0)
     ctx.db_drop(1)
+
+
+def test_database_selection_kernel(ctx, golden_dir):
+    """cledb_db_select == sdb_findelongationanddens of the unmodified reference on 4 000 (height, density) pairs over a
+    full-grid-shaped file table, bit-exact; the pixels for which the reference raises are reported, not guessed."""
+    g = np.load(os.path.join(golden_dir, 'dbselect.npz'))
+    sel = ctx.db_select(g['grid_y'], g['grid_d'], g['grid_table'])
+    assert np.array_equal(sel, g['grid_sel'])
+    y = np.array([np.nan, 1.09, 1.2], np.float32)
+    d = np.array([8.0, np.nan, 8.0], np.float32)
+    tab = np.array([[0, 109, 600], [1, 109, 795], [2, 109, 895], [3, 120, 800]], np.float32)
+    assert ctx.db_select(y, d, tab).tolist() == [native.lib_const('CLEDB_SELECT_NAN'), 0, native.lib_const('CLEDB_SELECT_EMPTY')]
+    # property on a big map: the chosen file is at the nearest height, and no other file of the slice is closer in density
+    rng = np.random.default_rng(3)
+    yy, dd = rng.uniform(1.01, 1.99, 200000).astype(np.float32), rng.uniform(6, 12, 200000).astype(np.float32)
+    big = ctx.db_select(yy, dd, g['grid_table'])
+    t = g['grid_table']
+    hdiff = np.abs(t[big, 1] / np.float32(100.) - yy)
+    assert (hdiff <= np.float32(0.0050001)).all()
+
+
+def test_sdb_preprocess_surface(golden_dir, tmp_path, monkeypatch):
+    """CLEDB_PREPINV.sdb_preprocess on a scratch database directory == the unmodified reference (db_enc, the file list, the
+    distinct files and the normalised arrays), and the databases it leaves resident are the ones cledb_invproc then uses."""
+    import CLEDB_PREPINV.CLEDB_PREPINV as prepinv
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    import ctrlparams
+    g = np.load(os.path.join(golden_dir, 'dbselect.npz'))
+    root = tmp_path / 'tests' / 'dbfiles'
+    rng = np.random.default_rng(4242)
+    for line in ('fe-xiii_1074', 'fe-xiii_1079'):
+        (root / line).mkdir(parents=True)
+        (root / line / 'db.hdr').write_text(' '.join(repr(float(v)) for v in g['mini_hdr_g']))
+    for h in (106, 109, 112, 120):
+        for d in (600, 795, 895, 1000, 1200):
+            l1, l2 = synth.make_raw_line_pair(h - 101, (d - 600) // 5, rng, ngx=3, nbphi=12, nbtheta=8)
+            np.save(root / 'fe-xiii_1074' / ('DB_h%03d_d%d.npy' % (h, d)), l1)
+            np.save(root / 'fe-xiii_1079' / ('DB_h%03d_d%d.npy' % (h, d)), l2)
+    monkeypatch.chdir(tmp_path)
+    params = ctrlparams.ctrlparams()
+    params.verbose = 4                                   # the reference's unit-test switch: ./tests/dbfiles/ + extended return
+    nx, ny = g['mini_yobs'].shape
+    kv = synth.make_keyvals(nx, ny)
+    procinv.OPTIONS.update(precision=0, dbencoding=native.ENC_F32, solution='device')
+    db_enc, database, dbhdr, dbnames, flnm, uniq = prepinv.sdb_preprocess(g['mini_yobs'], g['mini_dobs'], kv, g['mini_wlarr'], params)
+    assert np.array_equal(db_enc, g['mini_db_enc']) and db_enc.dtype == np.int32
+    assert np.array_equal(flnm, g['mini_db_enc_flnm']) and np.array_equal(uniq, g['mini_db_uniq'])
+    assert [os.path.basename(n) for n in dbnames[0]] == [str(n) for n in g['mini_names']]
+    import hashlib
+    assert [hashlib.sha256(np.ascontiguousarray(d).tobytes()).hexdigest() for d in database] == [str(x) for x in g['mini_sha']]
+    assert same(dbhdr[0], g['mini_hdr_g'])
+    # the arrays are resident: an inversion with them uploads nothing new
+    before = len(procinv._resident[procinv.OPTIONS['device']].ids)
+    obs = synth.make_observation(nx, ny, database, db_enc=db_enc, seed=3)
+    hdr = synth.make_dbhdr(3, 12, 8)
+    iss = obs['issuemask'].copy()
+    inv, sf = procinv.cledb_invproc(obs['sobs_totrot'], obs['sobs_dopp'], database, db_enc, g['mini_yobs'], obs['aobs'], g['mini_dobs'],
+                                    obs['snr'], iss, hdr, kv, 4, 1000, 0, False, 1, False, 0)
+    assert len(procinv._resident[procinv.OPTIONS['device']].ids) == before
+    iss2 = obs['issuemask'].copy()
+    ref, ref_sf = orc.invert_map(obs['sobs_totrot'], obs['sobs_dopp'], database, db_enc, g['mini_yobs'], obs['aobs'], g['mini_dobs'],
+                                 obs['snr'], iss2, hdr, kv, 4, 1000, 0, False)
+    assert (inv[..., 0] == ref[..., 0]).mean() > 0.97
+    np.testing.assert_allclose(inv[..., 1], ref[..., 1], rtol=CHI_RTOL, atol=CHI_ATOL)
+    # ingest errors keep the reference's convention
+    params.verbose = 0
+    params.dbdir = str(tmp_path / 'nowhere') + '/'
+    assert prepinv.sdb_preprocess(g['mini_yobs'], g['mini_dobs'], kv, g['mini_wlarr'], params) == (None, None, None)
+    procinv.release_databases()
+    procinv.OPTIONS.update(precision=0, dbencoding=0)

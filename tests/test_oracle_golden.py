@@ -139,3 +139,31 @@ def test_selection_quirk_examples():
     assert orc.selection_positions(np.array([1, 5, 6, 0, 7.]), 2).tolist() == [3, 3]
     assert orc.selection_positions(np.array([2, 1, 6, 0, 7, 0.5]), 4).tolist() == [3, 5, 5, 3]
     assert orc.stable_topk(np.array([2, 1, 6, 0, 7, 0.5]), 4).tolist() == [3, 5, 1, 0]
+
+
+def test_database_selection(golden_dir):
+    """sdb_findelongationanddens / sdb_preprocess of the unmodified reference (oracle/run_reference_next.py): file table
+    in sorted-glob order, nearest (height, density) file per pixel including the never-selected last density, the list of
+    distinct files, the per-pixel position in it and the normalised databases."""
+    g = np.load(os.path.join(golden_dir, 'dbselect.npz'))
+    names = [str(n) for n in g['grid_names']]
+    table = orc.file_table(names)
+    assert same(table, g['grid_table'])
+    sel = np.array([orc.nearest_database(g['grid_y'][i], g['grid_d'][i], table) for i in range(0, g['grid_y'].size, 5)], np.int32)
+    assert np.array_equal(sel, g['grid_sel'][::5])
+    mini = [str(n) for n in g['mini_names']]
+    assert mini == sorted(mini) and mini.index('DB_h106_d1000.npy') < mini.index('DB_h106_d600.npy')
+    flnm = orc.select_databases(g['mini_yobs'], g['mini_dobs'], orc.file_table(mini))
+    assert np.array_equal(flnm, g['mini_db_enc_flnm'])
+    uniq = np.unique(flnm)
+    assert np.array_equal(uniq, g['mini_db_uniq'])
+    assert np.array_equal(np.searchsorted(uniq, flnm), g['mini_db_enc'])
+    last_of_height = [i for i, n in enumerate(mini) if i + 1 == len(mini) or mini[i + 1][:8] != n[:8]]
+    assert not np.isin(flnm, last_of_height).any(), 'the reference never selects the last file of a height'
+    rng = np.random.default_rng(4242)                        # same stream as oracle/run_reference_next.py:mini_files
+    shas = {}
+    for h in (106, 109, 112, 120):
+        for d in (600, 795, 895, 1000, 1200):
+            l1, l2 = synth.make_raw_line_pair(h - 101, (d - 600) // 5, rng, ngx=3, nbphi=12, nbtheta=8)
+            shas['DB_h%03d_d%d.npy' % (h, d)] = sha(orc.normalise_database(l1, l2, g['mini_wlarr'][0, 0]))
+    assert [shas[mini[u]] for u in uniq] == [str(x) for x in g['mini_sha']]
