@@ -210,3 +210,11 @@ def sdb_preprocess(yobs, dobs, keyvals, wlarr, params):
     if params.verbose == 4:
         return db_enc, database, dbhdr, dbnames, db_enc_flnm, db_uniq
     return db_enc, database, dbhdr
+
+
+def __getattr__(name):
+    """Names outside the accelerated path (e.g. sobs_preprocess) come from the reference's own module, see cledb_b200/passthrough.py."""
+    if name.startswith('__'):
+        raise AttributeError(name)
+    from cledb_b200.passthrough import reference_attr
+    return reference_attr('CLEDB_PREPINV/CLEDB_PREPINV.py', name, globals())

@@ -221,3 +221,11 @@ def iss_block(x):
     """Issue codes set in one issuemask value (list of powers of two, zeros for clear bits); CLEDB_PREPINV.py:1563-1576."""
     x = int(x)
     return [(1 << b) if (x >> b) & 1 else 0 for b in range(x.bit_length())] if x > 0 else []
+
+
+def __getattr__(name):
+    """Names outside the accelerated path (e.g. spectro_proc) come from the reference's own module, see cledb_b200/passthrough.py."""
+    if name.startswith('__'):
+        raise AttributeError(name)
+    from cledb_b200.passthrough import reference_attr
+    return reference_attr('CLEDB_PROC/CLEDB_PROC.py', name, globals())

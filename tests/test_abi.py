@@ -129,3 +129,29 @@ def test_ctrlparams_and_constants_surface():
     assert consts.Constants('fe-xiii_1079').g_eff == 1.5 and consts.Constants('si-x_1430').F_factor == 0.5
     k = 1.e9 * (c.planckconst * c.l_speed / c.bohrmagneton / (c.line_ref ** 2))
     assert abs(k - 185481.06) < 0.5
+
+
+def test_out_of_scope_names_pass_through_to_the_reference(tmp_path, monkeypatch):
+    """The drop-in modules shadow the reference's; names they do not define resolve to the reference's module by file path,
+    names of the hot path never do."""
+    import importlib
+    ref = tmp_path / 'ref'
+    (ref / 'CLEDB_PREPINV').mkdir(parents=True)
+    (ref / 'CLEDB_PREPINV' / 'CLEDB_PREPINV.py').write_text(
+        "def sobs_preprocess(a, b, c):\n    return ('from the reference', a)\n"
+        "def calls_hot_path():\n    return obs_qurotate\n"
+        "def obs_qurotate(*a):\n    raise RuntimeError('hot-path name must not be taken from the reference')\n")
+    monkeypatch.setenv('CLEDB_REFERENCE_ROOT', str(ref))
+    import cledb_b200.passthrough as pt
+    pt._loaded.clear()
+    prepinv = importlib.import_module('CLEDB_PREPINV.CLEDB_PREPINV')
+    assert prepinv.sobs_preprocess(1, 2, 3) == ('from the reference', 1)
+    assert prepinv.obs_qurotate.__module__ == 'CLEDB_PREPINV.CLEDB_PREPINV'
+    assert prepinv.calls_hot_path() is prepinv.obs_qurotate      # reference code that calls a hot-path function gets the B200 one
+    with pytest.raises(AttributeError):
+        prepinv.no_such_function
+    pt._loaded.clear()
+    monkeypatch.setenv('CLEDB_REFERENCE_ROOT', str(tmp_path / 'missing'))
+    with pytest.raises(AttributeError, match='CLEDB_REFERENCE_ROOT'):
+        prepinv.sobs_preprocess
+    pt._loaded.clear()
