@@ -165,6 +165,39 @@ int cledb_invert_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
                      double maxchisq, int bcalc, int strict_topk,
                      float* invout, float* sfound, uint8_t* status_out, void* stream);
 
+/* ---- reduced-database mode (reduced = True) -------------------------------------------------------- *
+ * Replaces cledb_getsubsetiquv / cledb_getsubsetiqud and the search over their per-pixel output (CLEDB_PROC.py:1401-1568,
+ * 951-963, 1125-1134): for every phi index only the nsearch theta rows whose tan(theta)*sin(phi) is closest to the
+ * observed tan(Phi_B), and the nsearch closest to tan(pi - Phi_B), are searched (for every gx; duplicates and the all-zero
+ * rows of the phi = 0 plane included, in the reference's order).  The subset is enumerated on the device, never built.
+ *   outer      = ngx (PyCELP type) or ned*ngx (CLE type); every database used must have outer*nbphi*nbtheta rows
+ *   tan_btheta = tan(bthetamin + l*(bthetamax-bthetamin)/nbtheta), sin_bphi = sin(bphimin + k*(bphimax-bphimin)/nbphi),
+ *                float64, evaluated by the caller (:1417-1422)
+ *   tie_rank   = rank of theta index l in the caller's argsort of an all-equal array: the reference's presort uses
+ *                NumPy's default (unstable) argsort and the phi = 0 plane is one big tie
+ *   tan_phib   = [npix,2] float64: tan(Phi_B) and tan(pi - Phi_B) of every pixel (:1428-1430 / :1516-1518)
+ * Outputs as cledb_match, with idx the row of the FULL database (:1070-1071) and kpos the position inside the pixel's
+ * filtered subset; nan_slots_out[npix] = how many leading output slots the reference leaves empty because that many
+ * candidates have a NaN chi^2 (its selection sort picks NaNs first).  Host buffers only. */
+typedef struct cledb_reduced {
+    int32_t outer, nbphi, nbtheta;
+    const double*  tan_btheta;   /* [nbtheta] */
+    const double*  sin_bphi;     /* [nbphi]   */
+    const int32_t* tie_rank;     /* [nbtheta] */
+    const double*  tan_phib;     /* [npix,2]  */
+} cledb_reduced;
+int cledb_match_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
+                        const float* sobs, const float* snr, const int32_t* db_id, int nsearch, const cledb_reduced* red,
+                        int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out, float* rows_out,
+                        uint8_t* status_out, int32_t* nan_slots_out);
+/* the same followed by the solution building of cledb_invert */
+int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
+                         const float* sobs, const float* snr, const int32_t* db_id, int nsearch, const cledb_reduced* red,
+                         const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
+                         const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
+                         double maxchisq, int bcalc, int strict_topk,
+                         float* invout, float* sfound, uint8_t* status_out);
+
 /* ---- elementwise neighbours ------------------------------------------------------------------------ *
  * cledb_blos: blos_proc_1pix (CLEDB_PROC.py:874-914) for npix pixels of one line.
  *   iquv[npix,4]; kfac = 1e9*h*c/mu_B/lambda_ref^2, g_eff, ffac = F_factor as Python floats (they are

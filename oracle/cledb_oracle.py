@@ -126,8 +126,53 @@ def _null_result(nsearch, chi=None):
     return out, np.zeros((nsearch, 8), dtype=np.float32)
 
 
+def reduced_subset(mode, sobs, sobsd, dbhdr, database, nsearch):
+    """The per-pixel reduced database of ``reduced=True``; CLEDB_PROC.py:1401-1478 (IQUV) / 1487-1568 (IQUD).
+
+    For every phi index the ``nsearch`` theta entries whose ``tan(theta) sin(phi)`` is closest to the observed
+    ``tan(Phi_B)`` and the ``nsearch`` closest to the degenerate branch ``tan(pi - Phi_B)`` are kept (for all gx, and all
+    densities of a CLE-type database).  Returns ``(datasel[M,8] float32, outredindex[nbphi, 2 nsearch] int32)``; rows of
+    the phi = 0 plane stay zero when both branches start at theta index 0 (CLEDB_PROC.py:1446, 1466).  Ties are
+    ordered by NumPy's default ``argsort`` exactly as in the reference (not stable: machine dependent).
+    """
+    dbcgrid, ned, ngx, nbphi, nbtheta, xed, gxmin, gxmax, bphimin, bphimax, bthetamin, bthetamax, nline, wavel, dbtype = dbhdr
+    kk = np.arange(0, nbphi)
+    bphir = bphimin + kk * (bphimax - bphimin) / (nbphi)
+    ll = np.arange(0, nbtheta)
+    bthetar = bthetamin + ll * (bthetamax - bthetamin) / (nbtheta)
+    tt = np.tan(bthetar)
+    with np.errstate(all='ignore'):
+        phib = 0.5 * np.arctan2(sobs[2], sobs[1]) if mode == 0 else sobsd[1]      # :1428 / :1516
+        tmain = np.tan(phib)
+        tdeg = np.tan(np.pi - phib)
+    db = np.asarray(database)
+    lead = db.shape[:-3]                                  # (ngx,) for PyCELP, (ned, ngx) for CLE
+    datasel = np.zeros(lead + (nbphi, 2 * nsearch, 8), dtype=np.float32)
+    outredindex = np.zeros((nbphi, 2 * nsearch), dtype=np.int32)
+    with np.errstate(all='ignore'):
+        for ir in range(bphir.shape[0]):
+            ttp = tt * np.sin(bphir[ir])
+            srta = np.argsort(np.abs(tmain - ttp))[0:nsearch]
+            srtb = np.argsort(np.abs(tdeg - ttp))[0:nsearch]
+            if ir + srta[0] > 0 or ir + srtb[0] > 0:
+                datasel[..., ir, :nsearch, :] = db[..., ir, srta, :]
+                datasel[..., ir, nsearch:, :] = db[..., ir, srtb, :]
+                outredindex[ir, :nsearch] = srta
+                outredindex[ir, nsearch:] = srtb
+    return np.reshape(datasel, (-1, 8)), outredindex
+
+
+def reduced_original_index(pos, outredindex, dbhdr):
+    """Position in the reduced database -> row of the full database; CLEDB_PROC.py:1070-1071 (cledb_params on the grid with
+    ``nbtheta`` replaced by ``2 nsearch``, then cledb_invparams with the stored theta index)."""
+    dbcgrid, dbtype = dbhdr[0], dbhdr[14]
+    red = np.array((dbcgrid[0], dbcgrid[1], dbcgrid[2], dbcgrid[3], outredindex.shape[1], 0, 0, 0, 0, 0, 0, 0, 0, 0), dtype=np.float32)
+    i, j, k, l = db_unravel(pos, red, dbtype)
+    return np.int32(i * dbcgrid[2] * dbcgrid[3] * dbcgrid[4] + j * dbcgrid[3] * dbcgrid[4] + k * dbcgrid[4] + outredindex[k, l])
+
+
 def match_pixel(mode, sobs, sobsd, yobs, aobs, dobs, database, dbhdr, snr, nsearch, maxchisq, bcalc,
-                strict_topk=False, return_raw=False):
+                strict_topk=False, return_raw=False, reduced=False):
     """One pixel of the 2-line search.  mode 0 = IQUV (CLEDB_PROC.py:921-1087), 1 = IQUD (1094-1252).
 
     Full-database mode (``reduced=False``).  Returns ``(out[nsearch,11], smatch[nsearch,8])`` float32; with
@@ -142,7 +187,11 @@ def match_pixel(mode, sobs, sobsd, yobs, aobs, dobs, database, dbhdr, snr, nsear
         res = _null_result(nsearch)
         return res + (None,) if return_raw else res
 
-    flat = np.reshape(database, (-1, 8))                                      # :969-972 / 1141-1144
+    outredindex = None
+    if reduced:
+        flat, outredindex = reduced_subset(mode, sobs, sobsd, dbhdr, database, nsearch)   # :954 / :1128
+    else:
+        flat = np.reshape(database, (-1, 8))                                  # :969-972 / 1141-1144
     with np.errstate(all='ignore'):
         if mode == 0:
             keep = np.flatnonzero(np.sign(flat[:, 3]) == np.sign(sobs[3]))    # :974
@@ -183,9 +232,10 @@ def match_pixel(mode, sobs, sobsd, yobs, aobs, dobs, database, dbhdr, snr, nsear
                 else:
                     b = 0.5 * (ratio(7) + ratio(3))
             smatch[si, :] = derotate_entry(row, aobs, nf)                     # :1064
-            out[si, 0] = keep[p]                                              # :1080
+            ix = reduced_original_index(keep[p], outredindex, dbhdr) if reduced else keep[p]   # :1070-1071
+            out[si, 0] = ix                                                   # :1080
             out[si, 1] = c
-            out[si, 2:] = entry_physics(keep[p], yobs, dobs, dbhdr, bcalc, b)  # :1082
+            out[si, 2:] = entry_physics(ix, yobs, dobs, dbhdr, bcalc, b)      # :1082
     return (out, smatch, raw) if return_raw else (out, smatch)
 
 
@@ -219,9 +269,9 @@ def van_vleck_flag(out):
 
 
 def _pixel_job(args):
-    (mode, xx, yy, sobs, sobsd, yobs, aobs, dobs, dbk, dbhdr, snr, nsearch, maxchisq, bcalc, strict) = args
+    (mode, xx, yy, sobs, sobsd, yobs, aobs, dobs, dbk, dbhdr, snr, nsearch, maxchisq, bcalc, strict, reduced) = args
     out, smatch = match_pixel(mode, sobs, sobsd, yobs, aobs, dobs, _DBS[dbk], dbhdr, snr, nsearch, maxchisq,
-                              bcalc, strict_topk=strict)
+                              bcalc, strict_topk=strict, reduced=reduced)
     return xx, yy, out, smatch
 
 
@@ -229,7 +279,7 @@ _DBS = None
 
 
 def invert_map(sobs_totrot, sobs_dopp, database, db_enc, yobs, aobs, dobs, snr, issuemask, dbhdr, keyvals,
-               nsearch, maxchisq, bcalc, iqud, workers=1, strict_topk=False, pixels=None):
+               nsearch, maxchisq, bcalc, iqud, workers=1, strict_topk=False, pixels=None, reduced=False):
     """``cledb_invproc`` (CLEDB_PROC.py:93-363), full-database mode.
 
     ``workers`` > 1 uses a fork pool whose children inherit the databases (the "IPC-free" CPU baseline of
@@ -250,9 +300,9 @@ def invert_map(sobs_totrot, sobs_dopp, database, db_enc, yobs, aobs, dobs, snr, 
     mode = 1 if iqud == True else 0
     if pixels is None:
         pixels = [(xx, yy) for xx in range(nx) for yy in range(ny)]
-    jobs = [(mode, xx, yy, sobs_totrot[xx, yy, :], sobs_dopp[xx, yy, :] if mode == 1 else None,
+    jobs = [(mode, xx, yy, sobs_totrot[xx, yy, :], sobs_dopp[xx, yy, :] if (mode == 1 or (reduced and np.ndim(sobs_dopp) >= 3)) else None,
              yobs[xx, yy], aobs[xx, yy], dobs[xx, yy], int(db_enc[xx, yy]), dbhdr, snr[xx, yy, :],
-             nsearch, maxchisq, bcalc, strict_topk) for (xx, yy) in pixels]
+             nsearch, maxchisq, bcalc, strict_topk, reduced) for (xx, yy) in pixels]
     _DBS = database
     if workers > 1:
         import multiprocessing

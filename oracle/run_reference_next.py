@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Golden vectors for the rows SURVEY.md section 8(f) marks "next", from the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
 
-    python oracle/run_reference_next.py        # (re)writes tests/golden/dbselect.npz
+    python oracle/run_reference_next.py        # (re)writes tests/golden/dbselect.npz and tests/golden/reduced_maps.npz
 
 Runs only in the build container (needs /root/reference).  Same recipe as oracle/run_reference.py: astropy stub, scratch
 working directory that mirrors the relative paths the reference opens.
@@ -13,6 +13,11 @@ dbselect.npz
   * the reference's ``sdb_preprocess`` (verbose = 4, its unit-test switch) over a 9 x 8 map on a scratch directory of
     4 heights x 5 densities of small synthetic PyCELP-type files: db_enc, db_enc_flnm, db_uniq, file names and a SHA-256 of
     every normalised database it returns.
+
+reduced_maps.npz
+  * ``cledb_invproc(..., reduced=True)`` of the reference (IQUV and IQUD, nsearch 8 / 4 / 3) on an 8 x 9 map over two small
+    databases, with its ``np.argsort`` order of an all-equal array on this machine (``tie_order``: the phi = 0 plane of the
+    presort is one big tie and NumPy's default sort is not stable).
 """
 import os
 import sys
@@ -99,6 +104,43 @@ def main():
                mini_shape=np.array(np.asarray(database[0]).shape))
     print('sdb_preprocess: %d distinct databases of shape %s, db_enc[0] = %s' % (len(database), np.asarray(database[0]).shape, db_enc[0]))
     np.savez_compressed(os.path.join(rr.GOLDEN, 'dbselect.npz'), **out)
+
+    # ---- reduced-database mode (reduced=True) of cledb_invproc, small databases
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    assert procinv.__file__.startswith(rr.REF), procinv.__file__
+    small = synth.make_database(8, 39, ngx=5, nbphi=36, nbtheta=18)
+    small2 = synth.make_database(20, 70, ngx=5, nbphi=36, nbtheta=18)
+    hdr = prepinv.sdb_parseheader('./tests/dbfiles/fe-xiii_1074/db.hdr')
+    gg = hdr[0].copy()
+    gg[2], gg[3], gg[4] = 5, 36, 18
+    hdr = (gg, hdr[1], np.int32(5), np.int32(36), np.int32(18)) + tuple(hdr[5:])
+    dbs = [small, small2]
+    nx, ny = 8, 9
+    enc = (np.arange(nx * ny).reshape(nx, ny) % 2).astype(np.int32)
+    obs = synth.make_observation(nx, ny, dbs, db_enc=enc, seed=9, frac_nan=0.04, frac_zero=0.03)
+    rng = np.random.default_rng(5)
+    obs['sobs_dopp'][:, :, 1] = rng.uniform(-1.5, 1.5, (nx, ny)).astype(np.float32)        # wave angle, used only when reduced
+    s = obs['sobs_totrot']
+    s[1, 1, 2] = 0.0                                   # U = 0: Phi_B = 0 or pi/2
+    s[1, 2, 1] = 0.0                                   # Q = 0
+    obs['sobs_dopp'][2, 2, 1] = 0.0                    # wave angle 0: tan = 0, every theta ties at tan(theta)*sin(phi) ~ 0 rows
+    red = {}
+    for tag, iqud, bcalc, k in (('iquv_k8', False, 0, 8), ('iquv_k4', False, 2, 4), ('iqud_k8', True, 3, 8), ('iqud_k3', True, 3, 3)):
+        ss = s.copy()
+        if iqud:
+            ss[np.isnan(ss).any(axis=2) & ~np.isnan(ss).all(axis=2)] = np.nan
+        iss = obs['issuemask'].copy()
+        inv, sf = procinv.cledb_invproc(ss, obs['sobs_dopp'], dbs, enc, obs['yobs'], obs['aobs'], obs['dobs'], obs['snr'], iss, hdr,
+                                        obs['keyvals'], k, 1000, bcalc, iqud, 6, True, 0)
+        red['invout_' + tag], red['sfound_' + tag], red['issuemask_' + tag], red['sobs_' + tag] = inv, sf, iss, ss
+        red['cfg_' + tag] = np.array([int(iqud), bcalc, k, 1000], dtype=np.float64)
+        print('reduced', tag, 'searched', int((inv[..., 0, 0] >= 0).sum()), 'idx[0,0]', inv[0, 0, :, 0])
+    # one pixel's subset, for debugging the device-side construction
+    dsel, ored = procinv.cledb_getsubsetiquv(s[0, 0], hdr, dbs[enc[0, 0]], 8)
+    np.savez_compressed(os.path.join(rr.GOLDEN, 'reduced_maps.npz'), db0=small, db1=small2, db_enc=enc, hdr_g=hdr[0],
+                        sobs_dopp=obs['sobs_dopp'], snr=obs['snr'], yobs=obs['yobs'], aobs=obs['aobs'], dobs=obs['dobs'],
+                        cdelt=np.float64(obs['keyvals'][11]), tie_order=np.argsort(np.zeros(18)).astype(np.int32),
+                        outred_00=ored, datasel_00_sha=rr.sha(dsel), **red)
     import shutil
     shutil.rmtree(scratch, ignore_errors=True)
 

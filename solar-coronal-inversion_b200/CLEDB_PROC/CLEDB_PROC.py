@@ -27,7 +27,8 @@ import numpy as np
 
 from cledb_b200 import native, solution
 
-OPTIONS = dict(dbencoding=int(os.environ.get('CLEDB_B200_DBENCODING', '0')),
+OPTIONS = dict(reduced_tie_order=None,      # theta order of an all-equal presort row; None = this machine's np.argsort
+               dbencoding=int(os.environ.get('CLEDB_B200_DBENCODING', '0')),
                precision=int(os.environ.get('CLEDB_B200_PRECISION', '0')),
                strict_topk=False,
                solution=os.environ.get('CLEDB_B200_SOLUTION', 'device'),
@@ -94,7 +95,8 @@ def make_resident(database):
     _upload(database, range(len(database)))
 
 
-def _search_and_build(mode, sobs, sobs_dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc):
+def _search_and_build(mode, sobs, sobs_dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc,
+                      reduced=False):
     """Flattened pixels in, (invout[npix,k,11], sfound[npix,k,8]) out."""
     sobs = np.ascontiguousarray(sobs, dtype=np.float32).reshape(-1, 8)
     snr = np.ascontiguousarray(snr, dtype=np.float32).reshape(-1, 8)
@@ -103,6 +105,16 @@ def _search_and_build(mode, sobs, sobs_dopp, database, db_enc, yobs, aobs, dobs,
     lut = np.zeros(int(enc.max()) + 1, dtype=np.int32)
     for k, v in ids.items():
         lut[k] = v
+    if reduced:                                      # cledb_getsubsetiquv / cledb_getsubsetiqud + search over the subset
+        tie = OPTIONS['reduced_tie_order']
+        if OPTIONS['solution'] == 'device' and int(dbhdr[14]) == 1:
+            inv, sf, _ = ctx.invert_reduced(mode, sobs, snr, lut[enc], nsearch, yobs, dobs, aobs, sobs_dopp, dbhdr, maxchisq, bcalc,
+                                            strict_topk=OPTIONS['strict_topk'], precision=OPTIONS['precision'], tie_order=tie)
+            return inv, sf
+        raw = ctx.match_reduced(mode, sobs, snr, lut[enc], nsearch, sobs_dopp, dbhdr, precision=OPTIONS['precision'], tie_order=tie)
+        return solution.build_solutions(raw, mode, sobs, sobs_dopp, np.asarray(yobs).reshape(-1), np.asarray(aobs).reshape(-1),
+                                        np.asarray(dobs).reshape(-1), dbhdr, nsearch, maxchisq, bcalc,
+                                        strict_topk=OPTIONS['strict_topk'])
     if OPTIONS['solution'] == 'device' and int(dbhdr[14]) == 1:
         dopp0 = None if sobs_dopp is None else np.asarray(sobs_dopp).reshape(sobs.shape[0], -1)[:, 0]
         inv, sf, _ = ctx.invert(mode, sobs, snr, lut[enc], nsearch, yobs, dobs, aobs, dopp0, dbhdr, maxchisq, bcalc,
@@ -143,18 +155,17 @@ def cledb_invproc(sobs_totrot, sobs_dopp, database, db_enc, yobs, aobs, dobs, sn
         if verbose >= 1:
             print("CLEDB_INVPROC: FATAL! Field strength calculation incompatible with requested input data! Check bcalc and iqud keywords; Aborting!")
         return aborted()
-    if reduced == True:
-        raise NotImplementedError("cledb_b200: the reduced-database presort (cledb_getsubsetiquv/iqud) is not built yet; "
-                                  "run with reduced=False (full search is the default of the reference)")
     if verbose >= 2:
-        print("CLEDB_INVPROC: Using a full database search of size:", dbhdr[1] * dbhdr[2] * dbhdr[3] * dbhdr[4])
+        print("CLEDB_INVPROC: Using a %s database search of size:" % ("reduced" if reduced == True else "full"),
+              dbhdr[1] * dbhdr[2] * dbhdr[3] * dbhdr[4])
 
     mode = native.MODE_IQUD if iqud == True else native.MODE_IQUV
     dopp = None
     if mode == native.MODE_IQUD:
         dopp = np.asarray(sobs_dopp)
         dopp = dopp.reshape(nx * ny, -1)
-    inv, sf = _search_and_build(mode, sobs_totrot, dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc)
+    inv, sf = _search_and_build(mode, sobs_totrot, dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc,
+                                reduced=reduced == True)
     invout = np.ascontiguousarray(inv, dtype=np.float32).reshape(nx, ny, nsearch, 11)
     sfound = np.ascontiguousarray(sf, dtype=np.float32).reshape(nx, ny, nsearch, 8)
     solution.update_issuemask(issuemask, invout, np.asarray(snr), nx, ny)
@@ -166,22 +177,19 @@ def cledb_invproc(sobs_totrot, sobs_dopp, database, db_enc, yobs, aobs, dobs, sn
 def cledb_matchiquv(xx, yy, sobs_1pix, yobs_1pix, aobs_1pix, dobs_1pix, database_in, dbhdr, snr, nsearch, maxchisq,
                     bcalc, reduced, verbose):
     """One pixel, full Stokes IQUV; reference CLEDB_PROC.py:921-1087.  Returns ``(xx, yy, out, smatch)``."""
-    if reduced == True:
-        raise NotImplementedError("cledb_b200: reduced database search is not built yet")
     inv, sf = _search_and_build(native.MODE_IQUV, np.asarray(sobs_1pix).reshape(1, 8), None, [database_in], np.zeros(1, np.int32),
                                 np.array([yobs_1pix]), np.array([aobs_1pix]), np.array([dobs_1pix]), np.asarray(snr).reshape(1, 8),
-                                dbhdr, nsearch, maxchisq, bcalc)
+                                dbhdr, nsearch, maxchisq, bcalc, reduced=reduced == True)
     return xx, yy, inv[0], sf[0]
 
 
 def cledb_matchiqud(xx, yy, sobs_1pix, sobsd_1pix, yobs_1pix, aobs_1pix, dobs_1pix, database_in, dbhdr, snr, nsearch,
                     maxchisq, bcalc, reduced, verbose):
     """One pixel, IQU + Doppler; reference CLEDB_PROC.py:1094-1252.  Returns ``(xx, yy, out, smatch)``."""
-    if reduced == True:
-        raise NotImplementedError("cledb_b200: reduced database search is not built yet")
     inv, sf = _search_and_build(native.MODE_IQUD, np.asarray(sobs_1pix).reshape(1, 8), np.asarray(sobsd_1pix).reshape(1, -1),
                                 [database_in], np.zeros(1, np.int32), np.array([yobs_1pix]), np.array([aobs_1pix]),
-                                np.array([dobs_1pix]), np.asarray(snr).reshape(1, 8), dbhdr, nsearch, maxchisq, bcalc)
+                                np.array([dobs_1pix]), np.asarray(snr).reshape(1, 8), dbhdr, nsearch, maxchisq, bcalc,
+                                reduced=reduced == True)
     return xx, yy, inv[0], sf[0]
 
 

@@ -50,6 +50,9 @@ SIGNATURES = {
     'cledb_set_tuning': (_c.c_int, [_P, _c.c_int, _c.c_int]),
     'cledb_invert': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
                                 _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P]),
+    'cledb_match_reduced': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'cledb_invert_reduced': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _c.c_int,
+                                        _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P]),
     'cledb_invert_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
                                     _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'cledb_blos': (_c.c_int, [_P, _c.c_int64, _P, _c.c_double, _c.c_double, _c.c_double, _P, _P]),
@@ -140,6 +143,37 @@ def codec_decode(codes, shift):
     out = np.empty(codes.shape, dtype=np.float32)
     load_library().cledb_codec_decode(_ptr(codes), codes.size, int(shift), _ptr(out))
     return out
+
+
+class Reduced(ctypes.Structure):
+    """``cledb_reduced`` of the header: what the reduced-database presort (cledb_getsubsetiquv / cledb_getsubsetiqud,
+    CLEDB_PROC.py:1401-1568) needs, with every transcendental evaluated here by NumPy in the reference's own dtypes."""
+    _fields_ = [('outer', _c.c_int32), ('nbphi', _c.c_int32), ('nbtheta', _c.c_int32),
+                ('tan_btheta', _P), ('sin_bphi', _P), ('tie_rank', _P), ('tan_phib', _P)]
+
+    @classmethod
+    def build(cls, mode, sobs, sobs_dopp, dbhdr, tie_order=None):
+        dbcgrid, ned, ngx, nbphi, nbtheta, xed, gxmin, gxmax, bphimin, bphimax, bthetamin, bthetamax, nline, wavel, dbtype = dbhdr
+        with np.errstate(all='ignore'):
+            kk = np.arange(0, nbphi)
+            bphir = bphimin + kk * (bphimax - bphimin) / (nbphi)                 # :1417-1418
+            ll = np.arange(0, nbtheta)
+            bthetar = bthetamin + ll * (bthetamax - bthetamin) / (nbtheta)       # :1420-1421
+            if mode == MODE_IQUV:
+                phib = 0.5 * np.arctan2(sobs[:, 2], sobs[:, 1])                  # :1428 (float32)
+            else:
+                phib = np.asarray(sobs_dopp)[:, 1]                               # :1516 (wave angle, dtype of the input)
+            tans = np.stack([np.tan(phib), np.tan(np.pi - phib)], axis=1).astype(np.float64)
+            tt, sp = np.tan(bthetar).astype(np.float64), np.sin(bphir).astype(np.float64)
+        order = np.argsort(np.zeros(int(nbtheta))) if tie_order is None else np.asarray(tie_order)
+        rank = np.empty(int(nbtheta), dtype=np.int32)
+        rank[order] = np.arange(int(nbtheta), dtype=np.int32)
+        r = cls()
+        r.outer = int(ngx) if int(dbtype) == 1 else int(ned) * int(ngx)
+        r.nbphi, r.nbtheta = int(nbphi), int(nbtheta)
+        r._keep = [np.ascontiguousarray(tt), np.ascontiguousarray(sp), rank, np.ascontiguousarray(tans)]
+        r.tan_btheta, r.sin_bphi, r.tie_rank, r.tan_phib = (a.ctypes.data for a in r._keep)
+        return r
 
 
 class Context:
@@ -284,6 +318,51 @@ class Context:
                                           ctypes.addressof(grid), float(maxchisq), int(bcalc), 1 if strict_topk else 0,
                                           _ptr(out['invout']), _ptr(out['sfound']), _ptr(out['status'])))
         return out['invout'], out['sfound'], out['status']
+
+    def match_reduced(self, mode, sobs, snr, db_id, nsearch, sobs_dopp, dbhdr, precision=PREC_FP32, tie_order=None):
+        """Raw top-``nsearch`` of every pixel over its reduced database (``reduced=True``); dict as ``match`` plus
+        ``nan_slots`` (leading output slots the reference leaves empty)."""
+        sobs = _as(sobs, np.float32).reshape(-1, 8)
+        snr = _as(snr, np.float32).reshape(-1, 8)
+        npix = sobs.shape[0]
+        db_id = _as(np.broadcast_to(np.asarray(db_id, dtype=np.int32).reshape(-1), (npix,)), np.int32)
+        k = int(nsearch)
+        red = Reduced.build(mode, sobs, sobs_dopp, dbhdr, tie_order)
+        out = dict(idx=np.empty((npix, k), np.int32), chi=np.empty((npix, k), np.float32), kpos=np.empty((npix, k), np.int32),
+                   status=np.empty(npix, np.uint8), rows=np.empty((npix, k, 8), np.float32), nan_slots=np.empty(npix, np.int32),
+                   chi64=np.empty((npix, k), np.float64) if precision == PREC_FP64 else None, ncand=None)
+        self._check(self.lib.cledb_match_reduced(self.h, int(mode), int(precision), npix, _ptr(sobs), _ptr(snr), _ptr(db_id), k,
+                                                 ctypes.addressof(red), _ptr(out['idx']), _ptr(out['chi']), _ptr(out['chi64']),
+                                                 _ptr(out['kpos']), _ptr(out['rows']), _ptr(out['status']), _ptr(out['nan_slots'])))
+        return out
+
+    def invert_reduced(self, mode, sobs, snr, db_id, nsearch, yobs, dobs, aobs, sobs_dopp, dbhdr, maxchisq, bcalc,
+                       strict_topk=False, precision=PREC_FP32, tie_order=None):
+        """Reduced-database search + solution building on the device (cledb_invert_reduced)."""
+        sobs = _as(sobs, np.float32).reshape(-1, 8)
+        snr = _as(snr, np.float32).reshape(-1, 8)
+        npix = sobs.shape[0]
+        db_id = _as(np.broadcast_to(np.asarray(db_id, dtype=np.int32).reshape(-1), (npix,)), np.int32)
+        k = int(nsearch)
+        yobs = _as(np.asarray(yobs).reshape(-1), np.float32)
+        dobs = _as(np.asarray(dobs).reshape(-1), np.float32)
+        ang = _as(np.asarray(aobs).reshape(-1), np.float32)
+        with np.errstate(all='ignore'):
+            rot_cos, rot_sin = np.cos(-2. * ang), np.sin(-2. * ang)
+        dopp0, is64 = None, 0
+        if mode == MODE_IQUD:
+            dopp0 = np.asarray(sobs_dopp)[:, 0]
+            is64 = 1 if dopp0.dtype == np.float64 else 0
+            dopp0 = _as(dopp0, np.float64 if is64 else np.float32)
+        red = Reduced.build(mode, sobs, sobs_dopp, dbhdr, tie_order)
+        grid = DbGrid.from_dbhdr(dbhdr)
+        invout, sfound = np.empty((npix, k, 11), np.float32), np.empty((npix, k, 8), np.float32)
+        status = np.empty(npix, np.uint8)
+        self._check(self.lib.cledb_invert_reduced(self.h, int(mode), int(precision), npix, _ptr(sobs), _ptr(snr), _ptr(db_id), k,
+                                                  ctypes.addressof(red), _ptr(yobs), _ptr(dobs), _ptr(rot_cos), _ptr(rot_sin),
+                                                  _ptr(dopp0), is64, 1, ctypes.addressof(grid), float(maxchisq), int(bcalc),
+                                                  1 if strict_topk else 0, _ptr(invout), _ptr(sfound), _ptr(status)))
+        return invout, sfound, status
 
     def match_dev(self, mode, npix, sobs_ptr, snr_ptr, dbid_ptr, nsearch, idx_ptr, chi_ptr, chi64_ptr=None, kpos_ptr=None,
                   rows_ptr=None, status_ptr=None, ncand_ptr=None, stream=None, precision=PREC_FP32):

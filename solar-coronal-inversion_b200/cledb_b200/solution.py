@@ -146,7 +146,18 @@ def build_solutions(raw, mode, sobs, sobs_dopp, yobs, aobs, dobs, dbhdr_of_pixel
     searched = status == native.PIX_SEARCHED
     sel = np.broadcast_to(np.arange(k), (npix, k)) if strict_topk else replay_partsort(kpos, chi_cmp, valid)
     ar = np.arange(npix)[:, None]
-    idx_s, chi_s, rows_s, valid_s = idx[ar, sel], chi_cmp[ar, sel], rows[ar, sel], valid[ar, sel]
+    shift = raw.get('nan_slots')
+    if shift is not None and (shift > 0).any():
+        # reduced mode: candidates with a NaN chi^2 come first in the reference's selection sort and leave their output slots
+        # empty (they fail both chi^2 tests); the finite winners follow
+        sel = np.array(sel)
+        sel[shift > 0] = np.arange(k)
+        src = np.arange(k)[None, :] - shift[:, None]
+        sel = np.where(src >= 0, np.take_along_axis(sel, np.maximum(src, 0), axis=1), 0)
+        nan_lead = src < 0
+    else:
+        nan_lead = np.zeros((npix, k), bool)
+    idx_s, chi_s, rows_s, valid_s = idx[ar, sel], chi_cmp[ar, sel], rows[ar, sel], valid[ar, sel] & ~nan_lead
 
     invout = np.zeros((npix, k, 11), dtype=F32)
     invout[:, :, 0] = -1
@@ -154,7 +165,7 @@ def build_solutions(raw, mode, sobs, sobs_dopp, yobs, aobs, dobs, dbhdr_of_pixel
     with np.errstate(all='ignore'):
         limit = maxchisq * 10 if mode == native.MODE_IQUV else maxchisq
         best = chi_s[:, 0]
-        rejected = searched & valid_s[:, 0] & (best > limit)             # CLEDB_PROC.py:1027 / 1202
+        rejected = searched & valid_s[:, 0] & (best > limit)             # CLEDB_PROC.py:1027 / 1202 (a leading NaN is not > limit)
         invout[rejected, :, 1] = best[rejected, None].astype(F32)
         allinf = status == native.PIX_ALLINF                             # every chi^2 is +inf in the reference
         invout[allinf, :, 1] = np.inf

@@ -54,6 +54,7 @@ extern "C" int cledb_destroy(cledb_ctx* ctx) {
     if (ctx->ws.ptr) cudaFree(ctx->ws.ptr);
     if (ctx->ws2.ptr) cudaFree(ctx->ws2.ptr);
     if (ctx->raw.ptr) cudaFree(ctx->raw.ptr);
+    if (ctx->red.ptr) cudaFree(ctx->red.ptr);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     if (ctx->io.ptr) cudaFree(ctx->io.ptr);
     for (auto& pr : ctx->prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }

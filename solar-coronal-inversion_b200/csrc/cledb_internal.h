@@ -59,6 +59,7 @@ struct HostDb {
     int32_t* d_invperm = nullptr;
     int32_t* d_kept_rank = nullptr;
     int32_t* d_row_kpos = nullptr;
+    float*   d_rows8 = nullptr;          // decoded [n,8] copy, built on first use of the reduced mode
     int64_t  npad = 0, nnan = 0, bytes = 0;
     int      shift[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -84,6 +85,7 @@ struct cledb_ctx {
     bool tables_dirty = true;
     cledb::Workspace ws;                           // search workspace (grown on demand)
     cledb::Workspace ws2;                          // partial top-k lists of the search (sized once the work shape is known)
+    cledb::Workspace red;                          // small tables of the reduced search
     cledb::Workspace raw;                          // raw search outputs of the fused search + solution call
     cledb::Workspace io;                           // staging for the host entry points
     int32_t* h_cnt = nullptr;                      // pinned host copy of the bucket sizes
@@ -108,6 +110,41 @@ struct cledb_ctx {
         }                                                                                       \
     } while (0)
 
+#ifdef __CUDACC__
+namespace cledb {
+// ------------------------------------------------------------------------------------------------------
+// chi^2 of one (pixel, entry) pair, shared by the full and the reduced search
+// ------------------------------------------------------------------------------------------------------
+// fp32: 10 FFMA.  acc = c0 + sum_c (d_c*a_c + nb_c)^2 = 2 * chi^2 (the halving is exact and done at the end).
+__device__ __forceinline__ float eval_fp32(const float (&d)[kNC], const float (&a)[kNC], const float (&nb)[kNC], float c0) {
+    float acc = c0;
+#pragma unroll
+    for (int c = 0; c < kNC; ++c) {
+        const float r = fmaf(d[c], a[c], nb[c]);
+        acc = fmaf(r, r, acc);
+    }
+    return acc;
+}
+// fp64 validation: float32 subtract and divide, float64 weight/square, NumPy's pairwise order over the 8 terms
+// ((t0+t1)+(t2+t3))+((t4+t5)+(t6+t7)) with t3 = t7 = +0, /2, round to 15 decimals as rint(x*1e15)/1e15
+// (CLEDB_PROC.py:989-1005).  d must already be the decoded database value.
+__device__ __forceinline__ double eval_fp64(const float (&d)[kNC], const float (&st)[kNC], const float (&sig)[kNC], double c0) {
+    double q[kNC];
+#pragma unroll
+    for (int c = 0; c < kNC; ++c) {
+        const float r = __fdiv_rn(__fsub_rn(d[c], st[c]), sig[c]);
+        const double t = (c == 2) ? __dmul_rn((double)r, 0.01) : (double)r;
+        q[c] = __dmul_rn(t, t);
+    }
+    const double left = __dadd_rn(__dadd_rn(c0, q[0]), q[1]);
+    const double right = __dadd_rn(__dadd_rn(q[2], q[3]), q[4]);
+    const double half = __dmul_rn(__dadd_rn(left, right), 0.5);
+    return __ddiv_rn(rint(__dmul_rn(half, 1e15)), 1e15);
+}
+
+}  // namespace cledb
+#endif
+
 namespace cledb {
 int  ensure_workspace(cledb_ctx* ctx, Workspace& w, size_t bytes);
 int  sync_tables(cledb_ctx* ctx, cudaStream_t st);
@@ -129,5 +166,5 @@ int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsea
                  const float* dobs, const float* rot_cos, const float* rot_sin, const void* dopp, int dopp_is_f64,
                  int64_t dopp_stride, const cledb_dbgrid& grid_dev, double maxchisq, int bcalc, int strict_topk,
                  const int32_t* idx, const float* chi, const double* chi64, const int32_t* kpos, const float* rows,
-                 const uint8_t* status, float* invout, float* sfound, cudaStream_t st);
+                 const uint8_t* status, const int32_t* nan_slots, float* invout, float* sfound, cudaStream_t st);
 }  // namespace cledb

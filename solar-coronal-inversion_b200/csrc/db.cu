@@ -134,6 +134,7 @@ static void free_db(HostDb& h) {
     if (h.d_invperm) cudaFree(h.d_invperm);
     if (h.d_kept_rank) cudaFree(h.d_kept_rank);
     if (h.d_row_kpos) cudaFree(h.d_row_kpos);
+    if (h.d_rows8) cudaFree(h.d_rows8);
     h = HostDb();
     std::memset(&h.slot, 0, sizeof(DbSlot));
 }

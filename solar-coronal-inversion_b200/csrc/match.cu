@@ -144,16 +144,6 @@ template <int ENC> __device__ __forceinline__ void load_tile_regs(const unsigned
 // ------------------------------------------------------------------------------------------------------
 // chi^2 of one (pixel, entry) pair
 // ------------------------------------------------------------------------------------------------------
-// fp32: 10 FFMA.  acc = c0 + sum_c (d_c*a_c + nb_c)^2 = 2 * chi^2 (the halving is exact and done at the end).
-__device__ __forceinline__ float eval_fp32(const float (&d)[kNC], const float (&a)[kNC], const float (&nb)[kNC], float c0) {
-    float acc = c0;
-#pragma unroll
-    for (int c = 0; c < kNC; ++c) {
-        const float r = fmaf(d[c], a[c], nb[c]);
-        acc = fmaf(r, r, acc);
-    }
-    return acc;
-}
 // The same arithmetic for two entries at once with the packed FP32 FMA of sm_100 (fma.rn.f32x2, FFMA2 in SASS): one
 // issue slot per two FMAs.  The coefficients are scalars; ptxas encodes pack(a, a) as a broadcast .F32 operand.
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
@@ -185,23 +175,6 @@ __device__ __forceinline__ void eval_fp32_all(const float (&d)[kEPL][kNC], const
 #pragma unroll
     for (int e = 0; e < kEPL; e += 2) eval_fp32_pair(d[e], d[e + 1], a, nb, c0, v[e], v[e + 1]);
 }
-// fp64 validation: float32 subtract and divide, float64 weight/square, NumPy's pairwise order over the 8 terms
-// ((t0+t1)+(t2+t3))+((t4+t5)+(t6+t7)) with t3 = t7 = +0, /2, round to 15 decimals as rint(x*1e15)/1e15
-// (CLEDB_PROC.py:989-1005).  d must already be the decoded database value.
-__device__ __forceinline__ double eval_fp64(const float (&d)[kNC], const float (&st)[kNC], const float (&sig)[kNC], double c0) {
-    double q[kNC];
-#pragma unroll
-    for (int c = 0; c < kNC; ++c) {
-        const float r = __fdiv_rn(__fsub_rn(d[c], st[c]), sig[c]);
-        const double t = (c == 2) ? __dmul_rn((double)r, 0.01) : (double)r;
-        q[c] = __dmul_rn(t, t);
-    }
-    const double left = __dadd_rn(__dadd_rn(c0, q[0]), q[1]);
-    const double right = __dadd_rn(__dadd_rn(q[2], q[3]), q[4]);
-    const double half = __dmul_rn(__dadd_rn(left, right), 0.5);
-    return __ddiv_rn(rint(__dmul_rn(half, 1e15)), 1e15);
-}
-
 // ------------------------------------------------------------------------------------------------------
 // warp helpers
 // ------------------------------------------------------------------------------------------------------

@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
                                                int bcalc, int strict_topk, const int32_t* __restrict__ idx,
                                                const float* __restrict__ chi, const double* __restrict__ chi64,
                                                const int32_t* __restrict__ kpos, const float* __restrict__ rows,
-                                               const uint8_t* __restrict__ status, float* __restrict__ invout,
-                                               float* __restrict__ sfound) {
+                                               const uint8_t* __restrict__ status, const int32_t* __restrict__ nan_slots,
+                                               float* __restrict__ invout, float* __restrict__ sfound) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npix) return;
     float* inv = invout + p * k * 11;
@@ -86,11 +86,13 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
     }
     int sel[kMaxK];
     for (int s = 0; s < k; ++s) sel[s] = s;
-    if (!strict_topk && touched && all_valid) replay_partsort(k, kp, c64, sel);
+    // reduced mode: candidates with a NaN chi^2 come first in the reference's selection sort and leave their slots empty
+    const int shift = nan_slots ? nan_slots[p] : 0;
+    if (!strict_topk && touched && all_valid && shift == 0) replay_partsort(k, kp, c64, sel);
 
     const double limit = mode == CLEDB_MODE_IQUV ? maxchisq * 10.0 : maxchisq;          // CLEDB_PROC.py:1027 / 1202
     const int s0 = sel[0];
-    if (ix[s0] >= 0 && c64[s0] > limit) {
+    if (shift == 0 && ix[s0] >= 0 && c64[s0] > limit) {
         const float best = (float)c64[s0];
         for (int s = 0; s < k; ++s) inv[s * 11 + 1] = best;
         return;
@@ -109,8 +111,8 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
     const int64_t n3 = g.nbtheta, n4 = (int64_t)g.nbphi * g.nbtheta;
     const double dgx = (double)__fsub_rn(g.gxmax, g.gxmin), dphi = (double)__fsub_rn(g.bphimax, g.bphimin),
                  dth = (double)__fsub_rn(g.bthetamax, g.bthetamin);
-    for (int s = 0; s < k; ++s) {
-        const int w = sel[s];
+    for (int s = shift; s < k; ++s) {
+        const int w = sel[s - shift];
         if (ix[w] < 0 || !(c64[w] <= maxchisq)) continue;                                // :1044 / :1219
         const float* r = rows + ((size_t)p * k + w) * 8;
         // ---- field strength
@@ -178,15 +180,15 @@ int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsea
                  const float* dobs, const float* rot_cos, const float* rot_sin, const void* dopp, int dopp_is_f64,
                  int64_t dopp_stride, const cledb_dbgrid& g, double maxchisq, int bcalc, int strict_topk, const int32_t* idx,
                  const float* chi, const double* chi64, const int32_t* kpos, const float* rows, const uint8_t* status,
-                 float* invout, float* sfound, cudaStream_t st) {
+                 const int32_t* nan_slots, float* invout, float* sfound, cudaStream_t st) {
     (void)precision;
     const int nb = (int)((npix + 127) / 128);
     if (dopp_is_f64)
         k_build<true><<<nb, 128, 0, st>>>(mode, npix, nsearch, sobs, yobs, dobs, rot_cos, rot_sin, dopp, dopp_stride, g, maxchisq,
-                                          bcalc, strict_topk, idx, chi, chi64, kpos, rows, status, invout, sfound);
+                                          bcalc, strict_topk, idx, chi, chi64, kpos, rows, status, nan_slots, invout, sfound);
     else
         k_build<false><<<nb, 128, 0, st>>>(mode, npix, nsearch, sobs, yobs, dobs, rot_cos, rot_sin, dopp, dopp_stride, g, maxchisq,
-                                           bcalc, strict_topk, idx, chi, chi64, kpos, rows, status, invout, sfound);
+                                           bcalc, strict_topk, idx, chi, chi64, kpos, rows, status, nan_slots, invout, sfound);
     ctx->launches++;
     CLEDB_CUDA(ctx, cudaGetLastError());
     return CLEDB_OK;
@@ -259,7 +261,7 @@ extern "C" int cledb_invert_dev(cledb_ctx* ctx, int mode, int precision, int64_t
     if (rc) return rc;
     return launch_build(ctx, mode, precision, npix, nsearch, sobs, yobs, dobs, rot_cos, rot_sin, dopp, dopp_is_f64,
                         dopp_stride > 0 ? dopp_stride : 1, *grid, maxchisq, bcalc, strict_topk, raw.idx, raw.chi, raw.chi64, raw.kpos,
-                        raw.rows, status, invout, sfound, st);
+                        raw.rows, status, nullptr, invout, sfound, st);
 }
 
 extern "C" int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npix, const float* sobs, const float* snr,

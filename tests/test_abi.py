@@ -108,8 +108,9 @@ def test_invproc_guards_need_no_gpu():
     bad = (obs['sobs_totrot'][..., :4],) + args[1:]
     inv, sf = procinv.cledb_invproc(*bad, 8, 1000, 0, False, 4, False, 0)          # one-line observation
     assert (inv[..., 0] == -1).all()
-    with pytest.raises(NotImplementedError):
-        procinv.cledb_invproc(*args, 8, 1000, 0, False, 4, True, 0)                # reduced search: not built yet
+    from cledb_b200.native import CledbError
+    with pytest.raises(CledbError, match='no CPU fallback'):
+        procinv.cledb_invproc(*args, 8, 1000, 0, False, 4, True, 0)                # a real search needs the GPU: no CPU fallback
     params = ctrlparams.ctrlparams()
     params.iqud, params.verbose = True, 0
     assert procinv.blos_proc(obs['sobs_totrot'], obs['snr'], obs['issuemask'], obs['keyvals'], consts, params) == 0

@@ -394,3 +394,57 @@ def test_sdb_preprocess_surface(golden_dir, tmp_path, monkeypatch):
     assert prepinv.sdb_preprocess(g['mini_yobs'], g['mini_dobs'], kv, g['mini_wlarr'], params) == (None, None, None)
     procinv.release_databases()
     procinv.OPTIONS.update(precision=0, dbencoding=0)
+
+
+@pytest.mark.parametrize('tag', ['iquv_k8', 'iquv_k4', 'iqud_k8', 'iqud_k3'])
+@pytest.mark.parametrize('where', ['device', 'host'])
+def test_reduced_mode_golden(golden_dir, tag, where):
+    """cledb_invproc(..., reduced=True) on the GPU == the unmodified reference: fp64 validation kernel bit-exact in index
+    (duplicates of the two tangent branches included), chi^2, geometry and issue mask; fp32 kernel within tolerance."""
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    g = np.load(os.path.join(golden_dir, 'reduced_maps.npz'))
+    hdr = hdr_from_g(g['hdr_g'])
+    kv = synth.make_keyvals(8, 9, cdelt=float(g['cdelt']))
+    iqud, bcalc, k, mx = g['cfg_' + tag]
+    ref_inv, ref_sf = g['invout_' + tag], g['sfound_' + tag]
+    for prec in (native.PREC_FP64, native.PREC_FP32):
+        procinv.OPTIONS.update(precision=prec, dbencoding=native.ENC_F32, solution=where, reduced_tie_order=g['tie_order'])
+        iss = np.zeros((8, 9, 2), np.int32)
+        inv, sf = procinv.cledb_invproc(g['sobs_' + tag], g['sobs_dopp'], [g['db0'], g['db1']], g['db_enc'], g['yobs'], g['aobs'], g['dobs'],
+                                        g['snr'], iss, hdr, kv, int(k), mx, int(bcalc), bool(iqud), 4, True, 0)
+        if prec == native.PREC_FP64:
+            assert np.array_equal(inv[..., 0], ref_inv[..., 0])
+            assert np.array_equal(inv[..., 1], ref_inv[..., 1])
+            assert np.array_equal(inv[..., [2, 3, 4, 6, 7]], ref_inv[..., [2, 3, 4, 6, 7]])
+            np.testing.assert_allclose(inv[..., [5, 8, 9, 10]], ref_inv[..., [5, 8, 9, 10]], rtol=1e-6, atol=0)
+            np.testing.assert_allclose(sf, ref_sf, rtol=1e-6, atol=0)
+            assert same(iss, g['issuemask_' + tag])
+        else:
+            m = inv[..., 0] == ref_inv[..., 0]
+            assert m.mean() > 0.97
+            np.testing.assert_allclose(inv[..., 1], ref_inv[..., 1], rtol=CHI_RTOL, atol=CHI_ATOL)
+            np.testing.assert_allclose(sf[m], ref_sf[m], rtol=1e-6, atol=0)
+    procinv.OPTIONS.update(precision=0, dbencoding=0, solution='device', reduced_tie_order=None)
+    procinv.release_databases()
+
+
+def test_reduced_mode_full_size(ctx):
+    """Reduced search against a full-size database (60 480 subset rows per pixel): a seeded subset against the oracle."""
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    db = synth.make_database(9, 40)
+    obs = synth.make_observation(24, 24, [db], seed=13)
+    hdr = synth.make_dbhdr()
+    procinv.OPTIONS.update(precision=native.PREC_FP64, dbencoding=native.ENC_F32, solution='device', reduced_tie_order=None)
+    iss = obs['issuemask'].copy()
+    inv, sf = procinv.cledb_invproc(obs['sobs_totrot'], obs['sobs_dopp'], [db], obs['db_enc'], obs['yobs'], obs['aobs'], obs['dobs'],
+                                    obs['snr'], iss, hdr, obs['keyvals'], 8, 1000, 0, False, 4, True, 0)
+    pix = [(int(p // 24), int(p % 24)) for p in np.random.default_rng(4).choice(576, 6, replace=False)]
+    iss2 = obs['issuemask'].copy()
+    ref, ref_sf = orc.invert_map(obs['sobs_totrot'], obs['sobs_dopp'], [db], obs['db_enc'], obs['yobs'], obs['aobs'], obs['dobs'], obs['snr'],
+                                 iss2, hdr, obs['keyvals'], 8, 1000, 0, False, pixels=pix, reduced=True)
+    for (x, y) in pix:
+        assert np.array_equal(inv[x, y, :, :5], ref[x, y, :, :5]), (x, y)
+        np.testing.assert_allclose(inv[x, y], ref[x, y], rtol=1e-6)
+    assert (inv[..., 0, 0] >= 0).mean() > 0.7        # the presort can miss every acceptable match: rejected pixels (-1)
+    procinv.OPTIONS.update(precision=0, dbencoding=0)
+    procinv.release_databases()

@@ -167,3 +167,20 @@ def test_database_selection(golden_dir):
             l1, l2 = synth.make_raw_line_pair(h - 101, (d - 600) // 5, rng, ngx=3, nbphi=12, nbtheta=8)
             shas['DB_h%03d_d%d.npy' % (h, d)] = sha(orc.normalise_database(l1, l2, g['mini_wlarr'][0, 0]))
     assert [shas[mini[u]] for u in uniq] == [str(x) for x in g['mini_sha']]
+
+
+@pytest.mark.parametrize('tag', ['iquv_k8', 'iquv_k4', 'iqud_k8', 'iqud_k3'])
+def test_reduced_mode(golden_dir, tag):
+    """reduced=True (cledb_getsubsetiquv / cledb_getsubsetiqud presort + search over the per-pixel subset, with its duplicate
+    rows, all-zero phi = 0 plane, NaN chi^2 and index mapping back to the full database) against the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, 'reduced_maps.npz'))
+    hdr = hdr_from_g(g['hdr_g'])
+    kv = synth.make_keyvals(8, 9, cdelt=float(g['cdelt']))
+    iqud, bcalc, k, mx = g['cfg_' + tag]
+    iss = np.zeros((8, 9, 2), np.int32)
+    inv, sf = orc.invert_map(g['sobs_' + tag], g['sobs_dopp'], [g['db0'], g['db1']], g['db_enc'], g['yobs'], g['aobs'], g['dobs'],
+                             g['snr'], iss, hdr, kv, int(k), mx, int(bcalc), bool(iqud), reduced=True)
+    assert same(inv, g['invout_' + tag]) and same(sf, g['sfound_' + tag]) and same(iss, g['issuemask_' + tag])
+    if tag == 'iquv_k8':
+        dsel, ored = orc.reduced_subset(0, g['sobs_' + tag][0, 0], None, hdr, g['db%d' % g['db_enc'][0, 0]], 8)
+        assert same(ored, g['outred_00']) and sha(dsel) == str(g['datasel_00_sha'])
