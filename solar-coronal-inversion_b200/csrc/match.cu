@@ -543,9 +543,11 @@ __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, float c0f, Cand<PREC>
         while (m) {
             const int e = __ffs(m) - 1;
             m &= m - 1;
-            V mine = v[0];                               // v[e] for a warp-uniform runtime e, kept in registers
-#pragma unroll
-            for (int q = 1; q < kEPL; ++q) mine = (e == q) ? v[q] : mine;
+            // v[e] for a warp-uniform runtime e, kept in registers: a three-level select tree on the bits of e
+            const bool b0 = e & 1, b1 = e & 2, b2 = e & 4;
+            const V m01 = b0 ? v[1] : v[0], m23 = b0 ? v[3] : v[2], m45 = b0 ? v[5] : v[4], m67 = b0 ? v[7] : v[6];
+            const V m03 = b1 ? m23 : m01, m47 = b1 ? m67 : m45;
+            const V mine = b2 ? m47 : m03;
             const V cv = __shfl_sync(0xffffffffu, mine, src);
             const int cp = base + pos_in_tile<ENC>(src, e);
             if (cp < cnt_end) list_insert<PREC>(list, rec, c0f, k, cv, cp, perm, lane);   // re-checks against the list
