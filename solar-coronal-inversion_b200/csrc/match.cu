@@ -381,7 +381,9 @@ __global__ void __launch_bounds__(256) k_classify(Plan pl, const float* __restri
     const int key = slot * kParts + cls;
     pl.key[p] = key;
     pl.status[p] = CLEDB_PIX_SEARCHED;
-    atomicAdd(&pl.cnt[key], 1);
+    // warp-aggregated count: the lanes that reach this point with the same bucket send one atomic
+    const uint32_t peers = __match_any_sync(__activemask(), key);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&pl.cnt[key], __popc(peers));
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -435,7 +437,14 @@ __global__ void __launch_bounds__(256) k_scatter(Plan pl) {
     if (p >= pl.npix) return;
     const int key = pl.key[p];
     if (key < 0) { pl.rank[p] = -1; return; }
-    const int r = pl.off[key] + atomicAdd(&pl.cursor[key], 1);
+    // warp-aggregated slot allocation inside the bucket
+    const int lane = threadIdx.x & 31;
+    const uint32_t peers = __match_any_sync(__activemask(), key);
+    const int leader = __ffs(peers) - 1;
+    int first = 0;
+    if (lane == leader) first = atomicAdd(&pl.cursor[key], __popc(peers));
+    first = __shfl_sync(peers, first, leader);
+    const int r = pl.off[key] + first + __popc(peers & ((1u << lane) - 1u));
     pl.order[r] = (int32_t)p;
     pl.rank[p] = r;
 }

@@ -57,46 +57,53 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
                                                const int32_t* __restrict__ kpos, const float* __restrict__ rows,
                                                const uint8_t* __restrict__ status, const int32_t* __restrict__ nan_slots,
                                                float* __restrict__ invout, float* __restrict__ sfound) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npix) return;
-    float* inv = invout + p * k * 11;
-    float* sf = sfound + p * k * 8;
-    for (int s = 0; s < k; ++s) {
-        inv[s * 11] = -1.0f;
+    // one thread per (pixel, output slot): consecutive threads write consecutive 44- and 32-byte records
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npix * k) return;
+    const int64_t p = t / k;
+    const int s = (int)(t - p * k);
+    float* o = invout + t * 11;
+    float* f = sfound + t * 8;
+    o[0] = -1.0f;
 #pragma unroll
-        for (int c = 1; c < 11; ++c) inv[s * 11 + c] = 0.0f;
+    for (int c = 1; c < 11; ++c) o[c] = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) sf[s * 8 + c] = 0.0f;
-    }
+    for (int c = 0; c < 8; ++c) f[c] = 0.0f;
     const int st = status[p];
     if (st == CLEDB_PIX_ALLINF) {                       // every chi^2 is +inf in the reference: rejected with that value
-        for (int s = 0; s < k; ++s) inv[s * 11 + 1] = CUDART_INF_F;
+        o[1] = CUDART_INF_F;
         return;
     }
     if (st != CLEDB_PIX_SEARCHED) return;
 
     const int32_t* ix = idx + p * k;
     const int32_t* kp = kpos + p * k;
-    double c64[kMaxK];
     bool all_valid = true, touched = false;
-    for (int s = 0; s < k; ++s) {
-        c64[s] = chi64 ? chi64[p * k + s] : (double)chi[p * k + s];
-        all_valid = all_valid && ix[s] >= 0;
-        touched = touched || (ix[s] >= 0 && kp[s] >= 0 && kp[s] < k);
+    for (int q = 0; q < k; ++q) {
+        all_valid = all_valid && ix[q] >= 0;
+        touched = touched || (ix[q] >= 0 && kp[q] >= 0 && kp[q] < k);
     }
-    int sel[kMaxK];
-    for (int s = 0; s < k; ++s) sel[s] = s;
     // reduced mode: candidates with a NaN chi^2 come first in the reference's selection sort and leave their slots empty
     const int shift = nan_slots ? nan_slots[p] : 0;
-    if (!strict_topk && touched && all_valid && shift == 0) replay_partsort(k, kp, c64, sel);
+    int w = s - shift, w0 = 0;                          // winners shown in this slot and in slot 0
+    if (!strict_topk && touched && all_valid && shift == 0) {
+        double c64[kMaxK];
+        int sel[kMaxK];
+        for (int q = 0; q < k; ++q) c64[q] = chi64 ? chi64[p * k + q] : (double)chi[p * k + q];
+        replay_partsort(k, kp, c64, sel);
+        w = sel[s];
+        w0 = sel[0];
+    }
+    auto chi_of = [&](int q) { return chi64 ? chi64[p * k + q] : (double)chi[p * k + q]; };
 
     const double limit = mode == CLEDB_MODE_IQUV ? maxchisq * 10.0 : maxchisq;          // CLEDB_PROC.py:1027 / 1202
-    const int s0 = sel[0];
-    if (shift == 0 && ix[s0] >= 0 && c64[s0] > limit) {
-        const float best = (float)c64[s0];
-        for (int s = 0; s < k; ++s) inv[s * 11 + 1] = best;
+    if (shift == 0 && ix[w0] >= 0 && chi_of(w0) > limit) {
+        o[1] = (float)chi_of(w0);
         return;
     }
+    if (w < 0 || ix[w] < 0) return;
+    const double cw = chi_of(w);
+    if (!(cw <= maxchisq)) return;                                                       // :1044 / :1219
     float so[8];
     {
         const float4 a = reinterpret_cast<const float4*>(sobs)[2 * p], b = reinterpret_cast<const float4*>(sobs)[2 * p + 1];
@@ -111,9 +118,7 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
     const int64_t n3 = g.nbtheta, n4 = (int64_t)g.nbphi * g.nbtheta;
     const double dgx = (double)__fsub_rn(g.gxmax, g.gxmin), dphi = (double)__fsub_rn(g.bphimax, g.bphimin),
                  dth = (double)__fsub_rn(g.bthetamax, g.bthetamin);
-    for (int s = shift; s < k; ++s) {
-        const int w = sel[s - shift];
-        if (ix[w] < 0 || !(c64[w] <= maxchisq)) continue;                                // :1044 / :1219
+    {
         const float* r = rows + ((size_t)p * k + w) * 8;
         // ---- field strength
         float b32 = 0.f;
@@ -158,12 +163,10 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
             by = __fmul_rn(__fmul_rn(ab, sth), sp);
             bz = __fmul_rn(ab, cth);
         }
-        float* o = inv + s * 11;
         o[0] = (float)index;                       // the reference stores the index in a float32 array (exact below 2^24)
-        o[1] = (float)c64[w];
+        o[1] = (float)cw;
         o[2] = ed; o[3] = yo; o[4] = gx; o[5] = bo; o[6] = bphi; o[7] = bth; o[8] = bx; o[9] = by; o[10] = bz;
         // ---- matched profile, rotated back: cledb_quderotate (:1575-1588)
-        float* f = sf + s * 8;
         const float q1 = __fmul_rn(r[1], nf), u1 = __fmul_rn(r[2], nf), q2 = __fmul_rn(r[5], nf), u2 = __fmul_rn(r[6], nf);
         f[0] = __fmul_rn(r[0], nf);
         f[1] = __fsub_rn(__fmul_rn(q1, rc), __fmul_rn(u1, rs));
@@ -182,7 +185,7 @@ int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsea
                  const float* chi, const double* chi64, const int32_t* kpos, const float* rows, const uint8_t* status,
                  const int32_t* nan_slots, float* invout, float* sfound, cudaStream_t st) {
     (void)precision;
-    const int nb = (int)((npix + 127) / 128);
+    const int nb = (int)((npix * nsearch + 127) / 128);
     if (dopp_is_f64)
         k_build<true><<<nb, 128, 0, st>>>(mode, npix, nsearch, sobs, yobs, dobs, rot_cos, rot_sin, dopp, dopp_stride, g, maxchisq,
                                           bcalc, strict_topk, idx, chi, chi64, kpos, rows, status, nan_slots, invout, sfound);
