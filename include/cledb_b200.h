@@ -216,6 +216,25 @@ int cledb_qurotate(cledb_ctx* ctx, int nx, int ny, const double* xs, const doubl
 int cledb_qurotate_dev(cledb_ctx* ctx, int nx, int ny, const double* xs, const double* ys, double linpolref,
                        const float* hpxy, const float* in, float* out, float* aobs, float* yobs, void* stream);
 
+/* cledb_obs_integrate: obs_integrate_work_1pix (CLEDB_PREPINV.py:1164-1270) for npix spectra of one line: continuum
+ * subtraction, wavelength integration of I, Q, U, Stokes V from the median of V / (d(I/Itot)/dlambda), signal-to-noise
+ * ratio and the SNR issue codes 1 / 2.  float64 arithmetic in NumPy's order, including its pairwise summation, so the
+ * outputs are bit-identical to the reference's for float64 input spectra.
+ *   spec[npix,nw,4] float64;  sp: what the caller derives from the wavelength axis with its own NumPy
+ *     wcont  index of the clean-continuum window (:968-976);  lo, hi = int(0.25*nw), int(0.75*nw) (:1210)
+ *     dwv    mean dispersion (:1046);  the coefficients of numpy.gradient on that axis: uniform != 0 -> h2 = 2*dx,
+ *            else ga/gb/gc[nw-2] (interior points 1..nw-2); dx_first, dx_last for the two edges
+ *   tot[npix,4], snr[npix,4], background[npix,4] float32 (cast as the reference's output arrays do), issue[npix] int32;
+ *   pixels without counts or with a non-finite sample give zeros (:1168, :1267); status[npix]: 0 ok/empty, 1 = the
+ *   reference raises for this pixel (no sample inside the 0.3 % .. 99.7 % window of the running sum). */
+typedef struct cledb_spectral {
+    int32_t nw, wcont, lo, hi, uniform;
+    double  dwv, h2, dx_first, dx_last;
+    const double* ga; const double* gb; const double* gc;
+} cledb_spectral;
+int cledb_obs_integrate(cledb_ctx* ctx, int64_t npix, const double* spec, const cledb_spectral* sp,
+                        float* tot, float* snr, float* background, int32_t* issue, uint8_t* status);
+
 /* ---- int16 database codec (pure host code, usable without a GPU) ------------------------------------ *
  * code = IEEE binary16 bit pattern of x * 2^shift (round to nearest even), stored as int16;
  * decode = float(binary16) * 2^-shift, exact in float32.  cledb_codec_shift picks the shift that puts the

@@ -471,3 +471,86 @@ def qurotate_map(sobs_tot, keyvals, hpxygrid):
                 rot[xx, yy, q] = sobs_tot[xx, yy, q] * c - sobs_tot[xx, yy, q + 1] * s
                 rot[xx, yy, q + 1] = sobs_tot[xx, yy, q] * s + sobs_tot[xx, yy, q + 1] * c
     return rot, aobs, yobs
+
+
+# --------------------------------------------------------------------------------------------------
+# spectral integration: obs_integrate / obs_integrate_work_1pix / obs_cdf
+# --------------------------------------------------------------------------------------------------
+def spectrum_cdf(spectr):
+    """Normalised running sum of one Stokes I spectrum, float32; CLEDB_PREPINV.py:1356-1364 (every prefix is its own
+    ``np.sum``, i.e. NumPy's pairwise summation of that prefix, rounded to float32)."""
+    cdf = np.zeros((spectr.shape[0]), dtype=np.float32)
+    for i in range(0, spectr.shape[0]):
+        cdf[i] = np.sum(spectr[0:i + 1])
+    return cdf[:] / cdf[-1]
+
+
+def integrate_pixel(nw, wlarr, wcont, dwv, spec):
+    """One pixel of one line: (sobs_tot[4] float64, snr[4], background[4], issue code); CLEDB_PREPINV.py:1164-1270.
+
+    ``spec[nw,4]``: Stokes IQUV spectra.  Background = mean of three continuum samples at ``wcont``; I, Q, U are summed
+    times the dispersion ``dwv``; V is the median over the inner half of the window of V / (d(I/Itot)/dlambda + 1e-36);
+    SNR = rms of the middle third of the signal window (0.3 % .. 99.7 % of the Stokes I running sum) over the rms outside it.
+    """
+    zeros = (np.zeros((4), dtype=np.float32), np.zeros((4), dtype=np.float32), np.zeros((4), dtype=np.float32), 0)
+    if not ((np.count_nonzero(spec[:, 0])) and (np.isfinite(spec[:, :]).all())):
+        return zeros
+    with np.errstate(all='ignore'):
+        cdf = spectrum_cdf(spec[:, 0])
+        lr0 = np.argwhere((np.abs(cdf) > 0.003) & (np.abs(cdf) < 0.997))
+        background = np.mean(spec[wcont:wcont + 3:, :], axis=0)
+        tmp2 = spec[:, :] - background
+        tmp2[tmp2[:, 0] < 0, 0] = 0
+        tot = np.zeros((4), dtype=np.float64)
+        tot[0] = np.sum(tmp2[:, 0] * dwv)
+        slope = np.gradient(tmp2[:, 0] / tot[0], wlarr)
+        lo, hi = np.int32(0.25 * nw), np.int32(0.75 * nw)
+        vscl = tmp2[lo:hi, 3] / (slope[lo:hi] + 1e-36)
+        tot[3] = np.median(vscl[np.isfinite(vscl)])
+        tot[1] = np.sum(tmp2[:, 1] * dwv)
+        tot[2] = np.sum(tmp2[:, 2] * dwv)
+        rms_noise = np.sqrt(np.mean(np.concatenate((spec[0:lr0[0, 0] + 1, :], spec[lr0[-1, 0]:, :])) ** 2))
+        a = np.round(lr0[0, 0] + lr0.shape[0] / 3).astype(np.int16)
+        b = np.round(lr0[0, 0] + lr0.shape[0] * 2 / 3).astype(np.int16)
+        rms_signal = np.sqrt(np.mean(spec[a:b, :] ** 2, axis=0))
+        snr = rms_signal / rms_noise
+    iss = 0
+    for kk in range(3):
+        if snr[kk] < 1:
+            iss = 1
+    if snr[3] < 1:
+        iss += 2
+    return tot, snr, background, iss
+
+
+def continuum_samples(wlarr, nline):
+    """Per line: index of the clean continuum window; CLEDB_PREPINV.py:968-976.  None if a line is not Fe XIII 1074/1079."""
+    out = []
+    for zz in range(nline):
+        if 1074.65 > wlarr[:, zz].min() and 1074.65 < wlarr[:, zz].max():
+            out.append(np.argmin(np.abs(wlarr[:, zz] - 1074.)))
+        elif 1079.8 > wlarr[:, zz].min() and 1079.8 < wlarr[:, zz].max():
+            out.append(np.argmin(np.abs(wlarr[:, zz] - 1080.2)))
+    return out if len(out) else None
+
+
+def integrate_map(sobs_in, wlarr, keyvals):
+    """``obs_integrate`` without the atmospheric reduction branch (CLEDB_PREPINV.py:935-1063): (sobs_tot, snr, background,
+    issuemask) for a list of per-line arrays ``[nx,ny,nw,4]``."""
+    nx, ny, nw = keyvals[0:3]
+    nline = keyvals[3]
+    sobs_tot = np.zeros((nx, ny, nline * 4), dtype=np.float32)
+    background = np.zeros((nx, ny, nline * 4), dtype=np.float32)
+    snr = np.ones((nx, ny, nline * 4), dtype=np.float32)
+    iss = np.zeros((nx, ny, nline), dtype=np.int32)
+    wcont = continuum_samples(wlarr, nline)
+    if wcont is None:
+        return -1, -1, -1
+    for zz in range(nline):
+        dwv = np.mean(np.diff(wlarr[:, zz]))
+        for xx in range(nx):
+            for yy in range(ny):
+                t, s, b, i = integrate_pixel(nw, wlarr[:, zz], wcont[zz], dwv, sobs_in[zz][xx, yy, :, :])
+                sobs_tot[xx, yy, 4 * zz:4 * (zz + 1)], snr[xx, yy, 4 * zz:4 * (zz + 1)] = t, s
+                background[xx, yy, 4 * zz:4 * (zz + 1)], iss[xx, yy, zz] = b, i
+    return sobs_tot, snr, background, iss

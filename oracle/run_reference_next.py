@@ -141,6 +141,36 @@ def main():
                         sobs_dopp=obs['sobs_dopp'], snr=obs['snr'], yobs=obs['yobs'], aobs=obs['aobs'], dobs=obs['dobs'],
                         cdelt=np.float64(obs['keyvals'][11]), tie_order=np.argsort(np.zeros(18)).astype(np.int32),
                         outred_00=ored, datasel_00_sha=rr.sha(dsel), **red)
+    # ---- spectral integration (obs_integrate) on a small map of noisy spectra built from the reference's own test profiles
+    data = np.load('./tests/sample_test_stokesspectra.npz')
+    rng = np.random.default_rng(17)
+    nx, ny, nw = 5, 6, 134
+    cubes = []
+    for key, wkey in (('aas', 'awl'), ('bbs', 'bwl')):
+        base = data[key]                                                   # [134,4] float64, the profile tests/test_functions.py uses
+        amp = rng.uniform(0.3, 3.0, (nx, ny, 1, 1))
+        shift = rng.integers(-12, 13, (nx, ny))
+        cube = np.empty((nx, ny, nw, 4))
+        for xx in range(nx):
+            for yy in range(ny):
+                cube[xx, yy] = np.roll(base, shift[xx, yy], axis=0) * amp[xx, yy, 0]
+        noise = rng.normal(0.0, 1.0, cube.shape) * np.abs(base[:, 0]).max() * np.array([2e-3, 2e-3, 2e-3, 1e-4])
+        cube = cube + noise * rng.uniform(0.0, 3.0, (nx, ny, 1, 1))
+        cube[0, 0] = base                                                  # the reference's own unit-test pixel, untouched
+        cube[0, 1] = 0.0                                                   # no counts
+        cube[0, 2, 5, 1] = np.nan                                          # a NaN sample
+        cube[0, 3] = base * 1e-3 + noise[0, 3] * 30                        # noise dominated: SNR < 1 issue codes
+        cubes.append(cube)
+    wl = np.zeros((nw, 2), dtype=np.float32)                               # as obs_headstructproc builds it (CLEDB_PREPINV.py:720, 852)
+    for i, (crval3, cdelt3) in enumerate(((1074.2571372, 0.00538654), (1079.4203968, 0.00541243))):
+        for j in range(nw):
+            wl[j, i] = crval3 + (j * cdelt3)
+    kv = synth.make_keyvals(nx, ny)
+    kv[2] = nw
+    tot, snr, bkg, iss = prepinv.obs_integrate(cubes, wl, kv, 0, 4, False)
+    print('obs_integrate: tot[0,0]', tot[0, 0], 'issues', np.unique(iss))
+    np.savez_compressed(os.path.join(rr.GOLDEN, 'integrate.npz'), cube0=cubes[0], cube1=cubes[1], wl=wl, sobs_tot=tot, snr=snr,
+                        background=bkg, issuemask=iss, aat=data['aat'], bbt=data['bbt'])
     import shutil
     shutil.rmtree(scratch, ignore_errors=True)
 

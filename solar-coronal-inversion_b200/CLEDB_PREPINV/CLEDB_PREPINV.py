@@ -4,6 +4,7 @@
     obs_calcheight(keyvals, hpxygrid)          -> yobs                    CLEDB_PREPINV.py:897-926
     sdb_preprocess(yobs, dobs, keyvals, wlarr, params) -> (db_enc, database, dbhdr)   CLEDB_PREPINV.py:201-367
     sdb_fileingest / sdb_findelongationanddens / sdb_read / sdb_parseheader / sdb_lcgrid   CLEDB_PREPINV.py:380-569
+    obs_integrate(sobs_in, wlarr, keyvals, verbose, ncpu, atmred) -> (sobs_tot, snr, background, issuemask)   CLEDB_PREPINV.py:935-1063
     iss_block(x)                                                          CLEDB_PREPINV.py:1563-1576
 
 The rotation and the height map are one fused elementwise kernel (72 B/pixel) behind the C-ABI.  ``sdb_preprocess``
@@ -84,6 +85,54 @@ def sdb_parseheader(dbheaderfile):
     return (g, ned, ngx, nbphi, nbtheta, sdb_lcgrid(np.float32(g[5]), np.float32(g[6]), ned),
             np.float32(g[7]), np.float32(g[8]), np.float32(g[9]), np.float32(g[10]), np.float32(g[11]), np.float32(g[12]),
             nline, wavel, np.int32(g[-1]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# spectral integration of the observation
+# ---------------------------------------------------------------------------------------------------------
+def obs_integrate(sobs_in, wlarr, keyvals, verbose, ncpu, atmred):
+    """Background subtraction, wavelength integration and signal statistics of every pixel; CLEDB_PREPINV.py:935-1063.
+
+    ``sobs_in``: list of per-line arrays ``[nx,ny,nw,4]``; ``wlarr[nw,nline]``.  Returns ``(sobs_tot[nx,ny,4*nline],
+    snr, background)`` float32 and ``issuemask_obsint[nx,ny,nline]`` int32, or ``(-1,-1,-1)`` for an unknown wavelength
+    range (:978-980).  One kernel launch per line replaces the pool task per pixel (cledb_obs_integrate); the result is
+    bit-identical for float64 spectra.  The telluric/photospheric reduction branch (``atmred=True``) is unfinished in the
+    reference and needs downloads; it is passed through to the reference module.
+    """
+    if atmred == True:
+        from cledb_b200.passthrough import reference_attr
+        return reference_attr('CLEDB_PREPINV/CLEDB_PREPINV.py', 'obs_integrate')(sobs_in, wlarr, keyvals, verbose, ncpu, atmred)
+    nx, ny, nw = keyvals[0:3]
+    nline = keyvals[3]
+    wlarr = np.asarray(wlarr)
+    wcont = []
+    for zz in range(nline):                                                              # :968-976
+        lo, hi = wlarr[:, zz].min(), wlarr[:, zz].max()
+        if 1074.65 > lo and 1074.65 < hi:
+            wcont.append(np.argmin(np.abs(wlarr[:, zz] - 1074.)))
+        elif 1079.8 > lo and 1079.8 < hi:
+            wcont.append(np.argmin(np.abs(wlarr[:, zz] - 1080.2)))
+    if len(wcont) == 0:
+        if verbose >= 1:
+            print("OBS_INTEGRATE: FATAL! Wavelength case not handled for atlas fitting!")
+        return -1, -1, -1
+    sobs_tot = np.zeros((nx, ny, nline * 4), dtype=np.float32)
+    background = np.zeros((nx, ny, nline * 4), dtype=np.float32)
+    snr = np.ones((nx, ny, nline * 4), dtype=np.float32)
+    issuemask_obsint = np.zeros((nx, ny, nline), dtype=np.int32)
+    ctx = native.get_context(OPTIONS['device'])
+    if verbose >= 1:
+        print("OBS_INTEGRATE: Integrating the Stokes IQUV spectra:")
+    for zz in range(nline):
+        spec = np.ascontiguousarray(sobs_in[zz], dtype=np.float64).reshape(nx * ny, nw, 4)
+        tot, s, b, iss, status = ctx.obs_integrate(spec, wlarr[:, zz], wcont[zz])
+        if (status == 1).any():
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0")      # lr0[0,0] of an empty window, :1254
+        sobs_tot[:, :, 4 * zz:4 * (zz + 1)] = tot.reshape(nx, ny, 4)
+        snr[:, :, 4 * zz:4 * (zz + 1)] = s.reshape(nx, ny, 4)
+        background[:, :, 4 * zz:4 * (zz + 1)] = b.reshape(nx, ny, 4)
+        issuemask_obsint[:, :, zz] = iss.reshape(nx, ny)
+    return sobs_tot, snr, background, issuemask_obsint
 
 
 # ---------------------------------------------------------------------------------------------------------

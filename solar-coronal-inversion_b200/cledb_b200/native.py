@@ -45,6 +45,7 @@ SIGNATURES = {
     'cledb_gather_rows': (_c.c_int, [_P, _c.c_int, _P, _c.c_int64, _P]),
     'cledb_db_select': (_c.c_int, [_P, _c.c_int64, _P, _P, _c.c_int, _P, _P]),
     'cledb_db_select_dev': (_c.c_int, [_P, _c.c_int64, _P, _P, _c.c_int, _P, _P, _P]),
+    'cledb_obs_integrate': (_c.c_int, [_P, _c.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_match': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_match_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_set_tuning': (_c.c_int, [_P, _c.c_int, _c.c_int]),
@@ -176,6 +177,37 @@ class Reduced(ctypes.Structure):
         return r
 
 
+class Spectral(ctypes.Structure):
+    """``cledb_spectral`` of the header: everything ``obs_integrate_work_1pix`` derives from the wavelength axis of one line,
+    evaluated here with NumPy in the dtype the axis has (float32 in the reference, CLEDB_PREPINV.py:720)."""
+    _fields_ = [('nw', _c.c_int32), ('wcont', _c.c_int32), ('lo', _c.c_int32), ('hi', _c.c_int32), ('uniform', _c.c_int32),
+                ('dwv', _c.c_double), ('h2', _c.c_double), ('dx_first', _c.c_double), ('dx_last', _c.c_double),
+                ('ga', _P), ('gb', _P), ('gc', _P)]
+
+    @classmethod
+    def build(cls, wl, wcont):
+        wl = np.asarray(wl)
+        if np.issubdtype(wl.dtype, np.integer):
+            wl = wl.astype(np.float64)
+        nw = wl.shape[0]
+        r = cls()
+        r.nw, r.wcont = int(nw), int(wcont)
+        r.lo, r.hi = int(np.int32(0.25 * nw)), int(np.int32(0.75 * nw))          # :1210
+        with np.errstate(all='ignore'):
+            r.dwv = float(np.mean(np.diff(wl)))                                   # :1046
+            dx = np.diff(wl)                                                      # numpy.gradient, non-uniform spacing
+            r.uniform = 1 if (dx == dx[0]).all() else 0
+            r.h2 = float(2. * dx[0])
+            r.dx_first, r.dx_last = float(dx[0]), float(dx[-1])
+            dx1, dx2 = dx[0:-1], dx[1:]
+            a = -(dx2) / (dx1 * (dx1 + dx2))
+            b = (dx2 - dx1) / (dx1 * dx2)
+            c = dx1 / (dx2 * (dx1 + dx2))
+        r._keep = [np.ascontiguousarray(t, dtype=np.float64) for t in (a, b, c)]
+        r.ga, r.gb, r.gc = (t.ctypes.data for t in r._keep)
+        return r
+
+
 class Context:
     """One CUDA device.  Owns the resident databases and the search workspace."""
 
@@ -268,6 +300,18 @@ class Context:
         out = np.empty(y.size, dtype=np.int32)
         self._check(self.lib.cledb_db_select(self.h, y.size, _ptr(y), _ptr(d), t.shape[0], _ptr(t), _ptr(out)))
         return out
+
+    def obs_integrate(self, spec, wl, wcont):
+        """obs_integrate_work_1pix for ``spec[npix,nw,4]`` float64 spectra of one line with wavelength axis ``wl[nw]``.
+        Returns ``(tot, snr, background)`` float32 [npix,4], ``issue`` int32 [npix], ``status`` uint8 [npix]."""
+        spec = _as(spec, np.float64)
+        npix, nw = spec.shape[0], spec.shape[1]
+        sp = Spectral.build(wl, wcont)
+        tot, snr, bkg = (np.empty((npix, 4), np.float32) for _ in range(3))
+        iss, st = np.empty(npix, np.int32), np.empty(npix, np.uint8)
+        self._check(self.lib.cledb_obs_integrate(self.h, npix, _ptr(spec), ctypes.addressof(sp), _ptr(tot), _ptr(snr), _ptr(bkg),
+                                                 _ptr(iss), _ptr(st)))
+        return tot, snr, bkg, iss, st
 
     # ---- search
     def match(self, mode, sobs, snr, db_id, nsearch, precision=PREC_FP32, want_rows=True, want_chi64=False, out=None):

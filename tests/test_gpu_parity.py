@@ -448,3 +448,34 @@ def test_reduced_mode_full_size(ctx):
     assert (inv[..., 0, 0] >= 0).mean() > 0.7        # the presort can miss every acceptable match: rejected pixels (-1)
     procinv.OPTIONS.update(precision=0, dbencoding=0)
     procinv.release_databases()
+
+
+def test_spectral_integration_kernel(golden_dir):
+    """CLEDB_PREPINV.obs_integrate on the GPU == the unmodified reference, bit for bit (float64 arithmetic in NumPy's order:
+    pairwise sums, axis-0 means, gradient coefficients, median), plus a uniform wavelength axis and a long spectrum
+    against the oracle."""
+    import CLEDB_PREPINV.CLEDB_PREPINV as prepinv
+    g = np.load(os.path.join(golden_dir, 'integrate.npz'))
+    kv = synth.make_keyvals(5, 6)
+    kv[2] = 134
+    tot, snr, bkg, iss = prepinv.obs_integrate([g['cube0'], g['cube1']], g['wl'], kv, 0, 4, False)
+    assert same(tot, g['sobs_tot']) and same(snr, g['snr']) and same(bkg, g['background']) and same(iss, g['issuemask'])
+    np.testing.assert_allclose(tot[0, 0, :4], g['aat'], atol=1e-12, rtol=0)        # tests/test_functions.py:60
+    # a float64, exactly uniform axis (numpy.gradient takes its uniform branch) and nw = 300 (pairwise splits above 128 terms)
+    rng = np.random.default_rng(8)
+    nw = 300
+    wl = (1074.0 + 0.0078125 * np.arange(nw)).reshape(nw, 1)
+    x = (wl[:, 0] - 1074.65) / 0.08
+    prof = np.exp(-0.5 * x * x)
+    cube = np.zeros((3, 4, nw, 4))
+    cube[..., 0] = prof * rng.uniform(1, 5, (3, 4, 1)) + 0.01
+    cube[..., 1] = 0.03 * prof + 0.002 * rng.normal(size=(3, 4, nw))
+    cube[..., 2] = -0.02 * prof + 0.002 * rng.normal(size=(3, 4, nw))
+    cube[..., 3] = 1e-3 * np.gradient(prof, wl[:, 0]) + 1e-4 * rng.normal(size=(3, 4, nw))
+    kv = synth.make_keyvals(3, 4, nline=1)
+    kv[2] = nw
+    got = prepinv.obs_integrate([cube], wl, kv, 0, 4, False)
+    ref = orc.integrate_map([cube], wl, kv)
+    for a, b in zip(got, ref):
+        assert same(a, b)
+    assert prepinv.obs_integrate([cube], wl + 100.0, kv, 0, 4, False) == (-1, -1, -1)       # unknown line: the reference's triple

@@ -184,3 +184,17 @@ def test_reduced_mode(golden_dir, tag):
     if tag == 'iquv_k8':
         dsel, ored = orc.reduced_subset(0, g['sobs_' + tag][0, 0], None, hdr, g['db%d' % g['db_enc'][0, 0]], 8)
         assert same(ored, g['outred_00']) and sha(dsel) == str(g['datasel_00_sha'])
+
+
+def test_spectral_integration(golden_dir):
+    """obs_integrate of the unmodified reference on a 5 x 6 map built from the reference's own test spectra
+    (tests/sample_test_stokesspectra.npz): bit-exact, and pixel [0,0] reproduces the PyCELP emission coefficients the
+    reference's own unit test pins (tests/test_functions.py:60, atol 1e-12)."""
+    g = np.load(os.path.join(golden_dir, 'integrate.npz'))
+    kv = synth.make_keyvals(5, 6)
+    kv[2] = 134
+    tot, snr, bkg, iss = orc.integrate_map([g['cube0'], g['cube1']], g['wl'], kv)
+    assert same(tot, g['sobs_tot']) and same(snr, g['snr']) and same(bkg, g['background']) and same(iss, g['issuemask'])
+    np.testing.assert_allclose(tot[0, 0, :4], g['aat'], atol=1e-12, rtol=0)
+    np.testing.assert_allclose(tot[0, 0, 4:], g['bbt'], atol=1e-12, rtol=0)
+    assert not tot[0, 1].any() and not tot[0, 2].any() and set(np.unique(iss)) == {0, 2, 3}
