@@ -235,6 +235,18 @@ typedef struct cledb_spectral {
 int cledb_obs_integrate(cledb_ctx* ctx, int64_t npix, const double* spec, const cledb_spectral* sp,
                         float* tot, float* snr, float* background, int32_t* issue, uint8_t* status);
 
+/* cledb_obs_dens: obs_dens_work_1pix (CLEDB_PREPINV.py:1436-1479) for npix pixels: density from the Fe XIII 1074/1079
+ * intensity ratio through the CHIANTI look-up table.  The reference builds a quadratic interpolating spline of
+ * (ratio -> density) for the first table height above the pixel, per pixel; here the caller builds the nh splines once
+ * (knots[nh,nknots], coefs[nh,ncoef], degree 2, scipy.interpolate.interp1d(kind="quadratic")._spline) and the device
+ * evaluates them with de Boor's recurrence in scipy's operation order (extrapolating outside the table).
+ *   a_obs, b_obs = Stokes I of the two lines, yobs = height, float32;  heights[nh] float64
+ *   dens_out[npix] float32 = density as the reference stores it before its log10 (1 for b_obs == 0, 0 for a NaN/inf
+ *   ratio), issue_out[npix] = 4 where no table height lies above the pixel (the last row is used). */
+int cledb_obs_dens(cledb_ctx* ctx, int64_t npix, const float* a_obs, const float* b_obs, const float* yobs,
+                   int nh, const double* heights, int nknots, const double* knots, int ncoef, const double* coefs,
+                   float* dens_out, int32_t* issue_out);
+
 /* ---- int16 database codec (pure host code, usable without a GPU) ------------------------------------ *
  * code = IEEE binary16 bit pattern of x * 2^shift (round to nearest even), stored as int16;
  * decode = float(binary16) * 2^-shift, exact in float32.  cledb_codec_shift picks the shift that puts the

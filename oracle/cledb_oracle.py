@@ -554,3 +554,32 @@ def integrate_map(sobs_in, wlarr, keyvals):
                 sobs_tot[xx, yy, 4 * zz:4 * (zz + 1)], snr[xx, yy, 4 * zz:4 * (zz + 1)] = t, s
                 background[xx, yy, 4 * zz:4 * (zz + 1)], iss[xx, yy, zz] = b, i
     return sobs_tot, snr, background, iss
+
+
+def density_map(sobs_totrot, yobs, keyvals, table):
+    """``obs_dens`` (CLEDB_PREPINV.py:1371-1479): log10 density from the 1074/1079 Stokes I ratio and the CHIANTI table
+    ``{'h','den','rat'}``, one quadratic ``interp1d`` per pixel exactly like the reference.  Needs scipy."""
+    import scipy.interpolate
+    nx, ny = keyvals[0:2]
+    dobs = np.empty((nx, ny), dtype=np.float32)
+    iss = np.zeros((nx, ny), dtype=np.int32)
+    with np.errstate(all='ignore'):
+        for xx in range(nx):
+            for yy in range(ny):
+                a_obs, b_obs, y_obs = sobs_totrot[xx, yy, 0], sobs_totrot[xx, yy, 4], yobs[xx, yy]
+                if b_obs == 0:
+                    dobs[xx, yy] = 1
+                    continue
+                rat_obs = a_obs / b_obs
+                if np.isnan(rat_obs) or np.isinf(rat_obs):
+                    dobs[xx, yy] = 0
+                    continue
+                subh = np.argwhere(table['h'] > y_obs)
+                if len(subh) == 0:
+                    subh = [-1]
+                    iss[xx, yy] = 4
+                ifunc = scipy.interpolate.interp1d(table['rat'][subh[0], :].flatten(), table['den'], kind="quadratic",
+                                                   fill_value="extrapolate")
+                dobs[xx, yy] = ifunc(rat_obs)
+        dobs[dobs <= 0] = 1
+        return np.round(np.log10(dobs), 3), iss

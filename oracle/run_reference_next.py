@@ -14,6 +14,11 @@ dbselect.npz
     4 heights x 5 densities of small synthetic PyCELP-type files: db_enc, db_enc_flnm, db_uniq, file names and a SHA-256 of
     every normalised database it returns.
 
+integrate.npz / density.npz
+  * ``obs_integrate`` on a 5 x 6 map of noisy, shifted copies of the reference's own test spectra
+    (tests/sample_test_stokesspectra.npz; pixel [0,0] is the unit-test pixel itself), and ``obs_dens`` on a 7 x 8 map with a
+    small synthetic CHIANTI-shaped look-up table.
+
 reduced_maps.npz
   * ``cledb_invproc(..., reduced=True)`` of the reference (IQUV and IQUD, nsearch 8 / 4 / 3) on an 8 x 9 map over two small
     databases, with its ``np.argsort`` order of an all-equal array on this machine (``tie_order``: the phi = 0 plane of the
@@ -171,6 +176,29 @@ def main():
     print('obs_integrate: tot[0,0]', tot[0, 0], 'issues', np.unique(iss))
     np.savez_compressed(os.path.join(rr.GOLDEN, 'integrate.npz'), cube0=cubes[0], cube1=cubes[1], wl=wl, sobs_tot=tot, snr=snr,
                         background=bkg, issuemask=iss, aat=data['aat'], bbt=data['bbt'])
+    # ---- density from the line ratio (obs_dens) with a small synthetic CHIANTI-shaped look-up table
+    nh, nd = 12, 40
+    tab_h = 1.02 + 0.08 * np.arange(nh)
+    tab_den = 10 ** np.linspace(6.0, 12.0, nd)
+    xx_ = np.linspace(0.0, 1.0, nd)
+    tab_rat = np.stack([0.9 + (14.0 + 0.5 * i) * (1 - xx_) ** (1.5 + 0.05 * i) for i in range(nh)])       # decreasing with density
+    np.savez('lookup_small.npz', h=tab_h, den=tab_den, rat=tab_rat)
+    rng = np.random.default_rng(23)
+    nx, ny = 7, 8
+    st = np.zeros((nx, ny, 8), dtype=np.float32)
+    st[:, :, 4] = rng.uniform(0.5e-9, 1.5e-9, (nx, ny))
+    st[:, :, 0] = st[:, :, 4] * rng.uniform(0.5, 18.0, (nx, ny))                                         # ratios inside and outside the table
+    yo = rng.uniform(1.0, 2.1, (nx, ny)).astype(np.float32)                                              # some above the last table height
+    st[0, 0, 4] = 0.0
+    st[0, 1, 0] = np.nan
+    st[0, 2, 0] = -st[0, 2, 0]
+    params = ctrlparams.ctrlparams()
+    params.verbose = 0
+    params.ncpu = 4
+    params.lookuptb = './lookup_small.npz'
+    dobs_ref, issd = prepinv.obs_dens(st, yo, synth.make_keyvals(nx, ny), params)
+    print('obs_dens: dobs[0]', dobs_ref[0], 'issues', np.unique(issd))
+    np.savez_compressed(os.path.join(rr.GOLDEN, 'density.npz'), h=tab_h, den=tab_den, rat=tab_rat, sobs=st, yobs=yo, dobs=dobs_ref, iss=issd)
     import shutil
     shutil.rmtree(scratch, ignore_errors=True)
 

@@ -5,6 +5,7 @@
     sdb_preprocess(yobs, dobs, keyvals, wlarr, params) -> (db_enc, database, dbhdr)   CLEDB_PREPINV.py:201-367
     sdb_fileingest / sdb_findelongationanddens / sdb_read / sdb_parseheader / sdb_lcgrid   CLEDB_PREPINV.py:380-569
     obs_integrate(sobs_in, wlarr, keyvals, verbose, ncpu, atmred) -> (sobs_tot, snr, background, issuemask)   CLEDB_PREPINV.py:935-1063
+    obs_dens(sobs_totrot, yobs, keyvals, params) -> (dobs, iss_dens)      CLEDB_PREPINV.py:1371-1430
     iss_block(x)                                                          CLEDB_PREPINV.py:1563-1576
 
 The rotation and the height map are one fused elementwise kernel (72 B/pixel) behind the C-ABI.  ``sdb_preprocess``
@@ -133,6 +134,37 @@ def obs_integrate(sobs_in, wlarr, keyvals, verbose, ncpu, atmred):
         background[:, :, 4 * zz:4 * (zz + 1)] = b.reshape(nx, ny, 4)
         issuemask_obsint[:, :, zz] = iss.reshape(nx, ny)
     return sobs_tot, snr, background, issuemask_obsint
+
+
+def obs_dens(sobs_totrot, yobs, keyvals, params):
+    """Line-of-sight plasma density from the Fe XIII 1074/1079 ratio and the CHIANTI look-up table; CLEDB_PREPINV.py:1371-1479.
+
+    Returns ``(log10 density rounded to 3 decimals [nx,ny] float32, iss_dens[nx,ny] int32)`` (issue 4: no table height above
+    the pixel).  The reference builds one quadratic spline per PIXEL; here the ``nh`` splines of the table are built once with
+    the same scipy call and every pixel is evaluated by one kernel (cledb_obs_dens).
+    """
+    nx, ny = keyvals[0:2]
+    dobs = np.empty((nx, ny), dtype=np.float32)
+    iss_dens = np.zeros((nx, ny), dtype=np.int32)
+    if params.lookuptb[-4:] != ".npz":
+        if params.verbose >= 1:
+            print("OBS_DENS: FATAL! CHIANTI look-up table not found. Is the path correct?")
+        return dobs, iss_dens
+    import scipy.interpolate
+    table = dict(np.load(params.lookuptb))
+    splines = [scipy.interpolate.interp1d(table['rat'][i, :].flatten(), table['den'], kind="quadratic", fill_value="extrapolate")._spline
+               for i in range(table['h'].shape[0])]                                       # :1461, once per height
+    knots = np.stack([np.asarray(sp.t, dtype=np.float64) for sp in splines])
+    coefs = np.stack([np.asarray(sp.c, dtype=np.float64).reshape(-1) for sp in splines])
+    if params.verbose >= 1:
+        print("OBS_DENS: Calculating observation LOS plasma density:")
+    s = np.asarray(sobs_totrot)
+    dens, iss = native.get_context(OPTIONS['device']).obs_dens(s[:, :, 0], s[:, :, 4], yobs, table['h'], knots, coefs)
+    dobs[...] = dens.reshape(nx, ny)
+    iss_dens[...] = iss.reshape(nx, ny)
+    dobs[dobs <= 0] = 1
+    with np.errstate(all='ignore'):
+        return np.round(np.log10(dobs), 3), iss_dens
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -46,6 +46,7 @@ SIGNATURES = {
     'cledb_db_select': (_c.c_int, [_P, _c.c_int64, _P, _P, _c.c_int, _P, _P]),
     'cledb_db_select_dev': (_c.c_int, [_P, _c.c_int64, _P, _P, _c.c_int, _P, _P, _P]),
     'cledb_obs_integrate': (_c.c_int, [_P, _c.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    'cledb_obs_dens': (_c.c_int, [_P, _c.c_int64, _P, _P, _P, _c.c_int, _P, _c.c_int, _P, _c.c_int, _P, _P, _P]),
     'cledb_match': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_match_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_set_tuning': (_c.c_int, [_P, _c.c_int, _c.c_int]),
@@ -312,6 +313,18 @@ class Context:
         self._check(self.lib.cledb_obs_integrate(self.h, npix, _ptr(spec), ctypes.addressof(sp), _ptr(tot), _ptr(snr), _ptr(bkg),
                                                  _ptr(iss), _ptr(st)))
         return tot, snr, bkg, iss, st
+
+    def obs_dens(self, a_obs, b_obs, yobs, heights, knots, coefs):
+        """obs_dens_work_1pix for flat arrays of the two Stokes I and the heights; ``knots[nh,nknots]``/``coefs[nh,ncoef]``:
+        the quadratic splines of every table height.  Returns ``(density float32 [npix], issue int32 [npix])``."""
+        a = _as(np.asarray(a_obs).reshape(-1), np.float32)
+        b = _as(np.asarray(b_obs).reshape(-1), np.float32)
+        y = _as(np.asarray(yobs).reshape(-1), np.float32)
+        h, t, c = _as(heights, np.float64), _as(knots, np.float64), _as(coefs, np.float64)
+        dens, iss = np.empty(a.size, np.float32), np.empty(a.size, np.int32)
+        self._check(self.lib.cledb_obs_dens(self.h, a.size, _ptr(a), _ptr(b), _ptr(y), h.size, _ptr(h), t.shape[1], _ptr(t),
+                                            c.shape[1], _ptr(c), _ptr(dens), _ptr(iss)))
+        return dens, iss
 
     # ---- search
     def match(self, mode, sobs, snr, db_id, nsearch, precision=PREC_FP32, want_rows=True, want_chi64=False, out=None):

@@ -163,9 +163,96 @@ __global__ void __launch_bounds__(kIntWarps * 32) k_integrate(int64_t npix, cons
     }
 }
 
+// ---- density from the line ratio: obs_dens_work_1pix (CLEDB_PREPINV.py:1436-1479), one thread per pixel
+__global__ void __launch_bounds__(256) k_obs_dens(int64_t npix, const float* __restrict__ a_obs, const float* __restrict__ b_obs,
+                                                  const float* __restrict__ yobs, int nh, const double* __restrict__ heights, int nknots,
+                                                  const double* __restrict__ knots, int ncoef, const double* __restrict__ coefs,
+                                                  float* __restrict__ dens, int32_t* __restrict__ issue) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const float a = a_obs[p], b = b_obs[p];
+    if (b == 0.f) { dens[p] = 1.f; issue[p] = 0; return; }                       // :1444
+    const float rat = __fdiv_rn(a, b);
+    if (isnan(rat) || isinf(rat)) { dens[p] = 0.f; issue[p] = 0; return; }       // :1450
+    const double y = (double)yobs[p];
+    int row = -1;
+    for (int i = 0; i < nh; ++i)
+        if (heights[i] > y) { row = i; break; }                                  // first table height above the pixel, :1454
+    int iss = 0;
+    if (row < 0) { row = nh - 1; iss = 4; }                                      // :1457-1459
+    const double* t = knots + (size_t)row * nknots;
+    const double* c = coefs + (size_t)row * ncoef;
+    const double x = (double)rat;
+    // scipy's find_interval with extrapolation: t[l] <= x < t[l+1], clamped to [k, n-1]
+    const int k = 2, n = nknots - k - 1;
+    int l = k;
+    while (x < t[l] && l != k) --l;
+    ++l;
+    while (x >= t[l] && l != n) ++l;
+    const int ell = l - 1;
+    // de Boor's recurrence for the k+1 non-zero B-splines at x (scipy _deBoor_D, no derivative)
+    double h[3] = {1.0, 0.0, 0.0}, hh[3];
+    for (int j = 1; j <= k; ++j) {
+        for (int q = 0; q < j; ++q) hh[q] = h[q];
+        h[0] = 0.0;
+        for (int m = 1; m <= j; ++m) {
+            const int ind = ell + m;
+            const double xb = t[ind], xa = t[ind - j];
+            if (xb == xa) { h[m] = 0.0; continue; }
+            const double w = __ddiv_rn(hh[m - 1], __dsub_rn(xb, xa));
+            h[m - 1] = __dadd_rn(h[m - 1], __dmul_rn(w, __dsub_rn(xb, x)));
+            h[m] = __dmul_rn(w, __dsub_rn(x, xa));
+        }
+    }
+    double out = 0.0;
+    for (int q = 0; q <= k; ++q) out = __dadd_rn(out, __dmul_rn(c[ell + q - k], h[q]));
+    dens[p] = (float)out;
+    issue[p] = iss;
+}
+
 }  // namespace cledb
 
 using namespace cledb;
+
+extern "C" int cledb_obs_dens(cledb_ctx* ctx, int64_t npix, const float* a_obs, const float* b_obs, const float* yobs, int nh,
+                              const double* heights, int nknots, const double* knots, int ncoef, const double* coefs, float* dens_out,
+                              int32_t* issue_out) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    if (npix < 0 || !a_obs || !b_obs || !yobs || nh < 1 || !heights || nknots < 6 || !knots || ncoef != nknots - 3 || !coefs || !dens_out ||
+        !issue_out) {
+        ctx->err = "cledb_obs_dens: bad argument (degree-2 splines: ncoef = nknots - 3)";
+        return CLEDB_ERR_ARG;
+    }
+    if (npix == 0) return CLEDB_OK;
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)npix;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = up(off + b); return o; };
+    const size_t o_a = take(n * 4), o_b = take(n * 4), o_y = take(n * 4), o_h = take((size_t)nh * 8), o_t = take((size_t)nh * nknots * 8),
+                 o_c = take((size_t)nh * ncoef * 8), o_d = take(n * 4), o_i = take(n * 4);
+    int rc = ensure_workspace(ctx, ctx->io, off);
+    if (rc) return rc;
+    unsigned char* w = reinterpret_cast<unsigned char*>(ctx->io.ptr);
+    cudaStream_t st = ctx->stream;
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_a, a_obs, n * 4, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_b, b_obs, n * 4, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_y, yobs, n * 4, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_h, heights, (size_t)nh * 8, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_t, knots, (size_t)nh * nknots * 8, cudaMemcpyHostToDevice, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_c, coefs, (size_t)nh * ncoef * 8, cudaMemcpyHostToDevice, st));
+    k_obs_dens<<<(int)((npix + 255) / 256), 256, 0, st>>>(npix, reinterpret_cast<float*>(w + o_a), reinterpret_cast<float*>(w + o_b),
+                                                         reinterpret_cast<float*>(w + o_y), nh, reinterpret_cast<double*>(w + o_h), nknots,
+                                                         reinterpret_cast<double*>(w + o_t), ncoef, reinterpret_cast<double*>(w + o_c),
+                                                         reinterpret_cast<float*>(w + o_d), reinterpret_cast<int32_t*>(w + o_i));
+    ctx->launches++;
+    CLEDB_CUDA(ctx, cudaGetLastError());
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(dens_out, w + o_d, n * 4, cudaMemcpyDeviceToHost, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(issue_out, w + o_i, n * 4, cudaMemcpyDeviceToHost, st));
+    CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
+    return CLEDB_OK;
+}
+
 
 extern "C" int cledb_obs_integrate(cledb_ctx* ctx, int64_t npix, const double* spec, const cledb_spectral* sp, float* tot, float* snr,
                                    float* background, int32_t* issue, uint8_t* status) {

@@ -479,3 +479,35 @@ def test_spectral_integration_kernel(golden_dir):
     for a, b in zip(got, ref):
         assert same(a, b)
     assert prepinv.obs_integrate([cube], wl + 100.0, kv, 0, 4, False) == (-1, -1, -1)       # unknown line: the reference's triple
+
+
+def test_density_lookup_kernel(golden_dir, tmp_path):
+    """CLEDB_PREPINV.obs_dens on the GPU == the unmodified reference (golden) and == scipy's own spline evaluation, bit for
+    bit before the final rounding, on a larger random map."""
+    pytest.importorskip('scipy')
+    import scipy.interpolate
+    import CLEDB_PREPINV.CLEDB_PREPINV as prepinv
+    import ctrlparams
+    g = np.load(os.path.join(golden_dir, 'density.npz'))
+    np.savez(tmp_path / 'lookup.npz', h=g['h'], den=g['den'], rat=g['rat'])
+    params = ctrlparams.ctrlparams()
+    params.verbose, params.lookuptb = 0, str(tmp_path / 'lookup.npz')
+    dobs, iss = prepinv.obs_dens(g['sobs'], g['yobs'], synth.make_keyvals(7, 8), params)
+    assert same(dobs, g['dobs']) and same(iss, g['iss'])
+    rng = np.random.default_rng(2)
+    n = 20000
+    b = rng.uniform(0.5e-9, 1.5e-9, n).astype(np.float32)
+    a = (b * rng.uniform(0.3, 20.0, n)).astype(np.float32)
+    y = rng.uniform(1.0, 2.0, n).astype(np.float32)
+    splines = [scipy.interpolate.interp1d(g['rat'][i], g['den'], kind="quadratic", fill_value="extrapolate")._spline for i in range(g['h'].size)]
+    knots = np.stack([sp.t for sp in splines])
+    coefs = np.stack([np.asarray(sp.c).reshape(-1) for sp in splines])
+    dens, issue = native.get_context(0).obs_dens(a, b, y, g['h'], knots, coefs)
+    rows = np.array([np.argmax(g['h'] > yy) if (g['h'] > yy).any() else g['h'].size - 1 for yy in y])
+    ref = np.empty(n, np.float32)
+    for i in range(g['h'].size):
+        m = rows == i
+        ref[m] = splines[i]((a[m] / b[m]).astype(np.float64)).reshape(-1)
+    assert np.array_equal(dens, ref)
+    params.lookuptb = 'missing.txt'
+    assert prepinv.obs_dens(g['sobs'], g['yobs'], synth.make_keyvals(7, 8), params)[1].sum() == 0      # the reference's early return

@@ -198,3 +198,13 @@ def test_spectral_integration(golden_dir):
     np.testing.assert_allclose(tot[0, 0, :4], g['aat'], atol=1e-12, rtol=0)
     np.testing.assert_allclose(tot[0, 0, 4:], g['bbt'], atol=1e-12, rtol=0)
     assert not tot[0, 1].any() and not tot[0, 2].any() and set(np.unique(iss)) == {0, 2, 3}
+
+
+def test_density_lookup(golden_dir):
+    """obs_dens of the unmodified reference (ratio -> density through a quadratic spline of the look-up table row above the
+    pixel, issue 4 beyond the table, the 0 / NaN ratio conventions)."""
+    pytest.importorskip('scipy')
+    g = np.load(os.path.join(golden_dir, 'density.npz'))
+    dobs, iss = orc.density_map(g['sobs'], g['yobs'], synth.make_keyvals(7, 8), dict(h=g['h'], den=g['den'], rat=g['rat']))
+    assert same(dobs, g['dobs']) and same(iss, g['iss'])
+    assert dobs[0, 0] == 0 and dobs[0, 1] == 0 and 4 in iss
