@@ -141,6 +141,9 @@ int main() {
     run<16, 2, 0>(12, 1, sms, ghz, out);
     run<16, 1, 0>(16, 1, sms, ghz, out);
     run<16, 2, 0>(8, 2, sms, ghz, out);
+    run<16, 2, 0>(14, 1, sms, ghz, out);
+    run<16, 1, 0>(14, 1, sms, ghz, out);
+    run<16, 2, 0>(7, 2, sms, ghz, out);
     run<4, 2, 0>(8, 2, sms, ghz, out);
     run<4, 4, 0>(12, 2, sms, ghz, out);
     run<4, 4, 0>(16, 2, sms, ghz, out);

@@ -14,7 +14,7 @@ namespace cledb {
 constexpr int kTile     = 256;   // database entries per tile = one warp step (32 lanes x 8 entries)
 constexpr int kEPL      = 8;     // entries per lane
 constexpr int kNC       = 5;     // components that enter chi^2: Q1 U1 I2 Q2 U2 (indices 1 2 4 5 6)
-constexpr int kMaxP     = 32;    // pixels per work item
+constexpr int kMaxP     = 40;    // pixels per work item
 constexpr int kWarps    = 8;     // compute warps per CTA
 constexpr int kThreads  = kWarps * 32;
 constexpr int kParts    = 3;     // sign(V1) classes: 0 = positive, 1 = negative, 2 = zero

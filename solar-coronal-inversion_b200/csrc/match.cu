@@ -490,15 +490,19 @@ __device__ __forceinline__ Item make_item(const Plan& pl, const DbSlot* slots, i
 // ------------------------------------------------------------------------------------------------------
 // kernel 4: the search
 // ------------------------------------------------------------------------------------------------------
-constexpr int kListCap = 256;     // list entries per warp: pixels per item x nsearch <= 256
+constexpr int kListCap = 320;     // list entries per warp: pixels per item x nsearch <= 320 (40 pixels at nsearch 8)
 
 template <int ENC, int PREC> struct KCfg {
-    static constexpr int kWpc = (ENC == CLEDB_ENC_I16) ? 8 : 6;       // independent warps per CTA (shared memory budget)
+    static constexpr int kWpc = (ENC == CLEDB_ENC_I16) ? (PREC == CLEDB_PREC_FP32 ? 12 : 8) : 6;       // independent warps per CTA (shared memory budget)
     static constexpr int kTB = tile_bytes<ENC>();
+    // tiles per step: the fp32 kernel holds two tiles (16 entries per lane) in registers, so that a pixel record loaded
+    // from shared memory feeds 80 packed FMAs instead of 40 (hot-loop ceiling 82 % -> 87 %, profiles/r01_ubench_hot.txt)
+    static constexpr int kTPS = (PREC == CLEDB_PREC_FP32 && ENC == CLEDB_ENC_I16) ? 2 : 1;
+    static constexpr int kStageBytes = kTPS * kTB;
     static constexpr int kRecBytes = (kMaxP + 1) * (int)sizeof(Rec<PREC>);   // one spare record: prefetch overrun
     static constexpr int kListBytes = kListCap * (int)sizeof(Cand<PREC>);
     static constexpr int kC0Bytes = ((kMaxP + 3) / 4) * 16;                    // c0 of the item's pixels (fp32 kernel)
-    static constexpr int kWarpBytes = kStages * kTB + kRecBytes + kListBytes + kStages * 8 + 16 + kC0Bytes;
+    static constexpr int kWarpBytes = kStages * kStageBytes + kRecBytes + kListBytes + kStages * 8 + 16 + kC0Bytes;
 };
 
 // evaluate the lane's 8 entries against the pixel record in shared memory; returns the 8 values
@@ -614,18 +618,18 @@ __device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, float c0f, Cand<
 }
 
 template <int ENC, int PREC>
-__global__ void __launch_bounds__(KCfg<ENC, PREC>::kWpc * 32, PREC == CLEDB_PREC_FP32 ? 2 : 1)
+__global__ void __launch_bounds__(KCfg<ENC, PREC>::kWpc * 32, (PREC == CLEDB_PREC_FP32 && KCfg<ENC, PREC>::kTPS == 1) ? 2 : 1)
 k_match(Plan pl, const DbSlot* __restrict__ slots) {
     using C = KCfg<ENC, PREC>;
     using V = typename Val<PREC>::type;
     using CandT = Cand<PREC>;
     using RecT = Rec<PREC>;
-    constexpr int TB = C::kTB;
+    constexpr int TB = C::kTB, TPS = C::kTPS, SB = C::kStageBytes;
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* stages = smem + (size_t)warp * C::kWarpBytes;                        // [kStages][TB]
-    RecT* recs = reinterpret_cast<RecT*>(stages + kStages * TB);                        // [kMaxP + 1]
+    RecT* recs = reinterpret_cast<RecT*>(stages + kStages * SB);                        // [kMaxP + 1]
     CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);   // [npx][k]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);   // [kStages]
     float* c0s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + kStages * 8 + 16);         // [kMaxP]
@@ -649,13 +653,15 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
         const unsigned char* gt = reinterpret_cast<const unsigned char*>(db.tiles) + (size_t)im.tile0 * TB;
         CandT* gout = reinterpret_cast<CandT*>(pl.plist) + (size_t)it * pl.P * k;
 
-        // ---- stage the item: first tiles in flight, pixel records, empty lists
+        // ---- stage the item: first steps (TPS tiles each) in flight, pixel records, empty lists
+        const int nsteps = (im.ntiles + TPS - 1) / TPS;
         if (lane == 0) {
 #pragma unroll
             for (int s = 0; s < kStages; ++s) {
-                if (s < im.ntiles) {
-                    mbar_expect_tx(&bars[s], TB);
-                    tma_load_1d(stages + s * TB, gt + (size_t)s * TB, TB, &bars[s]);
+                if (s < nsteps) {
+                    const uint32_t bytes = (uint32_t)min(TPS, im.ntiles - s * TPS) * TB;
+                    mbar_expect_tx(&bars[s], bytes);
+                    tma_load_1d(stages + s * SB, gt + (size_t)s * SB, bytes, &bars[s]);
                 }
             }
         }
@@ -683,20 +689,32 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
         for (int c = 0; c < kNC; ++c) scale[c] = db.scale[chi_comp(c)];
         const uint32_t rec_base = smem_u32(recs);
 
-        float d[kEPL][kNC];
+        float d[kEPL][kNC];                       // tile A of the step
+        float d2[TPS == 2 ? kEPL : 1][kNC];       // tile B of the step (fp32 kernel)
         bool exact_only = false;
-        for (int t = 0; t < im.ntiles; ++t) {
-            const int s = t % kStages;
+        for (int step = 0; step < nsteps; ++step) {
+            const int s = step % kStages;
+            const int t = step * TPS, nt = min(TPS, im.ntiles - t);
             mbar_wait(&bars[s], (phase_bits >> s) & 1u);
             phase_bits ^= 1u << s;
-            load_tile_regs<ENC>(stages + s * TB, lane, d);
+            load_tile_regs<ENC>(stages + s * SB, lane, d);
+            if (TPS == 2) {
+                if (nt == 2) load_tile_regs<ENC>(stages + s * SB + TB, lane, reinterpret_cast<float(&)[kEPL][kNC]>(d2));
+                else {                            // odd tile count: the missing tile is NaN, never flagged, never a hit
+#pragma unroll
+                    for (int e = 0; e < kEPL; ++e)
+#pragma unroll
+                        for (int c = 0; c < kNC; ++c) d2[TPS == 2 ? e : 0][c] = CUDART_NAN_F;
+                }
+            }
             __syncwarp();                         // every lane has its registers: the stage can be refilled
-            if (lane == 0 && t + kStages < im.ntiles) {
-                mbar_expect_tx(&bars[s], TB);
-                tma_load_1d(stages + s * TB, gt + (size_t)(t + kStages) * TB, TB, &bars[s]);
+            if (lane == 0 && step + kStages < nsteps) {
+                const uint32_t bytes = (uint32_t)min(TPS, im.ntiles - (step + kStages) * TPS) * TB;
+                mbar_expect_tx(&bars[s], bytes);
+                tma_load_1d(stages + s * SB, gt + (size_t)(step + kStages) * SB, bytes, &bars[s]);
             }
             const int base = (im.tile0 + t) * kTile;
-            if (t == 0) {
+            if (step == 0) {
                 int rows[kEPL];                  // original rows of my 8 entries of the first tile (tie-break only)
 #pragma unroll
                 for (int e = 0; e < kEPL; ++e) {
@@ -707,45 +725,74 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                 for (int j = 0; j < im.npx; ++j) {
                     bootstrap_pixel<ENC, PREC>(recs + j, PREC == CLEDB_PREC_FP32 ? c0s[j] : 0.f, lists + j * k, d, scale, base,
                                                im.cnt_end, rows, k, lane);
+                    if (TPS == 2 && nt == 2)
+                        slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, reinterpret_cast<float(&)[kEPL][kNC]>(d2), scale,
+                                              base + kTile, im.cnt_end, db.perm, k, lane);
                     unfilled |= !(recs[j].tau < inf_of(V()));
                 }
                 exact_only = unfilled;
                 continue;
             }
             if (PREC == CLEDB_PREC_FP32 && pl.dbg != 3 && !exact_only) {
-                // fast pass: 40 packed FMAs per pixel, no control flow, no min tree.  The accumulators start at
-                // c0 - tau*(1 + 2^-19), so the OR of the sign bits says "one of my 8 entries may beat the threshold of
-                // pixel j"; one funnel shift moves that bit into bit (npx-1-j) of hmask.
-                uint32_t hmask = 0;
-                uint32_t ra = rec_base;
-                float4 n0 = lds128(ra), n1 = lds128(ra + 16), n2 = lds128(ra + 32);
+                // fast pass: 40 packed FMAs per pixel and tile, no control flow, no min tree.  The accumulators start at
+                // c0 - tau*(1 + 2^-19), so the OR of the sign bits says "one of my 8 entries of this tile may beat the
+                // threshold of pixel j"; one funnel shift moves that bit into bit (npx-1-j) of the tile's mask.
+                // Items can hold more than 32 pixels: the pixel loop runs in segments of <= 32 (one mask word per tile each).
+                for (int j0 = 0; j0 < im.npx; j0 += 32) {
+                    const int nseg = min(32, im.npx - j0);
+                    uint32_t hmask = 0, hmask2 = 0;
+                    uint32_t ra = rec_base + (uint32_t)j0 * (uint32_t)sizeof(RecT);
+                    float4 n0 = lds128(ra), n1 = lds128(ra + 16), n2 = lds128(ra + 32);
 #pragma unroll 2
-                for (int j = 0; j < im.npx; ++j) {
-                    const float4 x0 = n0, x1 = n1, x2 = n2;
-                    ra += (uint32_t)sizeof(RecT);
-                    n0 = lds128(ra); n1 = lds128(ra + 16); n2 = lds128(ra + 32);     // prefetch (recs has a spare slot)
-                    const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
-                    const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
-                    float v[kEPL];
-                    eval_fp32_all(d, a, nb, x2.z, v);
-                    const uint32_t sg = ((__float_as_uint(v[0]) | __float_as_uint(v[1]) | __float_as_uint(v[2])) |
-                                         (__float_as_uint(v[3]) | __float_as_uint(v[4]) | __float_as_uint(v[5]))) |
-                                        (__float_as_uint(v[6]) | __float_as_uint(v[7]));
-                    hmask = __funnelshift_l(sg, hmask, 1);
-                }
-                // rare pass: pixels flagged by any lane are evaluated again and their candidates inserted at once, so
-                // the threshold is exact before the pixel is visited for the next tile
-                uint32_t any = pl.dbg == 2 ? 0u : __reduce_or_sync(0xffffffffu, hmask);
-                while (any) {
-                    const int b = 31 - __clz(any);
-                    any &= ~(1u << b);
-                    const int j = im.npx - 1 - b;
-                    slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
+                    for (int j = 0; j < nseg; ++j) {
+                        const float4 x0 = n0, x1 = n1, x2 = n2;
+                        ra += (uint32_t)sizeof(RecT);
+                        n0 = lds128(ra); n1 = lds128(ra + 16); n2 = lds128(ra + 32);     // prefetch (recs has a spare slot)
+                        const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
+                        const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
+                        float v[kEPL];
+                        eval_fp32_all(d, a, nb, x2.z, v);
+                        const uint32_t sg = ((__float_as_uint(v[0]) | __float_as_uint(v[1]) | __float_as_uint(v[2])) |
+                                             (__float_as_uint(v[3]) | __float_as_uint(v[4]) | __float_as_uint(v[5]))) |
+                                            (__float_as_uint(v[6]) | __float_as_uint(v[7]));
+                        hmask = __funnelshift_l(sg, hmask, 1);
+                        if (TPS == 2) {
+                            float w[kEPL];
+                            eval_fp32_all(reinterpret_cast<float(&)[kEPL][kNC]>(d2), a, nb, x2.z, w);
+                            const uint32_t sg2 = ((__float_as_uint(w[0]) | __float_as_uint(w[1]) | __float_as_uint(w[2])) |
+                                                  (__float_as_uint(w[3]) | __float_as_uint(w[4]) | __float_as_uint(w[5]))) |
+                                                 (__float_as_uint(w[6]) | __float_as_uint(w[7]));
+                            hmask2 = __funnelshift_l(sg2, hmask2, 1);
+                        }
+                    }
+                    // rare pass: pixels flagged by any lane are evaluated again and their candidates inserted at once, so
+                    // the threshold is exact before the pixel is visited for the next step (tile A before tile B)
+                    uint32_t any = pl.dbg == 2 ? 0u : __reduce_or_sync(0xffffffffu, hmask);
+                    while (any) {
+                        const int b = 31 - __clz(any);
+                        any &= ~(1u << b);
+                        const int j = j0 + nseg - 1 - b;
+                        slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
+                    }
+                    if (TPS == 2) {
+                        any = pl.dbg == 2 ? 0u : __reduce_or_sync(0xffffffffu, hmask2);
+                        while (any) {
+                            const int b = 31 - __clz(any);
+                            any &= ~(1u << b);
+                            const int j = j0 + nseg - 1 - b;
+                            slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, reinterpret_cast<float(&)[kEPL][kNC]>(d2), scale,
+                                                  base + kTile, im.cnt_end, db.perm, k, lane);
+                        }
+                    }
                 }
             } else {
-                for (int j = 0; j < im.npx; ++j)
+                for (int j = 0; j < im.npx; ++j) {
                     slow_pixel<ENC, PREC>(recs + j, PREC == CLEDB_PREC_FP32 ? c0s[j] : 0.f, lists + j * k, d, scale, base,
                                           im.cnt_end, db.perm, k, lane);
+                    if (TPS == 2 && nt == 2)
+                        slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, reinterpret_cast<float(&)[kEPL][kNC]>(d2), scale,
+                                              base + kTile, im.cnt_end, db.perm, k, lane);
+                }
             }
         }
         __syncwarp();
