@@ -187,9 +187,7 @@ extern "C" int cledb_match(cledb_ctx* ctx, int mode, int precision, int64_t npix
     if (rows_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(rows_out, w + o_rows, n * k * 32, cudaMemcpyDeviceToHost, st));
     if (status_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(status_out, w + o_st, n, cudaMemcpyDeviceToHost, st));
     if (ncand_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(ncand_out, w + o_nc, n * 8, cudaMemcpyDeviceToHost, st));
-    int32_t flags[4] = {0, 0, 0, 0};
     CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
-    (void)flags;
     return CLEDB_OK;
 }
 

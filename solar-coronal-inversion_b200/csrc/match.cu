@@ -985,14 +985,19 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     k_classify<PREC><<<nb, 256, 0, st>>>(pl, sobs, snr, db_id, ctx->d_slots, ctx->d_slot_of_id, ctx->id_cap);
     ctx->launches += 1;
     // ---- the bucket sizes come back to the host (a few hundred bytes, one stream synchronisation) and fix the work shape
-    if ((int)ctx->h_cnt_cap < pl.nkeys) {
+    if ((int)ctx->h_cnt_cap < pl.nkeys + 4) {
         if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
         ctx->h_cnt = nullptr;
-        CLEDB_CUDA(ctx, cudaMallocHost(&ctx->h_cnt, sizeof(int32_t) * pl.nkeys));
-        ctx->h_cnt_cap = pl.nkeys;
+        CLEDB_CUDA(ctx, cudaMallocHost(&ctx->h_cnt, sizeof(int32_t) * (pl.nkeys + 4)));
+        ctx->h_cnt_cap = pl.nkeys + 4;
     }
     CLEDB_CUDA(ctx, cudaMemcpyAsync(ctx->h_cnt, pl.cnt, sizeof(int32_t) * pl.nkeys, cudaMemcpyDeviceToHost, st));
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(ctx->h_cnt + pl.nkeys, pl.counters, sizeof(int32_t) * 3, cudaMemcpyDeviceToHost, st));
     CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ctx->h_cnt[pl.nkeys + 1] != 0) {                   // k_classify met a searched pixel whose database id was never put
+        ctx->err = "cledb_match: a pixel refers to a database id that is not resident (cledb_db_put it first)";
+        return CLEDB_ERR_NODB;
+    }
     choose_shape(ctx, ctx->h_cnt, std::min<int>(pl.nkeys, (int)ctx->dbs.size() * kParts), pl.mode, pl.k, wslots, pmax, &pl.P, &pl.split);
     int64_t tiles_of_pixels = 0;
     for (int key = 0; key < pl.nkeys; ++key) tiles_of_pixels += (ctx->h_cnt[key] + pl.P - 1) / pl.P;

@@ -511,3 +511,44 @@ def test_density_lookup_kernel(golden_dir, tmp_path):
     assert np.array_equal(dens, ref)
     params.lookuptb = 'missing.txt'
     assert prepinv.obs_dens(g['sobs'], g['yobs'], synth.make_keyvals(7, 8), params)[1].sum() == 0      # the reference's early return
+
+
+def test_unit_test_database_choice_kernel(ctx):
+    """tests/test_functions.py:91-93 of the reference through cledb_db_select."""
+    names = ['DB_h106_d895.npy', 'DB_h109_d795.npy', 'DB_h109_d895.npy']
+    sel = ctx.db_select(np.float32([1.0920165]), np.float32([7.936]), orc.file_table(names))
+    assert names[int(sel[0])] == 'DB_h109_d795.npy'
+
+
+def test_error_paths_of_the_fused_calls(ctx):
+    """Argument errors of cledb_invert / cledb_invert_reduced / cledb_db_select / cledb_obs_integrate come back as error
+    codes with a message (CledbError), never as a crash or a silent result."""
+    db = synth.make_database(8, 39, ngx=3, nbphi=12, nbtheta=8)
+    obs = synth.make_observation(4, 4, [db], seed=1)
+    hdr = synth.make_dbhdr(3, 12, 8)
+    ctx.db_put(0, db, native.ENC_F32)
+    s, n = obs['sobs_totrot'].reshape(-1, 8), obs['snr'].reshape(-1, 8)
+    z = np.zeros(16, np.int32)
+    args = (s, n, z, 4, obs['yobs'], obs['dobs'], obs['aobs'])
+    with pytest.raises(native.CledbError, match='bcalc 3'):
+        ctx.invert(native.MODE_IQUV, *args, None, hdr, 1000, 3)                      # bcalc 3 without IQUD (CLEDB_PROC.py:174-178)
+    with pytest.raises(native.CledbError, match='Doppler'):
+        ctx.invert(native.MODE_IQUD, *args, None, hdr, 1000, 3)
+    cle = hdr[:14] + (np.int32(0),)
+    with pytest.raises(native.CledbError, match='PyCELP'):
+        ctx.invert(native.MODE_IQUV, *args, None, cle, 1000, 0)                      # CLE-type headers are built by the host path
+    with pytest.raises(native.CledbError, match='nsearch'):
+        ctx.invert(native.MODE_IQUV, s, n, z, 33, obs['yobs'], obs['dobs'], obs['aobs'], None, hdr, 1000, 0)
+    with pytest.raises(native.CledbError):
+        ctx.invert(native.MODE_IQUV, s, n, z + 7, 4, obs['yobs'], obs['dobs'], obs['aobs'], None, hdr, 1000, 0)   # unknown database id
+    big = synth.make_dbhdr(5, 12, 8)
+    with pytest.raises(native.CledbError, match='rows'):
+        ctx.invert_reduced(native.MODE_IQUV, *args, obs['sobs_dopp'].reshape(16, -1), big, 1000, 0)             # grid does not match the database
+    with pytest.raises(native.CledbError, match='nsearch exceeds'):
+        ctx.invert_reduced(native.MODE_IQUV, s, n, z, 9, obs['yobs'], obs['dobs'], obs['aobs'], obs['sobs_dopp'].reshape(16, -1), hdr, 1000, 0)
+    with pytest.raises(native.CledbError):
+        ctx.obs_integrate(np.zeros((2, 2, 4)), np.array([1074.0, 1074.1]), 0)       # fewer than three wavelength samples
+    # a result is still produced after the errors
+    inv, sf, st = ctx.invert(native.MODE_IQUV, *args, None, hdr, 1000, 0)
+    assert (st == native.PIX_SEARCHED).sum() > 8 and (inv[st == native.PIX_SEARCHED][:, 0, 0] >= 0).all()
+    ctx.db_drop(0)

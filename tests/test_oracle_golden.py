@@ -208,3 +208,11 @@ def test_density_lookup(golden_dir):
     dobs, iss = orc.density_map(g['sobs'], g['yobs'], synth.make_keyvals(7, 8), dict(h=g['h'], den=g['den'], rat=g['rat']))
     assert same(dobs, g['dobs']) and same(iss, g['iss'])
     assert dobs[0, 0] == 0 and dobs[0, 1] == 0 and 4 in iss
+
+
+def test_unit_test_database_choice():
+    """tests/test_functions.py:91-93 of the reference: its test pixel (height 1.092, log density 7.936) picks
+    DB_h109_d795.npy out of the three files of tests/dbfiles."""
+    names = ['DB_h106_d895.npy', 'DB_h109_d795.npy', 'DB_h109_d895.npy']
+    table = orc.file_table(names)
+    assert names[int(orc.nearest_database(np.float32(1.0920165), np.float32(7.936), table))] == 'DB_h109_d795.npy'
