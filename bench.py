@@ -42,7 +42,7 @@ def parse():
     ap.add_argument('--nx', type=int, default=256)
     ap.add_argument('--encoding', type=int, default=1)
     ap.add_argument('--ndb', type=int, default=1, help='number of distinct (height, density) databases the map touches')
-    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--cpu-seconds', type=float, default=20.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dbg', type=int, default=0, help='kernel timing experiment (results invalid)')
     ap.add_argument('--ppi', type=int, default=0, help='tuning: pixels per warp item (0 = library default)')
@@ -103,7 +103,7 @@ def cpu_workers():
 
 def cpu_baseline(args, db, obs):
     workers = cpu_workers()
-    n0 = 4 * workers
+    n0 = 16 * workers                   # probe large enough that pool start-up does not dominate the per-pixel estimate
     t = cpu_run(args, db, obs, n0, workers, 0)
     n1 = int(max(n0, min(args.nx * args.nx, n0 * args.cpu_seconds / max(t, 1e-3))))
     t1 = cpu_run(args, db, obs, n1, workers, 1)
@@ -308,6 +308,12 @@ def main():
         return
 
     kms = float(np.mean(kern_ms)) if len(kern_ms) else float('nan')
+    traffic = None                                        # DRAM bytes of the search kernel per launch, from the committed ncu capture
+    if args.nx == 256 and args.ndb == 1 and args.encoding == 1:
+        try:
+            traffic = json.load(open(os.path.join(REPO, 'profiles', 'k_match_traffic.json')))[args.mode]
+        except Exception:
+            traffic = None
     flops = 20.0 * ncand                                  # 10 FMA per candidate evaluation, this rank
     achieved = flops / (kms * 1e-3) / 1e12
     theo = props['sm_count'] * 128 * 2 * (clocks['sm_max_mhz'] or props['sm_clock_khz'] / 1e3) * 1e6 / 1e12
@@ -327,7 +333,7 @@ def main():
         e2e=dict(value=world * npix / e2e_s, unit='pixels/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  api='cledb_invert (C-ABI, pinned host buffers in, finished invout/sfound maps out)', ms_per_step=e2e_s * 1e3),
         roofline=dict(bound='fp32', kernel='k_match<int16,fp32>', achieved=achieved, peak=peak, unit='TFLOP/s',
-                      frac=achieved / peak if peak else None, traffic=None, kernel_ms=kms,
+                      frac=achieved / peak if peak else None, traffic=traffic, kernel_ms=kms,
                       kernel_share_of_step=kms / float(np.mean(step_ms)),
                       flop_per_candidate=20, candidates_per_launch=ncand,
                       peak_source='FFMA microkernel measured in this run (cledb_measure_fp32_peak); theoretical %.1f TFLOP/s '
