@@ -4,16 +4,17 @@
 //
 // Work decomposition:
 //   bucket  = all pixels that search the same candidate list: (database, sign(V_obs)) for IQUV, database for IQUD
-//   item    = <= 32 pixels of one bucket  x  one contiguous tile range of one sign partition of the database
+//   item    = <= 40 pixels of one bucket  x  one contiguous tile range of one sign partition of the database
 //   warp    = the unit of work: a warp fetches an item, owns its pixels exclusively and streams ALL tiles of the
 //             item past them.  Nothing is shared between warps: no locks, no queues, no __syncthreads.
-//             A lane holds 8 database entries (5 chi^2 components each, decoded from int16 in registers); per pixel
-//             3 broadcast LDS.128 (10 coefficients + constant + threshold tau) feed 80 FFMA.
+//             A step handles two tiles: a lane holds 2 x 8 database entries (5 chi^2 components each, decoded from
+//             int16 in registers); per pixel 3 broadcast LDS.128 (10 coefficients + flag start value + threshold tau)
+//             feed 80 packed FP32 FMAs (fma.rn.f32x2).
 //   top-k   = per pixel a sorted list of nsearch (value, position) pairs in the warp's shared-memory slice, kept
 //             distributed over the lanes while inserting (warp shuffles).  The k-th value tau is the pruning
-//             threshold: a lane whose entry beats tau drops (value, pixel, slot) into the warp's candidate buffer
-//             from inside the FFMA loop (rare, divergent, values still in registers); the buffer is merged into
-//             the lists once per tile, so tau is exact again before the pixel is visited next.
+//             threshold: the hot loop only sets a flag bit per (pixel, tile) - the sign of an accumulator started at
+//             c0 - tau - and flagged pixels are re-evaluated exactly and inserted right after the pixel loop, so tau
+//             is exact again before the pixel is visited for the next step.
 //   TMA     = database tiles are contiguous 2.5 KB (int16) / 5 KB (fp32) blocks moved global->shared with
 //             cp.async.bulk + mbarrier complete_tx, double buffered per warp.
 #include <math_constants.h>
