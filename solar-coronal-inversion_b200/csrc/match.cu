@@ -106,7 +106,9 @@ template <> struct EncTraits<CLEDB_ENC_I16> { static constexpr int kElem = 2; };
 template <> struct EncTraits<CLEDB_ENC_F32> { static constexpr int kElem = 4; };
 template <int ENC> __host__ __device__ constexpr int tile_bytes() { return kNC * kTile * EncTraits<ENC>::kElem; }
 
-constexpr int kStages = 2;
+// One shared-memory stage per warp: a step's tiles are copied into registers at once, the refill is issued right after and
+// is in flight during the step's compute (13 us for a 36-pixel item), so the registers are the second buffer.
+constexpr int kStages = 1;
 
 // position inside a tile of entry e of a lane.  Chosen so that the lane's shared-memory reads are 16-byte
 // vectors at a 16-byte lane stride (conflict free): int16 -> 8 consecutive entries per lane and component,
@@ -494,16 +496,17 @@ __device__ __forceinline__ Item make_item(const Plan& pl, const DbSlot* slots, i
 constexpr int kListCap = 320;     // list entries per warp: pixels per item x nsearch <= 320 (40 pixels at nsearch 8)
 
 template <int ENC, int PREC> struct KCfg {
-    static constexpr int kWpc = (ENC == CLEDB_ENC_I16) ? (PREC == CLEDB_PREC_FP32 ? 12 : 8) : 6;       // independent warps per CTA (shared memory budget)
+    static constexpr int kWpc = PREC == CLEDB_PREC_FP32 ? 12 : 8;       // independent warps per CTA (shared memory budget)
     static constexpr int kTB = tile_bytes<ENC>();
     // tiles per step: the fp32 kernel holds two tiles (16 entries per lane) in registers, so that a pixel record loaded
     // from shared memory feeds 80 packed FMAs instead of 40 (hot-loop ceiling 82 % -> 87 %, profiles/r01_ubench_hot.txt)
-    static constexpr int kTPS = (PREC == CLEDB_PREC_FP32 && ENC == CLEDB_ENC_I16) ? 2 : 1;
+    static constexpr int kTPS = PREC == CLEDB_PREC_FP32 ? 2 : 1;
     static constexpr int kStageBytes = kTPS * kTB;
     static constexpr int kRecBytes = (kMaxP + 1) * (int)sizeof(Rec<PREC>);   // one spare record: prefetch overrun
     static constexpr int kListBytes = kListCap * (int)sizeof(Cand<PREC>);
     static constexpr int kC0Bytes = ((kMaxP + 3) / 4) * 16;                    // c0 of the item's pixels (fp32 kernel)
-    static constexpr int kWarpBytes = kStages * kStageBytes + kRecBytes + kListBytes + kStages * 8 + 16 + kC0Bytes;
+    // every warp slice starts 128-byte aligned (bulk-copy destination, 16-byte vector loads)
+    static constexpr int kWarpBytes = (kStages * kStageBytes + kRecBytes + kListBytes + kStages * 8 + 16 + kC0Bytes + 127) / 128 * 128;
 };
 
 // evaluate the lane's 8 entries against the pixel record in shared memory; returns the 8 values
@@ -633,7 +636,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
     RecT* recs = reinterpret_cast<RecT*>(stages + kStages * SB);                        // [kMaxP + 1]
     CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);   // [npx][k]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);   // [kStages]
-    float* c0s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + kStages * 8 + 16);         // [kMaxP]
+    float* c0s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + (kStages * 8 + 15) / 16 * 16);   // [kMaxP]
     const int k = pl.k;
     uint32_t phase_bits = 0;
 
