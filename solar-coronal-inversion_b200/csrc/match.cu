@@ -837,74 +837,95 @@ __device__ __forceinline__ void decode_row(const DbSlot& db, int pos, float* row
 }
 
 constexpr int kMaxSub = 24;   // 3 sign partitions x up to 8 chunks
+constexpr int kFinPix = 64;   // pixels per block of the finalise kernel
 
+// Two phases per block of 64 pixels.  (1) one thread per pixel merges the pixel's partial lists (chunks / sign classes)
+// into shared memory: value, stored position, original row of its nsearch winners.  (2) one thread per (pixel, slot)
+// decodes the winner's row and writes idx / chi / kpos / rows: consecutive threads write consecutive elements.
 template <int PREC>
-__global__ void __launch_bounds__(128) k_finalize(Plan pl, const DbSlot* __restrict__ slots, int32_t* __restrict__ idx_out,
+__global__ void __launch_bounds__(256) k_finalize(Plan pl, const DbSlot* __restrict__ slots, int32_t* __restrict__ idx_out,
                                                    float* __restrict__ chi_out, double* __restrict__ chi64_out,
                                                    int32_t* __restrict__ kpos_out, float* __restrict__ rows_out,
                                                    int64_t* __restrict__ ncand_out) {
     using V = typename Val<PREC>::type;
     using CandT = Cand<PREC>;
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pl.npix) return;
+    extern __shared__ __align__(16) unsigned char fsm[];
     const int k = pl.k;
-    const int key = pl.key[p];
-    if (key < 0) {
-        for (int r = 0; r < k; ++r) {
-            idx_out[p * k + r] = -1;
-            chi_out[p * k + r] = 0.f;
-            if (chi64_out) chi64_out[p * k + r] = 0.0;
-            if (kpos_out) kpos_out[p * k + r] = -1;
-            if (rows_out) for (int c = 0; c < 8; ++c) rows_out[(p * k + r) * 8 + c] = 0.f;
+    V* s_val = reinterpret_cast<V*>(fsm);                                        // [kFinPix][k]
+    int32_t* s_pos = reinterpret_cast<int32_t*>(s_val + kFinPix * k);            // [kFinPix][k] stored position, -1 = empty slot
+    int32_t* s_idx = s_pos + kFinPix * k;                                        // [kFinPix][k] original row
+    int32_t* s_key = s_idx + kFinPix * k;                                        // [kFinPix]
+    const int64_t p0 = (int64_t)blockIdx.x * kFinPix;
+
+    if (threadIdx.x < kFinPix) {
+        const int64_t p = p0 + threadIdx.x;
+        const int lp = threadIdx.x;
+        int key = -1;
+        if (p < pl.npix) key = pl.key[p];
+        s_key[lp] = key;
+        if (key < 0) {
+            for (int r = 0; r < k; ++r) s_pos[lp * k + r] = -1;
+            if (ncand_out && p < pl.npix) ncand_out[p] = 0;
+        } else {
+            const DbSlot& db = slots[key / kParts];
+            const int local = pl.rank[p] - pl.off[key];
+            const int tile = local / pl.P, j = local - tile * pl.P;
+            const int ns = pl.nsub[key];
+            const CandT* base = reinterpret_cast<const CandT*>(pl.plist) + ((size_t)(pl.item0[key] + tile * ns) * pl.P + j) * k;
+            const size_t sub_stride = (size_t)pl.P * k;
+            unsigned char head[kMaxSub];
+            for (int s = 0; s < ns; ++s) head[s] = 0;
+            for (int r = 0; r < k; ++r) {
+                int best = -1, bpos = -1, bidx = 0x7fffffff;
+                V bv = inf_of(V());
+                for (int s = 0; s < ns; ++s) {
+                    if (head[s] >= k) continue;
+                    const CandT c = base[s * sub_stride + head[s]];
+                    if (c.pos < 0) { head[s] = (unsigned char)k; continue; }
+                    const int oi = db.perm[c.pos];             // lists carry stored positions; ties go to the lowest original row
+                    if (best < 0 || c.v < bv || (c.v == bv && oi < bidx)) { best = s; bv = c.v; bpos = c.pos; bidx = oi; }
+                }
+                if (best >= 0) head[best]++;
+                s_val[lp * k + r] = bv;
+                s_pos[lp * k + r] = best >= 0 ? bpos : -1;
+                s_idx[lp * k + r] = bidx;
+            }
+            if (ncand_out) {
+                const int cls = key % kParts;
+                ncand_out[p] = pl.mode == CLEDB_MODE_IQUV ? db.part_cnt[cls] : (int64_t)db.part_cnt[0] + db.part_cnt[1] + db.part_cnt[2];
+            }
         }
-        if (ncand_out) ncand_out[p] = 0;
-        return;
     }
-    const DbSlot& db = slots[key / kParts];
-    const int local = pl.rank[p] - pl.off[key];
-    const int tile = local / pl.P, j = local - tile * pl.P;
-    const int ns = pl.nsub[key];
-    const CandT* base = reinterpret_cast<const CandT*>(pl.plist) + ((size_t)(pl.item0[key] + tile * ns) * pl.P + j) * k;
-    const size_t sub_stride = (size_t)pl.P * k;
-    unsigned char head[kMaxSub];
-    for (int s = 0; s < ns; ++s) head[s] = 0;
-    const int cls = key % kParts;
-    for (int r = 0; r < k; ++r) {
-        int best = -1, bpos = -1, bidx = 0x7fffffff;
-        V bv = inf_of(V());
-        for (int s = 0; s < ns; ++s) {
-            if (head[s] >= k) continue;
-            const CandT c = base[s * sub_stride + head[s]];
-            if (c.pos < 0) { head[s] = (unsigned char)k; continue; }
-            const int oi = db.perm[c.pos];                 // lists carry stored positions; ties go to the lowest original row
-            if (best < 0 || c.v < bv || (c.v == bv && oi < bidx)) { best = s; bv = c.v; bpos = c.pos; bidx = oi; }
-        }
-        const int64_t o = p * k + r;
-        if (best < 0) {
+    __syncthreads();
+    const int64_t nout = min((int64_t)kFinPix, pl.npix - p0) * k;
+    for (int64_t t = threadIdx.x; t < nout; t += blockDim.x) {
+        const int lp = (int)(t / k);
+        const int64_t o = p0 * k + t;
+        const int bpos = s_pos[t];
+        float row[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (bpos < 0) {
             idx_out[o] = -1;
             chi_out[o] = 0.f;
             if (chi64_out) chi64_out[o] = 0.0;
             if (kpos_out) kpos_out[o] = -1;
-            if (rows_out) for (int c = 0; c < 8; ++c) rows_out[o * 8 + c] = 0.f;
-            continue;
-        }
-        head[best]++;
-        idx_out[o] = bidx;
-        const double chi = (PREC == CLEDB_PREC_FP32) ? (double)(0.5f * (float)bv) : (double)bv;
-        chi_out[o] = (float)chi;
-        if (chi64_out) chi64_out[o] = chi;
-        if (kpos_out) {
-            if (pl.mode == CLEDB_MODE_IQUV) kpos_out[o] = db.row_kpos[bidx];
-            else kpos_out[o] = db.kept_rank ? db.kept_rank[bidx] : bidx;
+        } else {
+            const DbSlot& db = slots[s_key[lp] / kParts];
+            const int bidx = s_idx[t];
+            const double chi = (PREC == CLEDB_PREC_FP32) ? (double)(0.5f * (float)s_val[t]) : (double)s_val[t];
+            idx_out[o] = bidx;
+            chi_out[o] = (float)chi;
+            if (chi64_out) chi64_out[o] = chi;
+            if (kpos_out) {
+                if (pl.mode == CLEDB_MODE_IQUV) kpos_out[o] = db.row_kpos[bidx];
+                else kpos_out[o] = db.kept_rank ? db.kept_rank[bidx] : bidx;
+            }
+            if (rows_out) decode_row(db, bpos, row);
         }
         if (rows_out) {
-            float row[8];
-            decode_row(db, bpos, row);
-            for (int c = 0; c < 8; ++c) rows_out[o * 8 + c] = row[c];
+            reinterpret_cast<float4*>(rows_out)[2 * o] = make_float4(row[0], row[1], row[2], row[3]);
+            reinterpret_cast<float4*>(rows_out)[2 * o + 1] = make_float4(row[4], row[5], row[6], row[7]);
         }
     }
-    if (ncand_out)
-        ncand_out[p] = (pl.mode == CLEDB_MODE_IQUV) ? db.part_cnt[cls] : (int64_t)db.part_cnt[0] + db.part_cnt[1] + db.part_cnt[2];
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1031,8 +1052,9 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
         CLEDB_CUDA(ctx, cudaEventRecord(ctx->prof[ctx->prof_used].second, st));
         ctx->prof_used++;
     }
-    k_finalize<PREC><<<(int)((npix + 127) / 128), 128, 0, st>>>(pl, ctx->d_slots, idx_out, chi_out, chi64_out, kpos_out,
-                                                               rows_out, ncand_out);
+    const size_t fin_smem = (size_t)kFinPix * pl.k * (sizeof(typename Val<PREC>::type) + 8) + kFinPix * 4;
+    k_finalize<PREC><<<(int)((npix + kFinPix - 1) / kFinPix), 256, fin_smem, st>>>(pl, ctx->d_slots, idx_out, chi_out, chi64_out,
+                                                                                  kpos_out, rows_out, ncand_out);
     ctx->launches += 2;
     CLEDB_CUDA(ctx, cudaGetLastError());
     return CLEDB_OK;

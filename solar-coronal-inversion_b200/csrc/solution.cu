@@ -57,24 +57,27 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
                                                const int32_t* __restrict__ kpos, const float* __restrict__ rows,
                                                const uint8_t* __restrict__ status, const int32_t* __restrict__ nan_slots,
                                                float* __restrict__ invout, float* __restrict__ sfound) {
-    // one thread per (pixel, output slot): consecutive threads write consecutive 44- and 32-byte records
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= npix * k) return;
-    const int64_t p = t / k;
-    const int s = (int)(t - p * k);
-    float* o = invout + t * 11;
-    float* f = sfound + t * 8;
+    // one thread per (pixel, output slot); the 44- and 32-byte records of a block are staged in shared memory and stored
+    // with coalesced 16-byte writes
+    __shared__ __align__(16) float s_inv[128 * 11];
+    __shared__ __align__(16) float s_sf[128 * 8];
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x, t = t0 + threadIdx.x;
+    float o[11], f[8];
     o[0] = -1.0f;
 #pragma unroll
     for (int c = 1; c < 11; ++c) o[c] = 0.0f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) f[c] = 0.0f;
+    do {
+    if (t >= npix * k) break;
+    const int64_t p = t / k;
+    const int s = (int)(t - p * k);
     const int st = status[p];
     if (st == CLEDB_PIX_ALLINF) {                       // every chi^2 is +inf in the reference: rejected with that value
         o[1] = CUDART_INF_F;
-        return;
+        break;
     }
-    if (st != CLEDB_PIX_SEARCHED) return;
+    if (st != CLEDB_PIX_SEARCHED) break;
 
     const int32_t* ix = idx + p * k;
     const int32_t* kp = kpos + p * k;
@@ -99,11 +102,11 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
     const double limit = mode == CLEDB_MODE_IQUV ? maxchisq * 10.0 : maxchisq;          // CLEDB_PROC.py:1027 / 1202
     if (shift == 0 && ix[w0] >= 0 && chi_of(w0) > limit) {
         o[1] = (float)chi_of(w0);
-        return;
+        break;
     }
-    if (w < 0 || ix[w] < 0) return;
+    if (w < 0 || ix[w] < 0) break;
     const double cw = chi_of(w);
-    if (!(cw <= maxchisq)) return;                                                       // :1044 / :1219
+    if (!(cw <= maxchisq)) break;                                                        // :1044 / :1219
     float so[8];
     {
         const float4 a = reinterpret_cast<const float4*>(sobs)[2 * p], b = reinterpret_cast<const float4*>(sobs)[2 * p + 1];
@@ -177,6 +180,20 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
         f[6] = __fadd_rn(__fmul_rn(q2, rs), __fmul_rn(u2, rc));
         f[7] = __fmul_rn(r[7], nf);
     }
+    } while (0);
+#pragma unroll
+    for (int c = 0; c < 11; ++c) s_inv[threadIdx.x * 11 + c] = o[c];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s_sf[threadIdx.x * 8 + c] = f[c];
+    __syncthreads();
+    const int64_t nthr = min((int64_t)blockDim.x, npix * k - t0);                       // output slots of this block
+    if (nthr <= 0) return;
+    float4* gi = reinterpret_cast<float4*>(invout + t0 * 11);                           // t0 * 44 B is a multiple of 16
+    float4* gs = reinterpret_cast<float4*>(sfound + t0 * 8);
+    const int n4i = (int)(nthr * 11 / 4), n4s = (int)(nthr * 2);
+    for (int i = threadIdx.x; i < n4i; i += blockDim.x) gi[i] = reinterpret_cast<const float4*>(s_inv)[i];
+    for (int i = n4i * 4 + threadIdx.x; i < nthr * 11; i += blockDim.x) invout[t0 * 11 + i] = s_inv[i];      // tail of a partial block
+    for (int i = threadIdx.x; i < n4s; i += blockDim.x) gs[i] = reinterpret_cast<const float4*>(s_sf)[i];
 }
 
 int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsearch, const float* sobs, const float* yobs,
