@@ -69,10 +69,12 @@ extern "C" int cledb_codec_shift(const float* x, int64_t n, int64_t stride) {
     return s;
 }
 extern "C" void cledb_codec_encode(const float* x, int64_t n, int shift, int16_t* codes) {
-    for (int64_t i = 0; i < n; ++i) codes[i] = (int16_t)f32_to_f16_bits_rn(std::ldexp(x[i], shift));
+    const float up = std::ldexp(1.0f, shift);      // a power of two: the product is exact (|shift| <= 100)
+    for (int64_t i = 0; i < n; ++i) codes[i] = (int16_t)f32_to_f16_bits_rn(x[i] * up);
 }
 extern "C" void cledb_codec_decode(const int16_t* codes, int64_t n, int shift, float* x) {
-    for (int64_t i = 0; i < n; ++i) x[i] = std::ldexp(f16_bits_to_f32((uint16_t)codes[i]), -shift);
+    const float down = std::ldexp(1.0f, -shift);
+    for (int64_t i = 0; i < n; ++i) x[i] = f16_bits_to_f32((uint16_t)codes[i]) * down;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -197,12 +199,14 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
             h.slot.scale[c] = std::ldexp(1.0f, -s);
         }
     }
+    float up2[8];                                  // 2^shift per component: scaling by a power of two is exact
+    for (int c = 0; c < 8; ++c) up2[c] = std::ldexp(1.0f, h.shift[c]);
     // ---- sign classes of the DECODED V1 (the decoded array is the database: a V1 that underflows the int16
     //      code is a zero, exactly as the oracle sees it), CLEDB_PROC.py:974
     for (int64_t i = 0; i < n; ++i) {
         if (cls[i] < 0) continue;
         float v = db[i * 8 + 3];
-        if (encoding == CLEDB_ENC_I16) v = f16_bits_to_f32(f32_to_f16_bits_rn(std::ldexp(v, h.shift[3])));
+        if (encoding == CLEDB_ENC_I16) v = f16_bits_to_f32(f32_to_f16_bits_rn(v * up2[3]));
         const int c = v > 0.f ? 0 : (v < 0.f ? 1 : 2);
         cls[i] = (int8_t)c;
         ++cnt[c];
@@ -277,7 +281,7 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
             const int oc = chi_comp(c);
             const size_t e = ((size_t)tl * kNC + c) * kTile + in;
             if (encoding == CLEDB_ENC_I16) {
-                const uint16_t code = f32_to_f16_bits_rn(std::ldexp(rr[oc], h.shift[oc]));
+                const uint16_t code = f32_to_f16_bits_rn(rr[oc] * up2[oc]);
                 reinterpret_cast<uint16_t*>(tiles.data())[e] = code;
                 if ((code & 0x7fffu) == 0) zero_bits[q] |= 1 << c;
             } else {
@@ -288,7 +292,7 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
         for (int w = 0; w < 2; ++w) {
             const int oc = w ? 7 : 3;
             if (encoding == CLEDB_ENC_I16)
-                reinterpret_cast<uint16_t*>(vcomp.data())[pos * 2 + w] = f32_to_f16_bits_rn(std::ldexp(rr[oc], h.shift[oc]));
+                reinterpret_cast<uint16_t*>(vcomp.data())[pos * 2 + w] = f32_to_f16_bits_rn(rr[oc] * up2[oc]);
             else
                 reinterpret_cast<float*>(vcomp.data())[pos * 2 + w] = rr[oc];
         }

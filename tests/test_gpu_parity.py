@@ -552,3 +552,33 @@ def test_error_paths_of_the_fused_calls(ctx):
     inv, sf, st = ctx.invert(native.MODE_IQUV, *args, None, hdr, 1000, 0)
     assert (st == native.PIX_SEARCHED).sum() > 8 and (inv[st == native.PIX_SEARCHED][:, 0, 0] >= 0).all()
     ctx.db_drop(0)
+
+
+@pytest.mark.parametrize('encoding', [native.ENC_F32, native.ENC_I16])
+@pytest.mark.parametrize('mode', [native.MODE_IQUV, native.MODE_IQUD])
+def test_large_items_and_odd_tile_counts(ctx, encoding, mode):
+    """Items of 40 pixels (two mask segments in the hot loop), sign classes with odd and even tile counts (the two-tile step
+    with a missing second tile) and a last tile that is only partly filled: same bits as with tiny items, and the oracle's
+    answer on a sample."""
+    for shape in ((5, 60, 30), (3, 37, 23)):                     # 9 000 and 2 553 entries: 18 / 5 tiles per sign class
+        db = synth.make_database(12, 44, ngx=shape[0], nbphi=shape[1], nbtheta=shape[2])
+        obs = synth.make_observation(25, 20, [db], seed=31, frac_nan=0.02, frac_zero=0.02)
+        sobs, snr = obs['sobs_totrot'].reshape(-1, 8), obs['snr'].reshape(-1, 8)
+        ids = np.zeros(sobs.shape[0], np.int32)
+        ctx.db_put(0, db, encoding)
+        dec = codec.decoded_database(db, encoding)
+        ctx.set_tuning(40, 1)
+        big = ctx.match(mode, sobs, snr, ids, 8)
+        ctx.set_tuning(5, 1)
+        small = ctx.match(mode, sobs, snr, ids, 8)
+        ctx.set_tuning(40, 2)
+        chunked = ctx.match(mode, sobs, snr, ids, 8)
+        ctx.set_tuning(0, 0)
+        for key in ('idx', 'chi', 'kpos', 'status', 'rows'):
+            assert np.array_equal(big[key], small[key], equal_nan=True), key
+            assert np.array_equal(big[key], chunked[key], equal_nan=True), key
+        pick = np.random.default_rng(3).choice(sobs.shape[0], 60, replace=False)
+        sub = {k: (v[pick] if v is not None else None) for k, v in big.items()}
+        searched, reordered = check_raw_against_oracle(sub, mode, sobs[pick], snr[pick], [dec], ids[pick], 8)
+        assert searched >= 45 and reordered <= 6
+        ctx.db_drop(0)
