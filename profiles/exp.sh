@@ -1,1 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -25
+python profiles/t_e2e.py
+CLEDB_B200_NO_CHUNK=1 python profiles/t_e2e.py

@@ -58,6 +58,7 @@ extern "C" int cledb_destroy(cledb_ctx* ctx) {
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     if (ctx->io.ptr) cudaFree(ctx->io.ptr);
     for (auto& pr : ctx->prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return CLEDB_OK;

@@ -74,6 +74,7 @@ struct Workspace {
 struct cledb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;            // device-to-host copies of finished chunks (big maps)
     cudaDeviceProp prop;
     std::string err;
     std::map<int, int> slot_of_id;                 // db_id -> slot
@@ -88,7 +89,8 @@ struct cledb_ctx {
     cledb::Workspace red;                          // small tables of the reduced search
     cledb::Workspace raw;                          // raw search outputs of the fused search + solution call
     cledb::Workspace io;                           // staging for the host entry points
-    int32_t* h_cnt = nullptr;                      // pinned host copy of the bucket sizes
+    int32_t* h_cnt = nullptr;                      // mapped pinned host copy of the bucket sizes
+    int32_t* d_cnt_mapped = nullptr;               // its device alias
     size_t h_cnt_cap = 0;
     int last_P = 0, last_split = 0;                // work shape of the last search
     int64_t launches = 0;

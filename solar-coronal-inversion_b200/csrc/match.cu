@@ -1001,6 +1001,13 @@ static void choose_shape(cledb_ctx* ctx, const int32_t* cnt, int nkeys, int mode
     *split_out = bs;
 }
 
+// bucket counts and the three counters into mapped host memory
+__global__ void k_export_counts(const int32_t* __restrict__ cnt, int nkeys, const int32_t* __restrict__ counters, int32_t* __restrict__ host) {
+    for (int i = threadIdx.x; i < nkeys; i += blockDim.x) host[i] = cnt[i];
+    if (threadIdx.x < 3) host[nkeys + threadIdx.x] = counters[threadIdx.x];
+    __threadfence_system();
+}
+
 template <int PREC>
 static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax, const float* sobs, const float* snr,
                      const int32_t* db_id, int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out,
@@ -1010,14 +1017,18 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     k_classify<PREC><<<nb, 256, 0, st>>>(pl, sobs, snr, db_id, ctx->d_slots, ctx->d_slot_of_id, ctx->id_cap);
     ctx->launches += 1;
     // ---- the bucket sizes come back to the host (a few hundred bytes, one stream synchronisation) and fix the work shape
+    // The counts travel through mapped pinned memory written by a tiny kernel, not through a copy-engine transfer: a
+    // device-to-host copy would queue behind the result maps of the previous chunk of a big map (cledb_invert) and stall
+    // this search until they have arrived.
     if ((int)ctx->h_cnt_cap < pl.nkeys + 4) {
         if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
         ctx->h_cnt = nullptr;
-        CLEDB_CUDA(ctx, cudaMallocHost(&ctx->h_cnt, sizeof(int32_t) * (pl.nkeys + 4)));
+        CLEDB_CUDA(ctx, cudaHostAlloc(&ctx->h_cnt, sizeof(int32_t) * (pl.nkeys + 4), cudaHostAllocMapped));
+        CLEDB_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_cnt_mapped, ctx->h_cnt, 0));
         ctx->h_cnt_cap = pl.nkeys + 4;
     }
-    CLEDB_CUDA(ctx, cudaMemcpyAsync(ctx->h_cnt, pl.cnt, sizeof(int32_t) * pl.nkeys, cudaMemcpyDeviceToHost, st));
-    CLEDB_CUDA(ctx, cudaMemcpyAsync(ctx->h_cnt + pl.nkeys, pl.counters, sizeof(int32_t) * 3, cudaMemcpyDeviceToHost, st));
+    k_export_counts<<<1, 256, 0, st>>>(pl.cnt, pl.nkeys, pl.counters, ctx->d_cnt_mapped);
+    ctx->launches += 1;
     CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
     if (ctx->h_cnt[pl.nkeys + 1] != 0) {                   // k_classify met a searched pixel whose database id was never put
         ctx->err = "cledb_match: a pixel refers to a database id that is not resident (cledb_db_put it first)";
