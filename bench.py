@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dbg', type=int, default=0, help='kernel timing experiment (results invalid)')
+    ap.add_argument('--prune', action='store_true', help='optional exact tile pruning (not the brute-force search of the headline)')
     ap.add_argument('--ppi', type=int, default=0, help='tuning: pixels per warp item (0 = library default)')
     ap.add_argument('--split', type=int, default=0, help='tuning: chunks per candidate list (0 = library default)')
     return ap.parse_args()
@@ -193,6 +194,8 @@ def main():
 
     db, obs = make_inputs(args, rank)
     ctx = native.Context(local)
+    if args.prune:
+        ctx.set_pruning(True)
     for i, d in enumerate(db):
         ctx.db_put(i, d, args.encoding)
     props = ctx.device_props()
@@ -326,6 +329,7 @@ def main():
                     parallelism='pixel-sharded x%d, database replicated, NCCL all_gather of idx/chi maps' % world if world > 1 else 'single GPU',
                     l2='flushed between timed steps (256 MiB memset, outside the per-step CUDA events)',
                     timing='CUDA events per step on the launching stream, mean of K, max over ranks'),
+        pruning=ctx.pruning_stats() if args.prune else None,
         evals_per_s=world * npix * 340200 / (ms * 1e-3),
         candidate_evals_per_s=ncand_all / (ms * 1e-3),
         pixels_searched=nsearched_all,

@@ -42,6 +42,12 @@ typedef struct cledb_ctx cledb_ctx;
 #define CLEDB_ENC_F32 0         /* database kept as float32 in HBM (lossless)                             */
 #define CLEDB_ENC_I16 1         /* database kept as int16 codes in HBM (see cledb_codec_*)                */
 
+/* Optional: exact tile pruning.  A database put while pruning is on (cledb_set_pruning) keeps its candidate rows in their
+ * original (gx, phi, theta) order inside each sign class, so that a 256-entry tile is a compact patch of parameter space,
+ * and stores the component bounds of every tile; the search then skips, per pixel, every tile whose chi^2 lower bound
+ * already exceeds the pixel's running threshold.  The lower bound is exact in floating point (fma and the accumulation
+ * chain are monotone), so results are bit-identical to the plain search; only the amount of arithmetic changes.
+ * Off by default: the plain search is the brute-force evaluation of every (pixel, entry) pair. */
 #define CLEDB_PREC_FP32 0       /* production kernel: fp32 FMA residuals                                  */
 #define CLEDB_PREC_FP64 1       /* validation kernel: the reference's operation order in f32/f64          */
 
@@ -129,6 +135,11 @@ int cledb_match_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
 /* tuning knobs: pixels per warp work item (1..40) and how many chunks each candidate list is cut into (1..8);
  * 0 = choose from the pixel count (default).  Results do not depend on them. */
 int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split);
+/* exact tile pruning on (1) / off (0) for databases put from now on; every resident database must have been put with
+ * the same setting when a search runs */
+int cledb_set_pruning(cledb_ctx* ctx, int on);
+/* after a pruned search: evaluated[0] = (pixel, tile) pairs evaluated, evaluated[1] = pairs skipped by the bound */
+int cledb_pruning_stats(cledb_ctx* ctx, int64_t evaluated[2]);
 
 /* ---- search + solution building in one call --------------------------------------------------------- *
  * Replaces everything cledb_invproc does per pixel (CLEDB_PROC.py:304-319 with the bodies of cledb_matchiquv /

@@ -1,2 +1,13 @@
-python profiles/t_e2e.py
-CLEDB_B200_NO_CHUNK=1 python profiles/t_e2e.py
+python -m pytest tests -m gpu -x -q -k "pruning" 2>&1 | tail -15
+mkdir -p gpurun_out/exp
+run() { python bench.py --steps 5 --warmup 3 --no-cpu-baseline "${@:2}" > gpurun_out/exp/$1.json 2>gpurun_out/exp/$1.err
+  python -c "
+import json
+try:
+    j=json.loads(open('gpurun_out/exp/$1.json').read().strip().splitlines()[-1])
+    print('%-22s value %.4e e2e %.4e kernel_ms %.3f frac %.3f'%('$1', j['value'], j['e2e']['value'], j['roofline']['kernel_ms'], j['roofline']['frac']), j.get('pruning'))
+except Exception as e: print('$1 failed', e); print(open('gpurun_out/exp/$1.err').read()[-800:])"
+}
+run plain
+run pruned --prune
+run pruned_iqud --prune --mode iqud

@@ -50,6 +50,8 @@ SIGNATURES = {
     'cledb_match': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_match_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_set_tuning': (_c.c_int, [_P, _c.c_int, _c.c_int]),
+    'cledb_set_pruning': (_c.c_int, [_P, _c.c_int]),
+    'cledb_pruning_stats': (_c.c_int, [_P, _P]),
     'cledb_invert': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
                                 _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P]),
     'cledb_match_reduced': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -265,6 +267,15 @@ class Context:
 
     def set_tuning(self, pixels_per_item=32, split=0):
         self._check(self.lib.cledb_set_tuning(self.h, int(pixels_per_item), int(split)))
+
+    def set_pruning(self, on):
+        """Exact tile pruning for databases put from now on (see the header); results do not change."""
+        self._check(self.lib.cledb_set_pruning(self.h, 1 if on else 0))
+
+    def pruning_stats(self):
+        v = np.zeros(2, dtype=np.int64)
+        self._check(self.lib.cledb_pruning_stats(self.h, _ptr(v)))
+        return dict(evaluated=int(v[0]), skipped=int(v[1]))
 
     # ---- databases
     def db_put(self, db_id, db, encoding=ENC_I16):

@@ -55,6 +55,7 @@ extern "C" int cledb_destroy(cledb_ctx* ctx) {
     if (ctx->ws2.ptr) cudaFree(ctx->ws2.ptr);
     if (ctx->raw.ptr) cudaFree(ctx->raw.ptr);
     if (ctx->red.ptr) cudaFree(ctx->red.ptr);
+    if (ctx->d_prune_stats) cudaFree(ctx->d_prune_stats);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     if (ctx->io.ptr) cudaFree(ctx->io.ptr);
     for (auto& pr : ctx->prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -134,6 +135,25 @@ extern "C" int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split) 
     if (pixels_per_item > kMaxP || split < 0 || split > 8) { ctx->err = "cledb_set_tuning: out of range"; return CLEDB_ERR_ARG; }
     ctx->pixels_per_item = pixels_per_item;
     ctx->split = split;
+    return CLEDB_OK;
+}
+
+extern "C" int cledb_set_pruning(cledb_ctx* ctx, int on) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    ctx->prune = on ? 1 : 0;
+    return CLEDB_OK;
+}
+
+extern "C" int cledb_pruning_stats(cledb_ctx* ctx, int64_t evaluated[2]) {
+    if (!ctx || !evaluated) return CLEDB_ERR_ARG;
+    evaluated[0] = evaluated[1] = 0;
+    if (!ctx->d_prune_stats) return CLEDB_OK;
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CLEDB_CUDA(ctx, cudaDeviceSynchronize());
+    unsigned long long h[2] = {0, 0};
+    CLEDB_CUDA(ctx, cudaMemcpy(h, ctx->d_prune_stats, 16, cudaMemcpyDeviceToHost));
+    evaluated[0] = (int64_t)h[0];
+    evaluated[1] = (int64_t)h[1];
     return CLEDB_OK;
 }
 

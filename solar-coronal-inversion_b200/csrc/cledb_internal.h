@@ -36,6 +36,9 @@ struct DbSlot {
     int32_t        part_zero[kParts];    // bit c set: some entry of the class has decoded chi-component c == 0
     int32_t        encoding;
     int32_t        live;
+    int32_t        blocked;          // 1: tiles are compact patches in original order and `boxes` holds their bounds
+    int32_t        pad_;
+    const float*   boxes;            // [ntiles_total][16]: lo[5], hi[5] of the stored (code) values of a tile, one representative entry[5], pad
     float          scale[8];         // 2^-shift per original component (1 for F32)
 };
 
@@ -59,7 +62,8 @@ struct HostDb {
     int32_t* d_invperm = nullptr;
     int32_t* d_kept_rank = nullptr;
     int32_t* d_row_kpos = nullptr;
-    float*   d_rows8 = nullptr;          // decoded [n,8] copy, built on first use of the reduced mode
+    float*   d_rows8 = nullptr;
+    float*   d_boxes = nullptr;          // decoded [n,8] copy, built on first use of the reduced mode
     int64_t  npad = 0, nnan = 0, bytes = 0;
     int      shift[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -97,6 +101,8 @@ struct cledb_ctx {
     int pixels_per_item = 0;                      // 0 = choose from the pixel count
     int split = 0;
     int dbg = 0;
+    int prune = 0;                                 // layout of databases put from now on
+    unsigned long long* d_prune_stats = nullptr;   // [2] evaluated / skipped (pixel, tile) pairs of the last pruned search
     int occ = 0, regs = 0, smem = 0;               // search kernel occupancy facts
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;   // event pairs around the search kernel
     int prof_used = 0;

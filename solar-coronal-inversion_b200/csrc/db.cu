@@ -3,6 +3,7 @@
 // (CLEDB_PROC.py:974-976) of the reference: both are done once per database here.
 #include <math_constants.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -137,6 +138,7 @@ static void free_db(HostDb& h) {
     if (h.d_kept_rank) cudaFree(h.d_kept_rank);
     if (h.d_row_kpos) cudaFree(h.d_row_kpos);
     if (h.d_rows8) cudaFree(h.d_rows8);
+    if (h.d_boxes) cudaFree(h.d_boxes);
     h = HostDb();
     std::memset(&h.slot, 0, sizeof(DbSlot));
 }
@@ -262,6 +264,54 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
         }
         stride[q] = st;
     }
+    const bool blocked = ctx->prune != 0;
+    // Pruning layout: the tiles of a sign class are the leaves of a k-d partition of its entries in the space of the five
+    // chi^2 components (median splits at multiples of the tile size, along the component with the widest weighted extent),
+    // so a tile is a small box in that space and the exact bound of k_match_pruned rejects most tiles of a pixel.
+    std::vector<int32_t> kdpos;
+    if (blocked) {
+        kdpos.assign(n, -1);
+        const float wdim[kNC] = {1.f, 1.f, 0.1f, 1.f, 1.f};               // sqrt(wtg_fact) of the components, CLEDB_PROC.py:981
+        std::vector<int32_t> ids;
+        for (int q = 0; q < kParts; ++q) {
+            ids.clear();
+            ids.reserve(cnt[q]);
+            for (int64_t i = 0; i < n; ++i) if (cls[i] == q) ids.push_back((int32_t)i);
+            std::vector<std::pair<int64_t, int64_t>> todo{{0, (int64_t)ids.size()}};
+            while (!todo.empty()) {
+                const auto [lo, hi] = todo.back();
+                todo.pop_back();
+                const int64_t nt = (hi - lo + kTile - 1) / kTile;
+                if (nt <= 1) continue;
+                int dim = 0;
+                float widest = -1.f;
+                for (int c = 0; c < kNC; ++c) {
+                    const int oc = chi_comp(c);
+                    float mn = INFINITY, mx = -INFINITY;
+                    for (int64_t j = lo; j < hi; ++j) { const float v = db[(int64_t)ids[j] * 8 + oc]; mn = std::min(mn, v); mx = std::max(mx, v); }
+                    const float ext = (mx - mn) * wdim[c];
+                    if (ext > widest) { widest = ext; dim = c; }
+                }
+                const int oc = chi_comp(dim);
+                const int64_t mid = lo + (nt / 2) * kTile;
+                std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int32_t x, int32_t y) {
+                    float vx = db[(int64_t)x * 8 + oc], vy = db[(int64_t)y * 8 + oc];
+                    if (std::isnan(vx)) vx = INFINITY;                     // keep the order strict and weak
+                    if (std::isnan(vy)) vy = INFINITY;
+                    return vx < vy || (vx == vy && x < y);
+                });
+                todo.push_back({lo, mid});
+                todo.push_back({mid, hi});
+            }
+            for (size_t j = 0; j < ids.size(); ++j) kdpos[ids[j]] = (int32_t)j;
+        }
+    }
+    std::vector<float> boxes;
+    if (blocked) {
+        boxes.assign((size_t)std::max<int64_t>(1, ntiles) * 16, 0.f);
+        for (int64_t t = 0; t < ntiles; ++t)
+            for (int c = 0; c < kNC; ++c) { boxes[t * 16 + c] = INFINITY; boxes[t * 16 + 5 + c] = -INFINITY; boxes[t * 16 + 10 + c] = NAN; }
+    }
     int64_t seen[kParts] = {0, 0, 0};
     int32_t zero_bits[kParts] = {0, 0, 0};
     int64_t rank = 0;
@@ -272,7 +322,9 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
         ++rank;
         const int64_t r = seen[q]++;                                  // rank inside the class, original order
         row_kpos[i] = (int32_t)r;
-        const int64_t pos = pos0[q] + (int64_t)(((__int128)r * stride[q]) % cnt[q]);
+        int64_t pos;
+        if (!blocked) pos = pos0[q] + (int64_t)(((__int128)r * stride[q]) % cnt[q]);
+        else pos = pos0[q] + kdpos[i];
         perm[pos] = (int32_t)i;
         invperm[i] = (int32_t)pos;
         const int64_t tl = pos / kTile, in = pos % kTile;
@@ -280,13 +332,21 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
         for (int c = 0; c < kNC; ++c) {
             const int oc = chi_comp(c);
             const size_t e = ((size_t)tl * kNC + c) * kTile + in;
+            float stored;                         // the value the kernel multiplies: the half code as a float, or the float
             if (encoding == CLEDB_ENC_I16) {
                 const uint16_t code = f32_to_f16_bits_rn(rr[oc] * up2[oc]);
                 reinterpret_cast<uint16_t*>(tiles.data())[e] = code;
                 if ((code & 0x7fffu) == 0) zero_bits[q] |= 1 << c;
+                stored = f16_bits_to_f32(code);
             } else {
                 reinterpret_cast<float*>(tiles.data())[e] = rr[oc];
                 if (rr[oc] == 0.f) zero_bits[q] |= 1 << c;
+                stored = rr[oc];
+            }
+            if (blocked) {
+                boxes[tl * 16 + c] = std::min(boxes[tl * 16 + c], stored);
+                boxes[tl * 16 + 5 + c] = std::max(boxes[tl * 16 + 5 + c], stored);
+                if (in == 0) boxes[tl * 16 + 10 + c] = stored;          // representative entry, replaced below
             }
         }
         for (int w = 0; w < 2; ++w) {
@@ -298,6 +358,35 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
         }
     }
     for (int q = 0; q < kParts; ++q) h.slot.part_zero[q] = zero_bits[q];
+    if (blocked) {
+        // representative entry of a tile: the stored entry nearest to the middle of its box
+        const float wdim[kNC] = {1.f, 1.f, 0.1f, 1.f, 1.f};
+        for (int64_t t = 0; t < ntiles; ++t) {
+            float* bx = &boxes[t * 16];
+            int best = -1;
+            float bestd = INFINITY;
+            for (int in = 0; in < kTile; ++in) {
+                const int32_t row = perm[t * kTile + in];
+                if (row < 0) continue;
+                float dist = 0.f;
+                for (int c = 0; c < kNC; ++c) {
+                    const int oc = chi_comp(c);
+                    const size_t e = ((size_t)t * kNC + c) * kTile + in;
+                    const float v = encoding == CLEDB_ENC_I16 ? f16_bits_to_f32(reinterpret_cast<const uint16_t*>(tiles.data())[e])
+                                                              : reinterpret_cast<const float*>(tiles.data())[e];
+                    const float dd = (v - 0.5f * (bx[c] + bx[5 + c])) * h.slot.scale[oc] * wdim[c];
+                    dist += dd * dd;
+                }
+                if (dist < bestd) { bestd = dist; best = in; }          // NaN distances never win
+            }
+            if (best < 0) continue;
+            for (int c = 0; c < kNC; ++c) {
+                const size_t e = ((size_t)t * kNC + c) * kTile + best;
+                bx[10 + c] = encoding == CLEDB_ENC_I16 ? f16_bits_to_f32(reinterpret_cast<const uint16_t*>(tiles.data())[e])
+                                                       : reinterpret_cast<const float*>(tiles.data())[e];
+            }
+        }
+    }
 
     // ---- upload
     auto fail = [&](const char* what) {
@@ -312,6 +401,10 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
     if (cudaMalloc(&h.d_invperm, invperm.size() * 4) != cudaSuccess) return fail("out of device memory (invperm)");
     if (nnan > 0 && cudaMalloc(&h.d_kept_rank, kept_rank.size() * 4) != cudaSuccess) return fail("out of device memory (rank)");
     if (cudaMalloc(&h.d_row_kpos, row_kpos.size() * 4) != cudaSuccess) return fail("out of device memory (kpos)");
+    if (blocked) {
+        if (cudaMalloc(&h.d_boxes, boxes.size() * 4) != cudaSuccess) return fail("out of device memory (tile bounds)");
+        CLEDB_CUDA(ctx, cudaMemcpy(h.d_boxes, boxes.data(), boxes.size() * 4, cudaMemcpyHostToDevice));
+    }
     CLEDB_CUDA(ctx, cudaMemcpy(h.d_tiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
     CLEDB_CUDA(ctx, cudaMemcpy(h.d_vcomp, vcomp.data(), vcomp.size(), cudaMemcpyHostToDevice));
     CLEDB_CUDA(ctx, cudaMemcpy(h.d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
@@ -328,6 +421,8 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
     h.slot.n = n;
     h.slot.encoding = encoding;
     h.slot.live = 1;
+    h.slot.blocked = blocked ? 1 : 0;
+    h.slot.boxes = h.d_boxes;
 
     int slot;
     if (!ctx->free_slots.empty()) { slot = ctx->free_slots.back(); ctx->free_slots.pop_back(); ctx->dbs[slot] = h; }

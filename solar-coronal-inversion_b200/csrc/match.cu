@@ -806,6 +806,226 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// kernel 4b: the search with exact tile pruning (optional, databases put while cledb_set_pruning is on)
+// ------------------------------------------------------------------------------------------------------
+// Same items, same lists, same exact per-(pixel, tile) evaluation as k_match, but a (pixel, tile) pair is evaluated only if
+// the tile's chi^2 lower bound does not exceed the pixel's threshold.  Lane L owns pixel L (and L+32) of the item for the
+// bound: with the tile's component bounds lo_c <= d_c <= hi_c, r_c(d) = fma(d, a_c, nb_c) is monotone in d, so
+// |r_c| >= m_c = distance of the interval [r_c(lo), r_c(hi)] from 0, and the accumulation chain acc = fma(r, r, acc) is
+// monotone in |r| and acc: the bound computed with the same chain is <= the computed chi^2 of every entry of the tile,
+// exactly, in floating point.  Tiles nobody needs are not even loaded.
+template <int ENC>
+__global__ void __launch_bounds__(KCfg<ENC, CLEDB_PREC_FP32>::kWpc * 32, 1)
+k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __restrict__ stats) {
+    constexpr int PREC = CLEDB_PREC_FP32;
+    using C = KCfg<ENC, PREC>;
+    using V = float;
+    using CandT = Cand<PREC>;
+    using RecT = Rec<PREC>;
+    constexpr int TB = C::kTB, SB = C::kStageBytes;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* stages = smem + (size_t)warp * C::kWarpBytes;
+    RecT* recs = reinterpret_cast<RecT*>(stages + kStages * SB);
+    CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);
+    float* c0s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + (kStages * 8 + 15) / 16 * 16);
+    const int k = pl.k;
+    uint32_t phase = 0;
+    unsigned long long n_eval = 0, n_skip = 0;
+
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&pl.counters[0], 1);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= pl.counters[2]) break;
+        const Item im = make_item(pl, slots, it);
+        const DbSlot& db = slots[im.slot];
+        const unsigned char* gt = reinterpret_cast<const unsigned char*>(db.tiles) + (size_t)im.tile0 * TB;
+        const float4* boxes = reinterpret_cast<const float4*>(db.boxes) + (size_t)im.tile0 * 4;
+        CandT* gout = reinterpret_cast<CandT*>(pl.plist) + (size_t)it * pl.P * k;
+        const int nsteps = (im.ntiles + 1) / 2;
+
+        for (int i = lane; i < im.npx * (int)(sizeof(RecT) / 16); i += 32) {
+            const int j = i / (int)(sizeof(RecT) / 16), w = i % (int)(sizeof(RecT) / 16);
+            const int p = pl.order[im.pix0 + j];
+            reinterpret_cast<uint4*>(recs + j)[w] = reinterpret_cast<const uint4*>(reinterpret_cast<const RecT*>(pl.recs) + p)[w];
+        }
+        for (int i = lane; i < im.npx * k; i += 32) {
+            lists[i].v = CUDART_INF_F;
+            lists[i].pos = -1;
+        }
+        __syncwarp();
+        for (int j = lane; j < im.npx; j += 32) {
+            c0s[j] = recs[j].cm;
+            recs[j].cm = -CUDART_INF_F;
+        }
+        __syncwarp();
+        float scale[kNC];
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) scale[c] = db.scale[chi_comp(c)];
+
+        // chi^2 lower bound of tile t for the lane's pixel of segment seg (+inf for a lane without pixel)
+        auto tile_bound = [&](int t, int seg) -> float {
+            const int j = seg * 32 + lane;
+            if (j >= im.npx) return CUDART_INF_F;
+            const float4 b0 = __ldg(boxes + (size_t)t * 4), b1 = __ldg(boxes + (size_t)t * 4 + 1), b2 = __ldg(boxes + (size_t)t * 4 + 2);
+            const float lo[kNC] = {b0.x, b0.y, b0.z, b0.w, b1.x};
+            const float hi[kNC] = {b1.y, b1.z, b1.w, b2.x, b2.y};
+            const float4* rp = reinterpret_cast<const float4*>(recs + j);
+            const float4 x0 = rp[0], x1 = rp[1], x2 = rp[2];
+            const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
+            const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
+            float lb = c0s[j];
+#pragma unroll
+            for (int c = 0; c < kNC; ++c) {
+                const float rl = fmaf(lo[c], a[c], nb[c]), rh = fmaf(hi[c], a[c], nb[c]);
+                float mn = 0.f;                                    // NaN / mixed signs: no bound from this component
+                if (rl > 0.f && rh > 0.f) mn = fminf(rl, rh);
+                else if (rl < 0.f && rh < 0.f) mn = fminf(-rl, -rh);
+                lb = fmaf(mn, mn, lb);
+            }
+            return lb;
+        };
+
+        // ---- seed: every pixel first visits the two tiles whose representative entry (stored next to the bounds) fits it
+        //      best - a coarse search over one entry per tile - which gives it a threshold close to the final one before
+        //      the scan starts (a tile sequence that suits every pixel does not exist)
+        int seed[2] = {-1, -1}, seed2[2] = {-1, -1};
+        {
+            float best[2] = {CUDART_INF_F, CUDART_INF_F}, second[2] = {CUDART_INF_F, CUDART_INF_F};
+            const int nseg = im.npx > 32 ? 2 : 1;
+            for (int t = 0; t < im.ntiles; ++t) {
+                const float4 b2 = __ldg(boxes + (size_t)t * 4 + 2), b3 = __ldg(boxes + (size_t)t * 4 + 3);
+                const float rep[kNC] = {b2.z, b2.w, b3.x, b3.y, b3.z};
+                for (int seg = 0; seg < nseg; ++seg) {
+                    const int j = seg * 32 + lane;
+                    if (j >= im.npx) continue;
+                    const float4* rp = reinterpret_cast<const float4*>(recs + j);
+                    const float4 x0 = rp[0], x1 = rp[1], x2 = rp[2];
+                    const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
+                    const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
+                    const float v = eval_fp32(rep, a, nb, c0s[j]);
+                    if (v < best[seg]) { second[seg] = best[seg]; seed2[seg] = seed[seg]; best[seg] = v; seed[seg] = t; }
+                    else if (v < second[seg]) { second[seg] = v; seed2[seg] = t; }
+                }
+            }
+            for (int seg = 0; seg < 2; ++seg) if (seed[seg] < 0) seed[seg] = 0;       // every chi^2 NaN: any tile will do
+        }
+        float d[kEPL][kNC], d2[kEPL][kNC];
+        for (int j = 0; j < im.npx; ++j) {
+            const int t = __shfl_sync(0xffffffffu, j < 32 ? seed[0] : seed[1], j & 31);
+            const int u = __shfl_sync(0xffffffffu, j < 32 ? seed2[0] : seed2[1], j & 31);
+            if (lane == 0) {
+                mbar_expect_tx(&bars[0], u >= 0 ? 2 * TB : TB);
+                tma_load_1d(stages, gt + (size_t)t * TB, TB, &bars[0]);
+                if (u >= 0) tma_load_1d(stages + TB, gt + (size_t)u * TB, TB, &bars[0]);
+            }
+            mbar_wait(&bars[0], phase);
+            phase ^= 1u;
+            load_tile_regs<ENC>(stages, lane, d);
+            if (u >= 0) load_tile_regs<ENC>(stages + TB, lane, d2);
+            __syncwarp();
+            const int base = (im.tile0 + t) * kTile;
+            int rows[kEPL];
+#pragma unroll
+            for (int e = 0; e < kEPL; ++e) {
+                const int pos = base + pos_in_tile<ENC>(lane, e);
+                rows[e] = pos < im.cnt_end ? db.perm[pos] : 0x7fffffff;
+            }
+            bootstrap_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, rows, k, lane);
+            if (u >= 0) slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d2, scale, (im.tile0 + u) * kTile, im.cnt_end, db.perm, k, lane);
+        }
+        n_eval += 2 * im.npx;
+
+        // survivors of one step: bit L of m[seg][tile] = pixel seg*32+L must evaluate that tile
+        auto survivors = [&](int step, uint32_t (&m)[2][2]) {
+            const int t = step * 2, nt = min(2, im.ntiles - t);
+#pragma unroll
+            for (int seg = 0; seg < 2; ++seg) {
+                const int j = seg * 32 + lane;
+                bool need[2] = {false, false};
+                if (j < im.npx && (seg == 0 || im.npx > 32)) {
+                    const float tau = recs[j].tau;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        need[q] = q < nt && t + q != seed[seg] && t + q != seed2[seg] && !(tile_bound(t + q, seg) > tau);   // NaN keeps the tile
+                }
+                m[seg][0] = __ballot_sync(0xffffffffu, need[0]);
+                m[seg][1] = __ballot_sync(0xffffffffu, need[1]);
+            }
+        };
+
+        uint32_t cur[2][2] = {{0, 0}, {0, 0}}, nxt[2][2] = {{0, 0}, {0, 0}};
+        bool loaded = false;
+        if (nsteps > 0) {
+            survivors(0, cur);
+            loaded = (cur[0][0] | cur[0][1] | cur[1][0] | cur[1][1]) != 0;
+            if (lane == 0 && loaded) {
+                const uint32_t bytes = (uint32_t)min(2, im.ntiles) * TB;
+                mbar_expect_tx(&bars[0], bytes);
+                tma_load_1d(stages, gt, bytes, &bars[0]);
+            }
+        }
+        for (int step = 0; step < nsteps; ++step) {
+            const int t = step * 2, nt = min(2, im.ntiles - t);
+            const int base = (im.tile0 + t) * kTile;
+            const bool any_a = (cur[0][0] | cur[1][0]) != 0, any_b = nt == 2 && (cur[0][1] | cur[1][1]) != 0;
+            if (loaded) {
+                mbar_wait(&bars[0], phase);
+                phase ^= 1u;
+                if (any_a) load_tile_regs<ENC>(stages, lane, d);
+                if (any_b) load_tile_regs<ENC>(stages + TB, lane, d2);
+                __syncwarp();
+            }
+            // bounds of the next step against the thresholds as they are now (they only tighten: a superset), then its load
+            bool load_next = false;
+            if (step + 1 < nsteps) {
+                survivors(step + 1, nxt);
+                load_next = (nxt[0][0] | nxt[0][1] | nxt[1][0] | nxt[1][1]) != 0;
+                if (lane == 0 && load_next) {
+                    const uint32_t bytes = (uint32_t)min(2, im.ntiles - (t + 2)) * TB;
+                    mbar_expect_tx(&bars[0], bytes);
+                    tma_load_1d(stages, gt + (size_t)(step + 1) * SB, bytes, &bars[0]);
+                }
+            }
+#pragma unroll
+            for (int seg = 0; seg < 2; ++seg) {
+                uint32_t ma = cur[seg][0], mb = cur[seg][1];
+                n_eval += __popc(ma) + __popc(mb);
+                while (ma) {
+                    const int j = seg * 32 + __ffs(ma) - 1;
+                    ma &= ma - 1;
+                    slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
+                }
+                while (mb) {
+                    const int j = seg * 32 + __ffs(mb) - 1;
+                    mb &= mb - 1;
+                    slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d2, scale, base + kTile, im.cnt_end, db.perm, k, lane);
+                }
+            }
+            cur[0][0] = nxt[0][0]; cur[0][1] = nxt[0][1]; cur[1][0] = nxt[1][0]; cur[1][1] = nxt[1][1];
+            loaded = load_next;
+        }
+        n_skip += (unsigned long long)im.npx * im.ntiles;
+        __syncwarp();
+        for (int i = lane; i < im.npx * k; i += 32) gout[i] = lists[i];
+        __syncwarp();
+    }
+    if (lane == 0 && stats) {
+        atomicAdd(&stats[0], n_eval);
+        atomicAdd(&stats[1], n_skip - n_eval);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // kernel 5: merge the partial lists of a pixel, map positions to original rows, decode winner rows
 // ------------------------------------------------------------------------------------------------------
 template <int ENC> __device__ __forceinline__ float decode_chi_comp(const DbSlot& db, int pos, int c) {
@@ -1055,9 +1275,27 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     if (rc) return rc;
     const int wpc = enc == CLEDB_ENC_I16 ? KCfg<CLEDB_ENC_I16, PREC>::kWpc : KCfg<CLEDB_ENC_F32, PREC>::kWpc;
     const int grid = (int)std::min<int64_t>((int64_t)ctx->prop.multiProcessorCount * occ, std::max<int64_t>(1, (max_items + wpc - 1) / wpc));
+    // exact tile pruning: only with the fp32 kernel, and only if every resident database was put in the pruning layout
+    int nblocked = 0, nlive = 0;
+    for (auto& h : ctx->dbs) {
+        if (!h.slot.live) continue;
+        ++nlive;
+        nblocked += h.slot.blocked ? 1 : 0;
+    }
+    if (nblocked != 0 && nblocked != nlive) { ctx->err = "cledb_match: resident databases mix the pruning and the plain layout"; return CLEDB_ERR_ARG; }
+    const bool pruned = PREC == CLEDB_PREC_FP32 && nblocked > 0;
+    if (pruned) {
+        if (!ctx->d_prune_stats) CLEDB_CUDA(ctx, cudaMalloc(&ctx->d_prune_stats, 16));
+        CLEDB_CUDA(ctx, cudaMemsetAsync(ctx->d_prune_stats, 0, 16, st));
+        if (enc == CLEDB_ENC_I16) CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_match_pruned<CLEDB_ENC_I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_match_pruned<CLEDB_ENC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const bool prof = ctx->prof_on && ctx->prof_used < (int)ctx->prof.size();
     if (prof) CLEDB_CUDA(ctx, cudaEventRecord(ctx->prof[ctx->prof_used].first, st));
-    if (enc == CLEDB_ENC_I16) k_match<CLEDB_ENC_I16, PREC><<<grid, KCfg<CLEDB_ENC_I16, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
+    if (pruned) {
+        if (enc == CLEDB_ENC_I16) k_match_pruned<CLEDB_ENC_I16><<<grid, KCfg<CLEDB_ENC_I16, CLEDB_PREC_FP32>::kWpc * 32, smem, st>>>(pl, ctx->d_slots, ctx->d_prune_stats);
+        else k_match_pruned<CLEDB_ENC_F32><<<grid, KCfg<CLEDB_ENC_F32, CLEDB_PREC_FP32>::kWpc * 32, smem, st>>>(pl, ctx->d_slots, ctx->d_prune_stats);
+    } else if (enc == CLEDB_ENC_I16) k_match<CLEDB_ENC_I16, PREC><<<grid, KCfg<CLEDB_ENC_I16, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
     else k_match<CLEDB_ENC_F32, PREC><<<grid, KCfg<CLEDB_ENC_F32, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
     if (prof) {
         CLEDB_CUDA(ctx, cudaEventRecord(ctx->prof[ctx->prof_used].second, st));

@@ -602,3 +602,30 @@ def test_big_map_is_pipelined_in_chunks(ctx):
         assert same(inv[lo:hi], i2) and same(sf[lo:hi], s2) and same(st[lo:hi], t2)
     assert (st == native.PIX_SEARCHED).mean() > 0.8
     ctx.db_drop(0)
+
+
+@pytest.mark.parametrize('encoding', [native.ENC_F32, native.ENC_I16])
+@pytest.mark.parametrize('mode', [native.MODE_IQUV, native.MODE_IQUD])
+def test_exact_tile_pruning_changes_nothing(ctx, golden_dir, encoding, mode):
+    """Optional exact tile pruning (cledb_set_pruning): the bound skips most (pixel, tile) pairs and every output bit stays
+    the same as in the plain brute-force search - small databases with engineered edge cases and a mid-size one."""
+    g, dbs = small_case(golden_dir)
+    cases = [(dbs, g['sobs_iquv_b0' if mode == 0 else 'sobs_iqud'].reshape(-1, 8), g['snr'].reshape(-1, 8), g['db_enc'].reshape(-1))]
+    mid = synth.make_database(12, 44, ngx=7, nbphi=90, nbtheta=45)
+    obs = synth.make_observation(30, 30, [mid], seed=17)
+    cases.append(([mid], obs['sobs_totrot'].reshape(-1, 8), obs['snr'].reshape(-1, 8), np.zeros(900, np.int32)))
+    for dbl, sobs, snr, enc in cases:
+        res = {}
+        for prune in (False, True):
+            ctx.set_pruning(prune)
+            for i, db in enumerate(dbl):
+                ctx.db_put(i, db, encoding)
+            res[prune] = ctx.match(mode, sobs, snr, enc, 8)
+            stats = ctx.pruning_stats()
+            for i in range(len(dbl)):
+                ctx.db_drop(i)
+        ctx.set_pruning(False)
+        for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
+            assert np.array_equal(res[False][key], res[True][key], equal_nan=True), key
+        assert stats['evaluated'] > 0
+    assert stats['skipped'] > 0
