@@ -17,6 +17,7 @@ constexpr int kNC       = 5;     // components that enter chi^2: Q1 U1 I2 Q2 U2 
 constexpr int kMaxP     = 40;    // pixels per work item
 constexpr int kWarps    = 8;     // compute warps per CTA
 constexpr int kThreads  = kWarps * 32;
+constexpr int kSuper    = 16;    // tiles per group of the two-level bounds (pruning layout)
 constexpr int kParts    = 3;     // sign(V1) classes: 0 = positive, 1 = negative, 2 = zero
 
 __host__ __device__ constexpr int chi_comp(int c) { return c == 0 ? 1 : c == 1 ? 2 : c == 2 ? 4 : c == 3 ? 5 : 6; }
@@ -39,6 +40,9 @@ struct DbSlot {
     int32_t        blocked;          // 1: tiles are compact patches in original order and `boxes` holds their bounds
     int32_t        pad_;
     const float*   boxes;            // [ntiles_total][16]: lo[5], hi[5] of the stored (code) values of a tile, one representative entry[5], pad
+    const float*   sboxes;           // [sum over classes of ceil(ntiles/16)][12]: lo[5], hi[5], pad[2] of groups of 16 consecutive tiles of a class
+    int32_t        part_sb0[kParts]; // first group of each sign class
+    int32_t        pad2_;
     float          scale[8];         // 2^-shift per original component (1 for F32)
 };
 
@@ -63,7 +67,7 @@ struct HostDb {
     int32_t* d_kept_rank = nullptr;
     int32_t* d_row_kpos = nullptr;
     float*   d_rows8 = nullptr;
-    float*   d_boxes = nullptr;          // decoded [n,8] copy, built on first use of the reduced mode
+    float*   d_boxes = nullptr;          // tile bounds, then the bounds of the tile groups (pruning layout only)
     int64_t  npad = 0, nnan = 0, bytes = 0;
     int      shift[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };

@@ -388,6 +388,29 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
         }
     }
 
+    size_t sbox_off = 0;                           // floats: the group bounds follow the tile bounds in one allocation
+    if (blocked) {
+        sbox_off = boxes.size();
+        int64_t sb = 0;
+        for (int q = 0; q < kParts; ++q) {
+            h.slot.part_sb0[q] = (int32_t)sb;
+            const int64_t ng = (h.slot.part_ntiles[q] + kSuper - 1) / kSuper;
+            for (int64_t g = 0; g < ng; ++g) {
+                float bx[12];
+                for (int c = 0; c < kNC; ++c) { bx[c] = INFINITY; bx[5 + c] = -INFINITY; }
+                bx[10] = bx[11] = 0.f;
+                const int64_t t0 = h.slot.part_tile0[q] + g * kSuper, t1 = std::min<int64_t>(t0 + kSuper, h.slot.part_tile0[q] + h.slot.part_ntiles[q]);
+                for (int64_t t = t0; t < t1; ++t)
+                    for (int c = 0; c < kNC; ++c) {
+                        bx[c] = std::min(bx[c], boxes[t * 16 + c]);
+                        bx[5 + c] = std::max(bx[5 + c], boxes[t * 16 + 5 + c]);
+                    }
+                boxes.insert(boxes.end(), bx, bx + 12);
+            }
+            sb += ng;
+        }
+    }
+
     // ---- upload
     auto fail = [&](const char* what) {
         cudaGetLastError();
@@ -423,6 +446,7 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
     h.slot.live = 1;
     h.slot.blocked = blocked ? 1 : 0;
     h.slot.boxes = h.d_boxes;
+    h.slot.sboxes = h.d_boxes ? h.d_boxes + sbox_off : nullptr;
 
     int slot;
     if (!ctx->free_slots.empty()) { slot = ctx->free_slots.back(); ctx->free_slots.pop_back(); ctx->dbs[slot] = h; }

@@ -262,6 +262,12 @@ struct Plan {                 // all pointers are device pointers into the works
     int32_t  k;
     int32_t  dbg;             // timing experiments only: 1 = no list lock, 2 = skip the rare pass (results invalid)
     int64_t  npix;
+    // exact tile pruning only (NULL otherwise)
+    int32_t* seed;            // [npix][kParts] tile (relative to its sign class) whose representative entry fits the pixel best, -1 = none
+    int32_t* fcnt;            // [slots * ftiles] pixels per (database, seed tile): the fine sort key inside a bucket
+    int32_t* fcursor;         // [slots * ftiles]
+    int32_t* foff;            // [slots * ftiles] first position of the fine bucket in `order`
+    int32_t  ftiles;          // fine keys per database slot (>= tiles of the largest resident database)
 };
 
 __device__ __forceinline__ int nonempty_parts(const DbSlot& s) {
@@ -572,6 +578,39 @@ __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, float c0f, Cand<PREC>
     }
 }
 
+// slow_pixel for tiles that may hold MANY entries under the threshold (the neighbours of a pixel's seed tile in the pruned
+// search): candidates go in best first, so the threshold drops to the tile's k-th best after at most k insertions and the
+// remaining hits fall out by comparison instead of being inserted one after the other.  Same list, same tie rule.
+template <int ENC>
+__device__ __forceinline__ void merge_pixel(Rec<CLEDB_PREC_FP32>* rec, float c0f, Cand<CLEDB_PREC_FP32>* list, const float (&d)[kEPL][kNC],
+                                            const float (&scale)[kNC], int base, int cnt_end, const int32_t* __restrict__ perm,
+                                            int k, int lane) {
+    float v[kEPL], tau;
+    eval_pixel<ENC, CLEDB_PREC_FP32>(rec, c0f, d, scale, v, tau);
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e)
+        if (!(v[e] <= tau) || base + pos_in_tile<ENC>(lane, e) >= cnt_end) v[e] = CUDART_INF_F;      // not a hit (NaN, padding)
+    for (;;) {
+        float lm = v[0];
+        int le = 0;
+#pragma unroll
+        for (int e = 1; e < kEPL; ++e)
+            if (v[e] < lm) { lm = v[e]; le = e; }
+        const float gm = warp_min(lm);
+        if (!(gm < CUDART_INF_F)) {
+            // hits of value +inf (threshold still +inf): leave them to the plain path
+            break;
+        }
+        const int src = __ffs(__ballot_sync(0xffffffffu, lm == gm)) - 1;
+        const int es = __shfl_sync(0xffffffffu, le, src);
+        list_insert<CLEDB_PREC_FP32>(list, rec, c0f, k, gm, base + pos_in_tile<ENC>(src, es), perm, lane);
+        tau = rec->tau;
+#pragma unroll
+        for (int e = 0; e < kEPL; ++e)
+            if ((lane == src && e == es) || !(v[e] <= tau)) v[e] = CUDART_INF_F;
+    }
+}
+
 // first tile of an item: exact top-k of its 256 entries by k rounds of warp-min selection
 template <int ENC, int PREC>
 __device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, float c0f, Cand<PREC>* list, const float (&d)[kEPL][kNC],
@@ -806,34 +845,142 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// kernel 4b: the search with exact tile pruning (optional, databases put while cledb_set_pruning is on)
+// kernels 4b: the search with exact tile pruning (optional, databases put while cledb_set_pruning is on)
 // ------------------------------------------------------------------------------------------------------
-// Same items, same lists, same exact per-(pixel, tile) evaluation as k_match, but a (pixel, tile) pair is evaluated only if
-// the tile's chi^2 lower bound does not exceed the pixel's threshold.  Lane L owns pixel L (and L+32) of the item for the
-// bound: with the tile's component bounds lo_c <= d_c <= hi_c, r_c(d) = fma(d, a_c, nb_c) is monotone in d, so
-// |r_c| >= m_c = distance of the interval [r_c(lo), r_c(hi)] from 0, and the accumulation chain acc = fma(r, r, acc) is
-// monotone in |r| and acc: the bound computed with the same chain is <= the computed chi^2 of every entry of the tile,
-// exactly, in floating point.  Tiles nobody needs are not even loaded.
+// The tiles of such a database are the leaves of a k-d partition (db.cu), each with the bounds lo_c <= d_c <= hi_c of its
+// entries and one representative entry.  With r_c(d) = fma(d, a_c, nb_c) monotone in d, |r_c| >= m_c = distance of the
+// interval [r_c(lo), r_c(hi)] from 0, and the accumulation chain acc = fma(r, r, acc) is monotone in |r| and in acc: the
+// bound computed with the SAME chain is <= the computed chi^2 of every entry of the tile, exactly, in floating point.  A
+// tile whose bound exceeds a pixel's threshold cannot change that pixel's list, so the result is bit-identical to k_match.
+//
+//   k_seed        one thread per pixel: the tile whose representative entry fits the pixel best (a coarse search over one
+//                 entry per tile).  Pixels are then ordered by (bucket, seed tile), so the pixels of an item are neighbours
+//                 in the space of the chi^2 components and need nearly the same tiles.
+//   k_match_pruned  one warp per item: (1) the item's distinct seed tiles, evaluated for all its pixels (bootstrap), give
+//                 every pixel a threshold close to the final one; (2) lane L computes the bound of every tile for pixel L,
+//                 the union over the lanes is the item's tile list; (3) the listed tiles run through the same fast pass /
+//                 rare pass as in k_match.  Tiles nobody needs are not even loaded.
+__device__ __forceinline__ float tile_lower_bound(const float4 b0, const float4 b1, const float4 b2, const float (&a)[kNC],
+                                                  const float (&nb)[kNC], float c0) {
+    const float lo[kNC] = {b0.x, b0.y, b0.z, b0.w, b1.x};
+    const float hi[kNC] = {b1.y, b1.z, b1.w, b2.x, b2.y};
+    float lb = c0;
+#pragma unroll
+    for (int c = 0; c < kNC; ++c) {
+        const float rl = fmaf(lo[c], a[c], nb[c]), rh = fmaf(hi[c], a[c], nb[c]);
+        float mn = fmaxf(fmaxf(fminf(rl, rh), -fmaxf(rl, rh)), 0.f);      // both > 0: the smaller; both < 0: the smaller |.|; else 0
+        const float t = rl + rh;
+        mn = (t == t) ? mn : 0.f;                                         // NaN anywhere: no bound from this component
+        lb = fmaf(mn, mn, lb);
+    }
+    return lb;
+}
+
+__global__ void __launch_bounds__(128) k_seed(Plan pl, const DbSlot* __restrict__ slots) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pl.npix) return;
+    const int key = pl.key[p];
+    if (key < 0) return;
+    const DbSlot& db = slots[key / kParts];
+    const Rec<CLEDB_PREC_FP32> r = reinterpret_cast<const Rec<CLEDB_PREC_FP32>*>(pl.recs)[p];
+    int sort_tile = -1;
+    for (int q = 0; q < kParts; ++q) {
+        int best_t = -1;
+        const bool mine = pl.mode == CLEDB_MODE_IQUV ? q == key % kParts : db.part_cnt[q] > 0;
+        if (mine) {
+            const float4* bx = reinterpret_cast<const float4*>(db.boxes) + (size_t)db.part_tile0[q] * 4;
+            float best = CUDART_INF_F;
+            const int nt = db.part_ntiles[q];
+#pragma unroll 4
+            for (int t = 0; t < nt; ++t) {
+                const float4 b2 = __ldg(bx + (size_t)t * 4 + 2), b3 = __ldg(bx + (size_t)t * 4 + 3);
+                const float rep[kNC] = {b2.z, b2.w, b3.x, b3.y, b3.z};
+                const float v = eval_fp32(rep, r.a, r.nb, r.cm);
+                if (v < best) { best = v; best_t = t; }
+            }
+            if (sort_tile < 0 && best_t >= 0) sort_tile = db.part_tile0[q] + best_t;
+        }
+        pl.seed[p * kParts + q] = best_t;
+    }
+    if (sort_tile < 0) sort_tile = 0;
+    atomicAdd(&pl.fcnt[(key / kParts) * pl.ftiles + sort_tile], 1);
+}
+
+// exclusive scan of the fine counts (one block)
+__global__ void __launch_bounds__(1024) k_fscan(Plan pl, int nf) {
+    __shared__ int s_sum[1024];
+    const int tid = threadIdx.x;
+    const int per = (nf + 1023) / 1024;
+    const int k0 = tid * per, k1 = min(nf, k0 + per);
+    int sum = 0;
+    for (int i = k0; i < k1; ++i) sum += pl.fcnt[i];
+    s_sum[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int a = 0;
+        if (tid >= o) a = s_sum[tid - o];
+        __syncthreads();
+        s_sum[tid] += a;
+        __syncthreads();
+    }
+    int run = s_sum[tid] - sum;
+    for (int i = k0; i < k1; ++i) { pl.foff[i] = run; run += pl.fcnt[i]; }
+}
+
+// pixels into (bucket, seed tile) order; the buckets of k_scan are unions of consecutive fine buckets
+__global__ void __launch_bounds__(256) k_scatter_fine(Plan pl, const DbSlot* __restrict__ slots) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pl.npix) return;
+    const int key = pl.key[p];
+    if (key < 0) { pl.rank[p] = -1; return; }
+    const DbSlot& db = slots[key / kParts];
+    int sort_tile = -1;
+    for (int q = 0; q < kParts && sort_tile < 0; ++q) {
+        const int t = pl.seed[p * kParts + q];
+        const bool mine = pl.mode == CLEDB_MODE_IQUV ? q == key % kParts : db.part_cnt[q] > 0;
+        if (mine && t >= 0) sort_tile = db.part_tile0[q] + t;
+    }
+    if (sort_tile < 0) sort_tile = 0;
+    const int f = (key / kParts) * pl.ftiles + sort_tile;
+    const int r = pl.foff[f] + atomicAdd(&pl.fcursor[f], 1);
+    pl.order[r] = (int32_t)p;
+    pl.rank[p] = r;
+}
+
+template <int ENC> struct PCfg {        // shared memory of one warp of the pruned search: one tile in flight, <= 32 pixels
+    static constexpr int kWpc = 16;
+    static constexpr int kTB = tile_bytes<ENC>();
+    static constexpr int kRecBytes = (32 + 1) * (int)sizeof(Rec<CLEDB_PREC_FP32>);
+    static constexpr int kListBytes = kListCap * (int)sizeof(Cand<CLEDB_PREC_FP32>);
+};
+constexpr int kTileListCap = 192;       // tile list of a warp: flushed at >= 64 entries, one bound chunk adds <= 128
+
+template <int ENC> __host__ __device__ constexpr int pruned_warp_bytes() {
+    return (PCfg<ENC>::kTB + PCfg<ENC>::kRecBytes + PCfg<ENC>::kListBytes + 16 + 128 + (2 * kTileListCap + 32) * 4 + 127) / 128 * 128;
+}
+
 template <int ENC>
-__global__ void __launch_bounds__(KCfg<ENC, CLEDB_PREC_FP32>::kWpc * 32, 1)
+__global__ void __launch_bounds__(PCfg<ENC>::kWpc * 32, 1)
 k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __restrict__ stats) {
     constexpr int PREC = CLEDB_PREC_FP32;
-    using C = KCfg<ENC, PREC>;
-    using V = float;
+    using C = PCfg<ENC>;
     using CandT = Cand<PREC>;
     using RecT = Rec<PREC>;
-    constexpr int TB = C::kTB, SB = C::kStageBytes;
+    constexpr int TB = C::kTB;
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* stages = smem + (size_t)warp * C::kWarpBytes;
-    RecT* recs = reinterpret_cast<RecT*>(stages + kStages * SB);
-    CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);
+    unsigned char* stages = smem + (size_t)warp * pruned_warp_bytes<ENC>();                 // one tile
+    RecT* recs = reinterpret_cast<RecT*>(stages + TB);                                       // [32 + 1]
+    CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);   // [npx][k]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);
-    float* c0s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + (kStages * 8 + 15) / 16 * 16);
+    float* c0s = reinterpret_cast<float*>(bars + 2);                                         // [32]
+    int32_t* tlist = reinterpret_cast<int32_t*>(c0s + 32);                                   // [kTileListCap] tiles to evaluate
+    uint32_t* tmask = reinterpret_cast<uint32_t*>(tlist + kTileListCap);                     // [kTileListCap] the pixels that need each of them
+    int32_t* slist = tlist + 2 * kTileListCap;                                               // [32] the item's seed tiles
     const int k = pl.k;
     uint32_t phase = 0;
-    unsigned long long n_eval = 0, n_skip = 0;
+    unsigned long long n_eval = 0, n_all = 0;
 
     if (lane == 0) {
         mbar_init(&bars[0], 1);
@@ -846,12 +993,14 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
         if (lane == 0) it = atomicAdd(&pl.counters[0], 1);
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= pl.counters[2]) break;
-        const Item im = make_item(pl, slots, it);
+        const Item im = make_item(pl, slots, it);                             // items hold <= 32 pixels and whole sign classes
         const DbSlot& db = slots[im.slot];
         const unsigned char* gt = reinterpret_cast<const unsigned char*>(db.tiles) + (size_t)im.tile0 * TB;
         const float4* boxes = reinterpret_cast<const float4*>(db.boxes) + (size_t)im.tile0 * 4;
         CandT* gout = reinterpret_cast<CandT*>(pl.plist) + (size_t)it * pl.P * k;
-        const int nsteps = (im.ntiles + 1) / 2;
+        int part = 0;
+        for (int q = 0; q < kParts; ++q) if (db.part_tile0[q] == im.tile0 && db.part_ntiles[q] == im.ntiles && db.part_cnt[q] > 0) part = q;
+        const float4* sboxes = reinterpret_cast<const float4*>(db.sboxes) + (size_t)db.part_sb0[part] * 3;
 
         for (int i = lane; i < im.npx * (int)(sizeof(RecT) / 16); i += 32) {
             const int j = i / (int)(sizeof(RecT) / 16), w = i % (int)(sizeof(RecT) / 16);
@@ -863,165 +1012,215 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
             lists[i].pos = -1;
         }
         __syncwarp();
-        for (int j = lane; j < im.npx; j += 32) {
-            c0s[j] = recs[j].cm;
-            recs[j].cm = -CUDART_INF_F;
+        // Lane L owns pixel L for the seeds.  For the bounds the warp is cut into 32/Pb groups of Pb lanes (Pb = 8, 16 or 32,
+        // the smallest that holds the item): lane L bounds pixel L % Pb and takes every (32/Pb)-th tile of a tile group.
+        const int Pb = im.npx <= 8 ? 8 : (im.npx <= 16 ? 16 : 32), lanes_per_pixel = 32 / Pb;
+        const int bj = lane % Pb, bg = lane / Pb;
+        float pa[kNC], pnb[kNC], pc0 = 0.f;
+        int my_seed = -1;
+        if (bj < im.npx) {
+            const float4* rp = reinterpret_cast<const float4*>(recs + bj);
+            const float4 x0 = rp[0], x1 = rp[1], x2 = rp[2];
+            pa[0] = x0.x; pa[1] = x0.y; pa[2] = x0.z; pa[3] = x0.w; pa[4] = x1.x;
+            pnb[0] = x1.y; pnb[1] = x1.z; pnb[2] = x1.w; pnb[3] = x2.x; pnb[4] = x2.y;
+            pc0 = x2.z;
+        } else {
+#pragma unroll
+            for (int c = 0; c < kNC; ++c) { pa[c] = 0.f; pnb[c] = 0.f; }
+        }
+        __syncwarp();
+        if (lane < im.npx) {                      // c0 to the side array, the flagging start value into its slot
+            c0s[lane] = pc0;
+            recs[lane].cm = -CUDART_INF_F;
+            my_seed = pl.seed[(size_t)pl.order[im.pix0 + lane] * kParts + part];
+            if (my_seed >= im.ntiles) my_seed = -1;
         }
         __syncwarp();
         float scale[kNC];
 #pragma unroll
         for (int c = 0; c < kNC; ++c) scale[c] = db.scale[chi_comp(c)];
-
-        // chi^2 lower bound of tile t for the lane's pixel of segment seg (+inf for a lane without pixel)
-        auto tile_bound = [&](int t, int seg) -> float {
-            const int j = seg * 32 + lane;
-            if (j >= im.npx) return CUDART_INF_F;
-            const float4 b0 = __ldg(boxes + (size_t)t * 4), b1 = __ldg(boxes + (size_t)t * 4 + 1), b2 = __ldg(boxes + (size_t)t * 4 + 2);
-            const float lo[kNC] = {b0.x, b0.y, b0.z, b0.w, b1.x};
-            const float hi[kNC] = {b1.y, b1.z, b1.w, b2.x, b2.y};
-            const float4* rp = reinterpret_cast<const float4*>(recs + j);
-            const float4 x0 = rp[0], x1 = rp[1], x2 = rp[2];
-            const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
-            const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
-            float lb = c0s[j];
-#pragma unroll
-            for (int c = 0; c < kNC; ++c) {
-                const float rl = fmaf(lo[c], a[c], nb[c]), rh = fmaf(hi[c], a[c], nb[c]);
-                float mn = 0.f;                                    // NaN / mixed signs: no bound from this component
-                if (rl > 0.f && rh > 0.f) mn = fminf(rl, rh);
-                else if (rl < 0.f && rh < 0.f) mn = fminf(-rl, -rh);
-                lb = fmaf(mn, mn, lb);
-            }
-            return lb;
-        };
-
-        // ---- seed: every pixel first visits the two tiles whose representative entry (stored next to the bounds) fits it
-        //      best - a coarse search over one entry per tile - which gives it a threshold close to the final one before
-        //      the scan starts (a tile sequence that suits every pixel does not exist)
-        int seed[2] = {-1, -1}, seed2[2] = {-1, -1};
-        {
-            float best[2] = {CUDART_INF_F, CUDART_INF_F}, second[2] = {CUDART_INF_F, CUDART_INF_F};
-            const int nseg = im.npx > 32 ? 2 : 1;
-            for (int t = 0; t < im.ntiles; ++t) {
-                const float4 b2 = __ldg(boxes + (size_t)t * 4 + 2), b3 = __ldg(boxes + (size_t)t * 4 + 3);
-                const float rep[kNC] = {b2.z, b2.w, b3.x, b3.y, b3.z};
-                for (int seg = 0; seg < nseg; ++seg) {
-                    const int j = seg * 32 + lane;
-                    if (j >= im.npx) continue;
-                    const float4* rp = reinterpret_cast<const float4*>(recs + j);
-                    const float4 x0 = rp[0], x1 = rp[1], x2 = rp[2];
-                    const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
-                    const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
-                    const float v = eval_fp32(rep, a, nb, c0s[j]);
-                    if (v < best[seg]) { second[seg] = best[seg]; seed2[seg] = seed[seg]; best[seg] = v; seed[seg] = t; }
-                    else if (v < second[seg]) { second[seg] = v; seed2[seg] = t; }
-                }
-            }
-            for (int seg = 0; seg < 2; ++seg) if (seed[seg] < 0) seed[seg] = 0;       // every chi^2 NaN: any tile will do
-        }
-        float d[kEPL][kNC], d2[kEPL][kNC];
-        for (int j = 0; j < im.npx; ++j) {
-            const int t = __shfl_sync(0xffffffffu, j < 32 ? seed[0] : seed[1], j & 31);
-            const int u = __shfl_sync(0xffffffffu, j < 32 ? seed2[0] : seed2[1], j & 31);
-            if (lane == 0) {
-                mbar_expect_tx(&bars[0], u >= 0 ? 2 * TB : TB);
-                tma_load_1d(stages, gt + (size_t)t * TB, TB, &bars[0]);
-                if (u >= 0) tma_load_1d(stages + TB, gt + (size_t)u * TB, TB, &bars[0]);
-            }
-            mbar_wait(&bars[0], phase);
-            phase ^= 1u;
-            load_tile_regs<ENC>(stages, lane, d);
-            if (u >= 0) load_tile_regs<ENC>(stages + TB, lane, d2);
+        const uint32_t rec_base = smem_u32(recs);
+        n_all += (unsigned long long)im.npx * im.ntiles;
+        if (im.ntiles == 0) {
+            for (int i = lane; i < im.npx * k; i += 32) gout[i] = lists[i];
             __syncwarp();
-            const int base = (im.tile0 + t) * kTile;
-            int rows[kEPL];
-#pragma unroll
-            for (int e = 0; e < kEPL; ++e) {
-                const int pos = base + pos_in_tile<ENC>(lane, e);
-                rows[e] = pos < im.cnt_end ? db.perm[pos] : 0x7fffffff;
-            }
-            bootstrap_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, rows, k, lane);
-            if (u >= 0) slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d2, scale, (im.tile0 + u) * kTile, im.cnt_end, db.perm, k, lane);
+            continue;
         }
-        n_eval += 2 * im.npx;
 
-        // survivors of one step: bit L of m[seg][tile] = pixel seg*32+L must evaluate that tile
-        auto survivors = [&](int step, uint32_t (&m)[2][2]) {
-            const int t = step * 2, nt = min(2, im.ntiles - t);
-#pragma unroll
-            for (int seg = 0; seg < 2; ++seg) {
-                const int j = seg * 32 + lane;
-                bool need[2] = {false, false};
-                if (j < im.npx && (seg == 0 || im.npx > 32)) {
-                    const float tau = recs[j].tau;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q)
-                        need[q] = q < nt && t + q != seed[seg] && t + q != seed2[seg] && !(tile_bound(t + q, seg) > tau);   // NaN keeps the tile
-                }
-                m[seg][0] = __ballot_sync(0xffffffffu, need[0]);
-                m[seg][1] = __ballot_sync(0xffffffffu, need[1]);
+        // ---- the distinct seed tiles of the item's pixels
+        int ns = 0;
+        {
+            uint32_t active = __ballot_sync(0xffffffffu, my_seed >= 0);
+            while (active) {
+                const int leader = __ffs(active) - 1;
+                const int ts = __shfl_sync(0xffffffffu, my_seed, leader);
+                active &= ~__ballot_sync(0xffffffffu, my_seed == ts);
+                if (lane == 0) slist[ns] = ts;
+                ++ns;
             }
-        };
-
-        uint32_t cur[2][2] = {{0, 0}, {0, 0}}, nxt[2][2] = {{0, 0}, {0, 0}};
-        bool loaded = false;
-        if (nsteps > 0) {
-            survivors(0, cur);
-            loaded = (cur[0][0] | cur[0][1] | cur[1][0] | cur[1][1]) != 0;
-            if (lane == 0 && loaded) {
-                const uint32_t bytes = (uint32_t)min(2, im.ntiles) * TB;
-                mbar_expect_tx(&bars[0], bytes);
-                tma_load_1d(stages, gt, bytes, &bars[0]);
-            }
+            if (ns == 0) { if (lane == 0) slist[0] = 0; ns = 1; }
+            __syncwarp();
         }
-        for (int step = 0; step < nsteps; ++step) {
-            const int t = step * 2, nt = min(2, im.ntiles - t);
-            const int base = (im.tile0 + t) * kTile;
-            const bool any_a = (cur[0][0] | cur[1][0]) != 0, any_b = nt == 2 && (cur[0][1] | cur[1][1]) != 0;
-            if (loaded) {
+
+        float d[kEPL][kNC];
+        bool exact_only = false;
+        // ---- every pixel starts with the exact top-k of its own seed tile: a threshold close to the final one
+        {
+            if (lane == 0) {
+                mbar_expect_tx(&bars[0], TB);
+                tma_load_1d(stages, gt + (size_t)slist[0] * TB, TB, &bars[0]);
+            }
+            for (int i = 0; i < ns; ++i) {
+                const int ts = slist[i];
                 mbar_wait(&bars[0], phase);
                 phase ^= 1u;
-                if (any_a) load_tile_regs<ENC>(stages, lane, d);
-                if (any_b) load_tile_regs<ENC>(stages + TB, lane, d2);
+                load_tile_regs<ENC>(stages, lane, d);
                 __syncwarp();
-            }
-            // bounds of the next step against the thresholds as they are now (they only tighten: a superset), then its load
-            bool load_next = false;
-            if (step + 1 < nsteps) {
-                survivors(step + 1, nxt);
-                load_next = (nxt[0][0] | nxt[0][1] | nxt[1][0] | nxt[1][1]) != 0;
-                if (lane == 0 && load_next) {
-                    const uint32_t bytes = (uint32_t)min(2, im.ntiles - (t + 2)) * TB;
-                    mbar_expect_tx(&bars[0], bytes);
-                    tma_load_1d(stages, gt + (size_t)(step + 1) * SB, bytes, &bars[0]);
+                if (lane == 0 && i + 1 < ns) {
+                    mbar_expect_tx(&bars[0], TB);
+                    tma_load_1d(stages, gt + (size_t)slist[i + 1] * TB, TB, &bars[0]);
                 }
+                const int base = (im.tile0 + ts) * kTile;
+                int rows[kEPL];
+#pragma unroll
+                for (int e = 0; e < kEPL; ++e) {
+                    const int pos = base + pos_in_tile<ENC>(lane, e);
+                    rows[e] = pos < im.cnt_end ? db.perm[pos] : 0x7fffffff;
+                }
+                uint32_t own = __ballot_sync(0xffffffffu, my_seed == ts);
+                n_eval += __popc(own);
+                while (own) {
+                    const int j = __ffs(own) - 1;
+                    own &= own - 1;
+                    bootstrap_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, rows, k, lane);
+                }
+            }
+            __syncwarp();
+            // a list its seed tile could not fill (or a pixel without seed) keeps tau = inf: exact path for the whole item
+            exact_only = __any_sync(0xffffffffu, lane < im.npx && !(recs[lane].tau < CUDART_INF_F));
+        }
+        // one tile against the pixels in `set` (bit j = pixel j): the fast pass of k_match over those pixels, then the exact
+        // re-evaluation of the flagged ones
+        auto tile_pixels = [&](uint32_t set, const float (&dd)[kEPL][kNC], int base) {
+            n_eval += __popc(set);
+            if (!exact_only) {
+                uint32_t hm = 0, rem = set;
+                int j = __ffs(rem) - 1;
+                rem &= rem - 1;
+                uint32_t ra = rec_base + (uint32_t)max(j, 0) * (uint32_t)sizeof(RecT);
+                float4 n0 = lds128(ra), n1 = lds128(ra + 16), n2 = lds128(ra + 32);
+                while (j >= 0) {
+                    const float4 x0 = n0, x1 = n1, x2 = n2;
+                    const int jn = __ffs(rem) - 1;                                  // -1 when none is left
+                    rem &= rem - 1;
+                    ra = rec_base + (uint32_t)max(jn, 0) * (uint32_t)sizeof(RecT);
+                    n0 = lds128(ra); n1 = lds128(ra + 16); n2 = lds128(ra + 32);    // next record in flight
+                    const float a[kNC] = {x0.x, x0.y, x0.z, x0.w, x1.x};
+                    const float nb[kNC] = {x1.y, x1.z, x1.w, x2.x, x2.y};
+                    float v[kEPL];
+                    eval_fp32_all(dd, a, nb, x2.z, v);
+                    const uint32_t sg = ((__float_as_uint(v[0]) | __float_as_uint(v[1]) | __float_as_uint(v[2])) |
+                                         (__float_as_uint(v[3]) | __float_as_uint(v[4]) | __float_as_uint(v[5]))) |
+                                        (__float_as_uint(v[6]) | __float_as_uint(v[7]));
+                    hm |= (sg >> 31) << j;
+                    j = jn;
+                }
+                uint32_t any = __reduce_or_sync(0xffffffffu, hm);
+                while (any) {
+                    const int jj = __ffs(any) - 1;
+                    any &= any - 1;
+                    merge_pixel<ENC>(recs + jj, c0s[jj], lists + jj * k, dd, scale, base, im.cnt_end, db.perm, k, lane);
+                }
+            } else {
+                while (set) {
+                    const int jj = __ffs(set) - 1;
+                    set &= set - 1;
+                    slow_pixel<ENC, PREC>(recs + jj, c0s[jj], lists + jj * k, dd, scale, base, im.cnt_end, db.perm, k, lane);
+                }
+            }
+        };
+        // the listed tiles one after the other, the next one in flight
+        auto run_tiles = [&](int n) {
+            auto issue = [&](int s) {
+                if (lane == 0) {
+                    mbar_expect_tx(&bars[0], TB);
+                    tma_load_1d(stages, gt + (size_t)tlist[s] * TB, TB, &bars[0]);
+                }
+            };
+            if (n > 0) issue(0);
+            for (int s = 0; s < n; ++s) {
+                const int ta = tlist[s];
+                const uint32_t set_a = tmask[s];
+                mbar_wait(&bars[0], phase);
+                phase ^= 1u;
+                load_tile_regs<ENC>(stages, lane, d);
+                __syncwarp();
+                if (s + 1 < n) issue(s + 1);
+                tile_pixels(set_a, d, (im.tile0 + ta) * kTile);
+            }
+            __syncwarp();
+        };
+
+        // ---- bounds in chunks of 128 tiles against the thresholds as they are by then (they only tighten: a superset of the
+        //      pairs that matter)
+        int nu = 0;
+        const uint32_t low = Pb == 32 ? 0xffffffffu : ((1u << Pb) - 1u);
+        for (int t0 = 0; t0 < im.ntiles; t0 += 128) {
+            const int nt = min(128, im.ntiles - t0);
+            const float tau = bj < im.npx ? recs[bj].tau : -CUDART_INF_F;        // a lane without pixel needs nothing
+            uint32_t m[4] = {0u, 0u, 0u, 0u};
+            // two levels: the bound of a group of 16 tiles first, the tiles of a group only if the group survives; the
+            // lanes that share a pixel take the tiles of a group in turns
+            const float4* sb = sboxes + (size_t)(t0 / kSuper) * 3;
+#pragma unroll
+            for (int g = 0; g < 128 / kSuper; ++g) {
+                if (g * kSuper < nt) {
+                    const float lbg = tile_lower_bound(__ldg(sb + g * 3), __ldg(sb + g * 3 + 1), __ldg(sb + g * 3 + 2), pa, pnb, pc0);
+                    if (!(lbg > tau)) {
+                        const int ng = min(kSuper, nt - g * kSuper);
+                        const float4* bx = boxes + (size_t)(t0 + g * kSuper) * 4;
+                        uint32_t mg = 0;
+                        for (int i = bg; i < ng; i += lanes_per_pixel) {
+                            const float lb = tile_lower_bound(__ldg(bx + i * 4), __ldg(bx + i * 4 + 1), __ldg(bx + i * 4 + 2), pa, pnb, pc0);
+                            mg |= (!(lb > tau) ? 1u : 0u) << i;                    // a NaN bound keeps the tile
+                        }
+                        m[g / 2] |= mg << ((g & 1) * kSuper);
+                    }
+                }
+            }
+            // the lanes of a pixel put their shares together; the pixel's own seed tile is in its list already
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (Pb <= 16) m[q] |= __shfl_xor_sync(0xffffffffu, m[q], 16);
+                if (Pb <= 8) m[q] |= __shfl_xor_sync(0xffffffffu, m[q], 8);
+            }
+            if (my_seed >= t0 && my_seed < t0 + 128) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (((my_seed - t0) >> 5) == q) m[q] &= ~(1u << ((my_seed - t0) & 31));
             }
 #pragma unroll
-            for (int seg = 0; seg < 2; ++seg) {
-                uint32_t ma = cur[seg][0], mb = cur[seg][1];
-                n_eval += __popc(ma) + __popc(mb);
-                while (ma) {
-                    const int j = seg * 32 + __ffs(ma) - 1;
-                    ma &= ma - 1;
-                    slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
-                }
-                while (mb) {
-                    const int j = seg * 32 + __ffs(mb) - 1;
-                    mb &= mb - 1;
-                    slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d2, scale, base + kTile, im.cnt_end, db.perm, k, lane);
+            for (int q = 0; q < 4; ++q) {
+                uint32_t w = __reduce_or_sync(0xffffffffu, lane < Pb ? m[q] : 0u);
+                while (w) {
+                    const int b = __ffs(w) - 1;
+                    w &= w - 1;
+                    const uint32_t set = __ballot_sync(0xffffffffu, (m[q] >> b) & 1u) & low;
+                    if (lane == 0) { tlist[nu] = t0 + q * 32 + b; tmask[nu] = set; }
+                    ++nu;
                 }
             }
-            cur[0][0] = nxt[0][0]; cur[0][1] = nxt[0][1]; cur[1][0] = nxt[1][0]; cur[1][1] = nxt[1][1];
-            loaded = load_next;
+            __syncwarp();
+            if (nu < 64 && t0 + 128 < im.ntiles) continue;
+            run_tiles(nu);
+            nu = 0;
         }
-        n_skip += (unsigned long long)im.npx * im.ntiles;
         __syncwarp();
         for (int i = lane; i < im.npx * k; i += 32) gout[i] = lists[i];
         __syncwarp();
     }
     if (lane == 0 && stats) {
         atomicAdd(&stats[0], n_eval);
-        atomicAdd(&stats[1], n_skip - n_eval);
+        atomicAdd(&stats[1], n_all - n_eval);
     }
 }
 
@@ -1254,6 +1453,14 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
         ctx->err = "cledb_match: a pixel refers to a database id that is not resident (cledb_db_put it first)";
         return CLEDB_ERR_NODB;
     }
+    const bool pruned = PREC == CLEDB_PREC_FP32 && pl.seed != nullptr;
+    if (pruned) {                                          // one lane per pixel for the bounds, whole sign classes per item
+        // 8, 16 or 32 pixels per item: the largest that still gives every resident warp about four items to pull
+        pl.P = npix >= 128 * wslots ? 32 : (npix >= 64 * wslots ? 16 : 8);
+        pl.P = std::min(pl.P, pmax);
+        if (ctx->pixels_per_item > 0) pl.P = std::min(std::min(32, pmax), ctx->pixels_per_item);
+        pl.split = 1;
+    } else
     choose_shape(ctx, ctx->h_cnt, std::min<int>(pl.nkeys, (int)ctx->dbs.size() * kParts), pl.mode, pl.k, wslots, pmax, &pl.P, &pl.split);
     int64_t tiles_of_pixels = 0;
     for (int key = 0; key < pl.nkeys; ++key) tiles_of_pixels += (ctx->h_cnt[key] + pl.P - 1) / pl.P;
@@ -1266,7 +1473,12 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     pl.plist = ctx->ws2.ptr;
 
     k_scan<<<1, 1024, 0, st>>>(pl, ctx->d_slots);
-    k_scatter<<<nb, 256, 0, st>>>(pl);
+    if (pruned) {
+        k_seed<<<(int)((npix + 127) / 128), 128, 0, st>>>(pl, ctx->d_slots);
+        k_fscan<<<1, 1024, 0, st>>>(pl, ctx->slots_cap * pl.ftiles);
+        k_scatter_fine<<<nb, 256, 0, st>>>(pl, ctx->d_slots);
+        ctx->launches += 2;
+    } else k_scatter<<<nb, 256, 0, st>>>(pl);
     ctx->launches += 2;
     int occ = 0;
     size_t smem = 0;
@@ -1275,26 +1487,21 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     if (rc) return rc;
     const int wpc = enc == CLEDB_ENC_I16 ? KCfg<CLEDB_ENC_I16, PREC>::kWpc : KCfg<CLEDB_ENC_F32, PREC>::kWpc;
     const int grid = (int)std::min<int64_t>((int64_t)ctx->prop.multiProcessorCount * occ, std::max<int64_t>(1, (max_items + wpc - 1) / wpc));
-    // exact tile pruning: only with the fp32 kernel, and only if every resident database was put in the pruning layout
-    int nblocked = 0, nlive = 0;
-    for (auto& h : ctx->dbs) {
-        if (!h.slot.live) continue;
-        ++nlive;
-        nblocked += h.slot.blocked ? 1 : 0;
-    }
-    if (nblocked != 0 && nblocked != nlive) { ctx->err = "cledb_match: resident databases mix the pruning and the plain layout"; return CLEDB_ERR_ARG; }
-    const bool pruned = PREC == CLEDB_PREC_FP32 && nblocked > 0;
+    int pgrid = 1;
     if (pruned) {
         if (!ctx->d_prune_stats) CLEDB_CUDA(ctx, cudaMalloc(&ctx->d_prune_stats, 16));
         CLEDB_CUDA(ctx, cudaMemsetAsync(ctx->d_prune_stats, 0, 16, st));
+        const int pw = enc == CLEDB_ENC_I16 ? PCfg<CLEDB_ENC_I16>::kWpc : PCfg<CLEDB_ENC_F32>::kWpc;
+        smem = (size_t)pw * (enc == CLEDB_ENC_I16 ? pruned_warp_bytes<CLEDB_ENC_I16>() : pruned_warp_bytes<CLEDB_ENC_F32>());
         if (enc == CLEDB_ENC_I16) CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_match_pruned<CLEDB_ENC_I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_match_pruned<CLEDB_ENC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pgrid = (int)std::min<int64_t>((int64_t)ctx->prop.multiProcessorCount, std::max<int64_t>(1, (max_items + pw - 1) / pw));
     }
     const bool prof = ctx->prof_on && ctx->prof_used < (int)ctx->prof.size();
     if (prof) CLEDB_CUDA(ctx, cudaEventRecord(ctx->prof[ctx->prof_used].first, st));
     if (pruned) {
-        if (enc == CLEDB_ENC_I16) k_match_pruned<CLEDB_ENC_I16><<<grid, KCfg<CLEDB_ENC_I16, CLEDB_PREC_FP32>::kWpc * 32, smem, st>>>(pl, ctx->d_slots, ctx->d_prune_stats);
-        else k_match_pruned<CLEDB_ENC_F32><<<grid, KCfg<CLEDB_ENC_F32, CLEDB_PREC_FP32>::kWpc * 32, smem, st>>>(pl, ctx->d_slots, ctx->d_prune_stats);
+        if (enc == CLEDB_ENC_I16) k_match_pruned<CLEDB_ENC_I16><<<pgrid, PCfg<CLEDB_ENC_I16>::kWpc * 32, smem, st>>>(pl, ctx->d_slots, ctx->d_prune_stats);
+        else k_match_pruned<CLEDB_ENC_F32><<<pgrid, PCfg<CLEDB_ENC_F32>::kWpc * 32, smem, st>>>(pl, ctx->d_slots, ctx->d_prune_stats);
     } else if (enc == CLEDB_ENC_I16) k_match<CLEDB_ENC_I16, PREC><<<grid, KCfg<CLEDB_ENC_I16, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
     else k_match<CLEDB_ENC_F32, PREC><<<grid, KCfg<CLEDB_ENC_F32, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
     if (prof) {
@@ -1351,6 +1558,18 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     const size_t o_key = take(npix * 4), o_rank = take(npix * 4), o_order = take(npix * 4);
     const size_t o_small = take((size_t)(5 * pl.nkeys + 1 + 4) * 4);
     const size_t o_recs = take(npix * rec_sz), o_status = take(npix);
+    // exact tile pruning: only with the fp32 kernel, and only if every resident database was put in the pruning layout
+    int nblocked = 0, nlive = 0, ftiles = 1;
+    for (auto& h : ctx->dbs) {
+        if (!h.slot.live) continue;
+        ++nlive;
+        nblocked += h.slot.blocked ? 1 : 0;
+        ftiles = std::max(ftiles, (int)(h.npad / kTile));
+    }
+    if (nblocked != 0 && nblocked != nlive) { ctx->err = "cledb_match: resident databases mix the pruning and the plain layout"; return CLEDB_ERR_ARG; }
+    const bool pruned = precision == CLEDB_PREC_FP32 && nblocked > 0;
+    const size_t nfine = pruned ? (size_t)ctx->slots_cap * ftiles : 0;
+    const size_t o_seed = take(pruned ? npix * kParts * 4 : 0), o_fine = take(3 * nfine * 4);
     if ((rc = ensure_workspace(ctx, ctx->ws, off))) return rc;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx->ws.ptr);
     pl.key = reinterpret_cast<int32_t*>(w + o_key);
@@ -1366,6 +1585,14 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     pl.recs = w + o_recs;
     pl.status = status_out ? status_out : (w + o_status);
     CLEDB_CUDA(ctx, cudaMemsetAsync(small, 0, (size_t)(5 * pl.nkeys + 1 + 4) * 4, st));
+    if (pruned) {
+        pl.seed = reinterpret_cast<int32_t*>(w + o_seed);
+        pl.fcnt = reinterpret_cast<int32_t*>(w + o_fine);
+        pl.fcursor = pl.fcnt + nfine;
+        pl.foff = pl.fcursor + nfine;
+        pl.ftiles = ftiles;
+        CLEDB_CUDA(ctx, cudaMemsetAsync(pl.fcnt, 0, 2 * nfine * 4, st));
+    }
     if (precision == CLEDB_PREC_FP32)
         rc = run_match<CLEDB_PREC_FP32>(ctx, enc, pl, wslots, pmax, sobs, snr, db_id, idx_out, chi_out, chi64_out, kpos_out, rows_out, ncand_out, st);
     else
