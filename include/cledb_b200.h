@@ -42,12 +42,15 @@ typedef struct cledb_ctx cledb_ctx;
 #define CLEDB_ENC_F32 0         /* database kept as float32 in HBM (lossless)                             */
 #define CLEDB_ENC_I16 1         /* database kept as int16 codes in HBM (see cledb_codec_*)                */
 
-/* Optional: exact tile pruning.  A database put while pruning is on (cledb_set_pruning) keeps its candidate rows in their
- * original (gx, phi, theta) order inside each sign class, so that a 256-entry tile is a compact patch of parameter space,
- * and stores the component bounds of every tile; the search then skips, per pixel, every tile whose chi^2 lower bound
- * already exceeds the pixel's running threshold.  The lower bound is exact in floating point (fma and the accumulation
- * chain are monotone), so results are bit-identical to the plain search; only the amount of arithmetic changes.
- * Off by default: the plain search is the brute-force evaluation of every (pixel, entry) pair. */
+/* Exact tile pruning (default on; cledb_set_pruning or the environment variable CLEDB_B200_PRUNING=0 turn it off).  A
+ * database put while pruning is on is stored, inside each sign class, as the leaves of a k-d partition of its entries in the
+ * space of the five chi^2 components: a 256-entry tile is a small box of that space, stored with its component bounds
+ * (and the bounds of every group of 16 tiles).  The search orders the pixels by the tile that fits them best and skips,
+ * per pixel, every tile whose chi^2 lower bound exceeds the pixel's running threshold.  The bound is exact in floating
+ * point (fma and the accumulation chain are monotone), so idx / chi / kpos / rows are bit-identical to the plain search;
+ * only the amount of arithmetic changes (about 2 % of the (pixel, tile) pairs are evaluated on BASELINE config 2).
+ * Pruning off = the brute-force evaluation of every (pixel, entry) pair, the kernel the FP32 roofline is quoted on.
+ * The fp64 validation kernel always searches by brute force. */
 #define CLEDB_PREC_FP32 0       /* production kernel: fp32 FMA residuals                                  */
 #define CLEDB_PREC_FP64 1       /* validation kernel: the reference's operation order in f32/f64          */
 

@@ -1,5 +1,6 @@
 // C-ABI entry points of libcledb_b200.so (include/cledb_b200.h): context management and the host-buffer
 // wrappers around the device paths.
+#include <cstdlib>
 #include <cstring>
 
 #include "cledb_internal.h"
@@ -25,6 +26,7 @@ extern "C" int cledb_create(int device, cledb_ctx** out) {
     if (device < 0 || device >= ndev) { g_create_error = "cledb_create: device ordinal out of range"; return CLEDB_ERR_ARG; }
     cledb_ctx* ctx = new cledb_ctx();
     ctx->device = device;
+    if (const char* e = std::getenv("CLEDB_B200_PRUNING")) ctx->prune = std::atoi(e) != 0 ? 1 : 0;   // default: on
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = std::string("cledb_create: ") + cudaGetErrorString(e);

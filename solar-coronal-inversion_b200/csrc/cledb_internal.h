@@ -105,7 +105,7 @@ struct cledb_ctx {
     int pixels_per_item = 0;                      // 0 = choose from the pixel count
     int split = 0;
     int dbg = 0;
-    int prune = 0;                                 // layout of databases put from now on
+    int prune = 1;                                 // layout of databases put from now on: 1 = k-d tiles with bounds (exact pruning)
     unsigned long long* d_prune_stats = nullptr;   // [2] evaluated / skipped (pixel, tile) pairs of the last pruned search
     int occ = 0, regs = 0, smem = 0;               // search kernel occupancy facts
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;   // event pairs around the search kernel

@@ -876,34 +876,78 @@ __device__ __forceinline__ float tile_lower_bound(const float4 b0, const float4 
     return lb;
 }
 
-__global__ void __launch_bounds__(128) k_seed(Plan pl, const DbSlot* __restrict__ slots) {
+// Fine sort key of a pixel inside its database slot: the buckets of k_scan (slot, sign class) must stay contiguous and in
+// order, so every class owns the keys [tile0 + q, tile0 + q + ntiles] - one per tile plus one for pixels without seed.
+__device__ __forceinline__ int fine_key(const Plan& pl, const DbSlot& db, int key, const int32_t* seed_of_pixel) {
+    int q = key % kParts;
+    if (pl.mode != CLEDB_MODE_IQUV) {
+        q = 0;
+        for (int i = kParts - 1; i >= 0; --i) if (db.part_cnt[i] > 0) q = i;      // the first class that has entries
+    }
+    int t = seed_of_pixel[q];
+    if (t < 0 || t >= db.part_ntiles[q]) t = db.part_ntiles[q];
+    return (key / kParts) * pl.ftiles + db.part_tile0[q] + q + t;
+}
+
+constexpr int kSeedCap = 2048;          // representative entries a block of k_seed stages in shared memory (40 KB)
+
+__global__ void __launch_bounds__(256) k_seed(Plan pl, const DbSlot* __restrict__ slots) {
+    __shared__ float s_rep[kSeedCap * kNC];
+    __shared__ int s_slot;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pl.npix) return;
-    const int key = pl.key[p];
+    const int key = p < pl.npix ? pl.key[p] : -1;
+    // the representative entries of the block's database into shared memory, if the whole block searches one database
+    // (the usual case) and they fit; otherwise every thread reads them from global memory
+    if (threadIdx.x == 0) s_slot = -1;
+    __syncthreads();
+    if (key >= 0) atomicMax(&s_slot, key / kParts);
+    __syncthreads();
+    const int bslot = s_slot;
+    const bool same = __syncthreads_and(key < 0 || key / kParts == bslot) != 0;
+    bool staged = false;
+    if (same && bslot >= 0) {
+        const DbSlot& db = slots[bslot];
+        const int nt = db.part_tile0[kParts - 1] + db.part_ntiles[kParts - 1];
+        if (nt <= kSeedCap) {
+            const float* bx = db.boxes;
+            for (int i = threadIdx.x; i < nt * kNC; i += blockDim.x) s_rep[i] = __ldg(bx + (size_t)(i / kNC) * 16 + 10 + i % kNC);
+            staged = true;
+        }
+    }
+    __syncthreads();
     if (key < 0) return;
     const DbSlot& db = slots[key / kParts];
     const Rec<CLEDB_PREC_FP32> r = reinterpret_cast<const Rec<CLEDB_PREC_FP32>*>(pl.recs)[p];
-    int sort_tile = -1;
+    int32_t seeds[kParts];
     for (int q = 0; q < kParts; ++q) {
         int best_t = -1;
         const bool mine = pl.mode == CLEDB_MODE_IQUV ? q == key % kParts : db.part_cnt[q] > 0;
         if (mine) {
-            const float4* bx = reinterpret_cast<const float4*>(db.boxes) + (size_t)db.part_tile0[q] * 4;
             float best = CUDART_INF_F;
-            const int nt = db.part_ntiles[q];
+            const int nt = db.part_ntiles[q], t0 = db.part_tile0[q];
+            if (staged) {
 #pragma unroll 4
-            for (int t = 0; t < nt; ++t) {
-                const float4 b2 = __ldg(bx + (size_t)t * 4 + 2), b3 = __ldg(bx + (size_t)t * 4 + 3);
-                const float rep[kNC] = {b2.z, b2.w, b3.x, b3.y, b3.z};
-                const float v = eval_fp32(rep, r.a, r.nb, r.cm);
-                if (v < best) { best = v; best_t = t; }
+                for (int t = 0; t < nt; ++t) {
+                    const float* sp = s_rep + (t0 + t) * kNC;
+                    const float rep[kNC] = {sp[0], sp[1], sp[2], sp[3], sp[4]};
+                    const float v = eval_fp32(rep, r.a, r.nb, r.cm);
+                    if (v < best) { best = v; best_t = t; }
+                }
+            } else {
+                const float4* bx = reinterpret_cast<const float4*>(db.boxes) + (size_t)t0 * 4;
+#pragma unroll 4
+                for (int t = 0; t < nt; ++t) {
+                    const float4 b2 = __ldg(bx + (size_t)t * 4 + 2), b3 = __ldg(bx + (size_t)t * 4 + 3);
+                    const float rep[kNC] = {b2.z, b2.w, b3.x, b3.y, b3.z};
+                    const float v = eval_fp32(rep, r.a, r.nb, r.cm);
+                    if (v < best) { best = v; best_t = t; }
+                }
             }
-            if (sort_tile < 0 && best_t >= 0) sort_tile = db.part_tile0[q] + best_t;
         }
         pl.seed[p * kParts + q] = best_t;
+        seeds[q] = best_t;
     }
-    if (sort_tile < 0) sort_tile = 0;
-    atomicAdd(&pl.fcnt[(key / kParts) * pl.ftiles + sort_tile], 1);
+    atomicAdd(&pl.fcnt[fine_key(pl, db, key, seeds)], 1);
 }
 
 // exclusive scan of the fine counts (one block)
@@ -933,15 +977,7 @@ __global__ void __launch_bounds__(256) k_scatter_fine(Plan pl, const DbSlot* __r
     if (p >= pl.npix) return;
     const int key = pl.key[p];
     if (key < 0) { pl.rank[p] = -1; return; }
-    const DbSlot& db = slots[key / kParts];
-    int sort_tile = -1;
-    for (int q = 0; q < kParts && sort_tile < 0; ++q) {
-        const int t = pl.seed[p * kParts + q];
-        const bool mine = pl.mode == CLEDB_MODE_IQUV ? q == key % kParts : db.part_cnt[q] > 0;
-        if (mine && t >= 0) sort_tile = db.part_tile0[q] + t;
-    }
-    if (sort_tile < 0) sort_tile = 0;
-    const int f = (key / kParts) * pl.ftiles + sort_tile;
+    const int f = fine_key(pl, slots[key / kParts], key, pl.seed + p * kParts);
     const int r = pl.foff[f] + atomicAdd(&pl.fcursor[f], 1);
     pl.order[r] = (int32_t)p;
     pl.rank[p] = r;
@@ -1012,9 +1048,9 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
             lists[i].pos = -1;
         }
         __syncwarp();
-        // Lane L owns pixel L for the seeds.  For the bounds the warp is cut into 32/Pb groups of Pb lanes (Pb = 8, 16 or 32,
+        // Lane L owns pixel L for the seeds.  For the bounds the warp is cut into 32/Pb groups of Pb lanes (Pb = 4, 8, 16 or 32,
         // the smallest that holds the item): lane L bounds pixel L % Pb and takes every (32/Pb)-th tile of a tile group.
-        const int Pb = im.npx <= 8 ? 8 : (im.npx <= 16 ? 16 : 32), lanes_per_pixel = 32 / Pb;
+        const int Pb = im.npx <= 4 ? 4 : (im.npx <= 8 ? 8 : (im.npx <= 16 ? 16 : 32)), lanes_per_pixel = 32 / Pb;
         const int bj = lane % Pb, bg = lane / Pb;
         float pa[kNC], pnb[kNC], pc0 = 0.f;
         int my_seed = -1;
@@ -1193,6 +1229,7 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
             for (int q = 0; q < 4; ++q) {
                 if (Pb <= 16) m[q] |= __shfl_xor_sync(0xffffffffu, m[q], 16);
                 if (Pb <= 8) m[q] |= __shfl_xor_sync(0xffffffffu, m[q], 8);
+                if (Pb <= 4) m[q] |= __shfl_xor_sync(0xffffffffu, m[q], 4);
             }
             if (my_seed >= t0 && my_seed < t0 + 128) {
 #pragma unroll
@@ -1455,8 +1492,9 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     }
     const bool pruned = PREC == CLEDB_PREC_FP32 && pl.seed != nullptr;
     if (pruned) {                                          // one lane per pixel for the bounds, whole sign classes per item
-        // 8, 16 or 32 pixels per item: the largest that still gives every resident warp about four items to pull
-        pl.P = npix >= 128 * wslots ? 32 : (npix >= 64 * wslots ? 16 : 8);
+        // 4, 8 or 32 pixels per item (measured on 128^2 .. 1024^2 maps): small maps need many small items to keep every warp busy to the end, big maps
+        // amortise the per-item work (staging, bounds) over more pixels
+        pl.P = npix >= 512 * wslots ? 32 : (npix >= 48 * wslots ? 8 : 4);
         pl.P = std::min(pl.P, pmax);
         if (ctx->pixels_per_item > 0) pl.P = std::min(std::min(32, pmax), ctx->pixels_per_item);
         pl.split = 1;
@@ -1474,7 +1512,7 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
 
     k_scan<<<1, 1024, 0, st>>>(pl, ctx->d_slots);
     if (pruned) {
-        k_seed<<<(int)((npix + 127) / 128), 128, 0, st>>>(pl, ctx->d_slots);
+        k_seed<<<nb, 256, 0, st>>>(pl, ctx->d_slots);
         k_fscan<<<1, 1024, 0, st>>>(pl, ctx->slots_cap * pl.ftiles);
         k_scatter_fine<<<nb, 256, 0, st>>>(pl, ctx->d_slots);
         ctx->launches += 2;
@@ -1564,7 +1602,7 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
         if (!h.slot.live) continue;
         ++nlive;
         nblocked += h.slot.blocked ? 1 : 0;
-        ftiles = std::max(ftiles, (int)(h.npad / kTile));
+        ftiles = std::max(ftiles, (int)(h.npad / kTile) + kParts);
     }
     if (nblocked != 0 && nblocked != nlive) { ctx->err = "cledb_match: resident databases mix the pruning and the plain layout"; return CLEDB_ERR_ARG; }
     const bool pruned = precision == CLEDB_PREC_FP32 && nblocked > 0;
@@ -1590,7 +1628,7 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
         pl.fcnt = reinterpret_cast<int32_t*>(w + o_fine);
         pl.fcursor = pl.fcnt + nfine;
         pl.foff = pl.fcursor + nfine;
-        pl.ftiles = ftiles;
+        pl.ftiles = ftiles;                          // tiles of the largest database + one key per sign class
         CLEDB_CUDA(ctx, cudaMemsetAsync(pl.fcnt, 0, 2 * nfine * 4, st));
     }
     if (precision == CLEDB_PREC_FP32)

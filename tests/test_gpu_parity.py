@@ -21,9 +21,13 @@ from oracle.compare import check_raw_against_oracle, CHI_RTOL, CHI_ATOL
 
 pytestmark = pytest.mark.gpu
 
-@pytest.fixture(scope='module')
-def ctx():
+@pytest.fixture(scope='module', params=['pruned', 'bruteforce'])
+def ctx(request):
+    """Every parity test runs twice: with exact tile pruning (the library default: k-d tile layout, k_match_pruned) and
+    with pruning off (plain layout, brute-force k_match)."""
     c = native.Context(0)
+    c.pruning_default = request.param == 'pruned'
+    c.set_pruning(c.pruning_default)
     yield c
     c.close()
 
@@ -607,8 +611,8 @@ def test_big_map_is_pipelined_in_chunks(ctx):
 @pytest.mark.parametrize('encoding', [native.ENC_F32, native.ENC_I16])
 @pytest.mark.parametrize('mode', [native.MODE_IQUV, native.MODE_IQUD])
 def test_exact_tile_pruning_changes_nothing(ctx, golden_dir, encoding, mode):
-    """Optional exact tile pruning (cledb_set_pruning): the bound skips most (pixel, tile) pairs and every output bit stays
-    the same as in the plain brute-force search - small databases with engineered edge cases and a mid-size one."""
+    """Exact tile pruning (cledb_set_pruning): the bound skips most (pixel, tile) pairs and every output bit stays the same
+    as in the plain brute-force search - small databases with engineered edge cases and a mid-size one."""
     g, dbs = small_case(golden_dir)
     cases = [(dbs, g['sobs_iquv_b0' if mode == 0 else 'sobs_iqud'].reshape(-1, 8), g['snr'].reshape(-1, 8), g['db_enc'].reshape(-1))]
     mid = synth.make_database(12, 44, ngx=7, nbphi=90, nbtheta=45)
@@ -624,8 +628,42 @@ def test_exact_tile_pruning_changes_nothing(ctx, golden_dir, encoding, mode):
             stats = ctx.pruning_stats()
             for i in range(len(dbl)):
                 ctx.db_drop(i)
-        ctx.set_pruning(False)
+        ctx.set_pruning(ctx.pruning_default)
         for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
             assert np.array_equal(res[False][key], res[True][key], equal_nan=True), key
         assert stats['evaluated'] > 0
     assert stats['skipped'] > 0
+
+
+@pytest.mark.parametrize('mode', [native.MODE_IQUV, native.MODE_IQUD])
+def test_pruning_full_size_properties(ctx, mode):
+    """BASELINE-size database (340 200 entries, 1 330 tiles): pruned and brute-force searches agree bit for bit for clean,
+    very noisy (thresholds so loose that most tiles survive) and rescaled observations, nsearch 1 / 8 / 32, two databases
+    of which one holds duplicated rows (exact chi^2 ties across tiles resolve to the lowest original row)."""
+    db0 = synth.make_database(9, 40)
+    db1 = synth.make_database(3, 12).reshape(-1, 8).copy()
+    db1[1000:5000] = db1[200000:204000]                              # duplicated rows: exact ties
+    obs = synth.make_observation(96, 64, [db0, db1], seed=23, frac_nan=0.02, frac_zero=0.02)
+    sobs, snr, ids = obs['sobs_totrot'].reshape(-1, 8).copy(), obs['snr'].reshape(-1, 8).copy(), obs['db_enc'].reshape(-1).astype(np.int32)
+    rng = np.random.default_rng(5)
+    noisy = sobs.copy()
+    noisy[:2048] += (rng.standard_normal((2048, 8)) * np.abs(sobs[:2048]) * 0.5).astype(np.float32)    # far from every entry
+    snr_low = snr.copy()
+    snr_low[2048:4096] *= 0.01                                      # flat chi^2 landscape
+    res = {}
+    for prune in (False, True):
+        ctx.set_pruning(prune)
+        ctx.db_put(0, db0, native.ENC_I16)
+        ctx.db_put(1, db1, native.ENC_I16)
+        res[prune] = [ctx.match(mode, noisy, snr_low, ids, k) for k in (1, 8, 32)]
+        if prune:
+            stats = ctx.pruning_stats()
+        ctx.db_drop(0)
+        ctx.db_drop(1)
+    ctx.set_pruning(ctx.pruning_default)
+    for a, b in zip(res[False], res[True]):
+        for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
+            assert np.array_equal(a[key], b[key], equal_nan=True), key
+    assert (res[True][1]['status'] == native.PIX_SEARCHED).mean() > 0.8
+    assert stats['skipped'] > stats['evaluated']
+
