@@ -47,6 +47,7 @@ def parse():
     ap.add_argument('--dbg', type=int, default=0, help='kernel timing experiment (results invalid)')
     ap.add_argument('--prune', action='store_true', help='(default) exact tile pruning, the library default')
     ap.add_argument('--no-prune', action='store_true', help='brute-force search as the measured path (the kernel the FP32 roofline is quoted on)')
+    ap.add_argument('--no-prune-pass', action='store_true', help='skip the extra brute-force pass of the default run')
     ap.add_argument('--ppi', type=int, default=0, help='tuning: pixels per warp item (0 = library default)')
     ap.add_argument('--split', type=int, default=0, help='tuning: chunks per candidate list (0 = library default)')
     return ap.parse_args()
@@ -308,7 +309,7 @@ def main():
     # ---- the same maps once more through the brute-force search (pruning off): the kernel that evaluates every
     #      (pixel, entry) pair, quoted against the FP32 peak
     brute = None
-    if pruned and world == 1:
+    if pruned and world == 1 and not args.no_prune_pass:
         for i in range(len(db)):
             ctx.db_drop(i)
         ctx.set_pruning(False)

@@ -19,6 +19,8 @@ Module-level options (not part of the reference surface; the defaults reproduce 
     OPTIONS['strict_topk'] False = reproduce the cledb_partsort index quirk, True = true top-nsearch
     OPTIONS['solution']    'device' = solutions built on the GPU right after the search (cledb_invert; PyCELP-type databases),
                            'host' = NumPy on the raw search result (cledb_b200.solution); both give the same bits
+    OPTIONS['pruning']     True (default) = exact tile pruning in the search (k-d tile layout, bit-identical results, several
+                           times faster), False = brute-force evaluation of every (pixel, entry) pair
     OPTIONS['device']      CUDA ordinal (default: $CLEDB_B200_DEVICE, else $LOCAL_RANK, else 0)
 """
 import os
@@ -32,6 +34,7 @@ OPTIONS = dict(reduced_tie_order=None,      # theta order of an all-equal presor
                precision=int(os.environ.get('CLEDB_B200_PRECISION', '0')),
                strict_topk=False,
                solution=os.environ.get('CLEDB_B200_SOLUTION', 'device'),
+               pruning=os.environ.get('CLEDB_B200_PRUNING', '1') != '0',
                device=int(os.environ.get('CLEDB_B200_DEVICE', os.environ.get('LOCAL_RANK', '0'))))
 
 
@@ -42,6 +45,7 @@ class _Resident:
     def __init__(self):
         self.ids = {}          # fingerprint -> db_id
         self.next_id = 0
+        self.pruning = None    # tile layout of the resident databases
 
     @staticmethod
     def fingerprint(arr, encoding):
@@ -84,8 +88,11 @@ def _upload(database, used):
     ctx = _context()
     res = _resident.setdefault(OPTIONS['device'], _Resident())
     encs = {k[2] for k in res.ids}
-    if encs and encs != {OPTIONS['dbencoding']}:
-        res.clear(ctx)                      # one encoding at a time lives on the device
+    want = bool(OPTIONS['pruning'])
+    if (encs and encs != {OPTIONS['dbencoding']}) or (res.ids and res.pruning != want):
+        res.clear(ctx)                      # one encoding and one tile layout at a time live on the device
+    ctx.set_pruning(want)
+    res.pruning = want
     return ctx, {int(k): res.ensure(ctx, database[int(k)], OPTIONS['dbencoding']) for k in used}
 
 

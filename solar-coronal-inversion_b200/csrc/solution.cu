@@ -330,9 +330,14 @@ extern "C" int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npi
     g.cos_bphi = tab + g.nbphi;
     g.sin_btheta = tab + 2 * g.nbphi;
     g.cos_btheta = tab + 2 * g.nbphi + g.nbtheta;
-    // Big maps go through in chunks of 256 Ki pixels: the search of chunk c+1 runs while the finished maps of chunk c
+    // Big maps go through in chunks of 128 Ki pixels: the search of chunk c+1 runs while the finished maps of chunk c
     // travel to the host on a second stream (608 B per pixel at nsearch 8 is a quarter of the search time on PCIe 5).
-    const int64_t chunk = (npix > 3 * (int64_t)(1 << 17) && !getenv("CLEDB_B200_NO_CHUNK")) ? (int64_t)(1 << 18) : npix;
+    int64_t chunk = npix;
+    if (!getenv("CLEDB_B200_NO_CHUNK")) {
+        if (npix >= (int64_t)1 << 18) chunk = (int64_t)1 << 17;      // measured on 512^2 and 1024^2 maps; smaller maps lose more
+                                                                      // to the per-chunk host round trip than the overlap gains
+        if (const char* e = getenv("CLEDB_B200_CHUNK")) chunk = std::max<int64_t>(1024, std::atoll(e));
+    }
     if (chunk < npix && !ctx->copy_stream) CLEDB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int64_t c0 = 0; c0 < npix; c0 += chunk) {
         const int64_t nc = std::min(chunk, npix - c0);

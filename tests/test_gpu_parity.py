@@ -589,10 +589,10 @@ def test_large_items_and_odd_tile_counts(ctx, encoding, mode):
 
 
 def test_big_map_is_pipelined_in_chunks(ctx):
-    """cledb_invert sends maps above 384 Ki pixels through in 256 Ki-pixel chunks (search of one chunk overlapping the
+    """cledb_invert sends maps of 256 Ki pixels and more through in 128 Ki-pixel chunks (search of one chunk overlapping the
     device-to-host copy of the previous one): same bits as inverting the pieces one by one."""
     db = synth.make_database(8, 39, ngx=3, nbphi=24, nbtheta=12)
-    nx, ny = 700, 600                                        # 420 000 pixels: two chunks
+    nx, ny = 700, 600                                        # 420 000 pixels: four chunks
     obs = synth.make_observation(nx, ny, [db], seed=5)
     hdr = synth.make_dbhdr(3, 24, 12)
     ctx.db_put(0, db, native.ENC_I16)
@@ -600,8 +600,8 @@ def test_big_map_is_pipelined_in_chunks(ctx):
     y, d, a = obs['yobs'].reshape(-1), obs['dobs'].reshape(-1), obs['aobs'].reshape(-1)
     z = np.zeros(nx * ny, np.int32)
     inv, sf, st = ctx.invert(native.MODE_IQUV, s, n, z, 8, y, d, a, None, hdr, 1000, 0)
-    cut = 1 << 18
-    for lo, hi in ((0, cut), (cut, nx * ny)):
+    cut = 1 << 17
+    for lo, hi in ((0, cut), (cut, 3 * cut), (3 * cut, nx * ny)):
         i2, s2, t2 = ctx.invert(native.MODE_IQUV, s[lo:hi], n[lo:hi], z[lo:hi], 8, y[lo:hi], d[lo:hi], a[lo:hi], None, hdr, 1000, 0)
         assert same(inv[lo:hi], i2) and same(sf[lo:hi], s2) and same(st[lo:hi], t2)
     assert (st == native.PIX_SEARCHED).mean() > 0.8
