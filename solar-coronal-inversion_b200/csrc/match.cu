@@ -578,18 +578,76 @@ __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, float c0f, Cand<PREC>
     }
 }
 
+// ---- selection for the pruned search ------------------------------------------------------------------------------------
+// rank_select: new list = the k smallest of (current list) + (the lane's entries with v[e] < inf), when they fit into one warp
+// (<= 32 candidates) and no two candidates have exactly the same value: every candidate goes to one lane, a lane's rank is
+// the number of smaller candidates, rank r < k is list element r.  Returns false (nothing changed) otherwise; the callers
+// then take the paths that know how to break exact ties by original row.
+template <int ENC>
+__device__ __forceinline__ bool rank_select(Rec<CLEDB_PREC_FP32>* rec, float c0f, Cand<CLEDB_PREC_FP32>* list, const float (&v)[kEPL],
+                                            int base, int k, int lane, Cand<CLEDB_PREC_FP32>* scratch) {
+    uint32_t em = 0;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) em |= (v[e] < CUDART_INF_F ? 1u : 0u) << e;
+    const int cnt = __popc(em);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int H = __shfl_sync(0xffffffffu, incl, 31);
+    float cv = CUDART_INF_F;
+    int cp = -1;
+    if (lane < k) { cv = list[lane].v; cp = list[lane].pos; }
+    const int L = __popc(__ballot_sync(0xffffffffu, cp >= 0));          // the filled slots are a prefix of the sorted list
+    const int n = L + H;
+    if (n > 32) return false;
+    int o = incl - cnt;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e)
+        if ((em >> e) & 1u) {
+            scratch[o].v = v[e];
+            scratch[o].pos = base + pos_in_tile<ENC>(lane, e);
+            ++o;
+        }
+    __syncwarp();
+    if (lane >= L) {
+        cv = CUDART_INF_F;
+        cp = -1;
+        if (lane < n) { cv = scratch[lane - L].v; cp = scratch[lane - L].pos; }
+    }
+    int rank = 0;
+    bool tie = false;
+    for (int i = 0; i < n; ++i) {
+        const float vi = __shfl_sync(0xffffffffu, cv, i);
+        rank += (vi < cv || (vi == cv && i < lane)) ? 1 : 0;
+        tie |= vi == cv && i != lane;
+    }
+    if (__any_sync(0xffffffffu, tie && lane < n)) return false;
+    __syncwarp();
+    if (lane < n && rank < k) {
+        list[rank].v = cv;
+        list[rank].pos = cp;
+        if (rank == k - 1) set_tau<CLEDB_PREC_FP32>(rec, c0f, cv);
+    }
+    __syncwarp();
+    return true;
+}
+
 // slow_pixel for tiles that may hold MANY entries under the threshold (the neighbours of a pixel's seed tile in the pruned
-// search): candidates go in best first, so the threshold drops to the tile's k-th best after at most k insertions and the
-// remaining hits fall out by comparison instead of being inserted one after the other.  Same list, same tie rule.
+// search): one rank_select when it applies; otherwise candidates go in best first, so the threshold drops to the tile's k-th
+// best after at most k insertions and the remaining hits fall out by comparison.  Same list, same tie rule as slow_pixel.
 template <int ENC>
 __device__ __forceinline__ void merge_pixel(Rec<CLEDB_PREC_FP32>* rec, float c0f, Cand<CLEDB_PREC_FP32>* list, const float (&d)[kEPL][kNC],
                                             const float (&scale)[kNC], int base, int cnt_end, const int32_t* __restrict__ perm,
-                                            int k, int lane) {
+                                            int k, int lane, Cand<CLEDB_PREC_FP32>* scratch) {
     float v[kEPL], tau;
     eval_pixel<ENC, CLEDB_PREC_FP32>(rec, c0f, d, scale, v, tau);
 #pragma unroll
     for (int e = 0; e < kEPL; ++e)
         if (!(v[e] <= tau) || base + pos_in_tile<ENC>(lane, e) >= cnt_end) v[e] = CUDART_INF_F;      // not a hit (NaN, padding)
+    if (rank_select<ENC>(rec, c0f, list, v, base, k, lane, scratch)) return;
     for (;;) {
         float lm = v[0];
         int le = 0;
@@ -597,10 +655,7 @@ __device__ __forceinline__ void merge_pixel(Rec<CLEDB_PREC_FP32>* rec, float c0f
         for (int e = 1; e < kEPL; ++e)
             if (v[e] < lm) { lm = v[e]; le = e; }
         const float gm = warp_min(lm);
-        if (!(gm < CUDART_INF_F)) {
-            // hits of value +inf (threshold still +inf): leave them to the plain path
-            break;
-        }
+        if (!(gm < CUDART_INF_F)) break;
         const int src = __ffs(__ballot_sync(0xffffffffu, lm == gm)) - 1;
         const int es = __shfl_sync(0xffffffffu, le, src);
         list_insert<CLEDB_PREC_FP32>(list, rec, c0f, k, gm, base + pos_in_tile<ENC>(src, es), perm, lane);
@@ -609,6 +664,33 @@ __device__ __forceinline__ void merge_pixel(Rec<CLEDB_PREC_FP32>* rec, float c0f
         for (int e = 0; e < kEPL; ++e)
             if ((lane == src && e == es) || !(v[e] <= tau)) v[e] = CUDART_INF_F;
     }
+}
+
+// a pixel's first tile in the pruned search (empty list): a threshold T with at least k entries under it - the k-th smallest
+// of the 32 lane minima - then one rank_select over the entries <= T.  Returns false if that does not apply (fewer than k
+// lanes hold a finite value, too many candidates, exact ties): the caller runs bootstrap_pixel.
+template <int ENC>
+__device__ __forceinline__ bool seed_pixel(Rec<CLEDB_PREC_FP32>* rec, float c0f, Cand<CLEDB_PREC_FP32>* list, const float (&d)[kEPL][kNC],
+                                           const float (&scale)[kNC], int base, int cnt_end, int k, int lane,
+                                           Cand<CLEDB_PREC_FP32>* scratch) {
+    float v[kEPL], tau_unused;
+    eval_pixel<ENC, CLEDB_PREC_FP32>(rec, c0f, d, scale, v, tau_unused);
+    float lm = CUDART_INF_F;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) {
+        if (!(v[e] < CUDART_INF_F) || base + pos_in_tile<ENC>(lane, e) >= cnt_end) v[e] = CUDART_INF_F;   // NaN, inf, padding
+        lm = fminf(lm, v[e]);
+    }
+    float T = CUDART_INF_F;
+    for (int r = 0; r < k; ++r) {
+        T = warp_min(lm);
+        if (lm == T) lm = CUDART_INF_F;
+    }
+    if (!(T < CUDART_INF_F)) return false;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e)
+        if (!(v[e] <= T)) v[e] = CUDART_INF_F;
+    return rank_select<ENC>(rec, c0f, list, v, base, k, lane, scratch);
 }
 
 // first tile of an item: exact top-k of its 256 entries by k rounds of warp-min selection
@@ -989,10 +1071,10 @@ template <int ENC> struct PCfg {        // shared memory of one warp of the prun
     static constexpr int kRecBytes = (32 + 1) * (int)sizeof(Rec<CLEDB_PREC_FP32>);
     static constexpr int kListBytes = kListCap * (int)sizeof(Cand<CLEDB_PREC_FP32>);
 };
-constexpr int kTileListCap = 192;       // tile list of a warp: flushed at >= 64 entries, one bound chunk adds <= 128
+constexpr int kTileListCap = 96;        // tile list of a warp: evaluated at >= 64 entries, one group adds <= 16
 
 template <int ENC> __host__ __device__ constexpr int pruned_warp_bytes() {
-    return (PCfg<ENC>::kTB + PCfg<ENC>::kRecBytes + PCfg<ENC>::kListBytes + 16 + 128 + (2 * kTileListCap + 32) * 4 + 127) / 128 * 128;
+    return (PCfg<ENC>::kTB + PCfg<ENC>::kRecBytes + PCfg<ENC>::kListBytes + 16 + 128 + (2 * kTileListCap + 32) * 4 + 32 * 8 + 127) / 128 * 128;
 }
 
 template <int ENC>
@@ -1014,6 +1096,7 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
     int32_t* tlist = reinterpret_cast<int32_t*>(c0s + 32);                                   // [kTileListCap] tiles to evaluate
     uint32_t* tmask = reinterpret_cast<uint32_t*>(tlist + kTileListCap);                     // [kTileListCap] the pixels that need each of them
     int32_t* slist = tlist + 2 * kTileListCap;                                               // [32] the item's seed tiles
+    CandT* scratch = reinterpret_cast<CandT*>(slist + 32);                                   // [32] candidates of one selection
     const int k = pl.k;
     uint32_t phase = 0;
     unsigned long long n_eval = 0, n_all = 0;
@@ -1128,7 +1211,8 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
                 while (own) {
                     const int j = __ffs(own) - 1;
                     own &= own - 1;
-                    bootstrap_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, rows, k, lane);
+                    if (!seed_pixel<ENC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, k, lane, scratch))
+                        bootstrap_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, rows, k, lane);
                 }
             }
             __syncwarp();
@@ -1165,7 +1249,7 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
                 while (any) {
                     const int jj = __ffs(any) - 1;
                     any &= any - 1;
-                    merge_pixel<ENC>(recs + jj, c0s[jj], lists + jj * k, dd, scale, base, im.cnt_end, db.perm, k, lane);
+                    merge_pixel<ENC>(recs + jj, c0s[jj], lists + jj * k, dd, scale, base, im.cnt_end, db.perm, k, lane, scratch);
                 }
             } else {
                 while (set) {
@@ -1197,59 +1281,69 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
             __syncwarp();
         };
 
-        // ---- bounds in chunks of 128 tiles against the thresholds as they are by then (they only tighten: a superset of the
-        //      pairs that matter)
-        int nu = 0;
+        // ---- bounds against the thresholds as they are by then (they only tighten: a superset of the pairs that matter).
+        //      Two levels: groups of 16 tiles first, 64 groups at a time and the lanes of a pixel taking them in turns; then
+        //      the tiles of the groups some pixel keeps, again in turns.  Listed tiles are evaluated whenever 64 have piled
+        //      up, which tightens the thresholds for the groups still to come.
         const uint32_t low = Pb == 32 ? 0xffffffffu : ((1u << Pb) - 1u);
-        for (int t0 = 0; t0 < im.ntiles; t0 += 128) {
-            const int nt = min(128, im.ntiles - t0);
-            const float tau = bj < im.npx ? recs[bj].tau : -CUDART_INF_F;        // a lane without pixel needs nothing
-            uint32_t m[4] = {0u, 0u, 0u, 0u};
-            // two levels: the bound of a group of 16 tiles first, the tiles of a group only if the group survives; the
-            // lanes that share a pixel take the tiles of a group in turns
-            const float4* sb = sboxes + (size_t)(t0 / kSuper) * 3;
-#pragma unroll
-            for (int g = 0; g < 128 / kSuper; ++g) {
-                if (g * kSuper < nt) {
-                    const float lbg = tile_lower_bound(__ldg(sb + g * 3), __ldg(sb + g * 3 + 1), __ldg(sb + g * 3 + 2), pa, pnb, pc0);
-                    if (!(lbg > tau)) {
-                        const int ng = min(kSuper, nt - g * kSuper);
-                        const float4* bx = boxes + (size_t)(t0 + g * kSuper) * 4;
-                        uint32_t mg = 0;
-                        for (int i = bg; i < ng; i += lanes_per_pixel) {
-                            const float lb = tile_lower_bound(__ldg(bx + i * 4), __ldg(bx + i * 4 + 1), __ldg(bx + i * 4 + 2), pa, pnb, pc0);
-                            mg |= (!(lb > tau) ? 1u : 0u) << i;                    // a NaN bound keeps the tile
+        const int ngroups = (im.ntiles + kSuper - 1) / kSuper;
+        int nu = 0, g0 = -64;
+        uint32_t gm0 = 0u, gm1 = 0u, gu0 = 0u, gu1 = 0u;             // surviving groups of the 64: my pixel's, any pixel's
+        float tau = bj < im.npx ? recs[bj].tau : -CUDART_INF_F;      // a lane without pixel needs nothing
+        for (;;) {
+            while (nu < 64) {
+                if ((gu0 | gu1) == 0u) {                             // next 64 groups
+                    g0 += 64;
+                    if (g0 >= ngroups) break;
+                    const int ng = min(64, ngroups - g0);
+                    const float4* sb = sboxes + (size_t)g0 * 3;
+                    gm0 = gm1 = 0u;
+                    for (int gi = bg; gi < ng; gi += lanes_per_pixel) {
+                        const float lbg = tile_lower_bound(__ldg(sb + gi * 3), __ldg(sb + gi * 3 + 1), __ldg(sb + gi * 3 + 2), pa, pnb, pc0);
+                        if (!(lbg > tau)) {                                           // a NaN bound keeps the group
+                            if (gi < 32) gm0 |= 1u << gi; else gm1 |= 1u << (gi - 32);
                         }
-                        m[g / 2] |= mg << ((g & 1) * kSuper);
+                    }
+                    if (Pb <= 16) { gm0 |= __shfl_xor_sync(0xffffffffu, gm0, 16); gm1 |= __shfl_xor_sync(0xffffffffu, gm1, 16); }
+                    if (Pb <= 8) { gm0 |= __shfl_xor_sync(0xffffffffu, gm0, 8); gm1 |= __shfl_xor_sync(0xffffffffu, gm1, 8); }
+                    if (Pb <= 4) { gm0 |= __shfl_xor_sync(0xffffffffu, gm0, 4); gm1 |= __shfl_xor_sync(0xffffffffu, gm1, 4); }
+                    gu0 = __reduce_or_sync(0xffffffffu, gm0);
+                    gu1 = __reduce_or_sync(0xffffffffu, gm1);
+                    continue;
+                }
+                const bool hi = gu0 == 0u;
+                uint32_t cur = hi ? gu1 : gu0;
+                const int gb = __ffs(cur) - 1;
+                cur &= cur - 1;
+                if (hi) gu1 = cur; else gu0 = cur;
+                const int t0 = (g0 + (hi ? 32 : 0) + gb) * kSuper, nt = min(kSuper, im.ntiles - t0);
+                uint32_t mg = 0;
+                if (((hi ? gm1 : gm0) >> gb) & 1u) {
+                    const float4* bx = boxes + (size_t)t0 * 4;
+                    for (int i = bg; i < nt; i += lanes_per_pixel) {
+                        const float lb = tile_lower_bound(__ldg(bx + i * 4), __ldg(bx + i * 4 + 1), __ldg(bx + i * 4 + 2), pa, pnb, pc0);
+                        mg |= (!(lb > tau) ? 1u : 0u) << i;                          // a NaN bound keeps the tile
                     }
                 }
-            }
-            // the lanes of a pixel put their shares together; the pixel's own seed tile is in its list already
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (Pb <= 16) m[q] |= __shfl_xor_sync(0xffffffffu, m[q], 16);
-                if (Pb <= 8) m[q] |= __shfl_xor_sync(0xffffffffu, m[q], 8);
-                if (Pb <= 4) m[q] |= __shfl_xor_sync(0xffffffffu, m[q], 4);
-            }
-            if (my_seed >= t0 && my_seed < t0 + 128) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) if (((my_seed - t0) >> 5) == q) m[q] &= ~(1u << ((my_seed - t0) & 31));
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t w = __reduce_or_sync(0xffffffffu, lane < Pb ? m[q] : 0u);
+                if (Pb <= 16) mg |= __shfl_xor_sync(0xffffffffu, mg, 16);          // the lanes of a pixel put their shares together
+                if (Pb <= 8) mg |= __shfl_xor_sync(0xffffffffu, mg, 8);
+                if (Pb <= 4) mg |= __shfl_xor_sync(0xffffffffu, mg, 4);
+                if (my_seed >= t0 && my_seed < t0 + kSuper) mg &= ~(1u << (my_seed - t0));   // the own seed tile is in the list already
+                uint32_t w = __reduce_or_sync(0xffffffffu, lane < Pb ? mg : 0u);
                 while (w) {
                     const int b = __ffs(w) - 1;
                     w &= w - 1;
-                    const uint32_t set = __ballot_sync(0xffffffffu, (m[q] >> b) & 1u) & low;
-                    if (lane == 0) { tlist[nu] = t0 + q * 32 + b; tmask[nu] = set; }
+                    const uint32_t set = __ballot_sync(0xffffffffu, (mg >> b) & 1u) & low;
+                    if (lane == 0) { tlist[nu] = t0 + b; tmask[nu] = set; }
                     ++nu;
                 }
             }
+            if (nu == 0) break;
             __syncwarp();
-            if (nu < 64 && t0 + 128 < im.ntiles) continue;
             run_tiles(nu);
             nu = 0;
+            if (g0 >= ngroups) break;
+            tau = bj < im.npx ? recs[bj].tau : -CUDART_INF_F;
         }
         __syncwarp();
         for (int i = lane; i < im.npx * k; i += 32) gout[i] = lists[i];
