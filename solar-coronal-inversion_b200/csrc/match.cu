@@ -973,10 +973,13 @@ __device__ __forceinline__ int fine_key(const Plan& pl, const DbSlot& db, int ke
 
 constexpr int kSeedCap = 2048;          // representative entries a block of k_seed stages in shared memory (40 KB)
 
+constexpr int kSeedLanes = 4;           // threads that share a pixel in k_seed (each takes every 4th tile)
+
 __global__ void __launch_bounds__(256) k_seed(Plan pl, const DbSlot* __restrict__ slots) {
     __shared__ float s_rep[kSeedCap * kNC];
     __shared__ int s_slot;
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kSeedLanes;
+    const int sub = threadIdx.x % kSeedLanes;
     const int key = p < pl.npix ? pl.key[p] : -1;
     // the representative entries of the block's database into shared memory, if the whole block searches one database
     // (the usual case) and they fit; otherwise every thread reads them from global memory
@@ -997,19 +1000,21 @@ __global__ void __launch_bounds__(256) k_seed(Plan pl, const DbSlot* __restrict_
         }
     }
     __syncthreads();
+    // the kSeedLanes threads of a pixel sit in one warp and leave together (shuffles below)
     if (key < 0) return;
     const DbSlot& db = slots[key / kParts];
     const Rec<CLEDB_PREC_FP32> r = reinterpret_cast<const Rec<CLEDB_PREC_FP32>*>(pl.recs)[p];
+    const uint32_t quad = 0xfu << ((threadIdx.x & 31) & ~(kSeedLanes - 1));
     int32_t seeds[kParts];
     for (int q = 0; q < kParts; ++q) {
-        int best_t = -1;
+        int best_t = 0x7fffffff;
         const bool mine = pl.mode == CLEDB_MODE_IQUV ? q == key % kParts : db.part_cnt[q] > 0;
         if (mine) {
             float best = CUDART_INF_F;
             const int nt = db.part_ntiles[q], t0 = db.part_tile0[q];
             if (staged) {
 #pragma unroll 4
-                for (int t = 0; t < nt; ++t) {
+                for (int t = sub; t < nt; t += kSeedLanes) {
                     const float* sp = s_rep + (t0 + t) * kNC;
                     const float rep[kNC] = {sp[0], sp[1], sp[2], sp[3], sp[4]};
                     const float v = eval_fp32(rep, r.a, r.nb, r.cm);
@@ -1018,18 +1023,25 @@ __global__ void __launch_bounds__(256) k_seed(Plan pl, const DbSlot* __restrict_
             } else {
                 const float4* bx = reinterpret_cast<const float4*>(db.boxes) + (size_t)t0 * 4;
 #pragma unroll 4
-                for (int t = 0; t < nt; ++t) {
+                for (int t = sub; t < nt; t += kSeedLanes) {
                     const float4 b2 = __ldg(bx + (size_t)t * 4 + 2), b3 = __ldg(bx + (size_t)t * 4 + 3);
                     const float rep[kNC] = {b2.z, b2.w, b3.x, b3.y, b3.z};
                     const float v = eval_fp32(rep, r.a, r.nb, r.cm);
                     if (v < best) { best = v; best_t = t; }
                 }
             }
+#pragma unroll
+            for (int o = 1; o < kSeedLanes; o <<= 1) {                  // best of the pixel's threads, lowest tile on ties
+                const float ov = __shfl_xor_sync(quad, best, o);
+                const int ot = __shfl_xor_sync(quad, best_t, o);
+                if (ov < best || (ov == best && ot < best_t)) { best = ov; best_t = ot; }
+            }
         }
-        pl.seed[p * kParts + q] = best_t;
+        if (best_t == 0x7fffffff) best_t = -1;
         seeds[q] = best_t;
+        if (sub == 0) pl.seed[p * kParts + q] = best_t;
     }
-    atomicAdd(&pl.fcnt[fine_key(pl, db, key, seeds)], 1);
+    if (sub == 0) atomicAdd(&pl.fcnt[fine_key(pl, db, key, seeds)], 1);
 }
 
 // exclusive scan of the fine counts (one block)
@@ -1200,19 +1212,20 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
                     tma_load_1d(stages, gt + (size_t)slist[i + 1] * TB, TB, &bars[0]);
                 }
                 const int base = (im.tile0 + ts) * kTile;
-                int rows[kEPL];
-#pragma unroll
-                for (int e = 0; e < kEPL; ++e) {
-                    const int pos = base + pos_in_tile<ENC>(lane, e);
-                    rows[e] = pos < im.cnt_end ? db.perm[pos] : 0x7fffffff;
-                }
                 uint32_t own = __ballot_sync(0xffffffffu, my_seed == ts);
                 n_eval += __popc(own);
                 while (own) {
                     const int j = __ffs(own) - 1;
                     own &= own - 1;
-                    if (!seed_pixel<ENC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, k, lane, scratch))
+                    if (!seed_pixel<ENC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, k, lane, scratch)) {
+                        int rows[kEPL];                   // original rows of my 8 entries: the tie-break of the exact selection
+#pragma unroll
+                        for (int e = 0; e < kEPL; ++e) {
+                            const int pos = base + pos_in_tile<ENC>(lane, e);
+                            rows[e] = pos < im.cnt_end ? db.perm[pos] : 0x7fffffff;
+                        }
                         bootstrap_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, rows, k, lane);
+                    }
                 }
             }
             __syncwarp();
@@ -1606,7 +1619,7 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
 
     k_scan<<<1, 1024, 0, st>>>(pl, ctx->d_slots);
     if (pruned) {
-        k_seed<<<nb, 256, 0, st>>>(pl, ctx->d_slots);
+        k_seed<<<(int)((npix * kSeedLanes + 255) / 256), 256, 0, st>>>(pl, ctx->d_slots);
         k_fscan<<<1, 1024, 0, st>>>(pl, ctx->slots_cap * pl.ftiles);
         k_scatter_fine<<<nb, 256, 0, st>>>(pl, ctx->d_slots);
         ctx->launches += 2;
