@@ -641,9 +641,11 @@ def test_pruning_full_size_properties(ctx, mode):
     very noisy (thresholds so loose that most tiles survive) and rescaled observations, nsearch 1 / 8 / 32, two databases
     of which one holds duplicated rows (exact chi^2 ties across tiles resolve to the lowest original row)."""
     db0 = synth.make_database(9, 40)
-    db1 = synth.make_database(3, 12).reshape(-1, 8).copy()
-    db1[1000:5000] = db1[200000:204000]                              # duplicated rows: exact ties
-    obs = synth.make_observation(96, 64, [db0, db1], seed=23, frac_nan=0.02, frac_zero=0.02)
+    db1 = synth.make_database(3, 12).copy()
+    flat1 = db1.reshape(-1, 8)
+    flat1[1000:5000] = flat1[200000:204000]                          # duplicated rows: exact ties
+    which = (np.arange(96 * 64).reshape(96, 64) // 7 % 2).astype(np.int32)           # both databases all over the map
+    obs = synth.make_observation(96, 64, [db0, db1], db_enc=which, seed=23, frac_nan=0.02, frac_zero=0.02)
     sobs, snr, ids = obs['sobs_totrot'].reshape(-1, 8).copy(), obs['snr'].reshape(-1, 8).copy(), obs['db_enc'].reshape(-1).astype(np.int32)
     rng = np.random.default_rng(5)
     noisy = sobs.copy()
@@ -666,4 +668,28 @@ def test_pruning_full_size_properties(ctx, mode):
             assert np.array_equal(a[key], b[key], equal_nan=True), key
     assert (res[True][1]['status'] == native.PIX_SEARCHED).mean() > 0.8
     assert stats['skipped'] > stats['evaluated']
+
+
+def test_pruning_large_and_tiny_databases(ctx):
+    """A database with more tiles than k_seed stages in shared memory (583 200 entries, 2 280 tiles: representatives are
+    read from global memory) next to one whose sign classes hold fewer entries than nsearch (the seed tile cannot fill the
+    list: exact path over every tile): pruned == brute force, both modes."""
+    big = synth.make_database(6, 20, ngx=36, nbphi=180, nbtheta=90)
+    tiny = synth.make_database(4, 11, ngx=1, nbphi=3, nbtheta=3)           # 9 entries
+    which = (np.arange(48 * 40).reshape(48, 40) % 5 == 0).astype(np.int32)            # every fifth pixel searches the tiny one
+    obs = synth.make_observation(48, 40, [big, tiny], db_enc=which, seed=41, frac_nan=0.02, frac_zero=0.02)
+    sobs, snr, ids = obs['sobs_totrot'].reshape(-1, 8), obs['snr'].reshape(-1, 8), obs['db_enc'].reshape(-1).astype(np.int32)
+    for mode in (native.MODE_IQUV, native.MODE_IQUD):
+        res = {}
+        for prune in (False, True):
+            ctx.set_pruning(prune)
+            ctx.db_put(0, big, native.ENC_I16)
+            ctx.db_put(1, tiny, native.ENC_I16)
+            res[prune] = ctx.match(mode, sobs, snr, ids, 8)
+            ctx.db_drop(0)
+            ctx.db_drop(1)
+        ctx.set_pruning(ctx.pruning_default)
+        for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
+            assert np.array_equal(res[False][key], res[True][key], equal_nan=True), (mode, key)
+        assert (res[True]['status'] == native.PIX_SEARCHED).mean() > 0.8
 
