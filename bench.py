@@ -212,14 +212,14 @@ def main():
     snr_h = torch.from_numpy(obs['snr'].reshape(-1, 8)).pin_memory()
     id_h = torch.from_numpy(np.ascontiguousarray(obs['db_enc'].reshape(-1).astype(np.int32))).pin_memory()
     sobs_d, snr_d, id_d = sobs_h.to(dev), snr_h.to(dev), id_h.to(dev)
-    idx_d = torch.empty((npix, k), dtype=torch.int32, device=dev)
-    chi_d = torch.empty((npix, k), dtype=torch.float32, device=dev)
+    maps_d = torch.empty((2, npix, k), dtype=torch.int32, device=dev)      # idx and chi side by side: one collective gathers both
+    idx_d = maps_d[0]
+    chi_d = maps_d[1].view(torch.float32)
     kpos_d = torch.empty((npix, k), dtype=torch.int32, device=dev)
     rows_d = torch.empty((npix, k, 8), dtype=torch.float32, device=dev)
     st_d = torch.empty(npix, dtype=torch.uint8, device=dev)
     nc_d = torch.empty(npix, dtype=torch.int64, device=dev)
-    gather_idx = [torch.empty_like(idx_d) for _ in range(world)] if world > 1 else None
-    gather_chi = [torch.empty_like(chi_d) for _ in range(world)] if world > 1 else None
+    gathered = torch.empty((world, 2, npix, k), dtype=torch.int32, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
     stream = torch.cuda.Stream(device=dev)      # an explicit stream: the library and the CUDA events share it
@@ -229,8 +229,7 @@ def main():
         ctx.match_dev(mode, npix, sobs_d.data_ptr(), snr_d.data_ptr(), id_d.data_ptr(), k, idx_d.data_ptr(), chi_d.data_ptr(),
                       None, kpos_d.data_ptr(), rows_d.data_ptr(), st_d.data_ptr(), nc_d.data_ptr(), stream.cuda_stream)
         if world > 1:                       # the only collective of the path: gather the result maps
-            dist.all_gather(gather_idx, idx_d)
-            dist.all_gather(gather_chi, chi_d)
+            dist.all_gather_into_tensor(gathered, maps_d)
 
     for _ in range(max(args.warmup, 3)):
         step()
