@@ -1,1 +1,1 @@
-python -m pytest tests -m gpu -x -q -k "pruning" 2>&1 | tail -5
+python -m pytest tests -m gpu -x -q -k "randomised" 2>&1 | tail -8

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "cledb_internal.h"
 
@@ -158,6 +159,39 @@ extern "C" int cledb_db_drop(cledb_ctx* ctx, int db_id) {
     return CLEDB_OK;
 }
 
+// k-d partition of ids[lo, hi) into leaves of kTile entries (the last one may be short): median split at a multiple of the
+// tile size along the component with the widest weighted extent; the upper levels run their halves on separate threads.
+static void kd_split(const float* db, int32_t* ids, int64_t lo, int64_t hi, int depth) {
+    const int64_t nt = (hi - lo + kTile - 1) / kTile;
+    if (nt <= 1) return;
+    const float wdim[kNC] = {1.f, 1.f, 0.1f, 1.f, 1.f};                   // sqrt(wtg_fact) of the components, CLEDB_PROC.py:981
+    int dim = 0;
+    float widest = -1.f;
+    for (int c = 0; c < kNC; ++c) {
+        const int oc = chi_comp(c);
+        float mn = INFINITY, mx = -INFINITY;
+        for (int64_t j = lo; j < hi; ++j) { const float v = db[(int64_t)ids[j] * 8 + oc]; mn = std::min(mn, v); mx = std::max(mx, v); }
+        const float ext = (mx - mn) * wdim[c];
+        if (ext > widest) { widest = ext; dim = c; }
+    }
+    const int oc = chi_comp(dim);
+    const int64_t mid = lo + (nt / 2) * kTile;
+    std::nth_element(ids + lo, ids + mid, ids + hi, [&](int32_t x, int32_t y) {
+        float vx = db[(int64_t)x * 8 + oc], vy = db[(int64_t)y * 8 + oc];
+        if (std::isnan(vx)) vx = INFINITY;                                 // keep the order strict and weak
+        if (std::isnan(vy)) vy = INFINITY;
+        return vx < vy || (vx == vy && x < y);
+    });
+    if (depth < 3 && hi - lo > 32768) {
+        std::thread left(kd_split, db, ids, lo, mid, depth + 1);
+        kd_split(db, ids, mid, hi, depth + 1);
+        left.join();
+    } else {
+        kd_split(db, ids, lo, mid, depth + 1);
+        kd_split(db, ids, mid, hi, depth + 1);
+    }
+}
+
 extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t n, int encoding) {
     if (!ctx) return CLEDB_ERR_ARG;
     if (!db || n <= 0 || db_id < 0 || db_id > (1 << 24)) { ctx->err = "cledb_db_put: bad argument"; return CLEDB_ERR_ARG; }
@@ -271,40 +305,16 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
     std::vector<int32_t> kdpos;
     if (blocked) {
         kdpos.assign(n, -1);
-        const float wdim[kNC] = {1.f, 1.f, 0.1f, 1.f, 1.f};               // sqrt(wtg_fact) of the components, CLEDB_PROC.py:981
-        std::vector<int32_t> ids;
+        std::vector<int32_t> ids[kParts];
+        std::vector<std::thread> workers;
         for (int q = 0; q < kParts; ++q) {
-            ids.clear();
-            ids.reserve(cnt[q]);
-            for (int64_t i = 0; i < n; ++i) if (cls[i] == q) ids.push_back((int32_t)i);
-            std::vector<std::pair<int64_t, int64_t>> todo{{0, (int64_t)ids.size()}};
-            while (!todo.empty()) {
-                const auto [lo, hi] = todo.back();
-                todo.pop_back();
-                const int64_t nt = (hi - lo + kTile - 1) / kTile;
-                if (nt <= 1) continue;
-                int dim = 0;
-                float widest = -1.f;
-                for (int c = 0; c < kNC; ++c) {
-                    const int oc = chi_comp(c);
-                    float mn = INFINITY, mx = -INFINITY;
-                    for (int64_t j = lo; j < hi; ++j) { const float v = db[(int64_t)ids[j] * 8 + oc]; mn = std::min(mn, v); mx = std::max(mx, v); }
-                    const float ext = (mx - mn) * wdim[c];
-                    if (ext > widest) { widest = ext; dim = c; }
-                }
-                const int oc = chi_comp(dim);
-                const int64_t mid = lo + (nt / 2) * kTile;
-                std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int32_t x, int32_t y) {
-                    float vx = db[(int64_t)x * 8 + oc], vy = db[(int64_t)y * 8 + oc];
-                    if (std::isnan(vx)) vx = INFINITY;                     // keep the order strict and weak
-                    if (std::isnan(vy)) vy = INFINITY;
-                    return vx < vy || (vx == vy && x < y);
-                });
-                todo.push_back({lo, mid});
-                todo.push_back({mid, hi});
-            }
-            for (size_t j = 0; j < ids.size(); ++j) kdpos[ids[j]] = (int32_t)j;
+            ids[q].reserve(cnt[q]);
+            for (int64_t i = 0; i < n; ++i) if (cls[i] == q) ids[q].push_back((int32_t)i);
+            if (!ids[q].empty()) workers.emplace_back(kd_split, db, ids[q].data(), (int64_t)0, (int64_t)ids[q].size(), 0);
         }
+        for (auto& w : workers) w.join();
+        for (int q = 0; q < kParts; ++q)
+            for (size_t j = 0; j < ids[q].size(); ++j) kdpos[ids[q][j]] = (int32_t)j;
     }
     std::vector<float> boxes;
     if (blocked) {

@@ -693,3 +693,38 @@ def test_pruning_large_and_tiny_databases(ctx):
             assert np.array_equal(res[False][key], res[True][key], equal_nan=True), (mode, key)
         assert (res[True]['status'] == native.PIX_SEARCHED).mean() > 0.8
 
+
+@pytest.mark.parametrize('seed', [0, 1, 2, 3, 4, 5])
+def test_pruning_randomised_databases(ctx, seed):
+    """Random database shapes (1 - 40 tiles per sign class, partly filled last tiles) with the values that stress the tile
+    bounds - NaN V1 rows (never candidates), zero chi^2 components, duplicated rows, one sign class missing (cledb_db_put
+    refuses non-finite I/Q/U in candidate rows) -
+    random nsearch, both modes and encodings: the pruned search returns the bits of the brute-force search."""
+    rng = np.random.default_rng(1000 + seed)
+    ngx, nbphi, nbtheta = int(rng.integers(1, 5)), int(rng.integers(5, 41)), int(rng.integers(5, 31))
+    db = synth.make_database(int(rng.integers(0, 12)), int(rng.integers(0, 50)), ngx=ngx, nbphi=nbphi, nbtheta=nbtheta).copy()
+    flat = db.reshape(-1, 8)
+    n = flat.shape[0]
+    obs = synth.make_observation(24, 18, [db], seed=50 + seed, frac_nan=0.03, frac_zero=0.03)        # drawn from the clean rows
+    pick = lambda m: rng.choice(n, size=max(1, n // m), replace=False)
+    flat[pick(40), 3] = np.nan
+    flat[pick(30), int(rng.choice([1, 2, 5, 6]))] = 0.0
+    src = pick(50)
+    flat[(src + n // 2) % n] = flat[src]                                 # duplicated rows: exact ties, far apart in row order
+    if seed % 3 == 0:
+        flat[:, 3] = np.abs(flat[:, 3])                                  # no negative-V class at all
+    sobs, snr = obs['sobs_totrot'].reshape(-1, 8), obs['snr'].reshape(-1, 8)
+    ids = np.zeros(sobs.shape[0], np.int32)
+    k = int(rng.choice([1, 3, 8, 17]))
+    for encoding in (native.ENC_F32, native.ENC_I16):
+        for mode in (native.MODE_IQUV, native.MODE_IQUD):
+            res = {}
+            for prune in (False, True):
+                ctx.set_pruning(prune)
+                ctx.db_put(0, db, encoding)
+                res[prune] = ctx.match(mode, sobs, snr, ids, k)
+                ctx.db_drop(0)
+            ctx.set_pruning(ctx.pruning_default)
+            for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
+                assert np.array_equal(res[False][key], res[True][key], equal_nan=True), (encoding, mode, k, key)
+
