@@ -75,7 +75,8 @@ template <int PREC> struct Rec;
 template <> struct __align__(16) Rec<CLEDB_PREC_FP32> {
     float a[kNC];
     float nb[kNC];
-    float cm;    // in HBM: c0 = constant component-0 term ((1 - s~_0)/sigma_0)^2, 0 for IQUV.  In shared memory:
+    float cm;    // in HBM: c0, the start value of the accumulation chain: 0 (the constant component-0 term
+                 // ((1 - s~_0)/sigma_0)^2 is kept apart in Plan::c0 and added when chi^2 is written).  In shared memory:
                  // c0 - tau*(1 + 2^-19), the start value of the flagging accumulators (c0 itself moves to a side array)
     float tau;   // running threshold: k-th best value so far (same units as the accumulators)
 };
@@ -253,6 +254,7 @@ struct Plan {                 // all pointers are device pointers into the works
     int32_t* nsub;            // [nkeys] candidate-list pieces (sign partitions x chunks) per pixel tile
     int32_t* counters;        // [0] next item to hand out, [1] error flag, [2] total items
     void*    recs;            // [npix] Rec<PREC>
+    double*  c0;              // [npix] fp32 search: the per-pixel constant term of chi^2*2 (I1 component), added when the result is written
     void*    plist;           // [maxitems][P][k] Cand<PREC>
     uint8_t* status;          // [npix]
     int32_t  nkeys;
@@ -372,7 +374,12 @@ __global__ void __launch_bounds__(256) k_classify(Plan pl, const float* __restri
             r.nb[c] = (float)(-(double)a * (double)st[oc]);
             r.a[c] = a * db.scale[oc];                           // fold the int16 block exponent (exact)
         }
-        r.cm = (float)c0;                                      // c0 in HBM, see Rec
+        // The I1 term c0 is the same for every candidate of the pixel, so the fp32 search ranks the candidates by the sum of the
+        // other five terms and c0 is added (in double) when chi^2 is written: in IQUD mode c0 can be 10^7 times those terms
+        // (I1 far below max(sobs) in a bad pixel), and accumulating on top of it would round thousands of candidates to the
+        // same float - wrong order against the reference's float64, and every one of those ties resolved by row lookups.
+        r.cm = 0.f;                                            // start value of the accumulation chain, see Rec
+        pl.c0[p] = c0;
         r.tau = CUDART_INF_F;
         *reinterpret_cast<Rec<CLEDB_PREC_FP32>*>(rec) = r;
     } else {
@@ -546,9 +553,30 @@ __device__ __forceinline__ void eval_pixel(const Rec<PREC>* rec, float c0f, cons
     }
 }
 
+// Entries whose value EQUALS the threshold enter the list only if their original row is lower than the row of the list's
+// last element (first-occurrence ties).  A pixel whose candidates all tie - every chi^2 the same float, e.g. an IQUD pixel
+// with max(sobs) ~ 0, or +inf everywhere - would otherwise send every entry of every tile through list_insert; this filter
+// looks the rows up once and drops the ties that cannot win (they are set to NaN: never a hit).
+template <int ENC, typename V>
+__device__ __forceinline__ void drop_losing_ties(V (&v)[kEPL], V tau, const Cand<(sizeof(V) == 8 ? CLEDB_PREC_FP64 : CLEDB_PREC_FP32)>* list,
+                                                 int base, int cnt_end, const int32_t* __restrict__ perm, int k, int lane) {
+    uint32_t tied = 0;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) tied |= (v[e] == tau ? 1u : 0u) << e;
+    if (!__any_sync(0xffffffffu, tied != 0u)) return;
+    const int last = list[k - 1].pos;
+    const int kth_row = last >= 0 ? perm[last] : 0x7fffffff;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e)
+        if ((tied >> e) & 1u) {
+            const int pos = base + pos_in_tile<ENC>(lane, e);
+            if (pos >= cnt_end || perm[pos] >= kth_row) v[e] = (V)CUDART_NAN;
+        }
+}
+
 // exact, unhurried handling of one (tile, pixel): evaluate, insert every entry that beats the live threshold.
 // Used by the fp64 validation kernel for every step and by the fp32 kernel when a candidate buffer overflows.
-template <int ENC, int PREC>
+template <int ENC, int PREC, bool TIE_FILTER = true>
 __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, float c0f, Cand<PREC>* list, const float (&d)[kEPL][kNC],
                                            const float (&scale)[kNC], int base, int cnt_end, const int32_t* __restrict__ perm,
                                            int k, int lane) {
@@ -559,6 +587,13 @@ __device__ __forceinline__ void slow_pixel(Rec<PREC>* rec, float c0f, Cand<PREC>
 #pragma unroll
     for (int e = 0; e < kEPL; ++e) em |= (v[e] <= tau) ? (1u << e) : 0u;        // padding evaluates to NaN: never true
     uint32_t lanes = __ballot_sync(0xffffffffu, em != 0);
+    if (TIE_FILTER && __popc(lanes) > 4) {        // many hits at once: usually ties with the threshold that cannot win
+        drop_losing_ties<ENC, V>(v, tau, list, base, cnt_end, perm, k, lane);
+        em = 0;
+#pragma unroll
+        for (int e = 0; e < kEPL; ++e) em |= (v[e] <= tau) ? (1u << e) : 0u;
+        lanes = __ballot_sync(0xffffffffu, em != 0);
+    }
     while (lanes) {
         const int src = __ffs(lanes) - 1;
         lanes &= lanes - 1;
@@ -648,6 +683,10 @@ __device__ __forceinline__ void merge_pixel(Rec<CLEDB_PREC_FP32>* rec, float c0f
     for (int e = 0; e < kEPL; ++e)
         if (!(v[e] <= tau) || base + pos_in_tile<ENC>(lane, e) >= cnt_end) v[e] = CUDART_INF_F;      // not a hit (NaN, padding)
     if (rank_select<ENC>(rec, c0f, list, v, base, k, lane, scratch)) return;
+    drop_losing_ties<ENC, float>(v, tau, list, base, cnt_end, perm, k, lane);
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e)
+        if (!(v[e] <= tau)) v[e] = CUDART_INF_F;                                                      // the dropped ties are NaN
     for (;;) {
         float lm = v[0];
         int le = 0;
@@ -1268,7 +1307,7 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
                 while (set) {
                     const int jj = __ffs(set) - 1;
                     set &= set - 1;
-                    slow_pixel<ENC, PREC>(recs + jj, c0s[jj], lists + jj * k, dd, scale, base, im.cnt_end, db.perm, k, lane);
+                    slow_pixel<ENC, PREC, false>(recs + jj, c0s[jj], lists + jj * k, dd, scale, base, im.cnt_end, db.perm, k, lane);
                 }
             }
         };
@@ -1474,7 +1513,7 @@ __global__ void __launch_bounds__(256) k_finalize(Plan pl, const DbSlot* __restr
         } else {
             const DbSlot& db = slots[s_key[lp] / kParts];
             const int bidx = s_idx[t];
-            const double chi = (PREC == CLEDB_PREC_FP32) ? (double)(0.5f * (float)s_val[t]) : (double)s_val[t];
+            const double chi = (PREC == CLEDB_PREC_FP32) ? 0.5 * ((double)s_val[t] + pl.c0[p0 + lp]) : (double)s_val[t];
             idx_out[o] = bidx;
             chi_out[o] = (float)chi;
             if (chi64_out) chi64_out[o] = chi;
@@ -1702,7 +1741,7 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_key = take(npix * 4), o_rank = take(npix * 4), o_order = take(npix * 4);
     const size_t o_small = take((size_t)(5 * pl.nkeys + 1 + 4) * 4);
-    const size_t o_recs = take(npix * rec_sz), o_status = take(npix);
+    const size_t o_recs = take(npix * rec_sz), o_status = take(npix), o_c0 = take(precision == CLEDB_PREC_FP32 ? npix * 8 : 0);
     // exact tile pruning: only with the fp32 kernel, and only if every resident database was put in the pruning layout
     int nblocked = 0, nlive = 0, ftiles = 1;
     for (auto& h : ctx->dbs) {
@@ -1728,6 +1767,7 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     pl.item0 = small + 4 * pl.nkeys;                 // nkeys + 1 entries
     pl.counters = small + 5 * pl.nkeys + 1;
     pl.recs = w + o_recs;
+    pl.c0 = reinterpret_cast<double*>(w + o_c0);
     pl.status = status_out ? status_out : (w + o_status);
     CLEDB_CUDA(ctx, cudaMemsetAsync(small, 0, (size_t)(5 * pl.nkeys + 1 + 4) * 4, st));
     if (pruned) {
