@@ -135,8 +135,9 @@ int cledb_match_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
                     const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
                     int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out,
                     float* rows_out, uint8_t* status_out, int64_t* ncand_out, void* stream);
-/* tuning knobs: pixels per warp work item (1..40) and how many chunks each candidate list is cut into (1..8);
- * 0 = choose from the pixel count (default).  Results do not depend on them. */
+/* tuning knobs: pixels per warp work item (1..40; the pruned search uses at most 32 and ignores the chunk count) and how
+ * many chunks each candidate list is cut into (1..8); 0 = choose from the pixel count (default).  Results do not depend on
+ * them. */
 int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split);
 /* exact tile pruning on (1) / off (0) for databases put from now on; every resident database must have been put with
  * the same setting when a search runs */
