@@ -1017,9 +1017,12 @@ constexpr int kSeedLanes = 4;           // threads that share a pixel in k_seed 
 __global__ void __launch_bounds__(256) k_seed(Plan pl, const DbSlot* __restrict__ slots) {
     __shared__ float s_rep[kSeedCap * kNC];
     __shared__ int s_slot;
-    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kSeedLanes;
+    // pixels are taken in bucket order (k_scatter ran before): a block works on one database, mostly on one sign class
+    const int64_t ro = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kSeedLanes;
     const int sub = threadIdx.x % kSeedLanes;
-    const int key = p < pl.npix ? pl.key[p] : -1;
+    const int64_t nsearched = (int64_t)pl.off[pl.nkeys - 1] + pl.cnt[pl.nkeys - 1];
+    const int64_t p = ro < nsearched ? pl.order[ro] : -1;
+    const int key = p >= 0 ? pl.key[p] : -1;
     // the representative entries of the block's database into shared memory, if the whole block searches one database
     // (the usual case) and they fit; otherwise every thread reads them from global memory
     if (threadIdx.x == 0) s_slot = -1;
@@ -1083,25 +1086,29 @@ __global__ void __launch_bounds__(256) k_seed(Plan pl, const DbSlot* __restrict_
     if (sub == 0) atomicAdd(&pl.fcnt[fine_key(pl, db, key, seeds)], 1);
 }
 
-// exclusive scan of the fine counts (one block)
-__global__ void __launch_bounds__(1024) k_fscan(Plan pl, int nf) {
-    __shared__ int s_sum[1024];
-    const int tid = threadIdx.x;
-    const int per = (nf + 1023) / 1024;
-    const int k0 = tid * per, k1 = min(nf, k0 + per);
+// exclusive scan of the fine counts: one block per database slot, starting from the slot's first position in `order`
+// (k_scan's offset of the slot's first bucket; the fine keys of a slot are class-major like the buckets)
+__global__ void __launch_bounds__(256) k_fscan(Plan pl) {
+    __shared__ int s_sum[256];
+    const int tid = threadIdx.x, slot = blockIdx.x;
+    const int n = pl.ftiles;
+    int32_t* cnt = pl.fcnt + (size_t)slot * n;
+    int32_t* off = pl.foff + (size_t)slot * n;
+    const int per = (n + 255) / 256;
+    const int k0 = tid * per, k1 = min(n, k0 + per);
     int sum = 0;
-    for (int i = k0; i < k1; ++i) sum += pl.fcnt[i];
+    for (int i = k0; i < k1; ++i) sum += cnt[i];
     s_sum[tid] = sum;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
+    for (int o = 1; o < 256; o <<= 1) {
         int a = 0;
         if (tid >= o) a = s_sum[tid - o];
         __syncthreads();
         s_sum[tid] += a;
         __syncthreads();
     }
-    int run = s_sum[tid] - sum;
-    for (int i = k0; i < k1; ++i) { pl.foff[i] = run; run += pl.fcnt[i]; }
+    int run = pl.off[slot * kParts] + s_sum[tid] - sum;
+    for (int i = k0; i < k1; ++i) { off[i] = run; run += cnt[i]; }
 }
 
 // pixels into (bucket, seed tile) order; the buckets of k_scan are unions of consecutive fine buckets
@@ -1658,10 +1665,11 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
 
     k_scan<<<1, 1024, 0, st>>>(pl, ctx->d_slots);
     if (pruned) {
+        k_scatter<<<nb, 256, 0, st>>>(pl);                 // bucket order first: k_seed then stages one database per block
         k_seed<<<(int)((npix * kSeedLanes + 255) / 256), 256, 0, st>>>(pl, ctx->d_slots);
-        k_fscan<<<1, 1024, 0, st>>>(pl, ctx->slots_cap * pl.ftiles);
+        k_fscan<<<ctx->slots_cap, 256, 0, st>>>(pl);
         k_scatter_fine<<<nb, 256, 0, st>>>(pl, ctx->d_slots);
-        ctx->launches += 2;
+        ctx->launches += 3;
     } else k_scatter<<<nb, 256, 0, st>>>(pl);
     ctx->launches += 2;
     int occ = 0;
