@@ -15,10 +15,12 @@ cat $out/bench_iqud.json
 if [ -z "$NO_NCU" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_launches.log 2>&1; echo "ncu launches exit $?"
+if [ -z "$NO_NCU_FULL" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_match_pruned -s 2 -c 1 -f -o $out/k_match_pruned_iquv \
     python profiles/prof_match.py iquv 256 prune > $out/ncu_full_pruned_iquv.log 2>&1; echo "ncu full pruned iquv exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_match_pruned -s 2 -c 1 -f -o $out/k_match_pruned_iqud \
     python profiles/prof_match.py iqud 256 prune > $out/ncu_full_pruned_iqud.log 2>&1; echo "ncu full pruned iqud exit $?"
+fi
 if [ -n "$NCU_BRUTE" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_match -s 2 -c 1 -f -o $out/k_match_iquv \
     python profiles/prof_match.py iquv 256 brute > $out/ncu_full_iquv.log 2>&1; echo "ncu full iquv exit $?"
