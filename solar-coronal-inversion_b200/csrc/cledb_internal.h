@@ -15,8 +15,6 @@ constexpr int kTile     = 256;   // database entries per tile = one warp step (3
 constexpr int kEPL      = 8;     // entries per lane
 constexpr int kNC       = 5;     // components that enter chi^2: Q1 U1 I2 Q2 U2 (indices 1 2 4 5 6)
 constexpr int kMaxP     = 40;    // pixels per work item
-constexpr int kWarps    = 8;     // compute warps per CTA
-constexpr int kThreads  = kWarps * 32;
 constexpr int kSuper    = 16;    // tiles per group of the two-level bounds (pruning layout)
 constexpr int kParts    = 3;     // sign(V1) classes: 0 = positive, 1 = negative, 2 = zero
 
@@ -37,7 +35,7 @@ struct DbSlot {
     int32_t        part_zero[kParts];    // bit c set: some entry of the class has decoded chi-component c == 0
     int32_t        encoding;
     int32_t        live;
-    int32_t        blocked;          // 1: tiles are compact patches in original order and `boxes` holds their bounds
+    int32_t        blocked;          // 1: pruning layout - the tiles of a sign class are k-d leaves, `boxes` / `sboxes` hold their bounds
     int32_t        pad_;
     const float*   boxes;            // [ntiles_total][16]: lo[5], hi[5] of the stored (code) values of a tile, one representative entry[5], pad
     const float*   sboxes;           // [sum over classes of ceil(ntiles/16)][12]: lo[5], hi[5], pad[2] of groups of 16 consecutive tiles of a class
