@@ -1,2 +1,5 @@
-for m in iquv iqud; do python bench.py --steps 20 --no-cpu-baseline --mode $m > gpurun_out/exp_$m.json 2> gpurun_out/exp_$m.err; echo exit $?; tail -3 gpurun_out/exp_$m.err; done
-python bench.py --steps 10 --no-cpu-baseline --nx 1024 > gpurun_out/exp_1024.json 2> gpurun_out/exp_1024.err; echo exit $?
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for m in iquv iqud; do python bench.py --steps 20 --no-cpu-baseline --no-prune-pass --mode $m | python -c "
+import json,sys
+j=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=j['roofline']
+print('$m value %.4e e2e %.4e step %.3f | pruned kernel %.3f'%(j['value'], j['e2e']['value'], j['ms_per_step'], r['kernel_ms']))"; done

@@ -475,7 +475,12 @@ __device__ __forceinline__ Item make_item(const Plan& pl, const DbSlot* slots, i
     const int key = lo;
     const int ns = pl.nsub[key];
     const int local = it - pl.item0[key];
-    const int tile = local / ns, sub = local - tile * ns;
+    // Items of a bucket: pixel tiles x pieces.  The brute-force search numbers them tile-major; the pruned search piece-major,
+    // so that warps working side by side are in the same sign class (IQUD: the tiny V = 0 class takes other code paths than
+    // the two big ones, and the kernel is sensitive to its instruction-cache footprint).
+    const int ntg = (pl.cnt[key] + pl.P - 1) / pl.P;
+    int tile = local / ns, sub = local - tile * ns;
+    if (pl.seed) { sub = local / ntg; tile = local - sub * ntg; }
     const DbSlot& db = slots[key / kParts];
     int part = key % kParts, chunk = sub;
     if (pl.mode == CLEDB_MODE_IQUD) {
@@ -1480,8 +1485,9 @@ __global__ void __launch_bounds__(256) k_finalize(Plan pl, const DbSlot* __restr
             const int local = pl.rank[p] - pl.off[key];
             const int tile = local / pl.P, j = local - tile * pl.P;
             const int ns = pl.nsub[key];
-            const CandT* base = reinterpret_cast<const CandT*>(pl.plist) + ((size_t)(pl.item0[key] + tile * ns) * pl.P + j) * k;
-            const size_t sub_stride = (size_t)pl.P * k;
+            const int ntg = (pl.cnt[key] + pl.P - 1) / pl.P;                    // item numbering: see make_item
+            const CandT* base = reinterpret_cast<const CandT*>(pl.plist) + ((size_t)(pl.item0[key] + (pl.seed ? tile : tile * ns)) * pl.P + j) * k;
+            const size_t sub_stride = (size_t)(pl.seed ? ntg : 1) * pl.P * k;
             unsigned char head[kMaxSub];
             for (int s = 0; s < ns; ++s) head[s] = 0;
             for (int r = 0; r < k; ++r) {
