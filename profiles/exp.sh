@@ -1,5 +1,5 @@
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for m in iquv iqud; do python bench.py --steps 20 --no-cpu-baseline --no-prune-pass --mode $m | python -c "
-import json,sys
-j=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=j['roofline']
-print('$m value %.4e e2e %.4e step %.3f | pruned kernel %.3f'%(j['value'], j['e2e']['value'], j['ms_per_step'], r['kernel_ms']))"; done
+mkdir -p gpurun_out/final
+python bench.py > gpurun_out/final/bench_iquv.json 2> gpurun_out/final/bench_iquv.err; echo exit $?
+python bench.py --mode iqud --steps 20 --no-cpu-baseline > gpurun_out/final/bench_iqud.json 2> gpurun_out/final/bench_iqud.err; echo exit $?
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/final/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/final/ncu.log 2>&1; echo exit $?
+python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -1
