@@ -971,21 +971,24 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// kernels 4b: the search with exact tile pruning (optional, databases put while cledb_set_pruning is on)
+// kernels 4b: the search with exact tile pruning (the default: databases put while cledb_set_pruning is on)
 // ------------------------------------------------------------------------------------------------------
 // The tiles of such a database are the leaves of a k-d partition (db.cu), each with the bounds lo_c <= d_c <= hi_c of its
-// entries and one representative entry.  With r_c(d) = fma(d, a_c, nb_c) monotone in d, |r_c| >= m_c = distance of the
-// interval [r_c(lo), r_c(hi)] from 0, and the accumulation chain acc = fma(r, r, acc) is monotone in |r| and in acc: the
-// bound computed with the SAME chain is <= the computed chi^2 of every entry of the tile, exactly, in floating point.  A
-// tile whose bound exceeds a pixel's threshold cannot change that pixel's list, so the result is bit-identical to k_match.
+// entries and one representative entry; groups of 16 consecutive tiles carry their joint bounds.  With r_c(d) =
+// fma(d, a_c, nb_c) monotone in d, |r_c| >= m_c = distance of the interval [r_c(lo), r_c(hi)] from 0, and the accumulation
+// chain acc = fma(r, r, acc) is monotone in |r| and in acc: the bound computed with the SAME chain is <= the computed chi^2 of
+// every entry of the tile, exactly, in floating point.  A tile whose bound exceeds a pixel's threshold cannot change that
+// pixel's list, so the result is bit-identical to k_match (tests/test_bound_property.py, tests/test_gpu_parity.py).
 //
-//   k_seed        one thread per pixel: the tile whose representative entry fits the pixel best (a coarse search over one
-//                 entry per tile).  Pixels are then ordered by (bucket, seed tile), so the pixels of an item are neighbours
-//                 in the space of the chi^2 components and need nearly the same tiles.
-//   k_match_pruned  one warp per item: (1) the item's distinct seed tiles, evaluated for all its pixels (bootstrap), give
-//                 every pixel a threshold close to the final one; (2) lane L computes the bound of every tile for pixel L,
-//                 the union over the lanes is the item's tile list; (3) the listed tiles run through the same fast pass /
-//                 rare pass as in k_match.  Tiles nobody needs are not even loaded.
+//   k_seed        four threads per pixel, pixels taken in bucket order (one database per block, its representatives staged in
+//                 shared memory): the tile whose representative entry fits the pixel best - a coarse search over one entry
+//                 per tile.  k_fscan + k_scatter_fine then order the pixels by (bucket, seed tile), so that the pixels of an
+//                 item are neighbours in the space of the chi^2 components and need nearly the same tiles.
+//   k_match_pruned  one warp per item of <= 32 pixels: (1) every pixel takes the exact top-k of its OWN seed tile: a
+//                 threshold close to the final one; (2) the lanes bound the tile groups, then the tiles of surviving groups,
+//                 for their pixel (32/P lanes share a pixel): a bit mask per pixel, whose union is the item's tile list;
+//                 (3) a listed tile is loaded (TMA) and runs through the fast pass of k_match for the pixels that need it,
+//                 flagged pairs are merged exactly.  Tiles nobody needs are not even loaded.
 __device__ __forceinline__ float tile_lower_bound(const float4 b0, const float4 b1, const float4 b2, const float (&a)[kNC],
                                                   const float (&nb)[kNC], float c0) {
     const float lo[kNC] = {b0.x, b0.y, b0.z, b0.w, b1.x};
