@@ -142,7 +142,8 @@ int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split);
 /* exact tile pruning on (1) / off (0) for databases put from now on; every resident database must have been put with
  * the same setting when a search runs */
 int cledb_set_pruning(cledb_ctx* ctx, int on);
-/* after a pruned search: evaluated[0] = (pixel, tile) pairs evaluated, evaluated[1] = pairs skipped by the bound */
+/* after a pruned search: evaluated[0] = (pixel, tile) pairs evaluated, evaluated[1] = pairs skipped by the bound; counts of the
+ * last search launched (cledb_invert sends maps of 256 Ki pixels and more through in 128 Ki-pixel chunks: the last chunk) */
 int cledb_pruning_stats(cledb_ctx* ctx, int64_t evaluated[2]);
 
 /* ---- search + solution building in one call --------------------------------------------------------- *
