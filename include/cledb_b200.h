@@ -10,7 +10,10 @@
  *   - plain C: pointers, sizes, ints.  No C++ or torch types cross the boundary, no exceptions.
  *   - return 0 on success, a negative CLEDB_ERR_* otherwise; cledb_last_error() gives the text.
  *   - one context per CUDA device and per thread of control; calls on one context are serialised by the
- *     caller; different contexts are independent.
+ *     caller; different contexts are independent.  ONE call in flight per context: the "_dev" entry points take a
+ *     stream, but every call on a context shares the context's workspaces (and may regrow them), so a second call on
+ *     the same context - on whatever stream - may only be issued after the first has been enqueued, and calls on
+ *     different streams of one context must be ordered by the caller (events).  Use one context per concurrent stream.
  *   - "host" entry points take C-contiguous host buffers (pageable or pinned), copy in, run, copy out and
  *     return when the results are in the output buffers.  "_dev" entry points take device pointers that are
  *     valid on the context's device and enqueue on the given cudaStream_t (passed as void*; NULL = the
@@ -35,6 +38,7 @@ typedef struct cledb_ctx cledb_ctx;
 #define CLEDB_ERR_NODB     -3   /* a pixel refers to a database id that was never put                     */
 #define CLEDB_ERR_DBFORMAT -4   /* database violates the layout contract (component 0 != 1, non-finite)   */
 #define CLEDB_ERR_NOMEM    -5   /* device or host allocation failed                                       */
+#define CLEDB_ERR_COMM     -6   /* multi-GPU: NCCL missing / failed, or no communicator on the context    */
 
 #define CLEDB_MODE_IQUV 0       /* cledb_matchiquv, CLEDB_PROC.py:921  */
 #define CLEDB_MODE_IQUD 1       /* cledb_matchiqud, CLEDB_PROC.py:1094 */
@@ -160,7 +164,13 @@ int cledb_pruning_stats(cledb_ctx* ctx, int64_t evaluated[2]);
  *   yobs[npix], dobs[npix] float32; dopp: B_POS of every pixel for IQUD (element p at dopp[p*dopp_stride],
  *   float32 or float64 as dopp_is_f64 says; NULL for IQUV); maxchisq, bcalc as in ctrlparams
  *   invout[npix,nsearch,11], sfound[npix,nsearch,8] float32; status_out[npix] (may be NULL)
- * The Van-Vleck / chi^2 / SNR issue codes (:323-355) are O(npix) work on invout and stay in the binding. */
+ *   issue_out[npix,2] uint8 (may be NULL): the tests behind the issue codes 512 / 1024 / 2048 of cledb_invproc (:323-355)
+ *     [p][0] bit 0 = Van-Vleck proximity of the LAST solution (53 deg <= vartheta_B <= 56 deg; `flg = 0` sits inside the
+ *            reference's loop over solutions, :324, so only slot nsearch-1 decides), evaluated in float64;
+ *            bit 1 = vartheta_B lies within 1e-3 deg of 53 or 56: the reference evaluates the chain in float32 with the
+ *            caller's NumPy, whose last bits decide such a pixel - the binding re-evaluates it (about 1 pixel in 50 000)
+ *     [p][1] bit 0 = chi^2 of the best solution > 10 (:351), bit 1 = snr[p,0] < 1 (:353)
+ *   The binding ORs 512 / 1024 / 2048 into its issuemask from these bits. */
 typedef struct cledb_dbgrid {
     int32_t dbtype, ngx, nbphi, nbtheta;               /* dbhdr[14], [2], [3], [4]  (CLEDB_PREPINV.py:482-508) */
     float   gxmin, gxmax, bphimin, bphimax, bthetamin, bthetamax;
@@ -172,14 +182,14 @@ int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npix,
                  const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
                  const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
                  double maxchisq, int bcalc, int strict_topk,
-                 float* invout, float* sfound, uint8_t* status_out);
+                 float* invout, float* sfound, uint8_t* status_out, uint8_t* issue_out);
 /* device-pointer variant: every array, including the four tables inside *grid, lives on the context's device */
 int cledb_invert_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
                      const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
                      const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
                      const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
                      double maxchisq, int bcalc, int strict_topk,
-                     float* invout, float* sfound, uint8_t* status_out, void* stream);
+                     float* invout, float* sfound, uint8_t* status_out, uint8_t* issue_out, void* stream);
 
 /* ---- reduced-database mode (reduced = True) -------------------------------------------------------- *
  * Replaces cledb_getsubsetiquv / cledb_getsubsetiqud and the search over their per-pixel output (CLEDB_PROC.py:1401-1568,
@@ -212,7 +222,58 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
                          const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
                          const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
                          double maxchisq, int bcalc, int strict_topk,
-                         float* invout, float* sfound, uint8_t* status_out);
+                         float* invout, float* sfound, uint8_t* status_out, uint8_t* issue_out);
+
+/* ---- multi-GPU: one process and one context per GPU, pixels sharded, databases replicated ------------ *
+ * The reference dispatches one pool task per pixel (CLEDB_PROC.py:304-313): pixels are independent, the search has no exchange
+ * step, and the only collective is the gather of the finished maps.  NCCL is bound at run time (the libnccl.so.2 already
+ * loaded into the process, else the system's; CLEDB_B200_NCCL overrides), single-GPU use needs none.
+ *   cledb_comm_unique_id   rank 0 creates the 128-byte id; the launcher ships it to the other ranks (torch.distributed
+ *                          broadcast, MPI, a file ...)
+ *   cledb_comm_init        collective over all ranks; nranks == 1 needs no id and no NCCL
+ *   cledb_comm_info        info[0]=rank, [1]=nranks, [2]=NCCL version code, [3]=1 if an NCCL communicator is live
+ *   cledb_allgather_dev    every rank contributes `bytes` bytes at `send`; `recv` receives nranks*bytes in rank order
+ *                          (device pointers, enqueued on the stream: ncclAllGather over NVLink / NVSwitch)
+ *   cledb_partition        pixels ordered by key[p] in 0..nkeys-1 (stable; the binding passes db_enc) and cut into nranks
+ *                          contiguous ranges of equal total weight (weight_of_key[key]: rows of that database, NULL = 1):
+ *                          order_out[npix], bounds_out[nranks+1]; rank r owns order_out[bounds[r] : bounds[r+1]], so it
+ *                          needs only the databases of its range resident.  Host arrays, pure host code, the same result
+ *                          on every rank.
+ *   cledb_shard_layout     byte offsets of the packed records of a shard of <= maxcount pixels:
+ *                          layout[0..3] = offsets of invout[maxcount,k,11], sfound[maxcount,k,8], status[maxcount],
+ *                          issue[maxcount,2]; layout[4] = bytes per rank (the all-gather count)
+ *   cledb_unshard_dev      scatters the gathered records of all ranks to their pixels: recv[nranks][layout] ->
+ *                          invout[npix,k,11], sfound[npix,k,8], status[npix], issue[npix,2] (device pointers; status and
+ *                          issue may be NULL)
+ *   cledb_invert_sharded   cledb_invert for one map of npix pixels over all ranks: every rank passes the inputs of ITS
+ *                          nlocal pixels (those of order[bounds[rank] : bounds[rank+1]], in that order; db_id = the ids
+ *                          under which this rank put their databases), searches and builds them, writes the packed
+ *                          records into the send buffer; ONE all-gather; ranks with root < 0 or root == rank scatter the
+ *                          records to their pixels and receive the full maps invout[npix,k,11] ... in their host buffers
+ *                          (the others may pass NULL outputs).  Collective: every rank must call it. */
+#define CLEDB_COMM_ID_BYTES 128
+int cledb_comm_unique_id(void* id128);
+int cledb_comm_init(cledb_ctx* ctx, int rank, int nranks, const void* id128);
+int cledb_comm_destroy(cledb_ctx* ctx);
+int cledb_comm_info(cledb_ctx* ctx, int32_t info[4]);
+int cledb_allgather_dev(cledb_ctx* ctx, const void* send, void* recv, int64_t bytes, void* stream);
+int cledb_partition(int64_t npix, const int32_t* key, int nkeys, const double* weight_of_key, int nranks,
+                    int32_t* order_out, int64_t* bounds_out);
+int cledb_shard_layout(int64_t maxcount, int nsearch, int64_t layout[5]);
+int cledb_unshard_dev(cledb_ctx* ctx, int nranks, const int64_t* bounds_dev, const int32_t* order_dev, int64_t npix,
+                      int64_t maxcount, int nsearch, const void* recv, float* invout, float* sfound, uint8_t* status,
+                      uint8_t* issue, void* stream);
+int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int64_t nlocal,
+                         const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
+                         const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
+                         const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
+                         double maxchisq, int bcalc, int strict_topk,
+                         int64_t npix, const int32_t* order, const int64_t* bounds, int root,
+                         float* invout, float* sfound, uint8_t* status_out, uint8_t* issue_out);
+
+/* ---- pinned host memory for the binding's staging buffers (cudaHostAlloc / cudaFreeHost) ------------- */
+int cledb_host_alloc(int64_t bytes, void** out);
+int cledb_host_free(void* p);
 
 /* ---- elementwise neighbours ------------------------------------------------------------------------ *
  * cledb_blos: blos_proc_1pix (CLEDB_PROC.py:874-914) for npix pixels of one line.

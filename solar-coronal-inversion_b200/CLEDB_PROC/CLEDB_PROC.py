@@ -11,7 +11,9 @@ Same function names, positional arguments, return arity and error conventions as
 The chi^2 search over the database runs in hand-written sm_100a kernels through the C-ABI of
 ``libcledb_b200.so``; there is no CPU fallback (a missing library or GPU raises).  ``ncpu`` and the Numba flags
 are accepted and ignored.  Everything after the search (thresholds, field strength, geometry, issue codes) is
-NumPy on ``[npix, nsearch]`` arrays in ``cledb_b200.solution``.
+built on the device too (``cledb_invert``: solutions and the tests behind the issue codes); ``cledb_b200.solution`` is the NumPy
+statement of the same steps, used for CLE-type headers and as a cross-check.  Result arrays live in pinned host memory
+(``cledb_b200.native.PinnedPool``); they are the caller's like any fresh NumPy array.
 
 Module-level options (not part of the reference surface; the defaults reproduce the reference):
     OPTIONS['dbencoding']  0 = database kept as float32 in HBM (lossless, default here), 1 = int16 codes
@@ -22,6 +24,9 @@ Module-level options (not part of the reference surface; the defaults reproduce 
     OPTIONS['pruning']     True (default) = exact tile pruning in the search (k-d tile layout, bit-identical results, several
                            times faster), False = brute-force evaluation of every (pixel, entry) pair
     OPTIONS['device']      CUDA ordinal (default: $CLEDB_B200_DEVICE, else $LOCAL_RANK, else 0)
+    OPTIONS['sharded']     True = cledb_invproc is a collective over the ranks of cledb_b200.dist.init_comm(): pixels sharded,
+                           one all-gather of the finished maps over NVLink; OPTIONS['shard_root'] = rank that receives the maps
+                           (-1, default: every rank)
 """
 import os
 
@@ -41,34 +46,10 @@ OPTIONS = dict(reduced_tie_order=None,      # theta order of an all-equal presor
 # ---------------------------------------------------------------------------------------------------------
 # database residency: upload each distinct database array once and keep it in HBM across calls
 # ---------------------------------------------------------------------------------------------------------
-class _Resident:
-    def __init__(self):
-        self.ids = {}          # fingerprint -> db_id
-        self.next_id = 0
-        self.pruning = None    # tile layout of the resident databases
+from cledb_b200.residency import Resident
 
-    @staticmethod
-    def fingerprint(arr, encoding):
-        flat = arr.reshape(-1)
-        step = max(1, flat.size // 4096)
-        return (arr.__array_interface__['data'][0], arr.shape, int(encoding), hash(flat[::step].tobytes()))
-
-    def ensure(self, ctx, arr, encoding):
-        arr = np.ascontiguousarray(arr, dtype=np.float32)
-        key = self.fingerprint(arr, encoding)
-        db_id = self.ids.get(key)
-        if db_id is None:
-            db_id = self.next_id
-            self.next_id += 1
-            ctx.db_put(db_id, arr, encoding)
-            self.ids[key] = db_id
-        return db_id
-
-    def clear(self, ctx):
-        for db_id in self.ids.values():
-            ctx.db_drop(db_id)
-        self.ids.clear()
-
+OPTIONS.setdefault('verify_resident', os.environ.get('CLEDB_B200_VERIFY_RESIDENT', 'sample'))   # 'sample' | 'full'
+OPTIONS.setdefault('hbm_budget_bytes', int(float(os.environ.get('CLEDB_B200_HBM_BUDGET', 120e9))))
 
 _resident = {}
 
@@ -86,14 +67,16 @@ def release_databases():
 
 def _upload(database, used):
     ctx = _context()
-    res = _resident.setdefault(OPTIONS['device'], _Resident())
-    encs = {k[2] for k in res.ids}
+    res = _resident.get(OPTIONS['device'])
+    if res is None:
+        res = _resident[OPTIONS['device']] = Resident()
+    res.verify, res.budget_bytes = OPTIONS['verify_resident'], OPTIONS['hbm_budget_bytes']
     want = bool(OPTIONS['pruning'])
-    if (encs and encs != {OPTIONS['dbencoding']}) or (res.ids and res.pruning != want):
+    if res.entries and (res.encoding != OPTIONS['dbencoding'] or res.pruning != want):
         res.clear(ctx)                      # one encoding and one tile layout at a time live on the device
     ctx.set_pruning(want)
-    res.pruning = want
-    return ctx, {int(k): res.ensure(ctx, database[int(k)], OPTIONS['dbencoding']) for k in used}
+    res.pruning, res.encoding = want, OPTIONS['dbencoding']
+    return ctx, res.ensure_all(ctx, {int(k): database[int(k)] for k in used}, OPTIONS['dbencoding'])
 
 
 def make_resident(database):
@@ -102,36 +85,80 @@ def make_resident(database):
     _upload(database, range(len(database)))
 
 
+def _used_databases(enc, ndb):
+    """Distinct values of ``db_enc`` (a bincount: cheaper than a sort for the small integer range)."""
+    if enc.size == 0:
+        return np.zeros(0, np.int64)
+    if np.issubdtype(enc.dtype, np.integer) and enc.min() >= 0 and enc.max() < max(ndb, 1) + 4096:
+        return np.flatnonzero(np.bincount(enc, minlength=1))
+    return np.unique(enc)
+
+
 def _search_and_build(mode, sobs, sobs_dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc,
                       reduced=False):
-    """Flattened pixels in, (invout[npix,k,11], sfound[npix,k,8]) out."""
+    """Flattened pixels in, (invout[npix,k,11], sfound[npix,k,8], issue codes [npix] or None) out."""
     sobs = np.ascontiguousarray(sobs, dtype=np.float32).reshape(-1, 8)
     snr = np.ascontiguousarray(snr, dtype=np.float32).reshape(-1, 8)
     enc = np.asarray(db_enc).reshape(-1)
-    ctx, ids = _upload(database, np.unique(enc))
-    lut = np.zeros(int(enc.max()) + 1, dtype=np.int32)
-    for k, v in ids.items():
-        lut[k] = v
+    if OPTIONS.get('sharded') and getattr(_context(), 'nranks', 1) > 1:
+        return _search_and_build_sharded(_context(), mode, sobs, sobs_dopp, database, enc, yobs, aobs, dobs, snr, dbhdr, nsearch,
+                                         maxchisq, bcalc, reduced)
+    ctx, ids = _upload(database, _used_databases(enc, len(database)))
+    if len(ids) == 1 and list(ids.values())[0] == 0 and not enc.any() and enc.dtype == np.int32:
+        dbid = np.ascontiguousarray(enc)             # one database, id 0: db_enc itself is the id map
+    else:
+        lut = np.zeros(int(enc.max()) + 1, dtype=np.int32)
+        for k, v in ids.items():
+            lut[k] = v
+        dbid = lut[enc]
     if reduced:                                      # cledb_getsubsetiquv / cledb_getsubsetiqud + search over the subset
         tie = OPTIONS['reduced_tie_order']
         if OPTIONS['solution'] == 'device' and int(dbhdr[14]) == 1:
-            inv, sf, _ = ctx.invert_reduced(mode, sobs, snr, lut[enc], nsearch, yobs, dobs, aobs, sobs_dopp, dbhdr, maxchisq, bcalc,
+            inv, sf, _ = ctx.invert_reduced(mode, sobs, snr, dbid, nsearch, yobs, dobs, aobs, sobs_dopp, dbhdr, maxchisq, bcalc,
                                             strict_topk=OPTIONS['strict_topk'], precision=OPTIONS['precision'], tie_order=tie)
-            return inv, sf
-        raw = ctx.match_reduced(mode, sobs, snr, lut[enc], nsearch, sobs_dopp, dbhdr, precision=OPTIONS['precision'], tie_order=tie)
+            return inv, sf, native.issue_codes(ctx.last_issue, inv)
+        raw = ctx.match_reduced(mode, sobs, snr, dbid, nsearch, sobs_dopp, dbhdr, precision=OPTIONS['precision'], tie_order=tie)
         return solution.build_solutions(raw, mode, sobs, sobs_dopp, np.asarray(yobs).reshape(-1), np.asarray(aobs).reshape(-1),
                                         np.asarray(dobs).reshape(-1), dbhdr, nsearch, maxchisq, bcalc,
-                                        strict_topk=OPTIONS['strict_topk'])
+                                        strict_topk=OPTIONS['strict_topk']) + (None,)
     if OPTIONS['solution'] == 'device' and int(dbhdr[14]) == 1:
         dopp0 = None if sobs_dopp is None else np.asarray(sobs_dopp).reshape(sobs.shape[0], -1)[:, 0]
-        inv, sf, _ = ctx.invert(mode, sobs, snr, lut[enc], nsearch, yobs, dobs, aobs, dopp0, dbhdr, maxchisq, bcalc,
+        inv, sf, _ = ctx.invert(mode, sobs, snr, dbid, nsearch, yobs, dobs, aobs, dopp0, dbhdr, maxchisq, bcalc,
                                 strict_topk=OPTIONS['strict_topk'], precision=OPTIONS['precision'])
-        return inv, sf
-    raw = ctx.match(mode, sobs, snr, lut[enc], nsearch, precision=OPTIONS['precision'], want_rows=True,
+        return inv, sf, native.issue_codes(ctx.last_issue, inv)
+    raw = ctx.match(mode, sobs, snr, dbid, nsearch, precision=OPTIONS['precision'], want_rows=True,
                     want_chi64=OPTIONS['precision'] == native.PREC_FP64)
     return solution.build_solutions(raw, mode, sobs, sobs_dopp, np.asarray(yobs).reshape(-1), np.asarray(aobs).reshape(-1),
                                     np.asarray(dobs).reshape(-1), dbhdr, nsearch, maxchisq, bcalc,
-                                    strict_topk=OPTIONS['strict_topk'])
+                                    strict_topk=OPTIONS['strict_topk']) + (None,)
+
+
+def _search_and_build_sharded(ctx, mode, sobs, sobs_dopp, database, enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc,
+                              reduced):
+    """The same over every rank of the context's communicator (cledb_b200.dist.init_comm; OPTIONS['sharded']): every rank is
+    called with the full map, takes its share of the pixel partition - contiguous ranges of the database-sorted pixel list,
+    balanced by database rows, so it uploads only the databases of its range -, and one all-gather of the packed records
+    over NVLink returns the finished maps (cledb_invert_sharded).  Collective."""
+    if reduced or OPTIONS['solution'] != 'device' or int(dbhdr[14]) != 1:
+        raise native.CledbError('sharded inversion covers the full search with device-side solutions of PyCELP-type databases')
+    npix = sobs.shape[0]
+    enc = np.ascontiguousarray(enc, dtype=np.int32)
+    weights = np.array([float(np.prod(np.shape(d)[:-1])) for d in database])
+    order, bounds = native.partition(enc, weights, ctx.nranks)
+    mine = order[bounds[ctx.rank]:bounds[ctx.rank + 1]]
+    emine = enc[mine]
+    _, ids = _upload(database, _used_databases(emine, len(database)))
+    lut = np.zeros(len(database), dtype=np.int32)
+    for k, v in ids.items():
+        lut[k] = v
+    flat = lambda a: np.asarray(a).reshape(-1)[mine]
+    dopp0 = None if sobs_dopp is None else np.asarray(sobs_dopp).reshape(npix, -1)[mine, 0]
+    inv, sf, _ = ctx.invert_sharded(mode, sobs[mine], snr[mine], lut[emine], nsearch, flat(yobs), flat(dobs), flat(aobs), dopp0, dbhdr,
+                                    maxchisq, bcalc, npix, order, bounds, root=int(OPTIONS.get('shard_root', -1)),
+                                    strict_topk=OPTIONS['strict_topk'], precision=OPTIONS['precision'])
+    if inv is None:                                  # a rank that does not receive the maps (shard_root names another)
+        return None, None, None
+    return inv, sf, native.issue_codes(ctx.last_issue, inv)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -171,11 +198,16 @@ def cledb_invproc(sobs_totrot, sobs_dopp, database, db_enc, yobs, aobs, dobs, sn
     if mode == native.MODE_IQUD:
         dopp = np.asarray(sobs_dopp)
         dopp = dopp.reshape(nx * ny, -1)
-    inv, sf = _search_and_build(mode, sobs_totrot, dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq, bcalc,
-                                reduced=reduced == True)
+    inv, sf, codes = _search_and_build(mode, sobs_totrot, dopp, database, db_enc, yobs, aobs, dobs, snr, dbhdr, nsearch, maxchisq,
+                                       bcalc, reduced=reduced == True)
+    if inv is None:                                            # sharded call on a rank other than OPTIONS['shard_root']
+        return None, None
     invout = np.ascontiguousarray(inv, dtype=np.float32).reshape(nx, ny, nsearch, 11)
     sfound = np.ascontiguousarray(sf, dtype=np.float32).reshape(nx, ny, nsearch, 8)
-    solution.update_issuemask(issuemask, invout, np.asarray(snr), nx, ny)
+    if codes is None:                                          # solutions built on the host (CLE-type header, OPTIONS['solution'])
+        solution.update_issuemask(issuemask, invout, np.asarray(snr), nx, ny)
+    else:                                                      # tests evaluated by k_build on the device (CLEDB_PROC.py:323-355)
+        solution.apply_issue_codes(issuemask, codes.reshape(nx, ny))
     if verbose >= 1:
         print('--------------------------------------\n--CLEDB_INVPROC - INVERSION FINALIZED-\n--------------------------------------')
     return invout, sfound
@@ -184,7 +216,7 @@ def cledb_invproc(sobs_totrot, sobs_dopp, database, db_enc, yobs, aobs, dobs, sn
 def cledb_matchiquv(xx, yy, sobs_1pix, yobs_1pix, aobs_1pix, dobs_1pix, database_in, dbhdr, snr, nsearch, maxchisq,
                     bcalc, reduced, verbose):
     """One pixel, full Stokes IQUV; reference CLEDB_PROC.py:921-1087.  Returns ``(xx, yy, out, smatch)``."""
-    inv, sf = _search_and_build(native.MODE_IQUV, np.asarray(sobs_1pix).reshape(1, 8), None, [database_in], np.zeros(1, np.int32),
+    inv, sf, _ = _search_and_build(native.MODE_IQUV, np.asarray(sobs_1pix).reshape(1, 8), None, [database_in], np.zeros(1, np.int32),
                                 np.array([yobs_1pix]), np.array([aobs_1pix]), np.array([dobs_1pix]), np.asarray(snr).reshape(1, 8),
                                 dbhdr, nsearch, maxchisq, bcalc, reduced=reduced == True)
     return xx, yy, inv[0], sf[0]
@@ -193,7 +225,7 @@ def cledb_matchiquv(xx, yy, sobs_1pix, yobs_1pix, aobs_1pix, dobs_1pix, database
 def cledb_matchiqud(xx, yy, sobs_1pix, sobsd_1pix, yobs_1pix, aobs_1pix, dobs_1pix, database_in, dbhdr, snr, nsearch,
                     maxchisq, bcalc, reduced, verbose):
     """One pixel, IQU + Doppler; reference CLEDB_PROC.py:1094-1252.  Returns ``(xx, yy, out, smatch)``."""
-    inv, sf = _search_and_build(native.MODE_IQUD, np.asarray(sobs_1pix).reshape(1, 8), np.asarray(sobsd_1pix).reshape(1, -1),
+    inv, sf, _ = _search_and_build(native.MODE_IQUD, np.asarray(sobs_1pix).reshape(1, 8), np.asarray(sobsd_1pix).reshape(1, -1),
                                 [database_in], np.zeros(1, np.int32), np.array([yobs_1pix]), np.array([aobs_1pix]),
                                 np.array([dobs_1pix]), np.asarray(snr).reshape(1, 8), dbhdr, nsearch, maxchisq, bcalc,
                                 reduced=reduced == True)

@@ -53,12 +53,24 @@ SIGNATURES = {
     'cledb_set_pruning': (_c.c_int, [_P, _c.c_int]),
     'cledb_pruning_stats': (_c.c_int, [_P, _P]),
     'cledb_invert': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
-                                _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P]),
+                                _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'cledb_match_reduced': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_invert_reduced': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _c.c_int,
-                                        _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P]),
+                                        _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'cledb_invert_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
-                                    _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P, _P]),
+                                    _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P, _P, _P]),
+    'cledb_invert_sharded': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
+                                        _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _c.c_int, _P, _P, _P, _P]),
+    'cledb_comm_unique_id': (_c.c_int, [_P]),
+    'cledb_comm_init': (_c.c_int, [_P, _c.c_int, _c.c_int, _P]),
+    'cledb_comm_destroy': (_c.c_int, [_P]),
+    'cledb_comm_info': (_c.c_int, [_P, _P]),
+    'cledb_allgather_dev': (_c.c_int, [_P, _P, _P, _c.c_int64, _P]),
+    'cledb_partition': (_c.c_int, [_c.c_int64, _P, _c.c_int, _P, _c.c_int, _P, _P]),
+    'cledb_shard_layout': (_c.c_int, [_c.c_int64, _c.c_int, _P]),
+    'cledb_unshard_dev': (_c.c_int, [_P, _c.c_int, _P, _P, _c.c_int64, _c.c_int64, _c.c_int, _P, _P, _P, _P, _P, _P]),
+    'cledb_host_alloc': (_c.c_int, [_c.c_int64, _c.POINTER(_P)]),
+    'cledb_host_free': (_c.c_int, [_P]),
     'cledb_blos': (_c.c_int, [_P, _c.c_int64, _P, _c.c_double, _c.c_double, _c.c_double, _P, _P]),
     'cledb_blos_dev': (_c.c_int, [_P, _c.c_int64, _P, _c.c_double, _c.c_double, _c.c_double, _P, _P, _P]),
     'cledb_qurotate': (_c.c_int, [_P, _c.c_int, _c.c_int, _P, _P, _c.c_double, _P, _P, _P, _P, _P]),
@@ -149,6 +161,87 @@ def codec_decode(codes, shift):
     return out
 
 
+# ---- pinned host memory ---------------------------------------------------------------------------------------
+class _PinnedBlock:
+    """Owner of one page-locked allocation; NumPy arrays made from it keep it alive through their ``base`` chain."""
+
+    def __init__(self, ptr, nbytes):
+        self.__array_interface__ = dict(data=(ptr, False), shape=(nbytes,), typestr='|u1', version=3)
+
+
+class PinnedPool:
+    """Result arrays in page-locked host memory (cledb_host_alloc): device-to-host copies into them run at full PCIe speed.
+
+    ``empty(shape, dtype)`` returns a NumPy array like ``np.empty``.  The caller owns it like any other fresh array; when
+    the array and every view of it have been garbage collected the block goes back to the pool (up to ``keep_bytes`` are
+    kept for reuse, the rest is freed), so a loop that drops its results reuses the same pinned blocks and a caller that
+    keeps them gets new ones - results of an earlier call are never overwritten."""
+
+    def __init__(self, keep_bytes=4 << 30):
+        self.free = {}                 # size class -> [ptr]
+        self.kept = 0
+        self.keep_bytes = keep_bytes
+        self.allocs = 0                # statistics (tests)
+
+    @staticmethod
+    def _size_class(nbytes):
+        c = 1 << 16
+        while c < nbytes:
+            c <<= 1
+        return c if c - nbytes <= c // 4 else (nbytes + (1 << 20) - 1) >> 20 << 20
+
+    def _release(self, cls, ptr):
+        if self.kept + cls <= self.keep_bytes:
+            self.free.setdefault(cls, []).append(ptr)
+            self.kept += cls
+        else:
+            try:
+                load_library().cledb_host_free(ctypes.c_void_p(ptr))
+            except Exception:
+                pass
+
+    def empty(self, shape, dtype):
+        import weakref
+        dtype = np.dtype(dtype)
+        nbytes = max(1, int(np.prod(shape, dtype=np.int64)) * dtype.itemsize)
+        cls = self._size_class(nbytes)
+        lst = self.free.get(cls)
+        if lst:
+            ptr = lst.pop()
+            self.kept -= cls
+        else:
+            h = ctypes.c_void_p()
+            if load_library().cledb_host_alloc(cls, ctypes.byref(h)) != 0 or not h.value:
+                return np.empty(shape, dtype)          # no pinned memory left: an ordinary array (slower copies, same result)
+            ptr = h.value
+            self.allocs += 1
+        block = _PinnedBlock(ptr, cls)
+        weakref.finalize(block, self._release, cls, ptr)
+        return np.asarray(block)[:nbytes].view(dtype).reshape(shape)
+
+    def trim(self):
+        for cls, lst in self.free.items():
+            for ptr in lst:
+                load_library().cledb_host_free(ctypes.c_void_p(ptr))
+        self.free.clear()
+        self.kept = 0
+
+
+pinned = PinnedPool()
+
+
+def issue_codes(flags, invout=None):
+    """Issue codes 512 / 1024 / 2048 of cledb_invproc (CLEDB_PROC.py:347-355) per pixel from the device's ``issue_out[npix,2]``
+    flags (see cledb_invert in the header).  Pixels whose Van-Vleck angle lies within 1e-3 deg of a limit are re-evaluated
+    with NumPy from ``invout[npix,k,11]`` - the reference's own float32 chain decides those."""
+    from . import solution
+    vv = (flags[:, 0] & 1).astype(bool)
+    amb = np.flatnonzero(flags[:, 0] & 2)
+    if amb.size and invout is not None:
+        vv[amb] = solution.van_vleck_last(invout[amb])
+    return (vv.astype(np.int32) << 9) | ((flags[:, 1] & 1).astype(np.int32) << 10) | ((flags[:, 1] & 2).astype(np.int32) << 10)
+
+
 class Reduced(ctypes.Structure):
     """``cledb_reduced`` of the header: what the reduced-database presort (cledb_getsubsetiquv / cledb_getsubsetiqud,
     CLEDB_PROC.py:1401-1568) needs, with every transcendental evaluated here by NumPy in the reference's own dtypes."""
@@ -209,6 +302,29 @@ class Spectral(ctypes.Structure):
         r._keep = [np.ascontiguousarray(t, dtype=np.float64) for t in (a, b, c)]
         r.ga, r.gb, r.gc = (t.ctypes.data for t in r._keep)
         return r
+
+
+def partition(key, weight_of_key, nranks):
+    """cledb_partition: ``(order[npix] int32, bounds[nranks+1] int64)``; rank r owns the pixels ``order[bounds[r]:bounds[r+1]]``.
+    ``key``: per-pixel database index (db_enc), ``weight_of_key``: cost of one pixel of each database (its rows) or None."""
+    key = _as(np.asarray(key).reshape(-1), np.int32)
+    w = None if weight_of_key is None else _as(weight_of_key, np.float64)
+    nkeys = int(w.size) if w is not None else (int(key.max()) + 1 if key.size else 1)
+    order = np.empty(key.size, np.int32)
+    bounds = np.empty(int(nranks) + 1, np.int64)
+    rc = load_library().cledb_partition(key.size, _ptr(key), nkeys, _ptr(w), int(nranks), _ptr(order), _ptr(bounds))
+    if rc != 0:
+        raise CledbError('cledb_partition: bad argument (a key outside 0..nkeys-1?)')
+    return order, bounds
+
+
+def comm_unique_id():
+    """128-byte NCCL id for ``Context.comm_init`` (made on rank 0, shipped to the other ranks by the launcher)."""
+    buf = ctypes.create_string_buffer(128)
+    rc = load_library().cledb_comm_unique_id(buf)
+    if rc != 0:
+        raise CledbError('cledb_comm_unique_id failed (%d): NCCL could not be loaded' % rc)
+    return buf.raw
 
 
 class Context:
@@ -357,15 +473,13 @@ class Context:
                                          _ptr(out['rows']), _ptr(out['status']), _ptr(out['ncand'])))
         return out
 
-    def invert(self, mode, sobs, snr, db_id, nsearch, yobs, dobs, aobs, dopp, dbhdr, maxchisq, bcalc, strict_topk=False,
-               precision=PREC_FP32, out=None):
-        """Search + solution building on the device (cledb_invert).  Returns ``(invout[npix,k,11], sfound[npix,k,8], status)``.
-        ``dopp``: per-pixel B_POS (float32 or float64, [npix]) for IQUD, else None."""
+    def _invert_inputs(self, sobs, snr, db_id, yobs, dobs, aobs, dopp):
         sobs = _as(sobs, np.float32).reshape(-1, 8)
         snr = _as(snr, np.float32).reshape(-1, 8)
         npix = sobs.shape[0]
-        db_id = _as(np.broadcast_to(np.asarray(db_id, dtype=np.int32).reshape(-1), (npix,)), np.int32)
-        k = int(nsearch)
+        db_id = np.asarray(db_id)
+        if db_id.dtype != np.int32 or db_id.size != npix or not db_id.flags.c_contiguous:
+            db_id = _as(np.broadcast_to(np.asarray(db_id, dtype=np.int32).reshape(-1), (npix,)), np.int32)
         yobs = _as(np.asarray(yobs).reshape(-1), np.float32)
         dobs = _as(np.asarray(dobs).reshape(-1), np.float32)
         ang = _as(np.asarray(aobs).reshape(-1), np.float32)
@@ -377,15 +491,87 @@ class Context:
             dopp = np.asarray(dopp).reshape(-1)
             is64 = 1 if dopp.dtype == np.float64 else 0
             dopp = _as(dopp, np.float64 if is64 else np.float32)
+        return sobs, snr, npix, db_id, yobs, dobs, rot_cos, rot_sin, dopp, is64
+
+    @staticmethod
+    def result_buffers(npix, k):
+        """Fresh result arrays in pinned host memory (see PinnedPool)."""
+        return dict(invout=pinned.empty((npix, k, 11), np.float32), sfound=pinned.empty((npix, k, 8), np.float32),
+                    status=pinned.empty((npix,), np.uint8), issue=pinned.empty((npix, 2), np.uint8))
+
+    def invert(self, mode, sobs, snr, db_id, nsearch, yobs, dobs, aobs, dopp, dbhdr, maxchisq, bcalc, strict_topk=False,
+               precision=PREC_FP32, out=None):
+        """Search + solution building on the device (cledb_invert).  Returns ``(invout[npix,k,11], sfound[npix,k,8], status)``.
+        ``dopp``: per-pixel B_POS (float32 or float64, [npix]) for IQUD, else None.  ``out``: dict of result arrays to fill
+        (keys invout, sfound, status and optionally issue); default: fresh arrays in pinned memory.  The issue flags of the
+        call are left in ``self.last_issue`` ([npix,2] uint8, see the header)."""
+        sobs, snr, npix, db_id, yobs, dobs, rot_cos, rot_sin, dopp, is64 = self._invert_inputs(sobs, snr, db_id, yobs, dobs, aobs, dopp)
+        k = int(nsearch)
         grid = DbGrid.from_dbhdr(dbhdr)
         if out is None:
-            out = dict(invout=np.empty((npix, k, 11), np.float32), sfound=np.empty((npix, k, 8), np.float32),
-                       status=np.empty(npix, np.uint8))
+            out = self.result_buffers(npix, k)
+        issue = out.get('issue')
         self._check(self.lib.cledb_invert(self.h, int(mode), int(precision), npix, _ptr(sobs), _ptr(snr), _ptr(db_id), k,
                                           _ptr(yobs), _ptr(dobs), _ptr(rot_cos), _ptr(rot_sin), _ptr(dopp), is64, 1,
                                           ctypes.addressof(grid), float(maxchisq), int(bcalc), 1 if strict_topk else 0,
-                                          _ptr(out['invout']), _ptr(out['sfound']), _ptr(out['status'])))
+                                          _ptr(out['invout']), _ptr(out['sfound']), _ptr(out['status']), _ptr(issue)))
+        self.last_issue = issue
         return out['invout'], out['sfound'], out['status']
+
+    # ---- multi-GPU (one process per GPU)
+    def comm_init(self, rank, nranks, unique_id=None):
+        """Collective.  ``unique_id``: the 128 bytes rank 0 got from ``comm_unique_id()`` (shipped by the launcher)."""
+        buf = None
+        if nranks > 1:
+            buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.cledb_comm_init(self.h, int(rank), int(nranks), buf))
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    def comm_destroy(self):
+        self._check(self.lib.cledb_comm_destroy(self.h))
+
+    def comm_info(self):
+        v = np.zeros(4, np.int32)
+        self._check(self.lib.cledb_comm_info(self.h, _ptr(v)))
+        return dict(rank=int(v[0]), nranks=int(v[1]), nccl_version=int(v[2]), nccl=bool(v[3]))
+
+    def allgather_dev(self, send_ptr, recv_ptr, nbytes, stream=None):
+        self._check(self.lib.cledb_allgather_dev(self.h, send_ptr, recv_ptr, int(nbytes), stream))
+
+    def unshard_dev(self, nranks, bounds_ptr, order_ptr, npix, maxcount, nsearch, recv_ptr, invout_ptr, sfound_ptr, status_ptr,
+                    issue_ptr, stream=None):
+        self._check(self.lib.cledb_unshard_dev(self.h, int(nranks), bounds_ptr, order_ptr, int(npix), int(maxcount), int(nsearch),
+                                               recv_ptr, invout_ptr, sfound_ptr, status_ptr, issue_ptr, stream))
+
+    def invert_dev(self, mode, npix, sobs_ptr, snr_ptr, dbid_ptr, nsearch, yobs_ptr, dobs_ptr, rc_ptr, rs_ptr, dopp_ptr, dopp_is_f64,
+                   grid, maxchisq, bcalc, invout_ptr, sfound_ptr, status_ptr, issue_ptr, stream=None, strict_topk=False,
+                   precision=PREC_FP32):
+        """cledb_invert_dev; ``grid``: a ``DbGrid`` whose four table pointers are device addresses."""
+        self._check(self.lib.cledb_invert_dev(self.h, int(mode), int(precision), int(npix), sobs_ptr, snr_ptr, dbid_ptr, int(nsearch),
+                                              yobs_ptr, dobs_ptr, rc_ptr, rs_ptr, dopp_ptr, int(dopp_is_f64), 1, ctypes.addressof(grid),
+                                              float(maxchisq), int(bcalc), 1 if strict_topk else 0, invout_ptr, sfound_ptr, status_ptr,
+                                              issue_ptr, stream))
+
+    def invert_sharded(self, mode, sobs, snr, db_id, nsearch, yobs, dobs, aobs, dopp, dbhdr, maxchisq, bcalc, npix, order, bounds,
+                       root=-1, strict_topk=False, precision=PREC_FP32, out=None):
+        """cledb_invert_sharded: one map of ``npix`` pixels over all ranks of the communicator (collective).  The arrays are
+        those of THIS rank's pixels ``order[bounds[rank]:bounds[rank+1]]``.  Returns ``(invout, sfound, status)`` of the FULL
+        map on the ranks that receive it (``root < 0``: all), else Nones."""
+        sobs, snr, nlocal, db_id, yobs, dobs, rot_cos, rot_sin, dopp, is64 = self._invert_inputs(sobs, snr, db_id, yobs, dobs, aobs, dopp)
+        k = int(nsearch)
+        grid = DbGrid.from_dbhdr(dbhdr)
+        order, bounds = _as(order, np.int32), _as(bounds, np.int64)
+        want = root < 0 or root == getattr(self, 'rank', 0)
+        if out is None and want:
+            out = self.result_buffers(int(npix), k)
+        o = out or dict(invout=None, sfound=None, status=None, issue=None)
+        self._check(self.lib.cledb_invert_sharded(self.h, int(mode), int(precision), nlocal, _ptr(sobs), _ptr(snr), _ptr(db_id), k,
+                                                  _ptr(yobs), _ptr(dobs), _ptr(rot_cos), _ptr(rot_sin), _ptr(dopp), is64, 1,
+                                                  ctypes.addressof(grid), float(maxchisq), int(bcalc), 1 if strict_topk else 0,
+                                                  int(npix), _ptr(order), _ptr(bounds), int(root),
+                                                  _ptr(o['invout']), _ptr(o['sfound']), _ptr(o['status']), _ptr(o.get('issue'))))
+        self.last_issue = o.get('issue')
+        return o['invout'], o['sfound'], o['status']
 
     def match_reduced(self, mode, sobs, snr, db_id, nsearch, sobs_dopp, dbhdr, precision=PREC_FP32, tie_order=None):
         """Raw top-``nsearch`` of every pixel over its reduced database (``reduced=True``); dict as ``match`` plus
@@ -425,11 +611,12 @@ class Context:
         red = Reduced.build(mode, sobs, sobs_dopp, dbhdr, tie_order)
         grid = DbGrid.from_dbhdr(dbhdr)
         invout, sfound = np.empty((npix, k, 11), np.float32), np.empty((npix, k, 8), np.float32)
-        status = np.empty(npix, np.uint8)
+        status, issue = np.empty(npix, np.uint8), np.empty((npix, 2), np.uint8)
         self._check(self.lib.cledb_invert_reduced(self.h, int(mode), int(precision), npix, _ptr(sobs), _ptr(snr), _ptr(db_id), k,
                                                   ctypes.addressof(red), _ptr(yobs), _ptr(dobs), _ptr(rot_cos), _ptr(rot_sin),
                                                   _ptr(dopp0), is64, 1, ctypes.addressof(grid), float(maxchisq), int(bcalc),
-                                                  1 if strict_topk else 0, _ptr(invout), _ptr(sfound), _ptr(status)))
+                                                  1 if strict_topk else 0, _ptr(invout), _ptr(sfound), _ptr(status), _ptr(issue)))
+        self.last_issue = issue
         return invout, sfound, status
 
     def match_dev(self, mode, npix, sobs_ptr, snr_ptr, dbid_ptr, nsearch, idx_ptr, chi_ptr, chi64_ptr=None, kpos_ptr=None,

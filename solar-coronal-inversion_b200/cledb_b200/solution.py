@@ -212,3 +212,17 @@ def update_issuemask(issuemask, invout, snr, nx, ny):
             add = cond & ((bits & code) == 0)
             m[add] += code
     return issuemask
+
+
+def apply_issue_codes(issuemask, codes):
+    """Add the per-pixel issue codes (a sum of 512 / 1024 / 2048, ``native.issue_codes``) to both lines of ``issuemask``,
+    each code only where it is not yet set (CLEDB_PROC.py:347-355).  Adding a power of two whose bit is clear is an OR."""
+    if isinstance(issuemask, np.ndarray) and np.issubdtype(issuemask.dtype, np.integer):
+        issuemask[:, :, 0:2] |= codes[:, :, None].astype(issuemask.dtype)
+        return issuemask
+    for line in range(2):                                  # exotic mask types: the reference's own arithmetic
+        mm = issuemask[:, :, line]
+        for code in (512, 1024, 2048):
+            add = ((codes & code) != 0) & ((mm.astype(np.int64) & code) == 0)
+            mm[add] += code
+    return issuemask

@@ -48,6 +48,7 @@ extern "C" int cledb_destroy(cledb_ctx* ctx) {
     if (!ctx) return CLEDB_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    cledb_comm_destroy(ctx);
     std::vector<int> ids;
     for (auto& kv : ctx->slot_of_id) ids.push_back(kv.first);
     for (int id : ids) cledb_db_drop(ctx, id);
@@ -125,6 +126,23 @@ extern "C" int cledb_measure_fp32_peak(cledb_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return CLEDB_ERR_ARG;
     CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
     return measure_fp32_peak(ctx, tflops);
+}
+
+// pinned (page-locked) host memory for the binding's staging buffers: copies to and from it run at full PCIe speed and
+// asynchronously; pageable memory goes through the driver's bounce buffers at about half of that
+extern "C" int cledb_host_alloc(int64_t bytes, void** out) {
+    if (!out || bytes <= 0) return CLEDB_ERR_ARG;
+    *out = nullptr;
+    if (cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return CLEDB_ERR_NOMEM;
+    }
+    return CLEDB_OK;
+}
+extern "C" int cledb_host_free(void* p) {
+    if (!p) return CLEDB_OK;
+    return cudaFreeHost(p) == cudaSuccess ? CLEDB_OK : CLEDB_ERR_CUDA;
 }
 
 extern "C" int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split) {

@@ -77,8 +77,11 @@ struct Workspace {
 
 }  // namespace cledb
 
+struct cledb_comm;                                 // multi-GPU state (comm.cu)
+
 struct cledb_ctx {
     int device = 0;
+    cledb_comm* comm = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;            // device-to-host copies of finished chunks (big maps)
     cudaDeviceProp prop;
@@ -176,5 +179,6 @@ int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsea
                  const float* dobs, const float* rot_cos, const float* rot_sin, const void* dopp, int dopp_is_f64,
                  int64_t dopp_stride, const cledb_dbgrid& grid_dev, double maxchisq, int bcalc, int strict_topk,
                  const int32_t* idx, const float* chi, const double* chi64, const int32_t* kpos, const float* rows,
-                 const uint8_t* status, const int32_t* nan_slots, float* invout, float* sfound, cudaStream_t st);
+                 const uint8_t* status, const int32_t* nan_slots, float* invout, float* sfound, cudaStream_t st,
+                 const float* snr = nullptr, uint8_t* issue_out = nullptr);
 }  // namespace cledb

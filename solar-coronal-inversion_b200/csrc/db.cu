@@ -204,19 +204,20 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
     int64_t cnt[kParts] = {0, 0, 0}, nnan = 0;
     for (int64_t i = 0; i < n; ++i) {
         const float* r = db + i * 8;
+        // A row whose V1 is NaN is never a candidate in the reference (np.sign(NaN) == ... is False, CLEDB_PROC.py:974; the
+        // "crutch" of :1148 drops it in IQUD), whatever its other components hold - e.g. the all-NaN row that the division
+        // by I1 == 0 leaves at a zero-intensity grid point.  Such rows are left out before anything else is checked.
+        if (std::isnan(r[3])) { cls[i] = -1; ++nnan; continue; }
         if (r[0] != 1.0f) {
-            ctx->err = "cledb_db_put: component 0 of row " + std::to_string(i) + " is not exactly 1 (database must be normalised by I1, CLEDB_PREPINV.py:306-317)";
+            ctx->err = "cledb_db_put: component 0 of candidate row " + std::to_string(i) + " is not exactly 1 (database must be normalised by I1, CLEDB_PREPINV.py:306-317)";
             return CLEDB_ERR_DBFORMAT;
         }
-        if (std::isnan(r[3])) { cls[i] = -1; ++nnan; continue; }
         cls[i] = 0;
         if (!(std::isfinite(r[1]) && std::isfinite(r[2]) && std::isfinite(r[4]) && std::isfinite(r[5]) && std::isfinite(r[6]))) {
             ctx->err = "cledb_db_put: non-finite Stokes I/Q/U in candidate row " + std::to_string(i);
             return CLEDB_ERR_DBFORMAT;
         }
     }
-    if (cledb_db_drop(ctx, db_id) != CLEDB_OK) ctx->err.clear();   // replace an existing database of this id
-
     HostDb h;
     std::memset(&h.slot, 0, sizeof(DbSlot));
     // ---- block exponents per component (int16 encoding); scale = 2^-shift
@@ -428,6 +429,12 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
         ctx->err = std::string("cledb_db_put: ") + what;
         return CLEDB_ERR_NOMEM;
     };
+    auto fail_cuda = [&](const char* what) {
+        const cudaError_t e = cudaGetLastError();
+        free_db(h);
+        ctx->err = std::string("cledb_db_put: ") + what + " (" + cudaGetErrorString(e) + ")";
+        return CLEDB_ERR_CUDA;
+    };
     if (cudaMalloc(&h.d_tiles, tiles.size()) != cudaSuccess) return fail("out of device memory (tiles)");
     if (cudaMalloc(&h.d_vcomp, vcomp.size()) != cudaSuccess) return fail("out of device memory (V components)");
     if (cudaMalloc(&h.d_perm, perm.size() * 4) != cudaSuccess) return fail("out of device memory (perm)");
@@ -436,14 +443,14 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
     if (cudaMalloc(&h.d_row_kpos, row_kpos.size() * 4) != cudaSuccess) return fail("out of device memory (kpos)");
     if (blocked) {
         if (cudaMalloc(&h.d_boxes, boxes.size() * 4) != cudaSuccess) return fail("out of device memory (tile bounds)");
-        CLEDB_CUDA(ctx, cudaMemcpy(h.d_boxes, boxes.data(), boxes.size() * 4, cudaMemcpyHostToDevice));
+        if (cudaMemcpy(h.d_boxes, boxes.data(), boxes.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail_cuda("upload failed");
     }
-    CLEDB_CUDA(ctx, cudaMemcpy(h.d_tiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
-    CLEDB_CUDA(ctx, cudaMemcpy(h.d_vcomp, vcomp.data(), vcomp.size(), cudaMemcpyHostToDevice));
-    CLEDB_CUDA(ctx, cudaMemcpy(h.d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
-    CLEDB_CUDA(ctx, cudaMemcpy(h.d_invperm, invperm.data(), invperm.size() * 4, cudaMemcpyHostToDevice));
-    if (nnan > 0) CLEDB_CUDA(ctx, cudaMemcpy(h.d_kept_rank, kept_rank.data(), kept_rank.size() * 4, cudaMemcpyHostToDevice));
-    CLEDB_CUDA(ctx, cudaMemcpy(h.d_row_kpos, row_kpos.data(), row_kpos.size() * 4, cudaMemcpyHostToDevice));
+    if (cudaMemcpy(h.d_tiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice) != cudaSuccess) return fail_cuda("upload failed");
+    if (cudaMemcpy(h.d_vcomp, vcomp.data(), vcomp.size(), cudaMemcpyHostToDevice) != cudaSuccess) return fail_cuda("upload failed");
+    if (cudaMemcpy(h.d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail_cuda("upload failed");
+    if (cudaMemcpy(h.d_invperm, invperm.data(), invperm.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail_cuda("upload failed");
+    if (nnan > 0) if (cudaMemcpy(h.d_kept_rank, kept_rank.data(), kept_rank.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail_cuda("upload failed");
+    if (cudaMemcpy(h.d_row_kpos, row_kpos.data(), row_kpos.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail_cuda("upload failed");
     h.bytes = (int64_t)(tiles.size() + vcomp.size() + perm.size() * 4 + invperm.size() * 4 + kept_rank.size() * 4 + row_kpos.size() * 4);
     h.slot.tiles = h.d_tiles;
     h.slot.vcomp = h.d_vcomp;
@@ -458,6 +465,9 @@ extern "C" int cledb_db_put(cledb_ctx* ctx, int db_id, const float* db, int64_t 
     h.slot.boxes = h.d_boxes;
     h.slot.sboxes = h.d_boxes ? h.d_boxes + sbox_off : nullptr;
 
+    // the new database is complete on the device: only now is an existing database of this id replaced, so that a
+    // failed put (format, out of memory) leaves the old one usable
+    if (ctx->slot_of_id.count(db_id) && cledb_db_drop(ctx, db_id) != CLEDB_OK) { free_db(h); return CLEDB_ERR_CUDA; }
     int slot;
     if (!ctx->free_slots.empty()) { slot = ctx->free_slots.back(); ctx->free_slots.pop_back(); ctx->dbs[slot] = h; }
     else { slot = (int)ctx->dbs.size(); ctx->dbs.push_back(h); }

@@ -380,13 +380,13 @@ def test_sdb_preprocess_surface(golden_dir, tmp_path, monkeypatch):
     assert [hashlib.sha256(np.ascontiguousarray(d).tobytes()).hexdigest() for d in database] == [str(x) for x in g['mini_sha']]
     assert same(dbhdr[0], g['mini_hdr_g'])
     # the arrays are resident: an inversion with them uploads nothing new
-    before = len(procinv._resident[procinv.OPTIONS['device']].ids)
+    before = len(procinv._resident[procinv.OPTIONS["device"]].entries)
     obs = synth.make_observation(nx, ny, database, db_enc=db_enc, seed=3)
     hdr = synth.make_dbhdr(3, 12, 8)
     iss = obs['issuemask'].copy()
     inv, sf = procinv.cledb_invproc(obs['sobs_totrot'], obs['sobs_dopp'], database, db_enc, g['mini_yobs'], obs['aobs'], g['mini_dobs'],
                                     obs['snr'], iss, hdr, kv, 4, 1000, 0, False, 1, False, 0)
-    assert len(procinv._resident[procinv.OPTIONS['device']].ids) == before
+    assert len(procinv._resident[procinv.OPTIONS["device"]].entries) == before
     iss2 = obs['issuemask'].copy()
     ref, ref_sf = orc.invert_map(obs['sobs_totrot'], obs['sobs_dopp'], database, db_enc, g['mini_yobs'], obs['aobs'], g['mini_dobs'],
                                  obs['snr'], iss2, hdr, kv, 4, 1000, 0, False)
