@@ -4,8 +4,9 @@ libcledb_b200.so, either directly (cledb_b200.native) or through the reference-s
 
 Tolerances (north_star: "bit-exact top-nsearch indices except chi^2 near-ties within 1e-5 relative"):
   fp64 validation kernel : indices, chi^2 (float64) and every derived column bit-exact against the reference
-  fp32 production kernel : chi^2 within rtol 2e-5 (+1e-9 abs); an index may differ from the oracle only where the
-                           oracle's own chi^2 of the two candidates agree within that tolerance (near-tie)
+  fp32 production kernel : chi^2 within rtol 1e-5 (+1e-9 abs); an index may differ from the oracle only where the
+                           oracle's own chi^2 of the two candidates agree within that tolerance (near-tie) - proven member
+                           by member (oracle.compare), never by a fraction of equal indices
   B, Bx, By, Bz, sfound  : rtol 1e-6 given equal index; ne, y, gx, phi, theta bit-equal given equal index
 """
 import os
@@ -17,7 +18,7 @@ import oracle.cledb_oracle as orc
 import cledb_b200.synth as synth
 from cledb_b200 import native, codec
 from helpers import hdr_from_g, same
-from oracle.compare import check_raw_against_oracle, CHI_RTOL, CHI_ATOL
+from oracle.compare import check_raw_against_oracle, check_invout_against_reference, CHI_RTOL, CHI_ATOL
 
 pytestmark = pytest.mark.gpu
 
@@ -151,14 +152,12 @@ def test_invproc_golden_fp32(golden_dir, tag):
     hdr = hdr_from_g(g['hdr_g'])
     inv, sf, iss = run_surface(g['cfg_' + tag], g, dbs, hdr, 10, 12, native.PREC_FP32, native.ENC_F32, 'sobs_' + tag)
     ref_inv, ref_sf = g['invout_' + tag], g['sfound_' + tag]
-    same_idx = inv[..., 0] == ref_inv[..., 0]
-    assert same_idx.mean() > 0.98
-    np.testing.assert_allclose(inv[..., 1], ref_inv[..., 1], rtol=CHI_RTOL, atol=CHI_ATOL)
-    m = same_idx
-    assert np.array_equal(inv[m][:, [2, 3, 4, 6, 7]], ref_inv[m][:, [2, 3, 4, 6, 7]])
-    np.testing.assert_allclose(inv[m][:, [5, 8, 9, 10]], ref_inv[m][:, [5, 8, 9, 10]], rtol=1e-6, atol=0)
-    np.testing.assert_allclose(sf[m], ref_sf[m], rtol=1e-6, atol=0)
-    assert (iss == g['issuemask_' + tag]).mean() > 0.98
+    mode, k, mx = int(g['cfg_' + tag][0]), int(g['cfg_' + tag][2]), float(g['cfg_' + tag][3])
+    n = 10 * 12
+    slots, subs = check_invout_against_reference(inv.reshape(n, k, 11), ref_inv.reshape(n, k, 11), mode, g['sobs_' + tag].reshape(n, 8),
+                                                 g['snr'].reshape(n, 8), dbs, g['db_enc'].reshape(-1), mx, sf.reshape(n, k, 8),
+                                                 ref_sf.reshape(n, k, 8), iss.reshape(n, 2), g['issuemask_' + tag].reshape(n, 2))
+    assert subs <= 0.03 * slots, (slots, subs)
 
 
 @pytest.mark.parametrize('tag', TAGS)
@@ -209,8 +208,11 @@ def test_full_db_golden(golden_dir):
                 assert same(iss, g['issuemask_' + tag])
                 np.testing.assert_allclose(sf, g['sfound_' + tag], rtol=1e-6, atol=0)
             else:
-                assert (inv[..., 0] == ref[..., 0]).mean() > 0.97
-                np.testing.assert_allclose(inv[..., 1], ref[..., 1], rtol=CHI_RTOL, atol=CHI_ATOL)
+                slots, subs = check_invout_against_reference(inv.reshape(36, 8, 11), ref.reshape(36, 8, 11), int(iqud), g['sobs'].reshape(36, 8),
+                                                             g['snr'].reshape(36, 8), [db], np.zeros(36, np.int32), 1000,
+                                                             sf.reshape(36, 8, 8), g['sfound_' + tag].reshape(36, 8, 8), iss.reshape(36, 2),
+                                                             g['issuemask_' + tag].reshape(36, 2))
+                assert subs <= 0.03 * slots, (slots, subs)
     procinv.OPTIONS.update(precision=0, dbencoding=0)
     procinv.release_databases()
 
@@ -390,8 +392,11 @@ def test_sdb_preprocess_surface(golden_dir, tmp_path, monkeypatch):
     iss2 = obs['issuemask'].copy()
     ref, ref_sf = orc.invert_map(obs['sobs_totrot'], obs['sobs_dopp'], database, db_enc, g['mini_yobs'], obs['aobs'], g['mini_dobs'],
                                  obs['snr'], iss2, hdr, kv, 4, 1000, 0, False)
-    assert (inv[..., 0] == ref[..., 0]).mean() > 0.97
-    np.testing.assert_allclose(inv[..., 1], ref[..., 1], rtol=CHI_RTOL, atol=CHI_ATOL)
+    n = nx * ny
+    slots, subs = check_invout_against_reference(inv.reshape(n, 4, 11), ref.reshape(n, 4, 11), 0, obs['sobs_totrot'].reshape(n, 8),
+                                                 obs['snr'].reshape(n, 8), [np.asarray(d) for d in database], db_enc.reshape(-1), 1000,
+                                                 sf.reshape(n, 4, 8), ref_sf.reshape(n, 4, 8), iss.reshape(n, 2), iss2.reshape(n, 2))
+    assert subs <= 0.03 * slots, (slots, subs)
     # ingest errors keep the reference's convention
     params.verbose = 0
     params.dbdir = str(tmp_path / 'nowhere') + '/'
@@ -424,9 +429,12 @@ def test_reduced_mode_golden(golden_dir, tag, where):
             np.testing.assert_allclose(sf, ref_sf, rtol=1e-6, atol=0)
             assert same(iss, g['issuemask_' + tag])
         else:
+            # the reduced search's candidate list is not the full database: a differing index must carry (within the parity
+            # tolerance) the chi^2 the reference has in that slot - the near-tie criterion on the values themselves
             m = inv[..., 0] == ref_inv[..., 0]
-            assert m.mean() > 0.97
             np.testing.assert_allclose(inv[..., 1], ref_inv[..., 1], rtol=CHI_RTOL, atol=CHI_ATOL)
+            assert ((inv[..., 0] >= 0) == (ref_inv[..., 0] >= 0)).all()
+            assert (~m).sum() <= 0.03 * m.size, ((~m).sum(), m.size)
             np.testing.assert_allclose(sf[m], ref_sf[m], rtol=1e-6, atol=0)
     procinv.OPTIONS.update(precision=0, dbencoding=0, solution='device', reduced_tie_order=None)
     procinv.release_databases()
@@ -728,3 +736,241 @@ def test_pruning_randomised_databases(ctx, seed):
             for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
                 assert np.array_equal(res[False][key], res[True][key], equal_nan=True), (encoding, mode, k, key)
 
+
+
+@pytest.mark.parametrize('tag', ['iquv_b0', 'iquv_b2', 'iqud'])
+def test_cle_type_surface(golden_dir, tag):
+    """CLE-type header (dbtype 0) through cledb_invproc: the search runs on the GPU, the solutions (density index, Baumbach
+    density of cledb_elecdens, CLEDB_PROC.py:1688-1697, 1744-1747) on the host path.  Golden = the unmodified reference."""
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    from test_oracle_golden import cle_header
+    g = np.load(os.path.join(golden_dir, 'cle_type.npz'))
+    hdr = cle_header(g)
+    iqud, bcalc, k, mx = (int(v) for v in g['cfg_' + tag])
+    nx, ny = g['sobs'].shape[:2]
+    kv = synth.make_keyvals(nx, ny, cdelt=float(g['cdelt']))
+    ref_inv, ref_sf = g['invout_' + tag], g['sfound_' + tag]
+    for prec in (native.PREC_FP64, native.PREC_FP32):
+        procinv.OPTIONS.update(precision=prec, dbencoding=native.ENC_F32, solution='device')
+        iss = np.zeros((nx, ny, 2), np.int32)
+        inv, sf = procinv.cledb_invproc(g['sobs'], g['sobs_dopp'], [g['db']], np.zeros((nx, ny), np.int32), g['yobs'], g['aobs'], g['dobs'],
+                                        g['snr'], iss, hdr, kv, k, mx, bcalc, bool(iqud), 2, False, 0)
+        if prec == native.PREC_FP64:
+            assert np.array_equal(inv[..., [0, 1, 3, 4, 6, 7]], ref_inv[..., [0, 1, 3, 4, 6, 7]])
+            np.testing.assert_allclose(inv[..., [2, 5, 8, 9, 10]], ref_inv[..., [2, 5, 8, 9, 10]], rtol=1e-6, atol=0)
+            np.testing.assert_allclose(sf, ref_sf, rtol=1e-6, atol=0)
+            assert same(iss, g['issuemask_' + tag])
+        else:
+            n = nx * ny
+            m = inv[..., 0] == ref_inv[..., 0]
+            np.testing.assert_allclose(inv[..., 1][m], ref_inv[..., 1][m], rtol=CHI_RTOL, atol=CHI_ATOL)
+            np.testing.assert_allclose(inv[..., 2][m], ref_inv[..., 2][m], rtol=1e-6, atol=0)
+            slots, subs = check_invout_against_reference(inv.reshape(n, k, 11)[..., [0, 1, 3, 3, 4, 5, 6, 7, 8, 9, 10]],
+                                                         ref_inv.reshape(n, k, 11)[..., [0, 1, 3, 3, 4, 5, 6, 7, 8, 9, 10]], iqud,
+                                                         g['sobs'].reshape(n, 8), g['snr'].reshape(n, 8), [g['db']], np.zeros(n, np.int32), mx,
+                                                         sf.reshape(n, k, 8), ref_sf.reshape(n, k, 8))
+            assert subs <= 0.03 * slots
+    procinv.OPTIONS.update(precision=0, dbencoding=0)
+    procinv.release_databases()
+
+
+@pytest.mark.parametrize('encoding', [native.ENC_F32, native.ENC_I16])
+def test_zero_intensity_rows_are_left_out(ctx, encoding):
+    """A grid point with I1 == 0 leaves an all-NaN row after the division by I1 (CLEDB_PREPINV.py:306-317).  The reference
+    never selects it - np.sign(NaN) == ... is False (CLEDB_PROC.py:974), the IQUD filter drops NaN V1 (:1148) - so
+    cledb_db_put must take the database and leave those rows out; the search equals the oracle's on the same array."""
+    db = synth.make_database(10, 33, ngx=4, nbphi=24, nbtheta=12).copy()
+    flat = db.reshape(-1, 8)
+    obs = synth.make_observation(12, 10, [db], seed=9, frac_nan=0.03, frac_zero=0.03)
+    dead = np.random.default_rng(1).choice(flat.shape[0], 25, replace=False)
+    flat[dead] = np.nan                                   # 0/0 in every component, component 0 included
+    flat[dead[:5], 0] = np.inf                            # x/0 with x != 0
+    ctx.db_put(0, db, encoding)
+    assert ctx.db_info(0)['nnan'] == 25
+    dec = ctx.db_decoded(0)
+    sobs, snr = obs['sobs_totrot'].reshape(-1, 8), obs['snr'].reshape(-1, 8)
+    ids = np.zeros(sobs.shape[0], np.int32)
+    for mode in (native.MODE_IQUV, native.MODE_IQUD):
+        raw = ctx.match(mode, sobs, snr, ids, 8, want_chi64=True)
+        searched, reordered = check_raw_against_oracle(raw, mode, sobs, snr, [dec], ids, 8)
+        assert searched > 100 and reordered <= 4
+        assert not np.isin(raw['idx'], dead).any()
+        raw64 = ctx.match(mode, sobs, snr, ids, 8, precision=native.PREC_FP64, want_chi64=True)
+        check_raw_against_oracle(raw64, mode, sobs, snr, [dec], ids, 8, exact=True)
+    # the oracle on the caller's own array (NaN rows and all) picks the same rows: they never were candidates
+    ref = orc.raw_topk(0, sobs[5], snr[5], flat, 8)
+    if ref is not None:
+        assert np.array_equal(ref[0], raw64['idx'][5][:len(ref[0])]) or encoding == native.ENC_I16
+    # a failed put leaves the database that was there
+    bad = db.copy()
+    bad.reshape(-1, 8)[3, 0] = 0.5
+    assert not np.isnan(bad.reshape(-1, 8)[3, 3])
+    with pytest.raises(native.CledbError):
+        ctx.db_put(0, bad, encoding)
+    again = ctx.match(native.MODE_IQUD, sobs, snr, ids, 8)
+    assert np.array_equal(again['idx'], raw['idx'])
+    ctx.db_drop(0)
+
+
+def test_resident_database_follows_the_callers_arrays():
+    """a freed database whose address NumPy hands to the next array of the same shape, and an in-place edit
+    of a resident array, must both reach the device - the inversion always searches the array it was given."""
+    import gc
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    procinv.OPTIONS.update(precision=native.PREC_FP64, dbencoding=native.ENC_F32, solution='device')
+    procinv.release_databases()
+    hdr = synth.make_dbhdr(4, 24, 12)
+    obs = None
+    for trial in range(6):
+        db = synth.make_database(10 + trial, 33, ngx=4, nbphi=24, nbtheta=12)
+        if obs is None:
+            obs = synth.make_observation(6, 6, [db], seed=9)
+        iss = obs['issuemask'].copy()
+        inv, sf = procinv.cledb_invproc(obs['sobs_totrot'], obs['sobs_dopp'], [db], obs['db_enc'], obs['yobs'], obs['aobs'], obs['dobs'],
+                                        obs['snr'], iss, hdr, obs['keyvals'], 4, 1e9, 0, False, 1, False, 0)
+        ref, _ = orc.invert_map(obs['sobs_totrot'], obs['sobs_dopp'], [db], obs['db_enc'], obs['yobs'], obs['aobs'], obs['dobs'], obs['snr'],
+                                obs['issuemask'].copy(), hdr, obs['keyvals'], 4, 1e9, 0, False)
+        assert np.array_equal(inv[..., :2], ref[..., :2]), 'trial %d searched a stale database' % trial
+        if trial == 3:                                     # in-place edit of the resident array
+            db[..., 1] *= np.float32(1.25)
+            inv, _ = procinv.cledb_invproc(obs['sobs_totrot'], obs['sobs_dopp'], [db], obs['db_enc'], obs['yobs'], obs['aobs'], obs['dobs'],
+                                           obs['snr'], obs['issuemask'].copy(), hdr, obs['keyvals'], 4, 1e9, 0, False, 1, False, 0)
+            ref, _ = orc.invert_map(obs['sobs_totrot'], obs['sobs_dopp'], [db], obs['db_enc'], obs['yobs'], obs['aobs'], obs['dobs'],
+                                    obs['snr'], obs['issuemask'].copy(), hdr, obs['keyvals'], 4, 1e9, 0, False)
+            assert np.array_equal(inv[..., :2], ref[..., :2]), 'in-place edit did not reach the device'
+        del db
+        gc.collect()
+    res = procinv._resident[procinv.OPTIONS['device']]
+    assert len(res.entries) <= 1
+    procinv.OPTIONS.update(precision=0, dbencoding=0)
+    procinv.release_databases()
+
+
+def test_results_are_fresh_pinned_arrays_and_issue_flags_match_numpy(ctx):
+    """cledb_invproc returns arrays the caller owns (a second call does not overwrite the first result although both live
+    in the pinned pool), and the issue codes k_build evaluates on the device equal the NumPy statement of
+    CLEDB_PROC.py:323-355 on the same invout, for a whole 256x256 map in both modes."""
+    import CLEDB_PROC.CLEDB_PROC as procinv
+    from cledb_b200 import solution
+    procinv.OPTIONS.update(precision=0, dbencoding=native.ENC_I16, solution='device', pruning=ctx.pruning_default)
+    db = synth.make_database(9, 40)
+    hdr = synth.make_dbhdr()
+    obs = synth.make_observation(256, 256, [db], seed=7)
+    snr = obs['snr'].copy()
+    snr[::5, ::3, 0] = 0.5                                  # code 2048 somewhere
+    for iqud, bcalc in ((False, 0), (True, 3)):
+        iss = np.zeros((256, 256, 2), np.int32)
+        iss[::4, :, 0] = 512 + 32                           # already set: not added twice
+        iss0 = iss.copy()
+        inv, sf = procinv.cledb_invproc(obs['sobs_totrot'], obs['sobs_dopp'], [db], obs['db_enc'], obs['yobs'], obs['aobs'], obs['dobs'],
+                                        snr, iss, hdr, obs['keyvals'], 8, 1000, bcalc, iqud, 1, False, 0)
+        keep_inv, keep_sf = inv.copy(), sf.copy()
+        ref_iss = iss0.copy()
+        solution.update_issuemask(ref_iss, inv, snr, 256, 256)
+        assert np.array_equal(iss, ref_iss)
+        assert ((iss & 512) != 0).any() and ((iss & 1024) != 0).any() and ((iss & 2048) != 0).any()
+        inv2, sf2 = procinv.cledb_invproc(obs['sobs_totrot'][::-1].copy(), obs['sobs_dopp'][::-1].copy(), [db], obs['db_enc'], obs['yobs'],
+                                          obs['aobs'], obs['dobs'], snr, iss0.copy(), hdr, obs['keyvals'], 8, 1000, bcalc, iqud, 1, False, 0)
+        assert np.array_equal(inv, keep_inv, equal_nan=True) and np.array_equal(sf, keep_sf, equal_nan=True), 'first result overwritten'
+        assert not np.shares_memory(inv, inv2)
+    del inv, sf, inv2, sf2
+    procinv.OPTIONS.update(precision=0, dbencoding=0, pruning=True)
+    procinv.release_databases()
+
+
+@pytest.mark.parametrize('mode', [native.MODE_IQUV, native.MODE_IQUD])
+def test_config5_shaped_map_against_the_oracle(ctx, mode):
+    """BASELINE config 5 shape on one GPU: a 512x512 map whose pixels choose among 64 full-size databases through
+    cledb_db_select (8 heights x 9 densities on disk; the reference's slice never reaches the last density of a height),
+    1 % NaN and 1 % all-zero pixels; the whole map is searched (pruned and brute force through the fixture), 300 seeded
+    pixels are compared with the oracle pixel by pixel, and the fused call with the oracle's full inversion on 40 of them."""
+    nx = 512
+    heights, dens = [105 + 3 * i for i in range(8)], [700 + 30 * j for j in range(9)]
+    names = sorted('DB_h%03d_d%d.npy' % (h, d) for h in heights for d in dens)
+    table = orc.file_table(names)
+    kv = synth.make_keyvals(nx, nx)
+    aobs, yobs = synth.geometry(nx, nx, kv)
+    rng = np.random.default_rng(77)
+    dobs = rng.uniform(7.0, 9.5, (nx, nx)).astype(np.float32)
+    sel = ctx.db_select(yobs, dobs, table)
+    assert (sel >= 0).all()
+    used = np.unique(sel)
+    assert used.size >= 48, used.size
+    lut = np.full(len(names), -1, np.int32)
+    lut[used] = np.arange(used.size)
+    db_enc = lut[sel].reshape(nx, nx)
+    dbs = []
+    for f in used:
+        h, d = int(names[f][4:7]), int(names[f].split('_d')[1].split('.')[0])
+        dbs.append(synth.make_database(h - 101, (d - 600) // 5))
+    for i, db in enumerate(dbs):
+        ctx.db_put(i, db, native.ENC_I16)
+    obs = synth.make_observation(nx, nx, dbs, db_enc=db_enc, seed=5, frac_nan=0.01, frac_zero=0.01)
+    sobs, snr, ids = obs['sobs_totrot'].reshape(-1, 8), obs['snr'].reshape(-1, 8), db_enc.reshape(-1).astype(np.int32)
+    raw = ctx.match(mode, sobs, snr, ids, 8)
+    pick = np.random.default_rng(11).choice(nx * nx, 300, replace=False)
+    need = np.unique(np.append(ids[pick], 0))
+    dec = {int(i): ctx.db_decoded(int(i)) for i in need}
+    sub = {k: (v[pick] if v is not None else None) for k, v in raw.items()}
+    searched, reordered = check_raw_against_oracle(sub, mode, sobs[pick], snr[pick], dec, ids[pick], 8)
+    assert searched >= 285 and reordered <= 12, (searched, reordered)
+    assert need.size >= 40, 'the sample touches most databases'
+    ok = raw['status'] == native.PIX_SEARCHED
+    assert 0.97 < ok.mean() < 0.99 and (raw['status'] == native.PIX_NULL).sum() > 0.015 * nx * nx
+    assert (np.diff(raw['chi'][ok], axis=1) >= 0).all()
+    # the fused call: solutions and issue flags on the device against the oracle's cledb_invproc on 40 of the pixels
+    hdr = synth.make_dbhdr()
+    bcalc = 3 if mode == native.MODE_IQUD else 0
+    dopp0 = obs['sobs_dopp'].reshape(nx * nx, -1)[:, 0] if mode == native.MODE_IQUD else None
+    inv, sf, st = ctx.invert(mode, sobs, snr, ids, 8, yobs, dobs, aobs, dopp0, hdr, 1000, bcalc)
+    codes = native.issue_codes(ctx.last_issue, inv)
+    few = pick[:40]
+    pix = [(int(p // nx), int(p % nx)) for p in few]
+    decl = [dec.get(i, None) for i in range(len(dbs))]
+    decl = [d.reshape(dbs[0].shape) if d is not None else None for d in decl]
+    iss = np.zeros((nx, nx, 2), np.int32)
+    ref, ref_sf = orc.invert_map(obs['sobs_totrot'], obs['sobs_dopp'], decl, db_enc, yobs, aobs, dobs, obs['snr'], iss, hdr, kv, 8, 1000,
+                                 bcalc, mode == native.MODE_IQUD, pixels=pix)
+    mine = np.zeros((nx * nx, 2), np.int32)
+    mine |= codes[:, None]
+    slots, subs = check_invout_against_reference(inv[few], ref.reshape(-1, 8, 11)[few], mode, sobs[few], snr[few], dec, ids[few], 1000,
+                                                 sf[few], ref_sf.reshape(-1, 8, 8)[few], mine[few], iss.reshape(-1, 2)[few])
+    assert subs <= 6, (slots, subs)
+    for i in range(len(dbs)):
+        ctx.db_drop(i)
+
+
+def test_sharded_call_on_one_rank_equals_the_plain_call():
+    """cledb_invert_sharded with a one-rank communicator (no NCCL needed): partition, packed send buffer, gather (a device
+    copy), scatter kernel - the full maps equal cledb_invert's bit for bit; a multi-database map, both modes.  The N > 1
+    path runs in tests/test_multigpu.py on a box with two GPUs."""
+    c = native.Context(0)
+    c.comm_init(0, 1)
+    assert c.comm_info() == dict(rank=0, nranks=1, nccl_version=c.comm_info()['nccl_version'], nccl=False)
+    dbs = [synth.make_database(5 + 3 * i, 30 + 2 * i, ngx=5, nbphi=36, nbtheta=18) for i in range(3)]
+    nx, ny = 40, 33
+    enc = np.random.default_rng(5).integers(0, 3, (nx, ny)).astype(np.int32)
+    obs = synth.make_observation(nx, ny, dbs, db_enc=enc, seed=21, frac_nan=0.03, frac_zero=0.03)
+    hdr = synth.make_dbhdr(5, 36, 18)
+    for i, d in enumerate(dbs):
+        c.db_put(i, d, native.ENC_I16)
+    n = nx * ny
+    sobs, snr, ids = obs['sobs_totrot'].reshape(n, 8), obs['snr'].reshape(n, 8), enc.reshape(-1)
+    y, d, a = obs['yobs'].reshape(-1), obs['dobs'].reshape(-1), obs['aobs'].reshape(-1)
+    order, bounds = native.partition(ids, [float(x.size // 8) for x in dbs], 1)
+    assert bounds.tolist() == [0, n] and (np.diff(ids[order]) >= 0).all()
+    for mode, bcalc in ((native.MODE_IQUV, 0), (native.MODE_IQUD, 3)):
+        dopp = obs['sobs_dopp'].reshape(n, -1)[:, 0] if mode else None
+        inv, sf, st = c.invert(mode, sobs, snr, ids, 8, y, d, a, dopp, hdr, 1000, bcalc)
+        iss = c.last_issue.copy()
+        inv, sf, st = inv.copy(), sf.copy(), st.copy()
+        m = order                                              # this rank's pixels, in partition order
+        inv2, sf2, st2 = c.invert_sharded(mode, sobs[m], snr[m], ids[m], 8, y[m], d[m], a[m], None if dopp is None else dopp[m], hdr,
+                                          1000, bcalc, n, order, bounds)
+        assert same(inv, inv2) and same(sf, sf2) and same(st, st2) and same(iss, c.last_issue)
+    with pytest.raises(native.CledbError, match='partition'):
+        c.invert_sharded(0, sobs[:5], snr[:5], ids[:5], 8, y[:5], d[:5], a[:5], None, hdr, 1000, 0, n, order, bounds)
+    c.comm_destroy()
+    with pytest.raises(native.CledbError, match='communicator'):
+        c.invert_sharded(0, sobs[order], snr[order], ids[order], 8, y[order], d[order], a[order], None, hdr, 1000, 0, n, order, bounds)
+    c.close()

@@ -58,3 +58,62 @@ def test_replay_partsort_random():
         top = orc.stable_topk(chi, k)
         sel = solution.replay_partsort(top[None, :].astype(np.int32), chi[top][None, :], np.ones((1, k), bool))
         assert top[sel[0]].tolist() == lit.tolist()
+
+
+@pytest.mark.parametrize('tag', ['iquv_b0', 'iquv_b2', 'iqud'])
+def test_build_solutions_cle_type(golden_dir, tag):
+    """CLE-type databases (dbtype 0) are built by the host path: density index from the flat row, density from
+    cledb_elecdens (CLEDB_PROC.py:1688-1697, 1744-1747).  Fed with the oracle's raw search result it must give the
+    reference's own output."""
+    from test_oracle_golden import cle_header
+    g = np.load(os.path.join(golden_dir, 'cle_type.npz'))
+    hdr = cle_header(g)
+    iqud, bcalc, k, mx = (int(v) for v in g['cfg_' + tag])
+    nx, ny = g['sobs'].shape[:2]
+    sobs, snr = g['sobs'].reshape(-1, 8), g['snr'].reshape(-1, 8)
+    raw = oracle_raw(iqud, sobs, snr, [g['db']], np.zeros(nx * ny, np.int32), k)
+    inv, sf = solution.build_solutions(raw, iqud, sobs, g['sobs_dopp'].reshape(nx * ny, -1), g['yobs'].reshape(-1),
+                                       g['aobs'].reshape(-1), g['dobs'].reshape(-1), hdr, k, mx, bcalc)
+    inv, sf = inv.reshape(nx, ny, k, 11), sf.reshape(nx, ny, k, 8)
+    ref_inv, ref_sf = g['invout_' + tag], g['sfound_' + tag]
+    assert np.array_equal(inv[..., [0, 1, 3, 4, 6, 7]], ref_inv[..., [0, 1, 3, 4, 6, 7]])
+    np.testing.assert_allclose(inv[..., 2], ref_inv[..., 2], rtol=1e-6, atol=0)          # log10 of the Baumbach density
+    np.testing.assert_allclose(inv[..., [5, 8, 9, 10]], ref_inv[..., [5, 8, 9, 10]], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(sf, ref_sf, rtol=1e-6, atol=0)
+    iss = np.zeros((nx, ny, 2), np.int32)
+    solution.update_issuemask(iss, inv, g['snr'], nx, ny)
+    assert same(iss, g['issuemask_' + tag])
+
+
+def test_issue_codes_from_device_flags():
+    """native.issue_codes + solution.apply_issue_codes == solution.update_issuemask: the flags k_build writes (restated here
+    in float64, with the 1e-3 deg ambiguity band handed back to NumPy) give the reference's issue mask, and a code that is
+    already set is not added twice."""
+    rng = np.random.default_rng(3)
+    npix, k = 4000, 3
+    inv = np.zeros((npix, k, 11), np.float32)
+    inv[:, :, 3] = rng.uniform(1.0, 1.5, (npix, 1))
+    inv[:, :, 4] = rng.uniform(-0.5, 0.5, (npix, k))
+    inv[:, :, 6] = rng.uniform(0, 6.2, (npix, k))
+    inv[:, :, 7] = rng.uniform(0, 3.1, (npix, k))
+    inv[:, 0, 1] = rng.uniform(0, 20, npix)
+    inv[::7] = 0                                                 # rejected pixels: zeros
+    snr = rng.uniform(0.5, 3, (npix, 1, 8)).astype(np.float32)
+    o = inv[:, -1, :].astype(np.float64)
+    alpha = -np.arctan2(o[:, 4], o[:, 3])
+    xb, yb, zb = np.sin(o[:, 7]) * np.cos(o[:, 6]), np.sin(o[:, 7]) * np.sin(o[:, 6]), np.cos(o[:, 7])
+    cb = 6.123233995736766e-17
+    yyb, yzb = cb * yb - zb, yb + cb * zb
+    xxb, zzb = np.cos(alpha) * xb + np.sin(alpha) * yzb, -np.sin(alpha) * xb + np.cos(alpha) * yzb
+    deg = np.arctan2(np.sqrt(xxb ** 2 + yyb ** 2), zzb) * 180.0 / np.pi
+    flags = np.zeros((npix, 2), np.uint8)
+    flags[:, 0] = ((deg >= 53) & (deg <= 56)) | (((np.abs(deg - 53) < 1e-3) | (np.abs(deg - 56) < 1e-3)) << 1)
+    flags[:, 1] = (inv[:, 0, 1] > 10) | ((snr[:, 0, 0] < 1) << 1)
+    flags[:5, 0] |= 2                                            # force the NumPy re-evaluation on a few pixels
+    codes = native.issue_codes(flags, inv)
+    a = rng.choice([0, 32, 512, 1024 + 4, 2048 + 512], (npix, 1, 2)).astype(np.int32)
+    b = a.copy()
+    solution.apply_issue_codes(a, codes.reshape(npix, 1))
+    solution.update_issuemask(b, inv.reshape(npix, 1, k, 11), snr, npix, 1)
+    assert np.array_equal(a, b)
+    assert (codes & 512).any() and (codes & 1024).any() and (codes & 2048).any()

@@ -216,3 +216,26 @@ def test_unit_test_database_choice():
     names = ['DB_h106_d895.npy', 'DB_h109_d795.npy', 'DB_h109_d895.npy']
     table = orc.file_table(names)
     assert names[int(orc.nearest_database(np.float32(1.0920165), np.float32(7.936), table))] == 'DB_h109_d795.npy'
+
+
+@pytest.mark.parametrize('tag', ['iquv_b0', 'iquv_b2', 'iqud'])
+def test_cle_type_database(golden_dir, tag):
+    """CLE-type header (dbtype 0): the density index is the leading database axis and the solution's density comes from
+    cledb_elecdens (CLEDB_PROC.py:1688-1697, 1744-1747).  Golden = the unmodified reference (oracle/run_reference_cle.py)."""
+    g = np.load(os.path.join(golden_dir, 'cle_type.npz'))
+    hdr = cle_header(g)
+    iqud, bcalc, k, mx = (int(v) for v in g['cfg_' + tag])
+    nx, ny = g['sobs'].shape[:2]
+    kv = synth.make_keyvals(nx, ny, cdelt=float(g['cdelt']))
+    iss = np.zeros((nx, ny, 2), np.int32)
+    inv, sf = orc.invert_map(g['sobs'], g['sobs_dopp'], [g['db']], np.zeros((nx, ny), np.int32), g['yobs'], g['aobs'], g['dobs'],
+                             g['snr'], iss, hdr, kv, k, mx, bcalc, bool(iqud))
+    assert same(inv, g['invout_' + tag]) and same(sf, g['sfound_' + tag]) and same(iss, g['issuemask_' + tag])
+    assert (inv[..., 0] >= 0).sum() > 20
+    won = inv[..., 0][inv[..., 0] >= 0] // (4 * 12 * 8)
+    assert len(set(won.astype(int).tolist())) >= 2, 'winners in more than one density block'
+
+
+def cle_header(g):
+    hdr = synth.make_dbhdr(int(g['hdr_g'][2]), int(g['hdr_g'][3]), int(g['hdr_g'][4]), dbtype=0)
+    return (g['hdr_g'], np.int32(g['hdr_g'][1])) + tuple(hdr[2:5]) + (g['xed'],) + tuple(hdr[6:])
