@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""Benchmark of the B200-native CLEDB 2-line database search (BASELINE.json metric).
+"""Benchmark of the B200-native CLEDB 2-line database search (BASELINE.json metric and configs).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode iquv|iqud] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--configs 2,3,4,5]
 
-One "step" = one pass of the hot path (cledb_match: classify, bucket, chi^2 search + top-nsearch, finalise) over one
-synthetic observation map per GPU.  N=1 workload = BASELINE config 2: 256x256-pixel 2-line Fe XIII IQUV map,
-one synthetic PyCELP-shaped database (340 200 entries, int16-encoded in HBM), nsearch 8.  For N>1 every rank
-processes its own 256x256 map (weak scaling, database replicated) and the result maps are gathered with NCCL.
+Prints ONE JSON line (rank 0).  Top level = BASELINE config 2, the configuration the metric is quoted on: one 256x256-pixel
+2-line Fe XIII IQUV map per GPU against one synthetic PyCELP-shaped database (340 200 entries, int16 in HBM), nsearch 8,
+through the library's default search (exact tile pruning).  A "step" is one pass of the hot path over one map (cledb_match:
+classify, bucket, chi^2 search + top-nsearch, finalise).  N > 1: every rank searches its own map (weak scaling, database
+replicated) and the result maps are all-gathered over NVLink by the library (cledb_allgather_dev, NCCL).
 
-Prints ONE JSON line (rank 0).  `value` = pixels/s with inputs resident in HBM; `e2e` = the same through the
-host-buffer C-ABI call (pinned host memory, H2D and D2H inside the timed region); `roofline` = the search kernel
-against the FP32 FFMA peak measured in the same run; `cpu_baseline` = the oracle port (NumPy restatement of the
-reference, fork pool) on a bounded pixel sample on this box's host cores.
+  value      pixels/s, inputs resident in HBM, CUDA events on the launching stream, L2 flushed between steps, max over ranks
+  e2e        the same through the host-buffer C-ABI call (cledb_invert: H2D of the inputs, search, solutions, issue flags,
+             D2H of the finished invout / sfound maps inside the timed region); e2e.python = CLEDB_PROC.cledb_invproc itself
+  roofline   the kernel `value` timed (k_match_pruned) against the FP32 peak measured in the same run
+  by_config  one record per BASELINE config, each with its own value / e2e / roofline / cpu_baseline:
+               config2_iquv_256_pruned (= top level), config2_iquv_256_bruteforce (the FP32-roofline record: every (pixel,
+               candidate) pair evaluated), config3_iqud_256_*, config4_blos_2048 / config4_qurotate_2048* (HBM roofline),
+               config5_iquv_1024_multidb (ONE 1024x1024 map over several hundred databases, pixel-sharded over the N ranks
+               through cledb_invert_dev + one all-gather: strong scaling; at N = 1 the whole map on one GPU)
+  cpu_baseline  the oracle port (NumPy restatement of the reference, fork pool) on a bounded pixel sample, this box's cores
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -30,6 +38,7 @@ for p in (REPO, PKG):
 import numpy as np  # noqa: E402
 
 NSEARCH = 8
+NDB_ROWS = 340200
 
 
 def parse():
@@ -38,64 +47,62 @@ def parse():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--mode', default='iquv', choices=['iquv', 'iqud'])
+    ap.add_argument('--mode', default='iquv', choices=['iquv', 'iqud'], help='mode of the top-level record')
     ap.add_argument('--nx', type=int, default=256)
     ap.add_argument('--encoding', type=int, default=1)
-    ap.add_argument('--ndb', type=int, default=1, help='number of distinct (height, density) databases the map touches')
-    ap.add_argument('--cpu-seconds', type=float, default=20.0)
+    ap.add_argument('--ndb', type=int, default=1, help='databases the top-level map touches')
+    ap.add_argument('--ndb5', type=int, default=247, help='databases of the config-5 map (the reference notebook loads 247 for a 1024^2 map)')
+    ap.add_argument('--nx5', type=int, default=1024)
+    ap.add_argument('--configs', default='', help='comma list of extra configs to run (default: 2b,3,4,5 at N=1; 2b,5 at N>1)')
+    ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dbg', type=int, default=0, help='kernel timing experiment (results invalid)')
-    ap.add_argument('--prune', action='store_true', help='(default) exact tile pruning, the library default')
-    ap.add_argument('--no-prune', action='store_true', help='brute-force search as the measured path (the kernel the FP32 roofline is quoted on)')
-    ap.add_argument('--no-prune-pass', action='store_true', help='skip the extra brute-force pass of the default run')
+    ap.add_argument('--no-prune', action='store_true', help='brute-force search as the top-level path')
     ap.add_argument('--ppi', type=int, default=0, help='tuning: pixels per warp item (0 = library default)')
     ap.add_argument('--split', type=int, default=0, help='tuning: chunks per candidate list (0 = library default)')
     return ap.parse_args()
 
 
-def workload_name(args):
-    dbs = 'single synthetic PyCELP-shaped DB' if args.ndb == 1 else '%d synthetic PyCELP-shaped DBs (height x density grid points)' % args.ndb
-    return ('2-line Fe XIII %s inversion, %dx%d synthetic map per GPU, %s '
-            '(21x180x90 = 340200 entries each), nsearch %d' % (args.mode.upper(), args.nx, args.nx, dbs, NSEARCH))
+def workload_name(mode, nx, ndb):
+    dbs = 'single synthetic PyCELP-shaped DB' if ndb == 1 else '%d synthetic PyCELP-shaped DBs (height x density grid points)' % ndb
+    return ('2-line Fe XIII %s inversion, %dx%d synthetic map per GPU, %s (21x180x90 = 340200 entries each), nsearch %d'
+            % (mode.upper(), nx, nx, dbs, NSEARCH))
 
 
-def make_inputs(args, rank):
-    """Returns (list of databases, observation dict).  With --ndb K the map touches K databases: rows of the map
-    fall into height bands (as yobs does on a real map) and the density index varies inside a band."""
+def make_inputs(nx, ndb, rank):
+    """(list of databases, observation dict).  With ndb = K the map touches K databases: rows of the map fall into height
+    bands (as yobs does on a real map) and the density index varies inside a band."""
     from cledb_b200 import synth
-    if args.ndb == 1:
-        dbs = [synth.make_database(9, 40)]
-        enc = None
+    if ndb == 1:
+        dbs, enc = [synth.make_database(9, 40)], None
     else:
-        nh = max(1, int(round(args.ndb ** 0.5)))
-        nd = (args.ndb + nh - 1) // nh
-        grid = [(h, d) for h in range(nh) for d in range(nd)][:args.ndb]
+        nh = max(1, int(round(ndb ** 0.5)))
+        nd = (ndb + nh - 1) // nh
+        grid = [(h, d) for h in range(nh) for d in range(nd)][:ndb]
         dbs = [synth.make_database(5 + 3 * h, 30 + 2 * d) for h, d in grid]
         rng = np.random.default_rng(1234 + rank)
-        band = (np.arange(args.nx) * nh // args.nx)[:, None]                       # height band of a map row
-        dens = rng.integers(0, nd, (args.nx, args.nx))
-        enc = np.minimum(band * nd + dens, args.ndb - 1).astype(np.int32)
-    obs = synth.make_observation(args.nx, args.nx, dbs, db_enc=enc, seed=7 + rank)
-    return dbs, obs
+        band = (np.arange(nx) * nh // nx)[:, None]
+        dens = rng.integers(0, nd, (nx, nx))
+        enc = np.minimum(band * nd + dens, ndb - 1).astype(np.int32)
+    return dbs, synth.make_observation(nx, nx, dbs, db_enc=enc, seed=7 + rank)
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (NumPy restatement of cledb_invproc, validated bit-for-bit against the reference)
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_run(args, db, obs, npixels, workers, seed):
+def cpu_run(mode, encoding, db, obs, npixels, workers, seed):
     import oracle.cledb_oracle as orc
     from cledb_b200 import synth, codec
-    dec = [codec.decoded_database(d, args.encoding).reshape(d.shape) for d in db]
+    dec = [codec.decoded_database(d, encoding).reshape(d.shape) for d in db]
     hdr = synth.make_dbhdr()
-    nx = args.nx
-    rng = np.random.default_rng(seed)
-    flat = rng.choice(nx * nx, npixels, replace=False)
-    pixels = [(int(f // nx), int(f % nx)) for f in flat]
+    nx, ny = obs['sobs_totrot'].shape[:2]
+    flat = np.random.default_rng(seed).choice(nx * ny, npixels, replace=False)
+    pixels = [(int(f // ny), int(f % ny)) for f in flat]
     iss = obs['issuemask'].copy()
     t0 = time.perf_counter()
     orc.invert_map(obs['sobs_totrot'], obs['sobs_dopp'], dec, obs['db_enc'], obs['yobs'], obs['aobs'], obs['dobs'],
-                   obs['snr'], iss, hdr, obs['keyvals'], NSEARCH, 1000, 3 if args.mode == 'iqud' else 0,
-                   args.mode == 'iqud', workers=workers, pixels=pixels)
+                   obs['snr'], iss, hdr, obs['keyvals'], NSEARCH, 1000, 3 if mode == 'iqud' else 0, mode == 'iqud',
+                   workers=workers, pixels=pixels)
     return time.perf_counter() - t0
 
 
@@ -104,45 +111,47 @@ def cpu_workers():
     return max(1, min(100, n - 2))          # the reference's pool size: min(ncpu, cpu_count()-2), ncpu = 100
 
 
-def cpu_baseline(args, db, obs):
+def cpu_baseline(mode, encoding, db, obs, seconds):
     workers = cpu_workers()
     n0 = 16 * workers                   # probe large enough that pool start-up does not dominate the per-pixel estimate
-    t = cpu_run(args, db, obs, n0, workers, 0)
-    n1 = int(max(n0, min(args.nx * args.nx, n0 * args.cpu_seconds / max(t, 1e-3))))
-    t1 = cpu_run(args, db, obs, n1, workers, 1)
+    t = cpu_run(mode, encoding, db, obs, n0, workers, 0)
+    npix = obs['sobs_totrot'].shape[0] * obs['sobs_totrot'].shape[1]
+    n1 = int(max(2048, min(npix, n0 * seconds / max(t, 1e-3))))
+    n1 = min(n1, npix)
+    t1 = cpu_run(mode, encoding, db, obs, n1, workers, 1)
     return dict(value=n1 / t1, unit='pixels/s', cores=workers, kind='port',
                 sample='%d of %d pixels of the same map (seeded subset), oracle/cledb_oracle.invert_map in a fork pool of '
-                       '%d workers (reference pool size min(ncpu, cpu_count-2)), %.1f s' % (n1, args.nx * args.nx, workers, t1))
+                       '%d workers (reference pool size min(ncpu, cpu_count-2)), %.1f s' % (n1, npix, workers, t1))
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
+    if int(os.environ.get('RANK', '0')) != 0:
         return
-    db, obs = make_inputs(args, 0)
+    db, obs = make_inputs(args.nx, args.ndb, 0)
     workers = cpu_workers()
-    n = 32 * workers
-    for w in range(args.warmup):
-        cpu_run(args, db, obs, max(workers, n // 4), workers, 100 + w)
-    times = [cpu_run(args, db, obs, n, workers, 200 + s) for s in range(args.steps)]
+    n = min(args.nx * args.nx, max(2048, 32 * workers))          # a seeded subset of >= 2048 pixels
+    for w in range(min(args.warmup, 1)):
+        cpu_run(args.mode, args.encoding, db, obs, max(workers, n // 4), workers, 100 + w)
+    steps = max(1, min(args.steps, 12))                          # bounded: each step is ~2-4 s of all host cores
+    times = [cpu_run(args.mode, args.encoding, db, obs, n, workers, 200 + s) for s in range(steps)]
     t = float(np.mean(times))
     val = n / t
-    line = dict(impl='reference', metric='2-line pixels/s', value=val, unit='pixels/s', n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+    line = dict(impl='reference', metric='2-line pixels/s', value=val, unit='pixels/s', n_gpus=args.gpus, steps=steps,
+                warmup=min(args.warmup, 1), ms_per_step=t * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f64', data='synthetic',
-                config=dict(workload=workload_name(args), sample_pixels_per_step=n,
-                            note='reference is pure Python/NumPy and cannot travel to the GPU box; this arm times the '
-                                 'oracle port of it (bit-identical outputs, tests/test_oracle_golden.py)'),
+                config=dict(workload=workload_name(args.mode, args.nx, args.ndb), sample_pixels_per_step=n,
+                            note='reference is pure Python/NumPy and cannot travel to the GPU box; this arm times the oracle port of '
+                                 'it (bit-identical outputs, tests/test_oracle_golden.py) on all host cores; steps capped at 12'),
                 cpu_baseline=dict(value=val, unit='pixels/s', cores=workers, kind='port',
                                   sample='%d seeded pixels per step of the %dx%d map' % (n, args.nx, args.nx)),
                 e2e=dict(value=val, unit='pixels/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                evals_per_s=val * 340200)
+                scanned_evals_per_s=val * NDB_ROWS)
     print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons while the timed regions run."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -159,279 +168,586 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
+    def mark(self):
+        return len(self.rows)
+
+    def summary(self, lo=0, hi=None):
+        rows = [r for r in self.rows[lo:hi] if len(r) >= 7]
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
         try:
-            sm = [float(r[0]) for r in self.rows if len(r) >= 7]
+            sm = [float(r[0]) for r in rows]
             if sm:
                 out['sm_mhz'] = float(np.median(sm))
-                out['sm_max_mhz'] = float(self.rows[0][1])
-                out['power_w_max'] = max(float(r[2]) for r in self.rows if len(r) >= 7)
+                out['sm_max_mhz'] = float(rows[0][1])
+                out['power_w_max'] = max(float(r[2]) for r in rows)
                 names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-                out['reasons'] = [n for i, n in enumerate(names) if any(r[3 + i] == 'Active' for r in self.rows if len(r) >= 7)]
+                out['reasons'] = [n for i, n in enumerate(names) if any(r[3 + i] == 'Active' for r in rows)]
                 out['samples'] = len(sm)
         except Exception:
             pass
         return out
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+class Bench:
+    """Shared state of one rank: device, stream, context, timing helpers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from cledb_b200 import native
+        self.torch, self.dist, self.native, self.args = torch, dist, native, args
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+        self.ctx = native.Context(self.local)
+        ids = [None]
+        if self.world > 1:                                   # the library's own communicator (NCCL bound at run time)
+            ids = [native.comm_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+        self.ctx.comm_init(self.rank, self.world, ids[0])    # one rank: no NCCL involved
+        self.stream = torch.cuda.Stream(device=self.dev)     # an explicit stream: the library and the CUDA events share it
+        torch.cuda.set_stream(self.stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)          # > 126 MB L2
+        self.props = self.ctx.device_props()
+        self.fp32_peak = None
+        self.sampler = ClockSampler(self.local)
+        if self.rank == 0:
+            self.sampler.start()
+            time.sleep(0.3)
+        try:
+            self.hbm_peak = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))['hbm_gbs']
+            self.hbm_src = 'MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)'
+        except Exception:
+            self.hbm_peak, self.hbm_src = 6553.9, 'fallback 6553.9 GB/s (B200_PROFILING.md)'
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, nsteps, profile=True):
+        """K steps, each between two CUDA events on the launching stream, L2 flushed before each step (outside the events).
+        Returns (per-step ms, per-launch ms of the search kernel from the library's own events)."""
+        torch = self.torch
+        if profile:
+            self.ctx.profile_begin()
+        evs = []
+        for _ in range(nsteps):
+            self.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(self.stream)
+            fn()
+            b.record(self.stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs], (self.ctx.profile_collect() if profile else None)
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, xs):
+        if self.world == 1:
+            return [int(x) for x in xs]
+        t = self.torch.tensor([int(x) for x in xs], device=self.dev, dtype=self.torch.int64)
+        self.dist.all_reduce(t)
+        return [int(v) for v in t.tolist()]
+
+    def pinned(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+    def traffic_of(self, name):
+        """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/kernel_traffic.json)."""
+        try:
+            return json.load(open(os.path.join(REPO, 'profiles', 'kernel_traffic.json'))).get(name)
+        except Exception:
+            return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# configs 2 and 3: the 256x256 map against one database, both searches
+# ---------------------------------------------------------------------------------------------------------------
+def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, want_e2e=True, want_python=True, want_stream=True):
+    """Returns {'pruned': record, 'bruteforce': record} for one mode on the nx x nx map."""
+    torch, native, ctx = B.torch, B.native, B.ctx
+    mode = native.MODE_IQUD if mode_name == 'iqud' else native.MODE_IQUV
+    db, obs = make_inputs(nx, ndb, B.rank)
+    npix, k = nx * nx, NSEARCH
+    sobs_h, snr_h = B.pinned(obs['sobs_totrot'].reshape(-1, 8)), B.pinned(obs['snr'].reshape(-1, 8))
+    id_h = B.pinned(obs['db_enc'].reshape(-1).astype(np.int32))
+    sobs_d, snr_d, id_d = sobs_h.to(B.dev), snr_h.to(B.dev), id_h.to(B.dev)
+    maps_d = torch.empty((2, npix, k), dtype=torch.int32, device=B.dev)      # idx and chi side by side: one collective gathers both
+    idx_d, chi_d = maps_d[0], maps_d[1].view(torch.float32)
+    kpos_d = torch.empty((npix, k), dtype=torch.int32, device=B.dev)
+    rows_d = torch.empty((npix, k, 8), dtype=torch.float32, device=B.dev)
+    st_d = torch.empty(npix, dtype=torch.uint8, device=B.dev)
+    nc_d = torch.empty(npix, dtype=torch.int64, device=B.dev)
+    gathered = torch.empty((B.world, 2, npix, k), dtype=torch.int32, device=B.dev) if with_gather and B.world > 1 else None
+
+    def step():
+        ctx.match_dev(mode, npix, sobs_d.data_ptr(), snr_d.data_ptr(), id_d.data_ptr(), k, idx_d.data_ptr(), chi_d.data_ptr(),
+                      None, kpos_d.data_ptr(), rows_d.data_ptr(), st_d.data_ptr(), nc_d.data_ptr(), B.stream.cuda_stream)
+        if gathered is not None:            # the only collective of the path: gather the result maps (library call, same stream)
+            ctx.allgather_dev(maps_d.data_ptr(), gathered.data_ptr(), maps_d.numel() * 4, B.stream.cuda_stream)
+
+    from cledb_b200 import synth
+    hdr = synth.make_dbhdr()
+    out_h = dict(invout=torch.empty((npix, k, 11), dtype=torch.float32).pin_memory().numpy(),
+                 sfound=torch.empty((npix, k, 8), dtype=torch.float32).pin_memory().numpy(),
+                 status=torch.empty(npix, dtype=torch.uint8).pin_memory().numpy(),
+                 issue=torch.empty((npix, 2), dtype=torch.uint8).pin_memory().numpy())
+    sobs_n, snr_n, id_n = sobs_h.numpy(), snr_h.numpy(), id_h.numpy()
+    yobs_n, dobs_n = B.pinned(obs['yobs'].reshape(-1)).numpy(), B.pinned(obs['dobs'].reshape(-1)).numpy()
+    aobs_n = obs['aobs'].reshape(-1)
+    dopp_n = np.ascontiguousarray(obs['sobs_dopp'].reshape(npix, -1)[:, 0]) if mode_name == 'iqud' else None
+    bcalc = 3 if mode_name == 'iqud' else 0
+
+    def e2e_step(c=ctx, o=out_h):
+        c.invert(mode, sobs_n, snr_n, id_n, k, yobs_n, dobs_n, aobs_n, dopp_n, hdr, 1000, bcalc, out=o)
+
+    h2d = npix * (32 + 32 + 4 + 4 + 4 + 4 + 4 + (4 if mode_name == 'iqud' else 0))
+    d2h = npix * (k * (44 + 32) + 1 + 2)
+    enc_name = 'int16' if encoding == 1 else 'float32'
+    recs = {}
+    for pruned in (True, False):
+        ctx.set_pruning(pruned)
+        for i, d in enumerate(db):
+            ctx.db_put(i, d, encoding)
+        if B.args.ppi or B.args.split:
+            ctx.set_tuning(B.args.ppi, B.args.split)
+        if B.args.dbg:
+            ctx.set_tuning(-B.args.dbg, 0)
+        for _ in range(max(warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        if B.fp32_peak is None:
+            B.fp32_peak = ctx.measure_fp32_peak()
+        B.barrier()
+        mark = B.sampler.mark()
+        launches0 = ctx.launch_count()
+        nst = steps if pruned else max(3, min(steps, 10))
+        step_ms, kern_ms = B.timed(step, nst)
+        B.barrier()
+        launches = ctx.launch_count() - launches0
+        stats = ctx.pruning_stats() if pruned else None
+        ms = B.max_over_ranks(float(np.mean(step_ms)))
+        kms = float(np.mean(kern_ms)) if len(kern_ms) else float('nan')
+        ncand, nsearched = int(nc_d.sum().item()), int((st_d == 0).sum().item())
+        ncand_all, nsearched_all = B.sum_over_ranks([ncand, nsearched])
+        peak = B.fp32_peak
+        clocks = B.sampler.summary(mark) if B.rank == 0 else None
+        theo = B.props['sm_count'] * 128 * 2 * ((clocks or {}).get('sm_max_mhz') or B.props['sm_clock_khz'] / 1e3) * 1e6 / 1e12
+        peak_src = ('FFMA microkernel measured in this run (cledb_measure_fp32_peak); theoretical %.1f TFLOP/s = %d SMs x 128 lanes '
+                    'x 2 x max SM clock.  MEASURED_PEAKS.json holds HBM and bf16 tensor peaks, neither bounds this kernel'
+                    % (theo, B.props['sm_count']))
+        if pruned:
+            evaluated = 256.0 * stats['evaluated']                      # entries actually evaluated (pairs x 256-entry tiles)
+            achieved = 20.0 * evaluated / (kms * 1e-3) / 1e12
+            pairs = stats['evaluated'] + stats['skipped']
+            roof = dict(bound='fp32 (instruction-issue limited: selection and bound code)', kernel='k_match_pruned<%s>' % enc_name,
+                        achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak if peak else None,
+                        traffic=B.traffic_of('k_match_pruned_' + mode_name), kernel_ms=kms, kernel_share_of_step=kms / float(np.mean(step_ms)),
+                        flop_per_evaluated_entry=20, evaluated_entries_per_launch=evaluated,
+                        frac_if_every_candidate_counted=20.0 * ncand / (kms * 1e-3) / 1e12 / peak if peak else None,
+                        note='FLOPs of the entries the kernel really evaluates: exact tile bounds skip %.1f %% of the (pixel, tile) pairs. '
+                             'frac_if_every_candidate_counted credits the skipped candidates too (SURVEY 8d algorithmic count; > 1 means '
+                             'work avoided, not throughput)' % (100.0 * stats['skipped'] / max(1, pairs)),
+                        peak_source=peak_src)
+            evals = evaluated * B.world
+        else:
+            achieved = 20.0 * ncand / (kms * 1e-3) / 1e12
+            roof = dict(bound='fp32', kernel='k_match<%s,fp32>' % enc_name, achieved=achieved, peak=peak, unit='TFLOP/s',
+                        frac=achieved / peak if peak else None, traffic=B.traffic_of('k_match_' + mode_name), kernel_ms=kms,
+                        kernel_share_of_step=kms / float(np.mean(step_ms)), flop_per_candidate=20, candidates_per_launch=ncand,
+                        peak_source=peak_src)
+            evals = ncand_all
+        rec = dict(value=B.world * npix / (ms * 1e-3), unit='pixels/s', ms_per_step=ms, steps=nst,
+                   workload=workload_name(mode_name, nx, ndb), search='exact tile pruning (library default)' if pruned else 'brute force (pruning off)',
+                   evals_per_s=evals / (ms * 1e-3), evals_definition='(pixel, database entry) chi^2 evaluations actually executed per second',
+                   nominal_scanned_evals_per_s=B.world * npix * float(NDB_ROWS) * max(1, ndb) / max(1, ndb) / (ms * 1e-3),
+                   nominal_candidate_evals_per_s=ncand_all / (ms * 1e-3), pixels_searched=nsearched_all, gpu_launches=int(launches),
+                   pruning=stats, roofline=roof, clocks=clocks)
+        if want_e2e:
+            for _ in range(3):
+                e2e_step()
+            B.barrier()
+            t0 = time.perf_counter()
+            for _ in range(nst):
+                e2e_step()
+            e2e_s = B.max_over_ranks((time.perf_counter() - t0) / nst)
+            rec['e2e'] = dict(value=B.world * npix / e2e_s, unit='pixels/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                              ms_per_step=e2e_s * 1e3,
+                              api='cledb_invert (C-ABI): pinned host buffers in, search + solutions + issue flags on the device, finished '
+                                  'invout / sfound maps out')
+        recs['pruned' if pruned else 'bruteforce'] = rec
+        if pruned and want_stream and B.world == 1:
+            # a stream of maps through TWO contexts on this GPU (two host threads, the same blocking call): the result copy of
+            # one map overlaps the search of the next
+            ctx2 = native.Context(B.local)
+            ctx2.set_pruning(True)
+            for i, d in enumerate(db):
+                ctx2.db_put(i, d, encoding)
+            out_h2 = {kk: torch.empty(v.shape, dtype=torch.from_numpy(v).dtype).pin_memory().numpy() for kk, v in out_h.items()}
+            nmaps = max(4, nst)
+
+            def worker(c, o, n):
+                for _ in range(n):
+                    e2e_step(c, o)
+
+            worker(ctx2, out_h2, 3)
+            ths = [threading.Thread(target=worker, args=(ctx, out_h, nmaps)), threading.Thread(target=worker, args=(ctx2, out_h2, nmaps))]
+            t0 = time.perf_counter()
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            es = (time.perf_counter() - t0) / (2 * nmaps)
+            same = bool(np.array_equal(out_h['invout'], out_h2['invout'], equal_nan=True) and np.array_equal(out_h['sfound'], out_h2['sfound'], equal_nan=True))
+            rec['e2e']['stream_of_maps'] = dict(value=npix / es, ms_per_map=es * 1e3, identical_outputs=same,
+                                                how='two contexts on this GPU, one host thread each, the same blocking call')
+            ctx2.close()
+        for i in range(len(db)):
+            ctx.db_drop(i)
+    ctx.set_pruning(True)
+    ctx.set_tuning(0, 0)
+    if want_python:
+        # the reference-shaped Python call itself (CLEDB_PROC.cledb_invproc): same map, same encoding, its own context; the
+        # database is resident after the first call, results land in the binding's pinned pool
+        import CLEDB_PROC.CLEDB_PROC as procinv
+        procinv.OPTIONS.update(device=B.local, dbencoding=encoding, precision=0, solution='device', pruning=True)
+        pargs = (obs['sobs_totrot'], obs['sobs_dopp'] if mode_name == 'iqud' else 0, db, obs['db_enc'], obs['yobs'], obs['aobs'],
+                 obs['dobs'], obs['snr'])
+        ptail = (hdr, obs['keyvals'], k, 1000, bcalc, mode_name == 'iqud', 1, False, 0)
+        for _ in range(3):
+            procinv.cledb_invproc(*pargs, obs['issuemask'].copy(), *ptail)
+        B.barrier()
+        nst = max(3, min(steps, 20))
+        iss = obs['issuemask'].copy()
+        t0 = time.perf_counter()
+        for _ in range(nst):
+            inv, sf = procinv.cledb_invproc(*pargs, iss, *ptail)
+        py_s = B.max_over_ranks((time.perf_counter() - t0) / nst)
+        agree = bool(np.array_equal(inv.reshape(npix, k, 11), recs['pruned']['e2e'] and out_h['invout'], equal_nan=True)) if want_e2e else None
+        recs['pruned'].setdefault('e2e', {})['python'] = dict(
+            value=B.world * npix / py_s, unit='pixels/s', ms_per_step=py_s * 1e3, same_invout_as_c_abi=agree,
+            api='CLEDB_PROC.cledb_invproc(...) - the reference-shaped call: pageable NumPy inputs, fresh result arrays from the pinned pool, '
+                'issuemask updated in place')
+        del inv, sf
+        procinv.release_databases()
+    recs['_inputs'] = (db, obs)
+    return recs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# config 4: the elementwise neighbours on a 2048 x 2048 map (HBM roofline)
+# ---------------------------------------------------------------------------------------------------------------
+def bench_elementwise(B, nx, steps, cpu=True):
+    torch, ctx = B.torch, B.ctx
+    from cledb_b200 import synth
+    import constants as consts
+    import oracle.cledb_oracle as orc
+    npix = nx * nx
+    out = {}
+
+    def timed(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        ms, _ = B.timed(fn, steps, profile=False)
+        return float(np.mean(ms))
+
+    def record(kernel, metric, workload, ms, bpp, e2e_s, h2d, d2h, cpu_rec):
+        gbs = bpp * npix / (ms * 1e-3) / 1e9
+        tr = B.traffic_of(kernel + ('_%d' % nx))
+        return dict(metric=metric, value=npix / (ms * 1e-3), unit='pixels/s', ms_per_step=ms, steps=steps, workload=workload,
+                    roofline=dict(bound='hbm', kernel=kernel, achieved=gbs, peak=B.hbm_peak, unit='GB/s', frac=gbs / B.hbm_peak, traffic=tr,
+                                  bytes_per_pixel=bpp, algorithmic_bytes_per_launch=bpp * npix, peak_source=B.hbm_src),
+                    e2e=dict(value=npix / e2e_s, unit='pixels/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_s * 1e3),
+                    cpu_baseline=cpu_rec)
+
+    one = synth.make_oneline_map(nx, nx)
+    c = consts.Constants('fe-xiii_1074')
+    kfac = 1.e9 * (c.planckconst * c.l_speed / c.bohrmagneton / (c.line_ref ** 2))
+    d_in = torch.from_numpy(one.reshape(-1, 4)).to(B.dev)
+    d_out = torch.empty_like(d_in)
+    d_fl = torch.empty((npix, 2), dtype=torch.uint8, device=B.dev)
+    ms = timed(lambda: ctx.blos_dev(npix, d_in.data_ptr(), kfac, c.g_eff, c.F_factor, d_out.data_ptr(), d_fl.data_ptr(), B.stream.cuda_stream))
+    one_p = B.pinned(one.reshape(-1, 4)).numpy()
+    ctx.blos(one_p, kfac, c.g_eff, c.F_factor)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        out_h, fl_h = ctx.blos(one_p, kfac, c.g_eff, c.F_factor)
+    e2e = (time.perf_counter() - t0) / 3
+    assert np.array_equal(out_h, d_out.cpu().numpy(), equal_nan=True)
+    cpu_rec = None
+    if cpu:
+        ns = 8192
+        t0 = time.perf_counter()
+        ref = np.stack([orc.blos_pixel(one.reshape(-1, 4)[i], c)[0] for i in range(ns)])
+        cpu_rec = dict(value=ns / (time.perf_counter() - t0), unit='pixels/s', cores=1, kind='port', sample='%d pixels, oracle blos_pixel loop' % ns)
+        assert np.allclose(ref, out_h[:ns], rtol=2e-6, atol=1e-30, equal_nan=True)
+    out['config4_blos_%d' % nx] = record('k_blos', '1-line B_LOS pixels/s',
+                                         'blos_proc_1pix on a %dx%d 1-line map (%.0f MB in+out, larger than L2)' % (nx, nx, 34.0 * npix / 1e6),
+                                         ms, 34, e2e, 16 * npix, 18 * npix, cpu_rec)
+    del d_in, d_out, d_fl
+
+    two = synth.make_twoline_raw(nx, nx)
+    kv = synth.make_keyvals(nx, nx, cdelt=5e-5)
+    xs = np.array([kv[8] + i * kv[11] for i in range(nx)], dtype=np.float64)
+    ys = np.array([kv[9] + i * kv[12] for i in range(nx)], dtype=np.float64)
+    d_xs, d_ys = torch.from_numpy(xs).to(B.dev), torch.from_numpy(ys).to(B.dev)
+    d2 = torch.from_numpy(two).to(B.dev)
+    o2 = torch.empty_like(d2)
+    d_a = torch.empty((nx, nx), dtype=torch.float32, device=B.dev)
+    d_y = torch.empty((nx, nx), dtype=torch.float32, device=B.dev)
+    two_p = B.pinned(two).numpy()
+    for label, hp in (('', None), ('_hpxy', 'grid')):
+        d_hp = hp_np = None
+        if hp:
+            hp_np = np.stack(np.meshgrid(xs.astype(np.float32), ys.astype(np.float32), indexing='ij')).astype(np.float32)
+            d_hp = torch.from_numpy(hp_np).to(B.dev)
+        ms = timed(lambda: ctx.qurotate_dev(nx, nx, d_xs.data_ptr(), d_ys.data_ptr(), kv[14], d_hp.data_ptr() if hp else None,
+                                            d2.data_ptr(), o2.data_ptr(), d_a.data_ptr(), d_y.data_ptr(), B.stream.cuda_stream))
+        ctx.qurotate(two_p, xs, ys, kv[14], hp_np)
+        t0 = time.perf_counter()
+        rot_h, a_h, y_h = ctx.qurotate(two_p, xs, ys, kv[14], hp_np)
+        e2e = time.perf_counter() - t0
+        cpu_rec = None
+        if cpu:
+            nsx = 48
+            sub_kv = list(kv)
+            sub_kv[0], sub_kv[1] = nsx, nsx
+            t0 = time.perf_counter()
+            r_ref, a_ref, y_ref = orc.qurotate_map(two[:nsx, :nsx], sub_kv, hp_np[:, :nsx, :nsx] if hp else np.zeros((2, nsx, nsx)))
+            cpu_rec = dict(value=nsx * nsx / (time.perf_counter() - t0), unit='pixels/s', cores=1, kind='port',
+                           sample='%dx%d pixels, oracle qurotate_map' % (nsx, nsx))
+            assert np.allclose(a_ref, a_h[:nsx, :nsx], atol=1e-6) and np.allclose(y_ref, y_h[:nsx, :nsx], rtol=1e-6)
+        bpp = 72 + (8 if hp else 0)
+        out['config4_qurotate_%d%s' % (nx, label)] = record(
+            'k_qurotate' + label, 'QU rotation + height pixels/s',
+            'obs_qurotate + obs_calcheight on a %dx%d 2-line map, %s (%.0f MB)' % (nx, nx, 'Cryo-NIRSP coordinate grid' if hp else 'rectangular grid', bpp * npix / 1e6),
+            ms, bpp, e2e, (32 + (8 if hp else 0)) * npix, 40 * npix, cpu_rec)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# config 5: ONE 1024 x 1024 map over several hundred databases, pixel-sharded over the ranks (strong scaling)
+# ---------------------------------------------------------------------------------------------------------------
+def bench_config5(B, nx, ndb, steps):
+    torch, native, ctx = B.torch, B.native, B.ctx
+    from cledb_b200 import synth
+    k, npix = NSEARCH, nx * nx
+    nh = max(1, int(round(ndb ** 0.5)))
+    nd = (ndb + nh - 1) // nh
+    grid = [(h, d) for h in range(nh) for d in range(nd)][:ndb]
+    rng = np.random.default_rng(4321)                        # the same map on every rank
+    band = (np.arange(nx) * nh // nx)[:, None]
+    enc = np.minimum(band * nd + rng.integers(0, nd, (nx, nx)), ndb - 1).astype(np.int32).reshape(-1)
+    kv = synth.make_keyvals(nx, nx)
+    aobs, yobs = synth.geometry(nx, nx, kv)
+    dobs = rng.uniform(7.0, 9.5, npix).astype(np.float32)
+    order, bounds = native.partition(enc, np.full(ndb, float(NDB_ROWS)), B.world)
+    mine = order[bounds[B.rank]:bounds[B.rank + 1]]
+    n = int(mine.size)
+    emine = enc[mine]
+    used = np.unique(emine)
+    t0 = time.perf_counter()
+    # this rank generates, uploads and draws its observation from only the databases of its range
+    sobs, snr = np.empty((n, 8), np.float32), np.empty((n, 8), np.float32)
+    ctx.set_pruning(True)
+    lut = np.full(ndb, -1, np.int32)
+    for j, e in enumerate(used):
+        h, d = grid[int(e)]
+        db = synth.make_database((5 + 3 * h) % 99, (30 + 2 * d) % 121)
+        sel = np.flatnonzero(emine == e)
+        o = synth.make_observation(sel.size, 1, [db], seed=1000 + int(e))
+        sobs[sel], snr[sel] = o['sobs_totrot'].reshape(-1, 8), o['snr'].reshape(-1, 8)
+        ctx.db_put(j, db, B.args.encoding)
+        lut[e] = j
+    setup_s = time.perf_counter() - t0
+    hdr = synth.make_dbhdr()
+    ang = aobs.reshape(-1)[mine]
+    with np.errstate(all='ignore'):
+        rc, rs = np.cos(-2. * ang), np.sin(-2. * ang)
+    ids = lut[emine]
+    yl, dl = yobs.reshape(-1)[mine], dobs[mine]
+    maxcount = int(np.max(np.diff(bounds)))
+    lay = np.zeros(5, np.int64)
+    native.load_library().cledb_shard_layout(maxcount, k, lay.ctypes.data_as(ctypes.c_void_p))
+    o_inv, o_sf, o_st, o_iss, rank_bytes = (int(v) for v in lay)
+    dt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(B.dev)
+    d_sobs, d_snr, d_ids, d_y, d_d, d_rc, d_rs = dt(sobs), dt(snr), dt(ids), dt(yl), dt(dl), dt(rc), dt(rs)
+    g = native.DbGrid.from_dbhdr(hdr)
+    tabs = [dt(t) for t in g._tables]
+    g.sin_bphi, g.cos_bphi, g.sin_btheta, g.cos_btheta = (t.data_ptr() for t in tabs)
+    send = torch.empty(rank_bytes, dtype=torch.uint8, device=B.dev)
+    recv = torch.empty(rank_bytes * B.world, dtype=torch.uint8, device=B.dev)
+    d_order, d_bounds = dt(order), dt(bounds)
+    f_inv = torch.empty((npix, k, 11), dtype=torch.float32, device=B.dev)
+    f_sf = torch.empty((npix, k, 8), dtype=torch.float32, device=B.dev)
+    f_st = torch.empty(npix, dtype=torch.uint8, device=B.dev)
+    f_iss = torch.empty((npix, 2), dtype=torch.uint8, device=B.dev)
+    sp = send.data_ptr()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    parts = []
+
+    def step(record=False):
+        if record:
+            ev[0].record(B.stream)
+        if n:
+            ctx.invert_dev(native.MODE_IQUV, n, d_sobs.data_ptr(), d_snr.data_ptr(), d_ids.data_ptr(), k, d_y.data_ptr(), d_d.data_ptr(),
+                           d_rc.data_ptr(), d_rs.data_ptr(), None, 0, g, 1000, 0, sp + o_inv, sp + o_sf, sp + o_st, sp + o_iss,
+                           B.stream.cuda_stream)
+        if record:
+            ev[1].record(B.stream)
+        if B.world > 1:
+            ctx.allgather_dev(sp, recv.data_ptr(), rank_bytes, B.stream.cuda_stream)
+        if record:
+            ev[2].record(B.stream)
+        ctx.unshard_dev(B.world, d_bounds.data_ptr(), d_order.data_ptr(), npix, maxcount, k, recv.data_ptr() if B.world > 1 else sp,
+                        f_inv.data_ptr(), f_sf.data_ptr(), f_st.data_ptr(), f_iss.data_ptr(), B.stream.cuda_stream)
+        if record:
+            ev[3].record(B.stream)
+            torch.cuda.synchronize()
+            parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+
+    for _ in range(3):
+        step()
+    B.barrier()
+    for _ in range(3):
+        B.flush.zero_()
+        step(record=True)                                   # where the step's time goes (search+build / all-gather / scatter)
+    B.barrier()
+    launches0 = ctx.launch_count()
+    nst = max(3, min(steps, 10))
+    step_ms, kern_ms = B.timed(step, nst)
+    B.barrier()
+    launches = ctx.launch_count() - launches0
+    ms = B.max_over_ranks(float(np.mean(step_ms)))
+    stats = ctx.pruning_stats()
+    part = np.mean(np.array(parts), axis=0)
+    part = [B.max_over_ranks(float(v)) for v in part]
+    nsearched = B.sum_over_ranks([int((f_st == 0).sum().item()) if B.rank == 0 else 0])[0]
+    rec = dict(metric='2-line pixels/s', value=npix / (ms * 1e-3), unit='pixels/s', ms_per_step=ms, steps=nst, scaling='strong',
+               workload='ONE %dx%d 2-line IQUV map over %d synthetic PyCELP-shaped databases (height bands x densities; %.1f GB of float32 '
+                        'databases, %s in HBM), pixel-sharded over %d GPU(s): cledb_partition -> cledb_invert_dev on the shard -> one '
+                        'all-gather of the packed finished records (%d B/pixel) -> scatter into the full maps on every rank'
+                        % (nx, nx, ndb, ndb * NDB_ROWS * 32 / 1e9, 'int16' if B.args.encoding == 1 else 'float32', B.world, k * 76 + 3),
+               search='exact tile pruning (library default)', pixels_searched=nsearched, databases_on_this_rank=int(used.size),
+               shard_pixels=n, gpu_launches=int(launches),
+               step_breakdown_ms=dict(search_and_build=part[0], all_gather=part[1], scatter=part[2],
+                                      note='CUDA events between the three calls of one step, max over ranks; the all-gather moves %.0f MB '
+                                           'into every GPU' % (rank_bytes * (B.world - 1) / 1e6)),
+               search_kernel_ms=float(np.mean(kern_ms)) if len(kern_ms) else None, pruning=stats, setup_seconds=setup_s)
+    # end to end: the host-buffer collective call (every rank its shard in, the full maps out on rank 0)
+    out = ctx.result_buffers(npix, k) if B.rank == 0 else None
+    for _ in range(2):
+        ctx.invert_sharded(native.MODE_IQUV, sobs, snr, ids, k, yl, dl, ang, None, hdr, 1000, 0, npix, order, bounds, root=0, out=out)
+    B.barrier()
+    ne = max(2, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(ne):
+        ctx.invert_sharded(native.MODE_IQUV, sobs, snr, ids, k, yl, dl, ang, None, hdr, 1000, 0, npix, order, bounds, root=0, out=out)
+    e2e_s = B.max_over_ranks((time.perf_counter() - t0) / ne)
+    rec['e2e'] = dict(value=npix / e2e_s, unit='pixels/s', ms_per_step=e2e_s * 1e3, h2d_bytes_per_step=int(n) * 84,
+                      d2h_bytes_per_step=npix * (k * 76 + 3),
+                      api='cledb_invert_sharded (C-ABI, collective): every rank uploads its shard, rank 0 receives the full invout / sfound '
+                          'maps in pinned host memory (%.0f MB over one PCIe link)' % (npix * (k * 76 + 3) / 1e6))
+    if B.rank == 0:
+        same = bool(np.array_equal(out['invout'], f_inv.cpu().numpy(), equal_nan=True))
+        rec['e2e']['same_maps_as_device_path'] = same
+    for j in range(used.size):
+        ctx.db_drop(j)
+    return rec
 
 
 def main():
     args = parse()
     if args.impl == 'reference':
         return run_reference_arm(args)
-
-    import torch
-    import torch.distributed as dist
-    from cledb_b200 import native
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    dev = torch.device('cuda', local)
-    mode = native.MODE_IQUD if args.mode == 'iqud' else native.MODE_IQUV
-
-    db, obs = make_inputs(args, rank)
-    ctx = native.Context(local)
-    pruned = not args.no_prune
-    ctx.set_pruning(pruned)
-    for i, d in enumerate(db):
-        ctx.db_put(i, d, args.encoding)
-    props = ctx.device_props()
-    if args.ppi or args.split:
-        ctx.set_tuning(args.ppi, args.split)
-    if args.dbg:
-        ctx.set_tuning(-args.dbg, 0)
-    npix = args.nx * args.nx
-    k = NSEARCH
-
-    sobs_h = torch.from_numpy(obs['sobs_totrot'].reshape(-1, 8)).pin_memory()
-    snr_h = torch.from_numpy(obs['snr'].reshape(-1, 8)).pin_memory()
-    id_h = torch.from_numpy(np.ascontiguousarray(obs['db_enc'].reshape(-1).astype(np.int32))).pin_memory()
-    sobs_d, snr_d, id_d = sobs_h.to(dev), snr_h.to(dev), id_h.to(dev)
-    maps_d = torch.empty((2, npix, k), dtype=torch.int32, device=dev)      # idx and chi side by side: one collective gathers both
-    idx_d = maps_d[0]
-    chi_d = maps_d[1].view(torch.float32)
-    kpos_d = torch.empty((npix, k), dtype=torch.int32, device=dev)
-    rows_d = torch.empty((npix, k, 8), dtype=torch.float32, device=dev)
-    st_d = torch.empty(npix, dtype=torch.uint8, device=dev)
-    nc_d = torch.empty(npix, dtype=torch.int64, device=dev)
-    gathered = torch.empty((world, 2, npix, k), dtype=torch.int32, device=dev) if world > 1 else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-
-    stream = torch.cuda.Stream(device=dev)      # an explicit stream: the library and the CUDA events share it
-    torch.cuda.set_stream(stream)
-
-    def step():
-        ctx.match_dev(mode, npix, sobs_d.data_ptr(), snr_d.data_ptr(), id_d.data_ptr(), k, idx_d.data_ptr(), chi_d.data_ptr(),
-                      None, kpos_d.data_ptr(), rows_d.data_ptr(), st_d.data_ptr(), nc_d.data_ptr(), stream.cuda_stream)
-        if world > 1:                       # the only collective of the path: gather the result maps
-            dist.all_gather_into_tensor(gathered, maps_d)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    fp32_peak = ctx.measure_fp32_peak()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    def timed(nsteps):
-        ctx.profile_begin()
-        evs = []
-        for _ in range(nsteps):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            step()
-            b.record(stream)
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        return [a.elapsed_time(b) for a, b in evs], ctx.profile_collect()
-
-    launches0 = ctx.launch_count()
-    step_ms, kern_ms = timed(args.steps)
-    if world > 1:
-        dist.barrier()
-    launches = ctx.launch_count() - launches0
-    prune_stats = ctx.pruning_stats() if pruned else None
-
-    ms = float(np.mean(step_ms))
-    ncand = int(nc_d.sum().item())
-    nsearched = int((st_d == 0).sum().item())
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        c = torch.tensor([ncand, nsearched], device=dev, dtype=torch.int64)
-        dist.all_reduce(c)
-        ncand_all, nsearched_all = int(c[0].item()), int(c[1].item())
-    else:
-        ncand_all, nsearched_all = ncand, nsearched
-
-    # ---- end to end through the host-buffer C-ABI call a reference binding makes (cledb_invert: search + solution
-    #      building, pinned host memory in, the finished invout / sfound maps in pinned host memory out)
-    from cledb_b200 import synth
-    hdr = synth.make_dbhdr()
-    out_h = dict(invout=torch.empty((npix, k, 11), dtype=torch.float32).pin_memory().numpy(),
-                 sfound=torch.empty((npix, k, 8), dtype=torch.float32).pin_memory().numpy(),
-                 status=torch.empty(npix, dtype=torch.uint8).pin_memory().numpy())
-    sobs_n, snr_n, id_n = sobs_h.numpy(), snr_h.numpy(), id_h.numpy()
-    yobs_n = torch.from_numpy(obs['yobs'].reshape(-1).copy()).pin_memory().numpy()
-    dobs_n = torch.from_numpy(obs['dobs'].reshape(-1).copy()).pin_memory().numpy()
-    aobs_n = obs['aobs'].reshape(-1)
-    dopp_n = np.ascontiguousarray(obs['sobs_dopp'].reshape(npix, -1)[:, 0]) if args.mode == 'iqud' else None
-    bcalc = 3 if args.mode == 'iqud' else 0
-
-    def e2e_step():
-        ctx.invert(mode, sobs_n, snr_n, id_n, k, yobs_n, dobs_n, aobs_n, dopp_n, hdr, 1000, bcalc, out=out_h)
-
-    for _ in range(3):
-        e2e_step()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    # ---- a stream of maps through TWO contexts on this GPU (two host threads, each the same blocking cledb_invert call on its
-    #      own pinned buffers): the result copy of one map overlaps the search of the next.  Extra information next to `e2e`
-    #      (which is the single synchronous call a reference binding makes), N = 1 only.
-    e2e_stream = None
-    if world == 1 and not args.no_prune_pass:
-        ctx2 = native.Context(local)
-        ctx2.set_pruning(pruned)
-        for i, d in enumerate(db):
-            ctx2.db_put(i, d, args.encoding)
-        out_h2 = dict(invout=torch.empty((npix, k, 11), dtype=torch.float32).pin_memory().numpy(),
-                      sfound=torch.empty((npix, k, 8), dtype=torch.float32).pin_memory().numpy(),
-                      status=torch.empty(npix, dtype=torch.uint8).pin_memory().numpy())
-        nmaps = max(4, args.steps)
-
-        def worker(c, o, n):
-            for _ in range(n):
-                c.invert(mode, sobs_n, snr_n, id_n, k, yobs_n, dobs_n, aobs_n, dopp_n, hdr, 1000, bcalc, out=o)
-
-        worker(ctx2, out_h2, 3)
-        ths = [threading.Thread(target=worker, args=(ctx, out_h, nmaps)), threading.Thread(target=worker, args=(ctx2, out_h2, nmaps))]
-        t0 = time.perf_counter()
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        e2e_stream = (time.perf_counter() - t0) / (2 * nmaps)
-        same = bool(np.array_equal(out_h['invout'], out_h2['invout'], equal_nan=True) and np.array_equal(out_h['sfound'], out_h2['sfound'], equal_nan=True))
-        ctx2.close()
-    # ---- the same maps once more through the brute-force search (pruning off): the kernel that evaluates every
-    #      (pixel, entry) pair, quoted against the FP32 peak
-    brute = None
-    if pruned and not args.no_prune_pass:
-        for i in range(len(db)):
-            ctx.db_drop(i)
-        ctx.set_pruning(False)
-        for i, d in enumerate(db):
-            ctx.db_put(i, d, args.encoding)
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        b_step, b_kern = timed(min(args.steps, 10))
-        brute = (float(np.mean(b_step)), float(np.mean(b_kern)) if len(b_kern) else float('nan'))
-    clocks = sampler.stop() if rank == 0 else None
-    h2d = npix * (32 + 32 + 4 + 4 + 4 + 4 + 4 + (4 if args.mode == 'iqud' else 0))
-    d2h = npix * (k * (44 + 32) + 1)
-
-    if rank != 0:
+    B = Bench(args)
+    world = B.world
+    extra = [c for c in args.configs.split(',') if c] or (['2b', '3', '4', '5'] if world == 1 else ['2b', '5'])
+    top = bench_search(B, args.mode, args.nx, args.ndb, args.encoding, args.steps, args.warmup, with_gather=True,
+                       want_python=True, want_stream=True)
+    db, obs = top.pop('_inputs')
+    main_rec = top['bruteforce' if args.no_prune else 'pruned']
+    by = {}
+    tag = 'config%s_%s_%d' % ('2' if args.mode == 'iquv' else '3', args.mode, args.nx)
+    by[tag + '_pruned'] = top['pruned']
+    if '2b' in extra:
+        by[tag + '_bruteforce'] = top['bruteforce']
+    cpu_main = None
+    if B.rank == 0 and not args.no_cpu_baseline:
+        cpu_main = cpu_baseline(args.mode, args.encoding, db, obs, args.cpu_seconds)
+        for r in (top['pruned'], top['bruteforce']):
+            r['cpu_baseline'] = cpu_main
+    del db, obs
+    if '3' in extra and args.mode == 'iquv':
+        other = bench_search(B, 'iqud', args.nx, args.ndb, args.encoding, max(5, args.steps // 2), args.warmup, with_gather=False,
+                             want_python=False, want_stream=False)
+        db3, obs3 = other.pop('_inputs')
+        by['config3_iqud_%d_pruned' % args.nx] = other['pruned']
+        by['config3_iqud_%d_bruteforce' % args.nx] = other['bruteforce']
+        if B.rank == 0 and not args.no_cpu_baseline:
+            c3 = cpu_baseline('iqud', args.encoding, db3, obs3, min(args.cpu_seconds, 10.0))
+            other['pruned']['cpu_baseline'] = other['bruteforce']['cpu_baseline'] = c3
+        del db3, obs3
+    if '4' in extra:
+        by.update(bench_elementwise(B, 2048, max(10, args.steps), cpu=not args.no_cpu_baseline))
+    if '5' in extra:
+        rec5 = bench_config5(B, args.nx5, args.ndb5, args.steps)
+        if cpu_main is not None:
+            rec5['cpu_baseline'] = dict(cpu_main, sample=cpu_main['sample'] + ' (per-pixel cost of the CPU path does not depend on how many '
+                                                                             'databases the map touches: same figure as config 2)')
+        by['config5_iquv_%d_multidb' % args.nx5] = rec5
+    B.barrier()
+    clocks = None
+    if B.rank == 0:
+        clocks = B.sampler.summary()
+        B.sampler.stop()
+    if B.rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            B.dist.destroy_process_group()
         return
-
-    kms = float(np.mean(kern_ms)) if len(kern_ms) else float('nan')
-
-    def traffic_of(name):                                 # DRAM bytes of the search kernel per launch, from the committed ncu capture
-        if args.nx == 256 and args.ndb == 1 and args.encoding == 1:
-            try:
-                return json.load(open(os.path.join(REPO, 'profiles', 'k_match_traffic.json'))).get(name)
-            except Exception:
-                return None
-        return None
-
-    flops = 20.0 * ncand                                  # 10 FMA per candidate evaluation, this rank
-    theo = props['sm_count'] * 128 * 2 * (clocks['sm_max_mhz'] or props['sm_clock_khz'] / 1e3) * 1e6 / 1e12
-    peak = fp32_peak
-    enc_name = 'int16' if args.encoding == 1 else 'float32'
-
-    def roof(kernel, kernel_ms, step_mean_ms, traffic):
-        achieved = flops / (kernel_ms * 1e-3) / 1e12
-        return dict(bound='fp32', kernel=kernel, achieved=achieved, peak=peak, unit='TFLOP/s',
-                    frac=achieved / peak if peak else None, traffic=traffic, kernel_ms=kernel_ms,
-                    kernel_share_of_step=kernel_ms / step_mean_ms, flop_per_candidate=20, candidates_per_launch=ncand,
-                    peak_source='FFMA microkernel measured in this run (cledb_measure_fp32_peak); theoretical %.1f TFLOP/s '
-                                '= %d SMs x 128 lanes x 2 x max SM clock' % (theo, props['sm_count']))
-
-    roofline_pruned = None
-    if pruned:
-        roofline_pruned = roof('k_match_pruned<%s>' % enc_name, kms, float(np.mean(step_ms)), traffic_of(args.mode + '_pruned'))
-        pairs = prune_stats['evaluated'] + prune_stats['skipped']
-        roofline_pruned['frac_algorithmic'] = roofline_pruned.pop('frac')
-        roofline_pruned['frac'] = (20.0 * 256 * prune_stats['evaluated'] / (kms * 1e-3) / 1e12 / peak) if peak else None
-        roofline_pruned['bound'] = 'instruction issue (selection and bound code); not FP32-bound'
-        roofline_pruned['note'] = ('the kernel of the timed steps (value, e2e): exact tile bounds skip %.1f %% of the (pixel, tile) pairs. '
-                                   'frac counts the FLOPs of the pairs it evaluates, frac_algorithmic the FLOPs of every (pixel, candidate) '
-                                   'pair as in SURVEY 8d (> 1: work avoided, not a throughput claim)'
-                                   % (100.0 * prune_stats['skipped'] / max(1, pairs)))
-    if brute is not None:
-        # the FP32-bound kernel of the path - the brute-force chi^2 search north_star's roofline target is set on - timed in
-        # this run on the same maps with pruning off
-        roofline = roof('k_match<%s,fp32>' % enc_name, brute[1], brute[0], traffic_of(args.mode))
-        roofline['path'] = 'pruning off (cledb_set_pruning(ctx, 0)): %.3f ms per step, %.4g pixels/s; value / e2e above are measured with ' \
-                           'pruning on, see roofline_pruned' % (brute[0], world * npix / (brute[0] * 1e-3))
-        roofline['value_pruning_off'] = world * npix / (brute[0] * 1e-3)
-    elif pruned:
-        roofline = roofline_pruned
-    else:
-        roofline = roof('k_match<%s,fp32>' % enc_name, kms, float(np.mean(step_ms)), traffic_of(args.mode))
     line = dict(
-        metric='2-line pixels/s', value=world * npix / (ms * 1e-3), unit='pixels/s', n_gpus=world, steps=args.steps,
-        warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-        data='synthetic',
-        config=dict(workload=workload_name(args), db_encoding='int16' if args.encoding == 1 else 'float32',
-                    parallelism='pixel-sharded x%d, database replicated, NCCL all_gather of idx/chi maps' % world if world > 1 else 'single GPU',
-                    search='exact tile pruning (library default)' if pruned else 'brute force (pruning off)',
+        metric='2-line pixels/s', value=main_rec['value'], unit='pixels/s', n_gpus=world, steps=main_rec['steps'],
+        warmup=max(args.warmup, 3), ms_per_step=main_rec['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None,
+        dtype='f32', data='synthetic',
+        config=dict(workload=main_rec['workload'], db_encoding='int16' if args.encoding == 1 else 'float32',
+                    parallelism=('pixel-sharded x%d (one map per rank), database replicated, one all-gather of the idx/chi maps by the '
+                                 'library (cledb_allgather_dev, NCCL over NVLink)' % world) if world > 1 else 'single GPU',
+                    search=main_rec['search'],
                     l2='flushed between timed steps (256 MiB memset, outside the per-step CUDA events)',
                     timing='CUDA events per step on the launching stream, mean of K, max over ranks'),
-        pruning=prune_stats,
-        evals_per_s=world * npix * 340200 / (ms * 1e-3),
-        candidate_evals_per_s=ncand_all / (ms * 1e-3),
-        pixels_searched=nsearched_all,
-        gpu_launches=int(launches),
-        e2e=dict(value=world * npix / e2e_s, unit='pixels/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                 api='cledb_invert (C-ABI, pinned host buffers in, finished invout/sfound maps out)', ms_per_step=e2e_s * 1e3,
-                 stream_of_maps=None if e2e_stream is None else dict(
-                     value=npix / e2e_stream, ms_per_map=e2e_stream * 1e3, identical_outputs=same,
-                     how='two contexts on this GPU, one host thread each, the same blocking call on its own pinned buffers: '
-                         'copies of one map overlap the search of the next')),
-        roofline=roofline,
-        clocks=clocks,
-        device=dict(sm_count=props['sm_count'], match_ctas_per_sm=props['match_ctas_per_sm'], match_regs=props['match_regs'],
-                    match_smem=props['match_smem']))
-    if roofline_pruned is not None and roofline is not roofline_pruned:
-        line['roofline_pruned'] = roofline_pruned
-    if not args.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_baseline(args, db, obs)
+        evals_per_s=main_rec['evals_per_s'], evals_definition=main_rec['evals_definition'],
+        nominal_scanned_evals_per_s=main_rec['nominal_scanned_evals_per_s'],
+        nominal_candidate_evals_per_s=main_rec['nominal_candidate_evals_per_s'],
+        pixels_searched=main_rec['pixels_searched'], gpu_launches=main_rec['gpu_launches'], pruning=main_rec['pruning'],
+        e2e=main_rec.get('e2e'), roofline=main_rec['roofline'], clocks=clocks,
+        device=dict(sm_count=B.props['sm_count'], match_ctas_per_sm=B.props['match_ctas_per_sm'], match_regs=B.props['match_regs'],
+                    match_smem=B.props['match_smem']),
+        by_config=by)
+    if cpu_main is not None:
+        line['cpu_baseline'] = cpu_main
+    if 'bruteforce' in top and not args.no_prune:
+        line['roofline_bruteforce'] = dict(top['bruteforce']['roofline'], value=top['bruteforce']['value'],
+                                           ms_per_step=top['bruteforce']['ms_per_step'],
+                                           note='the FP32-bound kernel of the path (pruning off), same maps, same run: by_config.%s_bruteforce' % tag)
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
 
 
 if __name__ == '__main__':
