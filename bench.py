@@ -306,7 +306,7 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
     out_h = dict(invout=torch.empty((npix, k, 11), dtype=torch.float32).pin_memory().numpy(),
                  sfound=torch.empty((npix, k, 8), dtype=torch.float32).pin_memory().numpy(),
                  status=torch.empty(npix, dtype=torch.uint8).pin_memory().numpy(),
-                 issue=torch.empty((npix, 2), dtype=torch.uint8).pin_memory().numpy())
+                 issue=torch.empty(npix, dtype=torch.int32).pin_memory().numpy())
     sobs_n, snr_n, id_n = sobs_h.numpy(), snr_h.numpy(), id_h.numpy()
     yobs_n, dobs_n = B.pinned(obs['yobs'].reshape(-1)).numpy(), B.pinned(obs['dobs'].reshape(-1)).numpy()
     aobs_n = obs['aobs'].reshape(-1)
@@ -317,7 +317,7 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
         c.invert(mode, sobs_n, snr_n, id_n, k, yobs_n, dobs_n, aobs_n, dopp_n, hdr, 1000, bcalc, out=o)
 
     h2d = npix * (32 + 32 + 4 + 4 + 4 + 4 + 4 + (4 if mode_name == 'iqud' else 0))
-    d2h = npix * (k * (44 + 32) + 1 + 2)
+    d2h = npix * (k * (44 + 32) + 1 + 4)
     enc_name = 'int16' if encoding == 1 else 'float32'
     recs = {}
     for pruned in (True, False):
@@ -429,18 +429,23 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
         pargs = (obs['sobs_totrot'], obs['sobs_dopp'] if mode_name == 'iqud' else 0, db, obs['db_enc'], obs['yobs'], obs['aobs'],
                  obs['dobs'], obs['snr'])
         ptail = (hdr, obs['keyvals'], k, 1000, bcalc, mode_name == 'iqud', 1, False, 0)
-        for _ in range(3):
-            procinv.cledb_invproc(*pargs, obs['issuemask'].copy(), *ptail)
+        keep = None
+        for _ in range(4):                                   # the binding's pinned pool reaches its steady state: two sets of result
+            keep = procinv.cledb_invproc(*pargs, obs['issuemask'].copy(), *ptail)      # arrays alive at a time, as in the loop below
         B.barrier()
         nst = max(3, min(steps, 20))
         iss = obs['issuemask'].copy()
-        t0 = time.perf_counter()
+        per_call = []
         for _ in range(nst):
+            t0 = time.perf_counter()
             inv, sf = procinv.cledb_invproc(*pargs, iss, *ptail)
-        py_s = B.max_over_ranks((time.perf_counter() - t0) / nst)
+            per_call.append(time.perf_counter() - t0)
+        del keep
+        py_s = B.max_over_ranks(float(np.mean(per_call)))
         agree = bool(np.array_equal(inv.reshape(npix, k, 11), recs['pruned']['e2e'] and out_h['invout'], equal_nan=True)) if want_e2e else None
         recs['pruned'].setdefault('e2e', {})['python'] = dict(
             value=B.world * npix / py_s, unit='pixels/s', ms_per_step=py_s * 1e3, same_invout_as_c_abi=agree,
+            ms_per_call_median=float(np.median(per_call)) * 1e3, ms_per_call_min=float(np.min(per_call)) * 1e3, ms_per_call_max=float(np.max(per_call)) * 1e3,
             api='CLEDB_PROC.cledb_invproc(...) - the reference-shaped call: pageable NumPy inputs, fresh result arrays from the pinned pool, '
                 'issuemask updated in place')
         del inv, sf
@@ -597,7 +602,7 @@ def bench_config5(B, nx, ndb, steps):
     f_inv = torch.empty((npix, k, 11), dtype=torch.float32, device=B.dev)
     f_sf = torch.empty((npix, k, 8), dtype=torch.float32, device=B.dev)
     f_st = torch.empty(npix, dtype=torch.uint8, device=B.dev)
-    f_iss = torch.empty((npix, 2), dtype=torch.uint8, device=B.dev)
+    f_iss = torch.empty(npix, dtype=torch.int32, device=B.dev)
     sp = send.data_ptr()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     parts = []
@@ -643,7 +648,7 @@ def bench_config5(B, nx, ndb, steps):
                workload='ONE %dx%d 2-line IQUV map over %d synthetic PyCELP-shaped databases (height bands x densities; %.1f GB of float32 '
                         'databases, %s in HBM), pixel-sharded over %d GPU(s): cledb_partition -> cledb_invert_dev on the shard -> one '
                         'all-gather of the packed finished records (%d B/pixel) -> scatter into the full maps on every rank'
-                        % (nx, nx, ndb, ndb * NDB_ROWS * 32 / 1e9, 'int16' if B.args.encoding == 1 else 'float32', B.world, k * 76 + 3),
+                        % (nx, nx, ndb, ndb * NDB_ROWS * 32 / 1e9, 'int16' if B.args.encoding == 1 else 'float32', B.world, k * 76 + 5),
                search='exact tile pruning (library default)', pixels_searched=nsearched, databases_on_this_rank=int(used.size),
                shard_pixels=n, gpu_launches=int(launches),
                step_breakdown_ms=dict(search_and_build=part[0], all_gather=part[1], scatter=part[2],
@@ -661,9 +666,9 @@ def bench_config5(B, nx, ndb, steps):
         ctx.invert_sharded(native.MODE_IQUV, sobs, snr, ids, k, yl, dl, ang, None, hdr, 1000, 0, npix, order, bounds, root=0, out=out)
     e2e_s = B.max_over_ranks((time.perf_counter() - t0) / ne)
     rec['e2e'] = dict(value=npix / e2e_s, unit='pixels/s', ms_per_step=e2e_s * 1e3, h2d_bytes_per_step=int(n) * 84,
-                      d2h_bytes_per_step=npix * (k * 76 + 3),
+                      d2h_bytes_per_step=npix * (k * 76 + 5),
                       api='cledb_invert_sharded (C-ABI, collective): every rank uploads its shard, rank 0 receives the full invout / sfound '
-                          'maps in pinned host memory (%.0f MB over one PCIe link)' % (npix * (k * 76 + 3) / 1e6))
+                          'maps in pinned host memory (%.0f MB over one PCIe link)' % (npix * (k * 76 + 5) / 1e6))
     if B.rank == 0:
         same = bool(np.array_equal(out['invout'], f_inv.cpu().numpy(), equal_nan=True))
         rec['e2e']['same_maps_as_device_path'] = same

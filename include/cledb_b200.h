@@ -17,8 +17,12 @@
  *   - "host" entry points take C-contiguous host buffers (pageable or pinned), copy in, run, copy out and
  *     return when the results are in the output buffers.  "_dev" entry points take device pointers that are
  *     valid on the context's device and enqueue on the given cudaStream_t (passed as void*; NULL = the
- *     context's own stream) without waiting for the results.  (cledb_match_dev synchronises that stream once
- *     internally, after its classification kernel, to size its work items from the bucket counts.)
+ *     context's own stream) without waiting for the results.  With the default search (exact tile pruning) a "_dev" call
+ *     is a pure enqueue - no host synchronisation, capturable in a CUDA graph once the workspaces have their size; only the
+ *     brute-force search (pruning off, or the fp64 validation kernel) synchronises the stream once internally, after its
+ *     classification kernel, to size its work items from the bucket counts.  Asynchronous errors: a searched pixel whose
+ *     database id is not resident gets status CLEDB_PIX_NULL and raises a flag that the next synchronising call on the
+ *     context reports as CLEDB_ERR_NODB (every host entry point, cledb_synchronize).
  *   - all arrays are row-major; float = IEEE binary32.
  */
 #ifndef CLEDB_B200_H
@@ -164,13 +168,13 @@ int cledb_pruning_stats(cledb_ctx* ctx, int64_t evaluated[2]);
  *   yobs[npix], dobs[npix] float32; dopp: B_POS of every pixel for IQUD (element p at dopp[p*dopp_stride],
  *   float32 or float64 as dopp_is_f64 says; NULL for IQUV); maxchisq, bcalc as in ctrlparams
  *   invout[npix,nsearch,11], sfound[npix,nsearch,8] float32; status_out[npix] (may be NULL)
- *   issue_out[npix,2] uint8 (may be NULL): the tests behind the issue codes 512 / 1024 / 2048 of cledb_invproc (:323-355)
- *     [p][0] bit 0 = Van-Vleck proximity of the LAST solution (53 deg <= vartheta_B <= 56 deg; `flg = 0` sits inside the
- *            reference's loop over solutions, :324, so only slot nsearch-1 decides), evaluated in float64;
- *            bit 1 = vartheta_B lies within 1e-3 deg of 53 or 56: the reference evaluates the chain in float32 with the
- *            caller's NumPy, whose last bits decide such a pixel - the binding re-evaluates it (about 1 pixel in 50 000)
- *     [p][1] bit 0 = chi^2 of the best solution > 10 (:351), bit 1 = snr[p,0] < 1 (:353)
- *   The binding ORs 512 / 1024 / 2048 into its issuemask from these bits. */
+ *   issue_out[npix] int32 (may be NULL): the issue codes of cledb_invproc (:323-355) this pixel raises, OR-ed together
+ *     512  = Van-Vleck proximity of the LAST solution (53 deg <= vartheta_B <= 56 deg; `flg = 0` sits inside the reference's
+ *            loop over solutions, :324, so only slot nsearch-1 decides), evaluated in float64
+ *     1024 = chi^2 of the best solution > 10 (:351)          2048 = snr[p,0] < 1 (:353)
+ *     1    = vartheta_B lies within 1e-3 deg of 53 or 56: the reference evaluates the chain in float32 with the caller's
+ *            NumPy, whose last bits decide such a pixel - the binding re-evaluates those (about 1 pixel in 50 000)
+ *   The binding ORs (issue_out[p] & ~1) into both lines of its issuemask: a code already set is not added twice. */
 typedef struct cledb_dbgrid {
     int32_t dbtype, ngx, nbphi, nbtheta;               /* dbhdr[14], [2], [3], [4]  (CLEDB_PREPINV.py:482-508) */
     float   gxmin, gxmax, bphimin, bphimax, bthetamin, bthetamax;
@@ -182,14 +186,14 @@ int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npix,
                  const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
                  const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
                  double maxchisq, int bcalc, int strict_topk,
-                 float* invout, float* sfound, uint8_t* status_out, uint8_t* issue_out);
+                 float* invout, float* sfound, uint8_t* status_out, int32_t* issue_out);
 /* device-pointer variant: every array, including the four tables inside *grid, lives on the context's device */
 int cledb_invert_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
                      const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
                      const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
                      const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
                      double maxchisq, int bcalc, int strict_topk,
-                     float* invout, float* sfound, uint8_t* status_out, uint8_t* issue_out, void* stream);
+                     float* invout, float* sfound, uint8_t* status_out, int32_t* issue_out, void* stream);
 
 /* ---- reduced-database mode (reduced = True) -------------------------------------------------------- *
  * Replaces cledb_getsubsetiquv / cledb_getsubsetiqud and the search over their per-pixel output (CLEDB_PROC.py:1401-1568,
@@ -222,7 +226,7 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
                          const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
                          const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
                          double maxchisq, int bcalc, int strict_topk,
-                         float* invout, float* sfound, uint8_t* status_out, uint8_t* issue_out);
+                         float* invout, float* sfound, uint8_t* status_out, int32_t* issue_out);
 
 /* ---- multi-GPU: one process and one context per GPU, pixels sharded, databases replicated ------------ *
  * The reference dispatches one pool task per pixel (CLEDB_PROC.py:304-313): pixels are independent, the search has no exchange
@@ -241,9 +245,9 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  *                          on every rank.
  *   cledb_shard_layout     byte offsets of the packed records of a shard of <= maxcount pixels:
  *                          layout[0..3] = offsets of invout[maxcount,k,11], sfound[maxcount,k,8], status[maxcount],
- *                          issue[maxcount,2]; layout[4] = bytes per rank (the all-gather count)
+ *                          issue[maxcount] int32; layout[4] = bytes per rank (the all-gather count)
  *   cledb_unshard_dev      scatters the gathered records of all ranks to their pixels: recv[nranks][layout] ->
- *                          invout[npix,k,11], sfound[npix,k,8], status[npix], issue[npix,2] (device pointers; status and
+ *                          invout[npix,k,11], sfound[npix,k,8], status[npix], issue[npix] (device pointers; status and
  *                          issue may be NULL)
  *   cledb_invert_sharded   cledb_invert for one map of npix pixels over all ranks: every rank passes the inputs of ITS
  *                          nlocal pixels (those of order[bounds[rank] : bounds[rank+1]], in that order; db_id = the ids
@@ -262,14 +266,14 @@ int cledb_partition(int64_t npix, const int32_t* key, int nkeys, const double* w
 int cledb_shard_layout(int64_t maxcount, int nsearch, int64_t layout[5]);
 int cledb_unshard_dev(cledb_ctx* ctx, int nranks, const int64_t* bounds_dev, const int32_t* order_dev, int64_t npix,
                       int64_t maxcount, int nsearch, const void* recv, float* invout, float* sfound, uint8_t* status,
-                      uint8_t* issue, void* stream);
+                      int32_t* issue, void* stream);
 int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int64_t nlocal,
                          const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
                          const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
                          const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
                          double maxchisq, int bcalc, int strict_topk,
                          int64_t npix, const int32_t* order, const int64_t* bounds, int root,
-                         float* invout, float* sfound, uint8_t* status_out, uint8_t* issue_out);
+                         float* invout, float* sfound, uint8_t* status_out, int32_t* issue_out);
 
 /* ---- pinned host memory for the binding's staging buffers (cudaHostAlloc / cudaFreeHost) ------------- */
 int cledb_host_alloc(int64_t bytes, void** out);

@@ -103,7 +103,10 @@ def _search_and_build(mode, sobs, sobs_dopp, database, db_enc, yobs, aobs, dobs,
     if OPTIONS.get('sharded') and getattr(_context(), 'nranks', 1) > 1:
         return _search_and_build_sharded(_context(), mode, sobs, sobs_dopp, database, enc, yobs, aobs, dobs, snr, dbhdr, nsearch,
                                          maxchisq, bcalc, reduced)
-    ctx, ids = _upload(database, _used_databases(enc, len(database)))
+    if enc.size and (int(enc.max()) >= len(database) or int(enc.min()) < 0):
+        raise IndexError('db_enc refers to database %d, the list holds %d' % (int(enc.max()), len(database)))   # as the reference's database[db_enc[xx,yy]]
+    used = np.zeros(1, np.int64) if len(database) == 1 else _used_databases(enc, len(database))
+    ctx, ids = _upload(database, used)
     if len(ids) == 1 and list(ids.values())[0] == 0 and not enc.any() and enc.dtype == np.int32:
         dbid = np.ascontiguousarray(enc)             # one database, id 0: db_enc itself is the id map
     else:

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcledb_b200.so')
+LIB_PATH = os.environ.get('CLEDB_B200_LIB') or os.path.join(os.path.dirname(_HERE), 'lib', 'libcledb_b200.so')
 
 MODE_IQUV, MODE_IQUD = 0, 1
 ENC_F32, ENC_I16 = 0, 1
@@ -230,16 +230,18 @@ class PinnedPool:
 pinned = PinnedPool()
 
 
-def issue_codes(flags, invout=None):
-    """Issue codes 512 / 1024 / 2048 of cledb_invproc (CLEDB_PROC.py:347-355) per pixel from the device's ``issue_out[npix,2]``
-    flags (see cledb_invert in the header).  Pixels whose Van-Vleck angle lies within 1e-3 deg of a limit are re-evaluated
+def issue_codes(codes, invout=None):
+    """Issue codes 512 / 1024 / 2048 of cledb_invproc (CLEDB_PROC.py:347-355) per pixel from the device's ``issue_out[npix]``
+    (see cledb_invert in the header).  Pixels whose Van-Vleck angle lies within 1e-3 deg of a limit (bit 0) are re-evaluated
     with NumPy from ``invout[npix,k,11]`` - the reference's own float32 chain decides those."""
     from . import solution
-    vv = (flags[:, 0] & 1).astype(bool)
-    amb = np.flatnonzero(flags[:, 0] & 2)
-    if amb.size and invout is not None:
-        vv[amb] = solution.van_vleck_last(invout[amb])
-    return (vv.astype(np.int32) << 9) | ((flags[:, 1] & 1).astype(np.int32) << 10) | ((flags[:, 1] & 2).astype(np.int32) << 10)
+    amb = np.flatnonzero(codes & 1)
+    if amb.size:
+        codes = codes & ~np.int32(1)
+        if invout is not None:
+            vv = solution.van_vleck_last(invout[amb])
+            codes[amb] = (codes[amb] & ~np.int32(512)) | (vv.astype(np.int32) << 9)
+    return codes
 
 
 class Reduced(ctypes.Structure):
@@ -497,7 +499,7 @@ class Context:
     def result_buffers(npix, k):
         """Fresh result arrays in pinned host memory (see PinnedPool)."""
         return dict(invout=pinned.empty((npix, k, 11), np.float32), sfound=pinned.empty((npix, k, 8), np.float32),
-                    status=pinned.empty((npix,), np.uint8), issue=pinned.empty((npix, 2), np.uint8))
+                    status=pinned.empty((npix,), np.uint8), issue=pinned.empty((npix,), np.int32))
 
     def invert(self, mode, sobs, snr, db_id, nsearch, yobs, dobs, aobs, dopp, dbhdr, maxchisq, bcalc, strict_topk=False,
                precision=PREC_FP32, out=None):
@@ -611,7 +613,7 @@ class Context:
         red = Reduced.build(mode, sobs, sobs_dopp, dbhdr, tie_order)
         grid = DbGrid.from_dbhdr(dbhdr)
         invout, sfound = np.empty((npix, k, 11), np.float32), np.empty((npix, k, 8), np.float32)
-        status, issue = np.empty(npix, np.uint8), np.empty((npix, 2), np.uint8)
+        status, issue = np.empty(npix, np.uint8), np.empty(npix, np.int32)
         self._check(self.lib.cledb_invert_reduced(self.h, int(mode), int(precision), npix, _ptr(sobs), _ptr(snr), _ptr(db_id), k,
                                                   ctypes.addressof(red), _ptr(yobs), _ptr(dobs), _ptr(rot_cos), _ptr(rot_sin),
                                                   _ptr(dopp0), is64, 1, ctypes.addressof(grid), float(maxchisq), int(bcalc),

@@ -218,7 +218,7 @@ def apply_issue_codes(issuemask, codes):
     """Add the per-pixel issue codes (a sum of 512 / 1024 / 2048, ``native.issue_codes``) to both lines of ``issuemask``,
     each code only where it is not yet set (CLEDB_PROC.py:347-355).  Adding a power of two whose bit is clear is an OR."""
     if isinstance(issuemask, np.ndarray) and np.issubdtype(issuemask.dtype, np.integer):
-        issuemask[:, :, 0:2] |= codes[:, :, None].astype(issuemask.dtype)
+        issuemask[:, :, 0:2] |= codes[:, :, None] if codes.dtype == issuemask.dtype else codes[:, :, None].astype(issuemask.dtype)
         return issuemask
     for line in range(2):                                  # exotic mask types: the reference's own arithmetic
         mm = issuemask[:, :, line]

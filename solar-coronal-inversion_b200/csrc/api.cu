@@ -60,6 +60,7 @@ extern "C" int cledb_destroy(cledb_ctx* ctx) {
     if (ctx->red.ptr) cudaFree(ctx->red.ptr);
     if (ctx->d_prune_stats) cudaFree(ctx->d_prune_stats);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->io.ptr) cudaFree(ctx->io.ptr);
     for (auto& pr : ctx->prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -89,7 +90,7 @@ extern "C" int cledb_synchronize(cledb_ctx* ctx) {
     if (!ctx) return CLEDB_ERR_ARG;
     CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
     CLEDB_CUDA(ctx, cudaDeviceSynchronize());
-    return CLEDB_OK;
+    return check_async_error(ctx);
 }
 
 extern "C" int64_t cledb_launch_count(cledb_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -229,7 +230,7 @@ extern "C" int cledb_match(cledb_ctx* ctx, int mode, int precision, int64_t npix
     if (status_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(status_out, w + o_st, n, cudaMemcpyDeviceToHost, st));
     if (ncand_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(ncand_out, w + o_nc, n * 8, cudaMemcpyDeviceToHost, st));
     CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
-    return CLEDB_OK;
+    return check_async_error(ctx);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -101,6 +101,8 @@ struct cledb_ctx {
     int32_t* h_cnt = nullptr;                      // mapped pinned host copy of the bucket sizes
     int32_t* d_cnt_mapped = nullptr;               // its device alias
     size_t h_cnt_cap = 0;
+    int32_t* h_err = nullptr;                      // mapped pinned word: a searched pixel named a database that is not resident
+    int32_t* d_err_mapped = nullptr;               // its device alias
     int last_P = 0, last_split = 0;                // work shape of the last search
     int64_t launches = 0;
     int pixels_per_item = 0;                      // 0 = choose from the pixel count
@@ -165,6 +167,7 @@ int  match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const f
                   const int32_t* db_id, int nsearch, int32_t* idx_out, float* chi_out, double* chi64_out,
                   int32_t* kpos_out, float* rows_out, uint8_t* status_out, int64_t* ncand_out, cudaStream_t st);
 int  match_occupancy(cledb_ctx* ctx);
+int  check_async_error(cledb_ctx* ctx);            // after a host synchronisation: CLEDB_ERR_NODB if a search met an unknown database id
 int  launch_decode_db(cledb_ctx* ctx, int slot, float* d_out, cudaStream_t st);
 int  launch_gather_rows(cledb_ctx* ctx, int slot, const int32_t* d_idx, int64_t n, float* d_rows, cudaStream_t st);
 int  launch_blos(cledb_ctx* ctx, int64_t npix, const float* iquv, double kfac, double g_eff, double ffac,
@@ -180,5 +183,5 @@ int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsea
                  int64_t dopp_stride, const cledb_dbgrid& grid_dev, double maxchisq, int bcalc, int strict_topk,
                  const int32_t* idx, const float* chi, const double* chi64, const int32_t* kpos, const float* rows,
                  const uint8_t* status, const int32_t* nan_slots, float* invout, float* sfound, cudaStream_t st,
-                 const float* snr = nullptr, uint8_t* issue_out = nullptr);
+                 const float* snr = nullptr, int32_t* issue_out = nullptr);
 }  // namespace cledb

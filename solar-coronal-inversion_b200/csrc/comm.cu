@@ -2,7 +2,7 @@
 //
 // The search has no exchange step - every pixel is independent (the reference dispatches one pool task per pixel,
 // CLEDB_PROC.py:304-313) - so the only collective of the path is the gather of the finished result maps.  Each rank
-// builds the packed records of its shard on the device (cledb_invert_dev writes invout | sfound | status | issue flags
+// builds the packed records of its shard on the device (cledb_invert_dev writes invout | sfound | status | issue codes
 // straight into the send buffer), ONE ncclAllGather moves them between the GPUs over NVLink / NVSwitch, and k_unshard
 // puts every record at its pixel's place in the full maps.  Nothing travels through host memory in between.
 //
@@ -194,34 +194,46 @@ Packed packed_layout(int64_t maxcount, int k) {
     L.o_inv = off; off = up(off + (size_t)maxcount * k * 44);
     L.o_sf = off;  off = up(off + (size_t)maxcount * k * 32);
     L.o_st = off;  off = up(off + (size_t)maxcount);
-    L.o_iss = off; off = up(off + (size_t)maxcount * 2);
+    L.o_iss = off; off = up(off + (size_t)maxcount * 4);
     L.bytes = off;
     return L;
 }
 }  // namespace
 
 namespace cledb {
-// one thread per 16-byte piece of a pixel's records: invout row k*44 B, sfound row k*32 B (both multiples of 16 for even k;
-// handled as 4-byte words otherwise), then the status byte and the two issue bytes
+// One warp per pixel: the pixel's invout row (k*44 B) and sfound row (k*32 B) move as 16-byte vectors when k is a multiple of
+// 4 (352 + 256 B at nsearch 8: 22 + 16 vectors, one or two per lane), as 4-byte words otherwise; lane 0 adds the status
+// byte and the two issue bytes.  Reads are contiguous (the packed records of a rank), writes are whole rows.
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_unshard(int nranks, const int64_t* __restrict__ bounds, const int32_t* __restrict__ order,
-                                                 int64_t maxcount, int k, const unsigned char* __restrict__ recv, size_t rank_bytes,
+                                                 int64_t npix, int k, const unsigned char* __restrict__ recv, size_t rank_bytes,
                                                  size_t o_inv, size_t o_sf, size_t o_st, size_t o_iss, float* __restrict__ invout,
-                                                 float* __restrict__ sfound, uint8_t* __restrict__ status, uint8_t* __restrict__ issue) {
-    const int words_inv = k * 11, words_sf = k * 8, words = words_inv + words_sf;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (sorted position, word)
-    const int64_t spos = i / words;
-    const int wd = (int)(i - spos * words);
-    if (spos >= bounds[nranks]) return;
+                                                 float* __restrict__ sfound, uint8_t* __restrict__ status, int32_t* __restrict__ issue) {
+    const int lane = threadIdx.x & 31;
+    const int64_t spos = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;          // position in the database-sorted order
+    if (spos >= npix) return;
     int r = 0;
     while (r + 1 < nranks && spos >= bounds[r + 1]) ++r;
     const int64_t j = spos - bounds[r];
     const int64_t p = order[spos];
     const unsigned char* blk = recv + (size_t)r * rank_bytes;
-    if (wd < words_inv) invout[p * words_inv + wd] = reinterpret_cast<const float*>(blk + o_inv)[j * words_inv + wd];
-    else sfound[p * words_sf + (wd - words_inv)] = reinterpret_cast<const float*>(blk + o_sf)[j * words_sf + (wd - words_inv)];
-    if (wd == 0) {
+    const int wi = k * 11, ws = k * 8;
+    if (VEC) {
+        const float4* si = reinterpret_cast<const float4*>(blk + o_inv) + j * (wi / 4);
+        const float4* ss = reinterpret_cast<const float4*>(blk + o_sf) + j * (ws / 4);
+        float4* di = reinterpret_cast<float4*>(invout) + p * (wi / 4);
+        float4* ds = reinterpret_cast<float4*>(sfound) + p * (ws / 4);
+        for (int w = lane; w < wi / 4; w += 32) di[w] = __ldcs(si + w);
+        for (int w = lane; w < ws / 4; w += 32) ds[w] = __ldcs(ss + w);
+    } else {
+        const float* si = reinterpret_cast<const float*>(blk + o_inv) + j * wi;
+        const float* ss = reinterpret_cast<const float*>(blk + o_sf) + j * ws;
+        for (int w = lane; w < wi; w += 32) invout[p * wi + w] = si[w];
+        for (int w = lane; w < ws; w += 32) sfound[p * ws + w] = ss[w];
+    }
+    if (lane == 0) {
         if (status) status[p] = blk[o_st + j];
-        if (issue) { issue[2 * p] = blk[o_iss + 2 * j]; issue[2 * p + 1] = blk[o_iss + 2 * j + 1]; }
+        if (issue) issue[p] = reinterpret_cast<const int32_t*>(blk + o_iss)[j];
     }
 }
 }  // namespace cledb
@@ -235,17 +247,20 @@ extern "C" int cledb_shard_layout(int64_t maxcount, int nsearch, int64_t layout[
 
 extern "C" int cledb_unshard_dev(cledb_ctx* ctx, int nranks, const int64_t* bounds_dev, const int32_t* order_dev, int64_t npix,
                                  int64_t maxcount, int nsearch, const void* recv, float* invout, float* sfound, uint8_t* status,
-                                 uint8_t* issue, void* stream) {
+                                 int32_t* issue, void* stream) {
     if (!ctx) return CLEDB_ERR_ARG;
     if (nranks < 1 || !bounds_dev || !order_dev || !recv || !invout || !sfound || nsearch < 1 || npix < 0) { ctx->err = "cledb_unshard: bad argument"; return CLEDB_ERR_ARG; }
     if (npix == 0) return CLEDB_OK;
     CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const Packed L = packed_layout(maxcount, nsearch);
-    const int64_t total = npix * (int64_t)nsearch * 19;
-    k_unshard<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(nranks, bounds_dev, order_dev, maxcount, nsearch,
-                                                              reinterpret_cast<const unsigned char*>(recv), L.bytes, L.o_inv, L.o_sf, L.o_st,
-                                                              L.o_iss, invout, sfound, status, issue);
+    const unsigned grid = (unsigned)((npix * 32 + 255) / 256);
+    if (nsearch % 4 == 0)
+        k_unshard<true><<<grid, 256, 0, st>>>(nranks, bounds_dev, order_dev, npix, nsearch, reinterpret_cast<const unsigned char*>(recv),
+                                              L.bytes, L.o_inv, L.o_sf, L.o_st, L.o_iss, invout, sfound, status, issue);
+    else
+        k_unshard<false><<<grid, 256, 0, st>>>(nranks, bounds_dev, order_dev, npix, nsearch, reinterpret_cast<const unsigned char*>(recv),
+                                               L.bytes, L.o_inv, L.o_sf, L.o_st, L.o_iss, invout, sfound, status, issue);
     ctx->launches++;
     CLEDB_CUDA(ctx, cudaGetLastError());
     return CLEDB_OK;
@@ -261,7 +276,7 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
                                     const float* rot_sin, const void* dopp, int dopp_is_f64, int64_t dopp_stride,
                                     const cledb_dbgrid* grid, double maxchisq, int bcalc, int strict_topk, int64_t npix,
                                     const int32_t* order, const int64_t* bounds, int root, float* invout, float* sfound,
-                                    uint8_t* status_out, uint8_t* issue_out) {
+                                    uint8_t* status_out, int32_t* issue_out) {
     if (!ctx) return CLEDB_ERR_ARG;
     if (!ctx->comm) { ctx->err = "cledb_invert_sharded: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
     cledb_comm* c = ctx->comm;
@@ -305,7 +320,7 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
     size_t foff = 0;
     auto ftake = [&](size_t b) { size_t o = foff; foff = up256(foff + b); return o; };
     const size_t f_inv = ftake(want ? (size_t)npix * k * 44 : 0), f_sf = ftake(want ? (size_t)npix * k * 32 : 0),
-                 f_st = ftake(want ? (size_t)npix : 0), f_iss = ftake(want ? (size_t)npix * 2 : 0);
+                 f_st = ftake(want ? (size_t)npix : 0), f_iss = ftake(want ? (size_t)npix * 4 : 0);
     if (want && (rc = ensure_workspace(ctx, c->full, foff))) return rc;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx->io.ptr);
     if (n > 0) {
@@ -344,7 +359,7 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
                               reinterpret_cast<int32_t*>(w + o_id), nsearch, reinterpret_cast<float*>(w + o_y), reinterpret_cast<float*>(w + o_d),
                               reinterpret_cast<float*>(w + o_rc), reinterpret_cast<float*>(w + o_rs), dsz ? w + o_dopp : nullptr, dopp_is_f64, 1,
                               &g, maxchisq, bcalc, strict_topk, reinterpret_cast<float*>(send + L.o_inv), reinterpret_cast<float*>(send + L.o_sf),
-                              send + L.o_st, send + L.o_iss, st);
+                              send + L.o_st, reinterpret_cast<int32_t*>(send + L.o_iss), st);
         if (rc) return rc;        // a rank that fails here leaves the others waiting in the collective: the launcher aborts the job
     }
     // ---- the one collective of the path, then every record to its pixel
@@ -352,13 +367,13 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
     if (want) {
         unsigned char* f = reinterpret_cast<unsigned char*>(c->full.ptr);
         rc = cledb_unshard_dev(ctx, R, reinterpret_cast<int64_t*>(dord + o_bounds), reinterpret_cast<int32_t*>(dord), npix, maxcount, nsearch,
-                               c->recv.ptr, reinterpret_cast<float*>(f + f_inv), reinterpret_cast<float*>(f + f_sf), f + f_st, f + f_iss, st);
+                               c->recv.ptr, reinterpret_cast<float*>(f + f_inv), reinterpret_cast<float*>(f + f_sf), f + f_st, reinterpret_cast<int32_t*>(f + f_iss), st);
         if (rc) return rc;
         CLEDB_CUDA(ctx, cudaMemcpyAsync(invout, f + f_inv, (size_t)npix * k * 44, cudaMemcpyDeviceToHost, st));
         CLEDB_CUDA(ctx, cudaMemcpyAsync(sfound, f + f_sf, (size_t)npix * k * 32, cudaMemcpyDeviceToHost, st));
         if (status_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(status_out, f + f_st, (size_t)npix, cudaMemcpyDeviceToHost, st));
-        if (issue_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(issue_out, f + f_iss, (size_t)npix * 2, cudaMemcpyDeviceToHost, st));
+        if (issue_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(issue_out, f + f_iss, (size_t)npix * 4, cudaMemcpyDeviceToHost, st));
     }
     CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
-    return CLEDB_OK;
+    return check_async_error(ctx);
 }

@@ -5,6 +5,8 @@
 // One thread per pixel, 128-bit coalesced loads/stores, grid sized from the pixel count.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "cledb_internal.h"
 
 namespace cledb {

@@ -253,6 +253,7 @@ struct Plan {                 // all pointers are device pointers into the works
     int32_t* item0;           // [nkeys+1] first item of the bucket; item0[nkeys] = total items
     int32_t* nsub;            // [nkeys] candidate-list pieces (sign partitions x chunks) per pixel tile
     int32_t* counters;        // [0] next item to hand out, [1] error flag, [2] total items
+    int32_t* err_mapped;      // mapped host word: set when a searched pixel names a database that is not resident
     void*    recs;            // [npix] Rec<PREC>
     double*  c0;              // [npix] fp32 search: the per-pixel constant term of chi^2*2 (I1 component), added when the result is written
     void*    plist;           // [maxitems][P][k] Cand<PREC>
@@ -309,6 +310,8 @@ __global__ void __launch_bounds__(256) k_classify(Plan pl, const float* __restri
     }
     if (slot < 0 || !slots[slot].live) {     // only searched pixels need their database
         atomicExch(&pl.counters[1], 1);
+        *reinterpret_cast<volatile int32_t*>(pl.err_mapped) = 1;      // the host reads it after its next synchronisation
+        __threadfence_system();
         pl.status[p] = CLEDB_PIX_NULL;
         return;
     }
@@ -1131,8 +1134,11 @@ __global__ void __launch_bounds__(256) k_scatter_fine(Plan pl, const DbSlot* __r
     pl.rank[p] = r;
 }
 
+#ifndef CLEDB_PRUNED_WPC
+#define CLEDB_PRUNED_WPC 16
+#endif
 template <int ENC> struct PCfg {        // shared memory of one warp of the pruned search: one tile in flight, <= 32 pixels
-    static constexpr int kWpc = 16;
+    static constexpr int kWpc = CLEDB_PRUNED_WPC;
     static constexpr int kTB = tile_bytes<ENC>();
     static constexpr int kRecBytes = (32 + 1) * (int)sizeof(Rec<CLEDB_PREC_FP32>);
     static constexpr int kListBytes = kListCap * (int)sizeof(Cand<CLEDB_PREC_FP32>);
@@ -1626,6 +1632,17 @@ __global__ void k_export_counts(const int32_t* __restrict__ cnt, int nkeys, cons
     __threadfence_system();
 }
 
+// A searched pixel that names a database which is not resident sets a word in mapped host memory (k_classify).  The host
+// looks at it whenever it has synchronised with the device anyway - never in the middle of an enqueue.
+int check_async_error(cledb_ctx* ctx) {
+    if (ctx->h_err && *reinterpret_cast<volatile int32_t*>(ctx->h_err) != 0) {
+        *reinterpret_cast<volatile int32_t*>(ctx->h_err) = 0;
+        ctx->err = "cledb_match: a pixel refers to a database id that is not resident (cledb_db_put it first)";
+        return CLEDB_ERR_NODB;
+    }
+    return CLEDB_OK;
+}
+
 template <int PREC>
 static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax, const float* sobs, const float* snr,
                      const int32_t* db_id, int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out,
@@ -1634,36 +1651,37 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     const int nb = (int)((npix + 255) / 256);
     k_classify<PREC><<<nb, 256, 0, st>>>(pl, sobs, snr, db_id, ctx->d_slots, ctx->d_slot_of_id, ctx->id_cap);
     ctx->launches += 1;
-    // ---- the bucket sizes come back to the host (a few hundred bytes, one stream synchronisation) and fix the work shape
-    // The counts travel through mapped pinned memory written by a tiny kernel, not through a copy-engine transfer: a
-    // device-to-host copy would queue behind the result maps of the previous chunk of a big map (cledb_invert) and stall
-    // this search until they have arrived.
-    if ((int)ctx->h_cnt_cap < pl.nkeys + 4) {
-        if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
-        ctx->h_cnt = nullptr;
-        CLEDB_CUDA(ctx, cudaHostAlloc(&ctx->h_cnt, sizeof(int32_t) * (pl.nkeys + 4), cudaHostAllocMapped));
-        CLEDB_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_cnt_mapped, ctx->h_cnt, 0));
-        ctx->h_cnt_cap = pl.nkeys + 4;
-    }
-    k_export_counts<<<1, 256, 0, st>>>(pl.cnt, pl.nkeys, pl.counters, ctx->d_cnt_mapped);
-    ctx->launches += 1;
-    CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
-    if (ctx->h_cnt[pl.nkeys + 1] != 0) {                   // k_classify met a searched pixel whose database id was never put
-        ctx->err = "cledb_match: a pixel refers to a database id that is not resident (cledb_db_put it first)";
-        return CLEDB_ERR_NODB;
-    }
     const bool pruned = PREC == CLEDB_PREC_FP32 && pl.seed != nullptr;
-    if (pruned) {                                          // one lane per pixel for the bounds, whole sign classes per item
-        // 4, 8 or 32 pixels per item (measured on 128^2 .. 1024^2 maps): small maps need many small items to keep every warp busy to the end, big maps
-        // amortise the per-item work (staging, bounds) over more pixels
+    int64_t tiles_of_pixels = 0;
+    if (pruned) {
+        // The pruned search needs nothing from the host in mid-call: its work shape follows from the pixel count alone - 4, 8
+        // or 32 pixels per item (measured on 128^2 .. 1024^2 maps: small maps need many small items to keep every warp busy
+        // to the end, big maps amortise the per-item work over more pixels) - and the number of items is bounded by
+        // npix/P + one partly filled item per bucket.  The call is a pure enqueue: no synchronisation, capturable in a graph.
         pl.P = npix >= 512 * wslots ? 32 : (npix >= 48 * wslots ? 8 : 4);
         pl.P = std::min(pl.P, pmax);
         if (ctx->pixels_per_item > 0) pl.P = std::min(std::min(32, pmax), ctx->pixels_per_item);
         pl.split = 1;
-    } else
-    choose_shape(ctx, ctx->h_cnt, std::min<int>(pl.nkeys, (int)ctx->dbs.size() * kParts), pl.mode, pl.k, wslots, pmax, &pl.P, &pl.split);
-    int64_t tiles_of_pixels = 0;
-    for (int key = 0; key < pl.nkeys; ++key) tiles_of_pixels += (ctx->h_cnt[key] + pl.P - 1) / pl.P;
+        tiles_of_pixels = npix / pl.P + pl.nkeys;
+    } else {
+        // ---- brute force: the bucket sizes come back to the host (a few hundred bytes, one stream synchronisation) and fix
+        // the work shape.  The counts travel through mapped pinned memory written by a tiny kernel, not through a copy-engine
+        // transfer: a device-to-host copy would queue behind the result maps of the previous chunk of a big map.
+        if ((int)ctx->h_cnt_cap < pl.nkeys + 4) {
+            if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
+            ctx->h_cnt = nullptr;
+            CLEDB_CUDA(ctx, cudaHostAlloc(&ctx->h_cnt, sizeof(int32_t) * (pl.nkeys + 4), cudaHostAllocMapped));
+            CLEDB_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_cnt_mapped, ctx->h_cnt, 0));
+            ctx->h_cnt_cap = pl.nkeys + 4;
+        }
+        k_export_counts<<<1, 256, 0, st>>>(pl.cnt, pl.nkeys, pl.counters, ctx->d_cnt_mapped);
+        ctx->launches += 1;
+        CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
+        int rc0 = check_async_error(ctx);
+        if (rc0) return rc0;
+        choose_shape(ctx, ctx->h_cnt, std::min<int>(pl.nkeys, (int)ctx->dbs.size() * kParts), pl.mode, pl.k, wslots, pmax, &pl.P, &pl.split);
+        for (int key = 0; key < pl.nkeys; ++key) tiles_of_pixels += (ctx->h_cnt[key] + pl.P - 1) / pl.P;
+    }
     ctx->last_P = pl.P;
     ctx->last_split = pl.split;
     const size_t cand_sz = sizeof(Cand<PREC>);
@@ -1736,9 +1754,15 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     int rc = sync_tables(ctx, st);
     if (rc) return rc;
     if (ctx->occ == 0 && (rc = match_occupancy(ctx))) return rc;
+    if (!ctx->h_err) {
+        CLEDB_CUDA(ctx, cudaHostAlloc(&ctx->h_err, 64, cudaHostAllocMapped));
+        std::memset(ctx->h_err, 0, 64);
+        CLEDB_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_err_mapped, ctx->h_err, 0));
+    }
 
     Plan pl;
     std::memset(&pl, 0, sizeof(pl));
+    pl.err_mapped = ctx->d_err_mapped;
     pl.npix = npix;
     pl.mode = mode;
     pl.k = nsearch;

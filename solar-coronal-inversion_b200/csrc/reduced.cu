@@ -313,7 +313,7 @@ static int reduced_host(cledb_ctx* ctx, int mode, int precision, int64_t npix, c
                         double* chi64_out, int32_t* kpos_out, float* rows_out, uint8_t* status_out, int32_t* nan_out,
                         const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin, const void* dopp,
                         int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid, double maxchisq, int bcalc, int strict_topk,
-                        float* invout, float* sfound, uint8_t* issue_out = nullptr) {
+                        float* invout, float* sfound, int32_t* issue_out = nullptr) {
     if (!ctx) return CLEDB_ERR_ARG;
     if (npix < 0 || !sobs || !snr || !db_id || !red) { ctx->err = "reduced search: null argument"; return CLEDB_ERR_ARG; }
     if (nsearch < 1 || nsearch > CLEDB_MAX_NSEARCH) { ctx->err = "reduced search: nsearch must be in 1..32"; return CLEDB_ERR_ARG; }
@@ -333,7 +333,7 @@ static int reduced_host(cledb_ctx* ctx, int mode, int precision, int64_t npix, c
                  o_y = take(grid ? n * 4 : 0), o_d = take(grid ? n * 4 : 0), o_rc = take(grid ? n * 4 : 0), o_rs = take(grid ? n * 4 : 0),
                  o_dopp = take(n * dsz), o_tab = take(grid ? (size_t)(2 * grid->nbphi + 2 * grid->nbtheta) * 4 : 0),
                  o_inv = take(grid ? n * k * 44 : 0), o_sf = take(grid ? n * k * 32 : 0),
-                 o_iss = take(grid && issue_out ? n * 2 : 0);
+                 o_iss = take(grid && issue_out ? n * 4 : 0);
     int rc = ensure_workspace(ctx, ctx->io, off);
     if (rc) return rc;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx->io.ptr);
@@ -381,9 +381,9 @@ static int reduced_host(cledb_ctx* ctx, int mode, int precision, int64_t npix, c
                           reinterpret_cast<float*>(w + o_d), reinterpret_cast<float*>(w + o_rc), reinterpret_cast<float*>(w + o_rs), d_dopp,
                           dopp_is_f64, 1, g, maxchisq, bcalc, strict_topk, d_idx, d_chi, d_c64, d_kp, d_rows, w + o_st, d_nan,
                           reinterpret_cast<float*>(w + o_inv), reinterpret_cast<float*>(w + o_sf), st, reinterpret_cast<float*>(w + o_snr),
-                          issue_out ? w + o_iss : nullptr);
+                          issue_out ? reinterpret_cast<int32_t*>(w + o_iss) : nullptr);
         if (rc) return rc;
-        if (issue_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(issue_out, w + o_iss, n * 2, cudaMemcpyDeviceToHost, st));
+        if (issue_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(issue_out, w + o_iss, n * 4, cudaMemcpyDeviceToHost, st));
         CLEDB_CUDA(ctx, cudaMemcpyAsync(invout, w + o_inv, n * k * 44, cudaMemcpyDeviceToHost, st));
         CLEDB_CUDA(ctx, cudaMemcpyAsync(sfound, w + o_sf, n * k * 32, cudaMemcpyDeviceToHost, st));
     }
@@ -410,7 +410,7 @@ extern "C" int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int
                                     const int32_t* db_id, int nsearch, const cledb_reduced* red, const float* yobs, const float* dobs,
                                     const float* rot_cos, const float* rot_sin, const void* dopp, int dopp_is_f64, int64_t dopp_stride,
                                     const cledb_dbgrid* grid, double maxchisq, int bcalc, int strict_topk, float* invout, float* sfound,
-                                    uint8_t* status_out, uint8_t* issue_out) {
+                                    uint8_t* status_out, int32_t* issue_out) {
     if (!ctx) return CLEDB_ERR_ARG;
     if (!yobs || !dobs || !rot_cos || !rot_sin || !grid || !invout || !sfound) { ctx->err = "cledb_invert_reduced: null argument"; return CLEDB_ERR_ARG; }
     if (grid->dbtype != 1) { ctx->err = "cledb_invert_reduced: only PyCELP-type databases (dbtype 1) are built on the device"; return CLEDB_ERR_ARG; }

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
                                                const int32_t* __restrict__ kpos, const float* __restrict__ rows,
                                                const uint8_t* __restrict__ status, const int32_t* __restrict__ nan_slots,
                                                float* __restrict__ invout, float* __restrict__ sfound,
-                                               const float* __restrict__ snr, uint8_t* __restrict__ issue_out) {
+                                               const float* __restrict__ snr, int32_t* __restrict__ issue_out) {
     // one thread per (pixel, output slot); the 44- and 32-byte records of a block are staged in shared memory and stored
     // with coalesced 16-byte writes
     __shared__ __align__(16) float s_inv[128 * 11];
@@ -184,16 +184,17 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
         f[7] = __fmul_rn(r[7], nf);
     }
     } while (0);
-    // ---- issue flags of cledb_invproc (CLEDB_PROC.py:323-355), two bytes per pixel:
-    //   [p][0] (written by the thread of the LAST solution: `flg = 0` sits inside the reference's loop over solutions, :324,
-    //          so only slot nsearch-1 decides code 512)   bit 0 = Van-Vleck proximity 53 deg <= vartheta_B <= 56 deg,
-    //          bit 1 = within 1e-3 deg of either limit: the reference evaluates the chain in float32 with NumPy's own
+    // ---- issue codes of cledb_invproc (CLEDB_PROC.py:323-355): one int32 per pixel (zeroed before the launch), OR-ed together by
+    //   the thread of the LAST solution (`flg = 0` sits inside the reference's loop over solutions, :324, so only slot
+    //          nsearch-1 decides code 512):  512 = Van-Vleck proximity 53 deg <= vartheta_B <= 56 deg, and bit 0 = the angle
+    //          lies within 1e-3 deg of either limit: the reference evaluates the chain in float32 with NumPy's own
     //          sin/cos/arctan2, whose last bits differ between CPUs; here it runs in float64, which decides every pixel that
     //          is not that close to a limit; the binding re-evaluates the marked ones (about 1 in 50 000) with NumPy
-    //   [p][1] (written by the thread of slot 0)   bit 0 = chi^2 of the best solution > 10 (:351), bit 1 = snr[p,0] < 1 (:353)
+    //   the thread of slot 0:  1024 = chi^2 of the best solution > 10 (:351), 2048 = snr[p,0] < 1 (:353)
     if (issue_out && t < npix * k) {
         const int64_t p = t / k;
         const int s = (int)(t - p * k);
+        int code = 0;
         if (s == k - 1) {
             const double alpha = -atan2((double)o[4], (double)o[3]);
             const double sb = 1.0, cb = 6.123233995736766e-17;                  // sin, cos of the float64 pi/2
@@ -202,11 +203,11 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
             const double yyb = cb * yb - sb * zb, yzb = sb * yb + cb * zb;
             const double xxb = cos(alpha) * xb + sin(alpha) * yzb, zzb = -sin(alpha) * xb + cos(alpha) * yzb;
             const double deg = atan2(sqrt(xxb * xxb + yyb * yyb), zzb) * 180.0 / 3.141592653589793;
-            uint8_t f = (deg >= 53.0 && deg <= 56.0) ? 1 : 0;
-            if (fabs(deg - 53.0) < 1e-3 || fabs(deg - 56.0) < 1e-3) f |= 2;
-            issue_out[p * 2] = f;
+            if (deg >= 53.0 && deg <= 56.0) code |= 512;
+            if (fabs(deg - 53.0) < 1e-3 || fabs(deg - 56.0) < 1e-3) code |= 1;
         }
-        if (s == 0) issue_out[p * 2 + 1] = (uint8_t)((o[1] > 10.0f ? 1 : 0) | ((snr && snr[p * 8] < 1.0f) ? 2 : 0));
+        if (s == 0) code |= (o[1] > 10.0f ? 1024 : 0) | ((snr && snr[p * 8] < 1.0f) ? 2048 : 0);
+        if (code) atomicOr(issue_out + p, code);
     }
 #pragma unroll
     for (int c = 0; c < 11; ++c) s_inv[threadIdx.x * 11 + c] = o[c];
@@ -227,8 +228,9 @@ int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsea
                  const float* dobs, const float* rot_cos, const float* rot_sin, const void* dopp, int dopp_is_f64,
                  int64_t dopp_stride, const cledb_dbgrid& g, double maxchisq, int bcalc, int strict_topk, const int32_t* idx,
                  const float* chi, const double* chi64, const int32_t* kpos, const float* rows, const uint8_t* status,
-                 const int32_t* nan_slots, float* invout, float* sfound, cudaStream_t st, const float* snr, uint8_t* issue_out) {
+                 const int32_t* nan_slots, float* invout, float* sfound, cudaStream_t st, const float* snr, int32_t* issue_out) {
     (void)precision;
+    if (issue_out) CLEDB_CUDA(ctx, cudaMemsetAsync(issue_out, 0, (size_t)npix * 4, st));
     const int nb = (int)((npix * nsearch + 127) / 128);
     if (dopp_is_f64)
         k_build<true><<<nb, 128, 0, st>>>(mode, npix, nsearch, sobs, yobs, dobs, rot_cos, rot_sin, dopp, dopp_stride, g, maxchisq,
@@ -291,7 +293,7 @@ extern "C" int cledb_invert_dev(cledb_ctx* ctx, int mode, int precision, int64_t
                                 const int32_t* db_id, int nsearch, const float* yobs, const float* dobs, const float* rot_cos,
                                 const float* rot_sin, const void* dopp, int dopp_is_f64, int64_t dopp_stride,
                                 const cledb_dbgrid* grid, double maxchisq, int bcalc, int strict_topk, float* invout,
-                                float* sfound, uint8_t* status_out, uint8_t* issue_out, void* stream) {
+                                float* sfound, uint8_t* status_out, int32_t* issue_out, void* stream) {
     if (!ctx) return CLEDB_ERR_ARG;
     int rc = check_invert_args(ctx, mode, npix, sobs, snr, db_id, nsearch, yobs, dobs, rot_cos, rot_sin, dopp, grid, bcalc, invout, sfound);
     if (rc) return rc;
@@ -315,7 +317,7 @@ extern "C" int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npi
                             const int32_t* db_id, int nsearch, const float* yobs, const float* dobs, const float* rot_cos,
                             const float* rot_sin, const void* dopp, int dopp_is_f64, int64_t dopp_stride, const cledb_dbgrid* grid,
                             double maxchisq, int bcalc, int strict_topk, float* invout, float* sfound, uint8_t* status_out,
-                            uint8_t* issue_out) {
+                            int32_t* issue_out) {
     if (!ctx) return CLEDB_ERR_ARG;
     int rc = check_invert_args(ctx, mode, npix, sobs, snr, db_id, nsearch, yobs, dobs, rot_cos, rot_sin, dopp, grid, bcalc, invout, sfound);
     if (rc) return rc;
@@ -329,7 +331,7 @@ extern "C" int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npi
     const size_t o_sobs = take(n * 32), o_snr = take(n * 32), o_id = take(n * 4), o_y = take(n * 4), o_d = take(n * 4),
                  o_rc = take(n * 4), o_rs = take(n * 4), o_dopp = take(n * dsz),
                  o_tab = take((size_t)(2 * grid->nbphi + 2 * grid->nbtheta) * 4), o_inv = take(n * k * 44), o_sf = take(n * k * 32),
-                 o_st = take(n), o_iss = take(n * 2);
+                 o_st = take(n), o_iss = take(n * 4);
     if ((rc = ensure_workspace(ctx, ctx->io, off))) return rc;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx->io.ptr);
     cudaStream_t st = ctx->stream;
@@ -373,7 +375,7 @@ extern "C" int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npi
                               reinterpret_cast<float*>(w + o_d) + o, reinterpret_cast<float*>(w + o_rc) + o,
                               reinterpret_cast<float*>(w + o_rs) + o, d_dopp ? reinterpret_cast<const unsigned char*>(d_dopp) + o * dsz : nullptr,
                               dopp_is_f64, 1, &g, maxchisq, bcalc, strict_topk, reinterpret_cast<float*>(w + o_inv) + o * k * 11,
-                              reinterpret_cast<float*>(w + o_sf) + o * k * 8, w + o_st + o, issue_out ? w + o_iss + o * 2 : nullptr, st);
+                              reinterpret_cast<float*>(w + o_sf) + o * k * 8, w + o_st + o, issue_out ? reinterpret_cast<int32_t*>(w + o_iss) + o : nullptr, st);
         if (rc) return rc;
         cudaStream_t cs = st;
         if (chunk < npix) {                                    // hand the chunk's results to the copy stream
@@ -387,9 +389,9 @@ extern "C" int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npi
         CLEDB_CUDA(ctx, cudaMemcpyAsync(invout + o * k * 11, w + o_inv + o * k * 44, (size_t)nc * k * 44, cudaMemcpyDeviceToHost, cs));
         CLEDB_CUDA(ctx, cudaMemcpyAsync(sfound + o * k * 8, w + o_sf + o * k * 32, (size_t)nc * k * 32, cudaMemcpyDeviceToHost, cs));
         if (status_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(status_out + o, w + o_st + o, (size_t)nc, cudaMemcpyDeviceToHost, cs));
-        if (issue_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(issue_out + o * 2, w + o_iss + o * 2, (size_t)nc * 2, cudaMemcpyDeviceToHost, cs));
+        if (issue_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(issue_out + o, w + o_iss + o * 4, (size_t)nc * 4, cudaMemcpyDeviceToHost, cs));
     }
     if (chunk < npix) CLEDB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CLEDB_CUDA(ctx, cudaStreamSynchronize(st));
-    return CLEDB_OK;
+    return check_async_error(ctx);
 }

@@ -959,13 +959,13 @@ def test_sharded_call_on_one_rank_equals_the_plain_call():
     y, d, a = obs['yobs'].reshape(-1), obs['dobs'].reshape(-1), obs['aobs'].reshape(-1)
     order, bounds = native.partition(ids, [float(x.size // 8) for x in dbs], 1)
     assert bounds.tolist() == [0, n] and (np.diff(ids[order]) >= 0).all()
-    for mode, bcalc in ((native.MODE_IQUV, 0), (native.MODE_IQUD, 3)):
+    for mode, bcalc, k in ((native.MODE_IQUV, 0, 8), (native.MODE_IQUD, 3, 8), (native.MODE_IQUV, 2, 3)):     # k = 3: rows that are no 16-byte multiples
         dopp = obs['sobs_dopp'].reshape(n, -1)[:, 0] if mode else None
-        inv, sf, st = c.invert(mode, sobs, snr, ids, 8, y, d, a, dopp, hdr, 1000, bcalc)
+        inv, sf, st = c.invert(mode, sobs, snr, ids, k, y, d, a, dopp, hdr, 1000, bcalc)
         iss = c.last_issue.copy()
         inv, sf, st = inv.copy(), sf.copy(), st.copy()
         m = order                                              # this rank's pixels, in partition order
-        inv2, sf2, st2 = c.invert_sharded(mode, sobs[m], snr[m], ids[m], 8, y[m], d[m], a[m], None if dopp is None else dopp[m], hdr,
+        inv2, sf2, st2 = c.invert_sharded(mode, sobs[m], snr[m], ids[m], k, y[m], d[m], a[m], None if dopp is None else dopp[m], hdr,
                                           1000, bcalc, n, order, bounds)
         assert same(inv, inv2) and same(sf, sf2) and same(st, st2) and same(iss, c.last_issue)
     with pytest.raises(native.CledbError, match='partition'):

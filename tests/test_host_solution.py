@@ -106,11 +106,12 @@ def test_issue_codes_from_device_flags():
     yyb, yzb = cb * yb - zb, yb + cb * zb
     xxb, zzb = np.cos(alpha) * xb + np.sin(alpha) * yzb, -np.sin(alpha) * xb + np.cos(alpha) * yzb
     deg = np.arctan2(np.sqrt(xxb ** 2 + yyb ** 2), zzb) * 180.0 / np.pi
-    flags = np.zeros((npix, 2), np.uint8)
-    flags[:, 0] = ((deg >= 53) & (deg <= 56)) | (((np.abs(deg - 53) < 1e-3) | (np.abs(deg - 56) < 1e-3)) << 1)
-    flags[:, 1] = (inv[:, 0, 1] > 10) | ((snr[:, 0, 0] < 1) << 1)
-    flags[:5, 0] |= 2                                            # force the NumPy re-evaluation on a few pixels
-    codes = native.issue_codes(flags, inv)
+    flags = np.zeros(npix, np.int32)
+    flags |= (((deg >= 53) & (deg <= 56)).astype(np.int32) << 9) | ((np.abs(deg - 53) < 1e-3) | (np.abs(deg - 56) < 1e-3)).astype(np.int32)
+    flags |= ((inv[:, 0, 1] > 10).astype(np.int32) << 10) | ((snr[:, 0, 0] < 1).astype(np.int32) << 11)
+    flags[:5] |= 1                                               # force the NumPy re-evaluation on a few pixels
+    codes = native.issue_codes(flags.copy(), inv)
+    assert not (codes & 1).any()
     a = rng.choice([0, 32, 512, 1024 + 4, 2048 + 512], (npix, 1, 2)).astype(np.int32)
     b = a.copy()
     solution.apply_issue_codes(a, codes.reshape(npix, 1))
