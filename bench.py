@@ -320,10 +320,12 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
     d2h = npix * (k * (44 + 32) + 1 + 4)
     enc_name = 'int16' if encoding == 1 else 'float32'
     recs = {}
-    for pruned in (True, False):
-        ctx.set_pruning(pruned)
-        for i, d in enumerate(db):
-            ctx.db_put(i, d, encoding)
+    for variant in (1, 2, 0):                                # exact tile pruning; seeded brute force (same k-d layout); plain brute force
+        pruned = variant == 1
+        ctx.set_pruning(variant)
+        if variant != 2:
+            for i, d in enumerate(db):
+                ctx.db_put(i, d, encoding)
         if B.args.ppi or B.args.split:
             ctx.set_tuning(B.args.ppi, B.args.split)
         if B.args.dbg:
@@ -336,7 +338,7 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
         B.barrier()
         mark = B.sampler.mark()
         launches0 = ctx.launch_count()
-        nst = steps if pruned else max(3, min(steps, 10))
+        nst = steps if pruned else max(3, min(steps, 10 if variant == 2 else 5))
         step_ms, kern_ms = B.timed(step, nst)
         B.barrier()
         launches = ctx.launch_count() - launches0
@@ -367,18 +369,21 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
             evals = evaluated * B.world
         else:
             achieved = 20.0 * ncand / (kms * 1e-3) / 1e12
-            roof = dict(bound='fp32', kernel='k_match<%s,fp32>' % enc_name, achieved=achieved, peak=peak, unit='TFLOP/s',
+            roof = dict(bound='fp32', kernel='k_match<%s,fp32>%s' % (enc_name, ' seeded, k-d tile layout' if variant == 2 else ' plain layout'),
+                        achieved=achieved, peak=peak, unit='TFLOP/s',
                         frac=achieved / peak if peak else None, traffic=B.traffic_of('k_match_' + mode_name), kernel_ms=kms,
                         kernel_share_of_step=kms / float(np.mean(step_ms)), flop_per_candidate=20, candidates_per_launch=ncand,
                         peak_source=peak_src)
             evals = ncand_all
         rec = dict(value=B.world * npix / (ms * 1e-3), unit='pixels/s', ms_per_step=ms, steps=nst,
-                   workload=workload_name(mode_name, nx, ndb), search='exact tile pruning (library default)' if pruned else 'brute force (pruning off)',
+                   workload=workload_name(mode_name, nx, ndb), search={1: 'exact tile pruning (library default, cledb_set_pruning 1)',
+                                                                      2: 'brute force, every (pixel, entry) pair evaluated; k-d tile layout, every pixel started from its seed tile (cledb_set_pruning 2)',
+                                                                      0: 'brute force, every (pixel, entry) pair evaluated; plain stride-permuted layout (cledb_set_pruning 0)'}[variant],
                    evals_per_s=evals / (ms * 1e-3), evals_definition='(pixel, database entry) chi^2 evaluations actually executed per second',
                    nominal_scanned_evals_per_s=B.world * npix * float(NDB_ROWS) * max(1, ndb) / max(1, ndb) / (ms * 1e-3),
                    nominal_candidate_evals_per_s=ncand_all / (ms * 1e-3), pixels_searched=nsearched_all, gpu_launches=int(launches),
                    pruning=stats, roofline=roof, clocks=clocks)
-        if want_e2e:
+        if want_e2e and variant != 0:
             for _ in range(3):
                 e2e_step()
             B.barrier()
@@ -390,7 +395,7 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
                               ms_per_step=e2e_s * 1e3,
                               api='cledb_invert (C-ABI): pinned host buffers in, search + solutions + issue flags on the device, finished '
                                   'invout / sfound maps out')
-        recs['pruned' if pruned else 'bruteforce'] = rec
+        recs[{1: 'pruned', 2: 'bruteforce', 0: 'bruteforce_plain'}[variant]] = rec
         if pruned and want_stream and B.world == 1:
             # a stream of maps through TWO contexts on this GPU (two host threads, the same blocking call): the result copy of
             # one map overlaps the search of the next
@@ -417,9 +422,10 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
             rec['e2e']['stream_of_maps'] = dict(value=npix / es, ms_per_map=es * 1e3, identical_outputs=same,
                                                 how='two contexts on this GPU, one host thread each, the same blocking call')
             ctx2.close()
-        for i in range(len(db)):
-            ctx.db_drop(i)
-    ctx.set_pruning(True)
+        if variant != 1:
+            for i in range(len(db)):
+                ctx.db_drop(i)
+    ctx.set_pruning(1)
     ctx.set_tuning(0, 0)
     if want_python:
         # the reference-shaped Python call itself (CLEDB_PROC.cledb_invproc): same map, same encoding, its own context; the
@@ -693,10 +699,11 @@ def main():
     by[tag + '_pruned'] = top['pruned']
     if '2b' in extra:
         by[tag + '_bruteforce'] = top['bruteforce']
+        by[tag + '_bruteforce_plain'] = top['bruteforce_plain']
     cpu_main = None
     if B.rank == 0 and not args.no_cpu_baseline:
         cpu_main = cpu_baseline(args.mode, args.encoding, db, obs, args.cpu_seconds)
-        for r in (top['pruned'], top['bruteforce']):
+        for r in (top['pruned'], top['bruteforce'], top['bruteforce_plain']):
             r['cpu_baseline'] = cpu_main
     del db, obs
     if '3' in extra and args.mode == 'iquv':
@@ -705,9 +712,10 @@ def main():
         db3, obs3 = other.pop('_inputs')
         by['config3_iqud_%d_pruned' % args.nx] = other['pruned']
         by['config3_iqud_%d_bruteforce' % args.nx] = other['bruteforce']
+        by['config3_iqud_%d_bruteforce_plain' % args.nx] = other['bruteforce_plain']
         if B.rank == 0 and not args.no_cpu_baseline:
             c3 = cpu_baseline('iqud', args.encoding, db3, obs3, min(args.cpu_seconds, 10.0))
-            other['pruned']['cpu_baseline'] = other['bruteforce']['cpu_baseline'] = c3
+            other['pruned']['cpu_baseline'] = other['bruteforce']['cpu_baseline'] = other['bruteforce_plain']['cpu_baseline'] = c3
         del db3, obs3
     if '4' in extra:
         by.update(bench_elementwise(B, 2048, max(10, args.steps), cpu=not args.no_cpu_baseline))
@@ -749,7 +757,8 @@ def main():
     if 'bruteforce' in top and not args.no_prune:
         line['roofline_bruteforce'] = dict(top['bruteforce']['roofline'], value=top['bruteforce']['value'],
                                            ms_per_step=top['bruteforce']['ms_per_step'],
-                                           note='the FP32-bound kernel of the path (pruning off), same maps, same run: by_config.%s_bruteforce' % tag)
+                                           note='the FP32-bound kernel of the path - every (pixel, entry) pair evaluated -, same maps, same run: '
+                                                'by_config.%s_bruteforce (k-d layout, seeded) and %s_bruteforce_plain' % (tag, tag))
     print(json.dumps(line))
     if world > 1:
         B.dist.destroy_process_group()

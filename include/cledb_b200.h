@@ -147,8 +147,14 @@ int cledb_match_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  * many chunks each candidate list is cut into (1..8); 0 = choose from the pixel count (default).  Results do not depend on
  * them. */
 int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split);
-/* exact tile pruning on (1) / off (0) for databases put from now on; every resident database must have been put with
- * the same setting when a search runs */
+/* search variant (results are bit-identical in all three):
+ *   0  plain layout, brute force: every (pixel, entry) pair evaluated, entries in a stride-permuted order
+ *   1  k-d tile layout with exact tile pruning (default)
+ *   2  k-d tile layout, seeded brute force: every (pixel, entry) pair is evaluated - the FP32-roofline kernel - but each
+ *      pixel starts from the exact top-nsearch of its seed tile, so its threshold is near final from the first tile on and
+ *      the exact re-evaluation of flagged (pixel, tile) pairs drops from ~54 to ~10 per pixel
+ * The layout is fixed when a database is put (0: plain, 1 or 2: k-d tiles); every resident database must have the same
+ * layout when a search runs; 1 and 2 can be switched between searches without putting the databases again. */
 int cledb_set_pruning(cledb_ctx* ctx, int on);
 /* after a pruned search: evaluated[0] = (pixel, tile) pairs evaluated, evaluated[1] = pairs skipped by the bound; counts of the
  * last search launched (cledb_invert sends maps of 256 Ki pixels and more through in 128 Ki-pixel chunks: the last chunk) */

@@ -21,8 +21,9 @@ Module-level options (not part of the reference surface; the defaults reproduce 
     OPTIONS['strict_topk'] False = reproduce the cledb_partsort index quirk, True = true top-nsearch
     OPTIONS['solution']    'device' = solutions built on the GPU right after the search (cledb_invert; PyCELP-type databases),
                            'host' = NumPy on the raw search result (cledb_b200.solution); both give the same bits
-    OPTIONS['pruning']     True (default) = exact tile pruning in the search (k-d tile layout, bit-identical results, several
-                           times faster), False = brute-force evaluation of every (pixel, entry) pair
+    OPTIONS['pruning']     True / 1 (default) = exact tile pruning in the search (k-d tile layout, bit-identical results, several
+                           times faster), False / 0 = brute-force evaluation of every (pixel, entry) pair on the plain layout,
+                           2 = brute force on the k-d layout with every pixel started from its seed tile
     OPTIONS['device']      CUDA ordinal (default: $CLEDB_B200_DEVICE, else $LOCAL_RANK, else 0)
     OPTIONS['sharded']     True = cledb_invproc is a collective over the ranks of cledb_b200.dist.init_comm(): pixels sharded,
                            one all-gather of the finished maps over NVLink; OPTIONS['shard_root'] = rank that receives the maps
@@ -71,11 +72,11 @@ def _upload(database, used):
     if res is None:
         res = _resident[OPTIONS['device']] = Resident()
     res.verify, res.budget_bytes = OPTIONS['verify_resident'], OPTIONS['hbm_budget_bytes']
-    want = bool(OPTIONS['pruning'])
-    if res.entries and (res.encoding != OPTIONS['dbencoding'] or res.pruning != want):
+    want = int(OPTIONS['pruning'])          # 0 plain layout / brute force, 1 exact tile pruning, 2 seeded brute force (k-d layout)
+    if res.entries and (res.encoding != OPTIONS['dbencoding'] or res.pruning != (want != 0)):
         res.clear(ctx)                      # one encoding and one tile layout at a time live on the device
     ctx.set_pruning(want)
-    res.pruning, res.encoding = want, OPTIONS['dbencoding']
+    res.pruning, res.encoding = want != 0, OPTIONS['dbencoding']
     return ctx, res.ensure_all(ctx, {int(k): database[int(k)] for k in used}, OPTIONS['dbencoding'])
 
 

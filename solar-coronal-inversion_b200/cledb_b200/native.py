@@ -387,8 +387,9 @@ class Context:
         self._check(self.lib.cledb_set_tuning(self.h, int(pixels_per_item), int(split)))
 
     def set_pruning(self, on):
-        """Exact tile pruning for databases put from now on (see the header); results do not change."""
-        self._check(self.lib.cledb_set_pruning(self.h, 1 if on else 0))
+        """Search variant: 0 / False = plain layout, brute force; 1 / True = exact tile pruning (default); 2 = k-d layout,
+        seeded brute force (see the header); results do not change."""
+        self._check(self.lib.cledb_set_pruning(self.h, int(on)))
 
     def pruning_stats(self):
         v = np.zeros(2, dtype=np.int64)

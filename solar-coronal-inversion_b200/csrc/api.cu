@@ -1,5 +1,6 @@
 // C-ABI entry points of libcledb_b200.so (include/cledb_b200.h): context management and the host-buffer
 // wrappers around the device paths.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -26,7 +27,7 @@ extern "C" int cledb_create(int device, cledb_ctx** out) {
     if (device < 0 || device >= ndev) { g_create_error = "cledb_create: device ordinal out of range"; return CLEDB_ERR_ARG; }
     cledb_ctx* ctx = new cledb_ctx();
     ctx->device = device;
-    if (const char* e = std::getenv("CLEDB_B200_PRUNING")) ctx->prune = std::atoi(e) != 0 ? 1 : 0;   // default: on
+    if (const char* e = std::getenv("CLEDB_B200_PRUNING")) ctx->prune = std::max(0, std::min(2, std::atoi(e)));   // default: 1
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = std::string("cledb_create: ") + cudaGetErrorString(e);
@@ -161,7 +162,8 @@ extern "C" int cledb_set_tuning(cledb_ctx* ctx, int pixels_per_item, int split) 
 
 extern "C" int cledb_set_pruning(cledb_ctx* ctx, int on) {
     if (!ctx) return CLEDB_ERR_ARG;
-    ctx->prune = on ? 1 : 0;
+    if (on < 0 || on > 2) { ctx->err = "cledb_set_pruning: 0 (plain layout, brute force), 1 (exact tile pruning) or 2 (k-d layout, seeded brute force)"; return CLEDB_ERR_ARG; }
+    ctx->prune = on;
     return CLEDB_OK;
 }
 

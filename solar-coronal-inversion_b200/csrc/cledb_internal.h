@@ -108,7 +108,8 @@ struct cledb_ctx {
     int pixels_per_item = 0;                      // 0 = choose from the pixel count
     int split = 0;
     int dbg = 0;
-    int prune = 1;                                 // layout of databases put from now on: 1 = k-d tiles with bounds (exact pruning)
+    int prune = 1;                                 // 0: plain layout, brute force; 1: k-d tiles with bounds, exact pruning (default);
+                                                   // 2: k-d tiles, seeded brute force (every pair evaluated).  1 and 2 share the layout
     unsigned long long* d_prune_stats = nullptr;   // [2] evaluated / skipped (pixel, tile) pairs of the last pruned search
     int occ = 0, regs = 0, smem = 0;               // search kernel occupancy facts
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;   // event pairs around the search kernel

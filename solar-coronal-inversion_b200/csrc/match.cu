@@ -526,8 +526,10 @@ template <int ENC, int PREC> struct KCfg {
     static constexpr int kRecBytes = (kMaxP + 1) * (int)sizeof(Rec<PREC>);   // one spare record: prefetch overrun
     static constexpr int kListBytes = kListCap * (int)sizeof(Cand<PREC>);
     static constexpr int kC0Bytes = ((kMaxP + 3) / 4) * 16;                    // c0 of the item's pixels (fp32 kernel)
+    // seeded brute force (k-d layout, fp32): seed tile of every pixel of the item + one selection's candidates
+    static constexpr int kSeedBytes = PREC == CLEDB_PREC_FP32 ? ((kMaxP * 4 + 15) / 16 * 16 + 32 * 8) : 0;
     // every warp slice starts 128-byte aligned (bulk-copy destination, 16-byte vector loads)
-    static constexpr int kWarpBytes = (kStages * kStageBytes + kRecBytes + kListBytes + kStages * 8 + 16 + kC0Bytes + 127) / 128 * 128;
+    static constexpr int kWarpBytes = (kStages * kStageBytes + kRecBytes + kListBytes + kStages * 8 + 16 + kC0Bytes + kSeedBytes + 127) / 128 * 128;
 };
 
 // evaluate the lane's 8 entries against the pixel record in shared memory; returns the 8 values
@@ -789,7 +791,7 @@ __device__ __forceinline__ void bootstrap_pixel(Rec<PREC>* rec, float c0f, Cand<
     __syncwarp();
 }
 
-template <int ENC, int PREC>
+template <int ENC, int PREC, bool SEEDED = false>
 __global__ void __launch_bounds__(KCfg<ENC, PREC>::kWpc * 32, (PREC == CLEDB_PREC_FP32 && KCfg<ENC, PREC>::kTPS == 1) ? 2 : 1)
 k_match(Plan pl, const DbSlot* __restrict__ slots) {
     using C = KCfg<ENC, PREC>;
@@ -805,8 +807,15 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
     CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);   // [npx][k]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);   // [kStages]
     float* c0s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + (kStages * 8 + 15) / 16 * 16);   // [kMaxP]
+    int32_t* seeds = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(c0s) + C::kC0Bytes);                // [kMaxP] (seeded)
+    Cand<CLEDB_PREC_FP32>* seed_scratch = reinterpret_cast<Cand<CLEDB_PREC_FP32>*>(reinterpret_cast<unsigned char*>(seeds) + (kMaxP * 4 + 15) / 16 * 16);
     const int k = pl.k;
     uint32_t phase_bits = 0;
+    // Seeded brute force: the database is in the k-d tile layout (pl.seed != NULL) and every pixel starts from the exact
+    // top-k of ITS OWN seed tile - the tile whose representative entry fits it best (k_seed) - so its threshold is close to
+    // final before the scan begins, and the scan over ALL tiles flags only the few tiles that really hold contenders
+    // (about 10 per pixel instead of the k ln(N/256) = 54 of a random-order scan).  Every (pixel, entry) pair is still evaluated.
+    constexpr bool seeded = SEEDED && PREC == CLEDB_PREC_FP32;      // a separate instantiation: the plain kernel carries none of it
 
     if (lane == 0) {
 #pragma unroll
@@ -827,7 +836,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
 
         // ---- stage the item: first steps (TPS tiles each) in flight, pixel records, empty lists
         const int nsteps = (im.ntiles + TPS - 1) / TPS;
-        if (lane == 0) {
+        if (lane == 0 && !seeded) {
 #pragma unroll
             for (int s = 0; s < kStages; ++s) {
                 if (s < nsteps) {
@@ -864,6 +873,73 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
         float d[kEPL][kNC];                       // tile A of the step
         float d2[TPS == 2 ? kEPL : 1][kNC];       // tile B of the step (fp32 kernel)
         bool exact_only = false;
+        if constexpr (PREC == CLEDB_PREC_FP32) {
+            if (seeded && im.ntiles > 0) {
+                // ---- seed pass: the distinct seed tiles of the item's pixels, one after the other; each pixel takes the exact
+                //      top-k of its own.  Seed tiles are counted relative to the item's first tile; a pixel without seed, or
+                //      whose seed lies outside this chunk of the class, starts from the chunk's first tile.
+                Cand<CLEDB_PREC_FP32>* scratch = seed_scratch;
+                const int part_tile0 = im.entry0 / kTile;
+                int part = 0;
+                for (int q = 0; q < kParts; ++q) if (db.part_tile0[q] == part_tile0 && db.part_cnt[q] > 0) part = q;
+                for (int j = lane; j < im.npx; j += 32) {
+                    int sd = pl.seed[(size_t)pl.order[im.pix0 + j] * kParts + part];
+                    sd = sd < 0 ? 0 : sd - (im.tile0 - part_tile0);
+                    seeds[j] = (sd < 0 || sd >= im.ntiles) ? 0 : sd;
+                }
+                __syncwarp();
+                for (int j0 = 0; j0 < im.npx; j0 += 32) {
+                    const int mine = j0 + lane < im.npx ? seeds[j0 + lane] : -1;
+                    uint32_t active = __ballot_sync(0xffffffffu, mine >= 0);
+                    while (active) {
+                        const int ts = __shfl_sync(0xffffffffu, mine, __ffs(active) - 1);
+                        uint32_t own = __ballot_sync(0xffffffffu, mine == ts);
+                        active &= ~own;
+                        if (lane == 0) {
+                            mbar_expect_tx(&bars[0], TB);
+                            tma_load_1d(stages, gt + (size_t)ts * TB, TB, &bars[0]);
+                        }
+                        mbar_wait(&bars[0], phase_bits & 1u);
+                        phase_bits ^= 1u;
+                        load_tile_regs<ENC>(stages, lane, d);
+                        __syncwarp();
+                        const int base = (im.tile0 + ts) * kTile;
+                        bool have_rows = false;
+                        int rows[kEPL];
+                        while (own) {
+                            const int j = j0 + __ffs(own) - 1;
+                            own &= own - 1;
+                            RecT* rj = recs + j;
+                            if (!seed_pixel<ENC>(rj, c0s[j], lists + j * k, d, scale, base, im.cnt_end, k, lane, scratch)) {
+                                if (!have_rows) {             // original rows of my 8 entries: the tie-break of the exact selection
+#pragma unroll
+                                    for (int e = 0; e < kEPL; ++e) {
+                                        const int pos = base + pos_in_tile<ENC>(lane, e);
+                                        rows[e] = pos < im.cnt_end ? db.perm[pos] : 0x7fffffff;
+                                    }
+                                    have_rows = true;
+                                }
+                                bootstrap_pixel<ENC, PREC>(rj, c0s[j], lists + j * k, d, scale, base, im.cnt_end, rows, k, lane);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                for (int j = lane; j < im.npx; j += 32) exact_only |= !(recs[j].tau < CUDART_INF_F);
+                exact_only = __any_sync(0xffffffffu, exact_only);
+                // the scan starts: first steps in flight
+                if (lane == 0) {
+#pragma unroll
+                    for (int s = 0; s < kStages; ++s) {
+                        if (s < nsteps) {
+                            const uint32_t bytes = (uint32_t)min(TPS, im.ntiles - s * TPS) * TB;
+                            mbar_expect_tx(&bars[s], bytes);
+                            tma_load_1d(stages + s * SB, gt + (size_t)s * SB, bytes, &bars[s]);
+                        }
+                    }
+                }
+            }
+        }
         for (int step = 0; step < nsteps; ++step) {
             const int s = step % kStages;
             const int t = step * TPS, nt = min(TPS, im.ntiles - t);
@@ -886,7 +962,7 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                 tma_load_1d(stages + s * SB, gt + (size_t)(step + kStages) * SB, bytes, &bars[s]);
             }
             const int base = (im.tile0 + t) * kTile;
-            if (step == 0) {
+            if (step == 0 && !seeded) {
                 int rows[kEPL];                  // original rows of my 8 entries of the first tile (tie-break only)
 #pragma unroll
                 for (int e = 0; e < kEPL; ++e) {
@@ -944,6 +1020,11 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                         const int b = 31 - __clz(any);
                         any &= ~(1u << b);
                         const int j = j0 + nseg - 1 - b;
+                        if constexpr (seeded) {
+                            if (seeds[j] == t) continue;                       // its own seed tile: those entries are in the list already
+                            // a neighbour of the seed tile can hold dozens of entries under the threshold: best first
+                            merge_pixel<ENC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane, seed_scratch);
+                        } else
                         slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, d, scale, base, im.cnt_end, db.perm, k, lane);
                     }
                     if (TPS == 2) {
@@ -952,6 +1033,11 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                             const int b = 31 - __clz(any);
                             any &= ~(1u << b);
                             const int j = j0 + nseg - 1 - b;
+                            if constexpr (seeded) {
+                                if (seeds[j] == t + 1) continue;
+                                merge_pixel<ENC>(recs + j, c0s[j], lists + j * k, reinterpret_cast<float(&)[kEPL][kNC]>(d2), scale,
+                                                 base + kTile, im.cnt_end, db.perm, k, lane, seed_scratch);
+                            } else
                             slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, reinterpret_cast<float(&)[kEPL][kNC]>(d2), scale,
                                                   base + kTile, im.cnt_end, db.perm, k, lane);
                         }
@@ -959,9 +1045,10 @@ k_match(Plan pl, const DbSlot* __restrict__ slots) {
                 }
             } else {
                 for (int j = 0; j < im.npx; ++j) {
-                    slow_pixel<ENC, PREC>(recs + j, PREC == CLEDB_PREC_FP32 ? c0s[j] : 0.f, lists + j * k, d, scale, base,
-                                          im.cnt_end, db.perm, k, lane);
-                    if (TPS == 2 && nt == 2)
+                    if (!(seeded && seeds[j] == t))
+                        slow_pixel<ENC, PREC>(recs + j, PREC == CLEDB_PREC_FP32 ? c0s[j] : 0.f, lists + j * k, d, scale, base,
+                                              im.cnt_end, db.perm, k, lane);
+                    if (TPS == 2 && nt == 2 && !(seeded && seeds[j] == t + 1))
                         slow_pixel<ENC, PREC>(recs + j, c0s[j], lists + j * k, reinterpret_cast<float(&)[kEPL][kNC]>(d2), scale,
                                               base + kTile, im.cnt_end, db.perm, k, lane);
                 }
@@ -1562,6 +1649,8 @@ template <int ENC, int PREC> static size_t match_smem_bytes(int) {
 template <int ENC, int PREC> static int configure_match(cledb_ctx* ctx, int k, int* occ_out, size_t* smem_out) {
     const size_t smem = match_smem_bytes<ENC, PREC>(k);
     CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_match<ENC, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (PREC == CLEDB_PREC_FP32)
+        CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_match<ENC, PREC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CLEDB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_match<ENC, PREC>, KCfg<ENC, PREC>::kWpc * 32, smem));
     if (occ < 1) { ctx->err = "search kernel does not fit on an SM"; return CLEDB_ERR_CUDA; }
@@ -1651,7 +1740,10 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     const int nb = (int)((npix + 255) / 256);
     k_classify<PREC><<<nb, 256, 0, st>>>(pl, sobs, snr, db_id, ctx->d_slots, ctx->d_slot_of_id, ctx->id_cap);
     ctx->launches += 1;
-    const bool pruned = PREC == CLEDB_PREC_FP32 && pl.seed != nullptr;
+    // k-d tile layout resident (fp32 search only): exact tile pruning (cledb_set_pruning 1, the default) or the seeded brute
+    // force (cledb_set_pruning 2: the same layout and seed tiles, no bounds - every (pixel, entry) pair is evaluated)
+    const bool blocked = PREC == CLEDB_PREC_FP32 && pl.seed != nullptr;
+    const bool pruned = blocked && ctx->prune != 2;
     int64_t tiles_of_pixels = 0;
     if (pruned) {
         // The pruned search needs nothing from the host in mid-call: its work shape follows from the pixel count alone - 4, 8
@@ -1691,7 +1783,7 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     pl.plist = ctx->ws2.ptr;
 
     k_scan<<<1, 1024, 0, st>>>(pl, ctx->d_slots);
-    if (pruned) {
+    if (blocked) {
         k_scatter<<<nb, 256, 0, st>>>(pl);                 // bucket order first: k_seed then stages one database per block
         k_seed<<<(int)((npix * kSeedLanes + 255) / 256), 256, 0, st>>>(pl, ctx->d_slots);
         k_fscan<<<ctx->slots_cap, 256, 0, st>>>(pl);
@@ -1721,6 +1813,9 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     if (pruned) {
         if (enc == CLEDB_ENC_I16) k_match_pruned<CLEDB_ENC_I16><<<pgrid, PCfg<CLEDB_ENC_I16>::kWpc * 32, smem, st>>>(pl, ctx->d_slots, ctx->d_prune_stats);
         else k_match_pruned<CLEDB_ENC_F32><<<pgrid, PCfg<CLEDB_ENC_F32>::kWpc * 32, smem, st>>>(pl, ctx->d_slots, ctx->d_prune_stats);
+    } else if (blocked) {
+        if (enc == CLEDB_ENC_I16) k_match<CLEDB_ENC_I16, PREC, true><<<grid, KCfg<CLEDB_ENC_I16, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
+        else k_match<CLEDB_ENC_F32, PREC, true><<<grid, KCfg<CLEDB_ENC_F32, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
     } else if (enc == CLEDB_ENC_I16) k_match<CLEDB_ENC_I16, PREC><<<grid, KCfg<CLEDB_ENC_I16, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
     else k_match<CLEDB_ENC_F32, PREC><<<grid, KCfg<CLEDB_ENC_F32, PREC>::kWpc * 32, smem, st>>>(pl, ctx->d_slots);
     if (prof) {

@@ -23,12 +23,13 @@ from oracle.compare import check_raw_against_oracle, check_invout_against_refere
 
 pytestmark = pytest.mark.gpu
 
-@pytest.fixture(scope='module', params=['pruned', 'bruteforce'])
+@pytest.fixture(scope='module', params=['pruned', 'bruteforce', 'seeded'])
 def ctx(request):
-    """Every parity test runs twice: with exact tile pruning (the library default: k-d tile layout, k_match_pruned) and
-    with pruning off (plain layout, brute-force k_match)."""
+    """Every parity test runs three times: with exact tile pruning (the library default: k-d tile layout, k_match_pruned),
+    with pruning off (plain layout, brute-force k_match) and with the seeded brute force (k-d tile layout, every pair
+    evaluated by k_match, each pixel started from its seed tile)."""
     c = native.Context(0)
-    c.pruning_default = request.param == 'pruned'
+    c.pruning_default = {'pruned': 1, 'bruteforce': 0, 'seeded': 2}[request.param]
     c.set_pruning(c.pruning_default)
     yield c
     c.close()
@@ -629,17 +630,23 @@ def test_exact_tile_pruning_changes_nothing(ctx, golden_dir, encoding, mode):
     cases.append(([mid], obs['sobs_totrot'].reshape(-1, 8), obs['snr'].reshape(-1, 8), np.zeros(900, np.int32)))
     for dbl, sobs, snr, enc in cases:
         res = {}
-        for prune in (False, True):
+        for prune in (0, 1, 2):
             ctx.set_pruning(prune)
             for i, db in enumerate(dbl):
                 ctx.db_put(i, db, encoding)
             res[prune] = ctx.match(mode, sobs, snr, enc, 8)
-            stats = ctx.pruning_stats()
+            if prune == 1:
+                stats = ctx.pruning_stats()
+                ctx.set_pruning(2)                           # the same resident k-d layout, searched without bounds
+                again = ctx.match(mode, sobs, snr, enc, 8)
+                ctx.set_pruning(1)
             for i in range(len(dbl)):
                 ctx.db_drop(i)
         ctx.set_pruning(ctx.pruning_default)
         for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
-            assert np.array_equal(res[False][key], res[True][key], equal_nan=True), key
+            assert np.array_equal(res[0][key], res[1][key], equal_nan=True), key
+            assert np.array_equal(res[0][key], res[2][key], equal_nan=True), key
+            assert np.array_equal(res[0][key], again[key], equal_nan=True), key
         assert stats['evaluated'] > 0
     assert stats['skipped'] > 0
 
@@ -662,20 +669,21 @@ def test_pruning_full_size_properties(ctx, mode):
     snr_low = snr.copy()
     snr_low[2048:4096] *= 0.01                                      # flat chi^2 landscape
     res = {}
-    for prune in (False, True):
+    for prune in (0, 1, 2):
         ctx.set_pruning(prune)
         ctx.db_put(0, db0, native.ENC_I16)
         ctx.db_put(1, db1, native.ENC_I16)
         res[prune] = [ctx.match(mode, noisy, snr_low, ids, k) for k in (1, 8, 32)]
-        if prune:
+        if prune == 1:
             stats = ctx.pruning_stats()
         ctx.db_drop(0)
         ctx.db_drop(1)
     ctx.set_pruning(ctx.pruning_default)
-    for a, b in zip(res[False], res[True]):
-        for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
-            assert np.array_equal(a[key], b[key], equal_nan=True), key
-    assert (res[True][1]['status'] == native.PIX_SEARCHED).mean() > 0.8
+    for other in (1, 2):
+        for a, b in zip(res[0], res[other]):
+            for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
+                assert np.array_equal(a[key], b[key], equal_nan=True), (other, key)
+    assert (res[1][1]['status'] == native.PIX_SEARCHED).mean() > 0.8
     assert stats['skipped'] > stats['evaluated']
 
 
@@ -690,7 +698,7 @@ def test_pruning_large_and_tiny_databases(ctx):
     sobs, snr, ids = obs['sobs_totrot'].reshape(-1, 8), obs['snr'].reshape(-1, 8), obs['db_enc'].reshape(-1).astype(np.int32)
     for mode in (native.MODE_IQUV, native.MODE_IQUD):
         res = {}
-        for prune in (False, True):
+        for prune in (0, 1, 2):
             ctx.set_pruning(prune)
             ctx.db_put(0, big, native.ENC_I16)
             ctx.db_put(1, tiny, native.ENC_I16)
@@ -699,8 +707,9 @@ def test_pruning_large_and_tiny_databases(ctx):
             ctx.db_drop(1)
         ctx.set_pruning(ctx.pruning_default)
         for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
-            assert np.array_equal(res[False][key], res[True][key], equal_nan=True), (mode, key)
-        assert (res[True]['status'] == native.PIX_SEARCHED).mean() > 0.8
+            assert np.array_equal(res[0][key], res[1][key], equal_nan=True), (mode, key)
+            assert np.array_equal(res[0][key], res[2][key], equal_nan=True), (mode, key)
+        assert (res[1]['status'] == native.PIX_SEARCHED).mean() > 0.8
 
 
 @pytest.mark.parametrize('seed', [0, 1, 2, 3, 4, 5])
@@ -728,14 +737,20 @@ def test_pruning_randomised_databases(ctx, seed):
     for encoding in (native.ENC_F32, native.ENC_I16):
         for mode in (native.MODE_IQUV, native.MODE_IQUD):
             res = {}
-            for prune in (False, True):
+            for prune in (0, 1, 2):
                 ctx.set_pruning(prune)
                 ctx.db_put(0, db, encoding)
                 res[prune] = ctx.match(mode, sobs, snr, ids, k)
+                if prune == 2:                              # chunked candidate lists: a seed tile outside a chunk
+                    ctx.set_tuning(7, 3)
+                    chunked = ctx.match(mode, sobs, snr, ids, k)
+                    ctx.set_tuning(0, 0)
                 ctx.db_drop(0)
             ctx.set_pruning(ctx.pruning_default)
             for key in ('idx', 'chi', 'kpos', 'status', 'rows', 'ncand'):
-                assert np.array_equal(res[False][key], res[True][key], equal_nan=True), (encoding, mode, k, key)
+                assert np.array_equal(res[0][key], res[1][key], equal_nan=True), (encoding, mode, k, key)
+                assert np.array_equal(res[0][key], res[2][key], equal_nan=True), (encoding, mode, k, key)
+                assert np.array_equal(res[0][key], chunked[key], equal_nan=True), (encoding, mode, k, key)
 
 
 
