@@ -661,6 +661,29 @@ def bench_config5(B, nx, ndb, steps):
                                       note='CUDA events between the three calls of one step, max over ranks; the all-gather moves %.0f MB '
                                            'into every GPU' % (rank_bytes * (B.world - 1) / 1e6)),
                search_kernel_ms=float(np.mean(kern_ms)) if len(kern_ms) else None, pruning=stats, setup_seconds=setup_s)
+    # the same step with the brute-force search (k-d layout, seeded: every (pixel, entry) pair evaluated - the FP32-bound kernel)
+    ctx.set_pruning(2)
+    for _ in range(2):
+        step()
+    B.barrier()
+    nb = max(2, min(steps, 4))
+    b_ms, b_kern = B.timed(step, nb)
+    B.barrier()
+    ctx.set_pruning(1)
+    bms = B.max_over_ranks(float(np.mean(b_ms)))
+    st_local = send[o_st:o_st + n].cpu().numpy() if n else np.zeros(0, np.uint8)
+    info = [ctx.db_info(j) for j in range(used.size)]
+    cnt_of = np.array([[i['npos'], i['nneg'], i['nzero']] for i in info], dtype=np.int64).reshape(-1, 3)
+    v = sobs[:, 3]
+    cls_of = np.where(v > 0, 0, np.where(v < 0, 1, 2))
+    ncand = int(cnt_of[ids, cls_of][st_local == 0].sum()) if n else 0
+    bk = float(np.mean(b_kern)) if len(b_kern) else float('nan')
+    frac = B.max_over_ranks(20.0 * ncand / (bk * 1e-3) / 1e12 / B.fp32_peak) if B.fp32_peak else None
+    rec['bruteforce'] = dict(value=npix / (bms * 1e-3), unit='pixels/s', ms_per_step=bms, steps=nb, search_kernel_ms=B.max_over_ranks(bk),
+                             search='brute force, every (pixel, entry) pair evaluated; k-d tile layout, seeded (cledb_set_pruning 2)',
+                             roofline=dict(bound='fp32', kernel='k_match<%s,fp32> seeded' % ('int16' if B.args.encoding == 1 else 'float32'),
+                                           frac=frac, peak=B.fp32_peak, unit='TFLOP/s', flop_per_candidate=20,
+                                           note='max over ranks of 20 FLOP x the rank\'s candidates / its kernel time / measured FP32 peak'))
     # end to end: the host-buffer collective call (every rank its shard in, the full maps out on rank 0)
     out = ctx.result_buffers(npix, k) if B.rank == 0 else None
     for _ in range(2):
