@@ -464,24 +464,34 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
 # config 4: the elementwise neighbours on a 2048 x 2048 map (HBM roofline)
 # ---------------------------------------------------------------------------------------------------------------
 def bench_elementwise(B, nx, steps, cpu=True):
+    """Both kernels are far shorter than the gap between two host-issued launches is stable (23 - 55 us), so a timed step is a
+    batch of NB launches between one pair of CUDA events, every launch on its own input / output buffers: NSET buffer sets,
+    0.6 - 1.3 GB in total, cycled through - no launch finds its data in the 126 MB L2, no flush needed between them."""
     torch, ctx = B.torch, B.ctx
     from cledb_b200 import synth
     import constants as consts
     import oracle.cledb_oracle as orc
     npix = nx * nx
     out = {}
+    NSET, NB = 4, 8
 
-    def timed(fn):
-        for _ in range(5):
-            fn()
+    def timed(fn_of_set):
+        for i in range(NSET):
+            fn_of_set(i)
         torch.cuda.synchronize()
-        ms, _ = B.timed(fn, steps, profile=False)
-        return float(np.mean(ms))
+
+        def batch():
+            for i in range(NB):
+                fn_of_set(i % NSET)
+        ms, _ = B.timed(batch, steps, profile=False)
+        return float(np.mean(ms)) / NB
 
     def record(kernel, metric, workload, ms, bpp, e2e_s, h2d, d2h, cpu_rec):
         gbs = bpp * npix / (ms * 1e-3) / 1e9
         tr = B.traffic_of(kernel + ('_%d' % nx))
-        return dict(metric=metric, value=npix / (ms * 1e-3), unit='pixels/s', ms_per_step=ms, steps=steps, workload=workload,
+        return dict(metric=metric, value=npix / (ms * 1e-3), unit='pixels/s', ms_per_step=ms, steps=steps * NB, workload=workload,
+                    timing='%d launches per CUDA-event pair over %d rotating buffer sets (working set %.0f MB, larger than L2)'
+                           % (NB, NSET, NSET * bpp * npix / 1e6),
                     roofline=dict(bound='hbm', kernel=kernel, achieved=gbs, peak=B.hbm_peak, unit='GB/s', frac=gbs / B.hbm_peak, traffic=tr,
                                   bytes_per_pixel=bpp, algorithmic_bytes_per_launch=bpp * npix, peak_source=B.hbm_src),
                     e2e=dict(value=npix / e2e_s, unit='pixels/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_s * 1e3),
@@ -490,26 +500,28 @@ def bench_elementwise(B, nx, steps, cpu=True):
     one = synth.make_oneline_map(nx, nx)
     c = consts.Constants('fe-xiii_1074')
     kfac = 1.e9 * (c.planckconst * c.l_speed / c.bohrmagneton / (c.line_ref ** 2))
-    d_in = torch.from_numpy(one.reshape(-1, 4)).to(B.dev)
-    d_out = torch.empty_like(d_in)
-    d_fl = torch.empty((npix, 2), dtype=torch.uint8, device=B.dev)
-    ms = timed(lambda: ctx.blos_dev(npix, d_in.data_ptr(), kfac, c.g_eff, c.F_factor, d_out.data_ptr(), d_fl.data_ptr(), B.stream.cuda_stream))
+    d_in = [torch.from_numpy(one.reshape(-1, 4)).to(B.dev) for _ in range(NSET)]
+    d_out = [torch.empty_like(d_in[0]) for _ in range(NSET)]
+    d_fl = [torch.empty((npix, 2), dtype=torch.uint8, device=B.dev) for _ in range(NSET)]
+    ms = timed(lambda i: ctx.blos_dev(npix, d_in[i].data_ptr(), kfac, c.g_eff, c.F_factor, d_out[i].data_ptr(), d_fl[i].data_ptr(),
+                                      B.stream.cuda_stream))
     one_p = B.pinned(one.reshape(-1, 4)).numpy()
     ctx.blos(one_p, kfac, c.g_eff, c.F_factor)
     t0 = time.perf_counter()
     for _ in range(3):
         out_h, fl_h = ctx.blos(one_p, kfac, c.g_eff, c.F_factor)
     e2e = (time.perf_counter() - t0) / 3
-    assert np.array_equal(out_h, d_out.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(out_h, d_out[0].cpu().numpy(), equal_nan=True)
     cpu_rec = None
     if cpu:
         ns = 8192
         t0 = time.perf_counter()
         ref = np.stack([orc.blos_pixel(one.reshape(-1, 4)[i], c)[0] for i in range(ns)])
         cpu_rec = dict(value=ns / (time.perf_counter() - t0), unit='pixels/s', cores=1, kind='port', sample='%d pixels, oracle blos_pixel loop' % ns)
-        assert np.allclose(ref, out_h[:ns], rtol=2e-6, atol=1e-30, equal_nan=True)
+        assert np.allclose(ref[:, :3], out_h[:ns, :3], rtol=2e-6, atol=1e-30, equal_nan=True)          # field strengths
+        assert np.allclose(ref[:, 3], out_h[:ns, 3], rtol=0, atol=1e-6, equal_nan=True)                   # azimuth
     out['config4_blos_%d' % nx] = record('k_blos', '1-line B_LOS pixels/s',
-                                         'blos_proc_1pix on a %dx%d 1-line map (%.0f MB in+out, larger than L2)' % (nx, nx, 34.0 * npix / 1e6),
+                                         'blos_proc_1pix on a %dx%d 1-line map (%.0f MB in+out per launch)' % (nx, nx, 34.0 * npix / 1e6),
                                          ms, 34, e2e, 16 * npix, 18 * npix, cpu_rec)
     del d_in, d_out, d_fl
 
@@ -518,18 +530,18 @@ def bench_elementwise(B, nx, steps, cpu=True):
     xs = np.array([kv[8] + i * kv[11] for i in range(nx)], dtype=np.float64)
     ys = np.array([kv[9] + i * kv[12] for i in range(nx)], dtype=np.float64)
     d_xs, d_ys = torch.from_numpy(xs).to(B.dev), torch.from_numpy(ys).to(B.dev)
-    d2 = torch.from_numpy(two).to(B.dev)
-    o2 = torch.empty_like(d2)
-    d_a = torch.empty((nx, nx), dtype=torch.float32, device=B.dev)
-    d_y = torch.empty((nx, nx), dtype=torch.float32, device=B.dev)
+    d2 = [torch.from_numpy(two).to(B.dev) for _ in range(NSET)]
+    o2 = [torch.empty_like(d2[0]) for _ in range(NSET)]
+    d_a = [torch.empty((nx, nx), dtype=torch.float32, device=B.dev) for _ in range(NSET)]
+    d_y = [torch.empty((nx, nx), dtype=torch.float32, device=B.dev) for _ in range(NSET)]
     two_p = B.pinned(two).numpy()
     for label, hp in (('', None), ('_hpxy', 'grid')):
         d_hp = hp_np = None
         if hp:
             hp_np = np.stack(np.meshgrid(xs.astype(np.float32), ys.astype(np.float32), indexing='ij')).astype(np.float32)
-            d_hp = torch.from_numpy(hp_np).to(B.dev)
-        ms = timed(lambda: ctx.qurotate_dev(nx, nx, d_xs.data_ptr(), d_ys.data_ptr(), kv[14], d_hp.data_ptr() if hp else None,
-                                            d2.data_ptr(), o2.data_ptr(), d_a.data_ptr(), d_y.data_ptr(), B.stream.cuda_stream))
+            d_hp = [torch.from_numpy(hp_np).to(B.dev) for _ in range(NSET)]
+        ms = timed(lambda i: ctx.qurotate_dev(nx, nx, d_xs.data_ptr(), d_ys.data_ptr(), kv[14], d_hp[i].data_ptr() if hp else None,
+                                              d2[i].data_ptr(), o2[i].data_ptr(), d_a[i].data_ptr(), d_y[i].data_ptr(), B.stream.cuda_stream))
         ctx.qurotate(two_p, xs, ys, kv[14], hp_np)
         t0 = time.perf_counter()
         rot_h, a_h, y_h = ctx.qurotate(two_p, xs, ys, kv[14], hp_np)
@@ -547,7 +559,7 @@ def bench_elementwise(B, nx, steps, cpu=True):
         bpp = 72 + (8 if hp else 0)
         out['config4_qurotate_%d%s' % (nx, label)] = record(
             'k_qurotate' + label, 'QU rotation + height pixels/s',
-            'obs_qurotate + obs_calcheight on a %dx%d 2-line map, %s (%.0f MB)' % (nx, nx, 'Cryo-NIRSP coordinate grid' if hp else 'rectangular grid', bpp * npix / 1e6),
+            'obs_qurotate + obs_calcheight on a %dx%d 2-line map, %s (%.0f MB per launch)' % (nx, nx, 'Cryo-NIRSP coordinate grid' if hp else 'rectangular grid', bpp * npix / 1e6),
             ms, bpp, e2e, (32 + (8 if hp else 0)) * npix, 40 * npix, cpu_rec)
     return out
 

@@ -214,7 +214,7 @@ int cledb_invert_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  *   tan_phib   = [npix,2] float64: tan(Phi_B) and tan(pi - Phi_B) of every pixel (:1428-1430 / :1516-1518)
  * Outputs as cledb_match, with idx the row of the FULL database (:1070-1071) and kpos the position inside the pixel's
  * filtered subset; nan_slots_out[npix] = how many leading output slots the reference leaves empty because that many
- * candidates have a NaN chi^2 (its selection sort picks NaNs first).  Host buffers only. */
+ * candidates have a NaN chi^2 (its selection sort picks NaNs first). */
 typedef struct cledb_reduced {
     int32_t outer, nbphi, nbtheta;
     const double*  tan_btheta;   /* [nbtheta] */
@@ -226,6 +226,12 @@ int cledb_match_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
                         const float* sobs, const float* snr, const int32_t* db_id, int nsearch, const cledb_reduced* red,
                         int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out, float* rows_out,
                         uint8_t* status_out, int32_t* nan_slots_out);
+/* device-pointer variant: every array, the four tables inside *red included, lives on the context's device; enqueued on the
+ * stream (NULL = the context's own).  Every output is required (chi64_out only for the fp64 search). */
+int cledb_match_reduced_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix,
+                            const float* sobs, const float* snr, const int32_t* db_id, int nsearch, const cledb_reduced* red,
+                            int32_t* idx_out, float* chi_out, double* chi64_out, int32_t* kpos_out, float* rows_out,
+                            uint8_t* status_out, int32_t* nan_slots_out, void* stream);
 /* the same followed by the solution building of cledb_invert */
 int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
                          const float* sobs, const float* snr, const int32_t* db_id, int nsearch, const cledb_reduced* red,

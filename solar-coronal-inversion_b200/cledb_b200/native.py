@@ -55,6 +55,7 @@ SIGNATURES = {
     'cledb_invert': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
                                 _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'cledb_match_reduced': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'cledb_match_reduced_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'cledb_invert_reduced': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _P, _c.c_int,
                                         _c.c_int64, _P, _c.c_double, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'cledb_invert_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int,
@@ -592,6 +593,13 @@ class Context:
                                                  ctypes.addressof(red), _ptr(out['idx']), _ptr(out['chi']), _ptr(out['chi64']),
                                                  _ptr(out['kpos']), _ptr(out['rows']), _ptr(out['status']), _ptr(out['nan_slots'])))
         return out
+
+    def match_reduced_dev(self, mode, npix, sobs_ptr, snr_ptr, dbid_ptr, nsearch, red, idx_ptr, chi_ptr, chi64_ptr, kpos_ptr, rows_ptr,
+                          status_ptr, nan_ptr, stream=None, precision=PREC_FP32):
+        """cledb_match_reduced_dev; ``red``: a ``Reduced`` whose four table pointers are device addresses."""
+        self._check(self.lib.cledb_match_reduced_dev(self.h, int(mode), int(precision), int(npix), sobs_ptr, snr_ptr, dbid_ptr, int(nsearch),
+                                                     ctypes.addressof(red), idx_ptr, chi_ptr, chi64_ptr, kpos_ptr, rows_ptr, status_ptr,
+                                                     nan_ptr, stream))
 
     def invert_reduced(self, mode, sobs, snr, db_id, nsearch, yobs, dobs, aobs, sobs_dopp, dbhdr, maxchisq, bcalc,
                        strict_topk=False, precision=PREC_FP32, tie_order=None):

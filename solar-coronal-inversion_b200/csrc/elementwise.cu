@@ -13,21 +13,52 @@ namespace cledb {
 
 // 34 B/pixel: 16 in, 16 out, 2 flag bytes.  Four pixels per thread, 256 apart: four independent coalesced 16-byte loads
 // in flight per thread before the first use.
+//
+// The kernel is only bandwidth-bound if a pixel costs few instructions (ncu, round 2: with IEEE divisions, IEEE square root
+// and the library atan2f it ran at 172 instructions per pixel and 82 % issue-slot utilisation - bound by instruction issue at
+// 0.70 of the HBM copy bandwidth).  So: the two quotients that DECIDE the integer issue flags (Q/I, U/I against 1e-6) keep the
+// IEEE division the reference's float32 arithmetic has; the three field strengths and the azimuth are floating-point results
+// with a stated tolerance (tests: 2e-6 relative, 1e-6 rad absolute) and use reciprocal / reciprocal-square-root
+// approximations (2 ulp) and a degree-7 minimax polynomial for atan (3e-7 absolute, the accuracy of NumPy's own float32
+// arctan2).
+
+// atan2(y, x) for finite arguments: |error| <= 4e-7.  atan(t)/t on [0, 1] as a polynomial in t^2.
+__device__ __forceinline__ float atan2_poly(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float t = __fdividef(mn, mx);
+    if (mn == mx) t = mx > 0.f ? 1.f : 0.f;                 // 0/0 (atan2(0, 0) = 0 or pi), inf/inf
+    const float q = t * t;
+    float p = -0.00405456f;
+    p = fmaf(p, q, 0.02186293f);
+    p = fmaf(p, q, -0.05591229f);
+    p = fmaf(p, q, 0.09642195f);
+    p = fmaf(p, q, -0.13908629f);
+    p = fmaf(p, q, 0.19946566f);
+    p = fmaf(p, q, -0.33329861f);
+    p = fmaf(p, q, 0.99999934f);
+    float r = t * p;
+    if (ay > ax) r = 1.5707963267948966f - r;
+    if (signbit(x)) r = 3.141592653589793f - r;
+    return copysignf(r, y);
+}
+
 __device__ __forceinline__ void blos_one(const float4 s, float kfac, float geff, float c66f, float4& o, uchar2& f) {
     o = make_float4(0.f, 0.f, 0.f, 0.f);
     f = make_uchar2(0, 0);
     const bool bad = (s.x == 0.f) || isnan(s.x) || isnan(s.y) || isnan(s.z) || isnan(s.w);   // CLEDB_PROC.py:882
     if (bad) return;
     // float32 arithmetic in the reference: NumPy float32 scalars with Python-float constants (weak promotion)
-    const float lpol = __fsqrt_rn(__fadd_rn(__fmul_rn(s.y, s.y), __fmul_rn(s.z, s.z)));
+    const float l2 = __fadd_rn(__fmul_rn(s.y, s.y), __fmul_rn(s.z, s.z));
+    const float lpol = l2 > 0.f ? l2 * rsqrtf(l2) : 0.f;
     const float nv = -s.w;
     const float d0 = __fsub_rn(__fmul_rn(geff, __fsub_rn(s.x, lpol)), __fmul_rn(c66f, lpol));
     const float d1 = __fadd_rn(__fmul_rn(geff, __fadd_rn(s.x, lpol)), __fmul_rn(c66f, lpol));
     const float d2 = __fmul_rn(geff, s.x);
-    o.x = __fmul_rn(kfac, __fdiv_rn(nv, d0));
-    o.y = __fmul_rn(kfac, __fdiv_rn(nv, d1));
-    o.z = __fmul_rn(kfac, __fdiv_rn(nv, d2));
-    o.w = 0.5f * atan2f(s.z, s.y);
+    o.x = __fmul_rn(kfac, __fdividef(nv, d0));
+    o.y = __fmul_rn(kfac, __fdividef(nv, d1));
+    o.z = __fmul_rn(kfac, __fdividef(nv, d2));
+    o.w = 0.5f * atan2_poly(s.z, s.y);
     const float qi = __fdiv_rn(s.y, s.x), ui = __fdiv_rn(s.z, s.x);
     if (fabsf(qi) < 1e-6f || fabsf(ui) < 1e-6f) {            // :907
         f.x = 1;

@@ -406,6 +406,27 @@ extern "C" int cledb_match_reduced(cledb_ctx* ctx, int mode, int precision, int6
                         status_out, nan_slots_out, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 1, nullptr, 0.0, 0, 0, nullptr, nullptr);
 }
 
+// device-pointer variant of the raw reduced search: every array - the four tables inside *red included - lives on the
+// context's device; enqueued on the stream, no copies, no wait
+extern "C" int cledb_match_reduced_dev(cledb_ctx* ctx, int mode, int precision, int64_t npix, const float* sobs, const float* snr,
+                                       const int32_t* db_id, int nsearch, const cledb_reduced* red, int32_t* idx_out, float* chi_out,
+                                       double* chi64_out, int32_t* kpos_out, float* rows_out, uint8_t* status_out, int32_t* nan_slots_out,
+                                       void* stream) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    if (npix < 0 || !sobs || !snr || !db_id || !red || !idx_out || !chi_out || !kpos_out || !rows_out || !status_out || !nan_slots_out) {
+        ctx->err = "cledb_match_reduced_dev: null argument (every output is required)";
+        return CLEDB_ERR_ARG;
+    }
+    if (nsearch < 1 || nsearch > CLEDB_MAX_NSEARCH) { ctx->err = "reduced search: nsearch must be in 1..32"; return CLEDB_ERR_ARG; }
+    if (mode != CLEDB_MODE_IQUV && mode != CLEDB_MODE_IQUD) { ctx->err = "reduced search: unknown mode"; return CLEDB_ERR_ARG; }
+    if (precision == CLEDB_PREC_FP64 && !chi64_out) { ctx->err = "cledb_match_reduced_dev: the fp64 search needs chi64_out"; return CLEDB_ERR_ARG; }
+    if (npix == 0) return CLEDB_OK;
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return reduced_device(ctx, mode, precision, npix, sobs, snr, db_id, nsearch, *red, idx_out, chi_out,
+                          precision == CLEDB_PREC_FP64 ? chi64_out : nullptr, kpos_out, rows_out, status_out, nan_slots_out,
+                          stream ? (cudaStream_t)stream : ctx->stream);
+}
+
 extern "C" int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix, const float* sobs, const float* snr,
                                     const int32_t* db_id, int nsearch, const cledb_reduced* red, const float* yobs, const float* dobs,
                                     const float* rot_cos, const float* rot_sin, const void* dopp, int dopp_is_f64, int64_t dopp_stride,

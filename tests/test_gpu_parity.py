@@ -989,3 +989,43 @@ def test_sharded_call_on_one_rank_equals_the_plain_call():
     with pytest.raises(native.CledbError, match='communicator'):
         c.invert_sharded(0, sobs[order], snr[order], ids[order], 8, y[order], d[order], a[order], None, hdr, 1000, 0, n, order, bounds)
     c.close()
+
+
+def test_reduced_search_device_pointer_variant(golden_dir):
+    """cledb_match_reduced_dev (device buffers, caller's stream) returns what the host-buffer call returns, bit for bit."""
+    import torch
+    g = np.load(os.path.join(golden_dir, 'reduced_maps.npz'))
+    hdr = hdr_from_g(g['hdr_g'])
+    c = native.Context(0)
+    for i, db in enumerate((g['db0'], g['db1'])):
+        c.db_put(i, db, native.ENC_F32)
+    dev = torch.device('cuda', 0)
+    stream = torch.cuda.Stream(device=dev)
+    for tag, mode in (('iquv_k8', native.MODE_IQUV), ('iqud_k8', native.MODE_IQUD)):
+        sobs, snr = g['sobs_' + tag].reshape(-1, 8), g['snr'].reshape(-1, 8)
+        dopp = g['sobs_dopp'].reshape(sobs.shape[0], -1)
+        ids = g['db_enc'].reshape(-1).astype(np.int32)
+        n, k = sobs.shape[0], 8
+        for prec in (native.PREC_FP32, native.PREC_FP64):
+            ref = c.match_reduced(mode, sobs, snr, ids, k, dopp, hdr, precision=prec, tie_order=g['tie_order'])
+            red = native.Reduced.build(mode, np.ascontiguousarray(sobs, np.float32), dopp, hdr, g['tie_order'])
+            tabs = [torch.from_numpy(a).to(dev) for a in red._keep]
+            red.tan_btheta, red.sin_bphi, red.tie_rank, red.tan_phib = (t.data_ptr() for t in tabs)
+            d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            d_sobs, d_snr, d_ids = d(sobs.astype(np.float32)), d(snr.astype(np.float32)), d(ids)
+            idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+            chi = torch.empty((n, k), dtype=torch.float32, device=dev)
+            chi64 = torch.empty((n, k), dtype=torch.float64, device=dev)
+            kpos = torch.empty((n, k), dtype=torch.int32, device=dev)
+            rows = torch.empty((n, k, 8), dtype=torch.float32, device=dev)
+            st = torch.empty(n, dtype=torch.uint8, device=dev)
+            nan = torch.empty(n, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            c.match_reduced_dev(mode, n, d_sobs.data_ptr(), d_snr.data_ptr(), d_ids.data_ptr(), k, red, idx.data_ptr(), chi.data_ptr(),
+                                chi64.data_ptr(), kpos.data_ptr(), rows.data_ptr(), st.data_ptr(), nan.data_ptr(), stream.cuda_stream, precision=prec)
+            stream.synchronize()
+            assert same(idx.cpu().numpy(), ref['idx']) and same(chi.cpu().numpy(), ref['chi']) and same(kpos.cpu().numpy(), ref['kpos'])
+            assert same(rows.cpu().numpy(), ref['rows']) and same(st.cpu().numpy(), ref['status']) and same(nan.cpu().numpy(), ref['nan_slots'])
+            if prec == native.PREC_FP64:
+                assert same(chi64.cpu().numpy(), ref['chi64'])
+    c.close()
