@@ -359,7 +359,7 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
             pairs = stats['evaluated'] + stats['skipped']
             roof = dict(bound='fp32 (instruction-issue limited: selection and bound code)', kernel='k_match_pruned<%s>' % enc_name,
                         achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak if peak else None,
-                        traffic=B.traffic_of('k_match_pruned_' + mode_name), kernel_ms=kms, kernel_share_of_step=kms / float(np.mean(step_ms)),
+                        traffic=B.traffic_of('k_match_pruned_' + mode_name) if (nx, ndb, encoding) == (256, 1, 1) else None, kernel_ms=kms, kernel_share_of_step=kms / float(np.mean(step_ms)),
                         flop_per_evaluated_entry=20, evaluated_entries_per_launch=evaluated,
                         frac_if_every_candidate_counted=20.0 * ncand / (kms * 1e-3) / 1e12 / peak if peak else None,
                         note='FLOPs of the entries the kernel really evaluates: exact tile bounds skip %.1f %% of the (pixel, tile) pairs. '
@@ -371,7 +371,9 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
             achieved = 20.0 * ncand / (kms * 1e-3) / 1e12
             roof = dict(bound='fp32', kernel='k_match<%s,fp32>%s' % (enc_name, ' seeded, k-d tile layout' if variant == 2 else ' plain layout'),
                         achieved=achieved, peak=peak, unit='TFLOP/s',
-                        frac=achieved / peak if peak else None, traffic=B.traffic_of('k_match_' + mode_name), kernel_ms=kms,
+                        frac=achieved / peak if peak else None,
+                        traffic=B.traffic_of('k_match_%s_%s' % ('seeded' if variant == 2 else 'plain', mode_name)) if (nx, ndb, encoding) == (256, 1, 1) else None,
+                        kernel_ms=kms,
                         kernel_share_of_step=kms / float(np.mean(step_ms)), flop_per_candidate=20, candidates_per_launch=ncand,
                         peak_source=peak_src)
             evals = ncand_all
