@@ -180,6 +180,15 @@ extern "C" int cledb_pruning_stats(cledb_ctx* ctx, int64_t evaluated[2]) {
     return CLEDB_OK;
 }
 
+// timing experiments only (not in the header): raw words of the pruned search's statistics buffer
+extern "C" int cledb_debug_stats(cledb_ctx* ctx, unsigned long long* out, int n) {
+    if (!ctx || !out || n < 1 || n > (1 << 17) || !ctx->d_prune_stats) return CLEDB_ERR_ARG;
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CLEDB_CUDA(ctx, cudaDeviceSynchronize());
+    CLEDB_CUDA(ctx, cudaMemcpy(out, ctx->d_prune_stats, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return CLEDB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------------

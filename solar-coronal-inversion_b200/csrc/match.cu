@@ -272,6 +272,12 @@ struct Plan {                 // all pointers are device pointers into the works
     int32_t* foff;            // [slots * ftiles] first position of the fine bucket in `order`
     int32_t  ftiles;          // fine keys per database slot (>= tiles of the largest resident database)
     int32_t  fused;           // pruned IQUD search: one item per pixel group walks every sign class with one list per pixel
+    // longest-items-first queue of the pruned search (NULL: items are taken in index order)
+    float*   wpix;            // [npix] predicted weight of a pixel: chi^2 of the best tile representative (k_seed)
+    int32_t* qbin;            // [max items] weight bin of an item
+    int32_t* qorder;          // [max items] item indices, heaviest bin first
+    int32_t* qhist;           // [64] items per bin, then [64] cursors
+    int64_t  qcap;            // capacity of qbin / qorder
 };
 
 // the sign class with the most entries (ties: the lowest class)
@@ -1157,9 +1163,9 @@ __global__ void __launch_bounds__(256) k_seed(Plan pl, const DbSlot* __restrict_
     int32_t seeds[kParts];
     for (int q = 0; q < kParts; ++q) {
         int best_t = 0x7fffffff;
+        float best = CUDART_INF_F;
         const bool mine = pl.mode == CLEDB_MODE_IQUV ? q == key % kParts : (pl.fused ? q == largest_class(db) : db.part_cnt[q] > 0);
         if (mine) {
-            float best = CUDART_INF_F;
             const int nt = db.part_ntiles[q], t0 = db.part_tile0[q];
             if (staged) {
 #pragma unroll 4
@@ -1189,6 +1195,9 @@ __global__ void __launch_bounds__(256) k_seed(Plan pl, const DbSlot* __restrict_
         if (best_t == 0x7fffffff) best_t = -1;
         seeds[q] = best_t;
         if (sub == 0) pl.seed[p * kParts + q] = best_t;
+        // the search cost of a pixel grows with its threshold, and the chi^2 of the best representative is a monotone proxy of
+        // it; the class a pixel searches first (its own for IQUV, the largest for fused IQUD) gives the weight
+        if (sub == 0 && pl.wpix && mine && (pl.mode == CLEDB_MODE_IQUV || q == largest_class(db))) pl.wpix[p] = best_t < 0 ? CUDART_INF_F : best;
     }
     if (sub == 0) atomicAdd(&pl.fcnt[fine_key(pl, db, key, seeds)], 1);
 }
@@ -1233,16 +1242,44 @@ __global__ void __launch_bounds__(256) k_scatter_fine(Plan pl, const DbSlot* __r
 #ifndef CLEDB_PRUNED_WPC
 #define CLEDB_PRUNED_WPC 16
 #endif
+// Longest items first.  The items of the pruned search differ a lot in length - a pixel whose observation fits no entry well
+// keeps a loose threshold and has to look at a hundred tiles instead of ten - and the kernel ends when its longest item
+// ends: taken in index order, a long item that comes up late leaves the other warps idle (256^2 map: half the warps were
+// idle at 60 % of the kernel's duration).  So the queue hands the items out heaviest first: weight of an item = sum of the
+// seed chi^2 of its pixels (k_seed), quantised to 64 logarithmic bins, counting sort by bin.
+__global__ void __launch_bounds__(256) k_item_weight(Plan pl, const DbSlot* __restrict__ slots) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= pl.counters[2]) return;
+    const Item im = make_item(pl, slots, it);
+    float w = 0.f;
+    for (int j = 0; j < im.npx; ++j) w += pl.wpix[pl.order[im.pix0 + j]];
+    int bin = 63;                                                   // inf / NaN: a pixel without seed - the exact path over every tile
+    if (w < 1e30f) bin = min(62, max(0, (int)(2.f * log2f(fmaxf(w, 1e-6f))) + 24));
+    pl.qbin[it] = bin;
+    atomicAdd(&pl.qhist[bin], 1);
+}
+__global__ void __launch_bounds__(256) k_item_order(Plan pl) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= pl.counters[2]) return;
+    const int bin = pl.qbin[it];
+    int before = 0;
+    for (int b = 63; b > bin; --b) before += pl.qhist[b];           // heavier bins come first
+    pl.qorder[before + atomicAdd(&pl.qhist[64 + bin], 1)] = it;
+}
+
 template <int ENC> struct PCfg {        // shared memory of one warp of the pruned search: one tile in flight, <= 32 pixels
     static constexpr int kWpc = CLEDB_PRUNED_WPC;
     static constexpr int kTB = tile_bytes<ENC>();
+    // stage buffers of the tile walk (tile s + kNst is requested as soon as tile s sits in registers)
+    static constexpr int kNst = 1;       // measured (profiles/r02_tuning.txt): 2 or 3 stages are 5 - 8 % slower - the extra shared memory
+                                        // takes the L1 the bound tables live in, and the walk is not bound by the load latency
     static constexpr int kRecBytes = (32 + 1) * (int)sizeof(Rec<CLEDB_PREC_FP32>);
     static constexpr int kListBytes = kListCap * (int)sizeof(Cand<CLEDB_PREC_FP32>);
 };
 constexpr int kTileListCap = 96;        // tile list of a warp: evaluated at >= 64 entries, one group adds <= 16
 
 template <int ENC> __host__ __device__ constexpr int pruned_warp_bytes() {
-    return (PCfg<ENC>::kTB + PCfg<ENC>::kRecBytes + PCfg<ENC>::kListBytes + 16 + 128 + (2 * kTileListCap + 32) * 4 + 32 * 8 + 127) / 128 * 128;
+    return (PCfg<ENC>::kNst * PCfg<ENC>::kTB + PCfg<ENC>::kRecBytes + PCfg<ENC>::kListBytes + 32 + 128 + (2 * kTileListCap + 32) * 4 + 32 * 8 + 127) / 128 * 128;
 }
 
 template <int ENC>
@@ -1256,11 +1293,12 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* stages = smem + (size_t)warp * pruned_warp_bytes<ENC>();                 // one tile
-    RecT* recs = reinterpret_cast<RecT*>(stages + TB);                                       // [32 + 1]
+    constexpr int NST = C::kNst;
+    unsigned char* stages = smem + (size_t)warp * pruned_warp_bytes<ENC>();                 // NST tiles
+    RecT* recs = reinterpret_cast<RecT*>(stages + NST * TB);                                 // [32 + 1]
     CandT* lists = reinterpret_cast<CandT*>(reinterpret_cast<unsigned char*>(recs) + C::kRecBytes);   // [npx][k]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(lists) + C::kListBytes);
-    float* c0s = reinterpret_cast<float*>(bars + 2);                                         // [32]
+    float* c0s = reinterpret_cast<float*>(bars + 4);                                         // [32]
     int32_t* tlist = reinterpret_cast<int32_t*>(c0s + 32);                                   // [kTileListCap] tiles to evaluate
     uint32_t* tmask = reinterpret_cast<uint32_t*>(tlist + kTileListCap);                     // [kTileListCap] the pixels that need each of them
     int32_t* slist = tlist + 2 * kTileListCap;                                               // [32] the item's seed tiles
@@ -1270,18 +1308,30 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
     unsigned long long n_eval = 0, n_all = 0;
 
     if (lane == 0) {
-        mbar_init(&bars[0], 1);
+#pragma unroll
+        for (int q = 0; q < NST; ++q) mbar_init(&bars[q], 1);
         fence_barrier_init();
+        if (pl.dbg == 7 && stats && blockIdx.x == 0 && warp == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            stats[2] = t;
+        }
     }
     __syncwarp();
 
     for (;;) {
         int it = 0;
-        if (lane == 0) it = atomicAdd(&pl.counters[0], 1);
+        if (lane == 0) {
+            it = atomicAdd(&pl.counters[0], 1);
+            if (it < pl.counters[2] && pl.qorder) it = pl.qorder[it];        // the queue hands the items out heaviest first
+        }
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= pl.counters[2]) break;
         const Item im = make_item(pl, slots, it);                             // items hold <= 32 pixels and whole sign classes
         const DbSlot& db = slots[im.slot];
+        unsigned long long dbg_t0 = 0, dbg_e0 = n_eval;
+        int dbg_exact = 0;
+        if (pl.dbg == 7) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_t0));
         CandT* gout = reinterpret_cast<CandT*>(pl.plist) + (size_t)it * pl.P * k;
         // The sign classes this item searches: its own (IQUV), or - IQUD (pl.fused) - every non-empty class of the database, one
         // after the other with ONE list per pixel: the largest class first (seed tiles, thresholds close to final), so the
@@ -1371,7 +1421,7 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
             }
             for (int i = 0; i < ns; ++i) {
                 const int ts = slist[i];
-                mbar_wait(&bars[0], phase);
+                mbar_wait(&bars[0], phase & 1u);
                 phase ^= 1u;
                 load_tile_regs<ENC>(stages, lane, d);
                 __syncwarp();
@@ -1401,6 +1451,7 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
         }
         // a list its seed tile could not fill (or a pixel without seed) keeps tau = inf: exact path for the whole item
         exact_only = __any_sync(0xffffffffu, lane < im.npx && !(recs[lane].tau < CUDART_INF_F));
+        dbg_exact |= exact_only ? 1 : 0;
         // one tile against the pixels in `set` (bit j = pixel j): the fast pass of k_match over those pixels, then the exact
         // re-evaluation of the flagged ones
         auto tile_pixels = [&](uint32_t set, const float (&dd)[kEPL][kNC], int base) {
@@ -1441,23 +1492,25 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
                 }
             }
         };
-        // the listed tiles one after the other, the next one in flight
+        // the listed tiles one after the other, the next NST in flight
         auto run_tiles = [&](int n) {
             auto issue = [&](int s) {
                 if (lane == 0) {
-                    mbar_expect_tx(&bars[0], TB);
-                    tma_load_1d(stages, gt + (size_t)tlist[s] * TB, TB, &bars[0]);
+                    const int q = s % NST;
+                    mbar_expect_tx(&bars[q], TB);
+                    tma_load_1d(stages + q * TB, gt + (size_t)tlist[s] * TB, TB, &bars[q]);
                 }
             };
-            if (n > 0) issue(0);
+            for (int s = 0; s < min(n, NST); ++s) issue(s);
             for (int s = 0; s < n; ++s) {
                 const int ta = tlist[s];
                 const uint32_t set_a = tmask[s];
-                mbar_wait(&bars[0], phase);
-                phase ^= 1u;
-                load_tile_regs<ENC>(stages, lane, d);
+                const int q = s % NST;
+                mbar_wait(&bars[q], (phase >> q) & 1u);
+                phase ^= 1u << q;
+                load_tile_regs<ENC>(stages + q * TB, lane, d);
                 __syncwarp();
-                if (s + 1 < n) issue(s + 1);
+                if (s + NST < n) issue(s + NST);
                 tile_pixels(set_a, d, (c_tile0 + ta) * kTile);
             }
             __syncwarp();
@@ -1531,10 +1584,23 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
         }       // sign classes
         for (int i = lane; i < im.npx * k; i += 32) gout[i] = lists[i];
         __syncwarp();
+        if (pl.dbg == 7 && lane == 0 && stats && it < 30000) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            stats[4096 + it * 4 + 0] = dbg_t0;
+            stats[4096 + it * 4 + 1] = t1;
+            stats[4096 + it * 4 + 2] = n_eval - dbg_e0;
+            stats[4096 + it * 4 + 3] = (unsigned long long)dbg_exact | ((unsigned long long)im.npx << 8);
+        }
     }
     if (lane == 0 && stats) {
         atomicAdd(&stats[0], n_eval);
         atomicAdd(&stats[1], n_all - n_eval);
+        if (pl.dbg == 7) {                                 // timing experiment: when did this warp run out of items (globaltimer, ns)
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            stats[4 + blockIdx.x * C::kWpc + warp] = t;
+        }
     }
 }
 
@@ -1767,9 +1833,12 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     // force (cledb_set_pruning 2: the same layout and seed tiles, no bounds - every (pixel, entry) pair is evaluated)
     const bool blocked = PREC == CLEDB_PREC_FP32 && pl.seed != nullptr;
     const bool pruned = blocked && ctx->prune != 2;
-    // IQUD: one item per pixel group walks all sign classes with one list per pixel (17 % fewer tiles evaluated, 1024^2 map
-    // 10.2 -> 7.8 ms); small maps keep one item per class - twice as many, half as long: better balance at the tail
-    pl.fused = (pruned && pl.mode == CLEDB_MODE_IQUD && (npix >= 48 * wslots || ctx->pixels_per_item > 0)) ? 1 : 0;
+    // IQUD: one item per pixel group walks all sign classes with one list per pixel (17 % fewer tiles evaluated; 1024^2 map
+    // 10.2 -> 7.8 ms, 256^2 map 1.02 -> 0.95 ms)
+    pl.fused = (pruned && pl.mode == CLEDB_MODE_IQUD) ? 1 : 0;
+    // heaviest-first queue from 32 Ki pixels on; smaller maps last as long as their longest item whatever the order, and index
+    // order keeps neighbouring items - which share tiles - on one SM (128^2: 10 % faster).  dbg 8: index order (timing experiment)
+    if (!pruned || pl.dbg == 8 || npix < 32768) { pl.wpix = nullptr; pl.qorder = nullptr; }
     int64_t tiles_of_pixels = 0;
     if (pruned) {
         // The pruned search needs nothing from the host in mid-call: its work shape follows from the pixel count alone - 4, 8
@@ -1777,6 +1846,9 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
         // to the end, big maps amortise the per-item work over more pixels) - and the number of items is bounded by
         // npix/P + one partly filled item per bucket.  The call is a pure enqueue: no synchronisation, capturable in a graph.
         pl.P = npix >= 512 * wslots ? 32 : (npix >= 48 * wslots ? 8 : 4);
+        // fused IQUD items are twice as long: fewer, larger items balance better (profiles/exp_ppi.py: 8 below 100 Ki pixels,
+        // 16 up to 400 Ki, 32 above)
+        if (pl.fused) pl.P = npix >= 225 * wslots ? 32 : (npix >= 56 * wslots ? 16 : 8);
         pl.P = std::min(pl.P, pmax);
         if (ctx->pixels_per_item > 0) pl.P = std::min(std::min(32, pmax), ctx->pixels_per_item);
         pl.split = 1;
@@ -1815,6 +1887,13 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
         k_fscan<<<ctx->slots_cap, 256, 0, st>>>(pl);
         k_scatter_fine<<<nb, 256, 0, st>>>(pl, ctx->d_slots);
         ctx->launches += 3;
+        if (pruned && pl.qorder && max_items > pl.qcap) pl.qorder = nullptr;      // tiny items asked for by cledb_set_tuning
+        if (pruned && pl.qorder) {
+            const int nbi = (int)((max_items + 255) / 256);
+            k_item_weight<<<nbi, 256, 0, st>>>(pl, ctx->d_slots);
+            k_item_order<<<nbi, 256, 0, st>>>(pl);
+            ctx->launches += 2;
+        }
     } else k_scatter<<<nb, 256, 0, st>>>(pl);
     ctx->launches += 2;
     int occ = 0;
@@ -1826,8 +1905,8 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     const int grid = (int)std::min<int64_t>((int64_t)ctx->prop.multiProcessorCount * occ, std::max<int64_t>(1, (max_items + wpc - 1) / wpc));
     int pgrid = 1;
     if (pruned) {
-        if (!ctx->d_prune_stats) CLEDB_CUDA(ctx, cudaMalloc(&ctx->d_prune_stats, 16));
-        CLEDB_CUDA(ctx, cudaMemsetAsync(ctx->d_prune_stats, 0, 16, st));
+        if (!ctx->d_prune_stats) CLEDB_CUDA(ctx, cudaMalloc(&ctx->d_prune_stats, 1 << 20));
+        CLEDB_CUDA(ctx, cudaMemsetAsync(ctx->d_prune_stats, 0, ctx->dbg == 7 ? (1 << 20) : 16, st));
         const int pw = enc == CLEDB_ENC_I16 ? PCfg<CLEDB_ENC_I16>::kWpc : PCfg<CLEDB_ENC_F32>::kWpc;
         smem = (size_t)pw * (enc == CLEDB_ENC_I16 ? pruned_warp_bytes<CLEDB_ENC_I16>() : pruned_warp_bytes<CLEDB_ENC_F32>());
         if (enc == CLEDB_ENC_I16) CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_match_pruned<CLEDB_ENC_I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1916,6 +1995,8 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     const bool pruned = precision == CLEDB_PREC_FP32 && nblocked > 0;
     const size_t nfine = pruned ? (size_t)ctx->slots_cap * ftiles : 0;
     const size_t o_seed = take(pruned ? npix * kParts * 4 : 0), o_fine = take(3 * nfine * 4);
+    const size_t qcap = pruned ? (size_t)npix / 4 + pl.nkeys + 64 : 0;          // items at the smallest P, one partly filled item per bucket
+    const size_t o_wpix = take(pruned ? npix * 4 : 0), o_qbin = take(qcap * 4), o_qorder = take(qcap * 4), o_qhist = take(pruned ? 128 * 4 : 0);
     if ((rc = ensure_workspace(ctx, ctx->ws, off))) return rc;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx->ws.ptr);
     pl.key = reinterpret_cast<int32_t*>(w + o_key);
@@ -1939,6 +2020,12 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
         pl.foff = pl.fcursor + nfine;
         pl.ftiles = ftiles;                          // tiles of the largest database + one key per sign class
         CLEDB_CUDA(ctx, cudaMemsetAsync(pl.fcnt, 0, 2 * nfine * 4, st));
+        pl.wpix = reinterpret_cast<float*>(w + o_wpix);
+        pl.qbin = reinterpret_cast<int32_t*>(w + o_qbin);
+        pl.qorder = reinterpret_cast<int32_t*>(w + o_qorder);
+        pl.qhist = reinterpret_cast<int32_t*>(w + o_qhist);
+        pl.qcap = (int64_t)qcap;
+        CLEDB_CUDA(ctx, cudaMemsetAsync(pl.qhist, 0, 128 * 4, st));
     }
     if (precision == CLEDB_PREC_FP32)
         rc = run_match<CLEDB_PREC_FP32>(ctx, enc, pl, wslots, pmax, sobs, snr, db_id, idx_out, chi_out, chi64_out, kpos_out, rows_out, ncand_out, st);
