@@ -1845,10 +1845,10 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
         // or 32 pixels per item (measured on 128^2 .. 1024^2 maps: small maps need many small items to keep every warp busy
         // to the end, big maps amortise the per-item work over more pixels) - and the number of items is bounded by
         // npix/P + one partly filled item per bucket.  The call is a pure enqueue: no synchronisation, capturable in a graph.
-        pl.P = npix >= 512 * wslots ? 32 : (npix >= 48 * wslots ? 8 : 4);
-        // fused IQUD items are twice as long: fewer, larger items balance better (profiles/exp_ppi.py: 8 below 100 Ki pixels,
-        // 16 up to 400 Ki, 32 above)
-        if (pl.fused) pl.P = npix >= 225 * wslots ? 32 : (npix >= 56 * wslots ? 16 : 8);
+        pl.P = npix >= 512 * wslots ? 32 : (npix >= 64 * wslots ? 8 : 4);
+        // fused IQUD items are twice as long: fewer, larger items balance better (profiles/exp_ppi.py: 4 below 42 Ki pixels,
+        // 8 below 100 Ki, 16 up to 400 Ki, 32 above)
+        if (pl.fused) pl.P = npix >= 225 * wslots ? 32 : (npix >= 56 * wslots ? 16 : (npix >= 24 * wslots ? 8 : 4));
         pl.P = std::min(pl.P, pmax);
         if (ctx->pixels_per_item > 0) pl.P = std::min(std::min(32, pmax), ctx->pixels_per_item);
         pl.split = 1;
