@@ -25,9 +25,15 @@ for nx in (128, 256, 512, 1024):
         f(); f(); torch.cuda.synchronize()
         ctx.set_tuning(-8, 0); f(); torch.cuda.synchronize()
         ctx.profile_begin(); f(); f(); f(); k8 = float(np.mean(ctx.profile_collect()))
-        ctx.set_tuning(0, 0); f(); torch.cuda.synchronize()
-        ctx.profile_begin(); f(); f(); f(); k0 = float(np.mean(ctx.profile_collect()))
-        print('%d^2 %s kernel: items in index order %.1f us, heaviest first %.1f us' % (nx, 'IQUD' if mode else 'IQUV', k8 * 1e3, k0 * 1e3))
+        ctx.set_tuning(0, 0)
+        ks = []
+        for qs in ('0', '2', '4', '6', '8'):
+            os.environ['CLEDB_B200_QSPLIT'] = qs
+            f(); torch.cuda.synchronize()
+            ctx.profile_begin(); f(); f(); f(); ks.append(float(np.mean(ctx.profile_collect())) * 1e3)
+        os.environ.pop('CLEDB_B200_QSPLIT')
+        print('%d^2 %s kernel: items in index order %.1f us; heaviest first, heavy items in pieces from median bin + 0(never)/2/4/6/8: %s us'
+              % (nx, 'IQUD' if mode else 'IQUV', k8 * 1e3, ' '.join('%.1f' % v for v in ks)))
         ctx.set_tuning(-7, 0)
         ctx.profile_begin(); f(); kms = float(ctx.profile_collect()[0])
         buf = np.zeros(1 << 17, np.uint64)

@@ -20,6 +20,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "cledb_internal.h"
@@ -275,9 +276,12 @@ struct Plan {                 // all pointers are device pointers into the works
     // longest-items-first queue of the pruned search (NULL: items are taken in index order)
     float*   wpix;            // [npix] predicted weight of a pixel: chi^2 of the best tile representative (k_seed)
     int32_t* qbin;            // [max items] weight bin of an item
-    int32_t* qorder;          // [max items] item indices, heaviest bin first
-    int32_t* qhist;           // [64] items per bin, then [64] cursors
-    int64_t  qcap;            // capacity of qbin / qorder
+    int32_t* qorder;          // [qocap] queue entries, heaviest bin first: item | piece << 24 (piece 0 = the whole item), -1 = hole
+    int32_t* qhist;           // [64] items per bin, [64] cursors, [2] queue length and split bin
+    int64_t  qcap;            // capacity of qbin
+    int64_t  qocap;           // capacity of qorder
+    int32_t  qsplit;          // heavy items are handed out in pieces of qpiece pixels when their bin is >= median bin + qsplit (0: never)
+    int32_t  qpiece;
 };
 
 // the sign class with the most entries (ties: the lowest class)
@@ -1258,13 +1262,38 @@ __global__ void __launch_bounds__(256) k_item_weight(Plan pl, const DbSlot* __re
     pl.qbin[it] = bin;
     atomicAdd(&pl.qhist[bin], 1);
 }
+// Queue layout: bins from heavy to light; an item of a bin at least qsplit bins above the median bin (weight >= 2^(qsplit/2)
+// times the median item) is handed out in pieces of qpiece pixels - its pixels are independent, a piece is just a smaller item
+// with the same storage - so that the longest work unit of a small map is one heavy pixel, not four of them in a row.  Every
+// heavy item reserves P / qpiece entries; pieces beyond the item's pixel count stay holes (-1).
+__device__ __forceinline__ int queue_split_bin(const Plan& pl, int total_items) {
+    if (pl.qsplit <= 0) return 64;
+    int acc = 0, med = 0;
+    for (int b = 0; b < 64; ++b) { acc += pl.qhist[b]; if (2 * acc >= total_items) { med = b; break; } }
+    return min(64, med + pl.qsplit);
+}
 __global__ void __launch_bounds__(256) k_item_order(Plan pl) {
+    __shared__ int s_before[64], s_split;
+    const int total = pl.counters[2];
+    if (threadIdx.x == 0) {
+        const int sb = queue_split_bin(pl, total);
+        const int per = (pl.P + pl.qpiece - 1) / pl.qpiece;
+        s_split = sb;
+        int run = 0;
+        for (int b = 63; b >= 0; --b) { s_before[b] = run; run += pl.qhist[b] * (b >= sb ? per : 1); }    // heavier bins come first
+        if (blockIdx.x == 0) { pl.qhist[128] = run; pl.qhist[129] = sb; }
+    }
+    __syncthreads();
     const int it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= pl.counters[2]) return;
+    if (it >= total) return;
     const int bin = pl.qbin[it];
-    int before = 0;
-    for (int b = 63; b > bin; --b) before += pl.qhist[b];           // heavier bins come first
-    pl.qorder[before + atomicAdd(&pl.qhist[64 + bin], 1)] = it;
+    if (bin >= s_split) {
+        const int per = (pl.P + pl.qpiece - 1) / pl.qpiece;
+        const int pos = s_before[bin] + atomicAdd(&pl.qhist[64 + bin], per);
+        for (int c = 0; c < per; ++c) pl.qorder[pos + c] = it | ((c + 1) << 24);
+    } else {
+        pl.qorder[s_before[bin] + atomicAdd(&pl.qhist[64 + bin], 1)] = it;
+    }
 }
 
 template <int ENC> struct PCfg {        // shared memory of one warp of the pruned search: one tile in flight, <= 32 pixels
@@ -1323,16 +1352,27 @@ k_match_pruned(Plan pl, const DbSlot* __restrict__ slots, unsigned long long* __
         int it = 0;
         if (lane == 0) {
             it = atomicAdd(&pl.counters[0], 1);
-            if (it < pl.counters[2] && pl.qorder) it = pl.qorder[it];        // the queue hands the items out heaviest first
+            if (pl.qorder) it = it < pl.qhist[128] ? pl.qorder[it] : 0x7fffffff;   // the queue hands the items out heaviest first
+            else if (it >= pl.counters[2]) it = 0x7fffffff;
         }
         it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= pl.counters[2]) break;
-        const Item im = make_item(pl, slots, it);                             // items hold <= 32 pixels and whole sign classes
+        if (it == 0x7fffffff) break;
+        if (it < 0) continue;                                                 // a hole: piece of a heavy item beyond its pixels
+        const int piece = it >> 24;                                           // 0: the whole item, c: its c-th piece of qpiece pixels
+        it &= 0xffffff;
+        Item im = make_item(pl, slots, it);                                   // items hold <= 32 pixels and whole sign classes
+        int piece_j0 = 0;
+        if (piece > 0) {
+            piece_j0 = (piece - 1) * pl.qpiece;
+            if (piece_j0 >= im.npx) continue;
+            im.pix0 += piece_j0;
+            im.npx = min(pl.qpiece, im.npx - piece_j0);
+        }
         const DbSlot& db = slots[im.slot];
         unsigned long long dbg_t0 = 0, dbg_e0 = n_eval;
         int dbg_exact = 0;
         if (pl.dbg == 7) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_t0));
-        CandT* gout = reinterpret_cast<CandT*>(pl.plist) + (size_t)it * pl.P * k;
+        CandT* gout = reinterpret_cast<CandT*>(pl.plist) + ((size_t)it * pl.P + piece_j0) * k;
         // The sign classes this item searches: its own (IQUV), or - IQUD (pl.fused) - every non-empty class of the database, one
         // after the other with ONE list per pixel: the largest class first (seed tiles, thresholds close to final), so the
         // others start with tight thresholds, skip the seed pass and lose most of their tiles to the bounds at once.
@@ -1887,9 +1927,17 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
         k_fscan<<<ctx->slots_cap, 256, 0, st>>>(pl);
         k_scatter_fine<<<nb, 256, 0, st>>>(pl, ctx->d_slots);
         ctx->launches += 3;
-        if (pruned && pl.qorder && max_items > pl.qcap) pl.qorder = nullptr;      // tiny items asked for by cledb_set_tuning
+        pl.qpiece = pl.P >= 16 ? 4 : 1;
+        // pieces only on small maps and only for the items 16 x the median weight and more: single pixels lose the tile sharing of
+        // their item, so the total work grows (256^2 IQUV kernel 425 -> 387 us; from 512^2 on the queue order alone balances
+        // the load and pieces cost 5 - 10 %: profiles/r02_tuning.txt)
+        pl.qsplit = npix < 100000 ? 8 : 0;
+        if (const char* e = std::getenv("CLEDB_B200_QSPLIT")) pl.qsplit = std::atoi(e);
+        if (pruned && pl.qorder && (max_items > pl.qcap || max_items * ((pl.P + pl.qpiece - 1) / pl.qpiece) > pl.qocap || max_items >= (1 << 24)))
+            pl.qorder = nullptr;                                                  // tiny items asked for by cledb_set_tuning, huge maps
         if (pruned && pl.qorder) {
             const int nbi = (int)((max_items + 255) / 256);
+            CLEDB_CUDA(ctx, cudaMemsetAsync(pl.qorder, 0xff, (size_t)max_items * ((pl.P + pl.qpiece - 1) / pl.qpiece) * 4, st));
             k_item_weight<<<nbi, 256, 0, st>>>(pl, ctx->d_slots);
             k_item_order<<<nbi, 256, 0, st>>>(pl);
             ctx->launches += 2;
@@ -1996,7 +2044,8 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
     const size_t nfine = pruned ? (size_t)ctx->slots_cap * ftiles : 0;
     const size_t o_seed = take(pruned ? npix * kParts * 4 : 0), o_fine = take(3 * nfine * 4);
     const size_t qcap = pruned ? (size_t)npix / 4 + pl.nkeys + 64 : 0;          // items at the smallest P, one partly filled item per bucket
-    const size_t o_wpix = take(pruned ? npix * 4 : 0), o_qbin = take(qcap * 4), o_qorder = take(qcap * 4), o_qhist = take(pruned ? 128 * 4 : 0);
+    const size_t qocap = pruned ? (size_t)npix + (size_t)pl.nkeys * 32 + 64 : 0;  // every item in single-pixel pieces
+    const size_t o_wpix = take(pruned ? npix * 4 : 0), o_qbin = take(qcap * 4), o_qorder = take(qocap * 4), o_qhist = take(pruned ? 132 * 4 : 0);
     if ((rc = ensure_workspace(ctx, ctx->ws, off))) return rc;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx->ws.ptr);
     pl.key = reinterpret_cast<int32_t*>(w + o_key);
@@ -2025,7 +2074,8 @@ int match_device(cledb_ctx* ctx, int mode, int precision, int64_t npix, const fl
         pl.qorder = reinterpret_cast<int32_t*>(w + o_qorder);
         pl.qhist = reinterpret_cast<int32_t*>(w + o_qhist);
         pl.qcap = (int64_t)qcap;
-        CLEDB_CUDA(ctx, cudaMemsetAsync(pl.qhist, 0, 128 * 4, st));
+        pl.qocap = (int64_t)qocap;
+        CLEDB_CUDA(ctx, cudaMemsetAsync(pl.qhist, 0, 132 * 4, st));
     }
     if (precision == CLEDB_PREC_FP32)
         rc = run_match<CLEDB_PREC_FP32>(ctx, enc, pl, wslots, pmax, sobs, snr, db_id, idx_out, chi_out, chi64_out, kpos_out, rows_out, ncand_out, st);
