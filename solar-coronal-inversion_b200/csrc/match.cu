@@ -1127,83 +1127,100 @@ __device__ __forceinline__ int fine_key(const Plan& pl, const DbSlot& db, int ke
     return (key / kParts) * pl.ftiles + db.part_tile0[q] + q + t;
 }
 
-constexpr int kSeedCap = 2048;          // representative entries a block of k_seed stages in shared memory (40 KB)
-
+constexpr int kSeedCap = 1528;          // representative entries a block of k_seed stages in shared memory (8 floats each: 48 KB)
 constexpr int kSeedLanes = 4;           // threads that share a pixel in k_seed (each takes every 4th tile)
+constexpr int kSeedRounds = 2;          // pixels per thread quadruple: a block of 256 threads seeds 128 pixels with one staging
 
 __global__ void __launch_bounds__(256) k_seed(Plan pl, const DbSlot* __restrict__ slots) {
-    __shared__ float s_rep[kSeedCap * kNC];
-    __shared__ int s_slot;
+    __shared__ __align__(16) float4 s_rep[kSeedCap * 2];      // (r0 r1 r2 r3), (r4 - - -) per tile: two 16-byte reads per evaluation
+    __shared__ int s_slot, s_mixed;
     // pixels are taken in bucket order (k_scatter ran before): a block works on one database, mostly on one sign class
-    const int64_t ro = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kSeedLanes;
     const int sub = threadIdx.x % kSeedLanes;
     const int64_t nsearched = (int64_t)pl.off[pl.nkeys - 1] + pl.cnt[pl.nkeys - 1];
-    const int64_t p = ro < nsearched ? pl.order[ro] : -1;
-    const int key = p >= 0 ? pl.key[p] : -1;
+    const int64_t ro0 = (int64_t)blockIdx.x * (blockDim.x / kSeedLanes) * kSeedRounds + threadIdx.x / kSeedLanes;
     // the representative entries of the block's database into shared memory, if the whole block searches one database
     // (the usual case) and they fit; otherwise every thread reads them from global memory
-    if (threadIdx.x == 0) s_slot = -1;
+    if (threadIdx.x == 0) { s_slot = -1; s_mixed = 0; }
     __syncthreads();
-    if (key >= 0) atomicMax(&s_slot, key / kParts);
+    int64_t pr[kSeedRounds];
+    int keyr[kSeedRounds];
+#pragma unroll
+    for (int rd = 0; rd < kSeedRounds; ++rd) {
+        const int64_t ro = ro0 + (int64_t)rd * (blockDim.x / kSeedLanes);
+        pr[rd] = ro < nsearched ? pl.order[ro] : -1;
+        keyr[rd] = pr[rd] >= 0 ? pl.key[pr[rd]] : -1;
+        if (keyr[rd] >= 0) atomicMax(&s_slot, keyr[rd] / kParts);
+    }
     __syncthreads();
     const int bslot = s_slot;
-    const bool same = __syncthreads_and(key < 0 || key / kParts == bslot) != 0;
+#pragma unroll
+    for (int rd = 0; rd < kSeedRounds; ++rd)
+        if (keyr[rd] >= 0 && keyr[rd] / kParts != bslot) s_mixed = 1;
+    __syncthreads();
     bool staged = false;
-    if (same && bslot >= 0) {
+    if (!s_mixed && bslot >= 0) {
         const DbSlot& db = slots[bslot];
         const int nt = db.part_tile0[kParts - 1] + db.part_ntiles[kParts - 1];
         if (nt <= kSeedCap) {
-            const float* bx = db.boxes;
-            for (int i = threadIdx.x; i < nt * kNC; i += blockDim.x) s_rep[i] = __ldg(bx + (size_t)(i / kNC) * 16 + 10 + i % kNC);
+            const float4* bx = reinterpret_cast<const float4*>(db.boxes);
+            for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+                const float4 b2 = __ldg(bx + (size_t)i * 4 + 2), b3 = __ldg(bx + (size_t)i * 4 + 3);
+                s_rep[2 * i] = make_float4(b2.z, b2.w, b3.x, b3.y);
+                s_rep[2 * i + 1] = make_float4(b3.z, 0.f, 0.f, 0.f);
+            }
             staged = true;
         }
     }
     __syncthreads();
-    // the kSeedLanes threads of a pixel sit in one warp and leave together (shuffles below)
-    if (key < 0) return;
-    const DbSlot& db = slots[key / kParts];
-    const Rec<CLEDB_PREC_FP32> r = reinterpret_cast<const Rec<CLEDB_PREC_FP32>*>(pl.recs)[p];
     const uint32_t quad = 0xfu << ((threadIdx.x & 31) & ~(kSeedLanes - 1));
-    int32_t seeds[kParts];
-    for (int q = 0; q < kParts; ++q) {
-        int best_t = 0x7fffffff;
-        float best = CUDART_INF_F;
-        const bool mine = pl.mode == CLEDB_MODE_IQUV ? q == key % kParts : (pl.fused ? q == largest_class(db) : db.part_cnt[q] > 0);
-        if (mine) {
-            const int nt = db.part_ntiles[q], t0 = db.part_tile0[q];
-            if (staged) {
+    for (int rd = 0; rd < kSeedRounds; ++rd) {
+        // the kSeedLanes threads of a pixel sit in one warp and skip together (shuffles below)
+        const int64_t p = pr[rd];
+        const int key = keyr[rd];
+        if (key < 0) continue;
+        const DbSlot& db = slots[key / kParts];
+        const Rec<CLEDB_PREC_FP32> r = reinterpret_cast<const Rec<CLEDB_PREC_FP32>*>(pl.recs)[p];
+        int32_t seeds[kParts];
+        for (int q = 0; q < kParts; ++q) {
+            int best_t = 0x7fffffff;
+            float best = CUDART_INF_F;
+            const bool mine = pl.mode == CLEDB_MODE_IQUV ? q == key % kParts : (pl.fused ? q == largest_class(db) : db.part_cnt[q] > 0);
+            if (mine) {
+                const int nt = db.part_ntiles[q], t0 = db.part_tile0[q];
+                if (staged) {
 #pragma unroll 4
-                for (int t = sub; t < nt; t += kSeedLanes) {
-                    const float* sp = s_rep + (t0 + t) * kNC;
-                    const float rep[kNC] = {sp[0], sp[1], sp[2], sp[3], sp[4]};
-                    const float v = eval_fp32(rep, r.a, r.nb, r.cm);
-                    if (v < best) { best = v; best_t = t; }
-                }
-            } else {
-                const float4* bx = reinterpret_cast<const float4*>(db.boxes) + (size_t)t0 * 4;
+                    for (int t = sub; t < nt; t += kSeedLanes) {
+                        const float4 x = s_rep[2 * (t0 + t)], y = s_rep[2 * (t0 + t) + 1];
+                        const float rep[kNC] = {x.x, x.y, x.z, x.w, y.x};
+                        const float v = eval_fp32(rep, r.a, r.nb, r.cm);
+                        if (v < best) { best = v; best_t = t; }
+                    }
+                } else {
+                    const float4* bx = reinterpret_cast<const float4*>(db.boxes) + (size_t)t0 * 4;
 #pragma unroll 4
-                for (int t = sub; t < nt; t += kSeedLanes) {
-                    const float4 b2 = __ldg(bx + (size_t)t * 4 + 2), b3 = __ldg(bx + (size_t)t * 4 + 3);
-                    const float rep[kNC] = {b2.z, b2.w, b3.x, b3.y, b3.z};
-                    const float v = eval_fp32(rep, r.a, r.nb, r.cm);
-                    if (v < best) { best = v; best_t = t; }
+                    for (int t = sub; t < nt; t += kSeedLanes) {
+                        const float4 b2 = __ldg(bx + (size_t)t * 4 + 2), b3 = __ldg(bx + (size_t)t * 4 + 3);
+                        const float rep[kNC] = {b2.z, b2.w, b3.x, b3.y, b3.z};
+                        const float v = eval_fp32(rep, r.a, r.nb, r.cm);
+                        if (v < best) { best = v; best_t = t; }
+                    }
                 }
-            }
 #pragma unroll
-            for (int o = 1; o < kSeedLanes; o <<= 1) {                  // best of the pixel's threads, lowest tile on ties
-                const float ov = __shfl_xor_sync(quad, best, o);
-                const int ot = __shfl_xor_sync(quad, best_t, o);
-                if (ov < best || (ov == best && ot < best_t)) { best = ov; best_t = ot; }
+                for (int o = 1; o < kSeedLanes; o <<= 1) {                  // best of the pixel's threads, lowest tile on ties
+                    const float ov = __shfl_xor_sync(quad, best, o);
+                    const int ot = __shfl_xor_sync(quad, best_t, o);
+                    if (ov < best || (ov == best && ot < best_t)) { best = ov; best_t = ot; }
+                }
             }
+            if (best_t == 0x7fffffff) best_t = -1;
+            seeds[q] = best_t;
+            if (sub == 0) pl.seed[p * kParts + q] = best_t;
+            // the search cost of a pixel grows with its threshold, and the chi^2 of the best representative is a monotone proxy
+            // of it; the class a pixel searches first (its own for IQUV, the largest for fused IQUD) gives the weight
+            if (sub == 0 && pl.wpix && mine && (pl.mode == CLEDB_MODE_IQUV || q == largest_class(db))) pl.wpix[p] = best_t < 0 ? CUDART_INF_F : best;
         }
-        if (best_t == 0x7fffffff) best_t = -1;
-        seeds[q] = best_t;
-        if (sub == 0) pl.seed[p * kParts + q] = best_t;
-        // the search cost of a pixel grows with its threshold, and the chi^2 of the best representative is a monotone proxy of
-        // it; the class a pixel searches first (its own for IQUV, the largest for fused IQUD) gives the weight
-        if (sub == 0 && pl.wpix && mine && (pl.mode == CLEDB_MODE_IQUV || q == largest_class(db))) pl.wpix[p] = best_t < 0 ? CUDART_INF_F : best;
+        if (sub == 0) atomicAdd(&pl.fcnt[fine_key(pl, db, key, seeds)], 1);
     }
-    if (sub == 0) atomicAdd(&pl.fcnt[fine_key(pl, db, key, seeds)], 1);
 }
 
 // exclusive scan of the fine counts: one block per database slot, starting from the slot's first position in `order`
@@ -1266,21 +1283,22 @@ __global__ void __launch_bounds__(256) k_item_weight(Plan pl, const DbSlot* __re
 // times the median item) is handed out in pieces of qpiece pixels - its pixels are independent, a piece is just a smaller item
 // with the same storage - so that the longest work unit of a small map is one heavy pixel, not four of them in a row.  Every
 // heavy item reserves P / qpiece entries; pieces beyond the item's pixel count stay holes (-1).
-__device__ __forceinline__ int queue_split_bin(const Plan& pl, int total_items) {
-    if (pl.qsplit <= 0) return 64;
-    int acc = 0, med = 0;
-    for (int b = 0; b < 64; ++b) { acc += pl.qhist[b]; if (2 * acc >= total_items) { med = b; break; } }
-    return min(64, med + pl.qsplit);
-}
 __global__ void __launch_bounds__(256) k_item_order(Plan pl) {
-    __shared__ int s_before[64], s_split;
+    __shared__ int s_hist[64], s_before[64], s_split;
     const int total = pl.counters[2];
+    if (threadIdx.x < 64) s_hist[threadIdx.x] = pl.qhist[threadIdx.x];
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const int sb = queue_split_bin(pl, total);
+        int sb = 64;
+        if (pl.qsplit > 0) {
+            int acc = 0, med = 0;
+            for (int b = 0; b < 64; ++b) { acc += s_hist[b]; if (2 * acc >= total) { med = b; break; } }
+            sb = min(64, med + pl.qsplit);
+        }
         const int per = (pl.P + pl.qpiece - 1) / pl.qpiece;
         s_split = sb;
         int run = 0;
-        for (int b = 63; b >= 0; --b) { s_before[b] = run; run += pl.qhist[b] * (b >= sb ? per : 1); }    // heavier bins come first
+        for (int b = 63; b >= 0; --b) { s_before[b] = run; run += s_hist[b] * (b >= sb ? per : 1); }      // heavier bins come first
         if (blockIdx.x == 0) { pl.qhist[128] = run; pl.qhist[129] = sb; }
     }
     __syncthreads();
@@ -1923,7 +1941,7 @@ static int run_match(cledb_ctx* ctx, int enc, Plan& pl, int64_t wslots, int pmax
     k_scan<<<1, 1024, 0, st>>>(pl, ctx->d_slots);
     if (blocked) {
         k_scatter<<<nb, 256, 0, st>>>(pl);                 // bucket order first: k_seed then stages one database per block
-        k_seed<<<(int)((npix * kSeedLanes + 255) / 256), 256, 0, st>>>(pl, ctx->d_slots);
+        k_seed<<<(int)((npix + 64 * kSeedRounds - 1) / (64 * kSeedRounds)), 256, 0, st>>>(pl, ctx->d_slots);
         k_fscan<<<ctx->slots_cap, 256, 0, st>>>(pl);
         k_scatter_fine<<<nb, 256, 0, st>>>(pl, ctx->d_slots);
         ctx->launches += 3;
