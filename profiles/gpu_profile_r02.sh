@@ -11,9 +11,9 @@ cap() {  # name, kernel regex, skip, script args...
 }
 cap k_match_pruned_iquv  k_match_pruned 2 python profiles/prof_match.py iquv 256 prune
 cap k_match_pruned_iqud  k_match_pruned 2 python profiles/prof_match.py iqud 256 prune
-cap k_match_plain_iquv   '^k_match\$'   2 python profiles/prof_match.py iquv 256 brute
-cap k_match_seeded_iquv  '^k_match\$'   2 python profiles/prof_match.py iquv 256 seeded
-cap k_match_seeded_1024  '^k_match\$'   1 python profiles/prof_match.py iquv 1024 seeded
+cap k_match_plain_iquv   '^k_match$'   2 python profiles/prof_match.py iquv 256 brute
+cap k_match_seeded_iquv  '^k_match$'   2 python profiles/prof_match.py iquv 256 seeded
+cap k_match_seeded_1024  '^k_match$'   1 python profiles/prof_match.py iquv 1024 seeded
 cap k_blos               k_blos         1 python profiles/prof_elementwise.py
 cap k_qurotate           k_qurotate     1 python profiles/prof_elementwise.py
 python profiles/noise_sweep.py > $out/noise_sweep.txt 2>&1; echo "noise sweep exit $?"
