@@ -7,7 +7,8 @@ Prints ONE JSON line (rank 0).  Top level = BASELINE config 2, the configuration
 2-line Fe XIII IQUV map per GPU against one synthetic PyCELP-shaped database (340 200 entries, int16 in HBM), nsearch 8,
 through the library's default search (exact tile pruning).  A "step" is one pass of the hot path over one map (cledb_match:
 classify, bucket, chi^2 search + top-nsearch, finalise).  N > 1: every rank searches its own map (weak scaling, database
-replicated) and the result maps are all-gathered over NVLink by the library (cledb_allgather_dev, NCCL).
+replicated) and the result maps are all-gathered over NVLink by the library (cledb_allgather_dev: its own peer-memory
+stores where CUDA IPC works, else NCCL).
 
   value      pixels/s, inputs resident in HBM, CUDA events on the launching stream, L2 flushed between steps, max over ranks
   e2e        the same through the host-buffer C-ABI call (cledb_invert: H2D of the inputs, search, solutions, issue flags,
@@ -54,6 +55,9 @@ def parse():
     ap.add_argument('--ndb5', type=int, default=247, help='databases of the config-5 map (the reference notebook loads 247 for a 1024^2 map)')
     ap.add_argument('--nx5', type=int, default=1024)
     ap.add_argument('--configs', default='', help='comma list of extra configs to run (default: 2b,3,4,5 at N=1; 2b,5 at N>1)')
+    ap.add_argument('--transport', default='auto', choices=['auto', 'peer', 'nccl'],
+                    help='multi-GPU gathers: peer = the library\'s own stores into the peers\' windows (default where CUDA IPC works), nccl = ncclAllGather')
+    ap.add_argument('--no-overlap', action='store_true', help='N > 1: time search + gather back to back on one stream (no pipelining of the gather)')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dbg', type=int, default=0, help='kernel timing experiment (results invalid)')
@@ -192,6 +196,11 @@ class ClockSampler(threading.Thread):
             self.proc.terminate()
 
 
+class _DeviceBytes:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = dict(shape=(int(nbytes),), typestr='|u1', data=(int(ptr), False), version=2)
+
+
 class Bench:
     """Shared state of one rank: device, stream, context, timing helpers."""
 
@@ -213,6 +222,9 @@ class Bench:
             ids = [native.comm_unique_id() if self.rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
         self.ctx.comm_init(self.rank, self.world, ids[0])    # one rank: no NCCL involved
+        if args.transport != 'auto':
+            self.ctx.comm_transport(args.transport)
+        self.transport = self.ctx.comm_transport()           # 'peer': the library's own stores into the peers' windows; 'nccl'
         self.stream = torch.cuda.Stream(device=self.dev)     # an explicit stream: the library and the CUDA events share it
         torch.cuda.set_stream(self.stream)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)          # > 126 MB L2
@@ -250,6 +262,34 @@ class Bench:
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs], (self.ctx.profile_collect() if profile else None)
 
+    def timed_pipelined(self, search, gather, nsteps, side):
+        """K maps as a software pipeline: the gather of map i-1 (side stream) runs beside the search of map i (launching stream).
+        K + 1 brackets of CUDA events on the launching stream, L2 flushed before each (outside the events); bracket i opens, the
+        side stream waits for the opening event and gathers map i-1, the launching stream searches map i and joins the side
+        stream before the bracket closes - so every search and every gather lies inside exactly one bracket (the last bracket
+        holds the last gather alone) and nothing hides behind the untimed flush.  Returns ([sum of brackets / K], kernel ms)."""
+        torch = self.torch
+        self.ctx.profile_begin()
+        evs = []
+        for i in range(nsteps + 1):
+            self.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(self.stream)
+            join = None
+            if i > 0:
+                side.wait_event(a)
+                gather((i - 1) % 2, side.cuda_stream)
+                join = torch.cuda.Event()
+                join.record(side)
+            if i < nsteps:
+                search(i % 2)
+            if join is not None:
+                self.stream.wait_event(join)
+            b.record(self.stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [sum(a.elapsed_time(b) for a, b in evs) / nsteps], self.ctx.profile_collect()
+
     def max_over_ranks(self, x):
         if self.world == 1:
             return float(x)
@@ -266,6 +306,10 @@ class Bench:
 
     def pinned(self, a):
         return self.torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+    def view(self, ptr, nbytes):
+        """uint8 tensor over device memory the library owns (the receive window)."""
+        return self.torch.as_tensor(_DeviceBytes(ptr, nbytes), device=self.dev)
 
     def traffic_of(self, name):
         """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/kernel_traffic.json)."""
@@ -288,18 +332,29 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
     id_h = B.pinned(obs['db_enc'].reshape(-1).astype(np.int32))
     sobs_d, snr_d, id_d = sobs_h.to(B.dev), snr_h.to(B.dev), id_h.to(B.dev)
     maps_d = torch.empty((2, npix, k), dtype=torch.int32, device=B.dev)      # idx and chi side by side: one collective gathers both
-    idx_d, chi_d = maps_d[0], maps_d[1].view(torch.float32)
     kpos_d = torch.empty((npix, k), dtype=torch.int32, device=B.dev)
     rows_d = torch.empty((npix, k, 8), dtype=torch.float32, device=B.dev)
     st_d = torch.empty(npix, dtype=torch.uint8, device=B.dev)
     nc_d = torch.empty(npix, dtype=torch.int64, device=B.dev)
-    gathered = torch.empty((B.world, 2, npix, k), dtype=torch.int32, device=B.dev) if with_gather and B.world > 1 else None
+    # the gathered maps live in the library's receive window: with the peer transport every rank stores its block straight
+    # into every rank's window (k_push_block between the free / done flags), with the NCCL one it is a plain receive buffer
+    # Two sets of result maps and two receive regions: in the timed pipeline the gather of one map runs beside the search of the next.
+    map_bytes = maps_d.numel() * 4
+    gathered = ctx.comm_window(2 * B.world * map_bytes) if with_gather and B.world > 1 else None
+    maps2 = [maps_d, torch.empty_like(maps_d)] if gathered is not None else [maps_d]
+    side = torch.cuda.Stream(device=B.dev) if gathered is not None else None
 
-    def step():
-        ctx.match_dev(mode, npix, sobs_d.data_ptr(), snr_d.data_ptr(), id_d.data_ptr(), k, idx_d.data_ptr(), chi_d.data_ptr(),
+    def search(b=0):
+        ctx.match_dev(mode, npix, sobs_d.data_ptr(), snr_d.data_ptr(), id_d.data_ptr(), k, maps2[b][0].data_ptr(), maps2[b][1].data_ptr(),
                       None, kpos_d.data_ptr(), rows_d.data_ptr(), st_d.data_ptr(), nc_d.data_ptr(), B.stream.cuda_stream)
-        if gathered is not None:            # the only collective of the path: gather the result maps (library call, same stream)
-            ctx.allgather_dev(maps_d.data_ptr(), gathered.data_ptr(), maps_d.numel() * 4, B.stream.cuda_stream)
+
+    def gather(b, stream):                  # the only collective of the path: gather the result maps (library call)
+        ctx.allgather_dev(maps2[b].data_ptr(), gathered + b * B.world * map_bytes, map_bytes, stream)
+
+    def step():                             # search, then the gather on the same stream
+        search(0)
+        if gathered is not None:
+            gather(0, B.stream.cuda_stream)
 
     from cledb_b200 import synth
     hdr = synth.make_dbhdr()
@@ -339,7 +394,15 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
         mark = B.sampler.mark()
         launches0 = ctx.launch_count()
         nst = steps if pruned else max(3, min(steps, 10 if variant == 2 else 5))
-        step_ms, kern_ms = B.timed(step, nst)
+        serial_ms = None
+        if pruned and gathered is not None and not B.args.no_overlap:
+            s_ms, _ = B.timed(step, max(3, nst // 2))
+            serial_ms = B.max_over_ranks(float(np.mean(s_ms)))
+            B.barrier()
+            launches0 = ctx.launch_count()
+            step_ms, kern_ms = B.timed_pipelined(search, gather, nst, side)
+        else:
+            step_ms, kern_ms = B.timed(step, nst)
         B.barrier()
         launches = ctx.launch_count() - launches0
         stats = ctx.pruning_stats() if pruned else None
@@ -385,6 +448,12 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
                    nominal_scanned_evals_per_s=B.world * npix * float(NDB_ROWS) * max(1, ndb) / max(1, ndb) / (ms * 1e-3),
                    nominal_candidate_evals_per_s=ncand_all / (ms * 1e-3), pixels_searched=nsearched_all, gpu_launches=int(launches),
                    pruning=stats, roofline=roof, clocks=clocks)
+        if serial_ms is not None:
+            rec['gather_overlap'] = dict(ms_per_step_serial=serial_ms, value_serial=B.world * npix / (serial_ms * 1e-3),
+                                         how='ms_per_step: the gather of map i-1 runs on a second stream beside the search of map i (two sets of '
+                                             'result maps, two receive regions; every search and every gather lies inside one timed bracket, '
+                                             'the last gather in a bracket of its own).  ms_per_step_serial: search and gather back to back on '
+                                             'one stream.')
         if want_e2e and variant != 0:
             for _ in range(3):
                 e2e_step()
@@ -617,64 +686,108 @@ def bench_config5(B, nx, ndb, steps):
     tabs = [dt(t) for t in g._tables]
     g.sin_bphi, g.cos_bphi, g.sin_btheta, g.cos_btheta = (t.data_ptr() for t in tabs)
     send = torch.empty(rank_bytes, dtype=torch.uint8, device=B.dev)
-    recv = torch.empty(rank_bytes * B.world, dtype=torch.uint8, device=B.dev)
-    d_order, d_bounds = dt(order), dt(bounds)
-    f_inv = torch.empty((npix, k, 11), dtype=torch.float32, device=B.dev)
-    f_sf = torch.empty((npix, k, 8), dtype=torch.float32, device=B.dev)
-    f_st = torch.empty(npix, dtype=torch.uint8, device=B.dev)
-    f_iss = torch.empty(npix, dtype=torch.int32, device=B.dev)
     sp = send.data_ptr()
+    mlay = np.zeros(5, np.int64)
+    native.load_library().cledb_map_layout(npix, k, mlay.ctypes.data_as(ctypes.c_void_p))
+    m_inv, m_sf, m_st, m_iss, map_bytes = (int(v) for v in mlay)
+    win = ctx.comm_window(map_bytes)                        # the full maps of this rank: [invout | sfound | status | issue]
+    d_mine = dt(mine.astype(np.int32))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    parts = []
+    state = dict(recv=None, order=None, bounds=None, parts=[])
 
-    def step(record=False):
-        if record:
-            ev[0].record(B.stream)
+    def search():
         if n:
             ctx.invert_dev(native.MODE_IQUV, n, d_sobs.data_ptr(), d_snr.data_ptr(), d_ids.data_ptr(), k, d_y.data_ptr(), d_d.data_ptr(),
                            d_rc.data_ptr(), d_rs.data_ptr(), None, 0, g, 1000, 0, sp + o_inv, sp + o_sf, sp + o_st, sp + o_iss,
                            B.stream.cuda_stream)
+
+    def step_peer(record=False):
+        """search + solutions of the shard -> ONE kernel stores every record at its pixel in every rank's maps (NVLink)"""
+        if record:
+            ev[0].record(B.stream)
+        search()
+        if record:
+            ev[1].record(B.stream)
+        ctx.gather_maps_dev(npix, n, d_mine.data_ptr(), maxcount, k, sp, win, -1, B.stream.cuda_stream)
+        if record:
+            ev[2].record(B.stream)
+            torch.cuda.synchronize()
+            state['parts'].append([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), 0.0])
+
+    def step_nccl(record=False):
+        """search + solutions of the shard -> ncclAllGather of the packed records -> scatter kernel"""
+        if record:
+            ev[0].record(B.stream)
+        search()
         if record:
             ev[1].record(B.stream)
         if B.world > 1:
-            ctx.allgather_dev(sp, recv.data_ptr(), rank_bytes, B.stream.cuda_stream)
+            ctx.allgather_dev(sp, state['recv'].data_ptr(), rank_bytes, B.stream.cuda_stream)
         if record:
             ev[2].record(B.stream)
-        ctx.unshard_dev(B.world, d_bounds.data_ptr(), d_order.data_ptr(), npix, maxcount, k, recv.data_ptr() if B.world > 1 else sp,
-                        f_inv.data_ptr(), f_sf.data_ptr(), f_st.data_ptr(), f_iss.data_ptr(), B.stream.cuda_stream)
+        ctx.unshard_dev(B.world, state['bounds'].data_ptr(), state['order'].data_ptr(), npix, maxcount, k,
+                        state['recv'].data_ptr() if B.world > 1 else sp, win + m_inv, win + m_sf, win + m_st, win + m_iss, B.stream.cuda_stream)
         if record:
             ev[3].record(B.stream)
             torch.cuda.synchronize()
-            parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+            state['parts'].append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
 
-    for _ in range(3):
-        step()
-    B.barrier()
-    for _ in range(3):
-        B.flush.zero_()
-        step(record=True)                                   # where the step's time goes (search+build / all-gather / scatter)
-    B.barrier()
-    launches0 = ctx.launch_count()
+    def measure(step, nst):
+        state['parts'] = []
+        for _ in range(3):
+            step()
+        B.barrier()
+        for _ in range(3):
+            B.flush.zero_()
+            step(record=True)                               # where the step's time goes (search+build / gather / scatter)
+        B.barrier()
+        launches0 = ctx.launch_count()
+        step_ms, kern_ms = B.timed(step, nst)
+        B.barrier()
+        part = [B.max_over_ranks(float(v)) for v in np.mean(np.array(state['parts']), axis=0)]
+        return B.max_over_ranks(float(np.mean(step_ms))), kern_ms, part, ctx.launch_count() - launches0
+
     nst = max(3, min(steps, 10))
-    step_ms, kern_ms = B.timed(step, nst)
-    B.barrier()
-    launches = ctx.launch_count() - launches0
-    ms = B.max_over_ranks(float(np.mean(step_ms)))
+    peer = B.transport == 'peer'
+    nccl_rec = None
+    if not peer or B.world > 1:                             # the collective route (also measured beside the peer one when N > 1)
+        ctx.comm_transport('nccl')
+        state['recv'] = torch.empty(rank_bytes * B.world, dtype=torch.uint8, device=B.dev) if B.world > 1 else None
+        state['order'], state['bounds'] = dt(order), dt(bounds)
+        ms, kern_ms, part, launches = measure(step_nccl, nst)
+        maps_nccl = B.view(win, map_bytes).clone() if peer else None
+        nccl_rec = dict(value=npix / (ms * 1e-3), unit='pixels/s', ms_per_step=ms, steps=nst,
+                        step_breakdown_ms=dict(search_and_build=part[0], all_gather=part[1], scatter=part[2]),
+                        how='ncclAllGather of the packed records (%.0f MB into every GPU) + k_unshard' % (rank_bytes * (B.world - 1) / 1e6))
+        if peer:
+            state['recv'] = None
+    step = step_nccl
+    if peer:
+        ctx.comm_transport('peer')
+        ms, kern_ms, part, launches = measure(step_peer, nst)
+        step = step_peer
+        if nccl_rec is not None:
+            nccl_rec['same_maps_as_peer_transport'] = bool(torch.equal(maps_nccl, B.view(win, map_bytes)))
+            del maps_nccl
     stats = ctx.pruning_stats()
-    part = np.mean(np.array(parts), axis=0)
-    part = [B.max_over_ranks(float(v)) for v in part]
+    f_st = B.view(win + m_st, npix)
     nsearched = B.sum_over_ranks([int((f_st == 0).sum().item()) if B.rank == 0 else 0])[0]
+    how = ('ONE kernel (k_push_records) stores every finished record (%d B/pixel) straight at its pixel in the maps of every rank over '
+           'NVLink / NVSwitch peer memory, between two rounds of flags' if peer else
+           'one ncclAllGather of the packed finished records (%d B/pixel) -> scatter into the full maps on every rank') % (k * 76 + 5)
     rec = dict(metric='2-line pixels/s', value=npix / (ms * 1e-3), unit='pixels/s', ms_per_step=ms, steps=nst, scaling='strong',
                workload='ONE %dx%d 2-line IQUV map over %d synthetic PyCELP-shaped databases (height bands x densities; %.1f GB of float32 '
-                        'databases, %s in HBM), pixel-sharded over %d GPU(s): cledb_partition -> cledb_invert_dev on the shard -> one '
-                        'all-gather of the packed finished records (%d B/pixel) -> scatter into the full maps on every rank'
-                        % (nx, nx, ndb, ndb * NDB_ROWS * 32 / 1e9, 'int16' if B.args.encoding == 1 else 'float32', B.world, k * 76 + 5),
+                        'databases, %s in HBM), pixel-sharded over %d GPU(s): cledb_partition -> cledb_invert_dev on the shard -> %s'
+                        % (nx, nx, ndb, ndb * NDB_ROWS * 32 / 1e9, 'int16' if B.args.encoding == 1 else 'float32', B.world, how),
+               transport=B.transport,
                search='exact tile pruning (library default)', pixels_searched=nsearched, databases_on_this_rank=int(used.size),
                shard_pixels=n, gpu_launches=int(launches),
-               step_breakdown_ms=dict(search_and_build=part[0], all_gather=part[1], scatter=part[2],
-                                      note='CUDA events between the three calls of one step, max over ranks; the all-gather moves %.0f MB '
-                                           'into every GPU' % (rank_bytes * (B.world - 1) / 1e6)),
+               step_breakdown_ms=dict(search_and_build=part[0], gather=part[1], scatter=part[2],
+                                      note='CUDA events between the calls of one step, max over ranks; every GPU receives %.0f MB of '
+                                           'records from its peers' % ((npix - n) * (k * 76 + 5) / 1e6)),
                search_kernel_ms=float(np.mean(kern_ms)) if len(kern_ms) else None, pruning=stats, setup_seconds=setup_s)
+    if nccl_rec is not None and peer:
+        rec['nccl_transport'] = nccl_rec
     # the same step with the brute-force search (k-d layout, seeded: every (pixel, entry) pair evaluated - the FP32-bound kernel)
     ctx.set_pruning(2)
     for _ in range(2):
@@ -713,7 +826,8 @@ def bench_config5(B, nx, ndb, steps):
                       api='cledb_invert_sharded (C-ABI, collective): every rank uploads its shard, rank 0 receives the full invout / sfound '
                           'maps in pinned host memory (%.0f MB over one PCIe link)' % (npix * (k * 76 + 5) / 1e6))
     if B.rank == 0:
-        same = bool(np.array_equal(out['invout'], f_inv.cpu().numpy(), equal_nan=True))
+        f_inv = B.view(win + m_inv, npix * k * 44).cpu().numpy().view(np.float32).reshape(npix, k, 11)
+        same = bool(np.array_equal(out['invout'].reshape(npix, k, 11), f_inv, equal_nan=True))
         rec['e2e']['same_maps_as_device_path'] = same
     for j in range(used.size):
         ctx.db_drop(j)
@@ -777,15 +891,21 @@ def main():
         dtype='f32', data='synthetic',
         config=dict(workload=main_rec['workload'], db_encoding='int16' if args.encoding == 1 else 'float32',
                     parallelism=('pixel-sharded x%d (one map per rank), database replicated, one all-gather of the idx/chi maps by the '
-                                 'library (cledb_allgather_dev, NCCL over NVLink)' % world) if world > 1 else 'single GPU',
+                                 'library (cledb_allgather_dev: %s)'
+                                 % (world, 'every rank stores its block straight into every rank\'s window over NVLink / NVSwitch peer '
+                                           'memory, k_push_block between two rounds of flags' if B.transport == 'peer' else
+                                    'ncclAllGather over NVLink')) if world > 1 else 'single GPU',
+                    transport=B.transport if world > 1 else None,
                     search=main_rec['search'],
                     l2='flushed between timed steps (256 MiB memset, outside the per-step CUDA events)',
-                    timing='CUDA events per step on the launching stream, mean of K, max over ranks'),
+                    timing='CUDA events per step on the launching stream, mean of K, max over ranks' +
+                           ('; the gather of map i-1 (second stream) overlaps the search of map i, every gather joined inside a timed '
+                            'bracket (gather_overlap.ms_per_step_serial = without the overlap)' if main_rec.get('gather_overlap') else '')),
         evals_per_s=main_rec['evals_per_s'], evals_definition=main_rec['evals_definition'],
         nominal_scanned_evals_per_s=main_rec['nominal_scanned_evals_per_s'],
         nominal_candidate_evals_per_s=main_rec['nominal_candidate_evals_per_s'],
         pixels_searched=main_rec['pixels_searched'], gpu_launches=main_rec['gpu_launches'], pruning=main_rec['pruning'],
-        e2e=main_rec.get('e2e'), roofline=main_rec['roofline'], clocks=clocks,
+        e2e=main_rec.get('e2e'), roofline=main_rec['roofline'], clocks=clocks, gather_overlap=main_rec.get('gather_overlap'),
         device=dict(sm_count=B.props['sm_count'], match_ctas_per_sm=B.props['match_ctas_per_sm'], match_regs=B.props['match_regs'],
                     match_smem=B.props['match_smem']),
         by_config=by)

@@ -178,7 +178,7 @@ int cledb_pruning_stats(cledb_ctx* ctx, int64_t evaluated[2]);
  *     512  = Van-Vleck proximity of the LAST solution (53 deg <= vartheta_B <= 56 deg; `flg = 0` sits inside the reference's
  *            loop over solutions, :324, so only slot nsearch-1 decides), evaluated in float64
  *     1024 = chi^2 of the best solution > 10 (:351)          2048 = snr[p,0] < 1 (:353)
- *     1    = vartheta_B lies within 1e-3 deg of 53 or 56: the reference evaluates the chain in float32 with the caller's
+ *     1    = vartheta_B lies within 2e-3 deg of 53 or 56: the reference evaluates the chain in float32 with the caller's
  *            NumPy, whose last bits decide such a pixel - the binding re-evaluates those (about 1 pixel in 50 000)
  *   The binding ORs (issue_out[p] & ~1) into both lines of its issuemask: a code already set is not added twice. */
 typedef struct cledb_dbgrid {
@@ -248,8 +248,22 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  *                          broadcast, MPI, a file ...)
  *   cledb_comm_init        collective over all ranks; nranks == 1 needs no id and no NCCL
  *   cledb_comm_info        info[0]=rank, [1]=nranks, [2]=NCCL version code, [3]=1 if an NCCL communicator is live
+ *   cledb_comm_transport   how the gathers move data.  1 = PEER MEMORY (default where it works): cledb_comm_init maps a small flag
+ *                          array of every rank into every process with CUDA IPC, cledb_comm_window does the same for the
+ *                          receive window, and the gather is the library's own kernel storing each record once, straight at
+ *                          its place in every rank's window over NVLink / NVSwitch, bracketed by two rounds of flags
+ *                          (free / done epochs, st.release.sys / ld.acquire.sys) - no staging copy, no scatter pass.
+ *                          0 = ncclAllGather into a receive buffer + k_unshard.  want = -1 queries; *active receives the
+ *                          transport in effect.  Asking for 1 where IPC is unavailable returns CLEDB_ERR_COMM and the reason.
+ *                          Every rank must use the same transport (CLEDB_B200_PEER=0 in the environment starts with NCCL).
+ *   cledb_comm_window      collective: the receive window of this rank holds at least `bytes` bytes (device memory, 256-byte
+ *                          aligned; re-allocated and re-mapped on every rank when it has to grow - earlier pointers and
+ *                          contents are then gone).  One window per communicator; cledb_invert_sharded keeps its full maps at
+ *                          the start of the same window.
  *   cledb_allgather_dev    every rank contributes `bytes` bytes at `send`; `recv` receives nranks*bytes in rank order
- *                          (device pointers, enqueued on the stream: ncclAllGather over NVLink / NVSwitch)
+ *                          (device pointers, enqueued on the stream).  `recv` inside the window + peer transport (bytes and
+ *                          pointers multiples of 16): every rank stores its block into every rank's window (k_push_block);
+ *                          otherwise ncclAllGather over NVLink / NVSwitch
  *   cledb_partition        pixels ordered by key[p] in 0..nkeys-1 (stable; the binding passes db_enc) and cut into nranks
  *                          contiguous ranges of equal total weight (weight_of_key[key]: rows of that database, NULL = 1):
  *                          order_out[npix], bounds_out[nranks+1]; rank r owns order_out[bounds[r] : bounds[r+1]], so it
@@ -261,17 +275,26 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  *   cledb_unshard_dev      scatters the gathered records of all ranks to their pixels: recv[nranks][layout] ->
  *                          invout[npix,k,11], sfound[npix,k,8], status[npix], issue[npix] (device pointers; status and
  *                          issue may be NULL)
+ *   cledb_map_layout       byte offsets of the full maps of npix pixels inside the window: layout[0..3] = invout[npix,k,11],
+ *                          sfound[npix,k,8], status[npix], issue[npix] int32; layout[4] = bytes
+ *   cledb_gather_maps_dev  peer transport: the all-gather and the scatter in ONE kernel (k_push_records).  This rank's packed
+ *                          records (`send`, cledb_shard_layout of maxcount) of its nlocal pixels my_order_dev[nlocal] (their
+ *                          flat indices in the map) are stored at their pixels' places in the maps block `maps` (a pointer
+ *                          into the local window, the same offset on every rank) of every rank (root < 0) or of `root`
+ *                          only.  When the call's work has run on the stream, every record of every rank is in place.
  *   cledb_invert_sharded   cledb_invert for one map of npix pixels over all ranks: every rank passes the inputs of ITS
  *                          nlocal pixels (those of order[bounds[rank] : bounds[rank+1]], in that order; db_id = the ids
  *                          under which this rank put their databases), searches and builds them, writes the packed
- *                          records into the send buffer; ONE all-gather; ranks with root < 0 or root == rank scatter the
- *                          records to their pixels and receive the full maps invout[npix,k,11] ... in their host buffers
- *                          (the others may pass NULL outputs).  Collective: every rank must call it. */
+ *                          records into the send buffer; then cledb_gather_maps_dev (peer transport) or ONE ncclAllGather +
+ *                          k_unshard; ranks with root < 0 or root == rank receive the full maps invout[npix,k,11] ... in
+ *                          their host buffers (the others may pass NULL outputs).  Collective: every rank must call it. */
 #define CLEDB_COMM_ID_BYTES 128
 int cledb_comm_unique_id(void* id128);
 int cledb_comm_init(cledb_ctx* ctx, int rank, int nranks, const void* id128);
 int cledb_comm_destroy(cledb_ctx* ctx);
 int cledb_comm_info(cledb_ctx* ctx, int32_t info[4]);
+int cledb_comm_transport(cledb_ctx* ctx, int want, int32_t* active);
+int cledb_comm_window(cledb_ctx* ctx, int64_t bytes, void** ptr_out);
 int cledb_allgather_dev(cledb_ctx* ctx, const void* send, void* recv, int64_t bytes, void* stream);
 int cledb_partition(int64_t npix, const int32_t* key, int nkeys, const double* weight_of_key, int nranks,
                     int32_t* order_out, int64_t* bounds_out);
@@ -279,6 +302,9 @@ int cledb_shard_layout(int64_t maxcount, int nsearch, int64_t layout[5]);
 int cledb_unshard_dev(cledb_ctx* ctx, int nranks, const int64_t* bounds_dev, const int32_t* order_dev, int64_t npix,
                       int64_t maxcount, int nsearch, const void* recv, float* invout, float* sfound, uint8_t* status,
                       int32_t* issue, void* stream);
+int cledb_map_layout(int64_t npix, int nsearch, int64_t layout[5]);
+int cledb_gather_maps_dev(cledb_ctx* ctx, int64_t npix, int64_t nlocal, const int32_t* my_order_dev, int64_t maxcount,
+                          int nsearch, const void* send, void* maps, int root, void* stream);
 int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int64_t nlocal,
                          const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
                          const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,

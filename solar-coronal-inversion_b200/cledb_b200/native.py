@@ -66,7 +66,11 @@ SIGNATURES = {
     'cledb_comm_init': (_c.c_int, [_P, _c.c_int, _c.c_int, _P]),
     'cledb_comm_destroy': (_c.c_int, [_P]),
     'cledb_comm_info': (_c.c_int, [_P, _P]),
+    'cledb_comm_transport': (_c.c_int, [_P, _c.c_int, _P]),
+    'cledb_comm_window': (_c.c_int, [_P, _c.c_int64, _c.POINTER(_P)]),
     'cledb_allgather_dev': (_c.c_int, [_P, _P, _P, _c.c_int64, _P]),
+    'cledb_map_layout': (_c.c_int, [_c.c_int64, _c.c_int, _P]),
+    'cledb_gather_maps_dev': (_c.c_int, [_P, _c.c_int64, _c.c_int64, _P, _c.c_int64, _c.c_int, _P, _P, _c.c_int, _P]),
     'cledb_partition': (_c.c_int, [_c.c_int64, _P, _c.c_int, _P, _c.c_int, _P, _P]),
     'cledb_shard_layout': (_c.c_int, [_c.c_int64, _c.c_int, _P]),
     'cledb_unshard_dev': (_c.c_int, [_P, _c.c_int, _P, _P, _c.c_int64, _c.c_int64, _c.c_int, _P, _P, _P, _P, _P, _P]),
@@ -233,7 +237,7 @@ pinned = PinnedPool()
 
 def issue_codes(codes, invout=None):
     """Issue codes 512 / 1024 / 2048 of cledb_invproc (CLEDB_PROC.py:347-355) per pixel from the device's ``issue_out[npix]``
-    (see cledb_invert in the header).  Pixels whose Van-Vleck angle lies within 1e-3 deg of a limit (bit 0) are re-evaluated
+    (see cledb_invert in the header).  Pixels whose Van-Vleck angle lies within 2e-3 deg of a limit (bit 0) are re-evaluated
     with NumPy from ``invout[npix,k,11]`` - the reference's own float32 chain decides those."""
     from . import solution
     amb = np.flatnonzero(codes & 1)
@@ -539,8 +543,29 @@ class Context:
         self._check(self.lib.cledb_comm_info(self.h, _ptr(v)))
         return dict(rank=int(v[0]), nranks=int(v[1]), nccl_version=int(v[2]), nccl=bool(v[3]))
 
+    def comm_transport(self, want=None):
+        """The transport of the gathers: ``'peer'`` (the library's own stores into the peers' windows over NVLink - default where
+        CUDA IPC works) or ``'nccl'``.  ``want``: ``None`` queries, else one of the two names; every rank must ask for the same.
+        Raises ``CledbError`` with the reason when peer memory is asked for and not available."""
+        code = -1 if want is None else {'nccl': 0, 'peer': 1}[want]
+        act = ctypes.c_int32(-1)
+        self._check(self.lib.cledb_comm_transport(self.h, code, ctypes.byref(act)))
+        return 'peer' if act.value == 1 else 'nccl'
+
+    def comm_window(self, nbytes):
+        """Collective: device address of this rank's receive window of at least ``nbytes`` bytes (valid until a later call
+        asks for more; ``invert_sharded`` uses the start of the same window)."""
+        p = ctypes.c_void_p()
+        self._check(self.lib.cledb_comm_window(self.h, int(nbytes), ctypes.byref(p)))
+        return p.value
+
     def allgather_dev(self, send_ptr, recv_ptr, nbytes, stream=None):
         self._check(self.lib.cledb_allgather_dev(self.h, send_ptr, recv_ptr, int(nbytes), stream))
+
+    def gather_maps_dev(self, npix, nlocal, my_order_ptr, maxcount, nsearch, send_ptr, maps_ptr, root=-1, stream=None):
+        """cledb_gather_maps_dev (peer transport): all-gather + scatter of the packed records in one kernel."""
+        self._check(self.lib.cledb_gather_maps_dev(self.h, int(npix), int(nlocal), my_order_ptr, int(maxcount), int(nsearch), send_ptr,
+                                                   maps_ptr, int(root), stream))
 
     def unshard_dev(self, nranks, bounds_ptr, order_ptr, npix, maxcount, nsearch, recv_ptr, invout_ptr, sfound_ptr, status_ptr,
                     issue_ptr, stream=None):

@@ -71,11 +71,232 @@ bool load_nccl() {
 std::string nccl_text(int rc) { return g_nccl.error_string ? g_nccl.error_string(rc) : ("NCCL error " + std::to_string(rc)); }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------------
+// peer memory: every rank's window mapped into every process (CUDA IPC), collectives as plain stores over NVLink
+// ------------------------------------------------------------------------------------------------------
+// NCCL's all-gather costs the path three passes over the finished maps: k_build writes the packed records, NCCL copies
+// them into every rank's receive buffer, k_unshard reads that buffer and writes the maps.  With the maps of every rank
+// mapped into every process the push kernels below store each record ONCE, straight at its pixel's place in every rank's
+// maps (16-byte vectors, whole rows, NVLink / NVSwitch as the store target), and the only things left of the collective
+// are two rounds of flags:
+//   free[e]  "my window may be overwritten by operation e"      sent when a rank's stream reaches operation e
+//   done[e]  "all my stores of operation e have been performed" sent by the last block of the push kernel
+// Flags are 32-bit epochs in a small IPC allocation of their own; every rank writes its own slot in every peer's array
+// (st.release.sys after __threadfence_system) and spins on its local array (ld.acquire.sys).  Collective calls come in the
+// same order on every rank, so the host-side epoch counters agree without any exchange.
+constexpr int kMaxRanks = 16;
+constexpr int kFlagFree = 0, kFlagDone = 32, kFlagCount = 64, kFlagWords = 128;      // word offsets inside the flag array
+constexpr long long kSpinLimitNs = 20LL * 1000 * 1000 * 1000;                         // a peer that never arrives: give up, report
+
+struct Peers {
+    unsigned char* base[kMaxRanks];     // window of rank r as seen from this process (base[me] = the local allocation)
+    unsigned*      flags[kMaxRanks];    // flag array of rank r
+    int n, me;
+};
+
 struct cledb_comm {
     NcclComm comm = nullptr;
     int rank = 0, nranks = 1;
-    Workspace send, recv, full, order;          // device: packed records of this rank, of every rank, full maps, pixel order
+    Workspace send, order, scratch;             // device: packed records of this rank, pixel order + bounds, small exchange buffer
+    Workspace recv;                             // NCCL transport only: packed records of every rank
+    // peer transport
+    bool peer_ok = false;                       // flag arrays of all ranks are mapped: windows can be exchanged
+    int transport = 0;                          // 0 = NCCL collectives, 1 = stores into the peers' windows
+    std::string peer_why;                       // why peer_ok is false
+    Peers peers;                                // window bases (null until cledb_comm_window) and flag arrays
+    unsigned* flags_local = nullptr;
+    void* flags_opened[kMaxRanks] = {};         // what cudaIpcOpenMemHandle returned (block bases), for cudaIpcCloseMemHandle
+    void* win_opened[kMaxRanks] = {};
+    void* win = nullptr;                        // local window (plain allocation when peer_ok is false)
+    std::vector<size_t> win_bytes;              // size of every rank's window, tracked identically on all ranks
+    unsigned epoch = 0;
 };
+
+namespace {
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ long long now_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// thread r < n waits until rank r's slot of the local flag array has reached `epoch` (wrap-safe); a peer that does not
+// arrive within kSpinLimitNs leaves code 2 in the context's mapped error word instead of hanging the GPU
+__device__ __forceinline__ void wait_flags(const Peers& P, int which, unsigned epoch, int32_t* err_mapped) {
+    if ((int)threadIdx.x < P.n) {
+        const unsigned* f = P.flags[P.me] + which + threadIdx.x;
+        const long long t0 = now_ns();
+        while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+            __nanosleep(64);
+            if (now_ns() - t0 > kSpinLimitNs) { if (err_mapped) *err_mapped = 2; break; }
+        }
+    }
+}
+__device__ __forceinline__ void signal_flags(const Peers& P, int which, unsigned epoch) {
+    if ((int)threadIdx.x < P.n) st_release_sys(P.flags[threadIdx.x] + which + P.me, epoch);
+}
+// every thread has fenced its stores; the block that arrives last at the counter tells every peer that this rank is done
+__device__ __forceinline__ void block_done(const Peers& P, unsigned epoch) {
+    __shared__ int last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(P.flags[P.me] + kFlagCount, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) P.flags[P.me][kFlagCount] = 0;
+        __threadfence_system();
+        signal_flags(P, kFlagDone, epoch);
+    }
+}
+
+__global__ void k_peer_signal(Peers P, int which, unsigned epoch) {
+    __threadfence_system();
+    signal_flags(P, which, epoch);
+}
+__global__ void k_peer_wait(Peers P, int which, unsigned epoch, int32_t* err_mapped) { wait_flags(P, which, epoch, err_mapped); }
+
+// all-gather of contiguous blocks: the 16-byte vectors of this rank's block go to the same place of every rank's window
+__global__ void __launch_bounds__(512) k_push_block(Peers P, const uint4* __restrict__ send, size_t nvec, size_t dst_off, unsigned epoch,
+                                                    int32_t* err_mapped) {
+    wait_flags(P, kFlagFree, epoch, err_mapped);
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const uint4 v = __ldcs(send + i);
+        for (int q = 0; q < P.n; ++q) {
+            int r = P.me + 1 + q + (int)(blockIdx.x % (unsigned)P.n);      // blocks start at different peers
+            r %= P.n;
+            reinterpret_cast<uint4*>(P.base[r] + dst_off)[i] = v;
+        }
+    }
+    block_done(P, epoch);
+}
+}  // namespace
+
+static int ensure_err_word(cledb_ctx* ctx) {
+    if (!ctx->h_err) {
+        CLEDB_CUDA(ctx, cudaHostAlloc(&ctx->h_err, 64, cudaHostAllocMapped));
+        std::memset(ctx->h_err, 0, 64);
+        CLEDB_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_err_mapped, ctx->h_err, 0));
+    }
+    return CLEDB_OK;
+}
+static inline int32_t* comm_err_word(cledb_ctx* ctx) { return ctx->d_err_mapped ? ctx->d_err_mapped + 1 : nullptr; }
+
+// `bytes` per rank from `mine` (host) to `all` (host, nranks * bytes) through the communicator; doubles as a barrier
+static int exchange_host(cledb_ctx* ctx, const void* mine, void* all, size_t bytes) {
+    cledb_comm* c = ctx->comm;
+    if (c->nranks == 1) { std::memcpy(all, mine, bytes); return CLEDB_OK; }
+    int rc;
+    if ((rc = ensure_workspace(ctx, c->scratch, bytes * ((size_t)c->nranks + 1)))) return rc;
+    unsigned char* d = reinterpret_cast<unsigned char*>(c->scratch.ptr);
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int nrc = g_nccl.all_gather(d, d + bytes, bytes, kNcclUint8, c->comm, ctx->stream);
+    if (nrc != 0) { ctx->err = "ncclAllGather: " + nccl_text(nrc); return CLEDB_ERR_COMM; }
+    CLEDB_CUDA(ctx, cudaMemcpyAsync(all, d + bytes, bytes * (size_t)c->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    CLEDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CLEDB_OK;
+}
+
+// cudaMalloc may carve a small allocation out of a larger block, and an IPC handle always names the whole block: export
+// the block's base and ship the offset of `mine` inside it (cuMemGetAddressRange through the runtime's driver entry points).
+static void base_of(void* p, void** base, size_t* offset) {
+    typedef int (*fn_range)(unsigned long long*, size_t*, unsigned long long);
+    static fn_range range = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            range = (fn_range)f;
+        else
+            cudaGetLastError();
+    }
+    *base = p;
+    *offset = 0;
+    unsigned long long b = 0;
+    size_t sz = 0;
+    if (range && range(&b, &sz, (unsigned long long)(uintptr_t)p) == 0 && b) {
+        *base = (void*)(uintptr_t)b;
+        *offset = (size_t)((uintptr_t)p - (uintptr_t)b);
+    }
+}
+
+// Maps the `mine` allocation of every rank into this process: out[r] (out[me] = mine), opened[r] = what cudaIpcCloseMemHandle
+// wants back.  Collective.  Every rank stamps the first word of its allocation and reads the stamps of the others through the
+// new mappings (word at stamp_off); ok = 0 on return (with CLEDB_OK) when some rank could not export, open or verify: every rank then closes
+// what it opened.
+static int map_peers(cledb_ctx* ctx, void* mine, size_t stamp_off, void** out, void** opened, int* ok, std::string* why) {
+    cledb_comm* c = ctx->comm;
+    const int R = c->nranks, me = c->rank;
+    for (int r = 0; r < R; ++r) out[r] = opened[r] = nullptr;
+    out[me] = mine;
+    *ok = 1;
+    if (R == 1) return CLEDB_OK;
+    struct Msg { cudaIpcMemHandle_t h; unsigned long long offset; int good; int pad; };
+    Msg m;
+    std::memset(&m, 0, sizeof(m));
+    void* base = nullptr;
+    size_t offset = 0;
+    base_of(mine, &base, &offset);
+    m.offset = offset;
+    const unsigned stamp = 0xC1EDB000u + (unsigned)me;
+    cudaError_t e = cudaMemcpy(reinterpret_cast<unsigned char*>(mine) + stamp_off, &stamp, 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&m.h, base);
+    m.good = e == cudaSuccess;
+    if (!m.good) { *why = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); }
+    std::vector<Msg> all((size_t)R);
+    int rc;
+    if ((rc = exchange_host(ctx, &m, all.data(), sizeof(Msg)))) return rc;
+    int good = 1;
+    for (int r = 0; r < R; ++r) good &= all[(size_t)r].good;
+    if (!good && why->empty()) *why = "another rank could not export its memory (CUDA IPC)";
+    if (good)
+        for (int r = 0; r < R; ++r) {
+            if (r == me) continue;
+            e = cudaIpcOpenMemHandle(&opened[r], all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                *why = "cudaIpcOpenMemHandle (rank " + std::to_string(r) + "): " + cudaGetErrorString(e);
+                cudaGetLastError();
+                opened[r] = nullptr;
+                good = 0;
+                break;
+            }
+            out[r] = reinterpret_cast<unsigned char*>(opened[r]) + all[(size_t)r].offset;
+            unsigned seen = 0;
+            e = cudaMemcpy(&seen, reinterpret_cast<unsigned char*>(out[r]) + stamp_off, 4, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess || seen != 0xC1EDB000u + (unsigned)r) {
+                *why = "the mapping of rank " + std::to_string(r) + "'s memory does not show that rank's stamp" +
+                       (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : std::string());
+                cudaGetLastError();
+                good = 0;
+                break;
+            }
+        }
+    // second round: did every rank open and verify every handle?
+    std::vector<int> oks((size_t)R);
+    if ((rc = exchange_host(ctx, &good, oks.data(), sizeof(int)))) return rc;
+    for (int r = 0; r < R; ++r) good &= oks[(size_t)r];
+    if (!good) {
+        if (why->empty()) *why = "another rank could not map this rank's memory (CUDA IPC)";
+        for (int r = 0; r < R; ++r) {
+            if (r != me && opened[r]) cudaIpcCloseMemHandle(opened[r]);
+            if (r != me) out[r] = opened[r] = nullptr;
+        }
+        *ok = 0;
+    }
+    return CLEDB_OK;
+}
+
+static void unmap_peers(cledb_comm* c, void** opened) {
+    for (int r = 0; r < c->nranks; ++r)
+        if (r != c->rank && opened[r]) { cudaIpcCloseMemHandle(opened[r]); opened[r] = nullptr; }
+}
 
 extern "C" int cledb_comm_unique_id(void* id128) {
     if (!id128) return CLEDB_ERR_ARG;
@@ -90,12 +311,19 @@ extern "C" int cledb_comm_unique_id(void* id128) {
 
 extern "C" int cledb_comm_init(cledb_ctx* ctx, int rank, int nranks, const void* id128) {
     if (!ctx) return CLEDB_ERR_ARG;
-    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !id128)) { ctx->err = "cledb_comm_init: bad rank / nranks / id"; return CLEDB_ERR_ARG; }
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks || (nranks > 1 && !id128)) {
+        ctx->err = "cledb_comm_init: bad rank / nranks (1..16) / id";
+        return CLEDB_ERR_ARG;
+    }
     if (ctx->comm) { ctx->err = "cledb_comm_init: the context already has a communicator (cledb_comm_destroy it first)"; return CLEDB_ERR_ARG; }
     CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
     cledb_comm* c = new cledb_comm();
     c->rank = rank;
     c->nranks = nranks;
+    std::memset(&c->peers, 0, sizeof(c->peers));
+    c->peers.n = nranks;
+    c->peers.me = rank;
+    c->win_bytes.assign((size_t)nranks, 0);
     if (nranks > 1) {
         if (!load_nccl()) { ctx->err = "cledb_comm_init: " + g_nccl.err; delete c; return CLEDB_ERR_COMM; }
         NcclId id;
@@ -104,7 +332,42 @@ extern "C" int cledb_comm_init(cledb_ctx* ctx, int rank, int nranks, const void*
         if (rc != 0) { ctx->err = "cledb_comm_init: ncclCommInitRank: " + nccl_text(rc); delete c; return CLEDB_ERR_COMM; }
     }
     ctx->comm = c;
+    // flag arrays: zeroed, then mapped everywhere (the exchange inside map_peers is the barrier between the two)
+    int rc = ensure_err_word(ctx);
+    if (rc == CLEDB_OK && cudaMalloc(&c->flags_local, kFlagWords * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); rc = CLEDB_ERR_NOMEM; ctx->err = "cledb_comm_init: out of device memory"; }
+    if (rc == CLEDB_OK) {
+        cudaMemset(c->flags_local, 0, kFlagWords * sizeof(unsigned));
+        cudaDeviceSynchronize();
+        const char* env = std::getenv("CLEDB_B200_PEER");
+        void* fl[kMaxRanks];
+        int ok = 0;
+        rc = map_peers(ctx, c->flags_local, (kFlagWords - 1) * sizeof(unsigned), fl, c->flags_opened, &ok, &c->peer_why);
+        if (rc == CLEDB_OK) {
+            for (int r = 0; r < nranks; ++r) c->peers.flags[r] = reinterpret_cast<unsigned*>(fl[r]);
+            c->peer_ok = ok != 0;
+            c->transport = c->peer_ok && !(env && env[0] == '0') ? 1 : 0;
+        }
+    }
+    if (rc != CLEDB_OK) { cledb_comm_destroy(ctx); return rc; }
     return CLEDB_OK;
+}
+
+// everything enqueued has run on every rank
+static int comm_quiesce(cledb_ctx* ctx) {
+    cudaDeviceSynchronize();
+    int one = 1;
+    std::vector<int> all((size_t)ctx->comm->nranks);
+    return exchange_host(ctx, &one, all.data(), sizeof(int));
+}
+
+static void release_window(cledb_ctx* ctx) {
+    cledb_comm* c = ctx->comm;
+    unmap_peers(c, c->win_opened);
+    for (int r = 0; r < c->nranks; ++r) c->peers.base[r] = nullptr;
+    if (c->nranks > 1 && c->comm) comm_quiesce(ctx);      // nobody still holds a mapping of what is freed next
+    if (c->win) cudaFree(c->win);
+    c->win = nullptr;
+    std::fill(c->win_bytes.begin(), c->win_bytes.end(), (size_t)0);
 }
 
 extern "C" int cledb_comm_destroy(cledb_ctx* ctx) {
@@ -112,9 +375,14 @@ extern "C" int cledb_comm_destroy(cledb_ctx* ctx) {
     cledb_comm* c = ctx->comm;
     if (!c) return CLEDB_OK;
     cudaSetDevice(ctx->device);
-    cudaDeviceSynchronize();
+    if (c->nranks > 1 && c->comm) comm_quiesce(ctx);
+    else cudaDeviceSynchronize();
+    release_window(ctx);
+    unmap_peers(c, c->flags_opened);
+    if (c->nranks > 1 && c->comm) comm_quiesce(ctx);
+    if (c->flags_local) cudaFree(c->flags_local);
     if (c->comm) g_nccl.comm_destroy(c->comm);
-    for (Workspace* w : {&c->send, &c->recv, &c->full, &c->order})
+    for (Workspace* w : {&c->send, &c->recv, &c->order, &c->scratch})
         if (w->ptr) cudaFree(w->ptr);
     delete c;
     ctx->comm = nullptr;
@@ -132,6 +400,91 @@ extern "C" int cledb_comm_info(cledb_ctx* ctx, int32_t info[4]) {
     return CLEDB_OK;
 }
 
+extern "C" int cledb_comm_transport(cledb_ctx* ctx, int want, int32_t* active) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    cledb_comm* c = ctx->comm;
+    if (!c) { ctx->err = "cledb_comm_transport: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
+    if (want < -1 || want > 1) { ctx->err = "cledb_comm_transport: want must be -1 (query), 0 (NCCL) or 1 (peer memory)"; return CLEDB_ERR_ARG; }
+    if (want == 1 && !c->peer_ok) {
+        ctx->err = "cledb_comm_transport: peer memory is not available: " + (c->peer_why.empty() ? std::string("unknown reason") : c->peer_why);
+        if (active) *active = c->transport;
+        return CLEDB_ERR_COMM;
+    }
+    if (want == 0 && c->nranks > 1 && !c->comm) { ctx->err = "cledb_comm_transport: no NCCL communicator"; return CLEDB_ERR_COMM; }
+    if (want >= 0) c->transport = want;
+    if (active) *active = c->transport;
+    return CLEDB_OK;
+}
+
+// The window of rank r must hold need[r] bytes.  Collective (the sizes are tracked identically on every rank, so either all
+// ranks re-allocate or none does); the contents do not survive a re-allocation.
+static int ensure_window(cledb_ctx* ctx, const size_t* need) {
+    cledb_comm* c = ctx->comm;
+    const int R = c->nranks, me = c->rank;
+    bool grow = c->win == nullptr;
+    for (int r = 0; r < R; ++r) grow = grow || c->win_bytes[(size_t)r] < need[r];
+    if (!grow) return CLEDB_OK;
+    int rc;
+    if (R > 1 && (rc = comm_quiesce(ctx))) return rc;
+    release_window(ctx);
+    const size_t mine = std::max<size_t>(need[me], 256);
+    void* p = nullptr;
+    const cudaError_t e = cudaMalloc(&p, mine);
+    int good = e == cudaSuccess;
+    if (!good) cudaGetLastError();
+    std::vector<int> oks((size_t)R);
+    if ((rc = exchange_host(ctx, &good, oks.data(), sizeof(int)))) { if (p) cudaFree(p); return rc; }
+    for (int r = 0; r < R; ++r) good &= oks[(size_t)r];
+    if (!good) {
+        if (p) cudaFree(p);
+        ctx->err = "cledb_comm_window: out of device memory on some rank (" + std::to_string(mine >> 20) + " MiB asked here)";
+        return CLEDB_ERR_NOMEM;
+    }
+    c->win = p;
+    c->peers.base[me] = reinterpret_cast<unsigned char*>(p);
+    if (c->peer_ok) {
+        void* w[kMaxRanks];
+        int ok = 0;
+        std::string why;
+        if ((rc = map_peers(ctx, p, 0, w, c->win_opened, &ok, &why))) return rc;
+        if (ok)
+            for (int r = 0; r < R; ++r) c->peers.base[r] = reinterpret_cast<unsigned char*>(w[r]);
+        else {                                          // the same verdict on every rank: back to NCCL for good
+            unmap_peers(c, c->flags_opened);
+            for (int r = 0; r < R; ++r) if (r != me) c->peers.flags[r] = nullptr;
+            c->peer_ok = false;
+            c->transport = 0;
+            c->peer_why = why;
+        }
+    }
+    for (int r = 0; r < R; ++r) c->win_bytes[(size_t)r] = std::max<size_t>(need[r], 256);
+    return CLEDB_OK;
+}
+
+extern "C" int cledb_comm_window(cledb_ctx* ctx, int64_t bytes, void** ptr_out) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    if (!ctx->comm) { ctx->err = "cledb_comm_window: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
+    if (bytes < 0 || !ptr_out) { ctx->err = "cledb_comm_window: bad argument"; return CLEDB_ERR_ARG; }
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t need[kMaxRanks];
+    for (int r = 0; r < ctx->comm->nranks; ++r) need[r] = (size_t)bytes;
+    const int rc = ensure_window(ctx, need);
+    *ptr_out = rc ? nullptr : ctx->comm->win;
+    return rc;
+}
+
+static inline bool in_window(const cledb_comm* c, const void* p, size_t bytes) {
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(c->win);
+    const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
+    return b && q >= b && q + bytes <= b + c->win_bytes[(size_t)c->rank];
+}
+
+static int after_launch(cledb_ctx* ctx, int n = 1) {
+    ctx->launches += n;
+    CLEDB_CUDA(ctx, cudaGetLastError());
+    return CLEDB_OK;
+}
+
 extern "C" int cledb_allgather_dev(cledb_ctx* ctx, const void* send, void* recv, int64_t bytes, void* stream) {
     if (!ctx) return CLEDB_ERR_ARG;
     if (!ctx->comm) { ctx->err = "cledb_allgather: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
@@ -140,6 +493,18 @@ extern "C" int cledb_allgather_dev(cledb_ctx* ctx, const void* send, void* recv,
     CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     cledb_comm* c = ctx->comm;
+    const size_t total = (size_t)bytes * (size_t)c->nranks;
+    if (c->transport == 1 && in_window(c, recv, total) && bytes % 16 == 0 && ((uintptr_t)send % 16) == 0 && ((uintptr_t)recv % 16) == 0) {
+        // receive buffer inside the window: every rank stores its block into every rank's window
+        const unsigned e = ++c->epoch;
+        const size_t nvec = (size_t)bytes / 16;
+        const size_t off = (size_t)(reinterpret_cast<unsigned char*>(recv) - reinterpret_cast<unsigned char*>(c->win)) + (size_t)c->rank * (size_t)bytes;
+        const unsigned grid = (unsigned)std::min<size_t>((nvec + 511) / 512, (size_t)ctx->prop.multiProcessorCount * 2);
+        k_peer_signal<<<1, 32, 0, st>>>(c->peers, kFlagFree, e);
+        k_push_block<<<grid, 512, 0, st>>>(c->peers, reinterpret_cast<const uint4*>(send), nvec, off, e, comm_err_word(ctx));
+        k_peer_wait<<<1, 32, 0, st>>>(c->peers, kFlagDone, e, comm_err_word(ctx));
+        return after_launch(ctx, 3);
+    }
     if (c->nranks == 1) {
         if (send != recv) CLEDB_CUDA(ctx, cudaMemcpyAsync(recv, send, (size_t)bytes, cudaMemcpyDeviceToDevice, st));
         return CLEDB_OK;
@@ -236,6 +601,182 @@ __global__ void __launch_bounds__(256) k_unshard(int nranks, const int64_t* __re
         if (issue) issue[p] = reinterpret_cast<const int32_t*>(blk + o_iss)[j];
     }
 }
+
+// The collective and the scatter in one pass: one warp per pixel of THIS rank's shard reads the pixel's packed record once
+// and stores it at the pixel's place in the maps of every destination rank (the local one included) - whole rows as 16-byte
+// vectors, so every store instruction is one contiguous 352 / 256-byte piece for NVLink.  Warps start at different
+// destinations.  The kernel opens with the wait for the destinations' free flags and closes with this rank's done flag.
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_push_records(Peers P, unsigned dst_mask, const int32_t* __restrict__ my_order, int64_t nlocal, int k,
+                                                      const unsigned char* __restrict__ send, size_t o_inv, size_t o_sf, size_t o_st, size_t o_iss,
+                                                      size_t m_inv, size_t m_sf, size_t m_st, size_t m_iss, unsigned epoch,
+                                                      int32_t* err_mapped) {
+    wait_flags(P, kFlagFree, epoch, err_mapped);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int wi = k * 11, ws = k * 8;
+    if (VEC && wi <= 128) {
+        // nsearch <= 11: a row is at most 32 vectors, one per lane; four pixels per trip so that a lane has eight loads in flight
+        constexpr int U = 4;
+        const int ni = wi / 4, ns = ws / 4;
+        for (int64_t j0 = warp * U; j0 < nlocal; j0 += nwarps * U) {
+            int64_t p[U];
+            float4 vi[U], vs[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) p[u] = j0 + u < nlocal ? (int64_t)my_order[j0 + u] : -1;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (p[u] >= 0 && lane < ni) vi[u] = __ldcs(reinterpret_cast<const float4*>(send + o_inv) + (j0 + u) * ni + lane);
+                if (p[u] >= 0 && lane < ns) vs[u] = __ldcs(reinterpret_cast<const float4*>(send + o_sf) + (j0 + u) * ns + lane);
+            }
+            uint8_t stv = 0;
+            int32_t isv = 0;
+            int64_t pl = -1;                                        // lane u carries the status / issue words of pixel u
+#pragma unroll
+            for (int u = 0; u < U; ++u) pl = lane == u ? p[u] : pl;
+            if (pl >= 0) {
+                stv = send[o_st + j0 + lane];
+                isv = reinterpret_cast<const int32_t*>(send + o_iss)[j0 + lane];
+            }
+            const int first = (int)((j0 / U) % P.n);
+            for (int q = 0; q < P.n; ++q) {
+                const int r = (first + q) % P.n;
+                if (!(dst_mask >> r & 1)) continue;
+                unsigned char* b = P.base[r];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (p[u] < 0) continue;
+                    if (lane < ni) (reinterpret_cast<float4*>(b + m_inv) + p[u] * ni)[lane] = vi[u];
+                    if (lane < ns) (reinterpret_cast<float4*>(b + m_sf) + p[u] * ns)[lane] = vs[u];
+                }
+                if (pl >= 0) {
+                    (b + m_st)[pl] = stv;
+                    reinterpret_cast<int32_t*>(b + m_iss)[pl] = isv;
+                }
+            }
+        }
+    } else
+    for (int64_t j = warp; j < nlocal; j += nwarps) {
+        const int64_t p = my_order[j];
+        const int first = (int)(j % P.n);
+        if (VEC) {
+            const float4* si = reinterpret_cast<const float4*>(send + o_inv) + j * (wi / 4);
+            const float4* ss = reinterpret_cast<const float4*>(send + o_sf) + j * (ws / 4);
+            for (int w = lane; w < wi / 4; w += 32) {
+                const float4 v = __ldcs(si + w);
+                for (int q = 0; q < P.n; ++q) {
+                    const int r = (first + q) % P.n;
+                    if (dst_mask >> r & 1) (reinterpret_cast<float4*>(P.base[r] + m_inv) + p * (wi / 4))[w] = v;
+                }
+            }
+            for (int w = lane; w < ws / 4; w += 32) {
+                const float4 v = __ldcs(ss + w);
+                for (int q = 0; q < P.n; ++q) {
+                    const int r = (first + q) % P.n;
+                    if (dst_mask >> r & 1) (reinterpret_cast<float4*>(P.base[r] + m_sf) + p * (ws / 4))[w] = v;
+                }
+            }
+        } else {
+            const float* si = reinterpret_cast<const float*>(send + o_inv) + j * wi;
+            const float* ss = reinterpret_cast<const float*>(send + o_sf) + j * ws;
+            for (int q = 0; q < P.n; ++q) {
+                const int r = (first + q) % P.n;
+                if (!(dst_mask >> r & 1)) continue;
+                float* di = reinterpret_cast<float*>(P.base[r] + m_inv) + p * wi;
+                float* ds = reinterpret_cast<float*>(P.base[r] + m_sf) + p * ws;
+                for (int w = lane; w < wi; w += 32) di[w] = si[w];
+                for (int w = lane; w < ws; w += 32) ds[w] = ss[w];
+            }
+        }
+        if (lane < P.n && (dst_mask >> lane & 1)) {              // lane r serves destination r
+            (P.base[lane] + m_st)[p] = send[o_st + j];
+            reinterpret_cast<int32_t*>(P.base[lane] + m_iss)[p] = reinterpret_cast<const int32_t*>(send + o_iss)[j];
+        }
+    }
+    block_done(P, epoch);
+}
+
+// The same push through the TMA engine: a warp stages the rows of eight consecutive pixels of the shard in shared memory
+// with two bulk loads (they are contiguous in the send buffer), then its lanes issue one bulk store per (pixel, row,
+// destination) - cp.async.bulk.global.shared::cta, 352- and 256-byte pieces at nsearch 8 - so the copy engine of the SM, not
+// the load/store unit, forms the NVLink writes.  Rows must be multiples of 16 bytes (nsearch % 4 == 0).
+constexpr int kPushG = 8;            // pixels per trip of a warp
+constexpr int kPushWarps = 8;        // warps per block
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(kPushWarps * 32) k_push_records_tma(Peers P, unsigned dst_mask, const int32_t* __restrict__ my_order, int64_t nlocal,
+                                                                      int k, const unsigned char* __restrict__ send, size_t o_inv, size_t o_sf,
+                                                                      size_t o_st, size_t o_iss, size_t m_inv, size_t m_sf, size_t m_st,
+                                                                      size_t m_iss, unsigned epoch, int32_t* err_mapped) {
+    extern __shared__ __align__(128) unsigned char stage_all[];
+    __shared__ uint64_t bars[kPushWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t bi = (uint32_t)k * 44u, bs = (uint32_t)k * 32u;            // bytes of an invout / sfound row
+    unsigned char* stage = stage_all + (size_t)wib * kPushG * (bi + bs);
+    uint64_t* bar = bars + wib;
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    wait_flags(P, kFlagFree, epoch, err_mapped);
+    __syncthreads();
+    const int64_t nwarps = (int64_t)gridDim.x * kPushWarps;
+    const int64_t warp = (int64_t)blockIdx.x * kPushWarps + wib;
+    uint32_t parity = 0;
+    int ndst = 0;
+    for (int r = 0; r < P.n; ++r) ndst += dst_mask >> r & 1;
+    for (int64_t j0 = warp * kPushG; j0 < nlocal; j0 += nwarps * kPushG) {
+        const int g = (int)min((int64_t)kPushG, nlocal - j0);
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"((uint32_t)g * (bi + bs)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(stage)),
+                         "l"(send + o_inv + (size_t)j0 * bi), "r"((uint32_t)g * bi), "r"(smem_addr(bar)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(stage + kPushG * bi)),
+                         "l"(send + o_sf + (size_t)j0 * bs), "r"((uint32_t)g * bs), "r"(smem_addr(bar)) : "memory");
+        }
+        int64_t pl = -1;                                            // lane u < g: the place of pixel u
+        uint8_t stv = 0;
+        int32_t isv = 0;
+        if (lane < g) {
+            pl = my_order[j0 + lane];
+            stv = send[o_st + j0 + lane];
+            isv = reinterpret_cast<const int32_t*>(send + o_iss)[j0 + lane];
+        }
+        {
+            uint32_t done;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+            } while (!done);
+        }
+        parity ^= 1;
+        const int first = (int)((j0 / kPushG) % P.n);
+        // one bulk store per (destination, row kind, pixel): t = (q * 2 + kind) * g + u
+        const int total = ndst * 2 * g;
+        for (int t = lane; t < total; t += 32) {
+            const int u = t % g, kind = (t / g) & 1, qd = t / (2 * g);
+            int r = first, seen = -1;
+            for (int c = 0; c < P.n; ++c) {                        // the qd-th destination of the mask, starting at `first`
+                const int rr = (first + c) % P.n;
+                if (dst_mask >> rr & 1) { if (++seen == qd) { r = rr; break; } }
+            }
+            const int64_t pu = __shfl_sync(__activemask(), pl, u);
+            unsigned char* dst = P.base[r] + (kind ? m_sf + (size_t)pu * bs : m_inv + (size_t)pu * bi);
+            const unsigned char* src = stage + (kind ? kPushG * bi + (uint32_t)u * bs : (uint32_t)u * bi);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(kind ? bs : bi) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (pl >= 0)
+            for (int r = 0; r < P.n; ++r)
+                if (dst_mask >> r & 1) {
+                    (P.base[r] + m_st)[pl] = stv;
+                    reinterpret_cast<int32_t*>(P.base[r] + m_iss)[pl] = isv;
+                }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the stage may be refilled
+        __syncwarp();
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");                  // every bulk store of this thread has been performed
+    block_done(P, epoch);
+}
 }  // namespace cledb
 
 extern "C" int cledb_shard_layout(int64_t maxcount, int nsearch, int64_t layout[5]) {
@@ -264,6 +805,83 @@ extern "C" int cledb_unshard_dev(cledb_ctx* ctx, int nranks, const int64_t* boun
     ctx->launches++;
     CLEDB_CUDA(ctx, cudaGetLastError());
     return CLEDB_OK;
+}
+
+namespace {
+struct Maps { size_t o_inv, o_sf, o_st, o_iss, bytes; };
+Maps map_layout(int64_t npix, int k) {
+    Maps M;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t off = 0;
+    M.o_inv = off; off = up(off + (size_t)npix * k * 44);
+    M.o_sf = off;  off = up(off + (size_t)npix * k * 32);
+    M.o_st = off;  off = up(off + (size_t)npix);
+    M.o_iss = off; off = up(off + (size_t)npix * 4);
+    M.bytes = off;
+    return M;
+}
+}  // namespace
+
+extern "C" int cledb_map_layout(int64_t npix, int nsearch, int64_t layout[5]) {
+    if (!layout || npix < 0 || nsearch < 1) return CLEDB_ERR_ARG;
+    const Maps M = map_layout(npix, nsearch);
+    layout[0] = (int64_t)M.o_inv; layout[1] = (int64_t)M.o_sf; layout[2] = (int64_t)M.o_st; layout[3] = (int64_t)M.o_iss; layout[4] = (int64_t)M.bytes;
+    return CLEDB_OK;
+}
+
+extern "C" int cledb_gather_maps_dev(cledb_ctx* ctx, int64_t npix, int64_t nlocal, const int32_t* my_order_dev, int64_t maxcount,
+                                     int nsearch, const void* send, void* maps, int root, void* stream) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    cledb_comm* c = ctx->comm;
+    if (!c) { ctx->err = "cledb_gather_maps: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
+    if (c->transport != 1) { ctx->err = "cledb_gather_maps: needs the peer-memory transport (cledb_comm_transport); use cledb_allgather_dev + cledb_unshard_dev"; return CLEDB_ERR_COMM; }
+    if (npix < 0 || nlocal < 0 || nlocal > maxcount || nsearch < 1 || !maps || root >= c->nranks || (nlocal > 0 && (!my_order_dev || !send))) {
+        ctx->err = "cledb_gather_maps: bad argument";
+        return CLEDB_ERR_ARG;
+    }
+    const Maps M = map_layout(npix, nsearch);
+    bool fits = in_window(c, maps, 0) && ((uintptr_t)maps % 256) == 0;
+    if (fits) {
+        const size_t woff0 = (size_t)(reinterpret_cast<unsigned char*>(maps) - reinterpret_cast<unsigned char*>(c->win));
+        for (int r = 0; r < c->nranks; ++r)
+            if (root < 0 || root == r) fits = fits && woff0 + M.bytes <= c->win_bytes[(size_t)r];
+    }
+    if (!fits) {
+        ctx->err = "cledb_gather_maps: `maps` must be a 256-byte aligned block of cledb_map_layout bytes inside the window (cledb_comm_window)";
+        return CLEDB_ERR_ARG;
+    }
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const Packed L = packed_layout(maxcount, nsearch);
+    const size_t woff = (size_t)(reinterpret_cast<unsigned char*>(maps) - reinterpret_cast<unsigned char*>(c->win));
+    const unsigned mask = root < 0 ? (1u << c->nranks) - 1u : 1u << root;
+    const unsigned e = ++c->epoch;
+    const char* pg = std::getenv("CLEDB_B200_PUSH_GRID");                 // tuning: blocks per SM of the push kernels
+    const int push_grid = pg ? std::atoi(pg) : 0;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((nlocal * 32 + 255) / 256, (int64_t)ctx->prop.multiProcessorCount * (push_grid > 0 ? push_grid : 8)));
+    const unsigned char* s8 = reinterpret_cast<const unsigned char*>(send);
+    k_peer_signal<<<1, 32, 0, st>>>(c->peers, kFlagFree, e);
+    const char* how = std::getenv("CLEDB_B200_PUSH");
+    const size_t stage_bytes = (size_t)kPushWarps * kPushG * (size_t)nsearch * 76;
+    if (how && how[0] == 't' && nsearch % 4 == 0 && stage_bytes <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_push_records_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        const int per_sm = std::max(1, std::min(8, (int)((size_t)200 * 1024 / stage_bytes)));
+        const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((nlocal + kPushG * kPushWarps - 1) / (kPushG * kPushWarps),
+                                                                                (int64_t)ctx->prop.multiProcessorCount * (push_grid > 0 ? std::min(push_grid, per_sm) : std::min(4, per_sm))));
+        k_push_records_tma<<<tgrid, kPushWarps * 32, stage_bytes, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss,
+                                                                        woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx));
+    } else if (nsearch % 4 == 0)
+        k_push_records<true><<<grid, 256, 0, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss,
+                                                   woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx));
+    else
+        k_push_records<false><<<grid, 256, 0, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss,
+                                                    woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx));
+    k_peer_wait<<<1, 32, 0, st>>>(c->peers, kFlagDone, e, comm_err_word(ctx));
+    return after_launch(ctx, 3);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -304,7 +922,7 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
     for (int r = 0; r < R; ++r) maxcount = std::max(maxcount, bounds[r + 1] - bounds[r]);
     const Packed L = packed_layout(maxcount, nsearch);
 
-    // ---- device buffers: this rank's inputs (ctx->io), packed send / recv, pixel order + bounds, full maps
+    // ---- device buffers: this rank's inputs (ctx->io), packed send (/ recv), pixel order (+ bounds), full maps in the window
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off = up256(off + b); return o; };
     const size_t nn = std::max<size_t>(n, 1);
@@ -312,16 +930,19 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
                  o_rc = take(nn * 4), o_rs = take(nn * 4), o_dopp = take(nn * dsz),
                  o_tab = take((size_t)(2 * grid->nbphi + 2 * grid->nbtheta) * 4);
     int rc;
+    const Maps M = map_layout(npix, nsearch);
+    {
+        size_t need[kMaxRanks];
+        for (int r = 0; r < R; ++r) need[r] = (root < 0 || root == r) ? M.bytes : 256;
+        if ((rc = ensure_window(ctx, need))) return rc;           // collective when it has to grow
+    }
+    const bool peer = c->transport == 1;
     if ((rc = ensure_workspace(ctx, ctx->io, off))) return rc;
     if ((rc = ensure_workspace(ctx, c->send, L.bytes))) return rc;
-    if ((rc = ensure_workspace(ctx, c->recv, L.bytes * (size_t)R))) return rc;
+    if (!peer && (rc = ensure_workspace(ctx, c->recv, L.bytes * (size_t)R))) return rc;
     const size_t o_bounds = up256((size_t)npix * 4);
     if ((rc = ensure_workspace(ctx, c->order, o_bounds + ((size_t)R + 1) * 8))) return rc;
-    size_t foff = 0;
-    auto ftake = [&](size_t b) { size_t o = foff; foff = up256(foff + b); return o; };
-    const size_t f_inv = ftake(want ? (size_t)npix * k * 44 : 0), f_sf = ftake(want ? (size_t)npix * k * 32 : 0),
-                 f_st = ftake(want ? (size_t)npix : 0), f_iss = ftake(want ? (size_t)npix * 4 : 0);
-    if (want && (rc = ensure_workspace(ctx, c->full, foff))) return rc;
+    const size_t f_inv = M.o_inv, f_sf = M.o_sf, f_st = M.o_st, f_iss = M.o_iss;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx->io.ptr);
     if (n > 0) {
         CLEDB_CUDA(ctx, cudaMemcpyAsync(w + o_sobs, sobs, n * 32, cudaMemcpyHostToDevice, st));
@@ -347,7 +968,9 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
     g.sin_btheta = tab + 2 * g.nbphi;
     g.cos_btheta = tab + 2 * g.nbphi + g.nbtheta;
     unsigned char* dord = reinterpret_cast<unsigned char*>(c->order.ptr);
-    if (want) {
+    if (peer) {                                          // a rank pushes its own pixels: it needs their places, nothing else
+        if (n > 0) CLEDB_CUDA(ctx, cudaMemcpyAsync(dord, order + bounds[me], n * 4, cudaMemcpyHostToDevice, st));
+    } else if (want) {
         CLEDB_CUDA(ctx, cudaMemcpyAsync(dord, order, (size_t)npix * 4, cudaMemcpyHostToDevice, st));
         CLEDB_CUDA(ctx, cudaMemcpyAsync(dord + o_bounds, bounds, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, st));
     }
@@ -362,13 +985,19 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
                               send + L.o_st, reinterpret_cast<int32_t*>(send + L.o_iss), st);
         if (rc) return rc;        // a rank that fails here leaves the others waiting in the collective: the launcher aborts the job
     }
-    // ---- the one collective of the path, then every record to its pixel
-    if ((rc = cledb_allgather_dev(ctx, send, c->recv.ptr, (int64_t)L.bytes, st))) return rc;
+    // ---- the one collective of the path: every record to its pixel's place in the maps of the ranks that want them
+    unsigned char* f = reinterpret_cast<unsigned char*>(c->win);
+    if (peer) {
+        if ((rc = cledb_gather_maps_dev(ctx, npix, nlocal, reinterpret_cast<int32_t*>(dord), maxcount, nsearch, send, f, root, st))) return rc;
+    } else {
+        if ((rc = cledb_allgather_dev(ctx, send, c->recv.ptr, (int64_t)L.bytes, st))) return rc;
+        if (want) {
+            rc = cledb_unshard_dev(ctx, R, reinterpret_cast<int64_t*>(dord + o_bounds), reinterpret_cast<int32_t*>(dord), npix, maxcount, nsearch,
+                                   c->recv.ptr, reinterpret_cast<float*>(f + f_inv), reinterpret_cast<float*>(f + f_sf), f + f_st, reinterpret_cast<int32_t*>(f + f_iss), st);
+            if (rc) return rc;
+        }
+    }
     if (want) {
-        unsigned char* f = reinterpret_cast<unsigned char*>(c->full.ptr);
-        rc = cledb_unshard_dev(ctx, R, reinterpret_cast<int64_t*>(dord + o_bounds), reinterpret_cast<int32_t*>(dord), npix, maxcount, nsearch,
-                               c->recv.ptr, reinterpret_cast<float*>(f + f_inv), reinterpret_cast<float*>(f + f_sf), f + f_st, reinterpret_cast<int32_t*>(f + f_iss), st);
-        if (rc) return rc;
         CLEDB_CUDA(ctx, cudaMemcpyAsync(invout, f + f_inv, (size_t)npix * k * 44, cudaMemcpyDeviceToHost, st));
         CLEDB_CUDA(ctx, cudaMemcpyAsync(sfound, f + f_sf, (size_t)npix * k * 32, cudaMemcpyDeviceToHost, st));
         if (status_out) CLEDB_CUDA(ctx, cudaMemcpyAsync(status_out, f + f_st, (size_t)npix, cudaMemcpyDeviceToHost, st));

@@ -1714,22 +1714,31 @@ __global__ void __launch_bounds__(256) k_finalize(Plan pl, const DbSlot* __restr
     int32_t* s_key = s_idx + kFinPix * k;                                        // [kFinPix]
     const int64_t p0 = (int64_t)blockIdx.x * kFinPix;
 
-    if (threadIdx.x < kFinPix) {
-        const int64_t p = p0 + threadIdx.x;
-        const int lp = threadIdx.x;
+    // phase 1, one thread per (pixel, slot): a pixel with ONE list (the pruned search, unsplit classes) has nothing to merge -
+    // slot r is entry r of the list; a pixel with several lists is merged by the thread of its slot 0
+    for (int t = threadIdx.x; t < kFinPix * k; t += blockDim.x) {
+        const int lp = t / k, r0 = t - lp * k;
+        const int64_t p = p0 + lp;
         int key = -1;
         if (p < pl.npix) key = pl.key[p];
-        s_key[lp] = key;
+        if (r0 == 0) s_key[lp] = key;
         if (key < 0) {
-            for (int r = 0; r < k; ++r) s_pos[lp * k + r] = -1;
-            if (ncand_out && p < pl.npix) ncand_out[p] = 0;
-        } else {
-            const DbSlot& db = slots[key / kParts];
-            const int local = pl.rank[p] - pl.off[key];
-            const int tile = local / pl.P, j = local - tile * pl.P;
-            const int ns = pl.nsub[key];
-            const int ntg = (pl.cnt[key] + pl.P - 1) / pl.P;                    // item numbering: see make_item
-            const CandT* base = reinterpret_cast<const CandT*>(pl.plist) + ((size_t)(pl.item0[key] + (pl.seed ? tile : tile * ns)) * pl.P + j) * k;
+            s_pos[t] = -1;
+            if (r0 == 0 && ncand_out && p < pl.npix) ncand_out[p] = 0;
+            continue;
+        }
+        const DbSlot& db = slots[key / kParts];
+        const int local = pl.rank[p] - pl.off[key];
+        const int tile = local / pl.P, j = local - tile * pl.P;
+        const int ns = pl.nsub[key];
+        const int ntg = (pl.cnt[key] + pl.P - 1) / pl.P;                    // item numbering: see make_item
+        const CandT* base = reinterpret_cast<const CandT*>(pl.plist) + ((size_t)(pl.item0[key] + (pl.seed ? tile : tile * ns)) * pl.P + j) * k;
+        if (ns == 1) {
+            const CandT c = base[r0];
+            s_val[t] = c.v;
+            s_pos[t] = c.pos;                                  // a list is filled from the front: empty slots (-1) come last
+            s_idx[t] = c.pos >= 0 ? db.perm[c.pos] : 0x7fffffff;
+        } else if (r0 == 0) {
             const size_t sub_stride = (size_t)(pl.seed ? ntg : 1) * pl.P * k;
             unsigned char head[kMaxSub];
             for (int s = 0; s < ns; ++s) head[s] = 0;
@@ -1748,10 +1757,10 @@ __global__ void __launch_bounds__(256) k_finalize(Plan pl, const DbSlot* __restr
                 s_pos[lp * k + r] = best >= 0 ? bpos : -1;
                 s_idx[lp * k + r] = bidx;
             }
-            if (ncand_out) {
-                const int cls = key % kParts;
-                ncand_out[p] = pl.mode == CLEDB_MODE_IQUV ? db.part_cnt[cls] : (int64_t)db.part_cnt[0] + db.part_cnt[1] + db.part_cnt[2];
-            }
+        }
+        if (r0 == 0 && ncand_out) {
+            const int cls = key % kParts;
+            ncand_out[p] = pl.mode == CLEDB_MODE_IQUV ? db.part_cnt[cls] : (int64_t)db.part_cnt[0] + db.part_cnt[1] + db.part_cnt[2];
         }
     }
     __syncthreads();
@@ -1875,6 +1884,11 @@ int check_async_error(cledb_ctx* ctx) {
         *reinterpret_cast<volatile int32_t*>(ctx->h_err) = 0;
         ctx->err = "cledb_match: a pixel refers to a database id that is not resident (cledb_db_put it first)";
         return CLEDB_ERR_NODB;
+    }
+    if (ctx->h_err && reinterpret_cast<volatile int32_t*>(ctx->h_err)[1] != 0) {      // comm.cu: a flag wait gave up
+        reinterpret_cast<volatile int32_t*>(ctx->h_err)[1] = 0;
+        ctx->err = "multi-GPU: a peer rank did not arrive at a collective within 20 s (peer-memory transport); the gathered maps are incomplete";
+        return CLEDB_ERR_COMM;
     }
     return CLEDB_OK;
 }

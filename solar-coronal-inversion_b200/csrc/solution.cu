@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
     __shared__ __align__(16) float s_sf[128 * 8];
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x, t = t0 + threadIdx.x;
     float o[11], f[8];
+    float v_sth = 0.f, v_cth = 1.f, v_sph = 0.f, v_cph = 1.f;       // sin / cos of the solution's theta_B, phi_B (0, 0 without a solution)
     o[0] = -1.0f;
 #pragma unroll
     for (int c = 1; c < 11; ++c) o[c] = 0.0f;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
         const float bphi = (float)__dadd_rn((double)g.bphimin, __ddiv_rn(__dmul_rn((double)kk, dphi), (double)(g.nbphi - 1)));
         const float bth = (float)__dadd_rn((double)g.bthetamin, __ddiv_rn(__dmul_rn((double)l, dth), (double)(g.nbtheta - 1)));
         const float sp = g.sin_bphi[kk], cp = g.cos_bphi[kk], sth = g.sin_btheta[l], cth = g.cos_btheta[l];
+        v_sth = sth; v_cth = cth; v_sph = sp; v_cph = cp;
         float bo, bx, by, bz;
         if (DOPP64 && mode == CLEDB_MODE_IQUD) {                                         // float64 B_POS: NumPy promotes to float64
             double b = b64;
@@ -187,24 +189,42 @@ __global__ void __launch_bounds__(128) k_build(int mode, int64_t npix, int k, co
     // ---- issue codes of cledb_invproc (CLEDB_PROC.py:323-355): one int32 per pixel (zeroed before the launch), OR-ed together by
     //   the thread of the LAST solution (`flg = 0` sits inside the reference's loop over solutions, :324, so only slot
     //          nsearch-1 decides code 512):  512 = Van-Vleck proximity 53 deg <= vartheta_B <= 56 deg, and bit 0 = the angle
-    //          lies within 1e-3 deg of either limit: the reference evaluates the chain in float32 with NumPy's own
-    //          sin/cos/arctan2, whose last bits differ between CPUs; here it runs in float64, which decides every pixel that
-    //          is not that close to a limit; the binding re-evaluates the marked ones (about 1 in 50 000) with NumPy
+    //          lies within 2e-3 deg of either limit: the reference evaluates the chain in float32 with NumPy's own
+    //          sin/cos/arctan2, whose last bits differ between CPUs; here it runs in float64 without a single transcendental
+    //          (cos/sin of alpha = -atan2(a, b) are b/r and -a/r, the sines and cosines of the grid angles are the caller's
+    //          tables, and 53 deg <= atan2(s, z) <= 56 deg is tan(53 deg) z <= s <= tan(56 deg) z for z > 0), which decides every
+    //          pixel that is not that close to a limit; the binding re-evaluates the marked ones (about 1 in 25 000) with NumPy
     //   the thread of slot 0:  1024 = chi^2 of the best solution > 10 (:351), 2048 = snr[p,0] < 1 (:353)
     if (issue_out && t < npix * k) {
         const int64_t p = t / k;
         const int s = (int)(t - p * k);
         int code = 0;
         if (s == k - 1) {
-            const double alpha = -atan2((double)o[4], (double)o[3]);
-            const double sb = 1.0, cb = 6.123233995736766e-17;                  // sin, cos of the float64 pi/2
-            const double sth = sin((double)o[7]), cth = cos((double)o[7]), sph = sin((double)o[6]), cph = cos((double)o[6]);
-            const double xb = sth * cph, yb = sth * sph, zb = cth;
-            const double yyb = cb * yb - sb * zb, yzb = sb * yb + cb * zb;
-            const double xxb = cos(alpha) * xb + sin(alpha) * yzb, zzb = -sin(alpha) * xb + cos(alpha) * yzb;
-            const double deg = atan2(sqrt(xxb * xxb + yyb * yyb), zzb) * 180.0 / 3.141592653589793;
-            if (deg >= 53.0 && deg <= 56.0) code |= 512;
-            if (fabs(deg - 53.0) < 1e-3 || fabs(deg - 56.0) < 1e-3) code |= 1;
+            const double a = (double)o[4], b = (double)o[3];
+            const double r2 = a * a + b * b;
+            double ca, sa;
+            if (r2 > 0.0 && r2 < 1e300) {
+                const double ir = 1.0 / sqrt(r2);
+                ca = b * ir;
+                sa = -a * ir;
+            } else if (a == 0.0 && b == 0.0) {                                  // atan2(+-0, +0) = +-0, atan2(+-0, -0) = +-pi
+                ca = signbit(b) ? -1.0 : 1.0;
+                sa = 0.0;
+            } else {                                                            // infinities, NaN: the library's conventions
+                const double alpha = -atan2(a, b);
+                ca = cos(alpha);
+                sa = sin(alpha);
+            }
+            const double cb = 6.123233995736766e-17;                            // cos of the float64 pi/2 (its sine is 1)
+            const double xb = (double)v_sth * (double)v_cph, yb = (double)v_sth * (double)v_sph, zb = (double)v_cth;
+            const double yyb = cb * yb - zb, yzb = yb + cb * zb;
+            const double xxb = ca * xb + sa * yzb, zzb = -sa * xb + ca * yzb;
+            const double sq = sqrt(xxb * xxb + yyb * yyb);
+            constexpr double t53 = 1.3270448216204098, t56 = 1.4825609685127403;          // tan(53 deg), tan(56 deg)
+            constexpr double t53lo = 1.326948447329313, t53hi = 1.3271412048405367;       // tan((53 -+ 2e-3) deg)
+            constexpr double t56lo = 1.4824493434833603, t56hi = 1.4826726050961634;      // tan((56 -+ 2e-3) deg)
+            if (zzb > 0.0 && sq >= t53 * zzb && sq <= t56 * zzb) code |= 512;
+            if (zzb > 0.0 && ((sq > t53lo * zzb && sq < t53hi * zzb) || (sq > t56lo * zzb && sq < t56hi * zzb))) code |= 1;
         }
         if (s == 0) code |= (o[1] > 10.0f ? 1024 : 0) | ((snr && snr[p * 8] < 1.0f) ? 2048 : 0);
         if (code) atomicOr(issue_out + p, code);

@@ -45,3 +45,14 @@ def oracle_raw(mode, sobs, snr, dbs, enc, nsearch):
         out['idx'][p, :n], out['chi'][p, :n], out['chi64'][p, :n], out['kpos'][p, :n] = idx, chi, chi, pos
         out['rows'][p, :n] = db[idx]
     return out
+
+
+class _DeviceBytes:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = dict(shape=(int(nbytes),), typestr='|u1', data=(int(ptr), False), version=2)
+
+
+def device_view(ptr, nbytes, device):
+    """uint8 torch tensor over ``nbytes`` of device memory at ``ptr`` (memory the library owns, e.g. the receive window)."""
+    import torch
+    return torch.as_tensor(_DeviceBytes(ptr, nbytes), device=device)

@@ -18,7 +18,7 @@ import pytest
 import oracle.cledb_oracle as orc
 import cledb_b200.synth as synth
 from cledb_b200 import native, codec
-from helpers import hdr_from_g, same
+from helpers import hdr_from_g, same, device_view
 from oracle.compare import check_raw_against_oracle, check_invout_against_reference, assert_chi_close_map, CHI_RTOL, CHI_ATOL
 
 pytestmark = pytest.mark.gpu
@@ -955,13 +955,17 @@ def test_config5_shaped_map_against_the_oracle(ctx, mode):
         ctx.db_drop(i)
 
 
-def test_sharded_call_on_one_rank_equals_the_plain_call():
-    """cledb_invert_sharded with a one-rank communicator (no NCCL needed): partition, packed send buffer, gather (a device
-    copy), scatter kernel - the full maps equal cledb_invert's bit for bit; a multi-database map, both modes.  The N > 1
-    path runs in tests/test_multigpu.py on a box with two GPUs."""
+@pytest.mark.parametrize('transport', ['peer', 'nccl'])
+def test_sharded_call_on_one_rank_equals_the_plain_call(transport):
+    """cledb_invert_sharded with a one-rank communicator (no NCCL needed): partition, packed send buffer, then either the
+    peer-memory transport (flags + k_push_records storing every record at its pixel in the window) or the collective one (a
+    device copy + the scatter kernel) - the full maps equal cledb_invert's bit for bit; a multi-database map, both modes.
+    The N > 1 path runs in tests/test_multigpu.py on a box with two GPUs."""
     c = native.Context(0)
     c.comm_init(0, 1)
     assert c.comm_info() == dict(rank=0, nranks=1, nccl_version=c.comm_info()['nccl_version'], nccl=False)
+    assert c.comm_transport() == 'peer'                        # the default where peer memory works; one rank: always
+    assert c.comm_transport(transport) == transport
     dbs = [synth.make_database(5 + 3 * i, 30 + 2 * i, ngx=5, nbphi=36, nbtheta=18) for i in range(3)]
     nx, ny = 40, 33
     enc = np.random.default_rng(5).integers(0, 3, (nx, ny)).astype(np.int32)
@@ -988,6 +992,59 @@ def test_sharded_call_on_one_rank_equals_the_plain_call():
     c.comm_destroy()
     with pytest.raises(native.CledbError, match='communicator'):
         c.invert_sharded(0, sobs[order], snr[order], ids[order], 8, y[order], d[order], a[order], None, hdr, 1000, 0, n, order, bounds)
+    c.close()
+
+
+def test_window_allgather_and_gather_maps_on_one_rank():
+    """The device-pointer collectives of the peer transport with one rank: cledb_allgather_dev into the window (k_push_block
+    between the free / done flags) is a copy; cledb_gather_maps_dev puts packed records at their pixels like
+    cledb_unshard_dev does; repeated calls keep working (epochs); a receive buffer outside the window takes the other route."""
+    import torch
+    dev = torch.device('cuda', 0)
+    c = native.Context(0)
+    c.comm_init(0, 1)
+    rng = np.random.default_rng(3)
+    nbytes = 1 << 20
+    win = c.comm_window(2 * nbytes)
+    assert win and win % 256 == 0 and c.comm_window(nbytes) == win          # no growth: the same window
+    stream = torch.cuda.Stream(device=dev)
+    from cledb_b200.native import load_library
+    lib = load_library()
+    for rep in range(3):
+        src = torch.from_numpy(rng.integers(0, 256, nbytes, dtype=np.uint8)).to(dev)
+        torch.cuda.synchronize()
+        c.allgather_dev(src.data_ptr(), win + 4096, nbytes, stream.cuda_stream)
+        stream.synchronize()
+        assert torch.equal(device_view(win + 4096, nbytes, dev), src)
+        other = torch.empty(nbytes, dtype=torch.uint8, device=dev)             # not in the window: plain device copy
+        c.allgather_dev(src.data_ptr(), other.data_ptr(), nbytes, stream.cuda_stream)
+        stream.synchronize()
+        assert torch.equal(other, src)
+    # packed records -> maps, against the scatter kernel
+    import ctypes
+    npix, k = 3000, 8
+    order = rng.permutation(npix).astype(np.int32)
+    lay, mlay = np.zeros(5, np.int64), np.zeros(5, np.int64)
+    lib.cledb_shard_layout(npix, k, lay.ctypes.data_as(ctypes.c_void_p))
+    lib.cledb_map_layout(npix, k, mlay.ctypes.data_as(ctypes.c_void_p))
+    send_h = rng.integers(0, 256, int(lay[4]), dtype=np.uint8)
+    send = torch.from_numpy(send_h).to(dev)
+    win = c.comm_window(int(mlay[4]))
+    d_order = torch.from_numpy(order).to(dev)
+    d_bounds = torch.tensor([0, npix], dtype=torch.int64, device=dev)
+    ref = [torch.zeros((npix, k, 11), dtype=torch.float32, device=dev), torch.zeros((npix, k, 8), dtype=torch.float32, device=dev),
+           torch.zeros(npix, dtype=torch.uint8, device=dev), torch.zeros(npix, dtype=torch.int32, device=dev)]
+    c.unshard_dev(1, d_bounds.data_ptr(), d_order.data_ptr(), npix, npix, k, send.data_ptr(), *(t.data_ptr() for t in ref), stream.cuda_stream)
+    c.gather_maps_dev(npix, npix, d_order.data_ptr(), npix, k, send.data_ptr(), win, -1, stream.cuda_stream)
+    stream.synchronize()
+    got = device_view(win, int(mlay[4]), dev).cpu().numpy()
+    for t, o in zip(ref, mlay[:4]):
+        want = t.cpu().numpy().view(np.uint8).reshape(-1)
+        assert np.array_equal(got[int(o):int(o) + want.size], want)
+    c.comm_transport('nccl')
+    with pytest.raises(native.CledbError, match='peer-memory transport'):
+        c.gather_maps_dev(npix, npix, d_order.data_ptr(), npix, k, send.data_ptr(), win, -1, stream.cuda_stream)
+    c.comm_destroy()
     c.close()
 
 
