@@ -39,6 +39,7 @@ for p in (REPO, PKG):
 import numpy as np  # noqa: E402
 
 NSEARCH = 8
+NPOOL = 8          # observation maps the top-level record cycles through
 NDB_ROWS = 340200
 
 
@@ -57,6 +58,7 @@ def parse():
     ap.add_argument('--configs', default='', help='comma list of extra configs to run (default: 2b,3,4,5 at N=1; 2b,5 at N>1)')
     ap.add_argument('--transport', default='auto', choices=['auto', 'peer', 'nccl'],
                     help='multi-GPU gathers: peer = the library\'s own stores into the peers\' windows (default where CUDA IPC works), nccl = ncclAllGather')
+    ap.add_argument('--pieces', type=int, default=0, help='config 5: pieces of a shard in the pipelined gather (0 = library default)')
     ap.add_argument('--no-overlap', action='store_true', help='N > 1: time search + gather back to back on one stream (no pipelining of the gather)')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -297,6 +299,14 @@ class Bench:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(self, x):
+        if self.world == 1:
+            return [float(x)]
+        t = self.torch.zeros(self.world, device=self.dev, dtype=self.torch.float64)
+        t[self.rank] = float(x)
+        self.dist.all_reduce(t)
+        return [round(float(v), 5) for v in t.tolist()]
+
     def sum_over_ranks(self, xs):
         if self.world == 1:
             return [int(x) for x in xs]
@@ -344,8 +354,21 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
     maps2 = [maps_d, torch.empty_like(maps_d)] if gathered is not None else [maps_d]
     side = torch.cuda.Stream(device=B.dev) if gathered is not None else None
 
+    # The top-level record walks a pool of NPOOL observation maps (seeds 7 .. 7+NPOOL-1, the same pool at every N), rank r starting
+    # at map r: the pruned search's time depends on the map (its longest work item), so every rank - and the N = 1 run - sees the
+    # same mix of maps and the per-GPU work is the same at every N.
+    pool = [(sobs_d, snr_d, id_d)]
+    if with_gather:
+        for m in range(1, NPOOL):
+            o = make_inputs(nx, ndb, (B.rank + m) % NPOOL)[1]
+            pool.append(tuple(torch.from_numpy(np.ascontiguousarray(a)).to(B.dev) for a in
+                              (o['sobs_totrot'].reshape(-1, 8), o['snr'].reshape(-1, 8), o['db_enc'].reshape(-1).astype(np.int32))))
+    cursor = [0]
+
     def search(b=0):
-        ctx.match_dev(mode, npix, sobs_d.data_ptr(), snr_d.data_ptr(), id_d.data_ptr(), k, maps2[b][0].data_ptr(), maps2[b][1].data_ptr(),
+        s_d, n_d, i_d = pool[cursor[0] % len(pool)]
+        cursor[0] += 1
+        ctx.match_dev(mode, npix, s_d.data_ptr(), n_d.data_ptr(), i_d.data_ptr(), k, maps2[b][0].data_ptr(), maps2[b][1].data_ptr(),
                       None, kpos_d.data_ptr(), rows_d.data_ptr(), st_d.data_ptr(), nc_d.data_ptr(), B.stream.cuda_stream)
 
     def gather(b, stream):                  # the only collective of the path: gather the result maps (library call)
@@ -395,17 +418,32 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
         launches0 = ctx.launch_count()
         nst = steps if pruned else max(3, min(steps, 10 if variant == 2 else 5))
         serial_ms = None
+        cursor[0] = 0
         if pruned and gathered is not None and not B.args.no_overlap:
-            s_ms, _ = B.timed(step, max(3, nst // 2))
+            s_ms, _ = B.timed(step, nst)
             serial_ms = B.max_over_ranks(float(np.mean(s_ms)))
             B.barrier()
             launches0 = ctx.launch_count()
+            cursor[0] = 0
             step_ms, kern_ms = B.timed_pipelined(search, gather, nst, side)
         else:
             step_ms, kern_ms = B.timed(step, nst)
+        cursor[0] = 0
         B.barrier()
         launches = ctx.launch_count() - launches0
         stats = ctx.pruning_stats() if pruned else None
+        if pruned and len(pool) > 1:                        # (pixel, tile) pairs of the average map of the pool
+            acc = {}
+            for m in range(len(pool)):
+                cursor[0] = m
+                search(0)
+                torch.cuda.synchronize()
+                for kk, v in ctx.pruning_stats().items():
+                    acc[kk] = acc.get(kk, 0) + v
+            stats = {kk: int(round(v / len(pool))) for kk, v in acc.items()}
+            cursor[0] = 0
+            search(0)                                       # leave the results of this rank's first map in the buffers
+            torch.cuda.synchronize()
         ms = B.max_over_ranks(float(np.mean(step_ms)))
         kms = float(np.mean(kern_ms)) if len(kern_ms) else float('nan')
         ncand, nsearched = int(nc_d.sum().item()), int((st_d == 0).sum().item())
@@ -448,6 +486,12 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
                    nominal_scanned_evals_per_s=B.world * npix * float(NDB_ROWS) * max(1, ndb) / max(1, ndb) / (ms * 1e-3),
                    nominal_candidate_evals_per_s=ncand_all / (ms * 1e-3), pixels_searched=nsearched_all, gpu_launches=int(launches),
                    pruning=stats, roofline=roof, clocks=clocks)
+        if B.world > 1:
+            rec['per_rank'] = dict(step_ms=B.all_ranks(float(np.mean(step_ms))), search_kernel_ms=B.all_ranks(kms),
+                                   note='mean step and mean search-kernel time of every rank (value uses the slowest rank)')
+        if len(pool) > 1:
+            rec['map_pool'] = ('%d observation maps (seeds 7..%d) on the same database, rank r starts at map r and takes the next one each step: '
+                               'the same mix of maps on every rank and at every N' % (len(pool), 6 + len(pool)))
         if serial_ms is not None:
             rec['gather_overlap'] = dict(ms_per_step_serial=serial_ms, value_serial=B.world * npix / (serial_ms * 1e-3),
                                          how='ms_per_step: the gather of map i-1 runs on a second stream beside the search of map i (two sets of '
@@ -714,6 +758,16 @@ def bench_config5(B, nx, ndb, steps):
             torch.cuda.synchronize()
             state['parts'].append([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), 0.0])
 
+    def step_pipe(record=False):
+        """the same as a pipeline (cledb_invert_gather_dev): the shard in pieces, the records of a piece cross NVLink while the
+        next piece is searched"""
+        ctx.invert_gather_dev(native.MODE_IQUV, n, d_sobs.data_ptr(), d_snr.data_ptr(), d_ids.data_ptr(), k, d_y.data_ptr(), d_d.data_ptr(),
+                              d_rc.data_ptr(), d_rs.data_ptr(), None, 0, g, 1000, 0, npix, d_mine.data_ptr(), win, -1, B.args.pieces,
+                              B.stream.cuda_stream)
+        if record:
+            torch.cuda.synchronize()
+            state['parts'].append([0.0, 0.0, 0.0])
+
     def step_nccl(record=False):
         """search + solutions of the shard -> ncclAllGather of the packed records -> scatter kernel"""
         if record:
@@ -762,12 +816,21 @@ def bench_config5(B, nx, ndb, steps):
         if peer:
             state['recv'] = None
     step = step_nccl
+    unpiped = None
     if peer:
         ctx.comm_transport('peer')
         ms, kern_ms, part, launches = measure(step_peer, nst)
         step = step_peer
         if nccl_rec is not None:
             nccl_rec['same_maps_as_peer_transport'] = bool(torch.equal(maps_nccl, B.view(win, map_bytes)))
+        if B.world > 1:                                     # the pipelined call is the product's path (cledb_invert_sharded uses it)
+            unpiped = dict(ms_per_step=ms, value=npix / (ms * 1e-3), how='search + solutions of the whole shard, then one k_push_records')
+            maps_one = B.view(win, map_bytes).clone()
+            ms, kern_ms, _, launches = measure(step_pipe, nst)
+            unpiped['same_maps_as_pipelined'] = bool(torch.equal(maps_one, B.view(win, map_bytes)))
+            del maps_one
+            step = step_pipe
+        if nccl_rec is not None:
             del maps_nccl
     stats = ctx.pruning_stats()
     f_st = B.view(win + m_st, npix)
@@ -785,9 +848,14 @@ def bench_config5(B, nx, ndb, steps):
                step_breakdown_ms=dict(search_and_build=part[0], gather=part[1], scatter=part[2],
                                       note='CUDA events between the calls of one step, max over ranks; every GPU receives %.0f MB of '
                                            'records from its peers' % ((npix - n) * (k * 76 + 5) / 1e6)),
-               search_kernel_ms=float(np.mean(kern_ms)) if len(kern_ms) else None, pruning=stats, setup_seconds=setup_s)
+               search_kernel_ms=float(np.sum(kern_ms)) / nst if len(kern_ms) else None, pruning=stats, setup_seconds=setup_s)
     if nccl_rec is not None and peer:
         rec['nccl_transport'] = nccl_rec
+    if unpiped is not None:
+        rec['unpipelined'] = unpiped
+        rec['pipeline'] = ('cledb_invert_gather_dev: the shard goes through in pieces (2 from four ranks on when a piece still holds 64 Ki pixels, else 1); the records '
+                           'of a piece cross NVLink on a second stream (k_push_records on 16 blocks) while the next piece is searched; '
+                           'step_breakdown_ms is the unpipelined step')
     # the same step with the brute-force search (k-d layout, seeded: every (pixel, entry) pair evaluated - the FP32-bound kernel)
     ctx.set_pruning(2)
     for _ in range(2):
@@ -804,7 +872,7 @@ def bench_config5(B, nx, ndb, steps):
     v = sobs[:, 3]
     cls_of = np.where(v > 0, 0, np.where(v < 0, 1, 2))
     ncand = int(cnt_of[ids, cls_of][st_local == 0].sum()) if n else 0
-    bk = float(np.mean(b_kern)) if len(b_kern) else float('nan')
+    bk = float(np.sum(b_kern)) / nb if len(b_kern) else float('nan')        # search-kernel time per step (a piece = a launch)
     frac = B.max_over_ranks(20.0 * ncand / (bk * 1e-3) / 1e12 / B.fp32_peak) if B.fp32_peak else None
     rec['bruteforce'] = dict(value=npix / (bms * 1e-3), unit='pixels/s', ms_per_step=bms, steps=nb, search_kernel_ms=B.max_over_ranks(bk),
                              search='brute force, every (pixel, entry) pair evaluated; k-d tile layout, seeded (cledb_set_pruning 2)',

@@ -282,10 +282,16 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  *                          flat indices in the map) are stored at their pixels' places in the maps block `maps` (a pointer
  *                          into the local window, the same offset on every rank) of every rank (root < 0) or of `root`
  *                          only.  When the call's work has run on the stream, every record of every rank is in place.
+ *   cledb_invert_gather_dev  peer transport: search + solutions + gather of this rank's shard as a PIPELINE (device pointers as in
+ *                          cledb_invert_dev, grid tables on the device).  The shard goes through in `pieces` contiguous pieces
+ *                          (0 = chosen from npix and the rank count: 2 from four ranks on when a piece still holds 64 Ki pixels, else 1; the same
+ *                          on every rank - every rank runs `pieces` pushes, also one with no pixels); the records of piece i
+ *                          cross NVLink - a k_push_records of a few blocks on the communicator's second stream - while piece
+ *                          i+1 is searched on the caller's stream; the caller's stream then waits for the last push.
  *   cledb_invert_sharded   cledb_invert for one map of npix pixels over all ranks: every rank passes the inputs of ITS
  *                          nlocal pixels (those of order[bounds[rank] : bounds[rank+1]], in that order; db_id = the ids
  *                          under which this rank put their databases), searches and builds them, writes the packed
- *                          records into the send buffer; then cledb_gather_maps_dev (peer transport) or ONE ncclAllGather +
+ *                          records into the send buffer; then cledb_invert_gather_dev (peer transport) or ONE ncclAllGather +
  *                          k_unshard; ranks with root < 0 or root == rank receive the full maps invout[npix,k,11] ... in
  *                          their host buffers (the others may pass NULL outputs).  Collective: every rank must call it. */
 #define CLEDB_COMM_ID_BYTES 128
@@ -305,6 +311,12 @@ int cledb_unshard_dev(cledb_ctx* ctx, int nranks, const int64_t* bounds_dev, con
 int cledb_map_layout(int64_t npix, int nsearch, int64_t layout[5]);
 int cledb_gather_maps_dev(cledb_ctx* ctx, int64_t npix, int64_t nlocal, const int32_t* my_order_dev, int64_t maxcount,
                           int nsearch, const void* send, void* maps, int root, void* stream);
+int cledb_invert_gather_dev(cledb_ctx* ctx, int mode, int precision, int64_t nlocal,
+                            const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
+                            const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,
+                            const void* dopp, int dopp_is_f64, const cledb_dbgrid* grid_dev,
+                            double maxchisq, int bcalc, int strict_topk,
+                            int64_t npix, const int32_t* my_order_dev, void* maps, int root, int pieces, void* stream);
 int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int64_t nlocal,
                          const float* sobs, const float* snr, const int32_t* db_id, int nsearch,
                          const float* yobs, const float* dobs, const float* rot_cos, const float* rot_sin,

@@ -64,15 +64,16 @@ def timed(fn, reps=6):
 
 ref = None
 for how in ('lsu', 'tma'):
-    for grid in (2, 3, 4, 8, 16):
+    for grid in ((2, 8) if world > 2 else (2, 3, 4, 8, 16)):
         for root in (-1, 0):
             os.environ['CLEDB_B200_PUSH'] = how
             os.environ['CLEDB_B200_PUSH_GRID'] = str(grid)
             mean, best = timed(lambda: ctx.gather_maps_dev(npix, n, mine.data_ptr(), maxcount, k, send.data_ptr(), win, root, stream.cuda_stream))
             out_mb = n * (k * 76 + 5) * ((world - 1) if root < 0 else (0 if rank == root else 1)) / 1e6
-            if rank == world - 1:
-                print('push %s grid %2d root %2d: %.3f ms mean  %.3f ms min   %.0f MB out of this rank -> %.0f GB/s' %
-                      (how, grid, root, mean, best, out_mb, out_mb / best / 1e3 if best else 0), flush=True)
+            in_mb = (npix - n) * (k * 76 + 5) / 1e6 if (root < 0 or root == rank) else 0.0
+            if rank == 0:
+                print('push %s grid %2d root %2d: %.3f ms mean  %.3f ms min   %.0f MB into rank 0 -> %.0f GB/s' %
+                      (how, grid, root, mean, best, in_mb, in_mb / best if best else 0), flush=True)
     ctx.gather_maps_dev(npix, n, mine.data_ptr(), maxcount, k, send.data_ptr(), win, -1, stream.cuda_stream)
     torch.cuda.synchronize()
     dist.barrier()

@@ -71,6 +71,8 @@ SIGNATURES = {
     'cledb_allgather_dev': (_c.c_int, [_P, _P, _P, _c.c_int64, _P]),
     'cledb_map_layout': (_c.c_int, [_c.c_int64, _c.c_int, _P]),
     'cledb_gather_maps_dev': (_c.c_int, [_P, _c.c_int64, _c.c_int64, _P, _c.c_int64, _c.c_int, _P, _P, _c.c_int, _P]),
+    'cledb_invert_gather_dev': (_c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P, _P, _P, _P, _c.c_int, _P,
+                                           _c.c_double, _c.c_int, _c.c_int, _c.c_int64, _P, _P, _c.c_int, _c.c_int, _P]),
     'cledb_partition': (_c.c_int, [_c.c_int64, _P, _c.c_int, _P, _c.c_int, _P, _P]),
     'cledb_shard_layout': (_c.c_int, [_c.c_int64, _c.c_int, _P]),
     'cledb_unshard_dev': (_c.c_int, [_P, _c.c_int, _P, _P, _c.c_int64, _c.c_int64, _c.c_int, _P, _P, _P, _P, _P, _P]),
@@ -571,6 +573,16 @@ class Context:
                     issue_ptr, stream=None):
         self._check(self.lib.cledb_unshard_dev(self.h, int(nranks), bounds_ptr, order_ptr, int(npix), int(maxcount), int(nsearch),
                                                recv_ptr, invout_ptr, sfound_ptr, status_ptr, issue_ptr, stream))
+
+    def invert_gather_dev(self, mode, nlocal, sobs_ptr, snr_ptr, dbid_ptr, nsearch, yobs_ptr, dobs_ptr, rc_ptr, rs_ptr, dopp_ptr, dopp_is_f64,
+                          grid, maxchisq, bcalc, npix, my_order_ptr, maps_ptr, root=-1, pieces=0, stream=None, strict_topk=False,
+                          precision=PREC_FP32):
+        """cledb_invert_gather_dev (peer transport): the shard searched and built in ``pieces`` pieces, the records of a piece
+        stored at their pixels in the maps of every rank while the next piece is searched."""
+        self._check(self.lib.cledb_invert_gather_dev(self.h, int(mode), int(precision), int(nlocal), sobs_ptr, snr_ptr, dbid_ptr, int(nsearch),
+                                                     yobs_ptr, dobs_ptr, rc_ptr, rs_ptr, dopp_ptr, int(dopp_is_f64), ctypes.addressof(grid),
+                                                     float(maxchisq), int(bcalc), 1 if strict_topk else 0, int(npix), my_order_ptr,
+                                                     maps_ptr, int(root), int(pieces), stream))
 
     def invert_dev(self, mode, npix, sobs_ptr, snr_ptr, dbid_ptr, nsearch, yobs_ptr, dobs_ptr, rc_ptr, rs_ptr, dopp_ptr, dopp_is_f64,
                    grid, maxchisq, bcalc, invout_ptr, sfound_ptr, status_ptr, issue_ptr, stream=None, strict_topk=False,

@@ -62,6 +62,7 @@ extern "C" int cledb_destroy(cledb_ctx* ctx) {
     if (ctx->d_prune_stats) cudaFree(ctx->d_prune_stats);
     if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->d_tab) cudaFree(ctx->d_tab);
     if (ctx->io.ptr) cudaFree(ctx->io.ptr);
     for (auto& pr : ctx->prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

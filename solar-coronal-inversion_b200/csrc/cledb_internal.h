@@ -98,6 +98,8 @@ struct cledb_ctx {
     cledb::Workspace red;                          // small tables of the reduced search
     cledb::Workspace raw;                          // raw search outputs of the fused search + solution call
     cledb::Workspace io;                           // staging for the host entry points
+    float* d_tab = nullptr;                        // sin / cos tables of the grid angles as last uploaded (grid_to_device)
+    std::vector<float> tab_host;                   // their host copy: an unchanged grid is not uploaded again
     int32_t* h_cnt = nullptr;                      // mapped pinned host copy of the bucket sizes
     int32_t* d_cnt_mapped = nullptr;               // its device alias
     size_t h_cnt_cap = 0;
@@ -179,6 +181,9 @@ int  launch_qurotate(cledb_ctx* ctx, int nx, int ny, const double* xs, const dou
 }  // namespace cledb
 
 namespace cledb {
+// *g_dev = *grid with the four table pointers replaced by device copies (kept on the context; uploaded on `st` only when the
+// caller's tables differ from the ones already there).  One in-flight call per context, as everywhere.
+int grid_to_device(cledb_ctx* ctx, const cledb_dbgrid* grid, cledb_dbgrid* g_dev, cudaStream_t st);
 int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsearch, const float* sobs, const float* yobs,
                  const float* dobs, const float* rot_cos, const float* rot_sin, const void* dopp, int dopp_is_f64,
                  int64_t dopp_stride, const cledb_dbgrid& grid_dev, double maxchisq, int bcalc, int strict_topk,

@@ -78,13 +78,14 @@ std::string nccl_text(int rc) { return g_nccl.error_string ? g_nccl.error_string
 // them into every rank's receive buffer, k_unshard reads that buffer and writes the maps.  With the maps of every rank
 // mapped into every process the push kernels below store each record ONCE, straight at its pixel's place in every rank's
 // maps (16-byte vectors, whole rows, NVLink / NVSwitch as the store target), and the only things left of the collective
-// are two rounds of flags:
-//   free[e]  "my window may be overwritten by operation e"      sent when a rank's stream reaches operation e
-//   done[e]  "all my stores of operation e have been performed" sent by the last block of the push kernel
+// are two rounds of flags inside that one kernel:
+//   free[e]  "my window may be overwritten by operation e"      sent by block 0 when the push kernel starts; every block waits for all
+//   done[e]  "all my stores of operation e have been performed" sent by the block that finishes last, which then waits for all
 // Flags are 32-bit epochs in a small IPC allocation of their own; every rank writes its own slot in every peer's array
 // (st.release.sys after __threadfence_system) and spins on its local array (ld.acquire.sys).  Collective calls come in the
 // same order on every rank, so the host-side epoch counters agree without any exchange.
 constexpr int kMaxRanks = 16;
+constexpr int kMaxPieces = 8;         // pieces of a shard in the pipelined gather
 constexpr int kFlagFree = 0, kFlagDone = 32, kFlagCount = 64, kFlagWords = 128;      // word offsets inside the flag array
 constexpr long long kSpinLimitNs = 20LL * 1000 * 1000 * 1000;                         // a peer that never arrives: give up, report
 
@@ -107,6 +108,8 @@ struct cledb_comm {
     unsigned* flags_local = nullptr;
     void* flags_opened[kMaxRanks] = {};         // what cudaIpcOpenMemHandle returned (block bases), for cudaIpcCloseMemHandle
     void* win_opened[kMaxRanks] = {};
+    cudaStream_t side = nullptr;                // second stream + events of the pipelined gather (cledb_invert_gather_dev)
+    cudaEvent_t ev[kMaxPieces + 1] = {};
     void* win = nullptr;                        // local window (plain allocation when peer_ok is false)
     std::vector<size_t> win_bytes;              // size of every rank's window, tracked identically on all ranks
     unsigned epoch = 0;
@@ -139,8 +142,20 @@ __device__ __forceinline__ void wait_flags(const Peers& P, int which, unsigned e
 __device__ __forceinline__ void signal_flags(const Peers& P, int which, unsigned epoch) {
     if ((int)threadIdx.x < P.n) st_release_sys(P.flags[threadIdx.x] + which + P.me, epoch);
 }
-// every thread has fenced its stores; the block that arrives last at the counter tells every peer that this rank is done
-__device__ __forceinline__ void block_done(const Peers& P, unsigned epoch) {
+// A push kernel opens with this: block 0 tells every peer that this rank's window may be overwritten by operation `epoch`
+// (everything that read the window was enqueued before this kernel), every block waits until all peers have said the same.
+__device__ __forceinline__ void block_open(const Peers& P, unsigned epoch, int32_t* err_mapped) {
+    if (blockIdx.x == 0) {
+        __threadfence_system();
+        signal_flags(P, kFlagFree, epoch);
+    }
+    wait_flags(P, kFlagFree, epoch, err_mapped);
+    __syncthreads();
+}
+// ... and closes with this: every thread has fenced its stores; the block that arrives last at the counter tells every peer
+// that this rank is done and then waits for the done flags of all peers, so the kernel's completion on the stream means
+// that every record of every rank is in place in this rank's window.
+__device__ __forceinline__ void block_done(const Peers& P, unsigned epoch, int32_t* err_mapped) {
     __shared__ int last;
     __threadfence_system();
     __syncthreads();
@@ -150,20 +165,15 @@ __device__ __forceinline__ void block_done(const Peers& P, unsigned epoch) {
         if (threadIdx.x == 0) P.flags[P.me][kFlagCount] = 0;
         __threadfence_system();
         signal_flags(P, kFlagDone, epoch);
+        wait_flags(P, kFlagDone, epoch, err_mapped);
     }
 }
 
-__global__ void k_peer_signal(Peers P, int which, unsigned epoch) {
-    __threadfence_system();
-    signal_flags(P, which, epoch);
-}
-__global__ void k_peer_wait(Peers P, int which, unsigned epoch, int32_t* err_mapped) { wait_flags(P, which, epoch, err_mapped); }
 
 // all-gather of contiguous blocks: the 16-byte vectors of this rank's block go to the same place of every rank's window
 __global__ void __launch_bounds__(512) k_push_block(Peers P, const uint4* __restrict__ send, size_t nvec, size_t dst_off, unsigned epoch,
                                                     int32_t* err_mapped) {
-    wait_flags(P, kFlagFree, epoch, err_mapped);
-    __syncthreads();
+    block_open(P, epoch, err_mapped);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         const uint4 v = __ldcs(send + i);
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(512) k_push_block(Peers P, const uint4* __rest
             reinterpret_cast<uint4*>(P.base[r] + dst_off)[i] = v;
         }
     }
-    block_done(P, epoch);
+    block_done(P, epoch, err_mapped);
 }
 }  // namespace
 
@@ -381,6 +391,10 @@ extern "C" int cledb_comm_destroy(cledb_ctx* ctx) {
     unmap_peers(c, c->flags_opened);
     if (c->nranks > 1 && c->comm) comm_quiesce(ctx);
     if (c->flags_local) cudaFree(c->flags_local);
+    if (c->side) {
+        cudaStreamDestroy(c->side);
+        for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
+    }
     if (c->comm) g_nccl.comm_destroy(c->comm);
     for (Workspace* w : {&c->send, &c->recv, &c->order, &c->scratch})
         if (w->ptr) cudaFree(w->ptr);
@@ -500,10 +514,8 @@ extern "C" int cledb_allgather_dev(cledb_ctx* ctx, const void* send, void* recv,
         const size_t nvec = (size_t)bytes / 16;
         const size_t off = (size_t)(reinterpret_cast<unsigned char*>(recv) - reinterpret_cast<unsigned char*>(c->win)) + (size_t)c->rank * (size_t)bytes;
         const unsigned grid = (unsigned)std::min<size_t>((nvec + 511) / 512, (size_t)ctx->prop.multiProcessorCount * 2);
-        k_peer_signal<<<1, 32, 0, st>>>(c->peers, kFlagFree, e);
         k_push_block<<<grid, 512, 0, st>>>(c->peers, reinterpret_cast<const uint4*>(send), nvec, off, e, comm_err_word(ctx));
-        k_peer_wait<<<1, 32, 0, st>>>(c->peers, kFlagDone, e, comm_err_word(ctx));
-        return after_launch(ctx, 3);
+        return after_launch(ctx);
     }
     if (c->nranks == 1) {
         if (send != recv) CLEDB_CUDA(ctx, cudaMemcpyAsync(recv, send, (size_t)bytes, cudaMemcpyDeviceToDevice, st));
@@ -611,8 +623,7 @@ __global__ void __launch_bounds__(256) k_push_records(Peers P, unsigned dst_mask
                                                       const unsigned char* __restrict__ send, size_t o_inv, size_t o_sf, size_t o_st, size_t o_iss,
                                                       size_t m_inv, size_t m_sf, size_t m_st, size_t m_iss, unsigned epoch,
                                                       int32_t* err_mapped) {
-    wait_flags(P, kFlagFree, epoch, err_mapped);
-    __syncthreads();
+    block_open(P, epoch, err_mapped);
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -695,88 +706,9 @@ __global__ void __launch_bounds__(256) k_push_records(Peers P, unsigned dst_mask
             reinterpret_cast<int32_t*>(P.base[lane] + m_iss)[p] = reinterpret_cast<const int32_t*>(send + o_iss)[j];
         }
     }
-    block_done(P, epoch);
+    block_done(P, epoch, err_mapped);
 }
 
-// The same push through the TMA engine: a warp stages the rows of eight consecutive pixels of the shard in shared memory
-// with two bulk loads (they are contiguous in the send buffer), then its lanes issue one bulk store per (pixel, row,
-// destination) - cp.async.bulk.global.shared::cta, 352- and 256-byte pieces at nsearch 8 - so the copy engine of the SM, not
-// the load/store unit, forms the NVLink writes.  Rows must be multiples of 16 bytes (nsearch % 4 == 0).
-constexpr int kPushG = 8;            // pixels per trip of a warp
-constexpr int kPushWarps = 8;        // warps per block
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__global__ void __launch_bounds__(kPushWarps * 32) k_push_records_tma(Peers P, unsigned dst_mask, const int32_t* __restrict__ my_order, int64_t nlocal,
-                                                                      int k, const unsigned char* __restrict__ send, size_t o_inv, size_t o_sf,
-                                                                      size_t o_st, size_t o_iss, size_t m_inv, size_t m_sf, size_t m_st,
-                                                                      size_t m_iss, unsigned epoch, int32_t* err_mapped) {
-    extern __shared__ __align__(128) unsigned char stage_all[];
-    __shared__ uint64_t bars[kPushWarps];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t bi = (uint32_t)k * 44u, bs = (uint32_t)k * 32u;            // bytes of an invout / sfound row
-    unsigned char* stage = stage_all + (size_t)wib * kPushG * (bi + bs);
-    uint64_t* bar = bars + wib;
-    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(1) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    wait_flags(P, kFlagFree, epoch, err_mapped);
-    __syncthreads();
-    const int64_t nwarps = (int64_t)gridDim.x * kPushWarps;
-    const int64_t warp = (int64_t)blockIdx.x * kPushWarps + wib;
-    uint32_t parity = 0;
-    int ndst = 0;
-    for (int r = 0; r < P.n; ++r) ndst += dst_mask >> r & 1;
-    for (int64_t j0 = warp * kPushG; j0 < nlocal; j0 += nwarps * kPushG) {
-        const int g = (int)min((int64_t)kPushG, nlocal - j0);
-        if (lane == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"((uint32_t)g * (bi + bs)) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(stage)),
-                         "l"(send + o_inv + (size_t)j0 * bi), "r"((uint32_t)g * bi), "r"(smem_addr(bar)) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(stage + kPushG * bi)),
-                         "l"(send + o_sf + (size_t)j0 * bs), "r"((uint32_t)g * bs), "r"(smem_addr(bar)) : "memory");
-        }
-        int64_t pl = -1;                                            // lane u < g: the place of pixel u
-        uint8_t stv = 0;
-        int32_t isv = 0;
-        if (lane < g) {
-            pl = my_order[j0 + lane];
-            stv = send[o_st + j0 + lane];
-            isv = reinterpret_cast<const int32_t*>(send + o_iss)[j0 + lane];
-        }
-        {
-            uint32_t done;
-            do {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-            } while (!done);
-        }
-        parity ^= 1;
-        const int first = (int)((j0 / kPushG) % P.n);
-        // one bulk store per (destination, row kind, pixel): t = (q * 2 + kind) * g + u
-        const int total = ndst * 2 * g;
-        for (int t = lane; t < total; t += 32) {
-            const int u = t % g, kind = (t / g) & 1, qd = t / (2 * g);
-            int r = first, seen = -1;
-            for (int c = 0; c < P.n; ++c) {                        // the qd-th destination of the mask, starting at `first`
-                const int rr = (first + c) % P.n;
-                if (dst_mask >> rr & 1) { if (++seen == qd) { r = rr; break; } }
-            }
-            const int64_t pu = __shfl_sync(__activemask(), pl, u);
-            unsigned char* dst = P.base[r] + (kind ? m_sf + (size_t)pu * bs : m_inv + (size_t)pu * bi);
-            const unsigned char* src = stage + (kind ? kPushG * bi + (uint32_t)u * bs : (uint32_t)u * bi);
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(kind ? bs : bi) : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (pl >= 0)
-            for (int r = 0; r < P.n; ++r)
-                if (dst_mask >> r & 1) {
-                    (P.base[r] + m_st)[pl] = stv;
-                    reinterpret_cast<int32_t*>(P.base[r] + m_iss)[pl] = isv;
-                }
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the stage may be refilled
-        __syncwarp();
-    }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");                  // every bulk store of this thread has been performed
-    block_done(P, epoch);
-}
 }  // namespace cledb
 
 extern "C" int cledb_shard_layout(int64_t maxcount, int nsearch, int64_t layout[5]) {
@@ -829,14 +761,13 @@ extern "C" int cledb_map_layout(int64_t npix, int nsearch, int64_t layout[5]) {
     return CLEDB_OK;
 }
 
-extern "C" int cledb_gather_maps_dev(cledb_ctx* ctx, int64_t npix, int64_t nlocal, const int32_t* my_order_dev, int64_t maxcount,
-                                     int nsearch, const void* send, void* maps, int root, void* stream) {
-    if (!ctx) return CLEDB_ERR_ARG;
+// enqueue k_push_records; blocks > 0 bounds the grid (a push that runs beside a search leaves the other SMs to the search)
+static int push_records(cledb_ctx* ctx, int64_t npix, int64_t nlocal, const int32_t* my_order_dev, int64_t maxcount, int nsearch,
+                        const void* send, void* maps, int root, int blocks, cudaStream_t st, const char* who) {
     cledb_comm* c = ctx->comm;
-    if (!c) { ctx->err = "cledb_gather_maps: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
-    if (c->transport != 1) { ctx->err = "cledb_gather_maps: needs the peer-memory transport (cledb_comm_transport); use cledb_allgather_dev + cledb_unshard_dev"; return CLEDB_ERR_COMM; }
+    if (c->transport != 1) { ctx->err = std::string(who) + ": needs the peer-memory transport (cledb_comm_transport); use cledb_allgather_dev + cledb_unshard_dev"; return CLEDB_ERR_COMM; }
     if (npix < 0 || nlocal < 0 || nlocal > maxcount || nsearch < 1 || !maps || root >= c->nranks || (nlocal > 0 && (!my_order_dev || !send))) {
-        ctx->err = "cledb_gather_maps: bad argument";
+        ctx->err = std::string(who) + ": bad argument";
         return CLEDB_ERR_ARG;
     }
     const Maps M = map_layout(npix, nsearch);
@@ -847,41 +778,98 @@ extern "C" int cledb_gather_maps_dev(cledb_ctx* ctx, int64_t npix, int64_t nloca
             if (root < 0 || root == r) fits = fits && woff0 + M.bytes <= c->win_bytes[(size_t)r];
     }
     if (!fits) {
-        ctx->err = "cledb_gather_maps: `maps` must be a 256-byte aligned block of cledb_map_layout bytes inside the window (cledb_comm_window)";
+        ctx->err = std::string(who) + ": `maps` must be a 256-byte aligned block of cledb_map_layout bytes inside the window (cledb_comm_window)";
         return CLEDB_ERR_ARG;
     }
-    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     const Packed L = packed_layout(maxcount, nsearch);
     const size_t woff = (size_t)(reinterpret_cast<unsigned char*>(maps) - reinterpret_cast<unsigned char*>(c->win));
     const unsigned mask = root < 0 ? (1u << c->nranks) - 1u : 1u << root;
     const unsigned e = ++c->epoch;
-    const char* pg = std::getenv("CLEDB_B200_PUSH_GRID");                 // tuning: blocks per SM of the push kernels
-    const int push_grid = pg ? std::atoi(pg) : 0;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((nlocal * 32 + 255) / 256, (int64_t)ctx->prop.multiProcessorCount * (push_grid > 0 ? push_grid : 8)));
+    const char* pg = std::getenv("CLEDB_B200_PUSH_GRID");                 // tuning: blocks per SM of the push kernel
+    const int per_sm = pg && std::atoi(pg) > 0 ? std::atoi(pg) : 8;
+    int64_t grid = std::min<int64_t>((nlocal * 32 + 255) / 256, (int64_t)ctx->prop.multiProcessorCount * per_sm);
+    if (blocks > 0) grid = std::min<int64_t>(grid, blocks);
+    grid = std::max<int64_t>(grid, 1);
     const unsigned char* s8 = reinterpret_cast<const unsigned char*>(send);
-    k_peer_signal<<<1, 32, 0, st>>>(c->peers, kFlagFree, e);
-    const char* how = std::getenv("CLEDB_B200_PUSH");
-    const size_t stage_bytes = (size_t)kPushWarps * kPushG * (size_t)nsearch * 76;
-    if (how && how[0] == 't' && nsearch % 4 == 0 && stage_bytes <= 200 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            CLEDB_CUDA(ctx, cudaFuncSetAttribute(k_push_records_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
-        const int per_sm = std::max(1, std::min(8, (int)((size_t)200 * 1024 / stage_bytes)));
-        const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((nlocal + kPushG * kPushWarps - 1) / (kPushG * kPushWarps),
-                                                                                (int64_t)ctx->prop.multiProcessorCount * (push_grid > 0 ? std::min(push_grid, per_sm) : std::min(4, per_sm))));
-        k_push_records_tma<<<tgrid, kPushWarps * 32, stage_bytes, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss,
-                                                                        woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx));
-    } else if (nsearch % 4 == 0)
-        k_push_records<true><<<grid, 256, 0, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss,
-                                                   woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx));
+    if (nsearch % 4 == 0)
+        k_push_records<true><<<(unsigned)grid, 256, 0, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss,
+                                                             woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx));
     else
-        k_push_records<false><<<grid, 256, 0, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss,
-                                                    woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx));
-    k_peer_wait<<<1, 32, 0, st>>>(c->peers, kFlagDone, e, comm_err_word(ctx));
-    return after_launch(ctx, 3);
+        k_push_records<false><<<(unsigned)grid, 256, 0, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss,
+                                                              woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx));
+    return after_launch(ctx);
+}
+
+extern "C" int cledb_gather_maps_dev(cledb_ctx* ctx, int64_t npix, int64_t nlocal, const int32_t* my_order_dev, int64_t maxcount,
+                                     int nsearch, const void* send, void* maps, int root, void* stream) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    if (!ctx->comm) { ctx->err = "cledb_gather_maps: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return push_records(ctx, npix, nlocal, my_order_dev, maxcount, nsearch, send, maps, root, 0, stream ? (cudaStream_t)stream : ctx->stream,
+                        "cledb_gather_maps");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// search + solutions + gather of a shard as a pipeline: the shard goes through in pieces, and the records of piece i
+// cross NVLink (a narrow k_push_records on the communicator's second stream) while piece i+1 is being searched
+// ------------------------------------------------------------------------------------------------------
+extern "C" int cledb_invert_gather_dev(cledb_ctx* ctx, int mode, int precision, int64_t nlocal, const float* sobs, const float* snr,
+                                       const int32_t* db_id, int nsearch, const float* yobs, const float* dobs, const float* rot_cos,
+                                       const float* rot_sin, const void* dopp, int dopp_is_f64, const cledb_dbgrid* grid_dev,
+                                       double maxchisq, int bcalc, int strict_topk, int64_t npix, const int32_t* my_order_dev, void* maps,
+                                       int root, int pieces, void* stream) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    cledb_comm* c = ctx->comm;
+    if (!c) { ctx->err = "cledb_invert_gather: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
+    if (c->transport != 1) { ctx->err = "cledb_invert_gather: needs the peer-memory transport (cledb_comm_transport)"; return CLEDB_ERR_COMM; }
+    if (nlocal < 0 || npix < nlocal || pieces < 0 || pieces > kMaxPieces) { ctx->err = "cledb_invert_gather: bad argument"; return CLEDB_ERR_ARG; }
+    CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if (pieces == 0) {
+        // every rank must run the same number of pushes, so the choice depends on the map and the rank count only.  A search call
+        // has a fixed cost of about 0.3 ms (its launches and the tail of its longest work item), a second piece hides half of the
+        // NVLink time of the shard: that pays from four ranks on (each rank then receives >= 3/4 of the map), with pieces that
+        // still fill the GPU (64 Ki pixels)
+        const char* e = std::getenv("CLEDB_B200_PIECES");
+        pieces = e && std::atoi(e) > 0 ? std::min(std::atoi(e), kMaxPieces) : (c->nranks >= 4 && npix / c->nranks >= 2 * 65536 - 8 ? 2 : 1);
+    }
+    if (pieces > 1 && !c->side) {
+        CLEDB_CUDA(ctx, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxPieces + 1; ++i) CLEDB_CUDA(ctx, cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
+    }
+    // packed records of every piece, one block per piece
+    const int64_t per = (nlocal + pieces - 1) / pieces;
+    const Packed L = packed_layout(std::max<int64_t>(per, 1), nsearch);
+    int rc;
+    if ((rc = ensure_workspace(ctx, c->send, L.bytes * (size_t)pieces))) return rc;
+    const char* sb = std::getenv("CLEDB_B200_PUSH_SIDE");                // tuning: blocks of a push that runs beside a search
+    const int side_blocks = sb && std::atoi(sb) > 0 ? std::atoi(sb) : 16;
+    const size_t dsz = dopp ? (dopp_is_f64 ? 8 : 4) : 0;
+    for (int i = 0; i < pieces; ++i) {                   // a rank with nothing (left) still pushes: the others wait for its flags
+        const int64_t j0 = std::min(per * i, nlocal), n = std::min(per, nlocal - j0);
+        unsigned char* send = reinterpret_cast<unsigned char*>(c->send.ptr) + L.bytes * (size_t)i;
+        if (n > 0) {
+            rc = cledb_invert_dev(ctx, mode, precision, n, sobs + j0 * 8, snr + j0 * 8, db_id + j0, nsearch, yobs + j0, dobs + j0, rot_cos + j0,
+                                  rot_sin + j0, dopp ? reinterpret_cast<const unsigned char*>(dopp) + (size_t)j0 * dsz : nullptr, dopp_is_f64, 1,
+                                  grid_dev, maxchisq, bcalc, strict_topk, reinterpret_cast<float*>(send + L.o_inv),
+                                  reinterpret_cast<float*>(send + L.o_sf), send + L.o_st, reinterpret_cast<int32_t*>(send + L.o_iss), st);
+            if (rc) return rc;
+        }
+        cudaStream_t ps = st;
+        if (pieces > 1) {                                // every push on the second stream, in order: one operation at a time
+            CLEDB_CUDA(ctx, cudaEventRecord(c->ev[i], st));
+            CLEDB_CUDA(ctx, cudaStreamWaitEvent(c->side, c->ev[i], 0));
+            ps = c->side;
+        }
+        rc = push_records(ctx, npix, n, my_order_dev + j0, std::max<int64_t>(per, 1), nsearch, send, maps, root,
+                          i + 1 < pieces ? side_blocks : 0, ps, "cledb_invert_gather");
+        if (rc) return rc;
+    }
+    if (pieces > 1) {
+        CLEDB_CUDA(ctx, cudaEventRecord(c->ev[kMaxPieces], c->side));
+        CLEDB_CUDA(ctx, cudaStreamWaitEvent(st, c->ev[kMaxPieces], 0));
+    }
+    return CLEDB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -927,8 +915,7 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
     auto take = [&](size_t b) { size_t o = off; off = up256(off + b); return o; };
     const size_t nn = std::max<size_t>(n, 1);
     const size_t o_sobs = take(nn * 32), o_snr = take(nn * 32), o_id = take(nn * 4), o_y = take(nn * 4), o_d = take(nn * 4),
-                 o_rc = take(nn * 4), o_rs = take(nn * 4), o_dopp = take(nn * dsz),
-                 o_tab = take((size_t)(2 * grid->nbphi + 2 * grid->nbtheta) * 4);
+                 o_rc = take(nn * 4), o_rs = take(nn * 4), o_dopp = take(nn * dsz);
     int rc;
     const Maps M = map_layout(npix, nsearch);
     {
@@ -938,7 +925,7 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
     }
     const bool peer = c->transport == 1;
     if ((rc = ensure_workspace(ctx, ctx->io, off))) return rc;
-    if ((rc = ensure_workspace(ctx, c->send, L.bytes))) return rc;
+    if (!peer && (rc = ensure_workspace(ctx, c->send, L.bytes))) return rc;
     if (!peer && (rc = ensure_workspace(ctx, c->recv, L.bytes * (size_t)R))) return rc;
     const size_t o_bounds = up256((size_t)npix * 4);
     if ((rc = ensure_workspace(ctx, c->order, o_bounds + ((size_t)R + 1) * 8))) return rc;
@@ -957,16 +944,8 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
             else CLEDB_CUDA(ctx, cudaMemcpy2DAsync(w + o_dopp, dsz, dopp, (size_t)dopp_stride * dsz, dsz, n, cudaMemcpyHostToDevice, st));
         }
     }
-    cledb_dbgrid g = *grid;
-    float* tab = reinterpret_cast<float*>(w + o_tab);
-    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab, grid->sin_bphi, (size_t)g.nbphi * 4, cudaMemcpyHostToDevice, st));
-    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab + g.nbphi, grid->cos_bphi, (size_t)g.nbphi * 4, cudaMemcpyHostToDevice, st));
-    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab + 2 * g.nbphi, grid->sin_btheta, (size_t)g.nbtheta * 4, cudaMemcpyHostToDevice, st));
-    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab + 2 * g.nbphi + g.nbtheta, grid->cos_btheta, (size_t)g.nbtheta * 4, cudaMemcpyHostToDevice, st));
-    g.sin_bphi = tab;
-    g.cos_bphi = tab + g.nbphi;
-    g.sin_btheta = tab + 2 * g.nbphi;
-    g.cos_btheta = tab + 2 * g.nbphi + g.nbtheta;
+    cledb_dbgrid g;
+    if ((rc = grid_to_device(ctx, grid, &g, st))) return rc;
     unsigned char* dord = reinterpret_cast<unsigned char*>(c->order.ptr);
     if (peer) {                                          // a rank pushes its own pixels: it needs their places, nothing else
         if (n > 0) CLEDB_CUDA(ctx, cudaMemcpyAsync(dord, order + bounds[me], n * 4, cudaMemcpyHostToDevice, st));
@@ -975,21 +954,26 @@ extern "C" int cledb_invert_sharded(cledb_ctx* ctx, int mode, int precision, int
         CLEDB_CUDA(ctx, cudaMemcpyAsync(dord + o_bounds, bounds, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, st));
     }
 
-    // ---- search + solutions of the shard, written straight into the packed send buffer
-    unsigned char* send = reinterpret_cast<unsigned char*>(c->send.ptr);
-    if (n > 0) {
-        rc = cledb_invert_dev(ctx, mode, precision, nlocal, reinterpret_cast<float*>(w + o_sobs), reinterpret_cast<float*>(w + o_snr),
-                              reinterpret_cast<int32_t*>(w + o_id), nsearch, reinterpret_cast<float*>(w + o_y), reinterpret_cast<float*>(w + o_d),
-                              reinterpret_cast<float*>(w + o_rc), reinterpret_cast<float*>(w + o_rs), dsz ? w + o_dopp : nullptr, dopp_is_f64, 1,
-                              &g, maxchisq, bcalc, strict_topk, reinterpret_cast<float*>(send + L.o_inv), reinterpret_cast<float*>(send + L.o_sf),
-                              send + L.o_st, reinterpret_cast<int32_t*>(send + L.o_iss), st);
-        if (rc) return rc;        // a rank that fails here leaves the others waiting in the collective: the launcher aborts the job
-    }
-    // ---- the one collective of the path: every record to its pixel's place in the maps of the ranks that want them
     unsigned char* f = reinterpret_cast<unsigned char*>(c->win);
     if (peer) {
-        if ((rc = cledb_gather_maps_dev(ctx, npix, nlocal, reinterpret_cast<int32_t*>(dord), maxcount, nsearch, send, f, root, st))) return rc;
+        // ---- search + solutions of the shard in pieces, each piece's records stored at their pixels in the maps of the ranks
+        //      that want them while the next piece is searched
+        rc = cledb_invert_gather_dev(ctx, mode, precision, nlocal, reinterpret_cast<float*>(w + o_sobs), reinterpret_cast<float*>(w + o_snr),
+                                     reinterpret_cast<int32_t*>(w + o_id), nsearch, reinterpret_cast<float*>(w + o_y), reinterpret_cast<float*>(w + o_d),
+                                     reinterpret_cast<float*>(w + o_rc), reinterpret_cast<float*>(w + o_rs), dsz ? w + o_dopp : nullptr, dopp_is_f64,
+                                     &g, maxchisq, bcalc, strict_topk, npix, reinterpret_cast<int32_t*>(dord), f, root, 0, st);
+        if (rc) return rc;        // a rank that fails here leaves the others waiting in the collective: the launcher aborts the job
     } else {
+        // ---- search + solutions of the shard, written straight into the packed send buffer; ONE all-gather; scatter
+        unsigned char* send = reinterpret_cast<unsigned char*>(c->send.ptr);
+        if (n > 0) {
+            rc = cledb_invert_dev(ctx, mode, precision, nlocal, reinterpret_cast<float*>(w + o_sobs), reinterpret_cast<float*>(w + o_snr),
+                                  reinterpret_cast<int32_t*>(w + o_id), nsearch, reinterpret_cast<float*>(w + o_y), reinterpret_cast<float*>(w + o_d),
+                                  reinterpret_cast<float*>(w + o_rc), reinterpret_cast<float*>(w + o_rs), dsz ? w + o_dopp : nullptr, dopp_is_f64, 1,
+                                  &g, maxchisq, bcalc, strict_topk, reinterpret_cast<float*>(send + L.o_inv), reinterpret_cast<float*>(send + L.o_sf),
+                                  send + L.o_st, reinterpret_cast<int32_t*>(send + L.o_iss), st);
+            if (rc) return rc;
+        }
         if ((rc = cledb_allgather_dev(ctx, send, c->recv.ptr, (int64_t)L.bytes, st))) return rc;
         if (want) {
             rc = cledb_unshard_dev(ctx, R, reinterpret_cast<int64_t*>(dord + o_bounds), reinterpret_cast<int32_t*>(dord), npix, maxcount, nsearch,

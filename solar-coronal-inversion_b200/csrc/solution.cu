@@ -263,6 +263,33 @@ int launch_build(cledb_ctx* ctx, int mode, int precision, int64_t npix, int nsea
     return CLEDB_OK;
 }
 
+int grid_to_device(cledb_ctx* ctx, const cledb_dbgrid* grid, cledb_dbgrid* g_dev, cudaStream_t st) {
+    const size_t nphi = (size_t)grid->nbphi, nth = (size_t)grid->nbtheta, n = 2 * nphi + 2 * nth;
+    std::vector<float> now(n);
+    std::memcpy(now.data(), grid->sin_bphi, nphi * 4);
+    std::memcpy(now.data() + nphi, grid->cos_bphi, nphi * 4);
+    std::memcpy(now.data() + 2 * nphi, grid->sin_btheta, nth * 4);
+    std::memcpy(now.data() + 2 * nphi + nth, grid->cos_btheta, nth * 4);
+    const bool same = ctx->d_tab && now.size() == ctx->tab_host.size() && std::memcmp(now.data(), ctx->tab_host.data(), n * 4) == 0;
+    if (!same) {
+        if (!ctx->d_tab || now.size() > ctx->tab_host.capacity() || now.size() != ctx->tab_host.size()) {
+            CLEDB_CUDA(ctx, cudaStreamSynchronize(st));                 // nothing reads the old tables any more
+            if (ctx->d_tab) cudaFree(ctx->d_tab);
+            ctx->d_tab = nullptr;
+            ctx->tab_host.clear();
+            if (cudaMalloc(&ctx->d_tab, n * 4) != cudaSuccess) { cudaGetLastError(); ctx->err = "out of device memory (grid tables)"; return CLEDB_ERR_NOMEM; }
+        }
+        ctx->tab_host.swap(now);                                        // the copy below reads the context's own buffer
+        CLEDB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tab, ctx->tab_host.data(), n * 4, cudaMemcpyHostToDevice, st));
+    }
+    *g_dev = *grid;
+    g_dev->sin_bphi = ctx->d_tab;
+    g_dev->cos_bphi = ctx->d_tab + nphi;
+    g_dev->sin_btheta = ctx->d_tab + 2 * nphi;
+    g_dev->cos_btheta = ctx->d_tab + 2 * nphi + nth;
+    return CLEDB_OK;
+}
+
 }  // namespace cledb
 
 using namespace cledb;
@@ -349,8 +376,7 @@ extern "C" int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npi
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off = up256(off + b); return o; };
     const size_t o_sobs = take(n * 32), o_snr = take(n * 32), o_id = take(n * 4), o_y = take(n * 4), o_d = take(n * 4),
-                 o_rc = take(n * 4), o_rs = take(n * 4), o_dopp = take(n * dsz),
-                 o_tab = take((size_t)(2 * grid->nbphi + 2 * grid->nbtheta) * 4), o_inv = take(n * k * 44), o_sf = take(n * k * 32),
+                 o_rc = take(n * 4), o_rs = take(n * 4), o_dopp = take(n * dsz), o_inv = take(n * k * 44), o_sf = take(n * k * 32),
                  o_st = take(n), o_iss = take(n * 4);
     if ((rc = ensure_workspace(ctx, ctx->io, off))) return rc;
     unsigned char* w = reinterpret_cast<unsigned char*>(ctx->io.ptr);
@@ -368,16 +394,8 @@ extern "C" int cledb_invert(cledb_ctx* ctx, int mode, int precision, int64_t npi
         else CLEDB_CUDA(ctx, cudaMemcpy2DAsync(w + o_dopp, dsz, dopp, (size_t)dopp_stride * dsz, dsz, n, cudaMemcpyHostToDevice, st));
         d_dopp = w + o_dopp;
     }
-    cledb_dbgrid g = *grid;
-    float* tab = reinterpret_cast<float*>(w + o_tab);
-    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab, grid->sin_bphi, (size_t)g.nbphi * 4, cudaMemcpyHostToDevice, st));
-    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab + g.nbphi, grid->cos_bphi, (size_t)g.nbphi * 4, cudaMemcpyHostToDevice, st));
-    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab + 2 * g.nbphi, grid->sin_btheta, (size_t)g.nbtheta * 4, cudaMemcpyHostToDevice, st));
-    CLEDB_CUDA(ctx, cudaMemcpyAsync(tab + 2 * g.nbphi + g.nbtheta, grid->cos_btheta, (size_t)g.nbtheta * 4, cudaMemcpyHostToDevice, st));
-    g.sin_bphi = tab;
-    g.cos_bphi = tab + g.nbphi;
-    g.sin_btheta = tab + 2 * g.nbphi;
-    g.cos_btheta = tab + 2 * g.nbphi + g.nbtheta;
+    cledb_dbgrid g;
+    if ((rc = grid_to_device(ctx, grid, &g, st))) return rc;
     // Big maps go through in chunks of 128 Ki pixels: the search of chunk c+1 runs while the finished maps of chunk c
     // travel to the host on a second stream (608 B per pixel at nsearch 8 is a quarter of the search time on PCIe 5).
     int64_t chunk = npix;

@@ -42,8 +42,13 @@ print('rank %d/%d: default transport %s' % (rank, world, default_transport), flu
 transports = ['peer', 'nccl'] if default_transport == 'peer' else ['nccl']
 if os.environ.get('CLEDB_B200_REQUIRE_PEER') == '1':
     ok = ok and default_transport == 'peer'
-for transport, iqud, bcalc in [(t, q, b) for t in transports for q, b in ((False, 0), (True, 3))]:
-    ctx.comm_transport(transport)
+# 'peer/3': the pipelined gather with the shard in three pieces (a map this small goes through in one piece by default)
+variants = (['peer', 'peer/3'] if default_transport == 'peer' else []) + ['nccl']
+for transport, iqud, bcalc in [(t, q, b) for t in variants for q, b in ((False, 0), (True, 3))]:
+    ctx.comm_transport(transport.split('/')[0])
+    os.environ.pop('CLEDB_B200_PIECES', None)
+    if '/' in transport:
+        os.environ['CLEDB_B200_PIECES'] = transport.split('/')[1]
     tail = (hdr, obs['keyvals'], 8, 1000, bcalc, iqud, 1, False, 0)
     iss = obs['issuemask'].copy()
     iss[::3, :, 1] = 1024                                    # a code that is already set
@@ -55,7 +60,7 @@ for transport, iqud, bcalc in [(t, q, b) for t in transports for q, b in ((False
     same = np.array_equal(inv, inv1, equal_nan=True) and np.array_equal(sf, sf1, equal_nan=True) and np.array_equal(iss, iss1)
     print('rank %d/%d iqud=%s transport=%s: gathered maps == single-GPU maps: %s (NCCL %s)' % (rank, world, iqud, transport, same, info), flush=True)
     ok = ok and same and info['nranks'] == world and (world == 1 or info['nccl'])
-    if rank == 0 and transport == transports[0]:
+    if rank == 0 and transport == variants[0]:
         dec = [codec.decoded_database(d, native.ENC_I16).reshape(-1, 8) for d in dbs]
         pick = np.random.default_rng(2).choice(nx * nx, 48, replace=False)
         pix = [(int(p // nx), int(p % nx)) for p in pick]
@@ -69,6 +74,7 @@ for transport, iqud, bcalc in [(t, q, b) for t in transports for q, b in ((False
                                                      iss.reshape(n, 2)[pick], iss2.reshape(n, 2)[pick])
         print('oracle subset: %d slots, %d near-tie substitutions' % (slots, subs), flush=True)
         ok = ok and subs <= 8
+os.environ.pop('CLEDB_B200_PIECES', None)
 # root-only gather: the other ranks get (None, None); with every transport the root's maps are the single-GPU maps
 tail = (hdr, obs['keyvals'], 8, 1000, 0, False, 1, False, 0)
 inv1, sf1 = procinv.cledb_invproc(*args, obs['issuemask'].copy(), *tail)

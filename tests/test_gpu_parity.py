@@ -955,16 +955,19 @@ def test_config5_shaped_map_against_the_oracle(ctx, mode):
         ctx.db_drop(i)
 
 
-@pytest.mark.parametrize('transport', ['peer', 'nccl'])
-def test_sharded_call_on_one_rank_equals_the_plain_call(transport):
+@pytest.mark.parametrize('transport', ['peer', 'peer/3', 'nccl'])
+def test_sharded_call_on_one_rank_equals_the_plain_call(transport, monkeypatch):
     """cledb_invert_sharded with a one-rank communicator (no NCCL needed): partition, packed send buffer, then either the
-    peer-memory transport (flags + k_push_records storing every record at its pixel in the window) or the collective one (a
-    device copy + the scatter kernel) - the full maps equal cledb_invert's bit for bit; a multi-database map, both modes.
+    peer-memory transport (flags + k_push_records storing every record at its pixel in the window; 'peer/3': the shard in three
+    pieces, each pushed on a second stream beside the search of the next) or the collective one (a device copy + the scatter kernel) - the full maps equal cledb_invert's bit for bit; a multi-database map, both modes.
     The N > 1 path runs in tests/test_multigpu.py on a box with two GPUs."""
     c = native.Context(0)
     c.comm_init(0, 1)
     assert c.comm_info() == dict(rank=0, nranks=1, nccl_version=c.comm_info()['nccl_version'], nccl=False)
     assert c.comm_transport() == 'peer'                        # the default where peer memory works; one rank: always
+    if '/' in transport:                                       # the pipelined gather: the shard in three pieces, pushes on a second stream
+        monkeypatch.setenv('CLEDB_B200_PIECES', transport.split('/')[1])
+        transport = 'peer'
     assert c.comm_transport(transport) == transport
     dbs = [synth.make_database(5 + 3 * i, 30 + 2 * i, ngx=5, nbphi=36, nbtheta=18) for i in range(3)]
     nx, ny = 40, 33

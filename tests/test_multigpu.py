@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('world', [2])
+@pytest.mark.parametrize('world', [2, 8])
 def test_sharded_inversion_over_nccl(world):
     import torch
     if torch.cuda.device_count() < world:
