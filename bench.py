@@ -58,6 +58,7 @@ def parse():
     ap.add_argument('--configs', default='', help='comma list of extra configs to run (default: 2b,3,4,5 at N=1; 2b,5 at N>1)')
     ap.add_argument('--transport', default='auto', choices=['auto', 'peer', 'nccl'],
                     help='multi-GPU gathers: peer = the library\'s own stores into the peers\' windows (default where CUDA IPC works), nccl = ncclAllGather')
+    ap.add_argument('--push-blocks', type=int, default=24, help='N > 1: blocks of the gather kernel when it runs beside the next search')
     ap.add_argument('--pieces', type=int, default=0, help='config 5: pieces of a shard in the pipelined gather (0 = library default)')
     ap.add_argument('--no-overlap', action='store_true', help='N > 1: time search + gather back to back on one stream (no pipelining of the gather)')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
@@ -425,7 +426,11 @@ def bench_search(B, mode_name, nx, ndb, encoding, steps, warmup, with_gather, wa
             B.barrier()
             launches0 = ctx.launch_count()
             cursor[0] = 0
+            if B.transport == 'peer':
+                ctx.comm_push_blocks(B.args.push_blocks)    # the gather runs beside a search: it leaves most SMs to the search
             step_ms, kern_ms = B.timed_pipelined(search, gather, nst, side)
+            if B.transport == 'peer':
+                ctx.comm_push_blocks(0)
         else:
             step_ms, kern_ms = B.timed(step, nst)
         cursor[0] = 0
@@ -854,7 +859,7 @@ def bench_config5(B, nx, ndb, steps):
     if unpiped is not None:
         rec['unpipelined'] = unpiped
         rec['pipeline'] = ('cledb_invert_gather_dev: the shard goes through in pieces (2 from four ranks on when a piece still holds 64 Ki pixels, else 1); the records '
-                           'of a piece cross NVLink on a second stream (k_push_records on 16 blocks) while the next piece is searched; '
+                           'of a piece cross NVLink on a second stream (k_push_records on 24 blocks of 1024 threads) while the next piece is searched; '
                            'step_breakdown_ms is the unpipelined step')
     # the same step with the brute-force search (k-d layout, seeded: every (pixel, entry) pair evaluated - the FP32-bound kernel)
     ctx.set_pruning(2)

@@ -260,6 +260,9 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  *                          aligned; re-allocated and re-mapped on every rank when it has to grow - earlier pointers and
  *                          contents are then gone).  One window per communicator; cledb_invert_sharded keeps its full maps at
  *                          the start of the same window.
+ *   cledb_comm_push_blocks peer transport: bound of the grid of the push kernels of the following cledb_allgather_dev /
+ *                          cledb_gather_maps_dev calls (0 = no bound, the default).  A gather enqueued on a second stream beside
+ *                          a search should leave the SMs to the search: 24 blocks (of 1024 threads) reach the NVLink rate.
  *   cledb_allgather_dev    every rank contributes `bytes` bytes at `send`; `recv` receives nranks*bytes in rank order
  *                          (device pointers, enqueued on the stream).  `recv` inside the window + peer transport (bytes and
  *                          pointers multiples of 16): every rank stores its block into every rank's window (k_push_block);
@@ -300,6 +303,7 @@ int cledb_comm_init(cledb_ctx* ctx, int rank, int nranks, const void* id128);
 int cledb_comm_destroy(cledb_ctx* ctx);
 int cledb_comm_info(cledb_ctx* ctx, int32_t info[4]);
 int cledb_comm_transport(cledb_ctx* ctx, int want, int32_t* active);
+int cledb_comm_push_blocks(cledb_ctx* ctx, int blocks);
 int cledb_comm_window(cledb_ctx* ctx, int64_t bytes, void** ptr_out);
 int cledb_allgather_dev(cledb_ctx* ctx, const void* send, void* recv, int64_t bytes, void* stream);
 int cledb_partition(int64_t npix, const int32_t* key, int nkeys, const double* weight_of_key, int nranks,

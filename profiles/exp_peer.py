@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Tuning experiment of the peer-memory push kernels (run under torchrun, one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 profiles/exp_peer.py
-Times cledb_gather_maps_dev (k_push_records: load/store unit or TMA bulk stores, blocks per SM) on a random 1024^2-pixel
+Times cledb_gather_maps_dev (k_push_records with a bounded number of blocks) on a random 1024^2-pixel
 partition and cledb_allgather_dev into the window (k_push_block) on large blocks, CUDA events, max over ranks."""
 import ctypes
 import os
@@ -62,28 +62,15 @@ def timed(fn, reps=6):
     return t.tolist()
 
 
-ref = None
-for how in ('lsu', 'tma'):
-    for grid in ((2, 8) if world > 2 else (2, 3, 4, 8, 16)):
-        for root in (-1, 0):
-            os.environ['CLEDB_B200_PUSH'] = how
-            os.environ['CLEDB_B200_PUSH_GRID'] = str(grid)
-            mean, best = timed(lambda: ctx.gather_maps_dev(npix, n, mine.data_ptr(), maxcount, k, send.data_ptr(), win, root, stream.cuda_stream))
-            out_mb = n * (k * 76 + 5) * ((world - 1) if root < 0 else (0 if rank == root else 1)) / 1e6
-            in_mb = (npix - n) * (k * 76 + 5) / 1e6 if (root < 0 or root == rank) else 0.0
-            if rank == 0:
-                print('push %s grid %2d root %2d: %.3f ms mean  %.3f ms min   %.0f MB into rank 0 -> %.0f GB/s' %
-                      (how, grid, root, mean, best, in_mb, in_mb / best if best else 0), flush=True)
-    ctx.gather_maps_dev(npix, n, mine.data_ptr(), maxcount, k, send.data_ptr(), win, -1, stream.cuda_stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    got = device_view(win, int(mlay[4]), dev).clone()
-    if ref is None:
-        ref = got
-    else:
-        print('rank %d: tma maps == lsu maps: %s' % (rank, bool(torch.equal(ref, got))), flush=True)
-os.environ.pop('CLEDB_B200_PUSH', None)
-os.environ.pop('CLEDB_B200_PUSH_GRID', None)
+for blocks in (4, 8, 16, 24, 32, 64, 148, 0):
+    for root in (-1, 0):
+        os.environ['CLEDB_B200_PUSH_BLOCKS'] = str(blocks)
+        mean, best = timed(lambda: ctx.gather_maps_dev(npix, n, mine.data_ptr(), maxcount, k, send.data_ptr(), win, root, stream.cuda_stream))
+        in_mb = (npix - n) * (k * 76 + 5) / 1e6 if (root < 0 or root == rank) else 0.0
+        if rank == 0:
+            print('push with %3d blocks (0 = 8 per SM) root %2d: %.3f ms mean  %.3f ms min   %.0f MB into rank 0 -> %.0f GB/s' %
+                  (blocks, root, mean, best, in_mb, in_mb / best if best else 0), flush=True)
+os.environ.pop('CLEDB_B200_PUSH_BLOCKS', None)
 # contiguous blocks
 for mb in (4, 32, 160):
     nb = mb << 20

@@ -67,6 +67,7 @@ SIGNATURES = {
     'cledb_comm_destroy': (_c.c_int, [_P]),
     'cledb_comm_info': (_c.c_int, [_P, _P]),
     'cledb_comm_transport': (_c.c_int, [_P, _c.c_int, _P]),
+    'cledb_comm_push_blocks': (_c.c_int, [_P, _c.c_int]),
     'cledb_comm_window': (_c.c_int, [_P, _c.c_int64, _c.POINTER(_P)]),
     'cledb_allgather_dev': (_c.c_int, [_P, _P, _P, _c.c_int64, _P]),
     'cledb_map_layout': (_c.c_int, [_c.c_int64, _c.c_int, _P]),
@@ -553,6 +554,11 @@ class Context:
         act = ctypes.c_int32(-1)
         self._check(self.lib.cledb_comm_transport(self.h, code, ctypes.byref(act)))
         return 'peer' if act.value == 1 else 'nccl'
+
+    def comm_push_blocks(self, blocks):
+        """Bound of the grid of the peer transport's push kernels (0 = none): a gather that runs on a second stream beside a
+        search should leave the SMs to the search."""
+        self._check(self.lib.cledb_comm_push_blocks(self.h, int(blocks)))
 
     def comm_window(self, nbytes):
         """Collective: device address of this rank's receive window of at least ``nbytes`` bytes (valid until a later call

@@ -113,6 +113,7 @@ struct cledb_comm {
     void* win = nullptr;                        // local window (plain allocation when peer_ok is false)
     std::vector<size_t> win_bytes;              // size of every rank's window, tracked identically on all ranks
     unsigned epoch = 0;
+    int push_blocks = 0;                        // > 0: bound of the grid of the push kernels (cledb_comm_push_blocks)
 };
 
 namespace {
@@ -171,8 +172,9 @@ __device__ __forceinline__ void block_done(const Peers& P, unsigned epoch, int32
 
 
 // all-gather of contiguous blocks: the 16-byte vectors of this rank's block go to the same place of every rank's window
-__global__ void __launch_bounds__(512) k_push_block(Peers P, const uint4* __restrict__ send, size_t nvec, size_t dst_off, unsigned epoch,
-                                                    int32_t* err_mapped) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_push_block(Peers P, const uint4* __restrict__ send, size_t nvec, size_t dst_off, unsigned epoch,
+                                                        int32_t* err_mapped) {
     block_open(P, epoch, err_mapped);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -475,6 +477,14 @@ static int ensure_window(cledb_ctx* ctx, const size_t* need) {
     return CLEDB_OK;
 }
 
+extern "C" int cledb_comm_push_blocks(cledb_ctx* ctx, int blocks) {
+    if (!ctx) return CLEDB_ERR_ARG;
+    if (!ctx->comm) { ctx->err = "cledb_comm_push_blocks: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
+    if (blocks < 0) { ctx->err = "cledb_comm_push_blocks: blocks must be >= 0"; return CLEDB_ERR_ARG; }
+    ctx->comm->push_blocks = blocks;
+    return CLEDB_OK;
+}
+
 extern "C" int cledb_comm_window(cledb_ctx* ctx, int64_t bytes, void** ptr_out) {
     if (!ctx) return CLEDB_ERR_ARG;
     if (!ctx->comm) { ctx->err = "cledb_comm_window: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
@@ -513,8 +523,13 @@ extern "C" int cledb_allgather_dev(cledb_ctx* ctx, const void* send, void* recv,
         const unsigned e = ++c->epoch;
         const size_t nvec = (size_t)bytes / 16;
         const size_t off = (size_t)(reinterpret_cast<unsigned char*>(recv) - reinterpret_cast<unsigned char*>(c->win)) + (size_t)c->rank * (size_t)bytes;
-        const unsigned grid = (unsigned)std::min<size_t>((nvec + 511) / 512, (size_t)ctx->prop.multiProcessorCount * 2);
-        k_push_block<<<grid, 512, 0, st>>>(c->peers, reinterpret_cast<const uint4*>(send), nvec, off, e, comm_err_word(ctx));
+        if (c->push_blocks > 0) {              // a gather that runs beside a search: few SMs, each filled with one 1024-thread block
+            const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((nvec + 1023) / 1024, (size_t)c->push_blocks));
+            k_push_block<1024><<<grid, 1024, 0, st>>>(c->peers, reinterpret_cast<const uint4*>(send), nvec, off, e, comm_err_word(ctx));
+        } else {
+            const unsigned grid = (unsigned)std::min<size_t>((nvec + 511) / 512, (size_t)ctx->prop.multiProcessorCount * 2);
+            k_push_block<512><<<grid, 512, 0, st>>>(c->peers, reinterpret_cast<const uint4*>(send), nvec, off, e, comm_err_word(ctx));
+        }
         return after_launch(ctx);
     }
     if (c->nranks == 1) {
@@ -618,8 +633,8 @@ __global__ void __launch_bounds__(256) k_unshard(int nranks, const int64_t* __re
 // and stores it at the pixel's place in the maps of every destination rank (the local one included) - whole rows as 16-byte
 // vectors, so every store instruction is one contiguous 352 / 256-byte piece for NVLink.  Warps start at different
 // destinations.  The kernel opens with the wait for the destinations' free flags and closes with this rank's done flag.
-template <bool VEC>
-__global__ void __launch_bounds__(256) k_push_records(Peers P, unsigned dst_mask, const int32_t* __restrict__ my_order, int64_t nlocal, int k,
+template <bool VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_push_records(Peers P, unsigned dst_mask, const int32_t* __restrict__ my_order, int64_t nlocal, int k,
                                                       const unsigned char* __restrict__ send, size_t o_inv, size_t o_sf, size_t o_st, size_t o_iss,
                                                       size_t m_inv, size_t m_sf, size_t m_st, size_t m_iss, unsigned epoch,
                                                       int32_t* err_mapped) {
@@ -787,16 +802,21 @@ static int push_records(cledb_ctx* ctx, int64_t npix, int64_t nlocal, const int3
     const unsigned e = ++c->epoch;
     const char* pg = std::getenv("CLEDB_B200_PUSH_GRID");                 // tuning: blocks per SM of the push kernel
     const int per_sm = pg && std::atoi(pg) > 0 ? std::atoi(pg) : 8;
-    int64_t grid = std::min<int64_t>((nlocal * 32 + 255) / 256, (int64_t)ctx->prop.multiProcessorCount * per_sm);
+    int64_t grid = std::min<int64_t>((nlocal * 32 + 255) / 256, (int64_t)ctx->prop.multiProcessorCount * per_sm);          // 256-thread blocks
+    if (const char* pb = std::getenv("CLEDB_B200_PUSH_BLOCKS"))           // tuning: absolute bound of the grid
+        if (blocks == 0 && std::atoi(pb) > 0) blocks = std::atoi(pb);
     if (blocks > 0) grid = std::min<int64_t>(grid, blocks);
     grid = std::max<int64_t>(grid, 1);
     const unsigned char* s8 = reinterpret_cast<const unsigned char*>(send);
-    if (nsearch % 4 == 0)
-        k_push_records<true><<<(unsigned)grid, 256, 0, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss,
-                                                             woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx));
-    else
-        k_push_records<false><<<(unsigned)grid, 256, 0, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss,
-                                                              woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx));
+    // a narrow push (one that runs beside a search) takes the whole SM it sits on - the search kernel cannot share an SM anyway:
+    // 1024 threads per block; the wide one keeps 256-thread blocks at 72 registers
+#define CLEDB_PUSH(VEC, T)                                                                                                              \
+    k_push_records<VEC, T><<<(unsigned)grid, T, 0, st>>>(c->peers, mask, my_order_dev, nlocal, nsearch, s8, L.o_inv, L.o_sf, L.o_st, L.o_iss, \
+                                                         woff + M.o_inv, woff + M.o_sf, woff + M.o_st, woff + M.o_iss, e, comm_err_word(ctx))
+    const bool narrow = blocks > 0 && blocks <= 2 * ctx->prop.multiProcessorCount / 3;
+    if (nsearch % 4 == 0) { if (narrow) CLEDB_PUSH(true, 1024); else CLEDB_PUSH(true, 256); }
+    else                  { if (narrow) CLEDB_PUSH(false, 1024); else CLEDB_PUSH(false, 256); }
+#undef CLEDB_PUSH
     return after_launch(ctx);
 }
 
@@ -805,8 +825,8 @@ extern "C" int cledb_gather_maps_dev(cledb_ctx* ctx, int64_t npix, int64_t nloca
     if (!ctx) return CLEDB_ERR_ARG;
     if (!ctx->comm) { ctx->err = "cledb_gather_maps: no communicator (cledb_comm_init)"; return CLEDB_ERR_COMM; }
     CLEDB_CUDA(ctx, cudaSetDevice(ctx->device));
-    return push_records(ctx, npix, nlocal, my_order_dev, maxcount, nsearch, send, maps, root, 0, stream ? (cudaStream_t)stream : ctx->stream,
-                        "cledb_gather_maps");
+    return push_records(ctx, npix, nlocal, my_order_dev, maxcount, nsearch, send, maps, root, ctx->comm->push_blocks,
+                        stream ? (cudaStream_t)stream : ctx->stream, "cledb_gather_maps");
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -829,9 +849,9 @@ extern "C" int cledb_invert_gather_dev(cledb_ctx* ctx, int mode, int precision, 
         // every rank must run the same number of pushes, so the choice depends on the map and the rank count only.  A search call
         // has a fixed cost of about 0.3 ms (its launches and the tail of its longest work item), a second piece hides half of the
         // NVLink time of the shard: that pays from four ranks on (each rank then receives >= 3/4 of the map), with pieces that
-        // still fill the GPU (64 Ki pixels)
+        // still fill the GPU (64 Ki pixels).  The brute-force searches are two orders of magnitude longer than the push: one piece
         const char* e = std::getenv("CLEDB_B200_PIECES");
-        pieces = e && std::atoi(e) > 0 ? std::min(std::atoi(e), kMaxPieces) : (c->nranks >= 4 && npix / c->nranks >= 2 * 65536 - 8 ? 2 : 1);
+        pieces = e && std::atoi(e) > 0 ? std::min(std::atoi(e), kMaxPieces) : (c->nranks >= 4 && npix / c->nranks >= 2 * 65536 - 8 && ctx->prune == 1 ? 2 : 1);
     }
     if (pieces > 1 && !c->side) {
         CLEDB_CUDA(ctx, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
@@ -843,7 +863,7 @@ extern "C" int cledb_invert_gather_dev(cledb_ctx* ctx, int mode, int precision, 
     int rc;
     if ((rc = ensure_workspace(ctx, c->send, L.bytes * (size_t)pieces))) return rc;
     const char* sb = std::getenv("CLEDB_B200_PUSH_SIDE");                // tuning: blocks of a push that runs beside a search
-    const int side_blocks = sb && std::atoi(sb) > 0 ? std::atoi(sb) : 16;
+    const int side_blocks = sb && std::atoi(sb) > 0 ? std::atoi(sb) : 24;       // 24 SMs at 1024 threads reach the NVLink rate (profiles/r02_tuning.txt)
     const size_t dsz = dopp ? (dopp_is_f64 ? 8 : 4) : 0;
     for (int i = 0; i < pieces; ++i) {                   // a rank with nothing (left) still pushes: the others wait for its flags
         const int64_t j0 = std::min(per * i, nlocal), n = std::min(per, nlocal - j0);

@@ -1038,12 +1038,22 @@ def test_window_allgather_and_gather_maps_on_one_rank():
     ref = [torch.zeros((npix, k, 11), dtype=torch.float32, device=dev), torch.zeros((npix, k, 8), dtype=torch.float32, device=dev),
            torch.zeros(npix, dtype=torch.uint8, device=dev), torch.zeros(npix, dtype=torch.int32, device=dev)]
     c.unshard_dev(1, d_bounds.data_ptr(), d_order.data_ptr(), npix, npix, k, send.data_ptr(), *(t.data_ptr() for t in ref), stream.cuda_stream)
-    c.gather_maps_dev(npix, npix, d_order.data_ptr(), npix, k, send.data_ptr(), win, -1, stream.cuda_stream)
-    stream.synchronize()
-    got = device_view(win, int(mlay[4]), dev).cpu().numpy()
-    for t, o in zip(ref, mlay[:4]):
-        want = t.cpu().numpy().view(np.uint8).reshape(-1)
-        assert np.array_equal(got[int(o):int(o) + want.size], want)
+    for blocks in (0, 3):                                      # 3: the bounded grid of a gather that runs beside a search (1024-thread blocks)
+        c.comm_push_blocks(blocks)
+        device_view(win, int(mlay[4]), dev).zero_()
+        torch.cuda.synchronize()
+        c.gather_maps_dev(npix, npix, d_order.data_ptr(), npix, k, send.data_ptr(), win, -1, stream.cuda_stream)
+        stream.synchronize()
+        got = device_view(win, int(mlay[4]), dev).cpu().numpy()
+        for t, o in zip(ref, mlay[:4]):
+            want = t.cpu().numpy().view(np.uint8).reshape(-1)
+            assert np.array_equal(got[int(o):int(o) + want.size], want)
+        src = torch.from_numpy(rng.integers(0, 256, nbytes, dtype=np.uint8)).to(dev)
+        torch.cuda.synchronize()
+        c.allgather_dev(src.data_ptr(), win, nbytes, stream.cuda_stream)
+        stream.synchronize()
+        assert torch.equal(device_view(win, nbytes, dev), src)
+    c.comm_push_blocks(0)
     c.comm_transport('nccl')
     with pytest.raises(native.CledbError, match='peer-memory transport'):
         c.gather_maps_dev(npix, npix, d_order.data_ptr(), npix, k, send.data_ptr(), win, -1, stream.cuda_stream)
