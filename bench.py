@@ -58,7 +58,7 @@ def parse():
     ap.add_argument('--configs', default='', help='comma list of extra configs to run (default: 2b,3,4,5 at N=1; 2b,5 at N>1)')
     ap.add_argument('--transport', default='auto', choices=['auto', 'peer', 'nccl'],
                     help='multi-GPU gathers: peer = the library\'s own stores into the peers\' windows (default where CUDA IPC works), nccl = ncclAllGather')
-    ap.add_argument('--push-blocks', type=int, default=24, help='N > 1: blocks of the gather kernel when it runs beside the next search')
+    ap.add_argument('--push-blocks', type=int, default=12, help='N > 1: blocks of the gather kernel when it runs beside the next search')
     ap.add_argument('--pieces', type=int, default=0, help='config 5: pieces of a shard in the pipelined gather (0 = library default)')
     ap.add_argument('--no-overlap', action='store_true', help='N > 1: time search + gather back to back on one stream (no pipelining of the gather)')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
