@@ -858,7 +858,7 @@ def bench_config5(B, nx, ndb, steps):
         rec['nccl_transport'] = nccl_rec
     if unpiped is not None:
         rec['unpipelined'] = unpiped
-        rec['pipeline'] = ('cledb_invert_gather_dev: the shard goes through in pieces (2 from four ranks on when a piece still holds 64 Ki pixels, else 1); the records '
+        rec['pipeline'] = ('cledb_invert_gather_dev: the shard goes through in pieces (2 from six ranks on when a piece still holds 64 Ki pixels, else 1); the records '
                            'of a piece cross NVLink on a second stream (k_push_records on 24 blocks of 1024 threads) while the next piece is searched; '
                            'step_breakdown_ms is the unpipelined step')
     # the same step with the brute-force search (k-d layout, seeded: every (pixel, entry) pair evaluated - the FP32-bound kernel)

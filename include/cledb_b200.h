@@ -246,7 +246,8 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  * loaded into the process, else the system's; CLEDB_B200_NCCL overrides), single-GPU use needs none.
  *   cledb_comm_unique_id   rank 0 creates the 128-byte id; the launcher ships it to the other ranks (torch.distributed
  *                          broadcast, MPI, a file ...)
- *   cledb_comm_init        collective over all ranks; nranks == 1 needs no id and no NCCL
+ *   cledb_comm_init        collective over all ranks; nranks == 1 needs no id and no NCCL.  cledb_comm_destroy is collective too
+ *                          (the ranks unmap each other's memory before anyone frees it)
  *   cledb_comm_info        info[0]=rank, [1]=nranks, [2]=NCCL version code, [3]=1 if an NCCL communicator is live
  *   cledb_comm_transport   how the gathers move data.  1 = PEER MEMORY (default where it works): cledb_comm_init maps a small flag
  *                          array of every rank into every process with CUDA IPC, cledb_comm_window does the same for the
@@ -256,6 +257,9 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  *                          0 = ncclAllGather into a receive buffer + k_unshard.  want = -1 queries; *active receives the
  *                          transport in effect.  Asking for 1 where IPC is unavailable returns CLEDB_ERR_COMM and the reason.
  *                          Every rank must use the same transport (CLEDB_B200_PEER=0 in the environment starts with NCCL).
+ *                          One gather in flight per communicator: the flag epochs count the operations in the order they are
+ *                          enqueued, which must be the order they run in - enqueue gathers on one stream, or order the streams
+ *                          with events (cledb_invert_gather_dev does that for its second stream).
  *   cledb_comm_window      collective: the receive window of this rank holds at least `bytes` bytes (device memory, 256-byte
  *                          aligned; re-allocated and re-mapped on every rank when it has to grow - earlier pointers and
  *                          contents are then gone).  One window per communicator; cledb_invert_sharded keeps its full maps at
@@ -287,7 +291,7 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  *                          only.  When the call's work has run on the stream, every record of every rank is in place.
  *   cledb_invert_gather_dev  peer transport: search + solutions + gather of this rank's shard as a PIPELINE (device pointers as in
  *                          cledb_invert_dev, grid tables on the device).  The shard goes through in `pieces` contiguous pieces
- *                          (0 = chosen from npix and the rank count: 2 from four ranks on when a piece still holds 64 Ki pixels, else 1; the same
+ *                          (0 = chosen from npix and the rank count: 2 from six ranks on when a piece still holds 64 Ki pixels, else 1; the same
  *                          on every rank - every rank runs `pieces` pushes, also one with no pixels); the records of piece i
  *                          cross NVLink - a k_push_records of a few blocks on the communicator's second stream - while piece
  *                          i+1 is searched on the caller's stream; the caller's stream then waits for the last push.

@@ -848,10 +848,11 @@ extern "C" int cledb_invert_gather_dev(cledb_ctx* ctx, int mode, int precision, 
     if (pieces == 0) {
         // every rank must run the same number of pushes, so the choice depends on the map and the rank count only.  A search call
         // has a fixed cost of about 0.3 ms (its launches and the tail of its longest work item), a second piece hides half of the
-        // NVLink time of the shard: that pays from four ranks on (each rank then receives >= 3/4 of the map), with pieces that
-        // still fill the GPU (64 Ki pixels).  The brute-force searches are two orders of magnitude longer than the push: one piece
+        // NVLink time of the shard: measured on the 1024^2 map that is nothing at 2 and 4 ranks and 9 % at 8 (each rank then
+        // receives 7/8 of the map next to a search of 1/8 of it), so two pieces from six ranks on, with pieces that still fill
+        // the GPU (64 Ki pixels).  The brute-force searches are two orders of magnitude longer than the push: one piece
         const char* e = std::getenv("CLEDB_B200_PIECES");
-        pieces = e && std::atoi(e) > 0 ? std::min(std::atoi(e), kMaxPieces) : (c->nranks >= 4 && npix / c->nranks >= 2 * 65536 - 8 && ctx->prune == 1 ? 2 : 1);
+        pieces = e && std::atoi(e) > 0 ? std::min(std::atoi(e), kMaxPieces) : (c->nranks >= 6 && npix / c->nranks >= 2 * 65536 - 8 && ctx->prune == 1 ? 2 : 1);
     }
     if (pieces > 1 && !c->side) {
         CLEDB_CUDA(ctx, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
