@@ -243,7 +243,20 @@ def issue_codes(codes, invout=None):
     (see cledb_invert in the header).  Pixels whose Van-Vleck angle lies within 2e-3 deg of a limit (bit 0) are re-evaluated
     with NumPy from ``invout[npix,k,11]`` - the reference's own float32 chain decides those."""
     from . import solution
-    amb = np.flatnonzero(codes & 1)
+    # marked pixels are about 1 in 25 000: find the rows of a 2-D view that hold one first (an OR-reduction per row), then
+    # look inside those rows only - a fifth of the cost of a flat search on a 256 x 256 map
+    n = codes.size
+    w = 256 if n % 256 == 0 and n >= 4096 and codes.flags.c_contiguous else 0
+    if w:
+        c2 = codes.reshape(-1, w)
+        rows = np.flatnonzero(np.bitwise_or.reduce(c2, axis=1) & 1)
+        if rows.size:
+            r, c = np.nonzero(c2[rows] & 1)
+            amb = rows[r] * w + c
+        else:
+            amb = rows
+    else:
+        amb = np.flatnonzero(codes & 1)
     if amb.size:
         codes = codes & ~np.int32(1)
         if invout is not None:
@@ -495,8 +508,9 @@ class Context:
         dobs = _as(np.asarray(dobs).reshape(-1), np.float32)
         ang = _as(np.asarray(aobs).reshape(-1), np.float32)
         with np.errstate(all='ignore'):
-            rot_cos = np.cos(-2. * ang)           # cledb_quderotate, CLEDB_PROC.py:1584-1587, in the reference's float32
-            rot_sin = np.sin(-2. * ang)
+            twice = -2. * ang                     # cledb_quderotate, CLEDB_PROC.py:1584-1587, in the reference's float32
+            rot_cos = np.cos(twice)
+            rot_sin = np.sin(twice)
         is64 = 0
         if dopp is not None:
             dopp = np.asarray(dopp).reshape(-1)

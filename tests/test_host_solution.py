@@ -118,3 +118,42 @@ def test_issue_codes_from_device_flags():
     solution.update_issuemask(b, inv.reshape(npix, 1, k, 11), snr, npix, 1)
     assert np.array_equal(a, b)
     assert (codes & 512).any() and (codes & 1024).any() and (codes & 2048).any()
+
+
+def test_apply_issue_codes_on_every_mask_type():
+    """The vectorised paths of apply_issue_codes (integer masks: one OR per line; float masks - the reference's own issuemask is
+    float64, CLEDB_PREPINV.py:159 - one integer view and one addition per line) equal the reference's arithmetic (add a code
+    only where its bit is not set, CLEDB_PROC.py:347-355) on masks that already hold arbitrary codes; a third line is untouched."""
+    rng = np.random.default_rng(0)
+    for dt in (np.float64, np.float32, np.int32, np.int64, np.int16):
+        nx, ny = 37, 256
+        codes = rng.choice([0, 512, 1024, 1536, 2048, 2560, 3072, 3584], (nx, ny)).astype(np.int32)
+        a = rng.choice([0, 1, 32, 64, 512, 1024 + 4, 2048 + 512, 3584, 4096 + 1024], (nx, ny, 3)).astype(dt)
+        b = a.copy()
+        solution.apply_issue_codes(a, codes)
+        for line in range(2):
+            mm = b[:, :, line]
+            for code in (512, 1024, 2048):
+                add = ((codes & code) != 0) & ((mm.astype(np.int64) & code) == 0)
+                mm[add] += code
+        assert np.array_equal(a, b), dt
+
+
+def test_issue_codes_finds_every_marked_pixel():
+    """native.issue_codes looks for the marked pixels (bit 0) row by row of a 2-D view when the map allows it: the same pixels
+    as a flat search, whatever the map size."""
+    rng = np.random.default_rng(1)
+    for n in (65536, 4096, 5000, 256 * 300, 7):
+        codes = rng.choice([0, 512, 1024, 2048], n).astype(np.int32)
+        idx = rng.choice(n, min(5, n), replace=False)
+        codes[idx] |= 1
+        inv = np.zeros((n, 2, 11), np.float32)
+        inv[:, :, 3] = 1
+        inv[:, :, 7] = rng.uniform(0, 3.1, (n, 1))
+        inv[:, :, 6] = rng.uniform(0, 6, (n, 1))
+        want = codes.copy()
+        amb = np.flatnonzero(want & 1)
+        want &= ~np.int32(1)
+        vv = solution.van_vleck_last(inv[amb])
+        want[amb] = (want[amb] & ~np.int32(512)) | (vv.astype(np.int32) << 9)
+        assert np.array_equal(native.issue_codes(codes.copy(), inv), want), n
