@@ -26,7 +26,7 @@ Module-level options (not part of the reference surface; the defaults reproduce 
                            2 = brute force on the k-d layout with every pixel started from its seed tile
     OPTIONS['device']      CUDA ordinal (default: $CLEDB_B200_DEVICE, else $LOCAL_RANK, else 0)
     OPTIONS['sharded']     True = cledb_invproc is a collective over the ranks of cledb_b200.dist.init_comm(): pixels sharded,
-                           one all-gather of the finished maps over NVLink; OPTIONS['shard_root'] = rank that receives the maps
+                           the finished maps gathered over NVLink inside the library; OPTIONS['shard_root'] = rank that receives the maps
                            (-1, default: every rank)
 """
 import os
@@ -141,8 +141,8 @@ def _search_and_build_sharded(ctx, mode, sobs, sobs_dopp, database, enc, yobs, a
                               reduced):
     """The same over every rank of the context's communicator (cledb_b200.dist.init_comm; OPTIONS['sharded']): every rank is
     called with the full map, takes its share of the pixel partition - contiguous ranges of the database-sorted pixel list,
-    balanced by database rows, so it uploads only the databases of its range -, and one all-gather of the packed records
-    over NVLink returns the finished maps (cledb_invert_sharded).  Collective."""
+    balanced by database rows, so it uploads only the databases of its range -, and the library's gather over NVLink (its
+    peer-memory push kernel, or ncclAllGather + scatter) returns the finished maps (cledb_invert_sharded).  Collective."""
     if reduced or OPTIONS['solution'] != 'device' or int(dbhdr[14]) != 1:
         raise native.CledbError('sharded inversion covers the full search with device-side solutions of PyCELP-type databases')
     npix = sobs.shape[0]

@@ -3,14 +3,16 @@
 The search has no exchange step - every pixel is independent (the reference dispatches one pool task per pixel,
 CLEDB_PROC.py:304-313) - so the only collective is the gather of the finished result maps at the end.
 
-On GPUs (``device='cuda'``) that gather happens inside the library: ``init_comm()`` creates an NCCL communicator on the
-process's context (``cledb_comm_init``; the 128-byte id travels through ``torch.distributed``), and ``cledb_invproc`` with
-``OPTIONS['sharded']`` becomes a collective:
+On GPUs (``device='cuda'``) that gather happens inside the library: ``init_comm()`` creates the communicator on the
+process's context (``cledb_comm_init``; the 128-byte NCCL id travels through ``torch.distributed``; the ranks map each other's
+receive windows with CUDA IPC), and ``cledb_invproc`` with ``OPTIONS['sharded']`` becomes a collective:
 
     rank r:  order, bounds = cledb_partition(db_enc, rows per database)   the same on every rank
              pixels r      = order[bounds[r] : bounds[r+1]]               contiguous in database order: few databases per rank
-             cledb_invert_sharded: search + solutions of the shard on the device, written straight into the packed send
-             buffer -> ONE ncclAllGather (NVLink / NVSwitch) -> k_unshard scatters the records to their pixels -> full maps
+             cledb_invert_sharded: search + solutions of the shard on the device, packed records in the send buffer
+               peer-memory transport (default): k_push_records stores every record at its pixel in the maps of every
+                 rank over NVLink / NVSwitch (from six ranks on in two pieces, the first crossing NVLink while the second is searched)
+               NCCL transport (``ctx.comm_transport('nccl')``): ONE ncclAllGather -> k_unshard scatters the records -> full maps
 
 Nothing goes through NumPy or host memory between the search and the gathered maps.  The CPU path below (``device='cpu'``,
 gloo) runs the same partition around an injected single-device function and gathers one packed buffer per rank; the CPU

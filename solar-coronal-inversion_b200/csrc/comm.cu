@@ -3,12 +3,15 @@
 // The search has no exchange step - every pixel is independent (the reference dispatches one pool task per pixel,
 // CLEDB_PROC.py:304-313) - so the only collective of the path is the gather of the finished result maps.  Each rank
 // builds the packed records of its shard on the device (cledb_invert_dev writes invout | sfound | status | issue codes
-// straight into the send buffer), ONE ncclAllGather moves them between the GPUs over NVLink / NVSwitch, and k_unshard
-// puts every record at its pixel's place in the full maps.  Nothing travels through host memory in between.
+// straight into the send buffer); then, by transport:
+//   peer memory (default)  the receive windows of all ranks are mapped into every process (CUDA IPC) and k_push_records
+//                          stores every record once, at its pixel's place, in the maps of every rank over NVLink / NVSwitch
+//   NCCL                   ONE ncclAllGather moves the packed records, k_unshard puts every record at its pixel's place
+// Nothing travels through host memory in between.
 //
 // NCCL is bound at run time (dlopen of the libnccl.so.2 that is already loaded into the process - the one torch brought
 // along - else the system's), so single-GPU users need no NCCL at all and the library never carries a second copy of it
-// into a process that already has one.
+// into a process that already has one.  With the peer transport it only bootstraps (the exchange of the IPC handles).
 #include <dlfcn.h>
 
 #include <algorithm>
