@@ -90,7 +90,7 @@ std::string nccl_text(int rc) { return g_nccl.error_string ? g_nccl.error_string
 constexpr int kMaxRanks = 16;
 constexpr int kMaxPieces = 8;         // pieces of a shard in the pipelined gather
 constexpr int kFlagFree = 0, kFlagDone = 32, kFlagCount = 64, kFlagWords = 128;      // word offsets inside the flag array
-constexpr long long kSpinLimitNs = 20LL * 1000 * 1000 * 1000;                         // a peer that never arrives: give up, report
+constexpr long long kSpinLimitNs = 60LL * 1000 * 1000 * 1000;                         // a peer that never arrives: give up, report
 
 struct Peers {
     unsigned char* base[kMaxRanks];     // window of rank r as seen from this process (base[me] = the local allocation)

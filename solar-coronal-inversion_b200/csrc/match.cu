@@ -1887,7 +1887,7 @@ int check_async_error(cledb_ctx* ctx) {
     }
     if (ctx->h_err && reinterpret_cast<volatile int32_t*>(ctx->h_err)[1] != 0) {      // comm.cu: a flag wait gave up
         reinterpret_cast<volatile int32_t*>(ctx->h_err)[1] = 0;
-        ctx->err = "multi-GPU: a peer rank did not arrive at a collective within 20 s (peer-memory transport); the gathered maps are incomplete";
+        ctx->err = "multi-GPU: a peer rank did not arrive at a collective within 60 s (peer-memory transport); the gathered maps are incomplete";
         return CLEDB_ERR_COMM;
     }
     return CLEDB_OK;
