@@ -256,7 +256,8 @@ int cledb_invert_reduced(cledb_ctx* ctx, int mode, int precision, int64_t npix,
  *                          (free / done epochs, st.release.sys / ld.acquire.sys) - no staging copy, no scatter pass.
  *                          0 = ncclAllGather into a receive buffer + k_unshard.  want = -1 queries; *active receives the
  *                          transport in effect.  Asking for 1 where IPC is unavailable returns CLEDB_ERR_COMM and the reason.
- *                          Every rank must use the same transport (CLEDB_B200_PEER=0 in the environment starts with NCCL).
+ *                          Every rank must use the same transport (CLEDB_B200_PEER=0 in the environment starts with NCCL;
+ *                          CLEDB_B200_NO_IPC=1 makes the IPC export fail, which exercises the fall-back of all ranks to NCCL).
  *                          One gather in flight per communicator: the flag epochs count the operations in the order they are
  *                          enqueued, which must be the order they run in - enqueue gathers on one stream, or order the streams
  *                          with events (cledb_invert_gather_dev does that for its second stream).

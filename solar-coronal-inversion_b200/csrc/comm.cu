@@ -265,6 +265,7 @@ static int map_peers(cledb_ctx* ctx, void* mine, size_t stamp_off, void** out, v
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&m.h, base);
     m.good = e == cudaSuccess;
     if (!m.good) { *why = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); }
+    if (std::getenv("CLEDB_B200_NO_IPC")) { m.good = 0; *why = "CUDA IPC switched off by CLEDB_B200_NO_IPC"; }     // exercises the fallback
     std::vector<Msg> all((size_t)R);
     int rc;
     if ((rc = exchange_host(ctx, &m, all.data(), sizeof(Msg)))) return rc;

@@ -21,3 +21,18 @@ def test_sharded_inversion_over_nccl(world):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-4000:]
     assert 'gathered maps == single-GPU maps: True' in out.stdout
+
+
+def test_every_rank_falls_back_to_nccl_when_ipc_is_unavailable():
+    """CLEDB_B200_NO_IPC=1 makes the IPC export of the flag arrays fail on every rank: the ranks agree on the NCCL transport
+    (cledb_comm_transport reports it) and the same check passes through ncclAllGather + k_unshard alone."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    port = 29300 + os.getpid() % 300
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', str(port), os.path.join(REPO, 'tests', 'multigpu_check.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, CLEDB_B200_NO_IPC='1'))
+    assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-4000:]
+    assert 'default transport nccl' in out.stdout and 'transport=peer' not in out.stdout
+    assert 'gathered maps == single-GPU maps: True' in out.stdout
