@@ -19,7 +19,7 @@ stores where CUDA IPC works, else NCCL).
                candidate) pair evaluated), config3_iqud_256_*, config4_blos_2048 / config4_qurotate_2048* (HBM roofline),
                config5_iquv_1024_multidb (ONE 1024x1024 map over several hundred databases, pixel-sharded over the N ranks
                through cledb_invert_dev + one all-gather: strong scaling; at N = 1 the whole map on one GPU)
-  cpu_baseline  the oracle port (NumPy restatement of the reference, fork pool) on a bounded pixel sample, this box's cores
+  cpu_baseline  the oracle port (NumPy restatement of the reference, fork pool) on a bounded pixel sample, this box's cores (N = 1 only)
 """
 import argparse
 import ctypes
@@ -925,6 +925,9 @@ def main():
         by[tag + '_bruteforce'] = top['bruteforce']
         by[tag + '_bruteforce_plain'] = top['bruteforce_plain']
     cpu_main = None
+    # the CPU baseline is timed at N = 1 only (rank 0 of a larger job would keep the other ranks waiting in the next collective)
+    if world > 1:
+        args.no_cpu_baseline = True
     if B.rank == 0 and not args.no_cpu_baseline:
         cpu_main = cpu_baseline(args.mode, args.encoding, db, obs, args.cpu_seconds)
         for r in (top['pruned'], top['bruteforce'], top['bruteforce_plain']):

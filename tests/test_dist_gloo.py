@@ -69,3 +69,35 @@ def test_sharded_inversion_world2(tmp_path):
         assert np.array_equal(g['inv'], ref_inv, equal_nan=True)
         assert np.array_equal(g['sf'], ref_sf, equal_nan=True)
         assert np.array_equal(g['iss'], iss)
+
+
+def test_c_abi_partition_equals_the_numpy_statement():
+    """cledb_partition (pure host code of the library, no GPU) cuts the pixels exactly as cledb_b200.dist.partition does."""
+    from cledb_b200 import native
+    rng = np.random.default_rng(1)
+    for ndb, shape in ((5, (40, 30)), (247, (64, 64)), (1, (9, 7))):
+        enc = rng.integers(0, ndb, shape).astype(np.int32)
+        w = rng.integers(1, 3000, ndb).astype(np.float64)
+        for world in (1, 2, 3, 8):
+            order, bounds = native.partition(enc.reshape(-1), w, world)
+            parts = cdist.partition(enc, w, world)
+            assert bounds[0] == 0 and bounds[-1] == enc.size and len(bounds) == world + 1
+            for r in range(world):
+                assert np.array_equal(order[bounds[r]:bounds[r + 1]], parts[r])
+
+
+def test_shard_and_map_layouts():
+    """cledb_shard_layout / cledb_map_layout (pure host code): the four blocks of the packed records and of the full maps follow
+    one another, 256-byte aligned, each large enough for its rows - what cledb_gather_maps_dev and the bench rely on."""
+    import ctypes
+    from cledb_b200 import native
+    lib = native.load_library()
+    for fn in (lib.cledb_shard_layout, lib.cledb_map_layout):
+        for n, k in ((0, 8), (1, 1), (3000, 3), (131071, 8), (1 << 20, 32)):
+            lay = np.zeros(5, np.int64)
+            assert fn(n, k, lay.ctypes.data_as(ctypes.c_void_p)) == 0
+            o_inv, o_sf, o_st, o_iss, total = (int(v) for v in lay)
+            assert o_inv == 0 and all(v % 256 == 0 for v in lay)
+            assert o_sf - o_inv >= n * k * 44 and o_st - o_sf >= n * k * 32 and o_iss - o_st >= n and total - o_iss >= n * 4
+            assert total < n * (k * 76 + 5) + 4 * 256 + 1
+        assert fn(-1, 8, lay.ctypes.data_as(ctypes.c_void_p)) < 0 and fn(10, 0, lay.ctypes.data_as(ctypes.c_void_p)) < 0
